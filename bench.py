@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- keypoint-pairs/s of the MDGAT forward hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference ...                      (CPU arm: the oracle port on host cores)
+
+One "step" = one forward of MDGAT over one batch of synthetic pairs: encoder -> 18 GNN layers
+(full / top-k attention) -> score matrix -> 100 log-Sinkhorn iterations -> match extraction +
+triplet loss. Workload at every N: BASELINE.json configs[1] per GPU (batch 32, 2x512 keypoints,
+33-dim descriptors, L=9, T=100); ranks process independent batches (weak scaling, no data-path
+collective); the per-rank results are all-gathered once after the timed region.
+
+Prints ONE JSON line (rank 0). `value` = pairs/s with inputs resident in HBM; `e2e` = the same
+through MDGAT.forward() with pinned HOST inputs (H2D + D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+DEFAULT_K = [128, None, 128, None, 64, None, 64, None]     # /root/reference/test.py:83
+PRETRAINED = os.path.join(ROOT, 'oracle', '_ref', 'best_model_fp32.npz')   # data fixture, built by build()
+
+
+def net_config(L, T):
+    return {'sinkhorn_iterations': T, 'match_threshold': 0.2, 'lr': 1e-4, 'loss_method': 'triplet_loss',
+            'k': list(DEFAULT_K), 'descriptor': 'FPFH', 'mutual_check': False, 'triplet_loss_gamma': 0.5,
+            'train_step': 3, 'L': L}
+
+
+def load_weights(L):
+    """(state dict of torch tensors, description). Pre-trained weights when the fixture travelled
+    with the snapshot (L=9 only), else seeded random weights of the same architecture."""
+    from mdgat_matcher_b200 import synth
+    if L == 9 and os.path.isfile(PRETRAINED):
+        with np.load(PRETRAINED) as z:
+            sd = {k: torch.from_numpy(z[k].astype(np.float64) if z[k].dtype.kind == 'f' else z[k]) for k in z.files}
+        return sd, 'pre-trained checkpoint weights (fp64(fp32), test.py load order)'
+    return synth.seeded_state_dict(L, 0), 'seeded random-init weights'
+
+
+def flops_per_pair(N, M, L):
+    """Dense FLOPs of one pair: returns (linear layers incl. encoders/final/score, attention)."""
+    D = 128
+    enc = 106880 * (N + M)
+    lin = 2 * L * (20 * D * D) * (N + M)                  # 20*D^2 per point per layer, 2L layers
+    attn_self = 4 * D * (N * N + M * M)
+    attn_cross = 4 * D * (2 * N * M)
+    attn = L * (attn_self + attn_cross)
+    final = 2 * D * D * (N + M) + 2 * D * N * M
+    return enc + lin + final, attn
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:       # NVML missing: clocks are reported as unavailable, never invented
+            self.nv, self.err = None, repr(e)
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4): 'sw_power_cap',
+            getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8): 'hw_slowdown',
+            getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksThrottleReasonHwPowerBrakeSlowdown', 0x80): 'hw_power_brake',
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if self.nv is None or not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': [], 'note': 'NVML unavailable'}
+        return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(self.samples)}
+
+
+def cpu_port_pairs_per_s(cfg, sd_np, N, M, pairs, threads, seed=123):
+    """Times the oracle port (numpy float64 restatement of the reference) on `pairs` pairs."""
+    from oracle import mdgat_oracle as O
+    from mdgat_matcher_b200 import synth
+    data = synth.make_batch(seed, pairs, N, M)
+    t0 = time.perf_counter()
+    O.forward_threaded(sd_np, data, cfg, threads)
+    dt = time.perf_counter() - t0
+    return pairs / dt, dt
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path. The reference tree
+    does not exist on the GPU box, so this is the oracle port (oracle/mdgat_oracle.py, pinned to
+    the unmodified reference by tests/golden), one pair per host thread."""
+    if rank != 0:
+        return
+    from oracle import mdgat_oracle as O
+    threads = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=1)       # one BLAS thread per pair-task
+    except Exception:
+        limiter = None
+    cfg = net_config(args.layers, args.sinkhorn)
+    sd, wdesc = load_weights(args.layers)
+    sd_np = O.state_dict_to_numpy(sd)
+    pairs = args.cpu_pairs if args.cpu_pairs > 0 else max(threads, 8)
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_port_pairs_per_s(cfg, sd_np, args.n, args.n, min(pairs, threads), threads)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        cpu_port_pairs_per_s(cfg, sd_np, args.n, args.n, pairs, threads, seed=200 + s)
+    dt = time.perf_counter() - t0
+    value = pairs * args.steps / dt
+    line = {
+        'impl': 'reference', 'metric': 'keypoint-pairs/sec', 'value': value, 'unit': 'pairs/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic in-distribution keypoint pairs; ' + wdesc,
+        'config': {'workload': 'cfg2: batch 32, 2x512 keypoints, 33-dim desc, 9 MDGAT layers (L=9), 100 Sinkhorn iters',
+                   'N': args.n, 'L': args.layers, 'sinkhorn_iterations': args.sinkhorn,
+                   'step': '%d pairs per step (bounded sample of the batch-32 workload)' % pairs},
+        'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
+                         'sample': '%d steps x %d pairs of N=M=%d, L=%d, T=%d, one pair per thread' %
+                                   (args.steps, pairs, args.n, args.layers, args.sinkhorn)},
+        'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+    if limiter is not None:
+        limiter.restore_original_limits() if hasattr(limiter, 'restore_original_limits') else None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=32, help='pairs per GPU per step')
+    ap.add_argument('--n', type=int, default=512, help='keypoints per set')
+    ap.add_argument('--layers', type=int, default=9, help='L (2L GNN layers)')
+    ap.add_argument('--sinkhorn', type=int, default=100)
+    ap.add_argument('--cpu-pairs', type=int, default=0, help='pairs in the CPU baseline sample (0 = auto)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+
+    if args.impl == 'reference':
+        run_reference_arm(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py (impl b200) needs a CUDA device; there is no CPU fallback')
+    from mdgat_matcher_b200 import synth, _capi, ops, dist as mdist
+    from mdgat_matcher_b200.models.mdgat import MDGAT
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        mdist.init_process_group('nccl')
+
+    B, N, L, T = args.batch, args.n, args.layers, args.sinkhorn
+    cfg = net_config(L, T)
+    sd, wdesc = load_weights(L)
+    net = MDGAT(cfg)
+    net.load_state_dict(sd)
+    net = net.double().eval().to(dev)
+
+    host = synth.make_batch(1000 + rank, B, N)                    # every rank its own pairs
+    host = {k: v.pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    out_keys = ('matches0', 'matches1', 'matching_scores0', 'matching_scores1', 'loss')
+
+    def step_resident():
+        d = dict(resident)
+        d['gt_matches0'] = resident['gt_matches0'].clone()      # forward rewrites gt in place (mdgat.py:519)
+        d['gt_matches1'] = resident['gt_matches1'].clone()
+        return net(d)
+
+    host_out = {}
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        o = net(d)
+        for k in out_keys:
+            if k not in host_out:
+                host_out[k] = torch.empty(o[k].shape, dtype=o[k].dtype).pin_memory()
+            host_out[k].copy_(o[k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()               # the caller reads the results every step
+        return o
+
+    for _ in range(max(args.warmup, 3)):
+        out = step_resident()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    _capi.lib.mdgat_profile_enable(1)
+    l0 = _capi.lib.mdgat_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step_resident()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = _capi.lib.mdgat_launch_count() - l0
+    stages = _capi.profile_collect()
+    _capi.lib.mdgat_profile_enable(0)
+
+    # ---------------- timed region 2: end to end through MDGAT.forward with host buffers
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join()
+
+    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        # the one collective of the path: gather every rank's match results
+        gathered = mdist.all_gather_outputs({k: out[k] for k in out_keys[:4]})
+        assert gathered['matches0'].shape[0] == B * world
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+
+    if rank != 0:
+        return
+
+    pairs_total = B * world * args.steps
+    value = pairs_total / (ms_total * 1e-3)
+    e2e_value = pairs_total / (e2e_ms * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+
+    # ---------------- roofline of the dominant stage (device time from CUDA events on the launch stream)
+    lin_f, attn_f = flops_per_pair(N, N, L)
+    dmma_peak, dfma_peak = ops.measure_fp64_peak()
+    peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    measured = json.load(open(peaks_file)) if os.path.isfile(peaks_file) else None
+    k_sched = [0 if k is None else k for k in ([None] * (2 * L - len(DEFAULT_K)) + DEFAULT_K)][-2 * L:]
+    n_topk = sum(1 for k in k_sched if k)
+    attn_full_f = attn_f * (2 * L - n_topk) / (2 * L)
+    stage_flops = {'gemm': lin_f * B, 'attn_full': attn_full_f * B}
+    per_step = {s: v['ms'] / args.steps for s, v in stages.items()}
+    dominant = max(('gemm', 'attn_full'), key=lambda s: per_step[s])
+    seg = stages[dominant]
+    achieved = stage_flops[dominant] / (per_step[dominant] * 1e-3) / 1e12
+    roofline = {
+        'bound': 'tensor', 'kernel': {'gemm': 'gemm_f64_kernel (DMMA.8x8x4)', 'attn_full': 'attn_full_kernel (DMMA.8x8x4)'}[dominant],
+        'achieved': achieved, 'peak': dmma_peak, 'unit': 'TFLOP/s', 'frac': achieved / dmma_peak, 'traffic': None,
+        'peak_source': 'fp64 DMMA issue-loop microbenchmark run in this process (MEASURED_PEAKS.json has no fp64 entry; '
+                       'the path computes in float64 for parity, tcgen05 has no f64 kind)',
+        'dfma_peak_tflops': dfma_peak,
+        'launches_per_step': seg['launches'] / args.steps,
+        'avg_launch_ms': seg['ms'] / max(seg['launches'], 1),
+        'algorithmic_flops_per_step': stage_flops[dominant],
+        'measured_peaks_file': measured,
+        'stage_ms_per_step': per_step,
+        'stage_share': {s: per_step[s] / max(sum(per_step.values()), 1e-9) for s in per_step},
+        'all_fp64_tflops': (lin_f + attn_f) * B / ((per_step['gemm'] + per_step['attn_full'] + per_step['attn_topk']) * 1e-3) / 1e12,
+    }
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import mdgat_oracle as O
+        threads = os.cpu_count() or 1
+        try:
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(limits=1)
+        except Exception:
+            pass
+        pairs = args.cpu_pairs if args.cpu_pairs > 0 else max(threads, 8)
+        v, dt = cpu_port_pairs_per_s(cfg, O.state_dict_to_numpy(sd), N, N, pairs, threads)
+        cpu_baseline = {'value': v, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
+                        'sample': '%d pairs of N=M=%d, L=%d, T=%d (%.1f s), one pair per host thread' % (pairs, N, L, T, dt)}
+
+    line = {
+        'metric': 'keypoint-pairs/sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic in-distribution keypoint pairs (SURVEY 8d generator); ' + wdesc,
+        'config': {'workload': 'cfg2: batch 32 per GPU, 2x512 keypoints, 33-dim desc, 9 MDGAT layers (L=9), 100 Sinkhorn iters',
+                   'batch_per_gpu': B, 'N': N, 'M': N, 'L': L, 'sinkhorn_iterations': T, 'k': [k or 0 for k in DEFAULT_K],
+                   'loss_method': 'triplet_loss', 'parallelism': 'batch sharded over %d rank(s), no data-path collective' % world,
+                   'l2': 'per-step working set (activations + q/k/v + logits scratch, ~0.6 GB) exceeds the 126 MB L2'},
+        'e2e': {'value': e2e_value, 'unit': 'pairs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': e2e_ms / args.steps},
+        'gpu_launches': int(launches),
+        'clocks': sampler.summary(),
+        'roofline': roofline,
+        'cpu_baseline': cpu_baseline,
+        'candidate_correspondences_per_s': value * N * N,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == '__main__':
+    main()

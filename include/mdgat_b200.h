@@ -1,0 +1,175 @@
+/* mdgat_b200.h -- C ABI of the B200-native MDGAT-matcher hot path (libmdgat_b200.so).
+ *
+ * The reference exposes this path as a Python torch.nn.Module
+ * (/root/reference/models/mdgat.py:315-603 MDGAT, models/superglue.py:315-625 SuperGlue);
+ * it has no native code, so these entry points are what a ctypes/cffi binding inside the
+ * reference's own models/mdgat.py would call in place of its eager PyTorch ops
+ * (INTEGRATION.md shows that stub). Plain pointers and sizes only: every pointer named
+ * d_* is a device pointer on the current CUDA device, every launch goes to `stream`
+ * (a cudaStream_t passed as void*), nothing synchronises unless stated.
+ *
+ * All functions return MDGAT_OK (0) or a negative error; mdgat_last_error() has the text.
+ * Activation buffers are point-major float64: one row per keypoint, 128 channels, row
+ * stride MDGAT_LDX doubles; side 0 rows (B*N) come first, side 1 rows (B*M) after.
+ */
+#ifndef MDGAT_B200_H
+#define MDGAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDGAT_OK 0
+#define MDGAT_ERR_INVALID (-1)   /* bad argument (shape, alignment, k > M ...) */
+#define MDGAT_ERR_CUDA (-2)      /* a CUDA runtime call failed */
+#define MDGAT_ERR_WORKSPACE (-3) /* workspace too small */
+
+#define MDGAT_LDX 132            /* row stride (doubles) of 128-channel activation rows */
+#define MDGAT_DESC_IN 33         /* FPFH descriptor width (load_data.py:146-165) */
+
+/* match-extraction variants (mdgat.py:442-483) */
+#define MDGAT_MATCH_DUSTBIN 0    /* loss_method != 'superglue': arg-max including the dustbin */
+#define MDGAT_MATCH_THRESHOLD 1  /* loss_method == 'superglue': inner arg-max + match_threshold */
+
+/* loss variants computed on the device (mdgat.py:486-594) */
+#define MDGAT_LOSS_NONE 0
+#define MDGAT_LOSS_TRIPLET 1     /* mdgat.py:512-546 (test.py default) */
+
+/* input element types */
+#define MDGAT_F32 0
+#define MDGAT_F64 1
+
+const char* mdgat_last_error(void);
+int mdgat_abi_version(void);
+
+/* ---- packed weights ------------------------------------------------------------------
+ * One float64 blob, BatchNorm folded into the preceding 1x1 conv, q/k/v output channels
+ * and merge input channels permuted from the reference's interleaved c = d*4 + h
+ * (mdgat.py:227) to head-major c' = h*32 + d. Layout (row-major [Cout][Cin]):
+ *   kenc: W[32][4] b[32] W[64][32] b[64] W[128][64] b[128] W[128][128] b[128]
+ *   denc: W[64][36] (33 inputs zero-padded to 36) b[64] W[128][64] b[128] W[128][128] b[128]
+ *   per GNN layer (2L): Wqkv[384][128] bqkv[384] Wmerge[128][128] bmerge[128]
+ *                       Wmlp0[256][256] bmlp0[256] Wmlp3[128][256] bmlp3[128]
+ *   final_proj: W[128][128] b[128];  bin_score (1 double, padded to 4)
+ * mdgat_weight_blob_doubles(L) is the total length. Replaces MDGAT.__init__'s parameter
+ * registration (mdgat.py:325-360) on the device side. */
+size_t mdgat_weight_blob_doubles(int L);
+
+/* ---- whole forward (mdgat.py:369-483 + triplet loss 512-546) ------------------------- */
+typedef struct {
+    int B, N, M;              /* batch, keypoints in set 0 / set 1 */
+    int L;                    /* 2L GNN layers, names ['self','cross']*L (mdgat.py:353) */
+    int sinkhorn_iters;       /* config['sinkhorn_iterations'] */
+    const int* layer_k;       /* host array [2L]: top-k of layer i, 0 = full attention
+                                 (schedule of mdgat.py:268-272 evaluated by the caller) */
+    int match_mode;           /* MDGAT_MATCH_* */
+    int mutual_check;         /* config['mutual_check'] */
+    double match_threshold;   /* config['match_threshold'] */
+    int loss_mode;            /* MDGAT_LOSS_* */
+    double triplet_gamma;     /* config['triplet_loss_gamma'] */
+    int in_dtype;             /* MDGAT_F32 / MDGAT_F64: element type of kpts/desc inputs */
+    int score_dtype;          /* element type of scores0/1 (the reference does not cast them) */
+    int write_Z;              /* also materialise Z (B,N+1,M+1) into d_Z (debug / other losses) */
+} mdgat_forward_cfg;
+
+typedef struct {
+    const void* d_kpts0;      /* (B,N,3) */
+    const void* d_kpts1;      /* (B,M,3) */
+    const void* d_desc0;      /* (B,N,33) */
+    const void* d_desc1;      /* (B,M,33) */
+    const void* d_scores0;    /* (B,N) */
+    const void* d_scores1;    /* (B,M) */
+    const int16_t* d_gt0;     /* (B,N) int16, "no match" already mapped to M (mdgat.py:519) or NULL */
+    const int16_t* d_gt1;     /* (B,M) int16, "no match" already mapped to N, or NULL */
+} mdgat_forward_in;
+
+typedef struct {
+    int64_t* d_matches0;      /* (B,N) int64, -1 = invalid */
+    int64_t* d_matches1;      /* (B,M) */
+    double* d_mscores0;       /* (B,N) */
+    double* d_mscores1;       /* (B,M) */
+    double* d_loss;           /* 1 double: mean triplet loss (if loss_mode) */
+    int* d_nvalid0;           /* 1 int: number of valid matches0 (the reference branches on it, mdgat.py:465) */
+    double* d_Z;              /* (B,N+1,M+1) or NULL unless write_Z */
+} mdgat_forward_out;
+
+size_t mdgat_forward_workspace_bytes(const mdgat_forward_cfg* cfg);
+int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights,
+                  const mdgat_forward_in* in, const mdgat_forward_out* out,
+                  void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---- individual operators (unit-parity surface; same kernels the forward uses) -------- */
+
+/* Y[r][n] = act(scale * sum_k X[r][k] W[n][k] + bias[n]) + Res[r][n]
+ * X is the concatenation [X0 (K0 cols) | X1 (K1 cols)]; X1/bias/Res may be NULL.
+ * Replaces nn.Conv1d(k=1) + folded BatchNorm1d + ReLU of MLP() (mdgat.py:34-46). */
+int mdgat_linear_f64(const double* d_X0, int ldx0, int K0, const double* d_X1, int ldx1, int K1,
+                     const double* d_W, int ldw, const double* d_bias, const double* d_Res, int ldres,
+                     double* d_Y, int ldy, int R, int Nout, double scale, int relu, void* stream);
+
+/* Batched Y[z] = scale * X[z] W[z]^T, z < batch (element strides sX, sW, sY).
+ * Replaces torch.einsum('bdn,bdm->bnm') / sqrt(D) (mdgat.py:430-431) and the dense logits
+ * einsum of dynamic_attention (mdgat.py:201). */
+int mdgat_gemm_nt_f64(const double* d_X, int ldx, long long sX, const double* d_W, int ldw, long long sW,
+                      double* d_Y, int ldy, long long sY, int R, int Nout, int K, int batch,
+                      double scale, void* stream);
+
+/* Encoders: denc(desc) + kenc(kpts, scores) for rows of both sides (mdgat.py:176-188,144-155,392-393).
+ * d_X out: (B*N + B*M) x MDGAT_LDX. d_tmp: scratch of mdgat_encode_scratch_doubles(R). */
+size_t mdgat_encode_scratch_doubles(int R);
+int mdgat_encode(const mdgat_forward_in* in, int B, int N, int M, int in_dtype, int score_dtype,
+                 const double* d_weights, double* d_X, double* d_tmp, void* stream);
+
+/* Multi-head attention message for one side (mdgat.py:190-194 / 196-210), head-major inputs:
+ * d_Q (B,4,N,36), d_K (B,4,M,36), d_V (B,4,M,34). topk == 0 -> softmax over all M,
+ * else exactly-k selection (lowest index wins ties). d_logits: scratch (B,4,N,M) doubles,
+ * needed only when topk > 0. Output rows (B*N) x ldo, column h*32+d. */
+int mdgat_attention_f64(const double* d_Q, const double* d_K, const double* d_V, double* d_Out, int ldo,
+                        int B, int N, int M, int topk, double* d_logits, void* stream);
+
+/* log_optimal_transport (mdgat.py:279-308) on couplings already holding scores in [:N,:M]:
+ * fills the dustbin row/column with bin_score (read from d_bin_score), runs `iters`
+ * Sinkhorn iterations; leaves u (B,N+1), v (B,M+1) such that
+ * Z = couplings + u + v - norm. fp64 throughout. */
+int mdgat_sinkhorn_f64(double* d_couplings, const double* d_bin_score, double* d_u, double* d_v,
+                       int B, int N, int M, int iters, void* stream);
+
+/* Match extraction + optional triplet loss from (couplings, u, v) (mdgat.py:442-483,512-546). */
+int mdgat_match_extract(const double* d_couplings, const double* d_u, const double* d_v,
+                        int B, int N, int M, int match_mode, int mutual_check, double match_threshold,
+                        int loss_mode, double gamma, const int16_t* d_gt0, const int16_t* d_gt1,
+                        const mdgat_forward_out* out, double* d_scratch, void* stream);
+size_t mdgat_match_scratch_doubles(int B, int N, int M);
+
+/* knn() (mdgat.py:8-15): indices (B,n,k) int64 of the k nearest src points, nearest first.
+ * x (B,3,n), src (B,3,m) float64 channel-major as in the reference. */
+int mdgat_knn(const double* d_x, const double* d_src, int64_t* d_idx, int B, int n, int m, int k, void* stream);
+
+/* Measured fp64 tensor-pipe peak of this device (DMMA.8x8x4 issue loop), TFLOP/s.
+ * Synchronises. Used as the roofline denominator of the fp64 kernels. */
+int mdgat_measure_fp64_peak(double* tflops_dmma, double* tflops_dfma);
+
+/* ---- instrumentation (no reference counterpart; the reference has no tracing) ----
+ * mdgat_launch_count: kernels launched by this library since load.
+ * Stage timers: when enabled, mdgat_forward brackets each run of same-stage launches with CUDA
+ * events on the caller's stream; mdgat_profile_collect synchronises on the last event and returns
+ * accumulated device milliseconds, launch counts and segment counts per stage, in the order
+ * MDGAT_STAGE_* below. */
+#define MDGAT_STAGE_ENCODE 0
+#define MDGAT_STAGE_GEMM 1        /* q/k/v, merge, MLP, final_proj, score GEMMs */
+#define MDGAT_STAGE_ATTN_FULL 2
+#define MDGAT_STAGE_ATTN_TOPK 3   /* logits GEMM + selection/softmax/sparse PV */
+#define MDGAT_STAGE_SINKHORN 4
+#define MDGAT_STAGE_MATCH 5
+#define MDGAT_STAGE_COUNT 6
+long long mdgat_launch_count(void);
+int mdgat_profile_enable(int on);
+int mdgat_profile_collect(double* ms, long long* launches, long long* segments, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDGAT_B200_H */

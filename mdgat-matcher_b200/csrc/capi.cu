@@ -1,0 +1,383 @@
+// C ABI of libmdgat_b200.so (declared in include/mdgat_b200.h) and the host-side
+// orchestration of one forward pass: the layer loop of AttentionalGNN.forward
+// (/root/reference/models/mdgat.py:259-276) and the op order of MDGAT.forward (:369-483),
+// expressed as a fixed sequence of kernel launches on the caller's stream.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <atomic>
+#include <vector>
+
+#include "../../include/mdgat_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mdgat_host {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace mdgat_host
+
+using namespace mdgat;
+
+// ---- launch counter and per-stage device timers (CUDA events on the caller's stream) ----
+namespace {
+enum { ST_ENCODE = 0, ST_GEMM, ST_ATTN_FULL, ST_ATTN_TOPK, ST_SINKHORN, ST_MATCH, ST_COUNT };
+struct Profiler {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;       // ev[i] opens segment i; the last event closes the last segment
+    std::vector<int> stage;
+    std::vector<long long> launches_at;
+    size_t used = 0;
+    double ms[ST_COUNT] = {0};
+    long long launches[ST_COUNT] = {0};
+    long long segments[ST_COUNT] = {0};
+};
+Profiler g_prof;
+std::atomic<long long> g_launches{0};
+
+cudaEvent_t next_event() {
+    if (g_prof.used == g_prof.ev.size()) { cudaEvent_t e; cudaEventCreate(&e); g_prof.ev.push_back(e); }
+    return g_prof.ev[g_prof.used++];
+}
+// marks the beginning of a run of launches belonging to `stage` (ST_COUNT closes the forward)
+void prof_mark(int stage, cudaStream_t st) {
+    if (!g_prof.on) return;
+    cudaEventRecord(next_event(), st);
+    g_prof.stage.push_back(stage);
+    g_prof.launches_at.push_back(g_launches.load());
+}
+}  // namespace
+namespace mdgat { void count_launch(int n) { g_launches.fetch_add(n); } }
+
+namespace {
+
+// ---- packed weight blob offsets (doubles); must match mdgat_matcher_b200/packing.py ----
+struct EncOffsets { size_t w[4], b[4]; };
+struct LayerOffsets { size_t wqkv, bqkv, wm, bm, w1, b1, w2, b2; };
+
+constexpr size_t KENC_DIMS[5] = {4, 32, 64, 128, 128};
+constexpr size_t DENC_DIMS[4] = {36, 64, 128, 128};
+constexpr size_t LAYER_DOUBLES = 384 * 128 + 384 + 128 * 128 + 128 + 256 * 256 + 256 + 128 * 256 + 128;
+
+struct BlobLayout {
+    EncOffsets kenc, denc;
+    size_t layers0, wf, bf, bin, total;
+    explicit BlobLayout(int L) {
+        size_t o = 0;
+        for (int i = 0; i < 4; ++i) { kenc.w[i] = o; o += KENC_DIMS[i + 1] * KENC_DIMS[i]; kenc.b[i] = o; o += KENC_DIMS[i + 1]; }
+        for (int i = 0; i < 3; ++i) { denc.w[i] = o; o += DENC_DIMS[i + 1] * DENC_DIMS[i]; denc.b[i] = o; o += DENC_DIMS[i + 1]; }
+        layers0 = o; o += (size_t)(2 * L) * LAYER_DOUBLES;
+        wf = o; o += 128 * 128; bf = o; o += 128;
+        bin = o; o += 4;
+        total = o;
+    }
+    LayerOffsets layer(int l) const {
+        LayerOffsets r; size_t o = layers0 + (size_t)l * LAYER_DOUBLES;
+        r.wqkv = o; o += 384 * 128; r.bqkv = o; o += 384;
+        r.wm = o; o += 128 * 128; r.bm = o; o += 128;
+        r.w1 = o; o += 256 * 256; r.b1 = o; o += 256;
+        r.w2 = o; o += 128 * 256; r.b2 = o; o += 128;
+        return r;
+    }
+};
+
+constexpr int LDHID = 260;   // row stride of the 256-wide MLP hidden buffer
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Workspace {
+    double *X, *Xk, *Xd, *Qh, *Kh, *Vh, *Msg, *Mg, *Hd, *MD, *S, *C, *u, *v, *mscratch;
+    size_t bytes;
+};
+
+// Carves the workspace; with base == nullptr only computes the size.
+Workspace carve(char* base, int B, int N, int M, bool need_logits) {
+    Workspace w;
+    const size_t R = (size_t)B * N + (size_t)B * M;
+    size_t off = 0;
+    auto take = [&](size_t doubles) {
+        double* p = base ? reinterpret_cast<double*>(base + off) : nullptr;
+        off += align_up(doubles * sizeof(double), 256);
+        return p;
+    };
+    w.X = take(R * LDX);
+    w.Xk = take(R * 4);
+    w.Xd = take(R * 36);
+    w.Qh = take(R * HEADS * LDH_QK);
+    w.Kh = take(R * HEADS * LDH_QK);
+    w.Vh = take(R * HEADS * LDH_V);
+    w.Msg = take(R * LDX);
+    w.Mg = take(R * LDX);
+    w.Hd = take(R * LDHID);
+    w.MD = take(R * LDX);
+    const size_t nm = (size_t)(N > M ? N : M);
+    w.S = take(need_logits ? (size_t)B * HEADS * nm * nm : 0);   // self layers need N*N and M*M
+    w.C = take((size_t)B * (N + 1) * (M + 1));
+    w.u = take((size_t)B * (N + 1));
+    w.v = take((size_t)B * (M + 1));
+    w.mscratch = take(4 * R + 8);
+    w.bytes = off;
+    return w;
+}
+
+cudaError_t linear(const double* X0, int ld0, int K0, const double* X1, int ld1, int K1,
+                   const double* W, int ldw, const double* bias, const double* Res, int ldres,
+                   double* Y, int ldy, int R, int Nout, double scale, int relu, cudaStream_t st) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.A0 = X0; p.lda0 = ld0; p.K0 = K0; p.A1 = X1; p.lda1 = ld1;
+    p.W = W; p.ldw = ldw; p.bias = bias; p.Res = Res; p.ldres = ldres; p.Y = Y; p.ldy = ldy;
+    p.R = R; p.Nout = Nout; p.K = K0 + K1; p.scale = scale; p.relu = relu;
+    return launch_gemm(p, EPI_PLAIN, 1, st);
+}
+
+cudaError_t gemm_nt(const double* X, int ldx, long long sX, const double* W, int ldw, long long sW,
+                    double* Y, int ldy, long long sY, int R, int Nout, int K, int batch, double scale,
+                    cudaStream_t st) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.A0 = X; p.lda0 = ldx; p.K0 = K; p.W = W; p.ldw = ldw; p.Y = Y; p.ldy = ldy;
+    p.R = R; p.Nout = Nout; p.K = K; p.scale = scale; p.sA = sX; p.sW = sW; p.sY = sY;
+    return launch_gemm(p, EPI_PLAIN, batch, st);
+}
+
+cudaError_t attention_side(const double* Q, const double* K, const double* V, double* Out, int ldo,
+                           int B, int N, int M, int topk, double* S, cudaStream_t st) {
+    if (topk <= 0) return launch_attention_full(Q, K, V, Out, ldo, B, N, M, st);
+    // dense logits q.k / sqrt(32) for every (b, h): batched X W^T with K = 32 (mdgat.py:201)
+    cudaError_t e = gemm_nt(Q, LDH_QK, (long long)N * LDH_QK, K, LDH_QK, (long long)M * LDH_QK,
+                            S, M, (long long)N * M, N, M, HDIM, B * HEADS, 1.0 / sqrt((double)HDIM), st);
+    if (e != cudaSuccess) return e;
+    return launch_topk_softmax_pv(S, V, Out, ldo, B, N, M, topk, st);
+}
+
+cudaError_t encode(const mdgat_forward_in* in, int B, int N, int M, int in_dtype, int score_dtype,
+                   const double* Wt, const BlobLayout& lay, double* X, double* Xk, double* Xd,
+                   double* T0, double* T1, double* T2, int ldt2, cudaStream_t st) {
+    const int R = B * N + B * M;
+    cudaError_t e = launch_pack_inputs(in->d_kpts0, in->d_kpts1, in->d_desc0, in->d_desc1, in->d_scores0,
+                                       in->d_scores1, in_dtype, score_dtype, B, N, M, Xk, Xd, st);
+    if (e != cudaSuccess) return e;
+    // KeypointEncoder: 4 -> 32 -> 64 -> 128 -> 128 (mdgat.py:181), BN folded, ReLU on the first three
+    if ((e = linear(Xk, 4, 4, nullptr, 0, 0, Wt + lay.kenc.w[0], 4, Wt + lay.kenc.b[0], nullptr, 0, T0, LDX, R, 32, 1.0, 1, st))) return e;
+    if ((e = linear(T0, LDX, 32, nullptr, 0, 0, Wt + lay.kenc.w[1], 32, Wt + lay.kenc.b[1], nullptr, 0, T1, LDX, R, 64, 1.0, 1, st))) return e;
+    if ((e = linear(T1, LDX, 64, nullptr, 0, 0, Wt + lay.kenc.w[2], 64, Wt + lay.kenc.b[2], nullptr, 0, T0, LDX, R, 128, 1.0, 1, st))) return e;
+    if ((e = linear(T0, LDX, 128, nullptr, 0, 0, Wt + lay.kenc.w[3], 128, Wt + lay.kenc.b[3], nullptr, 0, T1, LDX, R, 128, 1.0, 0, st))) return e;
+    // DescriptorEncoder: 33(36) -> 64 -> 128 -> 128 (mdgat.py:148); the last layer adds kenc (mdgat.py:392)
+    if ((e = linear(Xd, 36, 36, nullptr, 0, 0, Wt + lay.denc.w[0], 36, Wt + lay.denc.b[0], nullptr, 0, T0, LDX, R, 64, 1.0, 1, st))) return e;
+    if ((e = linear(T0, LDX, 64, nullptr, 0, 0, Wt + lay.denc.w[1], 64, Wt + lay.denc.b[1], nullptr, 0, T2, ldt2, R, 128, 1.0, 1, st))) return e;
+    return linear(T2, ldt2, 128, nullptr, 0, 0, Wt + lay.denc.w[2], 128, Wt + lay.denc.b[2], T1, LDX, X, LDX, R, 128, 1.0, 0, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mdgat_last_error(void) { return mdgat_host::g_err; }
+int mdgat_abi_version(void) { return 1; }
+
+size_t mdgat_weight_blob_doubles(int L) { return BlobLayout(L).total; }
+
+size_t mdgat_forward_workspace_bytes(const mdgat_forward_cfg* cfg) {
+    bool need = false;
+    for (int i = 0; i < 2 * cfg->L; ++i) need = need || (cfg->layer_k && cfg->layer_k[i] > 0);
+    return carve(nullptr, cfg->B, cfg->N, cfg->M, need).bytes;
+}
+
+int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const mdgat_forward_in* in,
+                  const mdgat_forward_out* out, void* d_workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int B = cfg->B, N = cfg->N, M = cfg->M, L = cfg->L;
+    MDGAT_REQUIRE(B > 0 && N > 0 && M > 0 && L > 0, "mdgat_forward: B, N, M, L must be positive (got %d %d %d %d)", B, N, M, L);
+    MDGAT_REQUIRE(cfg->layer_k != nullptr, "mdgat_forward: layer_k is NULL");
+    MDGAT_REQUIRE((long long)B * (N + M) < (1ll << 31) / LDHID, "mdgat_forward: batch too large for 32-bit row indexing");
+    bool need = false;
+    for (int i = 0; i < 2 * L; ++i) {
+        const int k = cfg->layer_k[i];
+        if (k > 0) {
+            need = true;
+            // side 0 attends over N (self) or M (cross) sources, side 1 over M or N: topk() needs k <= both
+            MDGAT_REQUIRE(k <= N && k <= M, "selected index k out of range (layer %d: k=%d, N=%d, M=%d)", i, k, N, M);
+            MDGAT_REQUIRE(N <= 2048 && M <= 2048, "top-k attention supports at most 2048 source keypoints (N=%d, M=%d)", N, M);
+        }
+    }
+    if (cfg->loss_mode == MDGAT_LOSS_TRIPLET) {
+        MDGAT_REQUIRE(in->d_gt0 && in->d_gt1, "triplet loss needs gt_matches0/1");
+        MDGAT_REQUIRE(N == M, "triplet loss needs N == M (the reference raises IndexError otherwise, mdgat.py:537)");
+        MDGAT_REQUIRE(cfg->match_mode == MDGAT_MATCH_DUSTBIN, "triplet loss is defined on the dustbin match variant");
+    }
+    Workspace w = carve(reinterpret_cast<char*>(d_workspace), B, N, M, need);
+    if (w.bytes > workspace_bytes) {
+        mdgat_host::set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+        return MDGAT_ERR_WORKSPACE;
+    }
+    const BlobLayout lay(L);
+    const double* Wt = d_weights;
+    const int R0 = B * N, R1 = B * M, R = R0 + R1;
+
+    prof_mark(ST_ENCODE, st);
+    MDGAT_CUDA_OK(encode(in, B, N, M, cfg->in_dtype, cfg->score_dtype, Wt, lay, w.X, w.Xk, w.Xd, w.Msg, w.Mg, w.Hd, LDHID, st));
+
+    // head-major buffers: side 0 occupies the first R0*4 rows, side 1 the rest
+    const double* Q0 = w.Qh; const double* Q1 = w.Qh + (size_t)R0 * HEADS * LDH_QK;
+    const double* K0 = w.Kh; const double* K1 = w.Kh + (size_t)R0 * HEADS * LDH_QK;
+    const double* V0 = w.Vh; const double* V1 = w.Vh + (size_t)R0 * HEADS * LDH_V;
+
+    for (int l = 0; l < 2 * L; ++l) {
+        const LayerOffsets lo = lay.layer(l);
+        const bool cross = (l & 1) != 0;                  // names = ['self','cross']*L (mdgat.py:353)
+        const int k = cfg->layer_k[l];
+        // q/k/v of both sides with the shared layer weights (mdgat.py:227-232, :270)
+        GemmParams p;
+        memset(&p, 0, sizeof(p));
+        p.A0 = w.X; p.lda0 = LDX; p.K0 = DMODEL; p.W = Wt + lo.wqkv; p.ldw = DMODEL; p.bias = Wt + lo.bqkv;
+        p.R = R; p.Nout = 3 * DMODEL; p.K = DMODEL; p.scale = 1.0;
+        p.Qh = w.Qh; p.Kh = w.Kh; p.Vh = w.Vh; p.rows0 = R0; p.n0 = N; p.n1 = M;
+        prof_mark(ST_GEMM, st);
+        MDGAT_CUDA_OK(launch_gemm(p, EPI_QKV, 1, st));
+        prof_mark(k > 0 ? ST_ATTN_TOPK : ST_ATTN_FULL, st);
+        // messages: side 0 reads side (cross ? 1 : 0), side 1 the other way round (mdgat.py:263-266)
+        MDGAT_CUDA_OK(attention_side(Q0, cross ? K1 : K0, cross ? V1 : V0, w.Msg, LDX, B, N, cross ? M : N, k, w.S, st));
+        MDGAT_CUDA_OK(attention_side(Q1, cross ? K0 : K1, cross ? V0 : V1, w.Msg + (size_t)R0 * LDX, LDX, B, M, cross ? N : M, k, w.S, st));
+        prof_mark(ST_GEMM, st);
+        // merge conv (mdgat.py:237)
+        MDGAT_CUDA_OK(linear(w.Msg, LDX, DMODEL, nullptr, 0, 0, Wt + lo.wm, DMODEL, Wt + lo.bm, nullptr, 0, w.Mg, LDX, R, DMODEL, 1.0, 0, st));
+        // mlp(cat[x, message]) : 256 -> 256 (BN folded, ReLU) -> 128, then the residual (mdgat.py:248, :274)
+        MDGAT_CUDA_OK(linear(w.X, LDX, DMODEL, w.Mg, LDX, DMODEL, Wt + lo.w1, 2 * DMODEL, Wt + lo.b1, nullptr, 0, w.Hd, LDHID, R, 2 * DMODEL, 1.0, 1, st));
+        MDGAT_CUDA_OK(linear(w.Hd, LDHID, 2 * DMODEL, nullptr, 0, 0, Wt + lo.w2, 2 * DMODEL, Wt + lo.b2, w.X, LDX, w.X, LDX, R, DMODEL, 1.0, 0, st));
+    }
+    // final_proj (mdgat.py:397) and scores = mdesc0^T mdesc1 / sqrt(128) (:430-431) into the couplings
+    MDGAT_CUDA_OK(linear(w.X, LDX, DMODEL, nullptr, 0, 0, Wt + lay.wf, DMODEL, Wt + lay.bf, nullptr, 0, w.MD, LDX, R, DMODEL, 1.0, 0, st));
+    MDGAT_CUDA_OK(gemm_nt(w.MD, LDX, (long long)N * LDX, w.MD + (size_t)R0 * LDX, LDX, (long long)M * LDX,
+                          w.C, M + 1, (long long)(N + 1) * (M + 1), N, M, DMODEL, B, 1.0 / sqrt((double)DMODEL), st));
+    prof_mark(ST_SINKHORN, st);
+    MDGAT_CUDA_OK(launch_fill_dustbin(w.C, Wt + lay.bin, B, N, M, st));
+    MDGAT_CUDA_OK(launch_sinkhorn(w.C, w.u, w.v, B, N, M, cfg->sinkhorn_iters, st));
+    prof_mark(ST_MATCH, st);
+
+    MatchParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.C = w.C; mp.u = w.u; mp.v = w.v; mp.B = B; mp.N = N; mp.M = M;
+    mp.match_mode = cfg->match_mode; mp.mutual_check = cfg->mutual_check; mp.match_threshold = cfg->match_threshold;
+    mp.loss_mode = cfg->loss_mode; mp.gamma = cfg->triplet_gamma; mp.gt0 = in->d_gt0; mp.gt1 = in->d_gt1;
+    mp.matches0 = out->d_matches0; mp.matches1 = out->d_matches1; mp.ms0 = out->d_mscores0; mp.ms1 = out->d_mscores1;
+    mp.loss = out->d_loss; mp.nvalid0 = out->d_nvalid0; mp.Z = cfg->write_Z ? out->d_Z : nullptr;
+    mp.scratch = w.mscratch;
+    MDGAT_CUDA_OK(launch_match_extract(mp, st));
+    prof_mark(ST_COUNT, st);
+    return MDGAT_OK;
+}
+
+int mdgat_linear_f64(const double* d_X0, int ldx0, int K0, const double* d_X1, int ldx1, int K1,
+                     const double* d_W, int ldw, const double* d_bias, const double* d_Res, int ldres,
+                     double* d_Y, int ldy, int R, int Nout, double scale, int relu, void* stream) {
+    MDGAT_REQUIRE(K0 > 0 && (ldx0 % 2) == 0 && (ldw % 2) == 0 && (K0 % 2) == 0 && (K1 % 2) == 0,
+                  "mdgat_linear_f64: K0, K1, ldx, ldw must be even (16-byte staging)");
+    MDGAT_REQUIRE(d_X1 == nullptr || ((K0 % 32) == 0 && (ldx1 % 2) == 0), "mdgat_linear_f64: with a second input K0 must be a multiple of 32");
+    MDGAT_CUDA_OK(linear(d_X0, ldx0, K0, d_X1, ldx1, d_X1 ? K1 : 0, d_W, ldw, d_bias, d_Res, ldres, d_Y, ldy, R, Nout,
+                         scale, relu, reinterpret_cast<cudaStream_t>(stream)));
+    return MDGAT_OK;
+}
+
+int mdgat_gemm_nt_f64(const double* d_X, int ldx, long long sX, const double* d_W, int ldw, long long sW,
+                      double* d_Y, int ldy, long long sY, int R, int Nout, int K, int batch, double scale, void* stream) {
+    MDGAT_REQUIRE((ldx % 2) == 0 && (ldw % 2) == 0 && (K % 2) == 0 && (sX % 2) == 0 && (sW % 2) == 0,
+                  "mdgat_gemm_nt_f64: K, ld and batch strides must be even (16-byte staging)");
+    MDGAT_CUDA_OK(gemm_nt(d_X, ldx, sX, d_W, ldw, sW, d_Y, ldy, sY, R, Nout, K, batch, scale, reinterpret_cast<cudaStream_t>(stream)));
+    return MDGAT_OK;
+}
+
+size_t mdgat_encode_scratch_doubles(int R) { return (size_t)R * (4 + 36 + LDX + LDX + LDX); }
+
+int mdgat_encode(const mdgat_forward_in* in, int B, int N, int M, int in_dtype, int score_dtype,
+                 const double* d_weights, double* d_X, double* d_tmp, void* stream) {
+    const size_t R = (size_t)B * N + (size_t)B * M;
+    double* Xk = d_tmp; double* Xd = Xk + R * 4; double* T0 = Xd + R * 36; double* T1 = T0 + R * LDX; double* T2 = T1 + R * LDX;
+    const BlobLayout lay(1);      // encoder offsets do not depend on L
+    MDGAT_CUDA_OK(encode(in, B, N, M, in_dtype, score_dtype, d_weights, lay, d_X, Xk, Xd, T0, T1, T2, LDX,
+                         reinterpret_cast<cudaStream_t>(stream)));
+    return MDGAT_OK;
+}
+
+int mdgat_attention_f64(const double* d_Q, const double* d_K, const double* d_V, double* d_Out, int ldo,
+                        int B, int N, int M, int topk, double* d_logits, void* stream) {
+    MDGAT_REQUIRE(topk <= M, "selected index k out of range (k=%d, M=%d)", topk, M);
+    MDGAT_REQUIRE(topk <= 0 || (d_logits != nullptr && M <= 2048), "mdgat_attention_f64: top-k needs a logits scratch and M <= 2048");
+    MDGAT_REQUIRE((ldo % 2) == 0, "mdgat_attention_f64: ldo must be even");
+    MDGAT_CUDA_OK(attention_side(d_Q, d_K, d_V, d_Out, ldo, B, N, M, topk, d_logits, reinterpret_cast<cudaStream_t>(stream)));
+    return MDGAT_OK;
+}
+
+int mdgat_sinkhorn_f64(double* d_couplings, const double* d_bin_score, double* d_u, double* d_v,
+                       int B, int N, int M, int iters, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    MDGAT_REQUIRE(B > 0 && N > 0 && M > 0 && iters >= 0, "mdgat_sinkhorn_f64: bad shape");
+    MDGAT_CUDA_OK(launch_fill_dustbin(d_couplings, d_bin_score, B, N, M, st));
+    MDGAT_CUDA_OK(launch_sinkhorn(d_couplings, d_u, d_v, B, N, M, iters, st));
+    return MDGAT_OK;
+}
+
+size_t mdgat_match_scratch_doubles(int B, int N, int M) { return 4 * ((size_t)B * N + (size_t)B * M) + 8; }
+
+int mdgat_match_extract(const double* d_couplings, const double* d_u, const double* d_v, int B, int N, int M,
+                        int match_mode, int mutual_check, double match_threshold, int loss_mode, double gamma,
+                        const int16_t* d_gt0, const int16_t* d_gt1, const mdgat_forward_out* out,
+                        double* d_scratch, void* stream) {
+    MDGAT_REQUIRE(loss_mode == MDGAT_LOSS_NONE || (d_gt0 && d_gt1 && N == M && match_mode == MDGAT_MATCH_DUSTBIN),
+                  "mdgat_match_extract: triplet loss needs gt, N == M and the dustbin variant");
+    MatchParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.C = d_couplings; mp.u = d_u; mp.v = d_v; mp.B = B; mp.N = N; mp.M = M;
+    mp.match_mode = match_mode; mp.mutual_check = mutual_check; mp.match_threshold = match_threshold;
+    mp.loss_mode = loss_mode; mp.gamma = gamma; mp.gt0 = d_gt0; mp.gt1 = d_gt1;
+    mp.matches0 = out->d_matches0; mp.matches1 = out->d_matches1; mp.ms0 = out->d_mscores0; mp.ms1 = out->d_mscores1;
+    mp.loss = out->d_loss; mp.nvalid0 = out->d_nvalid0; mp.Z = out->d_Z; mp.scratch = d_scratch;
+    MDGAT_CUDA_OK(launch_match_extract(mp, reinterpret_cast<cudaStream_t>(stream)));
+    return MDGAT_OK;
+}
+
+int mdgat_knn(const double* d_x, const double* d_src, int64_t* d_idx, int B, int n, int m, int k, void* stream) {
+    MDGAT_REQUIRE(k > 0 && k <= m, "selected index k out of range (k=%d, m=%d)", k, m);
+    MDGAT_REQUIRE(m <= 2048, "mdgat_knn supports at most 2048 source points (m=%d)", m);
+    MDGAT_CUDA_OK(launch_knn(d_x, d_src, d_idx, B, n, m, k, reinterpret_cast<cudaStream_t>(stream)));
+    return MDGAT_OK;
+}
+
+long long mdgat_launch_count(void) { return g_launches.load(); }
+
+int mdgat_profile_enable(int on) {
+    g_prof.on = on != 0;
+    g_prof.used = 0; g_prof.stage.clear(); g_prof.launches_at.clear();
+    for (int i = 0; i < ST_COUNT; ++i) { g_prof.ms[i] = 0; g_prof.launches[i] = 0; g_prof.segments[i] = 0; }
+    return MDGAT_OK;
+}
+
+int mdgat_profile_collect(double* ms, long long* launches, long long* segments, int n) {
+    MDGAT_REQUIRE(n >= ST_COUNT, "mdgat_profile_collect: need room for %d stages", (int)ST_COUNT);
+    if (g_prof.used > 0) MDGAT_CUDA_OK(cudaEventSynchronize(g_prof.ev[g_prof.used - 1]));
+    for (size_t i = 0; i + 1 < g_prof.used; ++i) {
+        const int s = g_prof.stage[i];
+        if (s >= ST_COUNT) continue;                 // gap between two forwards
+        float t = 0.f;
+        MDGAT_CUDA_OK(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
+        g_prof.ms[s] += t;
+        g_prof.launches[s] += g_prof.launches_at[i + 1] - g_prof.launches_at[i];
+        g_prof.segments[s] += 1;
+    }
+    g_prof.used = 0; g_prof.stage.clear(); g_prof.launches_at.clear();
+    for (int i = 0; i < ST_COUNT; ++i) { ms[i] = g_prof.ms[i]; launches[i] = g_prof.launches[i]; segments[i] = g_prof.segments[i]; }
+    return MDGAT_OK;
+}
+
+int mdgat_measure_fp64_peak(double* tflops_dmma, double* tflops_dfma) {
+    MDGAT_CUDA_OK(measure_fp64_peak(tflops_dmma, tflops_dfma));
+    return MDGAT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+// Shared device helpers for the sm_100a kernels of mdgat-matcher_b200.
+//
+// Arithmetic policy (DESIGN.md "Precision"): the reference runs in float64 end to end
+// (/root/reference/test.py:193) and its top-k layers make the result discontinuous in the
+// logits, so everything that feeds a dynamic layer is computed in float64. tcgen05.mma has
+// no f64 kind; the f64 tensor path on sm_100a is mma.sync.m8n8k4 (SASS: DMMA.8x8x4).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define DEVINL __device__ __forceinline__
+
+namespace mdgat {
+
+constexpr int HEADS = 4;        // AttentionalPropagation(feature_dim, 4), mdgat.py:255
+constexpr int HDIM = 32;        // 128 / 4
+constexpr int DMODEL = 128;
+constexpr int LDH_QK = 36;      // row stride (doubles) of head-major Q and K buffers
+constexpr int LDH_V = 34;       // row stride (doubles) of the head-major V buffer
+constexpr int LDX = 132;        // row stride (doubles) of 128-wide activation buffers
+
+// D(8x8) += A(8x4, row) * B(4x8, col). Lane t holds A[t/4][t%4], B[t%4][t/4],
+// C[t/4][2*(t%4) + {0,1}].
+DEVINL void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// 16-byte async copy global -> shared (LDGSTS); bytes beyond src_bytes are zero-filled.
+DEVINL void cp_async16(void* smem, const void* gmem, bool pred) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    int sz = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(s), "l"(gmem), "r"(sz));
+}
+DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
+
+// ---- mbarrier + bulk (TMA engine) copies: 1-D cp.async.bulk global -> shared::cta ----
+DEVINL void mbar_init(uint64_t* bar, unsigned count) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(s), "r"(count));
+}
+DEVINL void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::); }
+DEVINL void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(s), "r"(bytes) : "memory");
+}
+DEVINL void mbar_arrive(uint64_t* bar) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(s) : "memory");
+}
+DEVINL void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" :: "r"(s), "r"(parity) : "memory");
+}
+// bytes must be a multiple of 16; both addresses 16-byte aligned.
+DEVINL void bulk_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem);
+    unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(d), "l"(gmem), "r"(bytes), "r"(b) : "memory");
+}
+
+DEVINL double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+DEVINL double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+DEVINL double warp_max_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, shfl_xor_d(v, o));
+    return v;
+}
+DEVINL double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(v, o);
+    return v;
+}
+
+}  // namespace mdgat
+
+// ---- host-side error plumbing shared by the C ABI translation units ----
+namespace mdgat_host {
+void set_error(const char* fmt, ...);
+}
+#define MDGAT_CUDA_OK(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            mdgat_host::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                  __FILE__, __LINE__);                                   \
+            return MDGAT_ERR_CUDA;                                                       \
+        }                                                                                \
+    } while (0)
+#define MDGAT_REQUIRE(cond, ...)                     \
+    do {                                             \
+        if (!(cond)) {                               \
+            mdgat_host::set_error(__VA_ARGS__);      \
+            return MDGAT_ERR_INVALID;                \
+        }                                            \
+    } while (0)

@@ -1,0 +1,61 @@
+// Internal (C++) launcher interface between the kernel translation units and the C ABI
+// in capi.cu. Not part of the public boundary (that is include/mdgat_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mdgat {
+
+enum { EPI_PLAIN = 0, EPI_QKV = 1 };
+
+// every kernel launch of this library is counted (bench.py reports it as gpu_launches)
+void count_launch(int n = 1);
+
+struct GemmParams {
+    const double* A0; int lda0; int K0;     // first K0 input columns
+    const double* A1; int lda1;             // remaining K - K0 columns (may be null)
+    const double* W; int ldw;               // [Nout][K]
+    const double* bias;                     // [Nout] or null
+    const double* Res; int ldres;           // [R][Nout] or null (may alias Y)
+    double* Y; int ldy;
+    int R, Nout, K;
+    double scale; int relu;
+    long long sA, sW, sY;                   // batch strides (elements) for blockIdx.z
+    // EPI_QKV: scatter the 384 output columns into head-major Q/K/V buffers
+    double *Qh, *Kh, *Vh; int rows0, n0, n1;
+};
+cudaError_t launch_gemm(const GemmParams& p, int epi, int batch, cudaStream_t st);
+
+// Full-softmax multi-head attention for one side (flash-style, fp64 DMMA).
+cudaError_t launch_attention_full(const double* Q, const double* K, const double* V, double* Out, int ldo,
+                                  int B, int N, int M, cudaStream_t st);
+// Exact top-k selection + softmax + sparse P.V from materialised logits S (B,4,N,M).
+cudaError_t launch_topk_softmax_pv(const double* S, const double* V, double* Out, int ldo,
+                                   int B, int N, int M, int topk, cudaStream_t st);
+
+// Encoder input staging: Xk (R x 4) = [x,y,z,score], Xd (R x 36) = [33 desc | 0 0 0]
+cudaError_t launch_pack_inputs(const void* kpts0, const void* kpts1, const void* desc0, const void* desc1,
+                               const void* sc0, const void* sc1, int in_dtype, int score_dtype,
+                               int B, int N, int M, double* Xk, double* Xd, cudaStream_t st);
+
+// Sinkhorn (general, global-memory resident couplings)
+cudaError_t launch_fill_dustbin(double* C, const double* bin_score, int B, int N, int M, cudaStream_t st);
+cudaError_t launch_sinkhorn(const double* C, double* u, double* v, int B, int N, int M, int iters, cudaStream_t st);
+
+struct MatchParams {
+    const double* C; const double* u; const double* v;
+    int B, N, M;
+    int match_mode, mutual_check; double match_threshold;
+    int loss_mode; double gamma;
+    const int16_t* gt0; const int16_t* gt1;
+    int64_t* matches0; int64_t* matches1; double* ms0; double* ms1;
+    double* loss; int* nvalid0; double* Z;
+    double* scratch;
+};
+cudaError_t launch_match_extract(const MatchParams& p, cudaStream_t st);
+
+cudaError_t launch_knn(const double* x, const double* src, int64_t* idx, int B, int n, int m, int k, cudaStream_t st);
+
+cudaError_t measure_fp64_peak(double* dmma_tflops, double* dfma_tflops);
+
+}  // namespace mdgat

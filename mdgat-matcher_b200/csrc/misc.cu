@@ -1,0 +1,175 @@
+// Input staging for the encoders, the stand-alone brute-force kNN, and the fp64 pipe
+// micro-benchmark that provides the roofline denominator of the float64 kernels.
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/mdgat_b200.h"
+
+namespace mdgat {
+
+DEVINL double load_as_f64(const void* p, long long i, int dtype) {
+    return dtype == MDGAT_F64 ? reinterpret_cast<const double*>(p)[i]
+                              : (double)reinterpret_cast<const float*>(p)[i];
+}
+
+// KeypointEncoder input cat[kpts^T, score] (mdgat.py:186) -> Xk[r][0..3];
+// DescriptorEncoder input desc^T (:154) -> Xd[r][0..32], columns 33..35 zero.
+__global__ void __launch_bounds__(256)
+pack_inputs_kernel(const void* kp0, const void* kp1, const void* de0, const void* de1,
+                   const void* sc0, const void* sc1, int in_dtype, int score_dtype,
+                   long long rows0, long long rows, double* __restrict__ Xk, double* __restrict__ Xd) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = t / 40;
+    const int c = (int)(t - r * 40);
+    if (r >= rows) return;
+    const bool s1 = r >= rows0;
+    const long long rr = s1 ? r - rows0 : r;
+    if (c < 36) {
+        Xd[r * 36 + c] = c < MDGAT_DESC_IN ? load_as_f64(s1 ? de1 : de0, rr * MDGAT_DESC_IN + c, in_dtype) : 0.0;
+    } else {
+        const int k = c - 36;
+        Xk[r * 4 + k] = k < 3 ? load_as_f64(s1 ? kp1 : kp0, rr * 3 + k, in_dtype)
+                              : load_as_f64(s1 ? sc1 : sc0, rr, score_dtype);
+    }
+}
+
+cudaError_t launch_pack_inputs(const void* kpts0, const void* kpts1, const void* desc0, const void* desc1,
+                               const void* sc0, const void* sc1, int in_dtype, int score_dtype,
+                               int B, int N, int M, double* Xk, double* Xd, cudaStream_t st) {
+    const long long rows0 = (long long)B * N, rows = rows0 + (long long)B * M;
+    if (rows == 0) return cudaSuccess;
+    const long long total = rows * 40;
+    pack_inputs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(kpts0, kpts1, desc0, desc1, sc0, sc1,
+                                                                      in_dtype, score_dtype, rows0, rows, Xk, Xd);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// knn() (mdgat.py:8-15): pairwise_distance = -xx - inner - ss with inner = -2 x.src, then
+// topk(k) largest, sorted. One warp per query point; candidates live in registers
+// (m <= 32*VPT); k rounds of warp arg-max with lowest-index tie-break.
+// ---------------------------------------------------------------------------------------
+template <int VPT>
+__global__ void __launch_bounds__(128)
+knn_kernel(const double* __restrict__ x, const double* __restrict__ src, int64_t* __restrict__ idx,
+           int n, int m, int k) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, i = blockIdx.x * 4 + warp;
+    if (i >= n) return;
+    const double* xb = x + (long long)b * 3 * n;
+    const double* sb = src + (long long)b * 3 * m;
+    const double x0 = xb[i], x1 = xb[n + i], x2 = xb[2 * n + i];
+    const double xx = x0 * x0 + x1 * x1 + x2 * x2;
+    double pd[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+        const int j = lane + 32 * v;
+        if (j < m) {
+            const double s0 = sb[j], s1 = sb[m + j], s2 = sb[2 * m + j];
+            const double inner = -2.0 * (x0 * s0 + x1 * s1 + x2 * s2);
+            const double ss = s0 * s0 + s1 * s1 + s2 * s2;
+            pd[v] = -xx - inner - ss;
+        } else {
+            pd[v] = -INFINITY;
+        }
+    }
+    unsigned long long taken = 0ull;
+    int64_t* out = idx + ((long long)b * n + i) * k;
+    for (int r = 0; r < k; ++r) {
+        double bv = -INFINITY; int bj = 0x7fffffff;
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+            const int j = lane + 32 * v;
+            if (j < m && !((taken >> v) & 1ull) && (pd[v] > bv || (pd[v] == bv && j < bj))) { bv = pd[v]; bj = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = shfl_xor_d(bv, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+            if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+        }
+        if ((bj & 31) == lane) taken |= 1ull << (bj >> 5);
+        if (lane == 0) out[r] = bj;
+    }
+}
+
+cudaError_t launch_knn(const double* x, const double* src, int64_t* idx, int B, int n, int m, int k, cudaStream_t st) {
+    if (B <= 0 || n <= 0) return cudaSuccess;
+    dim3 grid((n + 3) / 4, B);
+    if (m <= 512) knn_kernel<16><<<grid, 128, 0, st>>>(x, src, idx, n, m, k);
+    else if (m <= 2048) knn_kernel<64><<<grid, 128, 0, st>>>(x, src, idx, n, m, k);
+    else return cudaErrorInvalidValue;
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// fp64 pipe peak: 8 independent DMMA (or 16 DFMA) chains per warp, 16 warps per CTA,
+// 2 CTAs per SM. Reported in TFLOP/s (DMMA.8x8x4 = 512 FLOP per warp instruction).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) dmma_peak_kernel(double* out, int iters, double a0, double b0) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+    const double a = a0 + threadIdx.x * 1e-9, b = b0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s;
+}
+__global__ void __launch_bounds__(512) dfma_peak_kernel(double* out, int iters, double a0, double b0) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = i;
+    const double a = a0 + threadIdx.x * 1e-9, b = b0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 123.456) out[0] = s;
+}
+
+cudaError_t measure_fp64_peak(double* dmma_tflops, double* dfma_tflops) {
+    int dev = 0, sms = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    double* d = nullptr;
+    if ((e = cudaMalloc(&d, 64)) != cudaSuccess) return e;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    const int iters = 4000, grid = sms * 2;
+    float ms = 0.f;
+    for (int rep = 0; rep < 2; ++rep) {         // first rep warms up
+        cudaEventRecord(t0);
+        dmma_peak_kernel<<<grid, 512>>>(d, iters, 1.0000001, 0.5);
+        cudaEventRecord(t1);
+        cudaEventSynchronize(t1);
+        cudaEventElapsedTime(&ms, t0, t1);
+    }
+    *dmma_tflops = (double)grid * 16 * iters * 32 * 512.0 / (ms * 1e-3) / 1e12;
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(t0);
+        dfma_peak_kernel<<<grid, 512>>>(d, iters, 0.999999, 1e-3);
+        cudaEventRecord(t1);
+        cudaEventSynchronize(t1);
+        cudaEventElapsedTime(&ms, t0, t1);
+    }
+    *dfma_tflops = (double)grid * 512 * iters * 32 * 2.0 / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    cudaFree(d);
+    return cudaGetLastError();
+}
+
+}  // namespace mdgat

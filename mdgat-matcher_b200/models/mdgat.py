@@ -1,0 +1,359 @@
+"""MDGAT behind the reference's own nn.Module API, computed by the sm_100a kernels.
+
+Mirrors /root/reference/models/mdgat.py:315-603 (class MDGAT): the constructor takes the same
+config dict (test.py:137-151), registers parameters and buffers under the same names (so the
+shipped checkpoint loads with strict=True through DataParallel), and forward(dict) -> dict
+returns matches0/1 (int64, -1 = unmatched), matching_scores0/1 (float64) and loss.
+
+eval mode  -> hand-written CUDA path through the C ABI (include/mdgat_b200.h); CUDA tensors
+              only, no CPU or eager fallback.
+train mode -> a differentiable torch restatement (train.py needs autograd and batch-statistics
+              BatchNorm); same math, library kernels.
+"""
+import ctypes
+from copy import deepcopy
+
+import torch
+from torch import nn
+
+from .. import packing, losses
+
+_DESCRIPTORS_OUT_OF_SCOPE = ('pointnet', 'pointnetmsg', 'FPFH_gloabal', 'FPFH_only')
+
+
+def MLP(channels, do_bn=True):
+    """1x1-conv stack with BatchNorm + ReLU after every conv but the last. The Sequential
+    index layout (conv at 3i, BN at 3i+1, ReLU at 3i+2) is part of the checkpoint format."""
+    mods = []
+    last = len(channels) - 1
+    for i in range(1, len(channels)):
+        mods.append(nn.Conv1d(channels[i - 1], channels[i], kernel_size=1, bias=True))
+        if i < last:
+            if do_bn:
+                mods.append(nn.BatchNorm1d(channels[i]))
+            mods.append(nn.ReLU())
+    return nn.Sequential(*mods)
+
+
+class KeypointEncoder(nn.Module):
+    """(x, y, z, saliency) -> feature_dim (mdgat.py:176-188)."""
+
+    def __init__(self, feature_dim, layers):
+        super().__init__()
+        self.encoder = MLP([4] + list(layers) + [feature_dim])
+        nn.init.constant_(self.encoder[-1].bias, 0.0)
+
+    def forward(self, kpts, scores):
+        return self.encoder(torch.cat([kpts.transpose(1, 2), scores.unsqueeze(1)], dim=1))
+
+
+class DescriptorEncoder(nn.Module):
+    """33-bin FPFH -> feature_dim (mdgat.py:144-155)."""
+
+    def __init__(self, feature_dim, layers):
+        super().__init__()
+        self.encoder = MLP([33] + list(layers) + [feature_dim])
+        nn.init.constant_(self.encoder[-1].bias, 0.0)
+
+    def forward(self, desc):
+        return self.encoder(desc.transpose(1, 2))
+
+
+class MultiHeadedAttention(nn.Module):
+    """q/k/v 1x1 projections, 4 heads with channel c = d*4 + h, full or top-k softmax, merge."""
+
+    def __init__(self, num_heads, d_model):
+        super().__init__()
+        assert d_model % num_heads == 0
+        self.dim = d_model // num_heads
+        self.num_heads = num_heads
+        self.merge = nn.Conv1d(d_model, d_model, kernel_size=1)
+        self.proj = nn.ModuleList([deepcopy(self.merge) for _ in range(3)])
+
+    def forward(self, x, source, k):
+        b = x.size(0)
+        q, key, val = [f(t).view(b, self.dim, self.num_heads, -1)
+                       for f, t in zip(self.proj, (x, source, source))]
+        logits = torch.einsum('bdhn,bdhm->bhnm', q, key) / self.dim ** .5
+        if k is None:
+            prob = torch.softmax(logits, dim=-1)
+        else:
+            idx = logits.topk(k, dim=3).indices
+            prob = torch.zeros_like(logits).scatter(3, idx, torch.softmax(logits.gather(3, idx), dim=-1))
+        msg = torch.einsum('bhnm,bdhm->bdhn', prob, val)
+        return self.merge(msg.contiguous().view(b, self.dim * self.num_heads, -1))
+
+
+class AttentionalPropagation(nn.Module):
+    def __init__(self, feature_dim, num_heads):
+        super().__init__()
+        self.attn = MultiHeadedAttention(num_heads, feature_dim)
+        self.mlp = MLP([feature_dim * 2, feature_dim * 2, feature_dim])
+        nn.init.constant_(self.mlp[-1].bias, 0.0)
+
+    def forward(self, x, source, k):
+        return self.mlp(torch.cat([x, self.attn(x, source, k)], dim=1))
+
+
+class AttentionalGNN(nn.Module):
+    def __init__(self, feature_dim, layer_names):
+        super().__init__()
+        self.layers = nn.ModuleList([AttentionalPropagation(feature_dim, 4) for _ in layer_names])
+        self.names = layer_names
+
+    def forward(self, desc0, desc1, k_list, L):
+        sched = packing.layer_k_schedule(k_list, L)
+        for layer, name, k in zip(self.layers, self.names, sched):
+            s0, s1 = (desc1, desc0) if name == 'cross' else (desc0, desc1)
+            k = None if k == 0 else k
+            d0, d1 = layer(desc0, s0, k), layer(desc1, s1, k)
+            desc0, desc1 = desc0 + d0, desc1 + d1
+        return desc0, desc1
+
+
+def log_optimal_transport(scores, alpha, iters):
+    """Log-domain Sinkhorn with a dustbin row/column (torch path; mdgat.py:279-308)."""
+    b, m, n = scores.shape
+    Z = scores.new_empty(b, m + 1, n + 1)
+    Z[:, :m, :n] = scores
+    Z[:, m, :] = alpha
+    Z[:, :, n] = alpha
+    norm = -torch.log(scores.new_tensor(float(m + n)))
+    log_mu = torch.cat([norm.expand(m), norm + torch.log(scores.new_tensor(float(n)))[None]])[None].expand(b, -1)
+    log_nu = torch.cat([norm.expand(n), norm + torch.log(scores.new_tensor(float(m)))[None]])[None].expand(b, -1)
+    u, v = torch.zeros_like(log_mu), torch.zeros_like(log_nu)
+    for _ in range(iters):
+        u = log_mu - torch.logsumexp(Z + v.unsqueeze(1), dim=2)
+        v = log_nu - torch.logsumexp(Z + u.unsqueeze(2), dim=1)
+    return Z + u.unsqueeze(2) + v.unsqueeze(1) - norm
+
+
+def extract_matches_torch(Z, loss_method, mutual_check, threshold):
+    """Match extraction on a materialised Z (torch path; mdgat.py:442-483)."""
+    zero = Z.new_tensor(0)
+    if loss_method == 'superglue':
+        inner = Z[:, :-1, :-1]
+        max0, max1 = inner.max(2), inner.max(1)
+        i0, i1 = max0.indices, max1.indices
+        if mutual_check:
+            mut0 = torch.arange(i0.shape[1], device=Z.device)[None] == i1.gather(1, i0)
+            mut1 = torch.arange(i1.shape[1], device=Z.device)[None] == i0.gather(1, i1)
+            ms0 = torch.where(mut0, max0.values.exp(), zero)
+            ms1 = torch.where(mut1, ms0.gather(1, i1), zero)
+            v0 = mut0 & (ms0 > threshold)
+            v1 = mut1 & v0.gather(1, i1)
+        else:
+            v0, v1 = max0.values.exp() > threshold, max1.values.exp() > threshold
+            ms0 = torch.where(v0, max0.values.exp(), zero)
+            ms1 = torch.where(v1, max1.values.exp(), zero)
+    else:
+        max0, max1 = Z[:, :-1, :].max(2), Z[:, :, :-1].max(1)
+        i0, i1 = max0.indices, max1.indices
+        v0, v1 = i0 < Z.size(2) - 1, i1 < Z.size(1) - 1
+        k0, k1 = v0, v1
+        if mutual_check:
+            k0 = v0 & (torch.arange(i0.shape[1], device=Z.device)[None] == i1.gather(1, i0.clamp(max=Z.size(2) - 2)))
+            k1 = v1 & (torch.arange(i1.shape[1], device=Z.device)[None] == i0.gather(1, i1.clamp(max=Z.size(1) - 2)))
+        ms0 = torch.where(k0, max0.values.exp(), zero)
+        ms1 = torch.where(k1, max1.values.exp(), zero)
+    return (torch.where(v0, i0, i0.new_tensor(-1)), torch.where(v1, i1, i1.new_tensor(-1)), ms0, ms1)
+
+
+class MDGAT(nn.Module):
+    default_config = {
+        'descriptor_dim': 128,
+        'keypoint_encoder': [32, 64, 128],
+        'descritor_encoder': [64, 128],
+        'GNN_layers': ['self', 'cross'] * 9,
+        'sinkhorn_iterations': 100,
+        'match_threshold': 0.2,
+    }
+    # keys accepted for the ground-truth matches (SuperGlue upstream reads 'match0/1')
+    _gt_keys = ('gt_matches0', 'gt_matches1')
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = {**self.default_config, **config}
+        self.descriptor = config['descriptor']
+        if self.descriptor == 'FPFH':
+            self.kenc = KeypointEncoder(self.config['descriptor_dim'], self.config['keypoint_encoder'])
+            self.denc = DescriptorEncoder(self.config['descriptor_dim'], self.config['descritor_encoder'])
+        elif self.descriptor in _DESCRIPTORS_OUT_OF_SCOPE:
+            raise NotImplementedError(
+                "descriptor=%r is outside the accelerated hot path (needs raw clouds the shipped loader "
+                "no longer emits; only descriptor='FPFH' has pre-trained weights)" % self.descriptor)
+        else:
+            raise Exception('Invalid descriptor.')
+        if self.config['descriptor_dim'] != 128 or list(self.config['keypoint_encoder']) != [32, 64, 128] \
+                or list(self.config['descritor_encoder']) != [64, 128]:
+            raise NotImplementedError('the sm_100a kernels are built for the 128-dim / [32,64,128] / [64,128] architecture')
+        self.gnn = AttentionalGNN(self.config['descriptor_dim'], ['self', 'cross'] * self.config['L'])
+        self.final_proj = nn.Conv1d(self.config['descriptor_dim'], self.config['descriptor_dim'],
+                                    kernel_size=1, bias=True)
+        self.register_parameter('bin_score', torch.nn.Parameter(torch.tensor(1.)))
+        self.lr = config['lr']
+        self.loss_method = config['loss_method']
+        self.k = config['k']
+        self.mutual_check = config['mutual_check']
+        self.triplet_loss_gamma = config['triplet_loss_gamma']
+        self.train_step = config['train_step']
+        self._packed = None          # (key, blob)
+        self._workspace = None       # uint8 tensor
+        self._layer_k = None
+
+    # ------------------------------------------------------------------ packed-weight cache
+    def _weights_key(self):
+        key = []
+        for t in list(self.parameters()) + list(self.buffers()):
+            key.append((t.data_ptr(), t._version, t.dtype))
+        return tuple(key)
+
+    def packed_weights(self):
+        """float64 blob on the parameters' device, rebuilt only when a parameter changed
+        (test.py calls net.double() before every batch; that keeps storage and version)."""
+        key = self._weights_key()
+        if self._packed is None or self._packed[0] != key:
+            sd = {k: v for k, v in self.state_dict(keep_vars=True).items()}
+            with torch.no_grad():
+                blob = packing.pack_state_dict(sd, self.config['L'])
+            self._packed = (key, blob)
+        return self._packed[1]
+
+    # ------------------------------------------------------------------ forward
+    def _gt(self, data):
+        return data[self._gt_keys[0]], data[self._gt_keys[1]]
+
+    def forward(self, data):
+        kpts0, kpts1 = data['keypoints0'], data['keypoints1']
+        if kpts0.shape[1] == 0 or kpts1.shape[1] == 0:          # no keypoints (mdgat.py:374-382)
+            shape0, shape1 = kpts0.shape[:-1], kpts1.shape[:-1]
+            k0, k1 = kpts0.double(), kpts1.double()
+            return {
+                'matches0': k0.new_full(shape0, -1, dtype=torch.int)[0],
+                'matches1': k1.new_full(shape1, -1, dtype=torch.int)[0],
+                'matching_scores0': k0.new_zeros(shape0)[0],
+                'matching_scores1': k1.new_zeros(shape1)[0],
+                'skip_train': True,
+            }
+        if self.training:
+            return self._forward_torch(data)
+        return self._forward_cuda(data)
+
+    def _forward_cuda(self, data):
+        from .. import _capi                      # fails loudly if the library is not built
+        kpts0, kpts1 = data['keypoints0'], data['keypoints1']
+        if not kpts0.is_cuda:
+            raise RuntimeError('mdgat-matcher_b200 runs on CUDA tensors only (sm_100a kernels); got device %s. '
+                               'There is no CPU fallback.' % kpts0.device)
+        dev = kpts0.device
+        B, N, M = kpts0.shape[0], kpts0.shape[1], kpts1.shape[1]
+        L = self.config['L']
+        sched = packing.layer_k_schedule(self.k, L)
+        for k in sched:
+            if k > min(N, M):
+                raise RuntimeError('selected index k out of range')      # what torch.topk raises upstream
+
+        def prep(t, allow=(torch.float32, torch.float64)):
+            if t.dtype not in allow:
+                t = t.double()
+            return t.contiguous()
+
+        with torch.cuda.device(dev):
+            in_dtype = torch.float64
+            tens = [prep(data[k]) for k in ('keypoints0', 'keypoints1', 'descriptors0', 'descriptors1')]
+            if len({t.dtype for t in tens}) != 1:
+                tens = [t.double() for t in tens]
+            in_dtype = tens[0].dtype
+            sc = [prep(data['scores0']), prep(data['scores1'])]
+            if sc[0].dtype != sc[1].dtype:
+                sc = [t.double() for t in sc]
+            blob = self.packed_weights()
+            if blob.device != dev:
+                raise RuntimeError('module parameters live on %s but inputs on %s' % (blob.device, dev))
+
+            loss_mode = _capi.LOSS_NONE
+            gt0 = gt1 = None
+            have_gt = self._gt_keys[0] in data and self._gt_keys[1] in data
+            if self.loss_method in ('triplet_loss', 'gap_loss'):
+                gt0_t, gt1_t = self._gt(data)
+                # the reference rewrites the caller's tensors in place (mdgat.py:519-520, 554-555)
+                gt0_t[gt0_t == -1] = M
+                gt1_t[gt1_t == -1] = N
+                if self.loss_method == 'triplet_loss':
+                    if N != M:
+                        raise IndexError('triplet_loss needs N == M (mdgat.py:537)')
+                    loss_mode = _capi.LOSS_TRIPLET
+                    gt0 = gt0_t.to(torch.int16).contiguous()
+                    gt1 = gt1_t.to(torch.int16).contiguous()
+            elif self.loss_method == 'superglue' and have_gt:
+                gt0_t, gt1_t = self._gt(data)
+            write_Z = self.loss_method in ('gap_loss', 'superglue') or bool(self.config.get('return_assignment', False))
+
+            matches0 = torch.empty((B, N), dtype=torch.int64, device=dev)
+            matches1 = torch.empty((B, M), dtype=torch.int64, device=dev)
+            ms0 = torch.empty((B, N), dtype=torch.float64, device=dev)
+            ms1 = torch.empty((B, M), dtype=torch.float64, device=dev)
+            loss = torch.zeros((), dtype=torch.float64, device=dev)
+            nvalid = torch.zeros((), dtype=torch.int32, device=dev)
+            Z = torch.empty((B, N + 1, M + 1), dtype=torch.float64, device=dev) if write_Z else None
+
+            karr = (ctypes.c_int * len(sched))(*sched)
+            cfg = _capi.ForwardCfg(
+                B=B, N=N, M=M, L=L, sinkhorn_iters=int(self.config['sinkhorn_iterations']), layer_k=karr,
+                match_mode=_capi.MATCH_THRESHOLD if self.loss_method == 'superglue' else _capi.MATCH_DUSTBIN,
+                mutual_check=int(bool(self.mutual_check)), match_threshold=float(self.config['match_threshold']),
+                loss_mode=loss_mode, triplet_gamma=float(self.triplet_loss_gamma),
+                in_dtype=_capi.F64 if in_dtype == torch.float64 else _capi.F32,
+                score_dtype=_capi.F64 if sc[0].dtype == torch.float64 else _capi.F32,
+                write_Z=int(write_Z))
+            need = _capi.lib.mdgat_forward_workspace_bytes(ctypes.byref(cfg))
+            ws = self._workspace
+            if ws is None or ws.device != dev or ws.numel() < need:
+                ws = torch.empty(need, dtype=torch.uint8, device=dev)
+                self._workspace = ws
+            fin = _capi.ForwardIn(tens[0].data_ptr(), tens[1].data_ptr(), tens[2].data_ptr(), tens[3].data_ptr(),
+                                  sc[0].data_ptr(), sc[1].data_ptr(),
+                                  gt0.data_ptr() if gt0 is not None else None,
+                                  gt1.data_ptr() if gt1 is not None else None)
+            fout = _capi.ForwardOut(matches0.data_ptr(), matches1.data_ptr(), ms0.data_ptr(), ms1.data_ptr(),
+                                    loss.data_ptr(), nvalid.data_ptr(), Z.data_ptr() if Z is not None else None)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _capi.check(_capi.lib.mdgat_forward(ctypes.byref(cfg), blob.data_ptr(), ctypes.byref(fin),
+                                                ctypes.byref(fout), ws.data_ptr(), ws.numel(), stream))
+            if self.loss_method == 'gap_loss':
+                loss = losses.gap_loss(Z, gt0_t.long(), gt1_t.long(), self.triplet_loss_gamma)
+            elif self.loss_method == 'superglue':
+                loss = losses.superglue_loss(Z, gt0_t, gt1_t) if have_gt else None
+            if self.config.get('strict_degenerate_dtypes', False) and self.loss_method != 'superglue' \
+                    and int(nvalid.item()) == 0:
+                # the reference returns int64 zeros when nothing is valid (mdgat.py:465-467)
+                ms0, ms1 = torch.zeros_like(matches0), torch.zeros_like(matches1)
+        out = {'matches0': matches0, 'matches1': matches1, 'matching_scores0': ms0, 'matching_scores1': ms1,
+               'loss': loss}
+        if self.config.get('return_assignment', False):
+            out['assignment'] = Z
+        return out
+
+    def _forward_torch(self, data):
+        """Differentiable path for train.py (batch-statistics BatchNorm, autograd)."""
+        kpts0, kpts1 = data['keypoints0'].double(), data['keypoints1'].double()
+        d0, d1 = data['descriptors0'].double(), data['descriptors1'].double()
+        desc0 = self.denc(d0) + self.kenc(kpts0, data['scores0'])
+        desc1 = self.denc(d1) + self.kenc(kpts1, data['scores1'])
+        desc0, desc1 = self.gnn(desc0, desc1, self.k, self.config['L'])
+        md0, md1 = self.final_proj(desc0), self.final_proj(desc1)
+        scores = torch.einsum('bdn,bdm->bnm', md0, md1) / self.config['descriptor_dim'] ** .5
+        Z = log_optimal_transport(scores, self.bin_score, self.config['sinkhorn_iterations'])
+        m0, m1, ms0, ms1 = extract_matches_torch(Z, self.loss_method, self.mutual_check, self.config['match_threshold'])
+        n, m = kpts0.shape[1], kpts1.shape[1]
+        loss = None
+        if self.loss_method in ('triplet_loss', 'gap_loss'):
+            gt0, gt1 = self._gt(data)
+            gt0[gt0 == -1] = m
+            gt1[gt1 == -1] = n
+            fn = losses.triplet_loss if self.loss_method == 'triplet_loss' else losses.gap_loss
+            loss = fn(Z, gt0.long(), gt1.long(), self.triplet_loss_gamma)
+        elif self.loss_method == 'superglue':
+            gt0, gt1 = self._gt(data)
+            loss = losses.superglue_loss(Z, gt0, gt1)
+        return {'matches0': m0, 'matches1': m1, 'matching_scores0': ms0, 'matching_scores1': ms1, 'loss': loss}

@@ -1,0 +1,180 @@
+"""Torch-tensor front ends of the individual C-ABI operators (include/mdgat_b200.h).
+
+These are the same kernels mdgat_forward() launches; they exist so that each block of the
+reference can be checked on its own. Inputs must be CUDA tensors.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _capi
+from ._capi import LDX, LDH_QK, LDH_V
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _need_cuda(t):
+    if not t.is_cuda:
+        raise RuntimeError('mdgat-matcher_b200 operators need CUDA tensors (no CPU fallback)')
+
+
+def linear(x, w, bias=None, relu=False, residual=None, x2=None, scale=1.0):
+    """y = act(scale * [x | x2] w^T + bias) + residual; x (R,K0), w (Nout,K) float64."""
+    _need_cuda(x)
+    x = x.double().contiguous()
+    w = w.double().contiguous()
+    R, K0 = x.shape
+    K1 = 0
+    if x2 is not None:
+        x2 = x2.double().contiguous()
+        K1 = x2.shape[1]
+    nout = w.shape[0]
+    y = torch.empty((R, nout), dtype=torch.float64, device=x.device)
+    b = bias.double().contiguous() if bias is not None else None
+    r = residual.double().contiguous() if residual is not None else None
+    with torch.cuda.device(x.device):
+        _capi.check(_capi.lib.mdgat_linear_f64(
+            x.data_ptr(), x.stride(0), K0, x2.data_ptr() if x2 is not None else None,
+            x2.stride(0) if x2 is not None else 0, K1, w.data_ptr(), w.stride(0),
+            b.data_ptr() if b is not None else None, r.data_ptr() if r is not None else None,
+            r.stride(0) if r is not None else 0, y.data_ptr(), y.stride(0), R, nout, float(scale), int(relu),
+            _stream(x.device)))
+    return y
+
+
+def gemm_nt(x, w, scale=1.0):
+    """Batched y[z] = scale * x[z] w[z]^T; x (Z,R,K), w (Z,Nout,K) float64."""
+    _need_cuda(x)
+    x = x.double().contiguous()
+    w = w.double().contiguous()
+    Z, R, K = x.shape
+    nout = w.shape[1]
+    y = torch.empty((Z, R, nout), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        _capi.check(_capi.lib.mdgat_gemm_nt_f64(x.data_ptr(), K, R * K, w.data_ptr(), K, nout * K,
+                                                y.data_ptr(), nout, R * nout, R, nout, K, Z, float(scale),
+                                                _stream(x.device)))
+    return y
+
+
+def to_head_major(t, ld):
+    """(B, 128, N) reference-layout q/k/v (channel c = d*4 + h, mdgat.py:227) -> (B,4,N,ld) padded."""
+    b, c, n = t.shape
+    x = t.double().reshape(b, 32, 4, n).permute(0, 2, 3, 1)          # (B, h, N, d)
+    out = torch.zeros((b, 4, n, ld), dtype=torch.float64, device=t.device)
+    out[..., :32] = x
+    return out.contiguous()
+
+
+def attention(q, k, v, topk=None):
+    """q (B,128,N), k/v (B,128,M) in the reference's channel layout. Returns the message
+    (B,128,N) in the reference layout (what attention()/dynamic_attention() return after
+    .view(B, 128, N), mdgat.py:229-237 before the merge conv)."""
+    _need_cuda(q)
+    B, _, N = q.shape
+    M = k.shape[2]
+    qh, kh, vh = to_head_major(q, LDH_QK), to_head_major(k, LDH_QK), to_head_major(v, LDH_V)
+    out = torch.empty((B * N, LDX), dtype=torch.float64, device=q.device)
+    kk = 0 if topk is None else int(topk)
+    logits = torch.empty((B, 4, N, M), dtype=torch.float64, device=q.device) if kk > 0 else None
+    with torch.cuda.device(q.device):
+        _capi.check(_capi.lib.mdgat_attention_f64(qh.data_ptr(), kh.data_ptr(), vh.data_ptr(), out.data_ptr(), LDX,
+                                                  B, N, M, kk, logits.data_ptr() if logits is not None else None,
+                                                  _stream(q.device)))
+    msg = out[:, :128].reshape(B, N, 4, 32)                        # (B, N, h, d)
+    return msg.permute(0, 3, 2, 1).reshape(B, 128, N).contiguous()  # channel c = d*4 + h
+
+
+def sinkhorn(scores, bin_score, iters):
+    """scores (B,N,M) -> Z (B,N+1,M+1) = log_optimal_transport(scores, bin_score, iters)."""
+    _need_cuda(scores)
+    B, N, M = scores.shape
+    dev = scores.device
+    C = torch.empty((B, N + 1, M + 1), dtype=torch.float64, device=dev)
+    C[:, :N, :M] = scores.double()
+    u = torch.empty((B, N + 1), dtype=torch.float64, device=dev)
+    v = torch.empty((B, M + 1), dtype=torch.float64, device=dev)
+    alpha = torch.as_tensor(bin_score, dtype=torch.float64, device=dev).reshape(1).contiguous()
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib.mdgat_sinkhorn_f64(C.data_ptr(), alpha.data_ptr(), u.data_ptr(), v.data_ptr(),
+                                                 B, N, M, int(iters), _stream(dev)))
+    return C, u, v
+
+
+def match_extract(C, u, v, loss_method='triplet_loss', mutual_check=False, match_threshold=0.2,
+                  gt0=None, gt1=None, gamma=0.5, want_Z=False):
+    _need_cuda(C)
+    dev = C.device
+    B, N, M = C.shape[0], C.shape[1] - 1, C.shape[2] - 1
+    m0 = torch.empty((B, N), dtype=torch.int64, device=dev)
+    m1 = torch.empty((B, M), dtype=torch.int64, device=dev)
+    s0 = torch.empty((B, N), dtype=torch.float64, device=dev)
+    s1 = torch.empty((B, M), dtype=torch.float64, device=dev)
+    loss = torch.zeros((), dtype=torch.float64, device=dev)
+    nvalid = torch.zeros((), dtype=torch.int32, device=dev)
+    Z = torch.empty_like(C) if want_Z else None
+    scratch = torch.empty(_capi.lib.mdgat_match_scratch_doubles(B, N, M), dtype=torch.float64, device=dev)
+    loss_mode = _capi.LOSS_TRIPLET if (loss_method == 'triplet_loss' and gt0 is not None) else _capi.LOSS_NONE
+    g0 = gt0.to(torch.int16).contiguous() if gt0 is not None else None
+    g1 = gt1.to(torch.int16).contiguous() if gt1 is not None else None
+    fout = _capi.ForwardOut(m0.data_ptr(), m1.data_ptr(), s0.data_ptr(), s1.data_ptr(), loss.data_ptr(),
+                            nvalid.data_ptr(), Z.data_ptr() if Z is not None else None)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib.mdgat_match_extract(
+            C.data_ptr(), u.data_ptr(), v.data_ptr(), B, N, M,
+            _capi.MATCH_THRESHOLD if loss_method == 'superglue' else _capi.MATCH_DUSTBIN,
+            int(bool(mutual_check)), float(match_threshold), loss_mode, float(gamma),
+            g0.data_ptr() if g0 is not None else None, g1.data_ptr() if g1 is not None else None,
+            ctypes.byref(fout), scratch.data_ptr(), _stream(dev)))
+    return {'matches0': m0, 'matches1': m1, 'matching_scores0': s0, 'matching_scores1': s1,
+            'loss': loss, 'nvalid0': nvalid, 'Z': Z}
+
+
+def knn(x, src, k):
+    """x (B,3,n), src (B,3,m) -> (B,n,k) int64 indices of the k nearest sources (mdgat.py:8-15)."""
+    _need_cuda(x)
+    x = x.double().contiguous()
+    src = src.double().contiguous()
+    B, _, n = x.shape
+    m = src.shape[2]
+    idx = torch.empty((B, n, k), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        _capi.check(_capi.lib.mdgat_knn(x.data_ptr(), src.data_ptr(), idx.data_ptr(), B, n, m, int(k), _stream(x.device)))
+    return idx
+
+
+def get_graph_feature(x, src, k):
+    """One-hot kNN adjacency (B,n,m) int64 (mdgat.py:17-32)."""
+    idx = knn(x, src, k)
+    adj = torch.zeros((x.shape[0], x.shape[2], src.shape[2]), dtype=torch.int64, device=x.device)
+    return adj.scatter_(2, idx, 1)
+
+
+def encode(blob, data):
+    """denc(desc) + kenc(kpts, scores) for both sides -> (desc0 (B,128,N), desc1 (B,128,M))."""
+    k0 = data['keypoints0']
+    _need_cuda(k0)
+    dev = k0.device
+    B, N, M = k0.shape[0], k0.shape[1], data['keypoints1'].shape[1]
+    t = [data[k].double().contiguous() for k in ('keypoints0', 'keypoints1', 'descriptors0', 'descriptors1',
+                                                 'scores0', 'scores1')]
+    R = B * (N + M)
+    X = torch.empty((R, LDX), dtype=torch.float64, device=dev)
+    tmp = torch.empty(_capi.lib.mdgat_encode_scratch_doubles(R), dtype=torch.float64, device=dev)
+    fin = _capi.ForwardIn(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(),
+                          t[5].data_ptr(), None, None)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib.mdgat_encode(ctypes.byref(fin), B, N, M, _capi.F64, _capi.F64, blob.data_ptr(),
+                                           X.data_ptr(), tmp.data_ptr(), _stream(dev)))
+    d0 = X[:B * N, :128].reshape(B, N, 128).transpose(1, 2).contiguous()
+    d1 = X[B * N:, :128].reshape(B, M, 128).transpose(1, 2).contiguous()
+    return d0, d1
+
+
+def measure_fp64_peak():
+    a, b = ctypes.c_double(), ctypes.c_double()
+    _capi.check(_capi.lib.mdgat_measure_fp64_peak(ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value

@@ -1,0 +1,98 @@
+"""Weight packer: reference state-dict layout -> the float64 blob of include/mdgat_b200.h.
+
+* eval-mode BatchNorm1d is folded into the preceding 1x1 conv (MLP(), mdgat.py:34-46):
+  W' = W * g / sqrt(var + 1e-5), b' = (b - mean) * g / sqrt(var + 1e-5) + beta;
+* the three projections proj.0/1/2 are stacked into one [384][128] matrix;
+* MultiHeadedAttention views channels as (dim=32, heads=4), i.e. channel c = d*4 + h
+  (mdgat.py:227); q/k/v output rows and merge input columns are permuted once to the
+  head-major order c' = h*32 + d the kernels use;
+* the 33-wide descriptor conv is zero-padded to 36 input columns (DMMA K granularity 4).
+
+All arithmetic is done in float64 on whatever the parameters currently hold, so calling the
+module as test.py does (fp32 module -> load_state_dict -> .double()) yields fp64(fp32(ckpt)).
+"""
+import torch
+
+BN_EPS = 1e-5
+KENC_DIMS = (4, 32, 64, 128, 128)
+DENC_DIMS = (36, 64, 128, 128)
+LAYER_DOUBLES = 384 * 128 + 384 + 128 * 128 + 128 + 256 * 256 + 256 + 128 * 256 + 128
+
+
+def blob_doubles(L):
+    n = sum(KENC_DIMS[i + 1] * KENC_DIMS[i] + KENC_DIMS[i + 1] for i in range(4))
+    n += sum(DENC_DIMS[i + 1] * DENC_DIMS[i] + DENC_DIMS[i + 1] for i in range(3))
+    n += 2 * L * LAYER_DOUBLES + 128 * 128 + 128 + 4
+    return n
+
+
+def _head_major_perm(device):
+    # position c' = h*32 + d takes reference channel c = d*4 + h
+    cp = torch.arange(128, device=device)
+    return (cp % 32) * 4 + cp // 32
+
+
+def _conv(sd, name):
+    w = sd[name + '.weight'].detach().double()
+    return w.reshape(w.shape[0], w.shape[1]), sd[name + '.bias'].detach().double()
+
+
+def _fold_bn(w, b, sd, name):
+    g = sd[name + '.weight'].detach().double()
+    beta = sd[name + '.bias'].detach().double()
+    mean = sd[name + '.running_mean'].detach().double()
+    var = sd[name + '.running_var'].detach().double()
+    s = g / torch.sqrt(var + BN_EPS)
+    return w * s[:, None], (b - mean) * s + beta
+
+
+def pack_state_dict(sd, L):
+    """sd: mapping name -> tensor (no 'module.' prefix). Returns a contiguous 1-D float64 tensor."""
+    dev = sd['bin_score'].device
+    parts = []
+
+    def mlp(prefix, n_conv, pad_in=None):
+        for i in range(n_conv):
+            w, b = _conv(sd, '%s.%d' % (prefix, 3 * i))
+            if i < n_conv - 1:
+                w, b = _fold_bn(w, b, sd, '%s.%d' % (prefix, 3 * i + 1))
+            if i == 0 and pad_in is not None and w.shape[1] < pad_in:
+                w = torch.cat([w, w.new_zeros(w.shape[0], pad_in - w.shape[1])], dim=1)
+            parts.extend([w.reshape(-1), b])
+
+    mlp('kenc.encoder', 4)
+    mlp('denc.encoder', 3, pad_in=36)
+    perm = _head_major_perm(dev)
+    for l in range(2 * L):
+        p = 'gnn.layers.%d.' % l
+        ws, bs = [], []
+        for j in range(3):
+            w, b = _conv(sd, p + 'attn.proj.%d' % j)
+            ws.append(w[perm])
+            bs.append(b[perm])
+        parts.extend([torch.cat(ws, 0).reshape(-1), torch.cat(bs, 0)])
+        w, b = _conv(sd, p + 'attn.merge')
+        parts.extend([w[:, perm].reshape(-1), b])
+        w, b = _conv(sd, p + 'mlp.0')
+        w, b = _fold_bn(w, b, sd, p + 'mlp.1')
+        parts.extend([w.reshape(-1), b])
+        w, b = _conv(sd, p + 'mlp.3')
+        parts.extend([w.reshape(-1), b])
+    w, b = _conv(sd, 'final_proj')
+    parts.extend([w.reshape(-1), b])
+    bin_score = sd['bin_score'].detach().double().reshape(1)
+    parts.extend([bin_score, bin_score.new_zeros(3)])
+    blob = torch.cat([x.contiguous().reshape(-1) for x in parts]).contiguous()
+    assert blob.numel() == blob_doubles(L), (blob.numel(), blob_doubles(L))
+    return blob
+
+
+def layer_k_schedule(k_list, L):
+    """Per-layer top-k of AttentionalGNN.forward (mdgat.py:268-272); 0 means full attention."""
+    out = []
+    for i in range(2 * L):
+        k = None
+        if i > 2 * L - 1 - len(k_list):
+            k = k_list[i - 2 * L + len(k_list)]
+        out.append(0 if k is None else int(k))
+    return out

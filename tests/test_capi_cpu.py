@@ -1,0 +1,132 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol that
+include/mdgat_b200.h declares; the weight packer and the k schedule; the drop-in module keeps
+the reference's state-dict layout. No compute calls (no GPU here)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from mdgat_matcher_b200 import _capi
+    hdr = open(os.path.join(ROOT, 'include', 'mdgat_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(mdgat_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(_capi.EXPORTS) == declared
+    assert _capi.lib.mdgat_abi_version() == 1
+
+
+def test_error_text_without_gpu():
+    from mdgat_matcher_b200 import _capi
+    rc = _capi.lib.mdgat_knn(None, None, None, 1, 4, 4, 9, None)          # k > m is rejected before any CUDA call
+    assert rc == -1 and b'out of range' in _capi.lib.mdgat_last_error()
+
+
+def test_blob_size_and_k_schedule():
+    from mdgat_matcher_b200 import _capi, packing, synth
+    for L in (1, 4, 9):
+        assert packing.blob_doubles(L) == _capi.lib.mdgat_weight_blob_doubles(L)
+        blob = packing.pack_state_dict(synth.seeded_state_dict(L, 1), L)
+        assert blob.dtype == torch.float64 and blob.numel() == packing.blob_doubles(L)
+    k = [128, None, 128, None, 64, None, 64, None]
+    assert packing.layer_k_schedule(k, 9) == [0] * 10 + [128, 0, 128, 0, 64, 0, 64, 0]
+    assert packing.layer_k_schedule(k, 4) == [128, 0, 128, 0, 64, 0, 64, 0]
+    assert packing.layer_k_schedule([], 9) == [0] * 18
+    from oracle import mdgat_oracle as O
+    for L in (4, 9):
+        assert [O.layer_topk(i, k, L) or 0 for i in range(2 * L)] == packing.layer_k_schedule(k, L)
+
+
+def test_packed_blob_reproduces_reference_layers_on_cpu():
+    """Folded-BN + head permutation: emulate one GNN layer from the blob with numpy and compare
+    with the oracle's unfused layer."""
+    from mdgat_matcher_b200 import packing, synth
+    from oracle import mdgat_oracle as O
+    L = 1
+    sd_t = synth.seeded_state_dict(L, 3)
+    sd = O.state_dict_to_numpy(sd_t)
+    blob = packing.pack_state_dict(sd_t, L).numpy()
+    off = sum(packing.KENC_DIMS[i + 1] * packing.KENC_DIMS[i] + packing.KENC_DIMS[i + 1] for i in range(4))
+    off += sum(packing.DENC_DIMS[i + 1] * packing.DENC_DIMS[i] + packing.DENC_DIMS[i + 1] for i in range(3))
+
+    def take(n, shape=None):
+        nonlocal off
+        a = blob[off:off + n]
+        off += n
+        return a.reshape(shape) if shape else a
+    wqkv, bqkv = take(384 * 128, (384, 128)), take(384)
+    wm, bm = take(128 * 128, (128, 128)), take(128)
+    w1, b1 = take(256 * 256, (256, 256)), take(256)
+    w2, b2 = take(128 * 256, (128, 256)), take(128)
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(1, 128, 40)); src = rng.normal(size=(1, 128, 50))
+    want, _ = O.attentional_propagation(sd, 'gnn.layers.0', x, src, None)
+    xr, sr = x[0].T, src[0].T                                  # point-major rows
+    q = xr @ wqkv[:128].T + bqkv[:128]; k = sr @ wqkv[128:256].T + bqkv[128:256]; v = sr @ wqkv[256:].T + bqkv[256:]
+    msg = np.zeros((40, 128))
+    for h in range(4):
+        s = q[:, h * 32:(h + 1) * 32] @ k[:, h * 32:(h + 1) * 32].T / np.sqrt(32)
+        p = np.exp(s - s.max(1, keepdims=True)); p /= p.sum(1, keepdims=True)
+        msg[:, h * 32:(h + 1) * 32] = p @ v[:, h * 32:(h + 1) * 32]
+    mg = msg @ wm.T + bm
+    hd = np.maximum(np.concatenate([xr, mg], 1) @ w1.T + b1, 0)
+    delta = hd @ w2.T + b2
+    assert np.abs(delta.T - want[0]).max() < 1e-11
+
+
+def test_dropin_module_state_dict_layout_and_checkpoint():
+    from mdgat_matcher_b200.models.mdgat import MDGAT
+    from mdgat_matcher_b200.models.superglue import SuperGlue
+    from mdgat_matcher_b200 import synth
+    from conftest import case_cfg
+    cfg = case_cfg({'L': 9, 'T': 100})
+    net = MDGAT(cfg)
+    keys = set(net.state_dict().keys())
+    assert len(keys) == 348 and keys == set(synth.seeded_state_dict(9).keys())
+    for k, v in synth.seeded_state_dict(9).items():
+        assert tuple(net.state_dict()[k].shape) == tuple(v.shape), k
+    from oracle.build_ref import load_checkpoint_state_dict
+    sd = load_checkpoint_state_dict()
+    if sd is not None:
+        wrapped = torch.nn.DataParallel(net)                 # test.py:158-159 loads through DataParallel
+        wrapped.load_state_dict({'module.' + k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+        SuperGlue(cfg).load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    with pytest.raises(KeyError):
+        MDGAT({k: v for k, v in cfg.items() if k != 'L'})
+    with pytest.raises(Exception, match='Invalid descriptor'):
+        MDGAT({**cfg, 'descriptor': 'nope'})
+
+
+def test_eval_forward_refuses_cpu_tensors_and_train_path_matches_oracle():
+    from mdgat_matcher_b200.models.mdgat import MDGAT
+    from mdgat_matcher_b200 import synth
+    from oracle import mdgat_oracle as O
+    from conftest import case_cfg
+    cfg = case_cfg({'L': 2, 'T': 10, 'k': [16, None]})
+    sd = synth.seeded_state_dict(2, 5)
+    net = MDGAT(cfg)
+    net.load_state_dict(sd)
+    net.double().eval()
+    data = synth.make_batch(2, 2, 48)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        net({k: v.clone() for k, v in data.items()})
+    with torch.no_grad():
+        out = net._forward_torch({k: v.clone() for k, v in data.items()})      # differentiable path, eval BN
+    want = O.forward(O.state_dict_to_numpy(sd), data, cfg)
+    assert np.array_equal(out['matches0'].numpy(), want['matches0'])
+    assert np.abs(out['matching_scores0'].numpy() - want['matching_scores0']).max() < 1e-9
+    assert abs(float(out['loss']) - float(want['loss'])) < 1e-9
+    # train mode is differentiable end to end
+    net.train()
+    out = net({k: v.clone() for k, v in data.items()})
+    out['loss'].backward()
+    assert net.final_proj.weight.grad is not None and torch.isfinite(net.final_proj.weight.grad).all()

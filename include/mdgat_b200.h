@@ -133,9 +133,13 @@ int mdgat_attention_f64(const double* d_Q, const double* d_K, const double* d_V,
 /* log_optimal_transport (mdgat.py:279-308) on couplings already holding scores in [:N,:M]:
  * fills the dustbin row/column with bin_score (read from d_bin_score), runs `iters`
  * Sinkhorn iterations; leaves u (B,N+1), v (B,M+1) such that
- * Z = couplings + u + v - norm. fp64 throughout. */
+ * Z = couplings + u + v - norm. fp64 throughout.
+ * d_scratch != NULL (mdgat_sinkhorn_scratch_doubles): fused path, one launch, one 8-CTA
+ * cluster per pair with the kernel matrix in distributed shared memory (what mdgat_forward
+ * uses). d_scratch == NULL: one kernel per half-iteration reading the couplings from L2. */
+size_t mdgat_sinkhorn_scratch_doubles(int B, int N, int M);
 int mdgat_sinkhorn_f64(double* d_couplings, const double* d_bin_score, double* d_u, double* d_v,
-                       int B, int N, int M, int iters, void* stream);
+                       int B, int N, int M, int iters, double* d_scratch, void* stream);
 
 /* Match extraction + optional triplet loss from (couplings, u, v) (mdgat.py:442-483,512-546). */
 int mdgat_match_extract(const double* d_couplings, const double* d_u, const double* d_v,
@@ -151,6 +155,8 @@ int mdgat_knn(const double* d_x, const double* d_src, int64_t* d_idx, int B, int
 /* Measured fp64 tensor-pipe peak of this device (DMMA.8x8x4 issue loop), TFLOP/s.
  * Synchronises. Used as the roofline denominator of the fp64 kernels. */
 int mdgat_measure_fp64_peak(double* tflops_dmma, double* tflops_dfma);
+/* Same, with DMMA and DFMA issued together (1 DMMA : 2 DFMA per warp): the rates each reaches in the mix. */
+int mdgat_measure_fp64_mixed(double* tflops_dmma, double* tflops_dfma);
 
 /* ---- instrumentation (no reference counterpart; the reference has no tracing) ----
  * mdgat_launch_count: kernels launched by this library since load.

@@ -55,11 +55,13 @@ def _load():
         'mdgat_encode_scratch_doubles': (sz, [i]),
         'mdgat_encode': (i, [C.POINTER(ForwardIn), i, i, i, i, i, vp, vp, vp, vp]),
         'mdgat_attention_f64': (i, [vp, vp, vp, vp, i, i, i, i, i, vp, vp]),
-        'mdgat_sinkhorn_f64': (i, [vp, vp, vp, vp, i, i, i, i, vp]),
+        'mdgat_sinkhorn_scratch_doubles': (sz, [i, i, i]),
+        'mdgat_sinkhorn_f64': (i, [vp, vp, vp, vp, i, i, i, i, vp, vp]),
         'mdgat_match_scratch_doubles': (sz, [i, i, i]),
         'mdgat_match_extract': (i, [vp, vp, vp, i, i, i, i, i, d, i, d, vp, vp, C.POINTER(ForwardOut), vp, vp]),
         'mdgat_knn': (i, [vp, vp, vp, i, i, i, i, vp]),
         'mdgat_measure_fp64_peak': (i, [C.POINTER(d), C.POINTER(d)]),
+        'mdgat_measure_fp64_mixed': (i, [C.POINTER(d), C.POINTER(d)]),
         'mdgat_launch_count': (ll, []),
         'mdgat_profile_enable': (i, [i]),
         'mdgat_profile_collect': (i, [C.POINTER(d), C.POINTER(ll), C.POINTER(ll), i]),

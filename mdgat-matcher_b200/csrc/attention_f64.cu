@@ -17,14 +17,16 @@
 namespace mdgat {
 
 constexpr int A_BM = 64, A_BN = 64, A_THREADS = 128, A_STAGES = 2;
-constexpr size_t A_SMEM = (size_t)A_STAGES * A_BN * (LDH_QK + LDH_V) * sizeof(double);
+constexpr size_t A_SMEM = ((size_t)A_STAGES * A_BN * (LDH_QK + LDH_V) + 64) * sizeof(double);
 
-__global__ void __launch_bounds__(A_THREADS, 2)
+__global__ void __launch_bounds__(A_THREADS, 3)
 attn_full_kernel(const double* __restrict__ Q, const double* __restrict__ K, const double* __restrict__ V,
                  double* __restrict__ Out, int ldo, int N, int M, double scale) {
     extern __shared__ __align__(16) double smem[];
     double* Ks = smem;                                   // [stage][A_BN][LDH_QK]
     double* Vs = smem + A_STAGES * A_BN * LDH_QK;        // [stage][A_BN][LDH_V]
+    double* etab = Vs + A_STAGES * A_BN * LDH_V;         // [64] 2^(j/64)
+    exp_table_to_shared(etab);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h = blockIdx.y, b = blockIdx.z;
@@ -118,13 +120,13 @@ attn_full_kernel(const double* __restrict__ Q, const double* __restrict__ K, con
             mx = fmax(mx, shfl_xor_d(mx, 1));
             mx = fmax(mx, shfl_xor_d(mx, 2));
             const double m_new = fmax(m_run[mt], mx);
-            const double alpha = exp((m_run[mt] - m_new) * scale);
+            const double alpha = exp_fast_neg((m_run[mt] - m_new) * scale, etab);
             m_run[mt] = m_new;
             double rs = 0.0;
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
-                s[mt][nt][0] = exp((s[mt][nt][0] - m_new) * scale);
-                s[mt][nt][1] = exp((s[mt][nt][1] - m_new) * scale);
+                s[mt][nt][0] = exp_fast_neg((s[mt][nt][0] - m_new) * scale, etab);
+                s[mt][nt][1] = exp_fast_neg((s[mt][nt][1] - m_new) * scale, etab);
                 rs += s[mt][nt][0] + s[mt][nt][1];
             }
             l_run[mt] = l_run[mt] * alpha + rs;            // per-lane partial; quad-reduced at the end
@@ -186,12 +188,22 @@ DEVINL unsigned long long order_key(double x) {
     return (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
 }
 
+constexpr int TK_WARPS = 8;
+
+// VPT = values per lane (M <= 32*VPT). Dynamic shared memory: per warp topk doubles (kept
+// logits, then probabilities) + topk ints (their column indices).
 template <int VPT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * TK_WARPS)
 topk_softmax_pv_kernel(const double* __restrict__ S, const double* __restrict__ V, double* __restrict__ Out,
                        int ldo, int N, int M, int topk, long long total_rows) {
+    extern __shared__ __align__(16) unsigned char tk_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long g = (long long)blockIdx.x * 8 + warp;          // row in (B,4,N) order
+    double* kept = reinterpret_cast<double*>(tk_smem) + (size_t)warp * topk;
+    int* kcol = reinterpret_cast<int*>(tk_smem + (size_t)TK_WARPS * topk * sizeof(double) + 64 * sizeof(double)) + (size_t)warp * topk;
+    double* etab = reinterpret_cast<double*>(tk_smem) + (size_t)TK_WARPS * topk;
+    exp_table_to_shared(etab);
+    __syncthreads();
+    const long long g = (long long)blockIdx.x * TK_WARPS + warp;          // row in (B,4,N) order
     if (g >= total_rows) return;
     const long long bh = g / N;
     const int i = (int)(g - bh * N);
@@ -200,85 +212,116 @@ topk_softmax_pv_kernel(const double* __restrict__ S, const double* __restrict__ 
     const double* Vbh = V + bh * (long long)M * LDH_V;
 
     double s[VPT];
-    double mx = -INFINITY;
+    unsigned long long key[VPT];
+    double mx = -INFINITY, mn = INFINITY;
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
         const int j = lane + 32 * v;
-        s[v] = j < M ? srow[j] : -INFINITY;
-        mx = fmax(mx, s[v]);
+        const bool ok = j < M;
+        s[v] = ok ? srow[j] : -INFINITY;
+        key[v] = ok ? order_key(s[v]) : 0ull;            // padding sorts below every real value
+        if (ok) { mx = fmax(mx, s[v]); mn = fmin(mn, s[v]); }
     }
     mx = warp_max_d(mx);
-    // entries past M get key 0 (below every real value, even -inf)
-    auto keyof = [&](int v) -> unsigned long long { return (lane + 32 * v) < M ? order_key(s[v]) : 0ull; };
+    mn = -warp_max_d(-mn);
 
-    unsigned long long prefix = 0ull;
+    // bits above the highest bit in which max and min differ are common to every key: skip them
+    const unsigned long long kmax = order_key(mx), kmin = order_key(mn);
+    const unsigned long long diff = kmax ^ kmin;
+    unsigned long long prefix = kmax;
     bool exact = false;
-    for (int bit = 63; bit >= 0; --bit) {
-        const unsigned long long cand = prefix | (1ull << bit);
-        int c = 0;
+    if (topk >= M) {                                     // k == M: keep everything
+        prefix = kmin; exact = true;
+    } else if (diff != 0ull) {
+        const int top = 63 - __clzll((long long)diff);
+        prefix = (top == 63) ? 0ull : (kmax >> (top + 1)) << (top + 1);
+        for (int bit = top; bit >= 0; --bit) {
+            const unsigned long long cand = prefix | (1ull << bit);
+            int c = 0;
 #pragma unroll
-        for (int v = 0; v < VPT; ++v) c += (keyof(v) >= cand) ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (c >= topk) {
-            prefix = cand;
-            if (c == topk) { exact = true; break; }
+            for (int v = 0; v < VPT; ++v) c += (key[v] >= cand) ? 1 : 0;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c >= topk) {
+                prefix = cand;
+                if (c == topk) { exact = true; break; }
+            }
         }
     }
-    // selection flags (bit v of sel)
-    unsigned long long sel = 0ull;
-    if (exact) {
+    // prefix is now either a threshold keeping exactly k entries (exact) or the k-th largest key
+    int gt = 0;
+    if (!exact) {
 #pragma unroll
-        for (int v = 0; v < VPT; ++v) sel |= (unsigned long long)(keyof(v) >= prefix) << v;
-    } else {
-        // ties at the k-th value: keep everything above it plus the lowest-index equals
-        int gt = 0;
-#pragma unroll
-        for (int v = 0; v < VPT; ++v) gt += (keyof(v) > prefix) ? 1 : 0;
+        for (int v = 0; v < VPT; ++v) gt += (key[v] > prefix) ? 1 : 0;
         gt = __reduce_add_sync(0xffffffffu, gt);
-        int need = topk - gt, seen = 0;
+    }
+    const int need = topk - gt;                          // how many of the tied entries to keep (lowest index first)
+    int base = 0, seen = 0;
 #pragma unroll
-        for (int v = 0; v < VPT; ++v) {
-            const unsigned long long kv = keyof(v);
-            const bool eq = (kv == prefix);
+    for (int v = 0; v < VPT; ++v) {
+        bool take;
+        if (exact) {
+            take = key[v] >= prefix && key[v] != 0ull;
+        } else {
+            const bool eq = key[v] == prefix;
             const unsigned em = __ballot_sync(0xffffffffu, eq);
-            const int rank = seen + __popc(em & ((1u << lane) - 1u));
-            const bool take = (kv > prefix) || (eq && rank < need);
-            sel |= (unsigned long long)take << v;
+            take = (key[v] > prefix) || (eq && (seen + __popc(em & ((1u << lane) - 1u))) < need);
             seen += __popc(em);
         }
+        const unsigned tm = __ballot_sync(0xffffffffu, take);
+        if (take) {
+            const int pos = base + __popc(tm & ((1u << lane) - 1u));
+            kept[pos] = s[v];
+            kcol[pos] = lane + 32 * v;
+        }
+        base += __popc(tm);
     }
-
+    __syncwarp();
+    // softmax over the kept k (mdgat.py:206-207); the row maximum is always among them
     double sum = 0.0;
-#pragma unroll
-    for (int v = 0; v < VPT; ++v) {
-        s[v] = ((sel >> v) & 1ull) ? exp(s[v] - mx) : 0.0;
-        sum += s[v];
+    for (int t = lane; t < topk; t += 32) {
+        const double e = exp_fast_neg(kept[t] - mx, etab);
+        kept[t] = e;
+        sum += e;
     }
     sum = warp_sum_d(sum);
-
-    double acc = 0.0;                                   // lane = channel d of this head
-#pragma unroll
-    for (int v = 0; v < VPT; ++v) {
-        unsigned mask = __ballot_sync(0xffffffffu, (sel >> v) & 1ull);
-        while (mask) {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const double pj = shfl_d(s[v], src);
-            acc = fma(pj, __ldg(Vbh + (long long)(src + 32 * v) * LDH_V + lane), acc);
-        }
+    __syncwarp();
+    // sparse P.V: lane = channel d of this head; only k of the M value rows are read
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const double* vl = Vbh + lane;
+    int t = 0;
+    for (; t + 4 <= topk; t += 4) {
+        const double p0 = kept[t], p1 = kept[t + 1], p2 = kept[t + 2], p3 = kept[t + 3];
+        const int j0 = kcol[t], j1 = kcol[t + 1], j2 = kcol[t + 2], j3 = kcol[t + 3];
+        a0 = fma(p0, __ldg(vl + (long long)j0 * LDH_V), a0);
+        a1 = fma(p1, __ldg(vl + (long long)j1 * LDH_V), a1);
+        a2 = fma(p2, __ldg(vl + (long long)j2 * LDH_V), a2);
+        a3 = fma(p3, __ldg(vl + (long long)j3 * LDH_V), a3);
     }
-    Out[((long long)b * N + i) * ldo + h * HDIM + lane] = acc / sum;
+    for (; t < topk; ++t) a0 = fma(kept[t], __ldg(vl + (long long)kcol[t] * LDH_V), a0);
+    Out[((long long)b * N + i) * ldo + h * HDIM + lane] = ((a0 + a1) + (a2 + a3)) / sum;
+}
+
+template <int VPT>
+static cudaError_t launch_topk_t(const double* S, const double* V, double* Out, int ldo, int N, int M, int topk,
+                                 long long rows, cudaStream_t st) {
+    const size_t smem = (size_t)TK_WARPS * topk * (sizeof(double) + sizeof(int)) + 64 * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(topk_softmax_pv_kernel<VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((rows + TK_WARPS - 1) / TK_WARPS);
+    topk_softmax_pv_kernel<VPT><<<grid, 32 * TK_WARPS, smem, st>>>(S, V, Out, ldo, N, M, topk, rows);
+    return cudaSuccess;
 }
 
 cudaError_t launch_topk_softmax_pv(const double* S, const double* V, double* Out, int ldo,
                                    int B, int N, int M, int topk, cudaStream_t st) {
     if (B <= 0 || N <= 0) return cudaSuccess;
     const long long rows = (long long)B * HEADS * N;
-    const unsigned grid = (unsigned)((rows + 7) / 8);
-    if (M <= 512) topk_softmax_pv_kernel<16><<<grid, 256, 0, st>>>(S, V, Out, ldo, N, M, topk, rows);
-    else if (M <= 1024) topk_softmax_pv_kernel<32><<<grid, 256, 0, st>>>(S, V, Out, ldo, N, M, topk, rows);
-    else if (M <= 2048) topk_softmax_pv_kernel<64><<<grid, 256, 0, st>>>(S, V, Out, ldo, N, M, topk, rows);
+    cudaError_t e;
+    if (M <= 512) e = launch_topk_t<16>(S, V, Out, ldo, N, M, topk, rows, st);
+    else if (M <= 1024) e = launch_topk_t<32>(S, V, Out, ldo, N, M, topk, rows, st);
+    else if (M <= 2048) e = launch_topk_t<64>(S, V, Out, ldo, N, M, topk, rows, st);
     else return cudaErrorInvalidValue;
+    if (e != cudaSuccess) return e;
     count_launch();
     return cudaGetLastError();
 }

@@ -92,7 +92,7 @@ constexpr int LDHID = 260;   // row stride of the 256-wide MLP hidden buffer
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Workspace {
-    double *X, *Xk, *Xd, *Qh, *Kh, *Vh, *Msg, *Mg, *Hd, *MD, *S, *C, *u, *v, *mscratch;
+    double *X, *Xk, *Xd, *Qh, *Kh, *Vh, *Msg, *Mg, *Hd, *MD, *S, *C, *u, *v, *mscratch, *skscratch;
     size_t bytes;
 };
 
@@ -122,6 +122,7 @@ Workspace carve(char* base, int B, int N, int M, bool need_logits) {
     w.u = take((size_t)B * (N + 1));
     w.v = take((size_t)B * (M + 1));
     w.mscratch = take(4 * R + 8);
+    w.skscratch = take(sinkhorn_scratch_doubles(B, N, M));
     w.bytes = off;
     return w;
 }
@@ -258,7 +259,7 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const m
                           w.C, M + 1, (long long)(N + 1) * (M + 1), N, M, DMODEL, B, 1.0 / sqrt((double)DMODEL), st));
     prof_mark(ST_SINKHORN, st);
     MDGAT_CUDA_OK(launch_fill_dustbin(w.C, Wt + lay.bin, B, N, M, st));
-    MDGAT_CUDA_OK(launch_sinkhorn(w.C, w.u, w.v, B, N, M, cfg->sinkhorn_iters, st));
+    MDGAT_CUDA_OK(launch_sinkhorn_fused(w.C, w.u, w.v, w.skscratch, B, N, M, cfg->sinkhorn_iters, st));
     prof_mark(ST_MATCH, st);
 
     MatchParams mp;
@@ -314,12 +315,15 @@ int mdgat_attention_f64(const double* d_Q, const double* d_K, const double* d_V,
     return MDGAT_OK;
 }
 
+size_t mdgat_sinkhorn_scratch_doubles(int B, int N, int M) { return sinkhorn_scratch_doubles(B, N, M); }
+
 int mdgat_sinkhorn_f64(double* d_couplings, const double* d_bin_score, double* d_u, double* d_v,
-                       int B, int N, int M, int iters, void* stream) {
+                       int B, int N, int M, int iters, double* d_scratch, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     MDGAT_REQUIRE(B > 0 && N > 0 && M > 0 && iters >= 0, "mdgat_sinkhorn_f64: bad shape");
     MDGAT_CUDA_OK(launch_fill_dustbin(d_couplings, d_bin_score, B, N, M, st));
-    MDGAT_CUDA_OK(launch_sinkhorn(d_couplings, d_u, d_v, B, N, M, iters, st));
+    if (d_scratch) MDGAT_CUDA_OK(launch_sinkhorn_fused(d_couplings, d_u, d_v, d_scratch, B, N, M, iters, st));
+    else MDGAT_CUDA_OK(launch_sinkhorn(d_couplings, d_u, d_v, B, N, M, iters, st));
     return MDGAT_OK;
 }
 
@@ -372,6 +376,11 @@ int mdgat_profile_collect(double* ms, long long* launches, long long* segments, 
     }
     g_prof.used = 0; g_prof.stage.clear(); g_prof.launches_at.clear();
     for (int i = 0; i < ST_COUNT; ++i) { ms[i] = g_prof.ms[i]; launches[i] = g_prof.launches[i]; segments[i] = g_prof.segments[i]; }
+    return MDGAT_OK;
+}
+
+int mdgat_measure_fp64_mixed(double* tflops_dmma, double* tflops_dfma) {
+    MDGAT_CUDA_OK(measure_fp64_mixed(tflops_dmma, tflops_dfma));
     return MDGAT_OK;
 }
 

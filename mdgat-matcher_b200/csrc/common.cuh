@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "exp_table.h"
 
 #define DEVINL __device__ __forceinline__
 
@@ -81,6 +82,38 @@ DEVINL double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(v, o);
     return v;
+}
+
+// exp(x) for x <= 0 (softmax arguments after max subtraction), about 1-2 ulp.
+// x = (64 m + j) ln2/64 + r, |r| <= ln2/128: exp(x) = 2^m * 2^(j/64) * e^r with a 64-entry
+// table (in shared memory: lanes index it at random) and a degree-5 polynomial evaluated in
+// Estrin form. 11 FP64-pipe instructions with a 9-deep dependency chain, against 17 / 17 for
+// libm exp(): the softmax exponentials share the FP64 pipe with the DMMAs around them.
+// Results below 2^-1022 are flushed to zero.
+__device__ const double g_exp2_table[64] = MDGAT_EXP2_TABLE;
+
+DEVINL void exp_table_to_shared(double* tbl) {
+    if (threadIdx.x < 64) tbl[threadIdx.x] = g_exp2_table[threadIdx.x];
+}
+
+DEVINL double exp_fast_neg(double x, const double* tbl) {
+    const double xc = fmax(x, -745.0);
+    const double MAGIC = 6755399441055744.0;                // 1.5 * 2^52: rint() in the low mantissa bits
+    const double tn = fma(xc, EXP_INV_LN2_64, MAGIC);
+    const int n = __double2loint(tn);
+    const double nd = tn - MAGIC;
+    double r = fma(nd, -EXP_LN2_64_HI, xc);
+    r = fma(nd, -EXP_LN2_64_LO, r);
+    const double r2 = r * r;
+    const double a = fma(r, 1.0 / 6.0, 0.5);
+    const double b = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    const double c = fma(r2, b, a);
+    const double p = fma(r2, c, r);                         // e^r - 1
+    const double t = tbl[n & 63];
+    const double y = fma(t, p, t);                          // in [1, 2)
+    const int m = n >> 6;
+    const double ys = __hiloint2double(__double2hiint(y) + (m << 20), __double2loint(y));
+    return xc < -708.0 ? 0.0 : ys;
 }
 
 }  // namespace mdgat

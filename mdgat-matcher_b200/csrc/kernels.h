@@ -41,6 +41,10 @@ cudaError_t launch_pack_inputs(const void* kpts0, const void* kpts1, const void*
 // Sinkhorn (general, global-memory resident couplings)
 cudaError_t launch_fill_dustbin(double* C, const double* bin_score, int B, int N, int M, cudaStream_t st);
 cudaError_t launch_sinkhorn(const double* C, double* u, double* v, int B, int N, int M, int iters, cudaStream_t st);
+// Fused: one launch, one 8-CTA cluster per pair, kernel matrix in distributed shared memory.
+size_t sinkhorn_scratch_doubles(int B, int N, int M);
+cudaError_t launch_sinkhorn_fused(const double* C, double* u, double* v, double* scratch, int B, int N, int M,
+                                  int iters, cudaStream_t st);
 
 struct MatchParams {
     const double* C; const double* u; const double* v;
@@ -57,5 +61,6 @@ cudaError_t launch_match_extract(const MatchParams& p, cudaStream_t st);
 cudaError_t launch_knn(const double* x, const double* src, int64_t* idx, int B, int n, int m, int k, cudaStream_t st);
 
 cudaError_t measure_fp64_peak(double* dmma_tflops, double* dfma_tflops);
+cudaError_t measure_fp64_mixed(double* dmma_tflops, double* dfma_tflops);
 
 }  // namespace mdgat

@@ -140,6 +140,55 @@ __global__ void __launch_bounds__(512) dfma_peak_kernel(double* out, int iters, 
     if (s == 123.456) out[0] = s;
 }
 
+// DMMA and DFMA issued together: 8 DMMA chains + 8 DFMA chains per warp, ratio 1 DMMA : 2 DFMA
+// (about the mix of the attention kernel). Tells whether the two share one issue pipe.
+__global__ void __launch_bounds__(512) mixed_peak_kernel(double* out, int iters, double a0, double b0) {
+    double c[8][2], f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = c[i][1] = 0.0; f[i] = i; }
+    const double a = a0 + threadIdx.x * 1e-9, b = b0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                dmma884(c[i][0], c[i][1], a, b);
+                f[i] = fma(f[i], a, b);
+                f[(i + 4) & 7] = fma(f[(i + 4) & 7], b, a);
+            }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1] + f[i];
+    if (s == 123.456) out[0] = s;
+}
+
+cudaError_t measure_fp64_mixed(double* dmma_tflops, double* dfma_tflops) {
+    int dev = 0, sms = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    double* d = nullptr;
+    if ((e = cudaMalloc(&d, 64)) != cudaSuccess) return e;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    const int iters = 2000, grid = sms * 2;
+    float ms = 0.f;
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(t0);
+        mixed_peak_kernel<<<grid, 512>>>(d, iters, 1.0000001, 0.5);
+        cudaEventRecord(t1);
+        cudaEventSynchronize(t1);
+        cudaEventElapsedTime(&ms, t0, t1);
+    }
+    const double warps = (double)grid * 16;
+    *dmma_tflops = warps * iters * 32 * 512.0 / (ms * 1e-3) / 1e12;
+    *dfma_tflops = warps * iters * 64 * 64.0 / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    cudaFree(d);
+    return cudaGetLastError();
+}
+
 cudaError_t measure_fp64_peak(double* dmma_tflops, double* dfma_tflops) {
     int dev = 0, sms = 0;
     cudaError_t e;

@@ -7,6 +7,8 @@
 //     u_i = log_mu_i - LSE_j(C_ij + v_j)          (row pass, one warp per row)
 //     v_j = log_nu_j - LSE_i(C_ij + u_i)          (column pass, 32 columns x 16 row-groups per CTA)
 // The assignment matrix Z = C + u + v - norm is never written unless a caller asks for it.
+#include <cooperative_groups.h>
+#include <string.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -87,6 +89,281 @@ sinkhorn_col_kernel(const double* __restrict__ C, const double* __restrict__ u, 
         const double log_nu = (j < M) ? norm : (log((double)N) + norm);
         v[(long long)b * C1 + j] = log_nu - (mx + log(sum));
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused Sinkhorn: all iterations in ONE launch, one 8-CTA cluster per pair, the kernel matrix
+// resident on chip (shared memory + registers of the cluster).
+//
+// Algebra. With c_i = max_j C_ij and K_ij = exp(C_ij - c_i) in (0, 1] (computed once), the
+// log-domain updates of the reference (mdgat.py:283-284)
+//     u_i = log mu_i - LSE_j(C_ij + v_j),      v_j = log nu_j - LSE_i(C_ij + u_i)
+// are, for a_i = exp(u_i + c_i) and b_j = exp(v_j), exactly the scaling iteration
+//     a_i = mu_i / sum_j K_ij b_j,             b_j = nu_j / sum_i K_ij a_i,
+// i.e. one multiply-add per matrix entry and one division per row / column per half-iteration
+// instead of an exp per ENTRY, and no transcendental at all inside the loop. u = log a - c and
+// v = log b are taken once at the end. All K_ij <= 1 with a 1 in every row, so while every row
+// range max_j C_ij - min_j C_ij stays below SKF_MAX_RANGE the sums neither overflow nor lose
+// relative accuracy; pairs that violate the bound (ill-conditioned, out-of-distribution
+// inputs) are flagged and redone by the plain log-domain kernel below.
+//
+// Each CTA owns a slice of rows. Storage tiers for the K rows of a slice (local row r):
+//   r <  n_smem                    shared memory   Ks[r][j], j < M
+//   r <  n_smem + n_reg            registers       kreg[r - n_smem] = column j = tid (M <= 512)
+//   otherwise                      global scratch  (L2-resident for mid sizes, HBM for N = 2048)
+// The dustbin column j = M is one scalar per row (kd[r]) so that the main block has exactly M
+// columns (512 at the benchmark shape = one column per thread). A CTA does the row sums of its
+// rows, then the partial column sums over its rows; the 8 partials are combined through
+// distributed shared memory with one cluster barrier per iteration.
+// ------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int SKF_CLUSTER = 8, SKF_THREADS = 512, SKF_WARPS = SKF_THREADS / 32;
+constexpr int SKF_NREG = 16;                 // K rows a CTA can keep in registers (one column per thread)
+constexpr double SKF_MAX_RANGE = 300.0;
+
+// Reduces NV per-lane values across the warp with NV-1 + log2(32/NV) shuffles (instead of
+// 5 NV): each halving step trades half of the values with the partner lane. On return lane l
+// holds the total of value index (l >> (5 - log2 NV)) in v[0].
+template <int NV>
+DEVINL void warp_transpose_sum(double (&v)[NV], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = NV; n > 1; n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const double keep = up ? v[i + n / 2] : v[i];
+            const double send = up ? v[i] : v[i + n / 2];
+            v[i] = keep + shfl_xor_d(send, off);
+        }
+        off >>= 1;
+    }
+    for (; off > 0; off >>= 1) v[0] += shfl_xor_d(v[0], off);
+}
+
+__global__ void __launch_bounds__(SKF_THREADS, 1)
+sinkhorn_fused_kernel(const double* __restrict__ C, double* __restrict__ Kg, double* __restrict__ u_out,
+                      double* __restrict__ v_out, int* __restrict__ flags, int N, int M, int iters,
+                      int RS, int rows_smem, int nreg, int ldk) {
+    extern __shared__ __align__(16) double sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    const int b = blockIdx.x / SKF_CLUSTER;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int R1 = N + 1, C1 = M + 1;
+    const double mu_reg = 1.0 / (double)(N + M), mu_bin = (double)M / (double)(N + M);   // exp(log_mu)
+    const double nu_reg = mu_reg, nu_bin = (double)N / (double)(N + M);                  // exp(log_nu)
+
+    // shared layout (ldv = C1 rounded up to even, RSp = RS rounded up to a multiple of 4)
+    const int ldv = (C1 + 1) & ~1, RSp = (RS + 3) & ~3;
+    double* bs = sm;                        // [ldv]   b_j
+    double* part = bs + ldv;                // [2][ldv] column partials of this CTA (peers read them)
+    double* as = part + 2 * ldv;            // [RSp]   a_i of own rows (zero beyond nrows)
+    double* cmx = as + RSp;                 // [RSp]   row maxima of C
+    double* kd = cmx + RSp;                 // [RSp]   K of the dustbin column
+    double* red = kd + RSp;                 // [SKF_NREG][SKF_WARPS]
+    double* Ks = red + SKF_NREG * SKF_WARPS;   // [rows_smem][ldk]
+
+    const int r0 = crank * RS;
+    const int nrows = max(0, min(RS, R1 - r0));
+    const int n_smem = min(nrows, rows_smem);
+    const int n_reg = max(0, min(nrows - n_smem, nreg));
+    const int g0 = n_smem + n_reg;           // first local row that lives in global scratch
+    const double* Cb = C + (long long)b * R1 * C1;
+    double* Kb = Kg + (long long)b * R1 * ldk;
+
+    // ---- setup: row maxima, range check, K rows
+    for (int r = tid; r < RSp; r += SKF_THREADS) { as[r] = 0.0; kd[r] = 0.0; cmx[r] = 0.0; }
+    __syncthreads();
+    int bad = 0;
+    for (int r = warp; r < nrows; r += SKF_WARPS) {
+        const double* crow = Cb + (long long)(r0 + r) * C1;
+        double mx = -INFINITY, mn = INFINITY;
+        for (int j = lane; j < C1; j += 32) { const double c = crow[j]; mx = fmax(mx, c); mn = fmin(mn, c); }
+        mx = warp_max_d(mx);
+        mn = -warp_max_d(-mn);
+        if (!(mx - mn < SKF_MAX_RANGE)) bad = 1;          // also catches NaN / inf
+        if (r < n_smem || r >= g0) {
+            double* krow = r < n_smem ? Ks + (size_t)r * ldk : Kb + (long long)(r0 + r) * ldk;
+            for (int j = lane; j < M; j += 32) krow[j] = exp(crow[j] - mx);
+        }
+        if (lane == 0) { cmx[r] = mx; kd[r] = exp(crow[M] - mx); }
+    }
+    if (bad && lane == 0) atomicOr(flags + b, 1);
+    for (int j = tid; j < C1; j += SKF_THREADS) bs[j] = 1.0;      // v = 0 before the first row pass
+    __syncthreads();
+    double kreg[SKF_NREG];
+#pragma unroll
+    for (int q = 0; q < SKF_NREG; ++q) {
+        kreg[q] = 0.0;
+        if (q < n_reg && tid < M) kreg[q] = exp(Cb[(long long)(r0 + n_smem + q) * C1 + tid] - cmx[n_smem + q]);
+    }
+
+    for (int it = 0; it < iters; ++it) {
+        const int buf = it & 1;
+        const double bM = bs[M];
+        // ---- row sums s_r = sum_j K_rj b_j, then a_r = mu_r / s_r
+        // (1) register rows: per-thread products, reduced across the CTA through red[]
+        if (n_reg > 0) {
+            const double bj = tid < M ? bs[tid] : 0.0;
+            double pr[SKF_NREG];
+#pragma unroll
+            for (int q = 0; q < SKF_NREG; ++q) pr[q] = kreg[q] * bj;
+            warp_transpose_sum<SKF_NREG>(pr, lane);
+            if ((lane & 1) == 0) red[(lane >> 1) * SKF_WARPS + warp] = pr[0];
+        }
+        // (2) shared / global rows: a warp takes four rows at a time
+        for (int rb = warp * 4; rb < nrows; rb += SKF_WARPS * 4) {
+            if (rb >= n_smem && min(rb + 3, nrows - 1) < g0) continue;      // all four live in registers
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const double* kr[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = min(rb + q, nrows - 1);
+                kr[q] = r < n_smem ? Ks + (size_t)r * ldk : Kb + (long long)(r0 + r) * ldk;
+            }
+            for (int j = lane; j < M; j += 32) {
+                const double bj = bs[j];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] = fma(kr[q][j], bj, acc[q]);
+            }
+            warp_transpose_sum<4>(acc, lane);
+            const int r = rb + (lane >> 3);
+            if ((lane & 7) == 0 && r < nrows && !(r >= n_smem && r < g0))
+                as[r] = ((r0 + r < N) ? mu_reg : mu_bin) / fma(kd[r], bM, acc[0]);
+        }
+        __syncthreads();
+        if (tid < n_reg) {
+            const int r = n_smem + tid;
+            double sum = 0.0;
+#pragma unroll
+            for (int x = 0; x < SKF_WARPS; ++x) sum += red[tid * SKF_WARPS + x];
+            as[r] = ((r0 + r < N) ? mu_reg : mu_bin) / fma(kd[r], bM, sum);
+        }
+        __syncthreads();
+        // ---- partial column sums over own rows: part_j = sum_r K_rj a_r
+        double* pb = part + buf * ldv;
+        for (int j = tid; j < M; j += SKF_THREADS) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int r = 0;
+            for (; r + 3 < n_smem; r += 4) {
+                const double2 w01 = *reinterpret_cast<const double2*>(as + r);
+                const double2 w23 = *reinterpret_cast<const double2*>(as + r + 2);
+                a0 = fma(Ks[(size_t)r * ldk + j], w01.x, a0);
+                a1 = fma(Ks[(size_t)(r + 1) * ldk + j], w01.y, a1);
+                a2 = fma(Ks[(size_t)(r + 2) * ldk + j], w23.x, a2);
+                a3 = fma(Ks[(size_t)(r + 3) * ldk + j], w23.y, a3);
+            }
+            for (; r < n_smem; ++r) a0 = fma(Ks[(size_t)r * ldk + j], as[r], a0);
+            if (j == tid) {
+#pragma unroll
+                for (int q = 0; q < SKF_NREG; ++q) if (q < n_reg) a1 = fma(kreg[q], as[n_smem + q], a1);
+            }
+            for (r = g0; r < nrows; ++r) a2 = fma(Kb[(long long)(r0 + r) * ldk + j], as[r], a2);
+            pb[j] = (a0 + a1) + (a2 + a3);
+        }
+        if (warp == SKF_WARPS - 1) {                    // dustbin column
+            double a = 0.0;
+            for (int r = lane; r < nrows; r += 32) a = fma(kd[r], as[r], a);
+            a = warp_sum_d(a);
+            if (lane == 0) pb[M] = a;
+        }
+        cluster.sync();
+        // ---- b_j = nu_j / sum of the 8 partials (same order in every CTA -> identical b everywhere)
+        for (int j = tid; j < C1; j += SKF_THREADS) {
+            double pv[SKF_CLUSTER];
+#pragma unroll
+            for (int c = 0; c < SKF_CLUSTER; ++c) pv[c] = cluster.map_shared_rank(part, c)[buf * ldv + j];
+            const double tot = ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
+            bs[j] = ((j < M) ? nu_reg : nu_bin) / tot;
+        }
+        __syncthreads();
+    }
+    // peers may still be reading this CTA's partials of the last iteration
+    cluster.sync();
+    // u_i = log a_i - c_i, v_j = log b_j
+    for (int r = tid; r < nrows; r += SKF_THREADS) u_out[(long long)b * R1 + r0 + r] = iters > 0 ? log(as[r]) - cmx[r] : 0.0;
+    if (crank == 0)
+        for (int j = tid; j < C1; j += SKF_THREADS) v_out[(long long)b * C1 + j] = iters > 0 ? log(bs[j]) : 0.0;
+}
+
+// Plain log-domain Sinkhorn for flagged pairs: one CTA per pair, exact max subtraction.
+__global__ void __launch_bounds__(1024)
+sinkhorn_safe_kernel(const double* __restrict__ C, double* __restrict__ u, double* __restrict__ v,
+                     const int* __restrict__ flags, int N, int M, int iters) {
+    const int b = blockIdx.x;
+    if (flags[b] == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int R1 = N + 1, C1 = M + 1;
+    const double norm = -log((double)(N + M));
+    const double* Cb = C + (long long)b * R1 * C1;
+    double* ub = u + (long long)b * R1;
+    double* vb = v + (long long)b * C1;
+    for (int j = tid; j < C1; j += 1024) vb[j] = 0.0;
+    __syncthreads();
+    for (int it = 0; it < iters; ++it) {
+        for (int i = warp; i < R1; i += 32) {
+            const double* row = Cb + (long long)i * C1;
+            double mx = -INFINITY;
+            for (int j = lane; j < C1; j += 32) mx = fmax(mx, row[j] + vb[j]);
+            mx = warp_max_d(mx);
+            const double m0 = (mx == -INFINITY || mx == INFINITY) ? 0.0 : mx;
+            double sum = 0.0;
+            for (int j = lane; j < C1; j += 32) sum += exp(row[j] + vb[j] - m0);
+            sum = warp_sum_d(sum);
+            if (lane == 0) ub[i] = ((i < N) ? norm : (log((double)M) + norm)) - (m0 + log(sum));
+        }
+        __syncthreads();
+        for (int j = tid; j < C1; j += 1024) {
+            double mx = -INFINITY;
+            for (int i = 0; i < R1; ++i) mx = fmax(mx, Cb[(long long)i * C1 + j] + ub[i]);
+            const double m0 = (mx == -INFINITY || mx == INFINITY) ? 0.0 : mx;
+            double sum = 0.0;
+            for (int i = 0; i < R1; ++i) sum += exp(Cb[(long long)i * C1 + j] + ub[i] - m0);
+            vb[j] = ((j < M) ? norm : (log((double)N) + norm)) - (m0 + log(sum));
+        }
+        __syncthreads();
+    }
+}
+
+size_t sinkhorn_scratch_doubles(int B, int N, int M) {
+    const size_t ldk = (size_t)((M + 1) & ~1);
+    return (size_t)B * (N + 1) * ldk + (size_t)(B + 1) / 2 + 2;      // K scratch + per-pair flags (ints)
+}
+
+cudaError_t launch_sinkhorn_fused(const double* C, double* u, double* v, double* scratch, int B, int N, int M,
+                                  int iters, cudaStream_t st) {
+    const int R1 = N + 1, C1 = M + 1;
+    const int ldk = (M + 1) & ~1, ldv = (C1 + 1) & ~1;
+    const int RS = (R1 + SKF_CLUSTER - 1) / SKF_CLUSTER;
+    double* Kg = scratch;
+    int* flags = reinterpret_cast<int*>(scratch + (size_t)B * R1 * ldk);
+    int dev = 0, max_smem = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    const size_t fixed = ((size_t)3 * ldv + 3 * (size_t)((RS + 3) & ~3) + SKF_WARPS * SKF_NREG) * sizeof(double);
+    if (fixed + 1024 > (size_t)max_smem) return cudaErrorInvalidValue;
+    int rows_smem = (int)(((size_t)max_smem - fixed) / ((size_t)ldk * sizeof(double)));
+    if (rows_smem > RS) rows_smem = RS;
+    const int nreg = (M <= SKF_THREADS) ? SKF_NREG : 0;
+    const size_t smem = fixed + (size_t)rows_smem * ldk * sizeof(double);
+    if ((e = cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)B, st)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(sinkhorn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(SKF_CLUSTER * B);
+    cfg.blockDim = dim3(SKF_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = SKF_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if ((e = cudaLaunchKernelEx(&cfg, sinkhorn_fused_kernel, C, Kg, u, v, flags, N, M, iters, RS, rows_smem, nreg, ldk)) != cudaSuccess) return e;
+    sinkhorn_safe_kernel<<<B, 1024, 0, st>>>(C, u, v, flags, N, M, iters);
+    count_launch(2);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_sinkhorn(const double* C, double* u, double* v, int B, int N, int M, int iters, cudaStream_t st) {

@@ -88,8 +88,9 @@ def attention(q, k, v, topk=None):
     return msg.permute(0, 3, 2, 1).reshape(B, 128, N).contiguous()  # channel c = d*4 + h
 
 
-def sinkhorn(scores, bin_score, iters):
-    """scores (B,N,M) -> Z (B,N+1,M+1) = log_optimal_transport(scores, bin_score, iters)."""
+def sinkhorn(scores, bin_score, iters, fused=True):
+    """scores (B,N,M) -> (couplings, u, v) with Z = couplings + u[:, :, None] + v[:, None, :] - norm
+    = log_optimal_transport(scores, bin_score, iters). fused=False uses one launch per half-iteration."""
     _need_cuda(scores)
     B, N, M = scores.shape
     dev = scores.device
@@ -98,9 +99,11 @@ def sinkhorn(scores, bin_score, iters):
     u = torch.empty((B, N + 1), dtype=torch.float64, device=dev)
     v = torch.empty((B, M + 1), dtype=torch.float64, device=dev)
     alpha = torch.as_tensor(bin_score, dtype=torch.float64, device=dev).reshape(1).contiguous()
+    scratch = torch.empty(_capi.lib.mdgat_sinkhorn_scratch_doubles(B, N, M), dtype=torch.float64, device=dev) if fused else None
     with torch.cuda.device(dev):
         _capi.check(_capi.lib.mdgat_sinkhorn_f64(C.data_ptr(), alpha.data_ptr(), u.data_ptr(), v.data_ptr(),
-                                                 B, N, M, int(iters), _stream(dev)))
+                                                 B, N, M, int(iters), scratch.data_ptr() if fused else None,
+                                                 _stream(dev)))
     return C, u, v
 
 
@@ -177,4 +180,10 @@ def encode(blob, data):
 def measure_fp64_peak():
     a, b = ctypes.c_double(), ctypes.c_double()
     _capi.check(_capi.lib.mdgat_measure_fp64_peak(ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value
+
+
+def measure_fp64_mixed():
+    a, b = ctypes.c_double(), ctypes.c_double()
+    _capi.check(_capi.lib.mdgat_measure_fp64_mixed(ctypes.byref(a), ctypes.byref(b)))
     return a.value, b.value

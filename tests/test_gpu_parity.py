@@ -104,17 +104,33 @@ def test_attention_topk_k_out_of_range(dev):
         ops.attention(q, q, q, topk=32)
 
 
-@pytest.mark.parametrize('N,M,iters', [(128, 128, 20), (200, 77, 100), (512, 512, 100), (5, 9, 3)])
-def test_sinkhorn_vs_oracle(dev, N, M, iters):
+@pytest.mark.parametrize('fused', [True, False])
+@pytest.mark.parametrize('N,M,iters', [(128, 128, 20), (200, 77, 100), (512, 512, 100), (5, 9, 3), (700, 650, 10), (64, 64, 0)])
+def test_sinkhorn_vs_oracle(dev, N, M, iters, fused):
     from mdgat_matcher_b200 import ops
     from oracle import mdgat_oracle as O
     rng = np.random.default_rng(N + M)
-    scores = rng.normal(size=(2, N, M)) * 3 + 2
+    scores = rng.normal(size=(3, N, M)) * 3 + 2
     want = O.log_optimal_transport(scores, 1.977, iters)
-    C, u, v = ops.sinkhorn(_t(scores, dev), 1.977, iters)
+    C, u, v = ops.sinkhorn(_t(scores, dev), 1.977, iters, fused=fused)
     norm = -np.log(N + M)
     got = (C + u[:, :, None] + v[:, None, :] - norm).cpu().numpy()
     assert np.abs(got - want).max() < 1e-10
+
+
+def test_sinkhorn_fused_falls_back_on_ill_conditioned_pairs(dev):
+    """Row ranges beyond the factored form's safe bound (here ~ +-2000, like the out-of-distribution
+    logits of SURVEY.md fact 9) are redone by the plain log-domain kernel, pair by pair."""
+    from mdgat_matcher_b200 import ops
+    from oracle import mdgat_oracle as O
+    rng = np.random.default_rng(1)
+    scores = rng.normal(size=(3, 96, 80)) * 3
+    scores[1] *= 300.0                       # only the middle pair is ill-conditioned
+    want = O.log_optimal_transport(scores, 1.0, 25)
+    C, u, v = ops.sinkhorn(_t(scores, dev), 1.0, 25, fused=True)
+    got = (C + u[:, :, None] + v[:, None, :] + np.log(96 + 80)).cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() < 1e-8
 
 
 @pytest.mark.parametrize('loss_method,mutual', [('triplet_loss', False), ('triplet_loss', True),

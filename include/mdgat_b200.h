@@ -155,7 +155,9 @@ int mdgat_knn(const double* d_x, const double* d_src, int64_t* d_idx, int B, int
 /* Measured fp64 tensor-pipe peak of this device (DMMA.8x8x4 issue loop), TFLOP/s.
  * Synchronises. Used as the roofline denominator of the fp64 kernels. */
 int mdgat_measure_fp64_peak(double* tflops_dmma, double* tflops_dfma);
-/* Same, with DMMA and DFMA issued together (1 DMMA : 2 DFMA per warp): the rates each reaches in the mix. */
+/* Same, with DMMA and DFMA issued together (1 DMMA : 2 DFMA per warp): the rates each reaches in the mix.
+ * tflops_dfma must have room for 2 doubles: [1] receives the DMMA rate of a register-tiled 4x4
+ * outer-product loop at 16 warps/SM (the GEMM inner loop without its memory traffic). */
 int mdgat_measure_fp64_mixed(double* tflops_dmma, double* tflops_dfma);
 
 /* ---- instrumentation (no reference counterpart; the reference has no tracing) ----

@@ -19,6 +19,9 @@ namespace mdgat {
 constexpr int A_BM = 64, A_BN = 64, A_THREADS = 128, A_STAGES = 2;
 constexpr size_t A_SMEM = ((size_t)A_STAGES * A_BN * (LDH_QK + LDH_V) + 64) * sizeof(double);
 
+// LOGITS_ONLY = true: the same Q K^T pipeline, but the scaled logits are written to Out as a dense
+// (B,4,N,M) tensor (ldo = M) for the exact top-k selection below; no softmax, V is not read.
+template <bool LOGITS_ONLY>
 __global__ void __launch_bounds__(A_THREADS, 3)
 attn_full_kernel(const double* __restrict__ Q, const double* __restrict__ K, const double* __restrict__ V,
                  double* __restrict__ Out, int ldo, int N, int M, double scale) {
@@ -68,8 +71,9 @@ attn_full_kernel(const double* __restrict__ Q, const double* __restrict__ K, con
         const int kvalid = rows * LDH_QK / 2, vvalid = rows * LDH_V / 2;     // 16-byte units
         for (int i = tid; i < A_BN * LDH_QK / 2; i += A_THREADS)
             cp_async16(kd + 2 * i, i < kvalid ? ksrc + 2 * i : ksrc, i < kvalid);
-        for (int i = tid; i < A_BN * LDH_V / 2; i += A_THREADS)
-            cp_async16(vd + 2 * i, i < vvalid ? vsrc + 2 * i : vsrc, i < vvalid);
+        if (!LOGITS_ONLY)
+            for (int i = tid; i < A_BN * LDH_V / 2; i += A_THREADS)
+                cp_async16(vd + 2 * i, i < vvalid ? vsrc + 2 * i : vsrc, i < vvalid);
     };
 
     load_chunk(0, 0);
@@ -101,8 +105,27 @@ attn_full_kernel(const double* __restrict__ Q, const double* __restrict__ K, con
                 dmma884(s[1][nt][0], s[1][nt][1], qa[1][ks], bfrag);
             }
         }
-        // columns past M (last chunk only)
         const int j0 = c * A_BN;
+        if (LOGITS_ONLY) {
+            // scores = q.k / sqrt(d) (mdgat.py:201), row-major (b, h, n, m)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const int row = row_base + mt * 8 + qr;
+                if (row < N) {
+                    double* srow = Out + (bh * N + row) * (long long)M + j0 + 2 * qc;
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) {
+                        const int col = j0 + nt * 8 + 2 * qc;
+                        const double y0 = s[mt][nt][0] * scale, y1 = s[mt][nt][1] * scale;
+                        if (col + 1 < M && (M & 1) == 0) *reinterpret_cast<double2*>(srow + nt * 8) = make_double2(y0, y1);
+                        else { if (col < M) srow[nt * 8] = y0; if (col + 1 < M) srow[nt * 8 + 1] = y1; }
+                    }
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+        // columns past M (last chunk only)
         if (j0 + A_BN > M) {
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt)
@@ -151,6 +174,7 @@ attn_full_kernel(const double* __restrict__ Q, const double* __restrict__ K, con
         __syncthreads();
     }
 
+    if (LOGITS_ONLY) return;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
         double l = l_run[mt];
@@ -169,10 +193,20 @@ attn_full_kernel(const double* __restrict__ Q, const double* __restrict__ K, con
 cudaError_t launch_attention_full(const double* Q, const double* K, const double* V, double* Out, int ldo,
                                   int B, int N, int M, cudaStream_t st) {
     if (B <= 0 || N <= 0 || M <= 0) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(attn_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_full_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM);
     if (e != cudaSuccess) return e;
     dim3 grid((N + A_BM - 1) / A_BM, HEADS, B);
-    attn_full_kernel<<<grid, A_THREADS, A_SMEM, st>>>(Q, K, V, Out, ldo, N, M, 1.0 / sqrt((double)HDIM));
+    attn_full_kernel<false><<<grid, A_THREADS, A_SMEM, st>>>(Q, K, V, Out, ldo, N, M, 1.0 / sqrt((double)HDIM));
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_attention_logits(const double* Q, const double* K, double* S, int B, int N, int M, cudaStream_t st) {
+    if (B <= 0 || N <= 0 || M <= 0) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(attn_full_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM);
+    if (e != cudaSuccess) return e;
+    dim3 grid((N + A_BM - 1) / A_BM, HEADS, B);
+    attn_full_kernel<true><<<grid, A_THREADS, A_SMEM, st>>>(Q, K, nullptr, S, M, N, M, 1.0 / sqrt((double)HDIM));
     count_launch();
     return cudaGetLastError();
 }
@@ -190,17 +224,18 @@ DEVINL unsigned long long order_key(double x) {
 
 constexpr int TK_WARPS = 8;
 
-// VPT = values per lane (M <= 32*VPT). Dynamic shared memory: per warp topk doubles (kept
-// logits, then probabilities) + topk ints (their column indices).
+struct __align__(16) KeptEntry { double p; int col; int pad; };
+
+// VPT = values per lane (M <= 32*VPT). Dynamic shared memory: per warp `topk` KeptEntry
+// (kept logit -> probability, column), then the 64-entry exp table.
 template <int VPT>
-__global__ void __launch_bounds__(32 * TK_WARPS)
+__global__ void __launch_bounds__(32 * TK_WARPS, VPT == 16 ? 3 : 1)
 topk_softmax_pv_kernel(const double* __restrict__ S, const double* __restrict__ V, double* __restrict__ Out,
                        int ldo, int N, int M, int topk, long long total_rows) {
     extern __shared__ __align__(16) unsigned char tk_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* kept = reinterpret_cast<double*>(tk_smem) + (size_t)warp * topk;
-    int* kcol = reinterpret_cast<int*>(tk_smem + (size_t)TK_WARPS * topk * sizeof(double) + 64 * sizeof(double)) + (size_t)warp * topk;
-    double* etab = reinterpret_cast<double*>(tk_smem) + (size_t)TK_WARPS * topk;
+    KeptEntry* kept = reinterpret_cast<KeptEntry*>(tk_smem) + (size_t)warp * topk;
+    double* etab = reinterpret_cast<double*>(tk_smem + (size_t)TK_WARPS * topk * sizeof(KeptEntry));
     exp_table_to_shared(etab);
     __syncthreads();
     const long long g = (long long)blockIdx.x * TK_WARPS + warp;          // row in (B,4,N) order
@@ -212,66 +247,92 @@ topk_softmax_pv_kernel(const double* __restrict__ S, const double* __restrict__ 
     const double* Vbh = V + bh * (long long)M * LDH_V;
 
     double s[VPT];
-    unsigned long long key[VPT];
     double mx = -INFINITY, mn = INFINITY;
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
         const int j = lane + 32 * v;
         const bool ok = j < M;
-        s[v] = ok ? srow[j] : -INFINITY;
-        key[v] = ok ? order_key(s[v]) : 0ull;            // padding sorts below every real value
+        s[v] = ok ? srow[j] : -INFINITY;                  // padding never passes a ">= finite" test
         if (ok) { mx = fmax(mx, s[v]); mn = fmin(mn, s[v]); }
     }
     mx = warp_max_d(mx);
     mn = -warp_max_d(-mn);
 
-    // bits above the highest bit in which max and min differ are common to every key: skip them
-    const unsigned long long kmax = order_key(mx), kmin = order_key(mn);
-    const unsigned long long diff = kmax ^ kmin;
-    unsigned long long prefix = kmax;
-    bool exact = false;
-    if (topk >= M) {                                     // k == M: keep everything
-        prefix = kmin; exact = true;
-    } else if (diff != 0ull) {
-        const int top = 63 - __clzll((long long)diff);
-        prefix = (top == 63) ? 0ull : (kmax >> (top + 1)) << (top + 1);
-        for (int bit = top; bit >= 0; --bit) {
-            const unsigned long long cand = prefix | (1ull << bit);
+    // ---- fast path: bisect the VALUE interval [mn, mx] until a threshold keeps exactly k
+    double thr = mn;
+    bool exact = topk >= M;
+    if (!exact) {
+        double lo = mn, hi = mx;
+        for (int step = 0; step < 48; ++step) {
+            const double mid = lo + 0.5 * (hi - lo);
+            if (!(mid > lo && mid < hi)) break;           // interval collapsed: ties or adjacent doubles
             int c = 0;
 #pragma unroll
-            for (int v = 0; v < VPT; ++v) c += (key[v] >= cand) ? 1 : 0;
+            for (int v = 0; v < VPT; ++v) c += (s[v] >= mid) ? 1 : 0;
             c = __reduce_add_sync(0xffffffffu, c);
-            if (c >= topk) {
-                prefix = cand;
-                if (c == topk) { exact = true; break; }
+            if (c == topk) { thr = mid; exact = true; break; }
+            if (c > topk) lo = mid; else hi = mid;
+        }
+    }
+    unsigned long long sel = 0ull;                        // bit v: keep s[v]
+    if (exact) {
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) sel |= (unsigned long long)(s[v] >= thr && (lane + 32 * v) < M) << v;
+    } else {
+        // ---- exact path for ties at the k-th value: most-significant-bit-first search on the
+        // order-preserving integer image of the doubles, then lowest-index tie-break
+        auto keyof = [&](int v) -> unsigned long long { return (lane + 32 * v) < M ? order_key(s[v]) : 0ull; };
+        const unsigned long long kmax = order_key(mx), kmin = order_key(mn);
+        const unsigned long long diff = kmax ^ kmin;
+        unsigned long long prefix = kmax;
+        bool found = false;
+        if (diff != 0ull) {
+            const int top = 63 - __clzll((long long)diff);
+            prefix = (top == 63) ? 0ull : (kmax >> (top + 1)) << (top + 1);
+            for (int bit = top; bit >= 0; --bit) {
+                const unsigned long long cand = prefix | (1ull << bit);
+                int c = 0;
+#pragma unroll
+                for (int v = 0; v < VPT; ++v) c += (keyof(v) >= cand) ? 1 : 0;
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (c >= topk) {
+                    prefix = cand;
+                    if (c == topk) { found = true; break; }
+                }
             }
         }
-    }
-    // prefix is now either a threshold keeping exactly k entries (exact) or the k-th largest key
-    int gt = 0;
-    if (!exact) {
+        int gt = 0;
+        if (!found) {
 #pragma unroll
-        for (int v = 0; v < VPT; ++v) gt += (key[v] > prefix) ? 1 : 0;
-        gt = __reduce_add_sync(0xffffffffu, gt);
+            for (int v = 0; v < VPT; ++v) gt += (keyof(v) > prefix) ? 1 : 0;
+            gt = __reduce_add_sync(0xffffffffu, gt);
+        }
+        const int need = topk - gt;                       // tied entries to keep, lowest index first
+        int seen = 0;
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+            const unsigned long long kv = keyof(v);
+            bool take;
+            if (found) {
+                take = kv >= prefix && kv != 0ull;
+            } else {
+                const bool eq = kv == prefix;
+                const unsigned em = __ballot_sync(0xffffffffu, eq);
+                take = (kv > prefix) || (eq && (seen + __popc(em & ((1u << lane) - 1u))) < need);
+                seen += __popc(em);
+            }
+            sel |= (unsigned long long)take << v;
+        }
     }
-    const int need = topk - gt;                          // how many of the tied entries to keep (lowest index first)
-    int base = 0, seen = 0;
+    // ---- compaction of the kept (logit, column) pairs
+    int base = 0;
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
-        bool take;
-        if (exact) {
-            take = key[v] >= prefix && key[v] != 0ull;
-        } else {
-            const bool eq = key[v] == prefix;
-            const unsigned em = __ballot_sync(0xffffffffu, eq);
-            take = (key[v] > prefix) || (eq && (seen + __popc(em & ((1u << lane) - 1u))) < need);
-            seen += __popc(em);
-        }
+        const bool take = (sel >> v) & 1ull;
         const unsigned tm = __ballot_sync(0xffffffffu, take);
         if (take) {
-            const int pos = base + __popc(tm & ((1u << lane) - 1u));
-            kept[pos] = s[v];
-            kcol[pos] = lane + 32 * v;
+            KeptEntry e; e.p = s[v]; e.col = lane + 32 * v; e.pad = 0;
+            kept[base + __popc(tm & ((1u << lane) - 1u))] = e;
         }
         base += __popc(tm);
     }
@@ -279,8 +340,8 @@ topk_softmax_pv_kernel(const double* __restrict__ S, const double* __restrict__ 
     // softmax over the kept k (mdgat.py:206-207); the row maximum is always among them
     double sum = 0.0;
     for (int t = lane; t < topk; t += 32) {
-        const double e = exp_fast_neg(kept[t] - mx, etab);
-        kept[t] = e;
+        const double e = exp_fast_neg(kept[t].p - mx, etab);
+        kept[t].p = e;
         sum += e;
     }
     sum = warp_sum_d(sum);
@@ -290,21 +351,20 @@ topk_softmax_pv_kernel(const double* __restrict__ S, const double* __restrict__ 
     const double* vl = Vbh + lane;
     int t = 0;
     for (; t + 4 <= topk; t += 4) {
-        const double p0 = kept[t], p1 = kept[t + 1], p2 = kept[t + 2], p3 = kept[t + 3];
-        const int j0 = kcol[t], j1 = kcol[t + 1], j2 = kcol[t + 2], j3 = kcol[t + 3];
-        a0 = fma(p0, __ldg(vl + (long long)j0 * LDH_V), a0);
-        a1 = fma(p1, __ldg(vl + (long long)j1 * LDH_V), a1);
-        a2 = fma(p2, __ldg(vl + (long long)j2 * LDH_V), a2);
-        a3 = fma(p3, __ldg(vl + (long long)j3 * LDH_V), a3);
+        const KeptEntry e0 = kept[t], e1 = kept[t + 1], e2 = kept[t + 2], e3 = kept[t + 3];
+        a0 = fma(e0.p, __ldg(vl + e0.col * LDH_V), a0);
+        a1 = fma(e1.p, __ldg(vl + e1.col * LDH_V), a1);
+        a2 = fma(e2.p, __ldg(vl + e2.col * LDH_V), a2);
+        a3 = fma(e3.p, __ldg(vl + e3.col * LDH_V), a3);
     }
-    for (; t < topk; ++t) a0 = fma(kept[t], __ldg(vl + (long long)kcol[t] * LDH_V), a0);
+    for (; t < topk; ++t) a0 = fma(kept[t].p, __ldg(vl + kept[t].col * LDH_V), a0);
     Out[((long long)b * N + i) * ldo + h * HDIM + lane] = ((a0 + a1) + (a2 + a3)) / sum;
 }
 
 template <int VPT>
 static cudaError_t launch_topk_t(const double* S, const double* V, double* Out, int ldo, int N, int M, int topk,
                                  long long rows, cudaStream_t st) {
-    const size_t smem = (size_t)TK_WARPS * topk * (sizeof(double) + sizeof(int)) + 64 * sizeof(double);
+    const size_t smem = (size_t)TK_WARPS * topk * sizeof(KeptEntry) + 64 * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(topk_softmax_pv_kernel<VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((rows + TK_WARPS - 1) / TK_WARPS);

@@ -151,9 +151,8 @@ cudaError_t gemm_nt(const double* X, int ldx, long long sX, const double* W, int
 cudaError_t attention_side(const double* Q, const double* K, const double* V, double* Out, int ldo,
                            int B, int N, int M, int topk, double* S, cudaStream_t st) {
     if (topk <= 0) return launch_attention_full(Q, K, V, Out, ldo, B, N, M, st);
-    // dense logits q.k / sqrt(32) for every (b, h): batched X W^T with K = 32 (mdgat.py:201)
-    cudaError_t e = gemm_nt(Q, LDH_QK, (long long)N * LDH_QK, K, LDH_QK, (long long)M * LDH_QK,
-                            S, M, (long long)N * M, N, M, HDIM, B * HEADS, 1.0 / sqrt((double)HDIM), st);
+    // dense logits q.k / sqrt(32) for every (b, h) (mdgat.py:201), then exact-k selection
+    cudaError_t e = launch_attention_logits(Q, K, S, B, N, M, st);
     if (e != cudaSuccess) return e;
     return launch_topk_softmax_pv(S, V, Out, ldo, B, N, M, topk, st);
 }
@@ -381,6 +380,7 @@ int mdgat_profile_collect(double* ms, long long* launches, long long* segments, 
 
 int mdgat_measure_fp64_mixed(double* tflops_dmma, double* tflops_dfma) {
     MDGAT_CUDA_OK(measure_fp64_mixed(tflops_dmma, tflops_dfma));
+    MDGAT_CUDA_OK(measure_dmma_tiled(tflops_dfma + 1));
     return MDGAT_OK;
 }
 

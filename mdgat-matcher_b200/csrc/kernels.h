@@ -29,6 +29,8 @@ cudaError_t launch_gemm(const GemmParams& p, int epi, int batch, cudaStream_t st
 // Full-softmax multi-head attention for one side (flash-style, fp64 DMMA).
 cudaError_t launch_attention_full(const double* Q, const double* K, const double* V, double* Out, int ldo,
                                   int B, int N, int M, cudaStream_t st);
+// Dense scaled logits S (B,4,N,M) = q.k / sqrt(32) (the QK^T half of the flash kernel, stored).
+cudaError_t launch_attention_logits(const double* Q, const double* K, double* S, int B, int N, int M, cudaStream_t st);
 // Exact top-k selection + softmax + sparse P.V from materialised logits S (B,4,N,M).
 cudaError_t launch_topk_softmax_pv(const double* S, const double* V, double* Out, int ldo,
                                    int B, int N, int M, int topk, cudaStream_t st);
@@ -62,5 +64,6 @@ cudaError_t launch_knn(const double* x, const double* src, int64_t* idx, int B, 
 
 cudaError_t measure_fp64_peak(double* dmma_tflops, double* dfma_tflops);
 cudaError_t measure_fp64_mixed(double* dmma_tflops, double* dfma_tflops);
+cudaError_t measure_dmma_tiled(double* tflops);
 
 }  // namespace mdgat

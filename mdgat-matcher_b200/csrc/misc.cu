@@ -140,6 +140,56 @@ __global__ void __launch_bounds__(512) dfma_peak_kernel(double* out, int iters, 
     if (s == 123.456) out[0] = s;
 }
 
+// Register-tiled variant: the 4 x 4 outer-product pattern of the GEMM inner loop (distinct A and B
+// fragment registers, 16 accumulator pairs), no memory traffic.
+__global__ void __launch_bounds__(256, 2) dmma_tiled_kernel(double* out, int iters, double a0, double b0) {
+    double c[4][4][2], a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a[i] = a0 + i + threadIdx.x * 1e-9; b[i] = b0 - i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += c[i][j][0] + c[i][j][1];
+    if (s == 123.456) out[0] = s;
+}
+
+cudaError_t measure_dmma_tiled(double* tflops) {
+    int dev = 0, sms = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    double* d = nullptr;
+    if ((e = cudaMalloc(&d, 64)) != cudaSuccess) return e;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    const int iters = 4000, grid = sms * 2;
+    float ms = 0.f;
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(t0);
+        dmma_tiled_kernel<<<grid, 256>>>(d, iters, 1.0000001, 0.5);
+        cudaEventRecord(t1);
+        cudaEventSynchronize(t1);
+        cudaEventElapsedTime(&ms, t0, t1);
+    }
+    *tflops = (double)grid * 8 * iters * 32 * 512.0 / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    cudaFree(d);
+    return cudaGetLastError();
+}
+
 // DMMA and DFMA issued together: 8 DMMA chains + 8 DFMA chains per warp, ratio 1 DMMA : 2 DFMA
 // (about the mix of the attention kernel). Tells whether the two share one issue pipe.
 __global__ void __launch_bounds__(512) mixed_peak_kernel(double* out, int iters, double a0, double b0) {

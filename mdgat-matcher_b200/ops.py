@@ -184,6 +184,7 @@ def measure_fp64_peak():
 
 
 def measure_fp64_mixed():
-    a, b = ctypes.c_double(), ctypes.c_double()
-    _capi.check(_capi.lib.mdgat_measure_fp64_mixed(ctypes.byref(a), ctypes.byref(b)))
-    return a.value, b.value
+    """(DMMA TF/s in a DMMA+DFMA mix, DFMA TF/s in the mix, DMMA TF/s of a register-tiled 4x4 loop)."""
+    a, b = ctypes.c_double(), (ctypes.c_double * 2)()
+    _capi.check(_capi.lib.mdgat_measure_fp64_mixed(ctypes.byref(a), b))
+    return a.value, b[0], b[1]

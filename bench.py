@@ -170,6 +170,7 @@ def main():
     ap.add_argument('--sinkhorn', type=int, default=100)
     ap.add_argument('--cpu-pairs', type=int, default=0, help='pairs in the CPU baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-eager', action='store_true', help='skip the eager-PyTorch fp64 GPU timing of the same math')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -317,6 +318,36 @@ def main():
         cpu_baseline = {'value': v, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
                         'sample': '%d pairs of N=M=%d, L=%d, T=%d (%.1f s), one pair per host thread' % (pairs, N, L, T, dt)}
 
+    # the reference's own op sequence (einsum / softmax / topk / scatter / logsumexp, fp64) as eager PyTorch on
+    # this GPU: the drop-in's differentiable path in eval mode. Context for the >=10x north-star target; the
+    # reference tree itself is not on the GPU box.
+    eager = None
+    if not args.no_eager and world == 1:
+        try:
+            with torch.no_grad():
+                def step_eager():
+                    d = dict(resident)
+                    d['gt_matches0'] = resident['gt_matches0'].clone()
+                    d['gt_matches1'] = resident['gt_matches1'].clone()
+                    return net._forward_torch(d)
+                oe = step_eager()
+                torch.cuda.synchronize()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(3):
+                    oe = step_eager()
+                g1.record()
+                torch.cuda.synchronize()
+                ems = g0.elapsed_time(g1) / 3
+            eager = {'ms_per_step': ems, 'pairs_per_s': B / (ems * 1e-3), 'speedup_of_value': value / (B / (ems * 1e-3)),
+                     'matches_equal': bool(torch.equal(oe['matches0'], out['matches0']) and torch.equal(oe['matches1'], out['matches1'])),
+                     'max_score_diff': float((oe['matching_scores0'] - out['matching_scores0']).abs().max()),
+                     'what': 'eager PyTorch fp64 restatement of the reference op sequence (MDGAT._forward_torch, eval mode), same inputs'}
+            del oe
+            torch.cuda.empty_cache()
+        except Exception as e:          # e.g. out of memory on the dense prob tensors
+            eager = {'error': repr(e)[:200]}
+
     line = {
         'metric': 'keypoint-pairs/sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -331,6 +362,7 @@ def main():
         'clocks': sampler.summary(),
         'roofline': roofline,
         'cpu_baseline': cpu_baseline,
+        'gpu_eager_port': eager,
         'candidate_correspondences_per_s': value * N * N,
     }
     print(json.dumps(line), flush=True)

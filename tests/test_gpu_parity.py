@@ -293,3 +293,37 @@ def test_cfg2_full_size_properties(dev):
     outp = net({k: v[perm].clone() for k, v in data.items()})
     assert torch.equal(outp['matches0'], out['matches0'][perm])
     assert torch.equal(outp['matching_scores1'], out['matching_scores1'][perm])
+
+
+# ----------------------------------------------------------------------------- test.py-style plumbing
+
+def test_reference_eval_loop_plumbing(dev):
+    """The call sequence of /root/reference/test.py:152-214 against the drop-in: fp32 module ->
+    DataParallel -> load_state_dict (fp64 -> fp32) -> per batch net.double().eval(), tensors
+    .cuda(), net(pred), outputs read back with .cpu(). Weights are packed once and survive the
+    repeated .double() calls."""
+    from mdgat_matcher_b200.models.mdgat import MDGAT
+    rec = load_golden('ckpt_L9_duplicates')
+    case = rec['case']
+    net = MDGAT(case_cfg(case))                                   # fp32 parameters (test.py:156)
+    net = torch.nn.DataParallel(net, device_ids=[0])              # test.py:158
+    sd = case_weights(case)
+    net.load_state_dict({'module.' + k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    net.to(dev)
+    blobs = []
+    for it in range(3):
+        net.double().eval()                                       # test.py:193, every iteration
+        pred = {k: torch.from_numpy(v).cuda() for k, v in golden_inputs(rec).items()}
+        pred['sequence'] = ['10']                                 # extra keys are ignored
+        data = net(pred)
+        m0 = data['matches0'].cpu().detach().numpy()
+        assert np.array_equal(m0, rec['matches0'])
+        assert np.abs(data['matching_scores0'].cpu().numpy() - rec['matching_scores0']).max() <= 1e-7
+        blobs.append(net.module._packed[1].data_ptr())
+    assert len(set(blobs)) == 1, 'packed weights were rebuilt although no parameter changed'
+    # a parameter update invalidates the cache
+    with torch.no_grad():
+        net.module.bin_score.add_(0.5)
+    pred = {k: torch.from_numpy(v).cuda() for k, v in golden_inputs(rec).items()}
+    data = net(pred)
+    assert not np.array_equal(data['matching_scores0'].cpu().numpy(), rec['matching_scores0'])

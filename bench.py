@@ -49,10 +49,12 @@ def load_weights(L):
 
 
 def flops_per_pair(N, M, L):
-    """Dense FLOPs of one pair: returns (linear layers incl. encoders/final/score, attention)."""
+    """Dense FLOPs EXECUTED for one pair: (linear layers incl. encoders/final/score, attention).
+    SURVEY.md 8d counts 20*D^2 per point and layer for the reference; the merge conv (2*D^2 of
+    those) is folded into the MLP weights by the packer and never runs, so 18*D^2 are executed."""
     D = 128
     enc = 106880 * (N + M)
-    lin = 2 * L * (20 * D * D) * (N + M)                  # 20*D^2 per point per layer, 2L layers
+    lin = 2 * L * (18 * D * D) * (N + M)
     attn_self = 4 * D * (N * N + M * M)
     attn_cross = 4 * D * (2 * N * M)
     attn = L * (attn_self + attn_cross)

@@ -51,8 +51,9 @@ int mdgat_abi_version(void);
  * (mdgat.py:227) to head-major c' = h*32 + d. Layout (row-major [Cout][Cin]):
  *   kenc: W[32][4] b[32] W[64][32] b[64] W[128][64] b[128] W[128][128] b[128]
  *   denc: W[64][36] (33 inputs zero-padded to 36) b[64] W[128][64] b[128] W[128][128] b[128]
- *   per GNN layer (2L): Wqkv[384][128] bqkv[384] Wmerge[128][128] bmerge[128]
- *                       Wmlp0[256][256] bmlp0[256] Wmlp3[128][256] bmlp3[128]
+ *   per GNN layer (2L): Wqkv[384][128] bqkv[384] Wmlp0'[256][256] bmlp0'[256] Wmlp3[128][256] bmlp3[128]
+ *                       (Wmlp0' = [W1x | W1m Wmerge], bmlp0' = b1 + W1m bmerge: the merge conv of
+ *                        mdgat.py:237 composed with the first MLP conv of mdgat.py:248)
  *   final_proj: W[128][128] b[128];  bin_score (1 double, padded to 4)
  * mdgat_weight_blob_doubles(L) is the total length. Replaces MDGAT.__init__'s parameter
  * registration (mdgat.py:325-360) on the device side. */
@@ -138,6 +139,10 @@ int mdgat_attention_f64(const double* d_Q, const double* d_K, const double* d_V,
  * cluster per pair with the kernel matrix in distributed shared memory (what mdgat_forward
  * uses). d_scratch == NULL: one kernel per half-iteration reading the couplings from L2. */
 size_t mdgat_sinkhorn_scratch_doubles(int B, int N, int M);
+/* After a fused run (synchronises): per pair, whether the pair was redone by the log-domain
+ * fallback (h_flags) and how many iterations ran before the iterate repeated bit for bit --
+ * the fused kernel stops there, every further iteration being a no-op (h_iters <= iters). */
+int mdgat_sinkhorn_read_status(const double* d_scratch, int B, int N, int M, int* h_flags, int* h_iters);
 int mdgat_sinkhorn_f64(double* d_couplings, const double* d_bin_score, double* d_u, double* d_v,
                        int B, int N, int M, int iters, double* d_scratch, void* stream);
 

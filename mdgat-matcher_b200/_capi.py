@@ -56,6 +56,7 @@ def _load():
         'mdgat_encode': (i, [C.POINTER(ForwardIn), i, i, i, i, i, vp, vp, vp, vp]),
         'mdgat_attention_f64': (i, [vp, vp, vp, vp, i, i, i, i, i, vp, vp]),
         'mdgat_sinkhorn_scratch_doubles': (sz, [i, i, i]),
+        'mdgat_sinkhorn_read_status': (i, [vp, i, i, i, C.POINTER(i), C.POINTER(i)]),
         'mdgat_sinkhorn_f64': (i, [vp, vp, vp, vp, i, i, i, i, vp, vp]),
         'mdgat_match_scratch_doubles': (sz, [i, i, i]),
         'mdgat_match_extract': (i, [vp, vp, vp, i, i, i, i, i, d, i, d, vp, vp, C.POINTER(ForwardOut), vp, vp]),

@@ -23,8 +23,7 @@ constexpr size_t A_SMEM = ((size_t)A_STAGES * A_BN * (LDH_QK + LDH_V) + 64) * si
 // (B,4,N,M) tensor (ldo = M) for the exact top-k selection below; no softmax, V is not read.
 template <bool LOGITS_ONLY>
 __global__ void __launch_bounds__(A_THREADS, 3)
-attn_full_kernel(const double* __restrict__ Q, const double* __restrict__ K, const double* __restrict__ V,
-                 double* __restrict__ Out, int ldo, int N, int M, double scale) {
+attn_full_kernel(AttnSides ps, int B, int ldo, double scale) {
     extern __shared__ __align__(16) double smem[];
     double* Ks = smem;                                   // [stage][A_BN][LDH_QK]
     double* Vs = smem + A_STAGES * A_BN * LDH_QK;        // [stage][A_BN][LDH_V]
@@ -32,7 +31,16 @@ attn_full_kernel(const double* __restrict__ Q, const double* __restrict__ K, con
     exp_table_to_shared(etab);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int h = blockIdx.y, b = blockIdx.z;
+    // blockIdx.z = side * B + b: both sides of a GNN layer (they share the layer weights and are
+    // independent, mdgat.py:270) run in ONE launch, which also packs the waves better
+    const int side = blockIdx.z >= B ? 1 : 0;
+    const int h = blockIdx.y, b = blockIdx.z - side * B;
+    const int N = ps.N[side], M = ps.M[side];
+    if ((int)blockIdx.x * A_BM >= N) return;
+    const double* __restrict__ Q = ps.Q[side];
+    const double* __restrict__ K = ps.K[side];
+    const double* __restrict__ V = ps.V[side];
+    double* __restrict__ Out = ps.Out[side];
     const long long bh = (long long)b * HEADS + h;
     const double* Qbh = Q + bh * N * LDH_QK;
     const double* Kbh = K + bh * M * LDH_QK;
@@ -60,33 +68,42 @@ attn_full_kernel(const double* __restrict__ Q, const double* __restrict__ K, con
 
     const int nchunks = (M + A_BN - 1) / A_BN;
 
-    // K/V chunks are contiguous in the head-major buffers (padded rows included): flat copy.
+    // K/V chunks are contiguous in the head-major buffers (padded rows included): ONE bulk copy
+    // (TMA engine, cp.async.bulk -> SASS UBLKCP) per operand and chunk, issued by a single thread
+    // and completed on an mbarrier; the SM issues no per-thread copy instructions.
+    __shared__ __align__(8) uint64_t full_bar[A_STAGES];
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < A_STAGES; ++i) mbar_init(&full_bar[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
     auto load_chunk = [&](int c, int buf) {
         const int j0 = c * A_BN;
         const int rows = min(A_BN, M - j0);
-        const double* ksrc = Kbh + (long long)j0 * LDH_QK;
-        const double* vsrc = Vbh + (long long)j0 * LDH_V;
         double* kd = Ks + buf * A_BN * LDH_QK;
         double* vd = Vs + buf * A_BN * LDH_V;
-        const int kvalid = rows * LDH_QK / 2, vvalid = rows * LDH_V / 2;     // 16-byte units
-        for (int i = tid; i < A_BN * LDH_QK / 2; i += A_THREADS)
-            cp_async16(kd + 2 * i, i < kvalid ? ksrc + 2 * i : ksrc, i < kvalid);
-        if (!LOGITS_ONLY)
-            for (int i = tid; i < A_BN * LDH_V / 2; i += A_THREADS)
-                cp_async16(vd + 2 * i, i < vvalid ? vsrc + 2 * i : vsrc, i < vvalid);
+        if (tid == 0) {
+            const unsigned kbytes = (unsigned)(rows * LDH_QK * sizeof(double));
+            const unsigned vbytes = LOGITS_ONLY ? 0u : (unsigned)(rows * LDH_V * sizeof(double));
+            mbar_expect_tx(&full_bar[buf], kbytes + vbytes);
+            bulk_g2s(kd, Kbh + (long long)j0 * LDH_QK, kbytes, &full_bar[buf]);
+            if (!LOGITS_ONLY) bulk_g2s(vd, Vbh + (long long)j0 * LDH_V, vbytes, &full_bar[buf]);
+        }
+        if (rows < A_BN) {
+            // ragged last chunk: rows the copy does not write must not hold stale NaN/Inf bit patterns
+            // (their probabilities are exactly 0, and 0 * NaN would poison the message)
+            for (int i = rows * LDH_QK + tid; i < A_BN * LDH_QK; i += A_THREADS) kd[i] = 0.0;
+            if (!LOGITS_ONLY)
+                for (int i = rows * LDH_V + tid; i < A_BN * LDH_V; i += A_THREADS) vd[i] = 0.0;
+        }
     };
 
     load_chunk(0, 0);
-    cp_async_commit();
     for (int c = 0; c < nchunks; ++c) {
-        if (c + 1 < nchunks) {
-            load_chunk(c + 1, (c + 1) & 1);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
+        if (c + 1 < nchunks) load_chunk(c + 1, (c + 1) & 1);
+        mbar_wait(&full_bar[c & 1], (unsigned)((c >> 1) & 1));
+        if (c == 0) __syncthreads();        // zero-filled tail rows of a ragged first chunk
         const double* ks_ = Ks + (c & 1) * A_BN * LDH_QK;
         const double* vs_ = Vs + (c & 1) * A_BN * LDH_V;
 
@@ -190,25 +207,31 @@ attn_full_kernel(const double* __restrict__ Q, const double* __restrict__ K, con
     }
 }
 
-cudaError_t launch_attention_full(const double* Q, const double* K, const double* V, double* Out, int ldo,
-                                  int B, int N, int M, cudaStream_t st) {
-    if (B <= 0 || N <= 0 || M <= 0) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(attn_full_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM);
-    if (e != cudaSuccess) return e;
-    dim3 grid((N + A_BM - 1) / A_BM, HEADS, B);
-    attn_full_kernel<false><<<grid, A_THREADS, A_SMEM, st>>>(Q, K, V, Out, ldo, N, M, 1.0 / sqrt((double)HDIM));
+static cudaError_t launch_attn(const AttnSides& ps, int B, int nsides, int ldo, bool logits_only, cudaStream_t st) {
+    int nmax = 0;
+    for (int s = 0; s < nsides; ++s) nmax = ps.N[s] > nmax ? ps.N[s] : nmax;
+    if (B <= 0 || nmax <= 0) return cudaSuccess;
+    dim3 grid((nmax + A_BM - 1) / A_BM, HEADS, nsides * B);
+    const double scale = 1.0 / sqrt((double)HDIM);
+    cudaError_t e;
+    if (logits_only) {
+        if ((e = cudaFuncSetAttribute(attn_full_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM)) != cudaSuccess) return e;
+        attn_full_kernel<true><<<grid, A_THREADS, A_SMEM, st>>>(ps, B, ldo, scale);
+    } else {
+        if ((e = cudaFuncSetAttribute(attn_full_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM)) != cudaSuccess) return e;
+        attn_full_kernel<false><<<grid, A_THREADS, A_SMEM, st>>>(ps, B, ldo, scale);
+    }
     count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_attention_logits(const double* Q, const double* K, double* S, int B, int N, int M, cudaStream_t st) {
-    if (B <= 0 || N <= 0 || M <= 0) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(attn_full_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM);
-    if (e != cudaSuccess) return e;
-    dim3 grid((N + A_BM - 1) / A_BM, HEADS, B);
-    attn_full_kernel<true><<<grid, A_THREADS, A_SMEM, st>>>(Q, K, nullptr, S, M, N, M, 1.0 / sqrt((double)HDIM));
-    count_launch();
-    return cudaGetLastError();
+cudaError_t launch_attention_full(const AttnSides& ps, int B, int nsides, int ldo, cudaStream_t st) {
+    return launch_attn(ps, B, nsides, ldo, false, st);
+}
+
+// Out[side] receives the dense scaled logits (B,4,N,M) of that side
+cudaError_t launch_attention_logits(const AttnSides& ps, int B, int nsides, cudaStream_t st) {
+    return launch_attn(ps, B, nsides, 0, true, st);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -59,11 +59,11 @@ namespace {
 
 // ---- packed weight blob offsets (doubles); must match mdgat_matcher_b200/packing.py ----
 struct EncOffsets { size_t w[4], b[4]; };
-struct LayerOffsets { size_t wqkv, bqkv, wm, bm, w1, b1, w2, b2; };
+struct LayerOffsets { size_t wqkv, bqkv, w1, b1, w2, b2; };
 
 constexpr size_t KENC_DIMS[5] = {4, 32, 64, 128, 128};
 constexpr size_t DENC_DIMS[4] = {36, 64, 128, 128};
-constexpr size_t LAYER_DOUBLES = 384 * 128 + 384 + 128 * 128 + 128 + 256 * 256 + 256 + 128 * 256 + 128;
+constexpr size_t LAYER_DOUBLES = 384 * 128 + 384 + 256 * 256 + 256 + 128 * 256 + 128;
 
 struct BlobLayout {
     EncOffsets kenc, denc;
@@ -80,7 +80,6 @@ struct BlobLayout {
     LayerOffsets layer(int l) const {
         LayerOffsets r; size_t o = layers0 + (size_t)l * LAYER_DOUBLES;
         r.wqkv = o; o += 384 * 128; r.bqkv = o; o += 384;
-        r.wm = o; o += 128 * 128; r.bm = o; o += 128;
         r.w1 = o; o += 256 * 256; r.b1 = o; o += 256;
         r.w2 = o; o += 128 * 256; r.b2 = o; o += 128;
         return r;
@@ -116,8 +115,8 @@ Workspace carve(char* base, int B, int N, int M, bool need_logits) {
     w.Mg = take(R * LDX);
     w.Hd = take(R * LDHID);
     w.MD = take(R * LDX);
-    const size_t nm = (size_t)(N > M ? N : M);
-    w.S = take(need_logits ? (size_t)B * HEADS * nm * nm : 0);   // self layers need N*N and M*M
+    // logits of both sides at once: self layers need N*N + M*M, cross layers 2*N*M (never more)
+    w.S = take(need_logits ? (size_t)B * HEADS * ((size_t)N * N + (size_t)M * M) : 0);
     w.C = take((size_t)B * (N + 1) * (M + 1));
     w.u = take((size_t)B * (N + 1));
     w.v = take((size_t)B * (M + 1));
@@ -148,13 +147,20 @@ cudaError_t gemm_nt(const double* X, int ldx, long long sX, const double* W, int
     return launch_gemm(p, EPI_PLAIN, batch, st);
 }
 
-cudaError_t attention_side(const double* Q, const double* K, const double* V, double* Out, int ldo,
-                           int B, int N, int M, int topk, double* S, cudaStream_t st) {
-    if (topk <= 0) return launch_attention_full(Q, K, V, Out, ldo, B, N, M, st);
-    // dense logits q.k / sqrt(32) for every (b, h) (mdgat.py:201), then exact-k selection
-    cudaError_t e = launch_attention_logits(Q, K, S, B, N, M, st);
+// Messages of one GNN layer. nsides = 2: side 0 and side 1 in the same launches.
+cudaError_t attention_layer(const AttnSides& ps, int B, int nsides, int ldo, int topk, double* S, cudaStream_t st) {
+    if (topk <= 0) return launch_attention_full(ps, B, nsides, ldo, st);
+    // dense logits q.k / sqrt(32) for every (b, h) (mdgat.py:201), then exact-k selection per row
+    AttnSides lg = ps;
+    double* sp = S;
+    for (int s = 0; s < nsides; ++s) { lg.Out[s] = sp; sp += (size_t)B * HEADS * ps.N[s] * ps.M[s]; }
+    cudaError_t e = launch_attention_logits(lg, B, nsides, st);
     if (e != cudaSuccess) return e;
-    return launch_topk_softmax_pv(S, V, Out, ldo, B, N, M, topk, st);
+    for (int s = 0; s < nsides; ++s) {
+        e = launch_topk_softmax_pv(lg.Out[s], ps.V[s], ps.Out[s], ldo, B, ps.N[s], ps.M[s], topk, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t encode(const mdgat_forward_in* in, int B, int N, int M, int in_dtype, int score_dtype,
@@ -243,13 +249,14 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const m
         MDGAT_CUDA_OK(launch_gemm(p, EPI_QKV, 1, st));
         prof_mark(k > 0 ? ST_ATTN_TOPK : ST_ATTN_FULL, st);
         // messages: side 0 reads side (cross ? 1 : 0), side 1 the other way round (mdgat.py:263-266)
-        MDGAT_CUDA_OK(attention_side(Q0, cross ? K1 : K0, cross ? V1 : V0, w.Msg, LDX, B, N, cross ? M : N, k, w.S, st));
-        MDGAT_CUDA_OK(attention_side(Q1, cross ? K0 : K1, cross ? V0 : V1, w.Msg + (size_t)R0 * LDX, LDX, B, M, cross ? N : M, k, w.S, st));
+        AttnSides ps;
+        ps.Q[0] = Q0; ps.K[0] = cross ? K1 : K0; ps.V[0] = cross ? V1 : V0; ps.Out[0] = w.Msg; ps.N[0] = N; ps.M[0] = cross ? M : N;
+        ps.Q[1] = Q1; ps.K[1] = cross ? K0 : K1; ps.V[1] = cross ? V0 : V1; ps.Out[1] = w.Msg + (size_t)R0 * LDX; ps.N[1] = M; ps.M[1] = cross ? N : M;
+        MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st));
         prof_mark(ST_GEMM, st);
-        // merge conv (mdgat.py:237)
-        MDGAT_CUDA_OK(linear(w.Msg, LDX, DMODEL, nullptr, 0, 0, Wt + lo.wm, DMODEL, Wt + lo.bm, nullptr, 0, w.Mg, LDX, R, DMODEL, 1.0, 0, st));
+        // the merge conv (mdgat.py:237) is folded into the first MLP conv by the weight packer
         // mlp(cat[x, message]) : 256 -> 256 (BN folded, ReLU) -> 128, then the residual (mdgat.py:248, :274)
-        MDGAT_CUDA_OK(linear(w.X, LDX, DMODEL, w.Mg, LDX, DMODEL, Wt + lo.w1, 2 * DMODEL, Wt + lo.b1, nullptr, 0, w.Hd, LDHID, R, 2 * DMODEL, 1.0, 1, st));
+        MDGAT_CUDA_OK(linear(w.X, LDX, DMODEL, w.Msg, LDX, DMODEL, Wt + lo.w1, 2 * DMODEL, Wt + lo.b1, nullptr, 0, w.Hd, LDHID, R, 2 * DMODEL, 1.0, 1, st));
         MDGAT_CUDA_OK(linear(w.Hd, LDHID, 2 * DMODEL, nullptr, 0, 0, Wt + lo.w2, 2 * DMODEL, Wt + lo.b2, w.X, LDX, w.X, LDX, R, DMODEL, 1.0, 0, st));
     }
     // final_proj (mdgat.py:397) and scores = mdesc0^T mdesc1 / sqrt(128) (:430-431) into the couplings
@@ -310,11 +317,22 @@ int mdgat_attention_f64(const double* d_Q, const double* d_K, const double* d_V,
     MDGAT_REQUIRE(topk <= M, "selected index k out of range (k=%d, M=%d)", topk, M);
     MDGAT_REQUIRE(topk <= 0 || (d_logits != nullptr && M <= 2048), "mdgat_attention_f64: top-k needs a logits scratch and M <= 2048");
     MDGAT_REQUIRE((ldo % 2) == 0, "mdgat_attention_f64: ldo must be even");
-    MDGAT_CUDA_OK(attention_side(d_Q, d_K, d_V, d_Out, ldo, B, N, M, topk, d_logits, reinterpret_cast<cudaStream_t>(stream)));
+    AttnSides ps;
+    memset(&ps, 0, sizeof(ps));
+    ps.Q[0] = d_Q; ps.K[0] = d_K; ps.V[0] = d_V; ps.Out[0] = d_Out; ps.N[0] = N; ps.M[0] = M;
+    MDGAT_CUDA_OK(attention_layer(ps, B, 1, ldo, topk, d_logits, reinterpret_cast<cudaStream_t>(stream)));
     return MDGAT_OK;
 }
 
 size_t mdgat_sinkhorn_scratch_doubles(int B, int N, int M) { return sinkhorn_scratch_doubles(B, N, M); }
+
+int mdgat_sinkhorn_read_status(const double* d_scratch, int B, int N, int M, int* h_flags, int* h_iters) {
+    const size_t ldk = (size_t)((M + 1) & ~1);
+    const int* d = reinterpret_cast<const int*>(d_scratch + (size_t)B * (N + 1) * ldk);
+    MDGAT_CUDA_OK(cudaMemcpy(h_flags, d, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost));
+    MDGAT_CUDA_OK(cudaMemcpy(h_iters, d + B, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost));
+    return MDGAT_OK;
+}
 
 int mdgat_sinkhorn_f64(double* d_couplings, const double* d_bin_score, double* d_u, double* d_v,
                        int B, int N, int M, int iters, double* d_scratch, void* stream) {

@@ -50,17 +50,18 @@ DEVINL void mbar_arrive(uint64_t* bar) {
     unsigned s = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(s) : "memory");
 }
-DEVINL void mbar_wait(uint64_t* bar, unsigned parity) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+DEVINL bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(bar), ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" :: "r"(s), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(s), "r"(parity) : "memory");
+    return ok != 0;
+}
+DEVINL void mbar_wait(uint64_t* bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) {}
 }
 // bytes must be a multiple of 16; both addresses 16-byte aligned.
 DEVINL void bulk_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar) {

@@ -129,10 +129,13 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_f64_kernel(GemmParams p, in
                 for (int j = 0; j < 2; ++j) {
                     const int col = n0 + warp * 16 + j * 8 + 2 * qc;
                     if (col >= p.Nout) continue;
-                    double y0 = acc[i][j][0] * p.scale, y1 = acc[i][j][1] * p.scale;
+                    // the epilogue competes with the other warps' DMMAs for the FP64 pipe: keep its
+                    // FP64 instruction count minimal (no multiply when scale == 1, ReLU on the sign bit)
+                    double y0 = acc[i][j][0], y1 = acc[i][j][1];
+                    if (p.scale != 1.0) { y0 *= p.scale; y1 *= p.scale; }
                     const bool has1 = (col + 1 < p.Nout);
                     if (p.bias) { y0 += p.bias[col]; if (has1) y1 += p.bias[col + 1]; }
-                    if (p.relu) { y0 = fmax(y0, 0.0); y1 = fmax(y1, 0.0); }
+                    if (p.relu) { y0 = __double2hiint(y0) < 0 ? 0.0 : y0; y1 = __double2hiint(y1) < 0 ? 0.0 : y1; }
                     if (EPI == EPI_PLAIN) {
                         if (p.Res) {
                             const double* rr = p.Res + (long long)row * p.ldres + col;

@@ -26,11 +26,16 @@ struct GemmParams {
 };
 cudaError_t launch_gemm(const GemmParams& p, int epi, int batch, cudaStream_t st);
 
-// Full-softmax multi-head attention for one side (flash-style, fp64 DMMA).
-cudaError_t launch_attention_full(const double* Q, const double* K, const double* V, double* Out, int ldo,
-                                  int B, int N, int M, cudaStream_t st);
+// Per-side operands of one attention launch (side 0 and side 1 of a GNN layer share one grid).
+struct AttnSides {
+    const double* Q[2]; const double* K[2]; const double* V[2];   // head-major (B,4,n,36/36/34)
+    double* Out[2];                                              // message rows (B*N) x ldo, or logits (B,4,N,M)
+    int N[2], M[2];                                              // queries / sources of that side
+};
+// Full-softmax multi-head attention (flash-style, fp64 DMMA), nsides in {1, 2}.
+cudaError_t launch_attention_full(const AttnSides& ps, int B, int nsides, int ldo, cudaStream_t st);
 // Dense scaled logits S (B,4,N,M) = q.k / sqrt(32) (the QK^T half of the flash kernel, stored).
-cudaError_t launch_attention_logits(const double* Q, const double* K, double* S, int B, int N, int M, cudaStream_t st);
+cudaError_t launch_attention_logits(const AttnSides& ps, int B, int nsides, cudaStream_t st);
 // Exact top-k selection + softmax + sparse P.V from materialised logits S (B,4,N,M).
 cudaError_t launch_topk_softmax_pv(const double* S, const double* V, double* Out, int ldo,
                                    int B, int N, int M, int topk, cudaStream_t st);

@@ -162,7 +162,8 @@ sinkhorn_fused_kernel(const double* __restrict__ C, double* __restrict__ Kg, dou
     double* cmx = as + RSp;                 // [RSp]   row maxima of C
     double* kd = cmx + RSp;                 // [RSp]   K of the dustbin column
     double* red = kd + RSp;                 // [SKF_NREG][SKF_WARPS]
-    double* Ks = red + SKF_NREG * SKF_WARPS;   // [rows_smem][ldk]
+    int* chg = reinterpret_cast<int*>(red + SKF_NREG * SKF_WARPS);   // [8] "changed" flags of the cluster (+ pad)
+    double* Ks = red + SKF_NREG * SKF_WARPS + 4;   // [rows_smem][ldk]
 
     const int r0 = crank * RS;
     const int nrows = max(0, min(RS, R1 - r0));
@@ -199,6 +200,7 @@ sinkhorn_fused_kernel(const double* __restrict__ C, double* __restrict__ Kg, dou
         if (q < n_reg && tid < M) kreg[q] = exp(Cb[(long long)(r0 + n_smem + q) * C1 + tid] - cmx[n_smem + q]);
     }
 
+    int it_done = 0;
     for (int it = 0; it < iters; ++it) {
         const int buf = it & 1;
         const double bM = bs[M];
@@ -269,18 +271,44 @@ sinkhorn_fused_kernel(const double* __restrict__ C, double* __restrict__ Kg, dou
             if (lane == 0) pb[M] = a;
         }
         cluster.sync();
-        // ---- b_j = nu_j / sum of the 8 partials (same order in every CTA -> identical b everywhere)
-        for (int j = tid; j < C1; j += SKF_THREADS) {
-            double pv[SKF_CLUSTER];
-#pragma unroll
-            for (int c = 0; c < SKF_CLUSTER; ++c) pv[c] = cluster.map_shared_rank(part, c)[buf * ldv + j];
-            const double tot = ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
-            bs[j] = ((j < M) ? nu_reg : nu_bin) / tot;
+        // ---- reduce-scatter + broadcast through distributed shared memory: this CTA sums the 8
+        // partials of its own 1/8 of the columns (8 adjacent lanes fetch one partial each), forms
+        // b_j = nu_j / total and stores it into the b vector of every CTA of the cluster.
+        bool changed = false;
+        {
+            const int CS = (C1 + SKF_CLUSTER - 1) / SKF_CLUSTER;
+            const int c0 = crank * CS;
+            const int ncols = max(0, min(CS, C1 - c0));
+            const int src = tid & (SKF_CLUSTER - 1);
+            for (int base = 0; base < ncols * SKF_CLUSTER; base += SKF_THREADS) {
+                const int idx = base + tid;
+                const int j = c0 + (idx >> 3);
+                const bool ok = idx < ncols * SKF_CLUSTER;
+                const double old = ok ? bs[j] : 0.0;          // column j is written only by this CTA's lanes, below
+                double pv = ok ? cluster.map_shared_rank(part, src)[buf * ldv + j] : 0.0;
+                pv += shfl_xor_d(pv, 1);
+                pv += shfl_xor_d(pv, 2);
+                pv += shfl_xor_d(pv, 4);
+                if (ok) {
+                    const double nb = ((j < M) ? nu_reg : nu_bin) / pv;
+                    changed |= (__double_as_longlong(nb) != __double_as_longlong(old));
+                    cluster.map_shared_rank(bs, src)[j] = nb;
+                }
+            }
         }
-        __syncthreads();
+        // Exact early exit: the iteration is a deterministic map, so once b repeats bit for bit
+        // every further iteration is a no-op. Each CTA publishes "one of my columns changed" to all
+        // peers; everybody sees the same eight flags after the barrier and leaves together.
+        const int any_local = __syncthreads_or(changed ? 1 : 0);
+        if (tid < SKF_CLUSTER) cluster.map_shared_rank(chg, tid)[crank] = any_local;
+        cluster.sync();
+        ++it_done;
+        int any = 0;
+#pragma unroll
+        for (int c = 0; c < SKF_CLUSTER; ++c) any |= chg[c];
+        if (!any) break;
     }
-    // peers may still be reading this CTA's partials of the last iteration
-    cluster.sync();
+    if (crank == 0 && tid == 0) flags[gridDim.x / SKF_CLUSTER + b] = it_done;
     // u_i = log a_i - c_i, v_j = log b_j
     for (int r = tid; r < nrows; r += SKF_THREADS) u_out[(long long)b * R1 + r0 + r] = iters > 0 ? log(as[r]) - cmx[r] : 0.0;
     if (crank == 0)
@@ -328,7 +356,7 @@ sinkhorn_safe_kernel(const double* __restrict__ C, double* __restrict__ u, doubl
 
 size_t sinkhorn_scratch_doubles(int B, int N, int M) {
     const size_t ldk = (size_t)((M + 1) & ~1);
-    return (size_t)B * (N + 1) * ldk + (size_t)(B + 1) / 2 + 2;      // K scratch + per-pair flags (ints)
+    return (size_t)B * (N + 1) * ldk + (size_t)B + 2;      // K scratch + per-pair flags and iteration counts (ints)
 }
 
 cudaError_t launch_sinkhorn_fused(const double* C, double* u, double* v, double* scratch, int B, int N, int M,
@@ -342,13 +370,13 @@ cudaError_t launch_sinkhorn_fused(const double* C, double* u, double* v, double*
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
-    const size_t fixed = ((size_t)3 * ldv + 3 * (size_t)((RS + 3) & ~3) + SKF_WARPS * SKF_NREG) * sizeof(double);
+    const size_t fixed = ((size_t)3 * ldv + 3 * (size_t)((RS + 3) & ~3) + SKF_WARPS * SKF_NREG + 4) * sizeof(double);
     if (fixed + 1024 > (size_t)max_smem) return cudaErrorInvalidValue;
     int rows_smem = (int)(((size_t)max_smem - fixed) / ((size_t)ldk * sizeof(double)));
     if (rows_smem > RS) rows_smem = RS;
     const int nreg = (M <= SKF_THREADS) ? SKF_NREG : 0;
     const size_t smem = fixed + (size_t)rows_smem * ldk * sizeof(double);
-    if ((e = cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)B, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(flags, 0, sizeof(int) * 2 * (size_t)B, st)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(sinkhorn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

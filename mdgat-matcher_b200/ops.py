@@ -88,7 +88,7 @@ def attention(q, k, v, topk=None):
     return msg.permute(0, 3, 2, 1).reshape(B, 128, N).contiguous()  # channel c = d*4 + h
 
 
-def sinkhorn(scores, bin_score, iters, fused=True):
+def sinkhorn(scores, bin_score, iters, fused=True, return_status=False):
     """scores (B,N,M) -> (couplings, u, v) with Z = couplings + u[:, :, None] + v[:, None, :] - norm
     = log_optimal_transport(scores, bin_score, iters). fused=False uses one launch per half-iteration."""
     _need_cuda(scores)
@@ -104,6 +104,10 @@ def sinkhorn(scores, bin_score, iters, fused=True):
         _capi.check(_capi.lib.mdgat_sinkhorn_f64(C.data_ptr(), alpha.data_ptr(), u.data_ptr(), v.data_ptr(),
                                                  B, N, M, int(iters), scratch.data_ptr() if fused else None,
                                                  _stream(dev)))
+        if return_status and fused:
+            fl, it = (ctypes.c_int * B)(), (ctypes.c_int * B)()
+            _capi.check(_capi.lib.mdgat_sinkhorn_read_status(scratch.data_ptr(), B, N, M, fl, it))
+            return C, u, v, {'fallback': list(fl), 'iterations': list(it)}
     return C, u, v
 
 

@@ -3,6 +3,9 @@
 * eval-mode BatchNorm1d is folded into the preceding 1x1 conv (MLP(), mdgat.py:34-46):
   W' = W * g / sqrt(var + 1e-5), b' = (b - mean) * g / sqrt(var + 1e-5) + beta;
 * the three projections proj.0/1/2 are stacked into one [384][128] matrix;
+* the merge conv (mdgat.py:237) is composed with the message half of the first MLP conv
+  (mdgat.py:248): W1 [x ; Wm msg + bm] = W1x x + (W1m Wm) msg + W1m bm, an exact algebraic
+  identity evaluated in float64, so the 128x128 merge GEMM never runs;
 * MultiHeadedAttention views channels as (dim=32, heads=4), i.e. channel c = d*4 + h
   (mdgat.py:227); q/k/v output rows and merge input columns are permuted once to the
   head-major order c' = h*32 + d the kernels use;
@@ -16,7 +19,7 @@ import torch
 BN_EPS = 1e-5
 KENC_DIMS = (4, 32, 64, 128, 128)
 DENC_DIMS = (36, 64, 128, 128)
-LAYER_DOUBLES = 384 * 128 + 384 + 128 * 128 + 128 + 256 * 256 + 256 + 128 * 256 + 128
+LAYER_DOUBLES = 384 * 128 + 384 + 256 * 256 + 256 + 128 * 256 + 128
 
 
 def blob_doubles(L):
@@ -71,10 +74,14 @@ def pack_state_dict(sd, L):
             ws.append(w[perm])
             bs.append(b[perm])
         parts.extend([torch.cat(ws, 0).reshape(-1), torch.cat(bs, 0)])
-        w, b = _conv(sd, p + 'attn.merge')
-        parts.extend([w[:, perm].reshape(-1), b])
+        # merge conv folded into the first MLP conv: mlp.0([x ; merge(msg)]) =
+        #   W1x x + (W1m Wm) msg + (b1 + W1m bm)  -- one 128x128 GEMM per layer and side disappears
+        wm, bm = _conv(sd, p + 'attn.merge')
         w, b = _conv(sd, p + 'mlp.0')
         w, b = _fold_bn(w, b, sd, p + 'mlp.1')
+        w1m = w[:, 128:]
+        w = torch.cat([w[:, :128], w1m @ wm[:, perm]], dim=1)
+        b = b + w1m @ bm
         parts.extend([w.reshape(-1), b])
         w, b = _conv(sd, p + 'mlp.3')
         parts.extend([w.reshape(-1), b])

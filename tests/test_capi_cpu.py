@@ -64,7 +64,6 @@ def test_packed_blob_reproduces_reference_layers_on_cpu():
         off += n
         return a.reshape(shape) if shape else a
     wqkv, bqkv = take(384 * 128, (384, 128)), take(384)
-    wm, bm = take(128 * 128, (128, 128)), take(128)
     w1, b1 = take(256 * 256, (256, 256)), take(256)
     w2, b2 = take(128 * 256, (128, 256)), take(128)
     rng = np.random.default_rng(0)
@@ -77,8 +76,7 @@ def test_packed_blob_reproduces_reference_layers_on_cpu():
         s = q[:, h * 32:(h + 1) * 32] @ k[:, h * 32:(h + 1) * 32].T / np.sqrt(32)
         p = np.exp(s - s.max(1, keepdims=True)); p /= p.sum(1, keepdims=True)
         msg[:, h * 32:(h + 1) * 32] = p @ v[:, h * 32:(h + 1) * 32]
-    mg = msg @ wm.T + bm
-    hd = np.maximum(np.concatenate([xr, mg], 1) @ w1.T + b1, 0)
+    hd = np.maximum(np.concatenate([xr, msg], 1) @ w1.T + b1, 0)      # merge conv is folded into w1 / b1
     delta = hd @ w2.T + b2
     assert np.abs(delta.T - want[0]).max() < 1e-11
 

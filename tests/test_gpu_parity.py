@@ -118,6 +118,20 @@ def test_sinkhorn_vs_oracle(dev, N, M, iters, fused):
     assert np.abs(got - want).max() < 1e-10
 
 
+def test_sinkhorn_early_exit_is_exact(dev):
+    """The fused kernel stops once the iterate repeats bit for bit; asking for more iterations than
+    that must give bit-identical potentials, and a pair that needs every iteration must run them all."""
+    from mdgat_matcher_b200 import ops
+    rng = np.random.default_rng(4)
+    scores = rng.normal(size=(2, 100, 90)) * 2
+    C1, u1, v1, st1 = ops.sinkhorn(_t(scores, dev), 1.5, 400, return_status=True)
+    C2, u2, v2, st2 = ops.sinkhorn(_t(scores, dev), 1.5, 800, return_status=True)
+    assert torch.equal(u1, u2) and torch.equal(v1, v2)
+    assert st1['iterations'] == st2['iterations'] and max(st1['iterations']) < 400
+    _, _, _, st3 = ops.sinkhorn(_t(scores, dev), 1.5, 5, return_status=True)
+    assert st3['iterations'] == [5, 5]
+
+
 def test_sinkhorn_fused_falls_back_on_ill_conditioned_pairs(dev):
     """Row ranges beyond the factored form's safe bound (here ~ +-2000, like the out-of-distribution
     logits of SURVEY.md fact 9) are redone by the plain log-domain kernel, pair by pair."""

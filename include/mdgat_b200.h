@@ -48,7 +48,9 @@ int mdgat_abi_version(void);
 /* ---- packed weights ------------------------------------------------------------------
  * One float64 blob, BatchNorm folded into the preceding 1x1 conv, q/k/v output channels
  * and merge input channels permuted from the reference's interleaved c = d*4 + h
- * (mdgat.py:227) to head-major c' = h*32 + d. Layout (row-major [Cout][Cin]):
+ * (mdgat.py:227) to head-major c' = h*32 + d. Every W[Cout][Cin] below is stored TILE-MAJOR:
+ * [ceil(Cout/128)][ceil(Cin/32)][128][36] doubles, zero padded, so that one (128 x 32) GEMM stage is a
+ * contiguous block for a single TMA bulk copy (packing.tile_weight). Order:
  *   kenc: W[32][4] b[32] W[64][32] b[64] W[128][64] b[128] W[128][128] b[128]
  *   denc: W[64][36] (33 inputs zero-padded to 36) b[64] W[128][64] b[128] W[128][128] b[128]
  *   per GNN layer (2L): Wqkv[384][128] bqkv[384] Wmlp0'[256][256] bmlp0'[256] Wmlp3[128][256] bmlp3[128]

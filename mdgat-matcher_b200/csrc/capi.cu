@@ -63,25 +63,26 @@ struct LayerOffsets { size_t wqkv, bqkv, w1, b1, w2, b2; };
 
 constexpr size_t KENC_DIMS[5] = {4, 32, 64, 128, 128};
 constexpr size_t DENC_DIMS[4] = {36, 64, 128, 128};
-constexpr size_t LAYER_DOUBLES = 384 * 128 + 384 + 256 * 256 + 256 + 128 * 256 + 128;
+constexpr size_t tiled(size_t nout, size_t k) { return ((nout + 127) / 128) * ((k + 31) / 32) * 128 * 36; }
+constexpr size_t LAYER_DOUBLES = tiled(384, 128) + 384 + tiled(256, 256) + 256 + tiled(128, 256) + 128;
 
 struct BlobLayout {
     EncOffsets kenc, denc;
     size_t layers0, wf, bf, bin, total;
     explicit BlobLayout(int L) {
         size_t o = 0;
-        for (int i = 0; i < 4; ++i) { kenc.w[i] = o; o += KENC_DIMS[i + 1] * KENC_DIMS[i]; kenc.b[i] = o; o += KENC_DIMS[i + 1]; }
-        for (int i = 0; i < 3; ++i) { denc.w[i] = o; o += DENC_DIMS[i + 1] * DENC_DIMS[i]; denc.b[i] = o; o += DENC_DIMS[i + 1]; }
+        for (int i = 0; i < 4; ++i) { kenc.w[i] = o; o += tiled(KENC_DIMS[i + 1], KENC_DIMS[i]); kenc.b[i] = o; o += KENC_DIMS[i + 1]; }
+        for (int i = 0; i < 3; ++i) { denc.w[i] = o; o += tiled(DENC_DIMS[i + 1], DENC_DIMS[i]); denc.b[i] = o; o += DENC_DIMS[i + 1]; }
         layers0 = o; o += (size_t)(2 * L) * LAYER_DOUBLES;
-        wf = o; o += 128 * 128; bf = o; o += 128;
+        wf = o; o += tiled(128, 128); bf = o; o += 128;
         bin = o; o += 4;
         total = o;
     }
     LayerOffsets layer(int l) const {
         LayerOffsets r; size_t o = layers0 + (size_t)l * LAYER_DOUBLES;
-        r.wqkv = o; o += 384 * 128; r.bqkv = o; o += 384;
-        r.w1 = o; o += 256 * 256; r.b1 = o; o += 256;
-        r.w2 = o; o += 128 * 256; r.b2 = o; o += 128;
+        r.wqkv = o; o += tiled(384, 128); r.bqkv = o; o += 384;
+        r.w1 = o; o += tiled(256, 256); r.b1 = o; o += 256;
+        r.w2 = o; o += tiled(128, 256); r.b2 = o; o += 128;
         return r;
     }
 };
@@ -126,11 +127,13 @@ Workspace carve(char* base, int B, int N, int M, bool need_logits) {
     return w;
 }
 
+// w_tiled: W is a tile-major blob weight (TMA bulk staging); otherwise row-major [Nout][ldw]
 cudaError_t linear(const double* X0, int ld0, int K0, const double* X1, int ld1, int K1,
                    const double* W, int ldw, const double* bias, const double* Res, int ldres,
-                   double* Y, int ldy, int R, int Nout, double scale, int relu, cudaStream_t st) {
+                   double* Y, int ldy, int R, int Nout, double scale, int relu, cudaStream_t st, int w_tiled = 1) {
     GemmParams p;
     memset(&p, 0, sizeof(p));
+    p.w_tiled = w_tiled;
     p.A0 = X0; p.lda0 = ld0; p.K0 = K0; p.A1 = X1; p.lda1 = ld1;
     p.W = W; p.ldw = ldw; p.bias = bias; p.Res = Res; p.ldres = ldres; p.Y = Y; p.ldy = ldy;
     p.R = R; p.Nout = Nout; p.K = K0 + K1; p.scale = scale; p.relu = relu;
@@ -243,7 +246,7 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const m
         GemmParams p;
         memset(&p, 0, sizeof(p));
         p.A0 = w.X; p.lda0 = LDX; p.K0 = DMODEL; p.W = Wt + lo.wqkv; p.ldw = DMODEL; p.bias = Wt + lo.bqkv;
-        p.R = R; p.Nout = 3 * DMODEL; p.K = DMODEL; p.scale = 1.0;
+        p.R = R; p.Nout = 3 * DMODEL; p.K = DMODEL; p.scale = 1.0; p.w_tiled = 1;
         p.Qh = w.Qh; p.Kh = w.Kh; p.Vh = w.Vh; p.rows0 = R0; p.n0 = N; p.n1 = M;
         prof_mark(ST_GEMM, st);
         MDGAT_CUDA_OK(launch_gemm(p, EPI_QKV, 1, st));
@@ -288,7 +291,7 @@ int mdgat_linear_f64(const double* d_X0, int ldx0, int K0, const double* d_X1, i
                   "mdgat_linear_f64: K0, K1, ldx, ldw must be even (16-byte staging)");
     MDGAT_REQUIRE(d_X1 == nullptr || ((K0 % 32) == 0 && (ldx1 % 2) == 0), "mdgat_linear_f64: with a second input K0 must be a multiple of 32");
     MDGAT_CUDA_OK(linear(d_X0, ldx0, K0, d_X1, ldx1, d_X1 ? K1 : 0, d_W, ldw, d_bias, d_Res, ldres, d_Y, ldy, R, Nout,
-                         scale, relu, reinterpret_cast<cudaStream_t>(stream)));
+                         scale, relu, reinterpret_cast<cudaStream_t>(stream), 0));
     return MDGAT_OK;
 }
 

@@ -28,7 +28,10 @@ template <int MI> constexpr size_t gemm_smem_bytes() {
     return (size_t)G_STAGES * (8 * MI + G_BN) * G_LDS * sizeof(double);
 }
 
-template <int MI, int EPI>
+// WT = true: W is a tile-major blob weight; each (column tile, k chunk) stage is ONE contiguous
+// 128 x 36 block moved by a single TMA bulk copy (cp.async.bulk -> UBLKCP) that one thread issues and an
+// mbarrier completes. The A rows stay on 16-byte cp.async (they are strided in memory).
+template <int MI, int EPI, bool WT>
 __global__ void __launch_bounds__(G_THREADS, 2) gemm_f64_kernel(GemmParams p, int rows_per_stripe) {
     constexpr int BM = 8 * MI;
     extern __shared__ __align__(16) double smem[];
@@ -49,6 +52,11 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_f64_kernel(GemmParams p, in
     const int ntiles = (row_end - row_begin + BM - 1) / BM;
     const int nk = (p.K + G_BK - 1) / G_BK;
     const int total = ntiles * nk;
+    __shared__ __align__(8) uint64_t wbar[G_STAGES];
+    if (WT) {
+        if (tid == 0) { mbar_init(&wbar[0], 1); mbar_init(&wbar[1], 1); mbar_fence_init(); }
+        __syncthreads();
+    }
 
     auto load_stage = [&](int q, int buf) {
         const int t = q / nk, kc = q - t * nk;
@@ -66,13 +74,21 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_f64_kernel(GemmParams p, in
             const double* src = ok ? Ab + (long long)(m0 + r) * lda + kk + kc2 : Ab;
             cp_async16(as + r * G_LDS + kc2, src, ok);
         }
+        if (WT) {
+            if (tid == 0) {
+                constexpr unsigned bytes = G_BN * G_LDS * sizeof(double);
+                mbar_expect_tx(&wbar[buf], bytes);
+                bulk_g2s(ws, W + ((size_t)blockIdx.y * nk + kc) * (G_BN * G_LDS), bytes, &wbar[buf]);
+            }
+        } else {
 #pragma unroll
-        for (int i = 0; i < (G_BN * (G_BK / 2)) / G_THREADS; ++i) {
-            const int c = tid + i * G_THREADS;
-            const int r = c >> 4, kc2 = (c & 15) * 2;
-            const bool ok = (n0 + r < p.Nout) && (k0 + kc2 < p.K);
-            const double* src = ok ? W + (long long)(n0 + r) * p.ldw + k0 + kc2 : W;
-            cp_async16(ws + r * G_LDS + kc2, src, ok);
+            for (int i = 0; i < (G_BN * (G_BK / 2)) / G_THREADS; ++i) {
+                const int c = tid + i * G_THREADS;
+                const int r = c >> 4, kc2 = (c & 15) * 2;
+                const bool ok = (n0 + r < p.Nout) && (k0 + kc2 < p.K);
+                const double* src = ok ? W + (long long)(n0 + r) * p.ldw + k0 + kc2 : W;
+                cp_async16(ws + r * G_LDS + kc2, src, ok);
+            }
         }
     };
 
@@ -92,6 +108,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_f64_kernel(GemmParams p, in
         } else {
             cp_async_wait<0>();
         }
+        if (WT) mbar_wait(&wbar[q & 1], (unsigned)((q >> 1) & 1));
         __syncthreads();
         const double* as = As + (q & 1) * BM * G_LDS + qr * G_LDS + qc;
         const double* ws = Ws + (q & 1) * G_BN * G_LDS + (warp * 16 + qr) * G_LDS + qc;
@@ -161,19 +178,20 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_f64_kernel(GemmParams p, in
     }
 }
 
+template <int MI, int EPI, bool WT>
+static cudaError_t launch_inst(const GemmParams& p, dim3 grid, int rps, cudaStream_t st) {
+    const size_t smem = gemm_smem_bytes<MI>();
+    // per-device attribute; set on every launch (cheap) so multi-device processes stay correct
+    cudaError_t e = cudaFuncSetAttribute(gemm_f64_kernel<MI, EPI, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    gemm_f64_kernel<MI, EPI, WT><<<grid, G_THREADS, smem, st>>>(p, rps);
+    return cudaSuccess;
+}
+
 template <int MI>
 static cudaError_t launch_mi(const GemmParams& p, int epi, dim3 grid, int rps, cudaStream_t st) {
-    const size_t smem = gemm_smem_bytes<MI>();
-    cudaError_t e;
-    if (epi == EPI_PLAIN) {
-        // per-device attribute; set on every launch (cheap) so multi-device processes stay correct
-        if ((e = cudaFuncSetAttribute(gemm_f64_kernel<MI, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        gemm_f64_kernel<MI, EPI_PLAIN><<<grid, G_THREADS, smem, st>>>(p, rps);
-    } else {
-        if ((e = cudaFuncSetAttribute(gemm_f64_kernel<MI, EPI_QKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        gemm_f64_kernel<MI, EPI_QKV><<<grid, G_THREADS, smem, st>>>(p, rps);
-    }
-    return cudaSuccess;
+    if (epi == EPI_QKV) return p.w_tiled ? launch_inst<MI, EPI_QKV, true>(p, grid, rps, st) : cudaErrorInvalidValue;
+    return p.w_tiled ? launch_inst<MI, EPI_PLAIN, true>(p, grid, rps, st) : launch_inst<MI, EPI_PLAIN, false>(p, grid, rps, st);
 }
 
 static int g_sm_count[64] = {0};

@@ -14,7 +14,8 @@ void count_launch(int n = 1);
 struct GemmParams {
     const double* A0; int lda0; int K0;     // first K0 input columns
     const double* A1; int lda1;             // remaining K - K0 columns (may be null)
-    const double* W; int ldw;               // [Nout][K]
+    const double* W; int ldw;               // [Nout][K] row-major, or tile-major blob weight if w_tiled
+    int w_tiled;
     const double* bias;                     // [Nout] or null
     const double* Res; int ldres;           // [R][Nout] or null (may alias Y)
     double* Y; int ldy;

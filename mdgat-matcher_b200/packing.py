@@ -9,7 +9,9 @@
 * MultiHeadedAttention views channels as (dim=32, heads=4), i.e. channel c = d*4 + h
   (mdgat.py:227); q/k/v output rows and merge input columns are permuted once to the
   head-major order c' = h*32 + d the kernels use;
-* the 33-wide descriptor conv is zero-padded to 36 input columns (DMMA K granularity 4).
+* the 33-wide descriptor conv is zero-padded to 36 input columns (DMMA K granularity 4);
+* every weight matrix is stored tile-major (tile_weight) so that one TMA bulk copy stages a
+  whole (128 outputs x 32 inputs) block.
 
 All arithmetic is done in float64 on whatever the parameters currently hold, so calling the
 module as test.py does (fp32 module -> load_state_dict -> .double()) yields fp64(fp32(ckpt)).
@@ -19,13 +21,34 @@ import torch
 BN_EPS = 1e-5
 KENC_DIMS = (4, 32, 64, 128, 128)
 DENC_DIMS = (36, 64, 128, 128)
-LAYER_DOUBLES = 384 * 128 + 384 + 256 * 256 + 256 + 128 * 256 + 128
+TILE_N, TILE_K, TILE_LD = 128, 32, 36      # one GEMM weight stage: 128 output channels x 32 inputs, rows padded to 36
+
+
+def tiled_doubles(nout, k):
+    return -(-nout // TILE_N) * -(-k // TILE_K) * TILE_N * TILE_LD
+
+
+def tile_weight(w):
+    """[Nout][K] -> [ceil(Nout/128)][ceil(K/32)][128][36], zero padded: every (column tile, k chunk)
+    stage of the GEMM kernel is one contiguous 36 KB block that a single TMA bulk copy moves to
+    shared memory, already in the padded row layout the DMMA fragment reads need."""
+    nout, k = w.shape
+    ny, nk = -(-nout // TILE_N), -(-k // TILE_K)
+    full = w.new_zeros(ny * TILE_N, nk * TILE_K)
+    full[:nout, :k] = w
+    t = full.reshape(ny, TILE_N, nk, TILE_K).permute(0, 2, 1, 3)
+    out = w.new_zeros(ny, nk, TILE_N, TILE_LD)
+    out[..., :TILE_K] = t
+    return out.reshape(-1)
+
+
+LAYER_DOUBLES = tiled_doubles(384, 128) + 384 + tiled_doubles(256, 256) + 256 + tiled_doubles(128, 256) + 128
 
 
 def blob_doubles(L):
-    n = sum(KENC_DIMS[i + 1] * KENC_DIMS[i] + KENC_DIMS[i + 1] for i in range(4))
-    n += sum(DENC_DIMS[i + 1] * DENC_DIMS[i] + DENC_DIMS[i + 1] for i in range(3))
-    n += 2 * L * LAYER_DOUBLES + 128 * 128 + 128 + 4
+    n = sum(tiled_doubles(KENC_DIMS[i + 1], KENC_DIMS[i]) + KENC_DIMS[i + 1] for i in range(4))
+    n += sum(tiled_doubles(DENC_DIMS[i + 1], DENC_DIMS[i]) + DENC_DIMS[i + 1] for i in range(3))
+    n += 2 * L * LAYER_DOUBLES + tiled_doubles(128, 128) + 128 + 4
     return n
 
 
@@ -61,7 +84,7 @@ def pack_state_dict(sd, L):
                 w, b = _fold_bn(w, b, sd, '%s.%d' % (prefix, 3 * i + 1))
             if i == 0 and pad_in is not None and w.shape[1] < pad_in:
                 w = torch.cat([w, w.new_zeros(w.shape[0], pad_in - w.shape[1])], dim=1)
-            parts.extend([w.reshape(-1), b])
+            parts.extend([tile_weight(w), b])
 
     mlp('kenc.encoder', 4)
     mlp('denc.encoder', 3, pad_in=36)
@@ -73,7 +96,7 @@ def pack_state_dict(sd, L):
             w, b = _conv(sd, p + 'attn.proj.%d' % j)
             ws.append(w[perm])
             bs.append(b[perm])
-        parts.extend([torch.cat(ws, 0).reshape(-1), torch.cat(bs, 0)])
+        parts.extend([tile_weight(torch.cat(ws, 0)), torch.cat(bs, 0)])
         # merge conv folded into the first MLP conv: mlp.0([x ; merge(msg)]) =
         #   W1x x + (W1m Wm) msg + (b1 + W1m bm)  -- one 128x128 GEMM per layer and side disappears
         wm, bm = _conv(sd, p + 'attn.merge')
@@ -82,11 +105,11 @@ def pack_state_dict(sd, L):
         w1m = w[:, 128:]
         w = torch.cat([w[:, :128], w1m @ wm[:, perm]], dim=1)
         b = b + w1m @ bm
-        parts.extend([w.reshape(-1), b])
+        parts.extend([tile_weight(w), b])
         w, b = _conv(sd, p + 'mlp.3')
-        parts.extend([w.reshape(-1), b])
+        parts.extend([tile_weight(w), b])
     w, b = _conv(sd, 'final_proj')
-    parts.extend([w.reshape(-1), b])
+    parts.extend([tile_weight(w), b])
     bin_score = sd['bin_score'].detach().double().reshape(1)
     parts.extend([bin_score, bin_score.new_zeros(3)])
     blob = torch.cat([x.contiguous().reshape(-1) for x in parts]).contiguous()

@@ -55,17 +55,21 @@ def test_packed_blob_reproduces_reference_layers_on_cpu():
     sd_t = synth.seeded_state_dict(L, 3)
     sd = O.state_dict_to_numpy(sd_t)
     blob = packing.pack_state_dict(sd_t, L).numpy()
-    off = sum(packing.KENC_DIMS[i + 1] * packing.KENC_DIMS[i] + packing.KENC_DIMS[i + 1] for i in range(4))
-    off += sum(packing.DENC_DIMS[i + 1] * packing.DENC_DIMS[i] + packing.DENC_DIMS[i + 1] for i in range(3))
+    off = sum(packing.tiled_doubles(packing.KENC_DIMS[i + 1], packing.KENC_DIMS[i]) + packing.KENC_DIMS[i + 1] for i in range(4))
+    off += sum(packing.tiled_doubles(packing.DENC_DIMS[i + 1], packing.DENC_DIMS[i]) + packing.DENC_DIMS[i + 1] for i in range(3))
 
     def take(n, shape=None):
         nonlocal off
         a = blob[off:off + n]
         off += n
         return a.reshape(shape) if shape else a
-    wqkv, bqkv = take(384 * 128, (384, 128)), take(384)
-    w1, b1 = take(256 * 256, (256, 256)), take(256)
-    w2, b2 = take(128 * 256, (128, 256)), take(128)
+
+    def take_w(nout, k):          # undo packing.tile_weight
+        t = take(packing.tiled_doubles(nout, k)).reshape(-(-nout // 128), -(-k // 32), 128, 36)[..., :32]
+        return t.transpose(0, 2, 1, 3).reshape(t.shape[0] * 128, t.shape[1] * 32)[:nout, :k]
+    wqkv, bqkv = take_w(384, 128), take(384)
+    w1, b1 = take_w(256, 256), take(256)
+    w2, b2 = take_w(128, 256), take(128)
     rng = np.random.default_rng(0)
     x = rng.normal(size=(1, 128, 40)); src = rng.normal(size=(1, 128, 50))
     want, _ = O.attentional_propagation(sd, 'gnn.layers.0', x, src, None)

@@ -175,6 +175,9 @@ def main():
     ap.add_argument('--no-eager', action='store_true', help='skip the eager-PyTorch fp64 GPU timing of the same math')
     args = ap.parse_args()
 
+    # NCCL prints its version banner on STDOUT at level VERSION; this script owes the driver ONE json line
+    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+        os.environ['NCCL_DEBUG'] = 'WARN'
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -191,7 +194,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        mdist.init_process_group('nccl')
+        mdist.init_process_group('nccl', device_id=dev)
 
     B, N, L, T = args.batch, args.n, args.layers, args.sinkhorn
     cfg = net_config(L, T)
@@ -270,6 +273,7 @@ def main():
     ms_total, e2e_ms = float(t[0]), float(t[1])
 
     if rank != 0:
+        torch.distributed.destroy_process_group()
         return
 
     pairs_total = B * world * args.steps
@@ -368,6 +372,8 @@ def main():
         'candidate_correspondences_per_s': value * N * N,
     }
     print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -159,6 +159,17 @@ size_t mdgat_match_scratch_doubles(int B, int N, int M);
  * x (B,3,n), src (B,3,m) float64 channel-major as in the reference. */
 int mdgat_knn(const double* d_x, const double* d_src, int64_t* d_idx, int B, int n, int m, int k, void* stream);
 
+/* Output side of the path: batched one-shot rigid registration from the
+ * predicted matches and the match statistics the evaluation scripts accumulate, on the device.
+ * Replaces solve_icp / calculate_error2 (utils/utils_test.py:73-110, 27-39) and the TP/FP/TN/FN
+ * counting of test_registration_metric.py:216-246, which upstream run per pair on the CPU.
+ * d_T: (B,4,4) transform taking the matched keypoints1 onto keypoints0 (R = U V^T, no reflection
+ * fix, as upstream). d_stats: (B,8) = [n_valid, n_valid_gt, tp, fp, tn, fn, RTE, RRE]; RTE/RRE are
+ * NaN without d_T_gt, the counts beyond n_valid are 0 without d_gt0 (gt value M or -1 = no match). */
+int mdgat_register_pairs(const void* d_kpts0, const void* d_kpts1, int kp_dtype, const int64_t* d_matches0,
+                         const int16_t* d_gt0, const double* d_T_gt, int B, int N, int M,
+                         double* d_T, double* d_stats, void* stream);
+
 /* Measured fp64 tensor-pipe peak of this device (DMMA.8x8x4 issue loop), TFLOP/s.
  * Synchronises. Used as the roofline denominator of the fp64 kernels. */
 int mdgat_measure_fp64_peak(double* tflops_dmma, double* tflops_dfma);

@@ -399,6 +399,15 @@ int mdgat_profile_collect(double* ms, long long* launches, long long* segments, 
     return MDGAT_OK;
 }
 
+int mdgat_register_pairs(const void* d_kpts0, const void* d_kpts1, int kp_dtype, const int64_t* d_matches0,
+                         const int16_t* d_gt0, const double* d_T_gt, int B, int N, int M,
+                         double* d_T, double* d_stats, void* stream) {
+    MDGAT_REQUIRE(B >= 0 && N > 0 && M > 0 && d_T && d_stats, "mdgat_register_pairs: bad arguments");
+    MDGAT_CUDA_OK(launch_register_pairs(d_kpts0, d_kpts1, kp_dtype, d_matches0, d_gt0, d_T_gt, B, N, M, d_T, d_stats,
+                                        reinterpret_cast<cudaStream_t>(stream)));
+    return MDGAT_OK;
+}
+
 int mdgat_measure_fp64_mixed(double* tflops_dmma, double* tflops_dfma) {
     MDGAT_CUDA_OK(measure_fp64_mixed(tflops_dmma, tflops_dfma));
     MDGAT_CUDA_OK(measure_dmma_tiled(tflops_dfma + 1));

@@ -68,6 +68,11 @@ cudaError_t launch_match_extract(const MatchParams& p, cudaStream_t st);
 
 cudaError_t launch_knn(const double* x, const double* src, int64_t* idx, int B, int n, int m, int k, cudaStream_t st);
 
+// Batched Kabsch registration + match statistics (one CTA per pair)
+cudaError_t launch_register_pairs(const void* kpts0, const void* kpts1, int kp_dtype, const int64_t* matches0,
+                                  const int16_t* gt0, const double* T_gt, int B, int N, int M,
+                                  double* T_out, double* stats, cudaStream_t st);
+
 cudaError_t measure_fp64_peak(double* dmma_tflops, double* dfma_tflops);
 cudaError_t measure_fp64_mixed(double* dmma_tflops, double* dfma_tflops);
 cudaError_t measure_dmma_tiled(double* tflops);

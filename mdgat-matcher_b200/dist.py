@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 
 
-def init_process_group(backend=None):
+def init_process_group(backend=None, device_id=None):
     """Reads RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT from the environment (torchrun)."""
     if dist.is_initialized():
         return
@@ -18,8 +18,9 @@ def init_process_group(backend=None):
         backend = 'nccl' if torch.cuda.is_available() else 'gloo'
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     os.environ.setdefault('MASTER_PORT', '29511')
+    kw = {'device_id': device_id} if (device_id is not None and backend == 'nccl') else {}
     dist.init_process_group(backend=backend, rank=int(os.environ.get('RANK', '0')),
-                            world_size=int(os.environ.get('WORLD_SIZE', '1')))
+                            world_size=int(os.environ.get('WORLD_SIZE', '1')), **kw)
 
 
 def world():

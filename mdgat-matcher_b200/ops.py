@@ -192,3 +192,27 @@ def measure_fp64_mixed():
     a, b = ctypes.c_double(), (ctypes.c_double * 2)()
     _capi.check(_capi.lib.mdgat_measure_fp64_mixed(ctypes.byref(a), b))
     return a.value, b[0], b[1]
+
+
+def register_pairs(kpts0, kpts1, matches0, gt_matches0=None, T_gt=None):
+    """Batched Kabsch registration + match statistics from predicted matches (device side of
+    utils_test.solve_icp / calculate_error2 and the TP/FP/TN/FN counting of the eval scripts).
+    Returns T (B,4,4) and a dict of per-pair tensors."""
+    _need_cuda(kpts0)
+    dev = kpts0.device
+    if kpts0.dtype not in (torch.float32, torch.float64) or kpts1.dtype != kpts0.dtype:
+        kpts0, kpts1 = kpts0.double(), kpts1.double()
+    kpts0, kpts1 = kpts0.contiguous(), kpts1.contiguous()
+    B, N, M = kpts0.shape[0], kpts0.shape[1], kpts1.shape[1]
+    m0 = matches0.to(torch.int64).contiguous()
+    g0 = gt_matches0.to(torch.int16).contiguous() if gt_matches0 is not None else None
+    tg = T_gt.double().contiguous() if T_gt is not None else None
+    T = torch.empty((B, 4, 4), dtype=torch.float64, device=dev)
+    st = torch.empty((B, 8), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib.mdgat_register_pairs(
+            kpts0.data_ptr(), kpts1.data_ptr(), _capi.F64 if kpts0.dtype == torch.float64 else _capi.F32,
+            m0.data_ptr(), g0.data_ptr() if g0 is not None else None, tg.data_ptr() if tg is not None else None,
+            B, N, M, T.data_ptr(), st.data_ptr(), _stream(dev)))
+    names = ('n_valid', 'n_valid_gt', 'tp', 'fp', 'tn', 'fn', 'rte', 'rre')
+    return T, {n: st[:, i] for i, n in enumerate(names)}

@@ -379,3 +379,38 @@ def forward_threaded(sd, data, cfg, threads):
     with ThreadPoolExecutor(max_workers=threads) as ex:
         parts = list(ex.map(one, range(b)))
     return {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
+
+
+# --------------------------------------------------------------------------- output side (f-4)
+
+def solve_icp(P, Q):
+    """solve_icp() (/root/reference/utils/utils_test.py:73-110): one-shot Kabsch, P -> Q.
+    R = U V^T straight from the SVD of Q_c^T P_c (no reflection fix upstream)."""
+    up, uq = P.mean(axis=0), Q.mean(axis=0)
+    U, _, Vt = np.linalg.svd((Q - uq).T @ (P - up), full_matrices=True)
+    R = U @ Vt
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = uq - R @ up
+    return T
+
+
+def registration_error(mkpts0, mkpts1, T_gt):
+    """calculate_error2() (utils_test.py:27-39): T from solve_icp(mkpts1, mkpts0), RTE and RRE
+    of inv(T) T_gt."""
+    T = solve_icp(mkpts1, mkpts0)
+    E = np.linalg.inv(T) @ T_gt
+    rte = np.linalg.norm(E[:3, 3])
+    with np.errstate(invalid='ignore'):
+        rre = np.arccos((E[0, 0] + E[1, 1] + E[2, 2] - 1) / 2)
+    return T, rte, rre
+
+
+def match_statistics(matches, matches_gt, m):
+    """TP / FP / TN / FN counts of /root/reference/test_registration_metric.py:216-246 for one pair;
+    gt value m (or -1) means 'no match' (the forward rewrites -1 to m, the script maps it back)."""
+    g = np.where(matches_gt == m, -1, matches_gt)
+    valid, valid_gt = matches > -1, g > -1
+    return {'n_valid': int(valid.sum()), 'n_valid_gt': int(valid_gt.sum()),
+            'tp': int((valid & (matches == g)).sum()), 'fp': int((valid & (matches != g)).sum()),
+            'tn': int((~valid & (g == -1)).sum()), 'fn': int((~valid & (g > -1)).sum())}

@@ -341,3 +341,37 @@ def test_reference_eval_loop_plumbing(dev):
     pred = {k: torch.from_numpy(v).cuda() for k, v in golden_inputs(rec).items()}
     data = net(pred)
     assert not np.array_equal(data['matching_scores0'].cpu().numpy(), rec['matching_scores0'])
+
+
+# ----------------------------------------------------------------------------- output side (f-4)
+
+def test_register_pairs_vs_oracle(dev):
+    """Batched Kabsch + RTE/RRE + match counts against the numpy restatement of
+    utils_test.solve_icp / calculate_error2 and the eval script's counting."""
+    from mdgat_matcher_b200 import ops, synth
+    from oracle import mdgat_oracle as O
+    B, N = 5, 256
+    data = synth.make_batch(21, B, N, overlap=0.6, noise=0.03)
+    rng = np.random.default_rng(0)
+    gt0 = data['gt_matches0'].numpy().astype(np.int64)
+    matches = gt0.copy()
+    flip = rng.random(matches.shape) < 0.1                     # some wrong / dropped predictions
+    matches[flip & (matches >= 0)] = rng.integers(0, N, size=int((flip & (matches >= 0)).sum()))
+    matches[rng.random(matches.shape) < 0.1] = -1
+    gt_fwd = np.where(gt0 == -1, N, gt0).astype(np.int16)       # as the forward leaves it (mdgat.py:519)
+    yaw = 0.05
+    Tgt = np.eye(4); Tgt[:3, :3] = [[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]]; Tgt[:3, 3] = [3, .5, .02]
+    Tgt = np.broadcast_to(Tgt, (B, 4, 4)).copy()
+    T, st = ops.register_pairs(data['keypoints0'].to(dev), data['keypoints1'].to(dev), _t(matches, dev),
+                               _t(gt_fwd, dev), _t(Tgt, dev))
+    k0, k1 = data['keypoints0'].numpy(), data['keypoints1'].numpy()
+    for b in range(B):
+        v = matches[b] > -1
+        Tw, rte, rre = O.registration_error(k0[b][v], k1[b][matches[b][v]], Tgt[b])
+        assert np.abs(T[b].cpu().numpy() - Tw).max() < 1e-9
+        assert abs(float(st['rte'][b]) - rte) < 1e-9 and abs(float(st['rre'][b]) - rre) < 1e-7
+        want = O.match_statistics(matches[b], gt_fwd[b].astype(np.int64), N)
+        for key, val in want.items():
+            assert int(st[key][b]) == val, key
+    # the synthetic pair really is registered: set 1 = (set 0 - t) R + noise, so T ~ T_gt
+    assert float(st['rte'].max()) < 0.5

@@ -15,12 +15,12 @@ constexpr int LDS_ = 36;
 // 3: + cp.async refill of the other stage from global each chunk (latency exposed: wait_group 0).
 // 4: same loads but prefetched one chunk ahead (wait_group 1). 5: + epilogue every 4 chunks (scale, bias,
 // relu, double2 stores). 6: + residual loads in the epilogue.
-template <int MODE, int MI, int NI>
-__global__ void __launch_bounds__(256, 2) k(double* out, const double* g, int chunks) {
+template <int MODE, int MI, int NI, int WROWS = 128, int OCC = 2>
+__global__ void __launch_bounds__(256, OCC) k(double* out, const double* g, int chunks) {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qr = lane >> 2, qc = lane & 3;
-    constexpr int ROWS = 64 + 128;
+    constexpr int ROWS = 64 + WROWS;
     for (int i = tid; i < 2 * ROWS * LDS_; i += 256) sm[i] = 1e-3 * (i % 97);
     __syncthreads();
     double acc[MI][NI][2];
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256, 2) k(double* out, const double* g, int ch
             double* dst = sm + ((c + 1) & 1) * ROWS * LDS_;
             const double* src = g + ((size_t)blockIdx.x * 4096 + (c & 7) * 512) % (1 << 22);
 #pragma unroll
-            for (int i = 0; i < 12; ++i) { int idx = tid + i * 256; int r = idx >> 4, k2 = (idx & 15) * 2; cp_async16(dst + r * LDS_ + k2, src + r * 32 + k2); }
+            for (int i = 0; i < (ROWS * 16) / 256; ++i) { int idx = tid + i * 256; int r = idx >> 4, k2 = (idx & 15) * 2; cp_async16(dst + r * LDS_ + k2, src + r * 32 + k2); }
             asm volatile("cp.async.commit_group;\n" ::);
         }
 #pragma unroll
@@ -83,18 +83,19 @@ __global__ void __launch_bounds__(256, 2) k(double* out, const double* g, int ch
         for (int j = 0; j < NI; ++j) s += acc[i][j][0] + acc[i][j][1];
     if (s == 123.456) out[0] = s;
 }
-template <int MODE, int MI, int NI> void run(const char* name, double* d, const double* g) {
-    const int chunks = 2000, grid = 148 * 2;
-    const size_t smem = 2 * (64 + 128) * LDS_ * sizeof(double);
-    cudaFuncSetAttribute(k<MODE, MI, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int MODE, int MI, int NI, int WROWS = 128, int OCC = 2> void run(const char* name, double* d, const double* g) {
+    const int chunks = 2000, grid = 148 * OCC;
+    const size_t smem = 2 * (64 + WROWS) * LDS_ * sizeof(double);
+    cudaFuncSetAttribute(k<MODE, MI, NI, WROWS, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k<MODE, MI, NI, WROWS, OCC>, 256, smem);
     cudaEvent_t t0, t1; cudaEventCreate(&t0); cudaEventCreate(&t1);
     float ms = 0;
     for (int rep = 0; rep < 2; ++rep) {
-        cudaEventRecord(t0); k<MODE, MI, NI><<<grid, 256, smem>>>(d, g, chunks); cudaEventRecord(t1);
+        cudaEventRecord(t0); k<MODE, MI, NI, WROWS, OCC><<<grid, 256, smem>>>(d, g, chunks); cudaEventRecord(t1);
         cudaEventSynchronize(t1); cudaEventElapsedTime(&ms, t0, t1);
     }
     double fl = (double)grid * 8 * chunks * 8 * MI * NI * 512.0;
-    printf("%-44s %8.3f ms  %6.2f TFLOP/s  (%s)\n", name, ms, fl / (ms * 1e-3) / 1e12, cudaGetErrorString(cudaGetLastError()));
+    printf("%-52s occ %d %8.3f ms  %6.2f TFLOP/s  (%s)\n", name, nb, ms, fl / (ms * 1e-3) / 1e12, cudaGetErrorString(cudaGetLastError()));
 }
 int main() {
     double *d, *g; cudaMalloc(&d, 64); cudaMalloc(&g, (size_t)(1 << 23) * 8); cudaMemset(g, 0, (size_t)(1 << 23) * 8);
@@ -111,6 +112,11 @@ int main() {
     run<6, 7, 2>("7x2 + prefetch + epilogue + residual", d, g);
     run<4, 4, 4>("4x4 + prefetched cp.async (wait 1)", d, g);
     run<6, 4, 4>("4x4 + prefetch + epilogue + residual", d, g);
+    run<6, 7, 1, 64, 3>("7x1 W64 3 CTAs/SM: prefetch+epilogue+residual", d, g);
+    run<6, 7, 1, 64, 2>("7x1 W64 2 CTAs/SM: prefetch+epilogue+residual", d, g);
+    run<6, 7, 2, 128, 1>("7x2 W128 1 CTA/SM: prefetch+epilogue+residual", d, g);
+    run<4, 7, 1, 64, 3>("7x1 W64 3 CTAs/SM: prefetch only", d, g);
+    run<2, 7, 1, 64, 3>("7x1 W64 3 CTAs/SM: LDS+barrier", d, g);
     run<1, 8, 2>("8x2 + LDS", d, g);
     run<1, 4, 2>("4x2 + LDS", d, g);
     return 0;

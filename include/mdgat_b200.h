@@ -159,6 +159,16 @@ size_t mdgat_match_scratch_doubles(int B, int N, int M);
  * x (B,3,n), src (B,3,m) float64 channel-major as in the reference. */
 int mdgat_knn(const double* d_x, const double* d_src, int64_t* d_idx, int B, int n, int m, int k, void* stream);
 
+/* Input side of the path: the per-item CPU work of SparseDataset.__getitem__
+ * (load_data.py:213-292) batched on the device. kp1 (B,N,3) / kp2 (B,M,3) float64 in the LiDAR frame,
+ * pose1/pose2 (B,4,4) cam0 poses, T_cam0_velo (4,4) shared or (B,4,4) per pair. Outputs: gt matches
+ * (int16, -1 = none; nearest neighbour in world coordinates under `threshold`, optional mutual check),
+ * T_gt (B,4,4) = inv(T_cam0_velo) inv(pose1) pose2 T_cam0_velo, rep[b] = number of set-1 points with a
+ * neighbour closer than the threshold. */
+int mdgat_prepare_pairs(const double* d_kp1, const double* d_kp2, const double* d_pose1, const double* d_pose2,
+                        const double* d_T_cam0_velo, int calib_per_pair, int B, int N, int M, double threshold,
+                        int mutual_check, int16_t* d_match1, int16_t* d_match2, double* d_T_gt, int* d_rep, void* stream);
+
 /* Output side of the path: batched one-shot rigid registration from the
  * predicted matches and the match statistics the evaluation scripts accumulate, on the device.
  * Replaces solve_icp / calculate_error2 (utils/utils_test.py:73-110, 27-39) and the TP/FP/TN/FN

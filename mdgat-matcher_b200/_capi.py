@@ -61,6 +61,7 @@ def _load():
         'mdgat_match_scratch_doubles': (sz, [i, i, i]),
         'mdgat_match_extract': (i, [vp, vp, vp, i, i, i, i, i, d, i, d, vp, vp, C.POINTER(ForwardOut), vp, vp]),
         'mdgat_knn': (i, [vp, vp, vp, i, i, i, i, vp]),
+        'mdgat_prepare_pairs': (i, [vp, vp, vp, vp, vp, i, i, i, i, d, i, vp, vp, vp, vp, vp]),
         'mdgat_register_pairs': (i, [vp, vp, i, vp, vp, vp, i, i, i, vp, vp, vp]),
         'mdgat_measure_fp64_peak': (i, [C.POINTER(d), C.POINTER(d)]),
         'mdgat_measure_fp64_mixed': (i, [C.POINTER(d), C.POINTER(d)]),

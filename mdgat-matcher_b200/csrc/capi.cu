@@ -399,6 +399,16 @@ int mdgat_profile_collect(double* ms, long long* launches, long long* segments, 
     return MDGAT_OK;
 }
 
+int mdgat_prepare_pairs(const double* d_kp1, const double* d_kp2, const double* d_pose1, const double* d_pose2,
+                        const double* d_T_cam0_velo, int calib_per_pair, int B, int N, int M, double threshold,
+                        int mutual_check, int16_t* d_match1, int16_t* d_match2, double* d_T_gt, int* d_rep, void* stream) {
+    MDGAT_REQUIRE(B >= 0 && N > 0 && M > 0 && N < 32768 && M < 32768, "mdgat_prepare_pairs: bad shape (int16 match indices)");
+    MDGAT_REQUIRE(prepare_pairs_smem(N, M) <= 227 * 1024, "mdgat_prepare_pairs: N + M = %d keypoints do not fit in shared memory", N + M);
+    MDGAT_CUDA_OK(launch_prepare_pairs(d_kp1, d_kp2, d_pose1, d_pose2, d_T_cam0_velo, calib_per_pair, B, N, M, threshold,
+                                       mutual_check, d_match1, d_match2, d_T_gt, d_rep, reinterpret_cast<cudaStream_t>(stream)));
+    return MDGAT_OK;
+}
+
 int mdgat_register_pairs(const void* d_kpts0, const void* d_kpts1, int kp_dtype, const int64_t* d_matches0,
                          const int16_t* d_gt0, const double* d_T_gt, int B, int N, int M,
                          double* d_T, double* d_stats, void* stream) {

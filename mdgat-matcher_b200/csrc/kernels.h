@@ -73,6 +73,13 @@ cudaError_t launch_register_pairs(const void* kpts0, const void* kpts1, int kp_d
                                   const int16_t* gt0, const double* T_gt, int B, int N, int M,
                                   double* T_out, double* stats, cudaStream_t st);
 
+// Ground-truth matches / T_gt / repeatability of a batch of pairs from poses and calibration
+size_t prepare_pairs_smem(int N, int M);
+cudaError_t launch_prepare_pairs(const double* kp1, const double* kp2, const double* pose1, const double* pose2,
+                                 const double* calib, int calib_per_pair, int B, int N, int M, double threshold,
+                                 int mutual_check, int16_t* match1, int16_t* match2, double* T_gt, int* rep,
+                                 cudaStream_t st);
+
 cudaError_t measure_fp64_peak(double* dmma_tflops, double* dfma_tflops);
 cudaError_t measure_fp64_mixed(double* dmma_tflops, double* dfma_tflops);
 cudaError_t measure_dmma_tiled(double* tflops);

@@ -216,3 +216,24 @@ def register_pairs(kpts0, kpts1, matches0, gt_matches0=None, T_gt=None):
             B, N, M, T.data_ptr(), st.data_ptr(), _stream(dev)))
     names = ('n_valid', 'n_valid_gt', 'tp', 'fp', 'tn', 'fn', 'rte', 'rre')
     return T, {n: st[:, i] for i, n in enumerate(names)}
+
+
+def prepare_pairs(kp1, kp2, pose1, pose2, T_cam0_velo, threshold, mutual_check=False):
+    """Device version of the loader's per-item work (load_data.py:213-292): ground-truth matches,
+    T_gt and the repeatability count for a batch of pairs. Returns (gt_matches0, gt_matches1, T_gt, rep)."""
+    _need_cuda(kp1)
+    dev = kp1.device
+    kp1, kp2 = kp1.double().contiguous(), kp2.double().contiguous()
+    pose1, pose2 = pose1.double().contiguous(), pose2.double().contiguous()
+    calib = T_cam0_velo.double().contiguous()
+    B, N, M = kp1.shape[0], kp1.shape[1], kp2.shape[1]
+    m1 = torch.empty((B, N), dtype=torch.int16, device=dev)
+    m2 = torch.empty((B, M), dtype=torch.int16, device=dev)
+    T = torch.empty((B, 4, 4), dtype=torch.float64, device=dev)
+    rep = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib.mdgat_prepare_pairs(kp1.data_ptr(), kp2.data_ptr(), pose1.data_ptr(), pose2.data_ptr(),
+                                                  calib.data_ptr(), int(calib.dim() == 3), B, N, M, float(threshold),
+                                                  int(bool(mutual_check)), m1.data_ptr(), m2.data_ptr(), T.data_ptr(),
+                                                  rep.data_ptr(), _stream(dev)))
+    return m1, m2, T, rep

@@ -414,3 +414,33 @@ def match_statistics(matches, matches_gt, m):
     return {'n_valid': int(valid.sum()), 'n_valid_gt': int(valid_gt.sum()),
             'tp': int((valid & (matches == g)).sum()), 'fp': int((valid & (matches != g)).sum()),
             'tn': int((~valid & (g == -1)).sum()), 'fn': int((~valid & (g > -1)).sum())}
+
+
+# --------------------------------------------------------------------------- input side (f-2)
+
+def prepare_pair(kp1, kp2, pose1, pose2, T_cam0_velo, threshold, mutual_check=False):
+    """Ground truth of one pair as SparseDataset.__getitem__ builds it
+    (/root/reference/load_data.py:213-285): world coordinates, nearest neighbours under a
+    threshold (optionally mutual), T_gt and the repeatability count."""
+    h1 = np.concatenate([kp1, np.ones((len(kp1), 1))], axis=1)
+    h2 = np.concatenate([kp2, np.ones((len(kp2), 1))], axis=1)
+    T_gt = np.linalg.inv(T_cam0_velo) @ np.linalg.inv(pose1) @ pose2 @ T_cam0_velo           # :238
+    w1 = (pose1 @ T_cam0_velo @ h1.T).T[:, :3]                                               # :241-245
+    w2 = (pose2 @ T_cam0_velo @ h2.T).T[:, :3]
+    dists = np.sqrt(((w1[:, None, :] - w2[None, :, :]) ** 2).sum(-1))                        # cdist, :257
+    min1, min2 = np.argmin(dists, axis=0), np.argmin(dists, axis=1)
+    min1v = dists.min(axis=1)
+    min1f = min2[min1v < threshold]
+    rep = len(min1f)
+    match1 = -np.ones(len(kp1), dtype=np.int16)
+    match2 = -np.ones(len(kp2), dtype=np.int16)
+    if mutual_check:
+        xx = np.where(min2[min1] == np.arange(min1.shape[0]))[0]
+        matches = np.intersect1d(min1f, xx)
+        match1[min1[matches]] = matches
+        match2[matches] = min1[matches]
+    else:
+        match1[min1v < threshold] = min1f
+        min2v = dists.min(axis=0)
+        match2[min2v < threshold] = min1[min2v < threshold]
+    return match1, match2, T_gt, rep

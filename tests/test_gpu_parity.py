@@ -373,5 +373,74 @@ def test_register_pairs_vs_oracle(dev):
         want = O.match_statistics(matches[b], gt_fwd[b].astype(np.int64), N)
         for key, val in want.items():
             assert int(st[key][b]) == val, key
-    # the synthetic pair really is registered: set 1 = (set 0 - t) R + noise, so T ~ T_gt
-    assert float(st['rte'].max()) < 0.5
+    # with the uncorrupted ground-truth matches the synthetic pair really is registered:
+    # set 1 = (set 0 - t) R + noise, so T ~ T_gt
+    _, clean = ops.register_pairs(data['keypoints0'].to(dev), data['keypoints1'].to(dev), _t(gt0, dev), _t(gt_fwd, dev), _t(Tgt, dev))
+    assert float(clean['rte'].max()) < 0.1 and float(clean['rre'].max()) < 0.01
+    assert torch.equal(clean['tp'], clean['n_valid']) and float(clean['fp'].sum()) == 0
+
+
+# ----------------------------------------------------------------------------- input side (f-2)
+
+@pytest.mark.parametrize('mutual', [False, True])
+def test_prepare_pairs_vs_oracle(dev, mutual):
+    """Loader-side ground truth (load_data.py:213-285) on the device against its numpy restatement."""
+    from mdgat_matcher_b200 import ops
+    from oracle import mdgat_oracle as O
+    rng = np.random.default_rng(12)
+    B, N, M = 3, 200, 170
+
+    def rigid(yaw, t):
+        T = np.eye(4)
+        T[:3, :3] = [[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]]
+        T[:3, 3] = t
+        return T
+    calib = np.array([[4.3e-4, -0.99996, -8.1e-3, -1.2e-2], [-7.2e-3, 8.1e-3, -0.99994, -5.4e-2],
+                      [0.99997, 4.9e-4, -7.2e-3, -0.292], [0, 0, 0, 1.0]])            # KITTI-like Tr (velo -> cam0)
+    pose1 = np.stack([rigid(0.1 * b, [b, 0.1, 5.0 * b]) for b in range(B)])
+    pose2 = np.stack([rigid(0.1 * b + 0.04, [b + 0.5, 0.12, 5.0 * b + 2.0]) for b in range(B)])
+    world = rng.normal(size=(B, 400, 3)) * [20, 2, 20] + pose1[:, None, :3, 3]
+    kp1 = np.empty((B, N, 3)); kp2 = np.empty((B, M, 3))
+    for b in range(B):
+        to1 = np.linalg.inv(pose1[b] @ calib); to2 = np.linalg.inv(pose2[b] @ calib)
+        h = np.concatenate([world[b], np.ones((400, 1))], 1)
+        kp1[b] = (to1 @ h[rng.permutation(400)[:N]].T).T[:, :3]
+        kp2[b] = (to2 @ h[rng.permutation(400)[:M]].T).T[:, :3] + rng.normal(size=(M, 3)) * 0.05
+    m1, m2, T, rep = ops.prepare_pairs(_t(kp1, dev), _t(kp2, dev), _t(pose1, dev), _t(pose2, dev), _t(calib, dev), 0.5, mutual)
+    for b in range(B):
+        w1, w2, Tw, rw = O.prepare_pair(kp1[b], kp2[b], pose1[b], pose2[b], calib, 0.5, mutual)
+        assert np.array_equal(m1[b].cpu().numpy(), w1) and np.array_equal(m2[b].cpu().numpy(), w2)
+        assert np.abs(T[b].cpu().numpy() - Tw).max() < 1e-10
+        assert int(rep[b]) == rw
+        assert (w1 >= 0).sum() > 20          # the scene really overlaps
+
+
+def test_kitti_pipeline_files_to_registration(dev, tmp_path):
+    """cfg5 in miniature, GPU-resident end to end: synthetic KITTI-format files -> PairBatcher (device ground
+    truth) -> MDGAT.forward -> batched registration and match statistics; the batch assembled on the device
+    equals the oracle's loader restatement, and the forward on it equals the CPU oracle's forward."""
+    from mdgat_matcher_b200 import kitti_io, ops, synth
+    from mdgat_matcher_b200.models.mdgat import MDGAT
+    from oracle import mdgat_oracle as O
+    dirs = kitti_io.write_synthetic_sequence(str(tmp_path), seq=10, frames=8, n_kpts=128, n_landmarks=600, seed=5)
+    pb = kitti_io.PairBatcher(dirs['train_path'], dirs['txt_path'], dirs['keypoints_path'], 10, device=dev)
+    batch = pb.batch(0, 4)
+    poses, calib = kitti_io.read_poses(dirs['train_path'], 10), kitti_io.read_calib(dirs['train_path'], 10)
+    for i, (a, b) in enumerate(pb.pairs[:4]):
+        w1, w2, Tw, rep = O.prepare_pair(batch['keypoints0'][i].cpu().numpy(), batch['keypoints1'][i].cpu().numpy(),
+                                         poses[a], poses[b], calib, 0.5)
+        assert np.array_equal(batch['gt_matches0'][i].cpu().numpy(), w1) and int(batch['rep'][i]) == rep
+    cfg = case_cfg({'L': 4, 'T': 20})
+    sd = synth.seeded_state_dict(4, 2)
+    net = MDGAT(cfg); net.load_state_dict(sd); net = net.double().eval().to(dev)
+    host = {k: (v.cpu().clone() if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+    out = net(batch)
+    want = O.forward(O.state_dict_to_numpy(sd), host, cfg)
+    assert np.array_equal(out['matches0'].cpu().numpy(), want['matches0'])
+    assert np.abs(out['matching_scores0'].cpu().numpy() - want['matching_scores0']).max() < 1e-7
+    T, st = ops.register_pairs(batch['keypoints0'], batch['keypoints1'], out['matches0'], batch['gt_matches0'], batch['T_gt'])
+    assert T.shape == (4, 4, 4) and torch.isfinite(st['n_valid']).all()
+    gt_fwd = batch['gt_matches0'].cpu().numpy().astype(np.int64)            # forward rewrote -1 -> M in place
+    for i in range(4):
+        ws = O.match_statistics(want['matches0'][i], gt_fwd[i], 128)
+        assert int(st['tp'][i]) == ws['tp'] and int(st['fn'][i]) == ws['fn']

@@ -38,6 +38,10 @@ extern "C" {
 #define MDGAT_LOSS_NONE 0
 #define MDGAT_LOSS_TRIPLET 1     /* mdgat.py:512-546 (test.py default) */
 
+/* GEMM engines for the per-layer projections (q/k/v, MLP) */
+#define MDGAT_GEMM_DMMA_F64 0     /* mma.sync.m8n8k4.f64 (DMMA) on the FP64 pipe */
+#define MDGAT_GEMM_TCGEN05_I8 1   /* float64-faithful Ozaki splitting on tcgen05.mma kind::i8 (TMEM accumulators) */
+
 /* input element types */
 #define MDGAT_F32 0
 #define MDGAT_F64 1
@@ -76,6 +80,8 @@ typedef struct {
     int in_dtype;             /* MDGAT_F32 / MDGAT_F64: element type of kpts/desc inputs */
     int score_dtype;          /* element type of scores0/1 (the reference does not cast them) */
     int write_Z;              /* also materialise Z (B,N+1,M+1) into d_Z (debug / other losses) */
+    int gemm_mode;            /* MDGAT_GEMM_* */
+    int gemm_slices;          /* int8 slices per operand in MDGAT_GEMM_TCGEN05_I8 mode (6..8; 7 = 49 bits) */
 } mdgat_forward_cfg;
 
 typedef struct {
@@ -100,7 +106,9 @@ typedef struct {
 } mdgat_forward_out;
 
 size_t mdgat_forward_workspace_bytes(const mdgat_forward_cfg* cfg);
-int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights,
+/* d_weights_i8: int8-sliced copy of the per-layer GEMM weights (packing.pack_state_dict_i8), required in
+ * MDGAT_GEMM_TCGEN05_I8 mode, NULL otherwise. */
+int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const void* d_weights_i8,
                   const mdgat_forward_in* in, const mdgat_forward_out* out,
                   void* d_workspace, size_t workspace_bytes, void* stream);
 
@@ -112,6 +120,15 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights,
 int mdgat_linear_f64(const double* d_X0, int ldx0, int K0, const double* d_X1, int ldx1, int K1,
                      const double* d_W, int ldw, const double* d_bias, const double* d_Res, int ldres,
                      double* d_Y, int ldy, int R, int Nout, double scale, int relu, void* stream);
+
+/* Same contract as mdgat_linear_f64 (no scale), computed on the tcgen05 int8 tensor cores: X is split on
+ * the device into `slices` int8 digit planes per row, W arrives pre-split (packing.slice_weight: planes in
+ * UMMA canonical K-major order + colscale = 2^f_n); the int32 TMEM accumulators of the slice products are
+ * recombined in float64. K0 (+K1) in {128, 256, 512}, Nout multiple of 64. */
+size_t mdgat_linear_i8_scratch_bytes(int R, int K, int slices);
+int mdgat_linear_i8(const double* d_X0, int ldx0, int K0, const double* d_X1, int ldx1, int K1,
+                    const void* d_Wslices, const double* d_colscale, const double* d_bias, const double* d_Res, int ldres,
+                    double* d_Y, int ldy, int R, int Nout, int relu, int slices, void* d_scratch, void* stream);
 
 /* Batched Y[z] = scale * X[z] W[z]^T, z < batch (element strides sX, sW, sY).
  * Replaces torch.einsum('bdn,bdm->bnm') / sqrt(D) (mdgat.py:430-431) and the dense logits

@@ -13,6 +13,7 @@ MDGAT_OK = 0
 MATCH_DUSTBIN, MATCH_THRESHOLD = 0, 1
 LOSS_NONE, LOSS_TRIPLET = 0, 1
 F32, F64 = 0, 1
+GEMM_DMMA_F64, GEMM_TCGEN05_I8 = 0, 1
 LDX = 132
 LDH_QK, LDH_V = 36, 34
 
@@ -22,7 +23,8 @@ class ForwardCfg(C.Structure):
                 ('sinkhorn_iters', C.c_int), ('layer_k', C.POINTER(C.c_int)),
                 ('match_mode', C.c_int), ('mutual_check', C.c_int), ('match_threshold', C.c_double),
                 ('loss_mode', C.c_int), ('triplet_gamma', C.c_double),
-                ('in_dtype', C.c_int), ('score_dtype', C.c_int), ('write_Z', C.c_int)]
+                ('in_dtype', C.c_int), ('score_dtype', C.c_int), ('write_Z', C.c_int),
+                ('gemm_mode', C.c_int), ('gemm_slices', C.c_int)]
 
 
 class ForwardIn(C.Structure):
@@ -49,7 +51,9 @@ def _load():
         'mdgat_abi_version': (i, []),
         'mdgat_weight_blob_doubles': (sz, [i]),
         'mdgat_forward_workspace_bytes': (sz, [C.POINTER(ForwardCfg)]),
-        'mdgat_forward': (i, [C.POINTER(ForwardCfg), vp, C.POINTER(ForwardIn), C.POINTER(ForwardOut), vp, sz, vp]),
+        'mdgat_forward': (i, [C.POINTER(ForwardCfg), vp, vp, C.POINTER(ForwardIn), C.POINTER(ForwardOut), vp, sz, vp]),
+        'mdgat_linear_i8_scratch_bytes': (sz, [i, i, i]),
+        'mdgat_linear_i8': (i, [vp, i, i, vp, i, i, vp, vp, vp, vp, i, vp, i, i, i, i, i, vp, vp]),
         'mdgat_linear_f64': (i, [vp, i, i, vp, i, i, vp, i, vp, vp, i, vp, i, i, i, d, i, vp]),
         'mdgat_gemm_nt_f64': (i, [vp, i, ll, vp, i, ll, vp, i, ll, i, i, i, i, d, vp]),
         'mdgat_encode_scratch_doubles': (sz, [i]),

@@ -93,11 +93,12 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Workspace {
     double *X, *Xk, *Xd, *Qh, *Kh, *Vh, *Msg, *Mg, *Hd, *MD, *S, *C, *u, *v, *mscratch, *skscratch;
+    double *rs128, *rs256; int8_t *xs128, *xs256;      // tcgen05 path: sliced activations + row scales
     size_t bytes;
 };
 
 // Carves the workspace; with base == nullptr only computes the size.
-Workspace carve(char* base, int B, int N, int M, bool need_logits) {
+Workspace carve(char* base, int B, int N, int M, bool need_logits, int i8_slices = 0) {
     Workspace w;
     const size_t R = (size_t)B * N + (size_t)B * M;
     size_t off = 0;
@@ -123,6 +124,11 @@ Workspace carve(char* base, int B, int N, int M, bool need_logits) {
     w.v = take((size_t)B * (M + 1));
     w.mscratch = take(4 * R + 8);
     w.skscratch = take(sinkhorn_scratch_doubles(B, N, M));
+    const size_t Rpad = (R + 127) / 128 * 128;
+    w.rs128 = take(i8_slices ? Rpad : 0);
+    w.rs256 = take(i8_slices ? Rpad : 0);
+    w.xs128 = reinterpret_cast<int8_t*>(take(i8_slices ? (ozaki_slices_bytes((int)R, 128, i8_slices) + 7) / 8 : 0));
+    w.xs256 = reinterpret_cast<int8_t*>(take(i8_slices ? (ozaki_slices_bytes((int)R, 256, i8_slices) + 7) / 8 : 0));
     w.bytes = off;
     return w;
 }
@@ -196,11 +202,12 @@ size_t mdgat_weight_blob_doubles(int L) { return BlobLayout(L).total; }
 size_t mdgat_forward_workspace_bytes(const mdgat_forward_cfg* cfg) {
     bool need = false;
     for (int i = 0; i < 2 * cfg->L; ++i) need = need || (cfg->layer_k && cfg->layer_k[i] > 0);
-    return carve(nullptr, cfg->B, cfg->N, cfg->M, need).bytes;
+    return carve(nullptr, cfg->B, cfg->N, cfg->M, need, cfg->gemm_mode == MDGAT_GEMM_TCGEN05_I8 ? cfg->gemm_slices : 0).bytes;
 }
 
-int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const mdgat_forward_in* in,
-                  const mdgat_forward_out* out, void* d_workspace, size_t workspace_bytes, void* stream) {
+int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const void* d_weights_i8,
+                  const mdgat_forward_in* in, const mdgat_forward_out* out, void* d_workspace, size_t workspace_bytes,
+                  void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int B = cfg->B, N = cfg->N, M = cfg->M, L = cfg->L;
     MDGAT_REQUIRE(B > 0 && N > 0 && M > 0 && L > 0, "mdgat_forward: B, N, M, L must be positive (got %d %d %d %d)", B, N, M, L);
@@ -221,7 +228,10 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const m
         MDGAT_REQUIRE(N == M, "triplet loss needs N == M (the reference raises IndexError otherwise, mdgat.py:537)");
         MDGAT_REQUIRE(cfg->match_mode == MDGAT_MATCH_DUSTBIN, "triplet loss is defined on the dustbin match variant");
     }
-    Workspace w = carve(reinterpret_cast<char*>(d_workspace), B, N, M, need);
+    const bool i8 = cfg->gemm_mode == MDGAT_GEMM_TCGEN05_I8;
+    const int S8 = cfg->gemm_slices;
+    MDGAT_REQUIRE(!i8 || (d_weights_i8 != nullptr && S8 >= 6 && S8 <= 8), "tcgen05 int8 GEMM mode needs the sliced weight blob and 6..8 slices");
+    Workspace w = carve(reinterpret_cast<char*>(d_workspace), B, N, M, need, i8 ? S8 : 0);
     if (w.bytes > workspace_bytes) {
         mdgat_host::set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
         return MDGAT_ERR_WORKSPACE;
@@ -243,13 +253,26 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const m
         const bool cross = (l & 1) != 0;                  // names = ['self','cross']*L (mdgat.py:353)
         const int k = cfg->layer_k[l];
         // q/k/v of both sides with the shared layer weights (mdgat.py:227-232, :270)
-        GemmParams p;
-        memset(&p, 0, sizeof(p));
-        p.A0 = w.X; p.lda0 = LDX; p.K0 = DMODEL; p.W = Wt + lo.wqkv; p.ldw = DMODEL; p.bias = Wt + lo.bqkv;
-        p.R = R; p.Nout = 3 * DMODEL; p.K = DMODEL; p.scale = 1.0; p.w_tiled = 1;
-        p.Qh = w.Qh; p.Kh = w.Kh; p.Vh = w.Vh; p.rows0 = R0; p.n0 = N; p.n1 = M;
+        const size_t slice_tile = (size_t)S8 * 64 * 128;                // bytes of one (column tile, k chunk) of W slices
+        const unsigned char* Li8 = i8 ? reinterpret_cast<const unsigned char*>(d_weights_i8) + (size_t)l * (slice_tile * 18 + 768 * 8) : nullptr;
+        const double* cs8 = i8 ? reinterpret_cast<const double*>(Li8 + slice_tile * 18) : nullptr;
         prof_mark(ST_GEMM, st);
-        MDGAT_CUDA_OK(launch_gemm(p, EPI_QKV, 1, st));
+        if (i8) {
+            MDGAT_CUDA_OK(launch_slice_rows(w.X, LDX, DMODEL, nullptr, 0, 0, R, S8, w.xs128, w.rs128, st));
+            OzGemmArgs a;
+            memset(&a, 0, sizeof(a));
+            a.Xs = w.xs128; a.rowscale = w.rs128; a.Ws = reinterpret_cast<const int8_t*>(Li8); a.colscale = cs8;
+            a.bias = Wt + lo.bqkv; a.R = R; a.Nout = 3 * DMODEL; a.K = DMODEL; a.epi = EPI_QKV;
+            a.Qh = w.Qh; a.Kh = w.Kh; a.Vh = w.Vh; a.rows0 = R0; a.n0 = N; a.n1 = M;
+            MDGAT_CUDA_OK(launch_ozaki_gemm(a, S8, st));
+        } else {
+            GemmParams p;
+            memset(&p, 0, sizeof(p));
+            p.A0 = w.X; p.lda0 = LDX; p.K0 = DMODEL; p.W = Wt + lo.wqkv; p.ldw = DMODEL; p.bias = Wt + lo.bqkv;
+            p.R = R; p.Nout = 3 * DMODEL; p.K = DMODEL; p.scale = 1.0; p.w_tiled = 1;
+            p.Qh = w.Qh; p.Kh = w.Kh; p.Vh = w.Vh; p.rows0 = R0; p.n0 = N; p.n1 = M;
+            MDGAT_CUDA_OK(launch_gemm(p, EPI_QKV, 1, st));
+        }
         prof_mark(k > 0 ? ST_ATTN_TOPK : ST_ATTN_FULL, st);
         // messages: side 0 reads side (cross ? 1 : 0), side 1 the other way round (mdgat.py:263-266)
         AttnSides ps;
@@ -259,8 +282,21 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const m
         prof_mark(ST_GEMM, st);
         // the merge conv (mdgat.py:237) is folded into the first MLP conv by the weight packer
         // mlp(cat[x, message]) : 256 -> 256 (BN folded, ReLU) -> 128, then the residual (mdgat.py:248, :274)
-        MDGAT_CUDA_OK(linear(w.X, LDX, DMODEL, w.Msg, LDX, DMODEL, Wt + lo.w1, 2 * DMODEL, Wt + lo.b1, nullptr, 0, w.Hd, LDHID, R, 2 * DMODEL, 1.0, 1, st));
-        MDGAT_CUDA_OK(linear(w.Hd, LDHID, 2 * DMODEL, nullptr, 0, 0, Wt + lo.w2, 2 * DMODEL, Wt + lo.b2, w.X, LDX, w.X, LDX, R, DMODEL, 1.0, 0, st));
+        if (i8) {
+            OzGemmArgs a;
+            memset(&a, 0, sizeof(a));
+            MDGAT_CUDA_OK(launch_slice_rows(w.X, LDX, DMODEL, w.Msg, LDX, DMODEL, R, S8, w.xs256, w.rs256, st));
+            a.Xs = w.xs256; a.rowscale = w.rs256; a.Ws = reinterpret_cast<const int8_t*>(Li8 + slice_tile * 6); a.colscale = cs8 + 384;
+            a.bias = Wt + lo.b1; a.Y = w.Hd; a.ldy = LDHID; a.R = R; a.Nout = 2 * DMODEL; a.K = 2 * DMODEL; a.relu = 1; a.epi = EPI_PLAIN;
+            MDGAT_CUDA_OK(launch_ozaki_gemm(a, S8, st));
+            MDGAT_CUDA_OK(launch_slice_rows(w.Hd, LDHID, 2 * DMODEL, nullptr, 0, 0, R, S8, w.xs256, w.rs256, st));
+            a.Ws = reinterpret_cast<const int8_t*>(Li8 + slice_tile * 14); a.colscale = cs8 + 640;
+            a.bias = Wt + lo.b2; a.Res = w.X; a.ldres = LDX; a.Y = w.X; a.ldy = LDX; a.Nout = DMODEL; a.relu = 0;
+            MDGAT_CUDA_OK(launch_ozaki_gemm(a, S8, st));
+        } else {
+            MDGAT_CUDA_OK(linear(w.X, LDX, DMODEL, w.Msg, LDX, DMODEL, Wt + lo.w1, 2 * DMODEL, Wt + lo.b1, nullptr, 0, w.Hd, LDHID, R, 2 * DMODEL, 1.0, 1, st));
+            MDGAT_CUDA_OK(linear(w.Hd, LDHID, 2 * DMODEL, nullptr, 0, 0, Wt + lo.w2, 2 * DMODEL, Wt + lo.b2, w.X, LDX, w.X, LDX, R, DMODEL, 1.0, 0, st));
+        }
     }
     // final_proj (mdgat.py:397) and scores = mdesc0^T mdesc1 / sqrt(128) (:430-431) into the couplings
     MDGAT_CUDA_OK(linear(w.X, LDX, DMODEL, nullptr, 0, 0, Wt + lay.wf, DMODEL, Wt + lay.bf, nullptr, 0, w.MD, LDX, R, DMODEL, 1.0, 0, st));
@@ -292,6 +328,27 @@ int mdgat_linear_f64(const double* d_X0, int ldx0, int K0, const double* d_X1, i
     MDGAT_REQUIRE(d_X1 == nullptr || ((K0 % 32) == 0 && (ldx1 % 2) == 0), "mdgat_linear_f64: with a second input K0 must be a multiple of 32");
     MDGAT_CUDA_OK(linear(d_X0, ldx0, K0, d_X1, ldx1, d_X1 ? K1 : 0, d_W, ldw, d_bias, d_Res, ldres, d_Y, ldy, R, Nout,
                          scale, relu, reinterpret_cast<cudaStream_t>(stream), 0));
+    return MDGAT_OK;
+}
+
+size_t mdgat_linear_i8_scratch_bytes(int R, int K, int slices) { return ozaki_slices_bytes(R, K, slices) + (size_t)((R + 127) / 128 * 128) * sizeof(double); }
+
+int mdgat_linear_i8(const double* d_X0, int ldx0, int K0, const double* d_X1, int ldx1, int K1,
+                    const void* d_Wslices, const double* d_colscale, const double* d_bias, const double* d_Res, int ldres,
+                    double* d_Y, int ldy, int R, int Nout, int relu, int slices, void* d_scratch, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int K = K0 + (d_X1 ? K1 : 0);
+    MDGAT_REQUIRE(slices >= 6 && slices <= 8, "mdgat_linear_i8: 6..8 slices");
+    MDGAT_REQUIRE((K0 % 128) == 0 && (K == 128 || K == 256 || K == 512) && (Nout % 64) == 0, "mdgat_linear_i8: K0 multiple of 128, K in {128,256,512}, Nout multiple of 64");
+    MDGAT_REQUIRE((ldx0 % 2) == 0 && (ldy % 2) == 0, "mdgat_linear_i8: even leading dimensions");
+    double* rs = reinterpret_cast<double*>(d_scratch);
+    int8_t* xs = reinterpret_cast<int8_t*>(rs + (size_t)((R + 127) / 128 * 128));
+    MDGAT_CUDA_OK(launch_slice_rows(d_X0, ldx0, K0, d_X1, ldx1, d_X1 ? K1 : 0, R, slices, xs, rs, st));
+    OzGemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.Xs = xs; a.rowscale = rs; a.Ws = reinterpret_cast<const int8_t*>(d_Wslices); a.colscale = d_colscale; a.bias = d_bias;
+    a.Res = d_Res; a.ldres = ldres; a.Y = d_Y; a.ldy = ldy; a.R = R; a.Nout = Nout; a.K = K; a.relu = relu; a.epi = EPI_PLAIN;
+    MDGAT_CUDA_OK(launch_ozaki_gemm(a, slices, st));
     return MDGAT_OK;
 }
 

@@ -68,6 +68,20 @@ cudaError_t launch_match_extract(const MatchParams& p, cudaStream_t st);
 
 cudaError_t launch_knn(const double* x, const double* src, int64_t* idx, int B, int n, int m, int k, cudaStream_t st);
 
+// float64-faithful GEMM on tcgen05 int8 tensor cores (Ozaki splitting), see ozaki_gemm.cu
+struct OzGemmArgs {
+    const int8_t* Xs; const double* rowscale;     // from launch_slice_rows
+    const int8_t* Ws; const double* colscale;     // from packing.slice_weight
+    const double* bias; const double* Res; int ldres;
+    double* Y; int ldy;
+    int R, Nout, K, relu, epi;
+    double *Qh, *Kh, *Vh; int rows0, n0, n1;
+};
+size_t ozaki_slices_bytes(int R, int K, int S);
+cudaError_t launch_slice_rows(const double* A0, int ld0, int K0, const double* A1, int ld1, int K1, int R, int S,
+                              int8_t* Xs, double* rowscale, cudaStream_t st);
+cudaError_t launch_ozaki_gemm(const OzGemmArgs& a, int S, cudaStream_t st);
+
 // Batched Kabsch registration + match statistics (one CTA per pair)
 cudaError_t launch_register_pairs(const void* kpts0, const void* kpts1, int kp_dtype, const int64_t* matches0,
                                   const int16_t* gt0, const double* T_gt, int B, int N, int M,

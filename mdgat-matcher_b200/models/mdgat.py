@@ -198,6 +198,7 @@ class MDGAT(nn.Module):
         self.triplet_loss_gamma = config['triplet_loss_gamma']
         self.train_step = config['train_step']
         self._packed = None          # (key, blob)
+        self._packed_i8 = None       # (key, slices, int8 blob) for the tcgen05 GEMM mode
         self._workspace = None       # uint8 tensor
         self._layer_k = None
 
@@ -218,6 +219,23 @@ class MDGAT(nn.Module):
                 blob = packing.pack_state_dict(sd, self.config['L'])
             self._packed = (key, blob)
         return self._packed[1]
+
+    def gemm_engine(self):
+        """config['gemm']: 'tcgen05_i8' (float64-faithful Ozaki splitting on the int8 tensor cores, default)
+        or 'dmma' (FP64 pipe); config['gemm_slices']: int8 digit planes per operand (6..8, default 7)."""
+        mode = self.config.get('gemm', 'tcgen05_i8')
+        if mode not in ('tcgen05_i8', 'dmma'):
+            raise ValueError("config['gemm'] must be 'tcgen05_i8' or 'dmma'")
+        return mode, int(self.config.get('gemm_slices', 7))
+
+    def packed_weights_i8(self, slices):
+        key = (self._weights_key(), slices)
+        if self._packed_i8 is None or self._packed_i8[0] != key:
+            sd = {k: v for k, v in self.state_dict(keep_vars=True).items()}
+            with torch.no_grad():
+                blob = packing.pack_state_dict_i8(sd, self.config['L'], slices)
+            self._packed_i8 = (key, blob)
+        return self._packed_i8[1]
 
     # ------------------------------------------------------------------ forward
     def _gt(self, data):
@@ -268,6 +286,8 @@ class MDGAT(nn.Module):
             if sc[0].dtype != sc[1].dtype:
                 sc = [t.double() for t in sc]
             blob = self.packed_weights()
+            gemm_mode, gemm_slices = self.gemm_engine()
+            blob_i8 = self.packed_weights_i8(gemm_slices) if gemm_mode == 'tcgen05_i8' else None
             if blob.device != dev:
                 raise RuntimeError('module parameters live on %s but inputs on %s' % (blob.device, dev))
 
@@ -305,7 +325,9 @@ class MDGAT(nn.Module):
                 loss_mode=loss_mode, triplet_gamma=float(self.triplet_loss_gamma),
                 in_dtype=_capi.F64 if in_dtype == torch.float64 else _capi.F32,
                 score_dtype=_capi.F64 if sc[0].dtype == torch.float64 else _capi.F32,
-                write_Z=int(write_Z))
+                write_Z=int(write_Z),
+                gemm_mode=_capi.GEMM_TCGEN05_I8 if gemm_mode == 'tcgen05_i8' else _capi.GEMM_DMMA_F64,
+                gemm_slices=gemm_slices)
             need = _capi.lib.mdgat_forward_workspace_bytes(ctypes.byref(cfg))
             ws = self._workspace
             if ws is None or ws.device != dev or ws.numel() < need:
@@ -318,7 +340,8 @@ class MDGAT(nn.Module):
             fout = _capi.ForwardOut(matches0.data_ptr(), matches1.data_ptr(), ms0.data_ptr(), ms1.data_ptr(),
                                     loss.data_ptr(), nvalid.data_ptr(), Z.data_ptr() if Z is not None else None)
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _capi.check(_capi.lib.mdgat_forward(ctypes.byref(cfg), blob.data_ptr(), ctypes.byref(fin),
+            _capi.check(_capi.lib.mdgat_forward(ctypes.byref(cfg), blob.data_ptr(),
+                                                blob_i8.data_ptr() if blob_i8 is not None else None, ctypes.byref(fin),
                                                 ctypes.byref(fout), ws.data_ptr(), ws.numel(), stream))
             if self.loss_method == 'gap_loss':
                 loss = losses.gap_loss(Z, gt0_t.long(), gt1_t.long(), self.triplet_loss_gamma)

@@ -237,3 +237,30 @@ def prepare_pairs(kp1, kp2, pose1, pose2, T_cam0_velo, threshold, mutual_check=F
                                                   int(bool(mutual_check)), m1.data_ptr(), m2.data_ptr(), T.data_ptr(),
                                                   rep.data_ptr(), _stream(dev)))
     return m1, m2, T, rep
+
+
+def linear_i8(x, w, bias=None, relu=False, residual=None, x2=None, slices=7):
+    """y = act([x | x2] w^T + bias) + residual through the tcgen05 int8 tensor cores (Ozaki splitting,
+    float64-faithful). x (R,K0) [+ x2 (R,K1)], K in {128,256,512}; w (Nout,K) float64, Nout % 64 == 0."""
+    from . import packing
+    _need_cuda(x)
+    x = x.double().contiguous()
+    R, K0 = x.shape
+    K1 = 0
+    if x2 is not None:
+        x2 = x2.double().contiguous()
+        K1 = x2.shape[1]
+    w = w.double().contiguous()
+    nout = w.shape[0]
+    wsl, cs = packing.slice_weight(w, slices)
+    y = torch.empty((R, nout), dtype=torch.float64, device=x.device)
+    b = bias.double().contiguous() if bias is not None else None
+    r = residual.double().contiguous() if residual is not None else None
+    scratch = torch.empty(_capi.lib.mdgat_linear_i8_scratch_bytes(R, K0 + K1, slices), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _capi.check(_capi.lib.mdgat_linear_i8(
+            x.data_ptr(), x.stride(0), K0, x2.data_ptr() if x2 is not None else None, x2.stride(0) if x2 is not None else 0, K1,
+            wsl.data_ptr(), cs.data_ptr(), b.data_ptr() if b is not None else None,
+            r.data_ptr() if r is not None else None, r.stride(0) if r is not None else 0,
+            y.data_ptr(), y.stride(0), R, nout, int(relu), slices, scratch.data_ptr(), _stream(x.device)))
+    return y

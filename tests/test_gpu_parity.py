@@ -51,6 +51,35 @@ def test_linear_concat_inputs(dev):
     assert np.abs(got - want).max() < 1e-11
 
 
+@pytest.mark.parametrize('R,K,Nout,slices', [(128, 128, 64, 7), (1000, 128, 384, 7), (333, 256, 256, 7), (4096, 256, 128, 8), (500, 128, 128, 6)])
+def test_linear_i8_tensor_core_gemm_is_float64_faithful(dev, R, K, Nout, slices):
+    """tcgen05 int8 (Ozaki) GEMM against a float64 numpy product: error relative to |x|max |w|max sqrt(K)
+    must be at float64 rounding level for 7-8 slices (2^-42 class for 6)."""
+    from mdgat_matcher_b200 import ops
+    rng = np.random.default_rng(R + K + Nout)
+    x = rng.normal(size=(R, K)) * np.exp(rng.normal(size=(R, 1)) * 2)       # rows of very different scale
+    x[:, ::7] *= 1e-6                                                       # and tiny entries inside a row
+    w = rng.normal(size=(Nout, K)) / np.sqrt(K) * np.exp(rng.normal(size=(Nout, 1)))
+    b = rng.normal(size=Nout)
+    res = rng.normal(size=(R, Nout))
+    want = np.maximum(x @ w.T + b, 0) + res
+    got = ops.linear_i8(_t(x, dev), _t(w, dev), _t(b, dev), relu=True, residual=_t(res, dev), slices=slices).cpu().numpy()
+    scale = np.abs(x).max(1, keepdims=True) * np.abs(w).max(1)[None, :] * np.sqrt(K)
+    err = np.abs(got - want) / scale
+    assert err.max() < {6: 3e-12, 7: 5e-14, 8: 5e-14}[slices], err.max()       # 8: limited by the +residual rounding
+
+
+def test_linear_i8_concat_and_zero_rows(dev):
+    from mdgat_matcher_b200 import ops
+    rng = np.random.default_rng(8)
+    x0 = rng.normal(size=(260, 128)); x1 = rng.normal(size=(260, 128)) * 30
+    x0[5] = 0; x1[5] = 0                                                    # an all-zero row
+    w = rng.normal(size=(256, 256)) / 16
+    want = np.concatenate([x0, x1], 1) @ w.T
+    got = ops.linear_i8(_t(x0, dev), _t(w, dev), x2=_t(x1, dev)).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-11 and np.abs(got[5]).max() == 0.0
+
+
 def test_gemm_nt_batched(dev):
     from mdgat_matcher_b200 import ops
     rng = np.random.default_rng(6)
@@ -219,11 +248,12 @@ E2E = ['cfg1_seeded_L4_n128', 'ckpt_L9_n512_T100', 'ckpt_L9_ragged_gap', 'ckpt_L
        'seeded_L9_n512', 'ckpt_L9_duplicates', 'ckpt_L9_sgloss_mutual', 'ckpt_L9_n2048', 'ckpt_L9_n512_b8']
 
 
+@pytest.mark.parametrize('gemm', ['tcgen05_i8', 'dmma'])
 @pytest.mark.parametrize('name', E2E)
-def test_forward_matches_reference_golden(dev, name):
+def test_forward_matches_reference_golden(dev, name, gemm):
     rec = load_golden(name)
     case = rec['case']
-    net = _build_module(case, dev, extra={'return_assignment': True})
+    net = _build_module(case, dev, extra={'return_assignment': True, 'gemm': gemm})
     data = {k: _t(v, dev) for k, v in golden_inputs(rec).items()}
     out = net(data)
     torch.cuda.synchronize()

@@ -81,7 +81,7 @@ typedef struct {
     int score_dtype;          /* element type of scores0/1 (the reference does not cast them) */
     int write_Z;              /* also materialise Z (B,N+1,M+1) into d_Z (debug / other losses) */
     int gemm_mode;            /* MDGAT_GEMM_* */
-    int gemm_slices;          /* int8 slices per operand in MDGAT_GEMM_TCGEN05_I8 mode (6..8; 7 = 49 bits) */
+    int gemm_slices;          /* int8 slices per operand in MDGAT_GEMM_TCGEN05_I8 mode (6 or 7; 7 = 49 bits) */
 } mdgat_forward_cfg;
 
 typedef struct {

@@ -93,7 +93,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Workspace {
     double *X, *Xk, *Xd, *Qh, *Kh, *Vh, *Msg, *Mg, *Hd, *MD, *S, *C, *u, *v, *mscratch, *skscratch;
-    double *rs128, *rs256; int8_t *xs128, *xs256;      // tcgen05 path: sliced activations + row scales
+    double *rsX, *rsM, *rsH; int8_t *xsX, *xsM, *xsH;   // tcgen05 path: int8 slice planes + row scales of X, Msg, Hd (2 chunks)
     size_t bytes;
 };
 
@@ -125,10 +125,13 @@ Workspace carve(char* base, int B, int N, int M, bool need_logits, int i8_slices
     w.mscratch = take(4 * R + 8);
     w.skscratch = take(sinkhorn_scratch_doubles(B, N, M));
     const size_t Rpad = (R + 127) / 128 * 128;
-    w.rs128 = take(i8_slices ? Rpad : 0);
-    w.rs256 = take(i8_slices ? Rpad : 0);
-    w.xs128 = reinterpret_cast<int8_t*>(take(i8_slices ? (ozaki_slices_bytes((int)R, 128, i8_slices) + 7) / 8 : 0));
-    w.xs256 = reinterpret_cast<int8_t*>(take(i8_slices ? (ozaki_slices_bytes((int)R, 256, i8_slices) + 7) / 8 : 0));
+    w.rsX = take(i8_slices ? Rpad : 0);
+    w.rsM = take(i8_slices ? Rpad : 0);
+    w.rsH = take(i8_slices ? 2 * Rpad : 0);
+    const size_t chunk8 = i8_slices ? (ozaki_slices_bytes((int)R, 128, i8_slices) + 7) / 8 : 0;
+    w.xsX = reinterpret_cast<int8_t*>(take(chunk8));
+    w.xsM = reinterpret_cast<int8_t*>(take(chunk8));
+    w.xsH = reinterpret_cast<int8_t*>(take(2 * chunk8));
     w.bytes = off;
     return w;
 }
@@ -230,7 +233,7 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
     }
     const bool i8 = cfg->gemm_mode == MDGAT_GEMM_TCGEN05_I8;
     const int S8 = cfg->gemm_slices;
-    MDGAT_REQUIRE(!i8 || (d_weights_i8 != nullptr && S8 >= 6 && S8 <= 8), "tcgen05 int8 GEMM mode needs the sliced weight blob and 6..8 slices");
+    MDGAT_REQUIRE(!i8 || (d_weights_i8 != nullptr && S8 >= 6 && S8 <= 7), "tcgen05 int8 GEMM mode needs the sliced weight blob and 6 or 7 slices");
     Workspace w = carve(reinterpret_cast<char*>(d_workspace), B, N, M, need, i8 ? S8 : 0);
     if (w.bytes > workspace_bytes) {
         mdgat_host::set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
@@ -253,15 +256,17 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
         const bool cross = (l & 1) != 0;                  // names = ['self','cross']*L (mdgat.py:353)
         const int k = cfg->layer_k[l];
         // q/k/v of both sides with the shared layer weights (mdgat.py:227-232, :270)
-        const size_t slice_tile = (size_t)S8 * 64 * 128;                // bytes of one (column tile, k chunk) of W slices
-        const unsigned char* Li8 = i8 ? reinterpret_cast<const unsigned char*>(d_weights_i8) + (size_t)l * (slice_tile * 18 + 768 * 8) : nullptr;
-        const double* cs8 = i8 ? reinterpret_cast<const double*>(Li8 + slice_tile * 18) : nullptr;
+        // int8 blob of layer l: [qkv: 12 col tiles x 1 k chunk][mlp0: 8 x 2][mlp3: 4 x 2] slice tiles, then the column
+        // scales qkv[384] mlp0[2][256] mlp3[2][128]
+        const size_t slice_tile = (size_t)S8 * 32 * 128;                // bytes of one (column tile, k chunk) of W slices
+        const unsigned char* Li8 = i8 ? reinterpret_cast<const unsigned char*>(d_weights_i8) + (size_t)l * (slice_tile * 36 + 1152 * 8) : nullptr;
+        const double* cs8 = i8 ? reinterpret_cast<const double*>(Li8 + slice_tile * 36) : nullptr;
         prof_mark(ST_GEMM, st);
         if (i8) {
-            MDGAT_CUDA_OK(launch_slice_rows(w.X, LDX, DMODEL, nullptr, 0, 0, R, S8, w.xs128, w.rs128, st));
+            MDGAT_CUDA_OK(launch_slice_rows(w.X, LDX, DMODEL, nullptr, 0, 0, R, S8, w.xsX, w.rsX, st));
             OzGemmArgs a;
             memset(&a, 0, sizeof(a));
-            a.Xs = w.xs128; a.rowscale = w.rs128; a.Ws = reinterpret_cast<const int8_t*>(Li8); a.colscale = cs8;
+            a.Xs[0] = w.xsX; a.rowscale[0] = w.rsX; a.Ws = reinterpret_cast<const int8_t*>(Li8); a.colscale = cs8;
             a.bias = Wt + lo.bqkv; a.R = R; a.Nout = 3 * DMODEL; a.K = DMODEL; a.epi = EPI_QKV;
             a.Qh = w.Qh; a.Kh = w.Kh; a.Vh = w.Vh; a.rows0 = R0; a.n0 = N; a.n1 = M;
             MDGAT_CUDA_OK(launch_ozaki_gemm(a, S8, st));
@@ -285,12 +290,14 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
         if (i8) {
             OzGemmArgs a;
             memset(&a, 0, sizeof(a));
-            MDGAT_CUDA_OK(launch_slice_rows(w.X, LDX, DMODEL, w.Msg, LDX, DMODEL, R, S8, w.xs256, w.rs256, st));
-            a.Xs = w.xs256; a.rowscale = w.rs256; a.Ws = reinterpret_cast<const int8_t*>(Li8 + slice_tile * 6); a.colscale = cs8 + 384;
+            // k chunk 0 = x (its slice planes are the ones the q/k/v projection used), k chunk 1 = message
+            MDGAT_CUDA_OK(launch_slice_rows(w.Msg, LDX, DMODEL, nullptr, 0, 0, R, S8, w.xsM, w.rsM, st));
+            a.Xs[0] = w.xsX; a.rowscale[0] = w.rsX; a.Xs[1] = w.xsM; a.rowscale[1] = w.rsM; a.Ws = reinterpret_cast<const int8_t*>(Li8 + slice_tile * 12); a.colscale = cs8 + 384;
             a.bias = Wt + lo.b1; a.Y = w.Hd; a.ldy = LDHID; a.R = R; a.Nout = 2 * DMODEL; a.K = 2 * DMODEL; a.relu = 1; a.epi = EPI_PLAIN;
             MDGAT_CUDA_OK(launch_ozaki_gemm(a, S8, st));
-            MDGAT_CUDA_OK(launch_slice_rows(w.Hd, LDHID, 2 * DMODEL, nullptr, 0, 0, R, S8, w.xs256, w.rs256, st));
-            a.Ws = reinterpret_cast<const int8_t*>(Li8 + slice_tile * 14); a.colscale = cs8 + 640;
+            MDGAT_CUDA_OK(launch_slice_rows(w.Hd, LDHID, 2 * DMODEL, nullptr, 0, 0, R, S8, w.xsH, w.rsH, st));
+            a.Xs[0] = w.xsH; a.rowscale[0] = w.rsH; a.Xs[1] = w.xsH + ozaki_slices_bytes(R, 128, S8); a.rowscale[1] = w.rsH + (size_t)((R + 127) / 128 * 128);
+            a.Ws = reinterpret_cast<const int8_t*>(Li8 + slice_tile * 28); a.colscale = cs8 + 896;
             a.bias = Wt + lo.b2; a.Res = w.X; a.ldres = LDX; a.Y = w.X; a.ldy = LDX; a.Nout = DMODEL; a.relu = 0;
             MDGAT_CUDA_OK(launch_ozaki_gemm(a, S8, st));
         } else {
@@ -331,22 +338,24 @@ int mdgat_linear_f64(const double* d_X0, int ldx0, int K0, const double* d_X1, i
     return MDGAT_OK;
 }
 
-size_t mdgat_linear_i8_scratch_bytes(int R, int K, int slices) { return ozaki_slices_bytes(R, K, slices) + (size_t)((R + 127) / 128 * 128) * sizeof(double); }
+size_t mdgat_linear_i8_scratch_bytes(int R, int K, int slices) { return ozaki_slices_bytes(R, K, slices) + (size_t)((R + 127) / 128 * 128) * (K / 128) * sizeof(double); }
 
 int mdgat_linear_i8(const double* d_X0, int ldx0, int K0, const double* d_X1, int ldx1, int K1,
                     const void* d_Wslices, const double* d_colscale, const double* d_bias, const double* d_Res, int ldres,
                     double* d_Y, int ldy, int R, int Nout, int relu, int slices, void* d_scratch, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int K = K0 + (d_X1 ? K1 : 0);
-    MDGAT_REQUIRE(slices >= 6 && slices <= 8, "mdgat_linear_i8: 6..8 slices");
-    MDGAT_REQUIRE((K0 % 128) == 0 && (K == 128 || K == 256 || K == 512) && (Nout % 64) == 0, "mdgat_linear_i8: K0 multiple of 128, K in {128,256,512}, Nout multiple of 64");
+    MDGAT_REQUIRE(slices >= 6 && slices <= 7, "mdgat_linear_i8: 6 or 7 slices");
+    MDGAT_REQUIRE((K0 % 128) == 0 && (K == 128 || K == 256) && (Nout % 32) == 0 && Nout <= 384, "mdgat_linear_i8: K0 multiple of 128, K in {128,256}, Nout multiple of 32 and <= 384");
     MDGAT_REQUIRE((ldx0 % 2) == 0 && (ldy % 2) == 0, "mdgat_linear_i8: even leading dimensions");
+    MDGAT_REQUIRE(!(relu && d_Res == d_Y && d_Res && K > 128), "mdgat_linear_i8: in-place residual with ReLU needs K == 128");
     double* rs = reinterpret_cast<double*>(d_scratch);
-    int8_t* xs = reinterpret_cast<int8_t*>(rs + (size_t)((R + 127) / 128 * 128));
+    int8_t* xs = reinterpret_cast<int8_t*>(rs + (size_t)((R + 127) / 128 * 128) * (K / 128));
     MDGAT_CUDA_OK(launch_slice_rows(d_X0, ldx0, K0, d_X1, ldx1, d_X1 ? K1 : 0, R, slices, xs, rs, st));
     OzGemmArgs a;
     memset(&a, 0, sizeof(a));
-    a.Xs = xs; a.rowscale = rs; a.Ws = reinterpret_cast<const int8_t*>(d_Wslices); a.colscale = d_colscale; a.bias = d_bias;
+    a.Xs[0] = xs; a.rowscale[0] = rs; a.Xs[1] = xs + ozaki_slices_bytes(R, 128, slices); a.rowscale[1] = rs + (size_t)((R + 127) / 128 * 128);
+    a.Ws = reinterpret_cast<const int8_t*>(d_Wslices); a.colscale = d_colscale; a.bias = d_bias;
     a.Res = d_Res; a.ldres = ldres; a.Y = d_Y; a.ldy = ldy; a.R = R; a.Nout = Nout; a.K = K; a.relu = relu; a.epi = EPI_PLAIN;
     MDGAT_CUDA_OK(launch_ozaki_gemm(a, slices, st));
     return MDGAT_OK;

@@ -70,7 +70,7 @@ cudaError_t launch_knn(const double* x, const double* src, int64_t* idx, int B, 
 
 // float64-faithful GEMM on tcgen05 int8 tensor cores (Ozaki splitting), see ozaki_gemm.cu
 struct OzGemmArgs {
-    const int8_t* Xs; const double* rowscale;     // from launch_slice_rows
+    const int8_t* Xs[2]; const double* rowscale[2];   // per 128-column k chunk, from launch_slice_rows
     const int8_t* Ws; const double* colscale;     // from packing.slice_weight
     const double* bias; const double* Res; int ldres;
     double* Y; int ldy;
@@ -78,6 +78,7 @@ struct OzGemmArgs {
     double *Qh, *Kh, *Vh; int rows0, n0, n1;
 };
 size_t ozaki_slices_bytes(int R, int K, int S);
+// chunk c (128 columns) of the input goes to Xs + c * ozaki_slices_bytes(R, 128, S) and rowscale + c * Rpad
 cudaError_t launch_slice_rows(const double* A0, int ld0, int K0, const double* A1, int ld1, int K1, int R, int S,
                               int8_t* Xs, double* rowscale, cudaStream_t st);
 cudaError_t launch_ozaki_gemm(const OzGemmArgs& a, int S, cudaStream_t st);

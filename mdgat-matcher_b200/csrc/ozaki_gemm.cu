@@ -26,28 +26,31 @@
 
 namespace mdgat {
 
-constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KC = 128;
+constexpr int OZ_BM = 128, OZ_BN = 32, OZ_KC = 128;
 constexpr int OZ_XTILE = OZ_BM * OZ_KC, OZ_WTILE = OZ_BN * OZ_KC;       // bytes per slice tile
-constexpr int OZ_THREADS = 128;
+constexpr int OZ_WSTAGES = 3;                                             // W tile ring
+constexpr int OZ_EPI_THREADS = 256, OZ_THREADS = OZ_EPI_THREADS + 64;     // 8 epilogue warps + MMA warp + loader warp
+constexpr int OZ_MAXN = 384;                                               // widest GEMM (q/k/v stack): scales staged in smem
 
 DEVINL int oz_canon(int r, int k) { return (r >> 3) * (OZ_KC * 8) + (k >> 4) * 128 + (r & 7) * 16 + (k & 15); }
 
 DEVINL double pow2d(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }   // -1022 <= e <= 1023
 
 // ---------------------------------------------------------------------------------------------------
-// Slicing: one thread = 16 consecutive k of one row (8 lanes per 128-wide chunk row). Input = concat of
-// up to two row-major float64 buffers (K0 + K1 columns, both multiples of 128).
+// Slicing: one thread = 16 consecutive k of one row; the 8 lanes of a (row, 128-column chunk) share the
+// chunk's exponent. Input = concat of up to two row-major float64 buffers (K0 + K1 columns, multiples
+// of 128). rowscale[kchunk][Rpad] = 2^(e - 12).
 // ---------------------------------------------------------------------------------------------------
 template <int S>
 __global__ void __launch_bounds__(256)
 slice_rows_kernel(const double* __restrict__ A0, int ld0, int K0, const double* __restrict__ A1, int ld1, int K1,
-                  int R, int8_t* __restrict__ Xs, double* __restrict__ rowscale) {
+                  int R, int8_t* __restrict__ Xs, double* __restrict__ rowscale, size_t chunk_stride) {
     const int K = K0 + K1, tpr = K / 16;                 // threads per row
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long r = gid / tpr;
     const int kt = (int)(gid - r * tpr);                 // which 16-wide k group
     const int Rpad = ((R + OZ_BM - 1) / OZ_BM) * OZ_BM;
-    if (r >= Rpad) return;                               // warp-uniform: tpr divides 32 or is a multiple of it
+    if (r >= Rpad) return;                               // whole warps: Rpad * tpr is a multiple of 1024
     const int k0 = kt * 16;
     double x[16];
     if (r < R) {
@@ -61,18 +64,19 @@ slice_rows_kernel(const double* __restrict__ A0, int ld0, int K0, const double* 
     double mx = 0.0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) mx = fmax(mx, fabs(x[i]));
-    // row maximum over the tpr lanes of this row (tpr = 8 or 16: a power of two <= 32, lanes contiguous)
-    for (int o = 1; o < tpr && o < 32; o <<= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // maximum over the 8 lanes that share this (row, 128-column chunk)
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
     int e = 0;
     if (mx > 0.0) frexp(mx, &e);                         // mx = m * 2^e, m in [0.5, 1)  ->  |x| < 2^e
     e = max(-900, min(900, e));
-    if (kt == 0) rowscale[r] = pow2d(e - 12);
-    // digits: t = x * 2^(6-e); d = rint(t); t = (t - d) * 2^7; ...
-    const double sc = pow2d(6 - e);
     const int tile = (int)(r / OZ_BM), rr = (int)(r % OZ_BM);
     const int kchunk = k0 / OZ_KC, kk = k0 % OZ_KC;
-    const int nkc = K / OZ_KC;
-    int8_t* base = Xs + ((size_t)(tile * nkc + kchunk) * S) * OZ_XTILE + oz_canon(rr, kk);
+    if ((kt & 7) == 0) rowscale[(size_t)kchunk * Rpad + r] = pow2d(e - 12);
+    // digits: t = x * 2^(6-e); d = rint(t); t = (t - d) * 2^7; ...
+    const double sc = pow2d(6 - e);
+    int8_t* base = Xs + (size_t)kchunk * chunk_stride + ((size_t)tile * S) * OZ_XTILE + oz_canon(rr, kk);
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] *= sc;
 #pragma unroll
@@ -95,10 +99,16 @@ DEVINL uint64_t umma_desc(const void* smem, uint32_t lbo_bytes, uint32_t sbo_byt
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem);
     return (uint64_t)((a & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
-DEVINL void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
-                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+template <bool ACCUMULATE>
+DEVINL void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
+    if (ACCUMULATE)
+        asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\n"
+                     "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
+                     :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc) : "memory");
+    else
+        asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\n"
+                     "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
+                     :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc) : "memory");
 }
 DEVINL void umma_commit(uint64_t* bar) {
     const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
@@ -114,35 +124,56 @@ DEVINL void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 struct OzParams {
-    const int8_t* Xs; const double* rowscale;          // sliced activations (R padded to 128) + 2^(e_r - 12)
-    const int8_t* Ws; const double* colscale;          // sliced weights + 2^(f_n)
+    const int8_t* Xs[2]; const double* rowscale[2];    // per 128-column k chunk: slice planes [row_tile][S][128*128] + 2^(e - 12) per row
+    const int8_t* Ws; const double* colscale;          // sliced weights + 2^(f) per (k chunk, column)
     const double* bias;                                // [Nout] or null
     const double* Res; int ldres;                      // residual (may alias Y) or null
     double* Y; int ldy;
-    int R, Nout, K;                                    // K multiple of 128, Nout multiple of 64
+    int R, Nout, K;                                    // K multiple of 128, Nout multiple of 32
     int relu;
     int epi;                                           // EPI_PLAIN / EPI_QKV
     double *Qh, *Kh, *Vh; int rows0, n0, n1;
     int col_tiles_per_cta;                             // blockIdx.y selects a group of column tiles
 };
 
-// One CTA: one 128-row tile x a group of 64-column tiles. Thread 0 stages operands (bulk copies) and issues
-// the MMAs; all four warps run the epilogue, warp w owning TMEM lanes (= rows) 32w..32w+31.
+// One CTA = one 128-row tile x a group of 32-column tiles, warp specialised:
+//   warp 4, lane 0   producer + MMA issuer. For every k chunk it brings in the S slice planes of X (they stay for
+//                    all column tiles of the chunk), then walks the column tiles: W planes arrive through a 3-deep
+//                    ring of TMA bulk copies, the S(S+1)/2 slice products are issued into one of TWO TMEM accumulator
+//                    sets (S diagonals x 32 columns each), and tcgen05.commit hands the set to the epilogue and the
+//                    W stage back to the ring.
+//   warps 0..3       epilogue: thread = output row = TMEM lane. Horner over the diagonals (7 tcgen05.ld per 32
+//                    columns), scales, and -- k chunks being accumulated in float64 through the output buffer, each
+//                    with its own row/column scale -- bias, ReLU, residual or the q/k/v scatter after the last chunk.
+//                    While it works on one accumulator set the tensor core fills the other.
 template <int S>
-__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(OzParams p) {
+__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_constant__ OzParams p) {
     extern __shared__ __align__(128) unsigned char oz_smem[];
     int8_t* sX = reinterpret_cast<int8_t*>(oz_smem);                 // [S][128*128]
-    int8_t* sW = sX + (size_t)S * OZ_XTILE;                          // [S][64*128]
-    __shared__ __align__(8) uint64_t bar_load, bar_mma;
+    int8_t* sW = sX + (size_t)S * OZ_XTILE;                          // [OZ_WSTAGES][S][32*128]
+    __shared__ __align__(8) uint64_t x_full, x_free, w_full[OZ_WSTAGES], w_empty[OZ_WSTAGES], tm_full[2], tm_empty[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ double s_cs[2 * OZ_MAXN], s_bias[OZ_MAXN];             // column scales per k chunk, bias
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row_tile = blockIdx.x;
     const int nkc = p.K / OZ_KC;
+    const int Rpad = ((p.R + OZ_BM - 1) / OZ_BM) * OZ_BM;
     const int ct_begin = blockIdx.y * p.col_tiles_per_cta;
     const int ct_end = min(p.Nout / OZ_BN, ct_begin + p.col_tiles_per_cta);
+    const int nct = ct_end - ct_begin;
+    const int units = nkc * nct;                                     // unit u = (kc = u / nct, ct = ct_begin + u % nct)
 
-    if (tid == 0) { mbar_init(&bar_load, 1); mbar_init(&bar_mma, 1); mbar_fence_init(); }
-    if (warp == 0) {
+    if (tid == 0) {
+        mbar_init(&x_full, 1); mbar_init(&x_free, 1);
+#pragma unroll
+        for (int i = 0; i < OZ_WSTAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], OZ_EPI_THREADS); }
+        mbar_fence_init();
+    }
+    for (int i = tid; i < nkc * p.Nout; i += OZ_THREADS) s_cs[i] = p.colscale[i];
+    for (int i = tid; i < p.Nout; i += OZ_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.0;
+    if (warp == 8) {
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_s);
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(dst));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -151,110 +182,169 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(OzParams p) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = tmem_base_s;
-    // instruction descriptor: D = s32, A = B = signed int8, both K-major, N = 64, M = 128
-    constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+    constexpr int TM_SET = S * OZ_BN;                                // TMEM columns of one accumulator set
 
-    const int row = row_tile * OZ_BM + tid;                          // this thread's output row (TMEM lane tid)
-    const bool row_ok = row < p.R;
-    const double rs = row_ok ? p.rowscale[row] : 0.0;
-    long long hrow = 0; int npts = 0;
-    if (p.epi == EPI_QKV && row_ok) {
-        if (row < p.rows0) { const int b = row / p.n0; npts = p.n0; hrow = (long long)b * HEADS * p.n0 + (row - b * p.n0); }
-        else { const int r1 = row - p.rows0; const int b = r1 / p.n1; npts = p.n1;
-               hrow = (long long)p.rows0 * HEADS + (long long)b * HEADS * p.n1 + (r1 - b * p.n1); }
-    }
-
-    unsigned load_phase = 0, mma_phase = 0;
-    int x_resident_chunk = -1;
-    for (int ct = ct_begin; ct < ct_end; ++ct) {
-        for (int kc = 0; kc < nkc; ++kc) {
-            if (tid == 0) {
-                unsigned bytes = S * OZ_WTILE;
-                const bool need_x = (x_resident_chunk != kc);
-                if (need_x) bytes += S * OZ_XTILE;
-                mbar_expect_tx(&bar_load, bytes);
-                if (need_x) {
-                    const int8_t* xsrc = p.Xs + ((size_t)(row_tile * nkc + kc) * S) * OZ_XTILE;
+    if (warp == 9) {
+        // ------------------------------------------------------------------ loader: TMA bulk copies, runs ahead
+        if ((tid & 31) == 0 && units > 0) {
+            for (int u = 0; u < units; ++u) {
+                const int kc = u / nct, ct = ct_begin + u % nct, stage = u % OZ_WSTAGES;
+                if (u % nct == 0) {
+                    if (kc > 0) mbar_wait(&x_free, (unsigned)((kc - 1) & 1));        // MMAs of the previous chunk are done with sX
+                    mbar_expect_tx(&x_full, S * OZ_XTILE);
+                    const int8_t* xsrc = p.Xs[kc] + ((size_t)row_tile * S) * OZ_XTILE;
 #pragma unroll
-                    for (int s = 0; s < S; ++s) bulk_g2s(sX + (size_t)s * OZ_XTILE, xsrc + (size_t)s * OZ_XTILE, OZ_XTILE, &bar_load);
+                    for (int s = 0; s < S; ++s) bulk_g2s(sX + (size_t)s * OZ_XTILE, xsrc + (size_t)s * OZ_XTILE, OZ_XTILE, &x_full);
                 }
+                if (u >= OZ_WSTAGES) mbar_wait(&w_empty[stage], (unsigned)((u / OZ_WSTAGES - 1) & 1));
+                mbar_expect_tx(&w_full[stage], S * OZ_WTILE);
                 const int8_t* wsrc = p.Ws + ((size_t)(ct * nkc + kc) * S) * OZ_WTILE;
 #pragma unroll
-                for (int s = 0; s < S; ++s) bulk_g2s(sW + (size_t)s * OZ_WTILE, wsrc + (size_t)s * OZ_WTILE, OZ_WTILE, &bar_load);
-                mbar_wait(&bar_load, load_phase);
+                for (int s = 0; s < S; ++s)
+                    bulk_g2s(sW + ((size_t)stage * S + s) * OZ_WTILE, wsrc + (size_t)s * OZ_WTILE, OZ_WTILE, &w_full[stage]);
+            }
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------------------------ MMA issuer: one thread, never waits on loads it issued
+        if ((tid & 31) == 0 && units > 0) {
+            // Stacked-N issue. The S weight planes of a column tile sit back to back in shared memory, i.e. they form ONE
+            // K-major operand of S*32 rows. Multiplying activation plane s by planes 0..S-1-s in a single MMA of
+            // N = (S-s)*32 and writing it 32*s columns into the accumulator set drops product (s, t) onto diagonal
+            // s + t: the same S(S+1)/2 slice products as before, but in S wide instructions per k step instead of
+            // S(S+1)/2 narrow ones. A 128x32x32 MMA takes 45 cycles on this part (operand fetch bound, 16 in
+            // theory), a 128xNx32 one N/2 cycles from N = 128 up (tools/ubench/umma_i8_rate.cu).
+            const uint64_t xd0 = umma_desc(sX, 128, OZ_KC * 8), wd0 = umma_desc(sW, 128, OZ_KC * 8);
+            for (int u = 0; u < units; ++u) {
+                const int kc = u / nct, stage = u % OZ_WSTAGES, set = u & 1;
+                if (u % nct == 0) mbar_wait(&x_full, (unsigned)(kc & 1));
+                mbar_wait(&w_full[stage], (unsigned)((u / OZ_WSTAGES) & 1));
+                if (u >= 2) mbar_wait(&tm_empty[set], (unsigned)((u / 2 - 1) & 1));   // epilogue drained this accumulator set
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                // all slice products of this k chunk, diagonal by diagonal
+                const uint64_t wdu = wd0 + (uint64_t)((stage * S * OZ_WTILE) >> 4);
+                const uint32_t dbase = tmem + set * TM_SET;
 #pragma unroll
-                for (int dd = 0; dd < S; ++dd) {
+                for (int kk = 0; kk < OZ_KC / 32; ++kk) {
 #pragma unroll
-                    for (int s = 0; s <= dd; ++s) {
-                        const int t = dd - s;
-#pragma unroll
-                        for (int kk = 0; kk < OZ_KC / 32; ++kk) {
-                            const uint64_t da = umma_desc(sX + (size_t)s * OZ_XTILE + kk * 256, 128, OZ_KC * 8);
-                            const uint64_t db = umma_desc(sW + (size_t)t * OZ_WTILE + kk * 256, 128, OZ_KC * 8);
-                            umma_i8(tmem + dd * OZ_BN, da, db, idesc, (kc > 0 || s > 0 || kk > 0) ? 1u : 0u);
-                        }
+                    for (int s = 0; s < S; ++s) {
+                        // D = s32, A = B = signed int8, both K-major, M = 128, N = (S - s) * 32
+                        constexpr uint32_t ibase = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
+                        const uint32_t idesc = ibase | ((uint32_t)(((S - s) * OZ_BN) >> 3) << 17);
+                        const uint64_t da = xd0 + (uint64_t)((s * OZ_XTILE + kk * 256) >> 4);
+                        const uint64_t db = wdu + (uint64_t)((kk * 256) >> 4);
+                        if (s > 0 || kk > 0) umma_i8<true>(dbase + s * OZ_BN, da, db, idesc);
+                        else umma_i8<false>(dbase, da, db, idesc);
                     }
                 }
-                umma_commit(&bar_mma);          // arrives when every MMA issued so far has finished reading smem / writing TMEM
+                umma_commit(&tm_full[set]);                 // accumulator set ready for the epilogue
+                umma_commit(&w_empty[stage]);               // W stage free once these MMAs have read it
+                if (u % nct == nct - 1) umma_commit(&x_free);
             }
-            x_resident_chunk = (nkc == 1) ? 0 : kc;      // with one k chunk the X slices stay for all column tiles
-            load_phase ^= 1;
-            // everybody waits for the MMAs of this chunk before smem is overwritten / TMEM is read
-            mbar_wait(&bar_mma, mma_phase);
-            mma_phase ^= 1;
-            asm volatile("tcgen05.fence::after_thread_sync;");
         }
-        // ---- epilogue of column tile ct: Horner over the diagonals, 32 columns at a time
-        const int n0 = ct * OZ_BN;
-#pragma unroll 1
-        for (int c = 0; c < OZ_BN / 32; ++c) {
-            double t[32];
-            uint32_t r[32];
-            const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16) + c * 32;
-            tmem_ld32(lane_addr + (S - 1) * OZ_BN, r);
+    } else {
+        // ------------------------------------------------------------------ epilogue warps
+        // warp w reads TMEM lanes 32*(w%4)..: warps w and w+4 share a lane quarter and split the 32 columns of a
+        // unit 16 / 16, so every SM sub-partition has two epilogue warps to overlap latencies.
+        const int lane = tid & 31, quarter = warp & 3, half = warp >> 2;
+        const int row = row_tile * OZ_BM + quarter * 32 + lane;      // output row = TMEM lane
+        const bool row_ok = row < p.R;
+        long long hrow = 0; int npts = 0;
+        if (p.epi == EPI_QKV && row_ok) {
+            if (row < p.rows0) { const int b = row / p.n0; npts = p.n0; hrow = (long long)b * HEADS * p.n0 + (row - b * p.n0); }
+            else { const int r1 = row - p.rows0; const int b = r1 / p.n1; npts = p.n1;
+                   hrow = (long long)p.rows0 * HEADS + (long long)b * HEADS * p.n1 + (r1 - b * p.n1); }
+        }
+        const double MAGIC = 6755399441055744.0;                     // 1.5 * 2^52
+        for (int u = 0; u < units; ++u) {
+            const int kc = u / nct, ct = ct_begin + u % nct, set = u & 1;
+            const int col0 = ct * OZ_BN + half * 16;
+            const bool first = kc == 0, last = kc == nkc - 1;
+            const bool res_first = p.Res && !p.relu;
+            double* dst = p.Y + (long long)row * p.ldy + col0;
+            // operands that come from global memory are requested before the wait on the tensor core
+            double add[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) t[j] = (double)(int)r[j];
+            for (int j = 0; j < 16; ++j) add[j] = 0.0;
+            if (row_ok && p.epi == EPI_PLAIN) {
+                if (!first) {
 #pragma unroll
-            for (int dd = S - 2; dd >= 0; --dd) {
-                tmem_ld32(lane_addr + dd * OZ_BN, r);
+                    for (int j = 0; j < 16; j += 2) { const double2 v = *reinterpret_cast<const double2*>(dst + j); add[j] = v.x; add[j + 1] = v.y; }
+                } else if (res_first) {
+                    const double* rr = p.Res + (long long)row * p.ldres + col0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) t[j] = fma(t[j], 0.0078125, (double)(int)r[j]);
-            }
-            if (row_ok) {
-                const int col0 = n0 + c * 32;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    double y = t[j] * rs * p.colscale[col0 + j];
-                    if (p.bias) y += p.bias[col0 + j];
-                    if (p.relu) y = __double2hiint(y) < 0 ? 0.0 : y;
-                    t[j] = y;
+                    for (int j = 0; j < 16; j += 2) { const double2 v = *reinterpret_cast<const double2*>(rr + j); add[j] = v.x; add[j + 1] = v.y; }
                 }
-                double* dst;
-                if (p.epi == EPI_PLAIN) {
-                    if (p.Res) {
+            }
+            const double rs = row_ok ? p.rowscale[kc][row] : 0.0;
+            mbar_wait(&tm_full[set], (unsigned)((u / 2) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            // Horner over the diagonals. Two neighbouring diagonals are first merged exactly in int32
+            // (|acc_dd| <= (dd+1) * 128 * 64 * 64 < 2^23, so acc_dd * 128 + acc_dd+1 < 2^31), then converted with the
+            // 2^52 magic constant (integer ALU + one DADD instead of a quarter-rate I2F.F64) and chained in float64.
+            int acc[S][16];
+            const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + set * TM_SET + half * 16;
+#pragma unroll
+            for (int dd = 0; dd < S; ++dd) {
+                uint32_t r[16];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(r[0]),"=r"(r[1]),"=r"(r[2]),"=r"(r[3]),"=r"(r[4]),"=r"(r[5]),"=r"(r[6]),"=r"(r[7]),
+                               "=r"(r[8]),"=r"(r[9]),"=r"(r[10]),"=r"(r[11]),"=r"(r[12]),"=r"(r[13]),"=r"(r[14]),"=r"(r[15])
+                             : "r"(lane_addr + dd * OZ_BN));
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[dd][j] = (int)r[j];
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // all TMEM reads of this set are complete: hand it back to the tensor core
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            mbar_arrive(&tm_empty[set]);
+            if (!row_ok) continue;
+            double t[16];
+            auto to_f64 = [&](int v) {
+                return __hiloint2double(0x43380000 + (v >> 31), v) - MAGIC;      // exact for any int32
+            };
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                // pairs from the least significant end: (S-2,S-1), (S-4,S-3), ...; with S odd diagonal 0 stays single
+                double h = to_f64(acc[S - 2][j] * 128 + acc[S - 1][j]);
+#pragma unroll
+                for (int dd = S - 4; dd >= 0; dd -= 2) h = fma(h, 0.00006103515625, to_f64(acc[dd][j] * 128 + acc[dd + 1][j]));   // 2^-14
+                if (S & 1) h = fma(h, 0.00006103515625, to_f64(acc[0][j]));   // last pair sits at 2^-14, diagonal 0 at 2^0
+                else h *= 0.0078125;                                          // even S: last pair (0,1) carries acc_0 * 128
+                t[j] = h;
+            }
+            const double* cs = s_cs + kc * p.Nout + col0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) t[j] = fma(t[j] * rs, cs[j], add[j]);
+            if (p.epi == EPI_QKV) {
+                // single k chunk; 32 consecutive output channels = one head of q, k or v (head-major c' = h*32 + d)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) t[j] += s_bias[col0 + j];
+                const int which = col0 >> 7, h = (col0 & 127) >> 5;
+                double* base = which == 0 ? p.Qh : (which == 1 ? p.Kh : p.Vh);
+                double* q = base + (hrow + (long long)h * npts) * (which == 2 ? LDH_V : LDH_QK) + (col0 & 31);
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2*>(q + j) = make_double2(t[j], t[j + 1]);
+                continue;
+            }
+            if (last) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) t[j] += s_bias[col0 + j];
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) t[j] = __double2hiint(t[j]) < 0 ? 0.0 : t[j];
+                    if (p.Res) {        // launcher guarantees Res != Y here when there are several k chunks
                         const double* rr = p.Res + (long long)row * p.ldres + col0;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) { const double2 v = *reinterpret_cast<const double2*>(rr + j); t[j] += v.x; t[j + 1] += v.y; }
+                        for (int j = 0; j < 16; j += 2) { const double2 v = *reinterpret_cast<const double2*>(rr + j); t[j] += v.x; t[j + 1] += v.y; }
                     }
-                    dst = p.Y + (long long)row * p.ldy + col0;
-                } else {
-                    // 32 consecutive output channels = one head of q, k or v (head-major c' = h*32 + d)
-                    const int which = col0 >> 7, h = (col0 & 127) >> 5;
-                    double* base = which == 0 ? p.Qh : (which == 1 ? p.Kh : p.Vh);
-                    dst = base + (hrow + (long long)h * npts) * (which == 2 ? LDH_V : LDH_QK);
                 }
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(t[j], t[j + 1]);
             }
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(t[j], t[j + 1]);
         }
-        // TMEM is reused by the next column tile: all reads must be done before its first MMA
-        asm volatile("tcgen05.fence::before_thread_sync;");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;");
     }
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem));
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem));
 }
 
 size_t ozaki_slices_bytes(int R, int K, int S) {
@@ -264,11 +354,11 @@ size_t ozaki_slices_bytes(int R, int K, int S) {
 
 template <int S>
 static cudaError_t slice_rows_t(const double* A0, int ld0, int K0, const double* A1, int ld1, int K1, int R,
-                                int8_t* Xs, double* rowscale, cudaStream_t st) {
+                                int8_t* Xs, double* rowscale, size_t chunk_stride, cudaStream_t st) {
     const int K = K0 + K1;
     const long long Rpad = (long long)((R + OZ_BM - 1) / OZ_BM) * OZ_BM;
     const long long threads = Rpad * (K / 16);
-    slice_rows_kernel<S><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale);
+    slice_rows_kernel<S><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale, chunk_stride);
     return cudaGetLastError();
 }
 
@@ -278,10 +368,10 @@ cudaError_t launch_slice_rows(const double* A0, int ld0, int K0, const double* A
     const int K = K0 + K1;
     if ((K0 % OZ_KC) != 0 || (K1 % OZ_KC) != 0 || (K != 128 && K != 256 && K != 512)) return cudaErrorInvalidValue;
     cudaError_t e;
+    const size_t chunk_stride = ozaki_slices_bytes(R, OZ_KC, S);     // chunk c of the input goes to Xs + c * chunk_stride
     switch (S) {
-        case 6: e = slice_rows_t<6>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale, st); break;
-        case 7: e = slice_rows_t<7>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale, st); break;
-        case 8: e = slice_rows_t<8>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale, st); break;
+        case 6: e = slice_rows_t<6>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale, chunk_stride, st); break;
+        case 7: e = slice_rows_t<7>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale, chunk_stride, st); break;
         default: return cudaErrorInvalidValue;
     }
     if (e == cudaSuccess) count_launch();
@@ -290,7 +380,7 @@ cudaError_t launch_slice_rows(const double* A0, int ld0, int K0, const double* A
 
 template <int S>
 static cudaError_t ozaki_gemm_t(const OzParams& p, dim3 grid, cudaStream_t st) {
-    const size_t smem = (size_t)S * (OZ_XTILE + OZ_WTILE);
+    const size_t smem = (size_t)S * (OZ_XTILE + OZ_WSTAGES * OZ_WTILE);
     cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     ozaki_gemm_kernel<S><<<grid, OZ_THREADS, smem, st>>>(p);
@@ -299,24 +389,24 @@ static cudaError_t ozaki_gemm_t(const OzParams& p, dim3 grid, cudaStream_t st) {
 
 cudaError_t launch_ozaki_gemm(const OzGemmArgs& a, int S, cudaStream_t st) {
     if (a.R <= 0) return cudaSuccess;
-    if ((a.K % OZ_KC) != 0 || (a.Nout % OZ_BN) != 0) return cudaErrorInvalidValue;
+    if ((a.K != OZ_KC && a.K != 2 * OZ_KC) || (a.Nout % OZ_BN) != 0 || a.Nout > OZ_MAXN) return cudaErrorInvalidValue;
+    if (a.relu && a.Res == a.Y && a.Res != nullptr && a.K > OZ_KC) return cudaErrorInvalidValue;   // see res_first
+    if (a.epi == EPI_QKV && a.K != OZ_KC) return cudaErrorInvalidValue;
     OzParams p;
-    p.Xs = a.Xs; p.rowscale = a.rowscale; p.Ws = a.Ws; p.colscale = a.colscale; p.bias = a.bias;
+    p.Xs[0] = a.Xs[0]; p.Xs[1] = a.Xs[1]; p.rowscale[0] = a.rowscale[0]; p.rowscale[1] = a.rowscale[1]; p.Ws = a.Ws; p.colscale = a.colscale; p.bias = a.bias;
     p.Res = a.Res; p.ldres = a.ldres; p.Y = a.Y; p.ldy = a.ldy; p.R = a.R; p.Nout = a.Nout; p.K = a.K;
     p.relu = a.relu; p.epi = a.epi; p.Qh = a.Qh; p.Kh = a.Kh; p.Vh = a.Vh; p.rows0 = a.rows0; p.n0 = a.n0; p.n1 = a.n1;
     const int row_tiles = (a.R + OZ_BM - 1) / OZ_BM, col_tiles = a.Nout / OZ_BN;
-    // with one k chunk the X slices stay resident across column tiles: keep all column tiles in one CTA unless
-    // that leaves SMs idle; otherwise every column tile reloads X anyway, so spread them out
+    // the X slice planes are loaded once per (CTA, k chunk): keep all column tiles in one CTA unless that leaves
+    // SMs idle
     int groups = 1;
-    if (a.K > OZ_KC) groups = col_tiles;
-    else while (row_tiles * groups < 148 && groups < col_tiles) ++groups;
+    while (row_tiles * groups < 148 && groups < col_tiles) ++groups;
     p.col_tiles_per_cta = (col_tiles + groups - 1) / groups;
     dim3 grid(row_tiles, (col_tiles + p.col_tiles_per_cta - 1) / p.col_tiles_per_cta);
     cudaError_t e;
     switch (S) {
         case 6: e = ozaki_gemm_t<6>(p, grid, st); break;
         case 7: e = ozaki_gemm_t<7>(p, grid, st); break;
-        case 8: e = ozaki_gemm_t<8>(p, grid, st); break;
         default: return cudaErrorInvalidValue;
     }
     if (e == cudaSuccess) count_launch();

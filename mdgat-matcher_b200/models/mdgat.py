@@ -222,7 +222,7 @@ class MDGAT(nn.Module):
 
     def gemm_engine(self):
         """config['gemm']: 'tcgen05_i8' (float64-faithful Ozaki splitting on the int8 tensor cores, default)
-        or 'dmma' (FP64 pipe); config['gemm_slices']: int8 digit planes per operand (6..8, default 7)."""
+        or 'dmma' (FP64 pipe); config['gemm_slices']: int8 digit planes per operand (6 or 7, default 7)."""
         mode = self.config.get('gemm', 'tcgen05_i8')
         if mode not in ('tcgen05_i8', 'dmma'):
             raise ValueError("config['gemm'] must be 'tcgen05_i8' or 'dmma'")

@@ -117,43 +117,42 @@ def pack_state_dict(sd, L):
     return blob
 
 
-OZ_BN, OZ_KC = 64, 128
+OZ_BN, OZ_KC = 32, 128
 
 
 def slice_weight(w, S):
     """Ozaki slices of a weight matrix for the tcgen05 int8 GEMM (csrc/ozaki_gemm.cu).
-    Row n of w is written as 2^f_n * sum_s g_s 2^(1-7s) with integer digits |g_s| <= 64 (exact float64
-    arithmetic), f_n the exponent of the row maximum. Returns (int8 tensor [col_tile][k_chunk][S][64*128]
-    in the canonical UMMA K-major core-matrix order, colscale = 2^f_n as float64 [Nout])."""
+    Every (row n, 128-column chunk c) of w is written as 2^f * sum_s g_s 2^(1-7s) with integer digits
+    |g_s| <= 64 (exact float64 arithmetic), f the exponent of the chunk's row maximum. Returns (int8 tensor
+    [col_tile][k_chunk][S][32*128] in the canonical UMMA K-major core-matrix order, colscale = 2^f as
+    float64 [k_chunk][Nout])."""
     nout, k = w.shape
     assert nout % OZ_BN == 0 and k % OZ_KC == 0, (nout, k)
-    mx = w.abs().amax(dim=1)
+    ct, kc = nout // OZ_BN, k // OZ_KC
+    wc = w.reshape(nout, kc, OZ_KC)
+    mx = wc.abs().amax(dim=2)                                # [Nout][kc]
     _, e = torch.frexp(mx)                                   # mx = m * 2^e, m in [0.5, 1)
     e = torch.where(mx > 0, e, torch.zeros_like(e)).to(torch.float64)
-    t = w * torch.exp2(6.0 - e)[:, None]
-    digits = []
+    t = wc * torch.exp2(6.0 - e)[:, :, None]
+    tiles = []
     for _ in range(S):
         d = torch.round(t)                                   # half to even, like rint()
-        digits.append(d.to(torch.int8))
         t = (t - d) * 128.0
-    ct, kc = nout // OZ_BN, k // OZ_KC
-    tiles = []
-    for d in digits:
-        # (r, k) -> (r/8)*1024 + (k/16)*128 + (r%8)*16 + k%16 inside a (64 x 128) tile
-        x = d.reshape(ct, 8, 8, kc, 8, 16).permute(0, 3, 1, 4, 2, 5)     # [ct][kc][r/8][k/16][r%8][k%16]
+        # (r, k) -> (r/8)*1024 + (k/16)*128 + (r%8)*16 + k%16 inside a (32 x 128) tile
+        x = d.to(torch.int8).reshape(ct, OZ_BN // 8, 8, kc, 8, 16).permute(0, 3, 1, 4, 2, 5)   # [ct][kc][r/8][k/16][r%8][k%16]
         tiles.append(x.reshape(ct, kc, OZ_BN * OZ_KC))
-    out = torch.stack(tiles, dim=2).contiguous()             # [ct][kc][S][8192]
-    return out.reshape(-1), torch.exp2(e)
+    out = torch.stack(tiles, dim=2).contiguous()             # [ct][kc][S][4096]
+    return out.reshape(-1), torch.exp2(e).t().contiguous()   # colscale [kc][Nout]
 
 
 def i8_layer_bytes(S):
-    return S * OZ_BN * OZ_KC * (6 * 1 + 4 * 2 + 2 * 2) + (384 + 256 + 128) * 8
+    return S * OZ_BN * OZ_KC * (12 * 1 + 8 * 2 + 4 * 2) + (384 + 2 * 256 + 2 * 128) * 8
 
 
 def pack_state_dict_i8(sd, L, S=7):
     """Int8-sliced copy of the per-layer GEMM weights (q/k/v stack, folded MLP conv 0, MLP conv 3) for the
     tcgen05 path: per layer [qkv slices | mlp0 slices | mlp3 slices | colscale qkv(384) mlp0(256) mlp3(128)]
-    as one uint8 tensor. Built from exactly the same float64 matrices pack_state_dict() stores."""
+    as one uint8 tensor (colscale per (k chunk, column): qkv 384, mlp0 2x256, mlp3 2x128). Built from exactly the same float64 matrices pack_state_dict() stores."""
     dev = sd['bin_score'].device
     perm = _head_major_perm(dev)
     chunks = []
@@ -169,7 +168,7 @@ def pack_state_dict_i8(sd, L, S=7):
         for w in (torch.cat(ws, 0), w1, w2):
             sl, cs = slice_weight(w, S)
             chunks.append(sl.view(torch.uint8))
-            scales.append(cs)
+            scales.append(cs.reshape(-1))
         chunks.append(torch.cat(scales).contiguous().view(torch.uint8))
     blob = torch.cat(chunks).contiguous()
     assert blob.numel() == 2 * L * i8_layer_bytes(S), (blob.numel(), 2 * L * i8_layer_bytes(S))

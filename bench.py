@@ -171,6 +171,8 @@ def main():
     ap.add_argument('--layers', type=int, default=9, help='L (2L GNN layers)')
     ap.add_argument('--sinkhorn', type=int, default=100)
     ap.add_argument('--cpu-pairs', type=int, default=0, help='pairs in the CPU baseline sample (0 = auto)')
+    ap.add_argument('--gemm', default='tcgen05_i8', choices=['tcgen05_i8', 'dmma'], help='engine of the per-layer projections')
+    ap.add_argument('--attention', default='tcgen05_i8', choices=['tcgen05_i8', 'dmma'], help='engine of Q K^T / P V')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-eager', action='store_true', help='skip the eager-PyTorch fp64 GPU timing of the same math')
     args = ap.parse_args()
@@ -198,6 +200,7 @@ def main():
 
     B, N, L, T = args.batch, args.n, args.layers, args.sinkhorn
     cfg = net_config(L, T)
+    cfg['gemm'], cfg['attention'] = args.gemm, args.attention
     sd, wdesc = load_weights(L)
     net = MDGAT(cfg)
     net.load_state_dict(sd)

@@ -42,6 +42,10 @@ extern "C" {
 #define MDGAT_GEMM_DMMA_F64 0     /* mma.sync.m8n8k4.f64 (DMMA) on the FP64 pipe */
 #define MDGAT_GEMM_TCGEN05_I8 1   /* float64-faithful Ozaki splitting on tcgen05.mma kind::i8 (TMEM accumulators) */
 
+/* attention engines (full-softmax layers and the logits of the dynamic layers) */
+#define MDGAT_ATTN_DMMA_F64 0     /* flash attention on DMMA (FP64 pipe) */
+#define MDGAT_ATTN_TCGEN05_I8 1   /* float64-faithful digit products on tcgen05.mma kind::i8: Q K^T and P V in TMEM */
+
 /* input element types */
 #define MDGAT_F32 0
 #define MDGAT_F64 1
@@ -82,6 +86,7 @@ typedef struct {
     int write_Z;              /* also materialise Z (B,N+1,M+1) into d_Z (debug / other losses) */
     int gemm_mode;            /* MDGAT_GEMM_* */
     int gemm_slices;          /* int8 slices per operand in MDGAT_GEMM_TCGEN05_I8 mode (6 or 7; 7 = 49 bits) */
+    int attn_mode;            /* MDGAT_ATTN_* (tcgen05 needs N, M <= 4096; larger sets use the DMMA kernel) */
 } mdgat_forward_cfg;
 
 typedef struct {
@@ -149,6 +154,13 @@ int mdgat_encode(const mdgat_forward_in* in, int B, int N, int M, int in_dtype, 
  * needed only when topk > 0. Output rows (B*N) x ldo, column h*32+d. */
 int mdgat_attention_f64(const double* d_Q, const double* d_K, const double* d_V, double* d_Out, int ldo,
                         int B, int N, int M, int topk, double* d_logits, void* stream);
+
+/* Same contract on the tcgen05 int8 tensor cores (attention_i8.cu): q, k, v are cut into base-256 digit planes on
+ * the device, Q K^T and P V are exact int32 digit products in TMEM, recombined in float64.
+ * d_scratch: mdgat_attention_i8_scratch_bytes(B, N, M) bytes. Requires N, M <= 4096. */
+size_t mdgat_attention_i8_scratch_bytes(int B, int N, int M);
+int mdgat_attention_i8(const double* d_Q, const double* d_K, const double* d_V, double* d_Out, int ldo,
+                       int B, int N, int M, int topk, double* d_logits, void* d_scratch, void* stream);
 
 /* log_optimal_transport (mdgat.py:279-308) on couplings already holding scores in [:N,:M]:
  * fills the dustbin row/column with bin_score (read from d_bin_score), runs `iters`

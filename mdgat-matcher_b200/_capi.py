@@ -14,6 +14,7 @@ MATCH_DUSTBIN, MATCH_THRESHOLD = 0, 1
 LOSS_NONE, LOSS_TRIPLET = 0, 1
 F32, F64 = 0, 1
 GEMM_DMMA_F64, GEMM_TCGEN05_I8 = 0, 1
+ATTN_DMMA_F64, ATTN_TCGEN05_I8 = 0, 1
 LDX = 132
 LDH_QK, LDH_V = 36, 34
 
@@ -24,7 +25,7 @@ class ForwardCfg(C.Structure):
                 ('match_mode', C.c_int), ('mutual_check', C.c_int), ('match_threshold', C.c_double),
                 ('loss_mode', C.c_int), ('triplet_gamma', C.c_double),
                 ('in_dtype', C.c_int), ('score_dtype', C.c_int), ('write_Z', C.c_int),
-                ('gemm_mode', C.c_int), ('gemm_slices', C.c_int)]
+                ('gemm_mode', C.c_int), ('gemm_slices', C.c_int), ('attn_mode', C.c_int)]
 
 
 class ForwardIn(C.Structure):
@@ -59,6 +60,8 @@ def _load():
         'mdgat_encode_scratch_doubles': (sz, [i]),
         'mdgat_encode': (i, [C.POINTER(ForwardIn), i, i, i, i, i, vp, vp, vp, vp]),
         'mdgat_attention_f64': (i, [vp, vp, vp, vp, i, i, i, i, i, vp, vp]),
+        'mdgat_attention_i8_scratch_bytes': (sz, [i, i, i]),
+        'mdgat_attention_i8': (i, [vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp]),
         'mdgat_sinkhorn_scratch_doubles': (sz, [i, i, i]),
         'mdgat_sinkhorn_read_status': (i, [vp, i, i, i, C.POINTER(i), C.POINTER(i)]),
         'mdgat_sinkhorn_f64': (i, [vp, vp, vp, vp, i, i, i, i, vp, vp]),

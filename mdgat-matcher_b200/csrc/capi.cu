@@ -94,11 +94,12 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct Workspace {
     double *X, *Xk, *Xd, *Qh, *Kh, *Vh, *Msg, *Mg, *Hd, *MD, *S, *C, *u, *v, *mscratch, *skscratch;
     double *rsX, *rsM, *rsH; int8_t *xsX, *xsM, *xsH;   // tcgen05 path: int8 slice planes + row scales of X, Msg, Hd (2 chunks)
+    AttnI8Side ai[2];                                   // tcgen05 attention: digit planes of q/k/v of side 0 / side 1
     size_t bytes;
 };
 
 // Carves the workspace; with base == nullptr only computes the size.
-Workspace carve(char* base, int B, int N, int M, bool need_logits, int i8_slices = 0) {
+Workspace carve(char* base, int B, int N, int M, bool need_logits, int i8_slices = 0, bool attn_i8 = false) {
     Workspace w;
     const size_t R = (size_t)B * N + (size_t)B * M;
     size_t off = 0;
@@ -132,6 +133,11 @@ Workspace carve(char* base, int B, int N, int M, bool need_logits, int i8_slices
     w.xsX = reinterpret_cast<int8_t*>(take(chunk8));
     w.xsM = reinterpret_cast<int8_t*>(take(chunk8));
     w.xsH = reinterpret_cast<int8_t*>(take(2 * chunk8));
+    for (int s = 0; s < 2; ++s) {
+        const int n = s == 0 ? N : M;
+        void* p = take(attn_i8 ? attn_i8_side_bytes(B, n) / 8 : 0);
+        if (attn_i8 && base) w.ai[s] = attn_i8_carve(p, B, n);
+    }
     w.bytes = off;
     return w;
 }
@@ -160,7 +166,21 @@ cudaError_t gemm_nt(const double* X, int ldx, long long sX, const double* W, int
 }
 
 // Messages of one GNN layer. nsides = 2: side 0 and side 1 in the same launches.
-cudaError_t attention_layer(const AttnSides& ps, int B, int nsides, int ldo, int topk, double* S, cudaStream_t st) {
+// qd / kvd != nullptr: tcgen05 engine; the digit planes of the query / source side of each grid side are already cut.
+cudaError_t attention_layer(const AttnSides& ps, int B, int nsides, int ldo, int topk, double* S, cudaStream_t st,
+                            const AttnI8Side* qd = nullptr, const AttnI8Side* kvd = nullptr) {
+    if (qd) {
+        if (topk <= 0) return launch_attn_i8(qd, kvd, ps.Out, B, nsides, ldo, false, st);
+        double* lg[2]; double* sp = S;
+        for (int s = 0; s < nsides; ++s) { lg[s] = sp; sp += (size_t)B * HEADS * ps.N[s] * ps.M[s]; }
+        cudaError_t e = launch_attn_i8(qd, kvd, lg, B, nsides, 0, true, st);
+        if (e != cudaSuccess) return e;
+        for (int s = 0; s < nsides; ++s) {
+            e = launch_topk_softmax_pv(lg[s], ps.V[s], ps.Out[s], ldo, B, ps.N[s], ps.M[s], topk, st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
     if (topk <= 0) return launch_attention_full(ps, B, nsides, ldo, st);
     // dense logits q.k / sqrt(32) for every (b, h) (mdgat.py:201), then exact-k selection per row
     AttnSides lg = ps;
@@ -205,7 +225,8 @@ size_t mdgat_weight_blob_doubles(int L) { return BlobLayout(L).total; }
 size_t mdgat_forward_workspace_bytes(const mdgat_forward_cfg* cfg) {
     bool need = false;
     for (int i = 0; i < 2 * cfg->L; ++i) need = need || (cfg->layer_k && cfg->layer_k[i] > 0);
-    return carve(nullptr, cfg->B, cfg->N, cfg->M, need, cfg->gemm_mode == MDGAT_GEMM_TCGEN05_I8 ? cfg->gemm_slices : 0).bytes;
+    const bool ai = cfg->attn_mode == MDGAT_ATTN_TCGEN05_I8 && attn_i8_supported(cfg->N, cfg->M) && attn_i8_supported(cfg->M, cfg->N);
+    return carve(nullptr, cfg->B, cfg->N, cfg->M, need, cfg->gemm_mode == MDGAT_GEMM_TCGEN05_I8 ? cfg->gemm_slices : 0, ai).bytes;
 }
 
 int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const void* d_weights_i8,
@@ -234,7 +255,8 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
     const bool i8 = cfg->gemm_mode == MDGAT_GEMM_TCGEN05_I8;
     const int S8 = cfg->gemm_slices;
     MDGAT_REQUIRE(!i8 || (d_weights_i8 != nullptr && S8 >= 6 && S8 <= 7), "tcgen05 int8 GEMM mode needs the sliced weight blob and 6 or 7 slices");
-    Workspace w = carve(reinterpret_cast<char*>(d_workspace), B, N, M, need, i8 ? S8 : 0);
+    const bool ai8 = cfg->attn_mode == MDGAT_ATTN_TCGEN05_I8 && attn_i8_supported(N, M) && attn_i8_supported(M, N);
+    Workspace w = carve(reinterpret_cast<char*>(d_workspace), B, N, M, need, i8 ? S8 : 0, ai8);
     if (w.bytes > workspace_bytes) {
         mdgat_host::set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
         return MDGAT_ERR_WORKSPACE;
@@ -283,7 +305,17 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
         AttnSides ps;
         ps.Q[0] = Q0; ps.K[0] = cross ? K1 : K0; ps.V[0] = cross ? V1 : V0; ps.Out[0] = w.Msg; ps.N[0] = N; ps.M[0] = cross ? M : N;
         ps.Q[1] = Q1; ps.K[1] = cross ? K0 : K1; ps.V[1] = cross ? V0 : V1; ps.Out[1] = w.Msg + (size_t)R0 * LDX; ps.N[1] = M; ps.M[1] = cross ? N : M;
-        MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st));
+        if (ai8) {
+            // digit planes of this layer's q, k, v (both sides), then the tcgen05 kernel: side s reads the k / v planes
+            // of side s (self) or 1 - s (cross)
+            MDGAT_CUDA_OK(launch_attn_i8_slice(Q0, K0, V0, w.ai[0], B, st));
+            MDGAT_CUDA_OK(launch_attn_i8_slice(Q1, K1, V1, w.ai[1], B, st));
+            const AttnI8Side qd[2] = {w.ai[0], w.ai[1]};
+            const AttnI8Side kvd[2] = {cross ? w.ai[1] : w.ai[0], cross ? w.ai[0] : w.ai[1]};
+            MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st, qd, kvd));
+        } else {
+            MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st));
+        }
         prof_mark(ST_GEMM, st);
         // the merge conv (mdgat.py:237) is folded into the first MLP conv by the weight packer
         // mlp(cat[x, message]) : 256 -> 256 (BN folded, ReLU) -> 128, then the residual (mdgat.py:248, :274)
@@ -390,6 +422,27 @@ int mdgat_attention_f64(const double* d_Q, const double* d_K, const double* d_V,
     memset(&ps, 0, sizeof(ps));
     ps.Q[0] = d_Q; ps.K[0] = d_K; ps.V[0] = d_V; ps.Out[0] = d_Out; ps.N[0] = N; ps.M[0] = M;
     MDGAT_CUDA_OK(attention_layer(ps, B, 1, ldo, topk, d_logits, reinterpret_cast<cudaStream_t>(stream)));
+    return MDGAT_OK;
+}
+
+size_t mdgat_attention_i8_scratch_bytes(int B, int N, int M) { return attn_i8_side_bytes(B, N) + attn_i8_side_bytes(B, M); }
+
+int mdgat_attention_i8(const double* d_Q, const double* d_K, const double* d_V, double* d_Out, int ldo,
+                       int B, int N, int M, int topk, double* d_logits, void* d_scratch, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    MDGAT_REQUIRE(topk <= M, "selected index k out of range (k=%d, M=%d)", topk, M);
+    MDGAT_REQUIRE(topk <= 0 || (d_logits != nullptr && M <= 2048), "mdgat_attention_i8: top-k needs a logits scratch and M <= 2048");
+    MDGAT_REQUIRE((ldo % 2) == 0 && d_scratch != nullptr, "mdgat_attention_i8: ldo must be even, scratch required");
+    MDGAT_REQUIRE(attn_i8_supported(N, M), "mdgat_attention_i8: M = %d source keypoints exceed the shared-memory budget", M);
+    // query planes from Q of the N-point set, source planes from K and V of the M-point set
+    AttnI8Side qs = attn_i8_carve(d_scratch, B, N);
+    AttnI8Side ks = attn_i8_carve(reinterpret_cast<char*>(d_scratch) + attn_i8_side_bytes(B, N), B, M);
+    MDGAT_CUDA_OK(launch_attn_i8_slice(d_Q, nullptr, nullptr, qs, B, st));
+    MDGAT_CUDA_OK(launch_attn_i8_slice(nullptr, d_K, d_V, ks, B, st));
+    AttnSides ps;
+    memset(&ps, 0, sizeof(ps));
+    ps.Q[0] = d_Q; ps.K[0] = d_K; ps.V[0] = d_V; ps.Out[0] = d_Out; ps.N[0] = N; ps.M[0] = M;
+    MDGAT_CUDA_OK(attention_layer(ps, B, 1, ldo, topk, d_logits, st, &qs, &ks));
     return MDGAT_OK;
 }
 

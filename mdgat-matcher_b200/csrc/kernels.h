@@ -83,6 +83,21 @@ cudaError_t launch_slice_rows(const double* A0, int ld0, int K0, const double* A
                               int8_t* Xs, double* rowscale, cudaStream_t st);
 cudaError_t launch_ozaki_gemm(const OzGemmArgs& a, int S, cudaStream_t st);
 
+// float64-faithful attention on tcgen05 int8 tensor cores (digit planes of q/k/v, exact int32 accumulation in
+// TMEM), see attention_i8.cu. One AttnI8Side holds the digit planes of ONE side's q, k and v head vectors.
+struct AttnI8Side {
+    int8_t *Qs, *Ks, *Vs;                 // Q planes per 128-row query tile, K / V^T planes per 32-row source tile
+    double *qscale, *kscale, *vscale;     // per query row, per source row, per (b, h, channel)
+    float *kscale_f, *ktilemax;           // fp32 copy of kscale, largest kscale per source tile
+    int n;                                // keypoints of this side
+};
+size_t attn_i8_side_bytes(int B, int n);
+AttnI8Side attn_i8_carve(void* base, int B, int n);
+bool attn_i8_supported(int N, int M);
+cudaError_t launch_attn_i8_slice(const double* Qh, const double* Kh, const double* Vh, const AttnI8Side& o, int B, cudaStream_t st);
+cudaError_t launch_attn_i8(const AttnI8Side* q, const AttnI8Side* kv, double* const* Out, int B, int nsides, int ldo,
+                           bool logits_only, cudaStream_t st);
+
 // Batched Kabsch registration + match statistics (one CTA per pair)
 cudaError_t launch_register_pairs(const void* kpts0, const void* kpts1, int kp_dtype, const int64_t* matches0,
                                   const int16_t* gt0, const double* T_gt, int B, int N, int M,

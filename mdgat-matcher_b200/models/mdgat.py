@@ -228,6 +228,14 @@ class MDGAT(nn.Module):
             raise ValueError("config['gemm'] must be 'tcgen05_i8' or 'dmma'")
         return mode, int(self.config.get('gemm_slices', 7))
 
+    def attention_engine(self):
+        """config['attention']: 'tcgen05_i8' (default; Q K^T and P V as exact int8 digit products in TMEM)
+        or 'dmma' (flash attention on the FP64 pipe)."""
+        mode = self.config.get('attention', 'tcgen05_i8')
+        if mode not in ('tcgen05_i8', 'dmma'):
+            raise ValueError("config['attention'] must be 'tcgen05_i8' or 'dmma'")
+        return mode
+
     def packed_weights_i8(self, slices):
         key = (self._weights_key(), slices)
         if self._packed_i8 is None or self._packed_i8[0] != key:
@@ -327,7 +335,8 @@ class MDGAT(nn.Module):
                 score_dtype=_capi.F64 if sc[0].dtype == torch.float64 else _capi.F32,
                 write_Z=int(write_Z),
                 gemm_mode=_capi.GEMM_TCGEN05_I8 if gemm_mode == 'tcgen05_i8' else _capi.GEMM_DMMA_F64,
-                gemm_slices=gemm_slices)
+                gemm_slices=gemm_slices,
+                attn_mode=_capi.ATTN_TCGEN05_I8 if self.attention_engine() == 'tcgen05_i8' else _capi.ATTN_DMMA_F64)
             need = _capi.lib.mdgat_forward_workspace_bytes(ctypes.byref(cfg))
             ws = self._workspace
             if ws is None or ws.device != dev or ws.numel() < need:

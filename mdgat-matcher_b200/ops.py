@@ -69,7 +69,7 @@ def to_head_major(t, ld):
     return out.contiguous()
 
 
-def attention(q, k, v, topk=None):
+def attention(q, k, v, topk=None, engine='dmma'):
     """q (B,128,N), k/v (B,128,M) in the reference's channel layout. Returns the message
     (B,128,N) in the reference layout (what attention()/dynamic_attention() return after
     .view(B, 128, N), mdgat.py:229-237 before the merge conv)."""
@@ -81,9 +81,17 @@ def attention(q, k, v, topk=None):
     kk = 0 if topk is None else int(topk)
     logits = torch.empty((B, 4, N, M), dtype=torch.float64, device=q.device) if kk > 0 else None
     with torch.cuda.device(q.device):
-        _capi.check(_capi.lib.mdgat_attention_f64(qh.data_ptr(), kh.data_ptr(), vh.data_ptr(), out.data_ptr(), LDX,
-                                                  B, N, M, kk, logits.data_ptr() if logits is not None else None,
-                                                  _stream(q.device)))
+        if engine == 'tcgen05_i8':
+            scratch = torch.empty(_capi.lib.mdgat_attention_i8_scratch_bytes(B, N, M), dtype=torch.uint8, device=q.device)
+            _capi.check(_capi.lib.mdgat_attention_i8(qh.data_ptr(), kh.data_ptr(), vh.data_ptr(), out.data_ptr(), LDX,
+                                                     B, N, M, kk, logits.data_ptr() if logits is not None else None,
+                                                     scratch.data_ptr(), _stream(q.device)))
+        elif engine == 'dmma':
+            _capi.check(_capi.lib.mdgat_attention_f64(qh.data_ptr(), kh.data_ptr(), vh.data_ptr(), out.data_ptr(), LDX,
+                                                      B, N, M, kk, logits.data_ptr() if logits is not None else None,
+                                                      _stream(q.device)))
+        else:
+            raise ValueError("engine must be 'dmma' or 'tcgen05_i8'")
     msg = out[:, :128].reshape(B, N, 4, 32)                        # (B, N, h, d)
     return msg.permute(0, 3, 2, 1).reshape(B, 128, N).contiguous()  # channel c = d*4 + h
 

@@ -89,29 +89,52 @@ def test_gemm_nt_batched(dev):
     assert np.abs(got - want).max() < 1e-12
 
 
-@pytest.mark.parametrize('N,M', [(128, 128), (200, 77), (64, 512), (513, 300)])
-def test_attention_full_vs_oracle(dev, N, M):
+ENGINE_TOL = {'dmma': 1e-12, 'tcgen05_i8': 5e-12}     # digit planes: 55-bit q/k/v, 47-bit probabilities
+
+
+@pytest.mark.parametrize('engine', ['dmma', 'tcgen05_i8'])
+@pytest.mark.parametrize('N,M', [(128, 128), (200, 77), (64, 512), (513, 300), (33, 17), (1, 1)])
+def test_attention_full_vs_oracle(dev, N, M, engine):
     from mdgat_matcher_b200 import ops
     from oracle import mdgat_oracle as O
     rng = np.random.default_rng(N * 7 + M)
     q = rng.normal(size=(2, 128, N)) * 3; k = rng.normal(size=(2, 128, M)) * 3; v = rng.normal(size=(2, 128, M))
     want, _ = O.attention(q.reshape(2, 32, 4, N), k.reshape(2, 32, 4, M), v.reshape(2, 32, 4, M))
-    got = ops.attention(_t(q, dev), _t(k, dev), _t(v, dev)).cpu().numpy()
-    assert np.abs(got - want.reshape(2, 128, N)).max() < 1e-12
+    got = ops.attention(_t(q, dev), _t(k, dev), _t(v, dev), engine=engine).cpu().numpy()
+    assert np.abs(got - want.reshape(2, 128, N)).max() < ENGINE_TOL[engine]
 
 
+def test_attention_i8_wide_dynamic_range(dev):
+    """Rows and channels of very different magnitude, logits up to +-300: the digit scales are
+    per query row, per source row and per value channel, so small entries keep their relative accuracy."""
+    from mdgat_matcher_b200 import ops
+    from oracle import mdgat_oracle as O
+    rng = np.random.default_rng(5)
+    N, M = 256, 384
+    q = rng.normal(size=(2, 128, N)) * 8; k = rng.normal(size=(2, 128, M)) * 8; v = rng.normal(size=(2, 128, M)) * 5
+    q[:, :, ::7] *= 1e-3; k[:, :, ::5] *= 1e-4; v[:, ::3, :] *= 1e-6; v[:, 5, :] = 0.0
+    want, _ = O.attention(q.reshape(2, 32, 4, N), k.reshape(2, 32, 4, M), v.reshape(2, 32, 4, M))
+    want = want.reshape(2, 128, N)
+    got = ops.attention(_t(q, dev), _t(k, dev), _t(v, dev), engine='tcgen05_i8').cpu().numpy()
+    scale = np.abs(v).max(axis=2, keepdims=True) + 1e-300                 # per channel
+    assert (np.abs(got - want) / scale).max() < 1e-11
+    assert np.abs(got[:, 5]).max() == 0.0
+
+
+@pytest.mark.parametrize('engine', ['dmma', 'tcgen05_i8'])
 @pytest.mark.parametrize('N,M,topk', [(128, 128, 128), (128, 256, 64), (200, 300, 128), (96, 1000, 64), (40, 2048, 128)])
-def test_attention_topk_vs_oracle(dev, N, M, topk):
+def test_attention_topk_vs_oracle(dev, N, M, topk, engine):
     from mdgat_matcher_b200 import ops
     from oracle import mdgat_oracle as O
     rng = np.random.default_rng(N + M + topk)
     q = rng.normal(size=(2, 128, N)) * 2; k = rng.normal(size=(2, 128, M)) * 2; v = rng.normal(size=(2, 128, M))
     want, _ = O.dynamic_attention(q.reshape(2, 32, 4, N), k.reshape(2, 32, 4, M), v.reshape(2, 32, 4, M), topk)
-    got = ops.attention(_t(q, dev), _t(k, dev), _t(v, dev), topk=topk).cpu().numpy()
-    assert np.abs(got - want.reshape(2, 128, N)).max() < 1e-12
+    got = ops.attention(_t(q, dev), _t(k, dev), _t(v, dev), topk=topk, engine=engine).cpu().numpy()
+    assert np.abs(got - want.reshape(2, 128, N)).max() < ENGINE_TOL[engine]
 
 
-def test_attention_topk_exact_ties(dev):
+@pytest.mark.parametrize('engine', ['dmma', 'tcgen05_i8'])
+def test_attention_topk_exact_ties(dev, engine):
     """Duplicated source keypoints give bit-identical logits; exactly k must be kept
     (a threshold mask would keep more and change the softmax denominator)."""
     from mdgat_matcher_b200 import ops
@@ -122,8 +145,8 @@ def test_attention_topk_exact_ties(dev):
     k[:, :, 80:] = k[:, :, :80]; v[:, :, 80:] = v[:, :, :80]          # every column has an exact twin
     want, prob = O.dynamic_attention(q.reshape(1, 32, 4, N), k.reshape(1, 32, 4, M), v.reshape(1, 32, 4, M), topk)
     assert ((prob > 0).sum(-1) == topk).all()
-    got = ops.attention(_t(q, dev), _t(k, dev), _t(v, dev), topk=topk).cpu().numpy()
-    assert np.abs(got - want.reshape(1, 128, N)).max() < 1e-12
+    got = ops.attention(_t(q, dev), _t(k, dev), _t(v, dev), topk=topk, engine=engine).cpu().numpy()
+    assert np.abs(got - want.reshape(1, 128, N)).max() < ENGINE_TOL[engine]
 
 
 def test_attention_topk_k_out_of_range(dev):
@@ -248,12 +271,12 @@ E2E = ['cfg1_seeded_L4_n128', 'ckpt_L9_n512_T100', 'ckpt_L9_ragged_gap', 'ckpt_L
        'seeded_L9_n512', 'ckpt_L9_duplicates', 'ckpt_L9_sgloss_mutual', 'ckpt_L9_n2048', 'ckpt_L9_n512_b8']
 
 
-@pytest.mark.parametrize('gemm', ['tcgen05_i8', 'dmma'])
+@pytest.mark.parametrize('gemm,attention', [('tcgen05_i8', 'tcgen05_i8'), ('tcgen05_i8', 'dmma'), ('dmma', 'dmma')])
 @pytest.mark.parametrize('name', E2E)
-def test_forward_matches_reference_golden(dev, name, gemm):
+def test_forward_matches_reference_golden(dev, name, gemm, attention):
     rec = load_golden(name)
     case = rec['case']
-    net = _build_module(case, dev, extra={'return_assignment': True, 'gemm': gemm})
+    net = _build_module(case, dev, extra={'return_assignment': True, 'gemm': gemm, 'attention': attention})
     data = {k: _t(v, dev) for k, v in golden_inputs(rec).items()}
     out = net(data)
     torch.cuda.synchronize()

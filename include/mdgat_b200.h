@@ -231,6 +231,10 @@ int mdgat_measure_fp64_mixed(double* tflops_dmma, double* tflops_dfma);
 #define MDGAT_STAGE_MATCH 5
 #define MDGAT_STAGE_COUNT 6
 long long mdgat_launch_count(void);
+/* Debug timeline: d_buf = NULL (default, off) or a zeroed device buffer of 8 roles x (2 + 2*1024) int64. While set, CTA
+ * (0,0,0) of the tcgen05 kernels records (tag, clock64) pairs per role (loader, MMA issuer, two epilogue warps):
+ * buf[role*2050] = count, then the pairs. tools/trace_tcgen05.py prints the timeline. */
+int mdgat_debug_trace(void* d_buf);
 int mdgat_profile_enable(int on);
 int mdgat_profile_collect(double* ms, long long* launches, long long* segments, int n);
 

@@ -73,6 +73,7 @@ def _load():
         'mdgat_measure_fp64_peak': (i, [C.POINTER(d), C.POINTER(d)]),
         'mdgat_measure_fp64_mixed': (i, [C.POINTER(d), C.POINTER(d)]),
         'mdgat_launch_count': (ll, []),
+        'mdgat_debug_trace': (i, [vp]),
         'mdgat_profile_enable': (i, [i]),
         'mdgat_profile_collect': (i, [C.POINTER(d), C.POINTER(ll), C.POINTER(ll), i]),
     }

@@ -71,6 +71,19 @@ DEVINL void bulk_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar
                  :: "r"(d), "l"(gmem), "r"(bytes), "r"(b) : "memory");
 }
 
+// ---- timeline probe (debug): one CTA records (tag, clock64) pairs per role into a global buffer set with
+// mdgat_debug_trace() and handed to the kernels as a parameter; a null buffer (the default) costs one predicate per probe.
+constexpr int TRACE_CAP = 1024;                 // records per role
+struct Tracer {
+    long long* base; int n;
+    DEVINL void init(long long* b, int role, bool cta_selected) {
+        base = (b != nullptr && cta_selected) ? b + (size_t)role * (2 * TRACE_CAP + 2) : nullptr; n = 0;
+    }
+    DEVINL void mark(int tag) {
+        if (base != nullptr && n < TRACE_CAP) { base[2 + 2 * n] = tag; base[3 + 2 * n] = clock64(); ++n; base[0] = n; }
+    }
+};
+
 DEVINL double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 DEVINL double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 

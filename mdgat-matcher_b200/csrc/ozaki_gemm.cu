@@ -134,6 +134,7 @@ struct OzParams {
     int epi;                                           // EPI_PLAIN / EPI_QKV
     double *Qh, *Kh, *Vh; int rows0, n0, n1;
     int col_tiles_per_cta;                             // blockIdx.y selects a group of column tiles
+    long long* trace;                                  // debug timeline (null = off)
 };
 
 // One CTA = one 128-row tile x a group of 32-column tiles, warp specialised:
@@ -183,25 +184,27 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = tmem_base_s;
     constexpr int TM_SET = S * OZ_BN;                                // TMEM columns of one accumulator set
+    Tracer tr;
+    tr.init(p.trace, warp == 9 ? 0 : (warp == 8 ? 1 : (warp == 0 ? 2 : 3)), blockIdx.x == 0 && blockIdx.y == 0 && (tid & 31) == 0 && (warp >= 8 || warp == 0 || warp == 4));
 
     if (warp == 9) {
         // ------------------------------------------------------------------ loader: TMA bulk copies, runs ahead
         if ((tid & 31) == 0 && units > 0) {
             for (int u = 0; u < units; ++u) {
                 const int kc = u / nct, ct = ct_begin + u % nct, stage = u % OZ_WSTAGES;
+                tr.mark(1000 + u);
                 if (u % nct == 0) {
                     if (kc > 0) mbar_wait(&x_free, (unsigned)((kc - 1) & 1));        // MMAs of the previous chunk are done with sX
                     mbar_expect_tx(&x_full, S * OZ_XTILE);
-                    const int8_t* xsrc = p.Xs[kc] + ((size_t)row_tile * S) * OZ_XTILE;
-#pragma unroll
-                    for (int s = 0; s < S; ++s) bulk_g2s(sX + (size_t)s * OZ_XTILE, xsrc + (size_t)s * OZ_XTILE, OZ_XTILE, &x_full);
+                    // the S planes of a row tile are contiguous in global and in shared memory: one bulk copy
+                    const int8_t* xsrc = (kc == 0 ? p.Xs[0] : p.Xs[1]) + ((size_t)row_tile * S) * OZ_XTILE;
+                    bulk_g2s(sX, xsrc, S * OZ_XTILE, &x_full);
                 }
                 if (u >= OZ_WSTAGES) mbar_wait(&w_empty[stage], (unsigned)((u / OZ_WSTAGES - 1) & 1));
                 mbar_expect_tx(&w_full[stage], S * OZ_WTILE);
                 const int8_t* wsrc = p.Ws + ((size_t)(ct * nkc + kc) * S) * OZ_WTILE;
-#pragma unroll
-                for (int s = 0; s < S; ++s)
-                    bulk_g2s(sW + ((size_t)stage * S + s) * OZ_WTILE, wsrc + (size_t)s * OZ_WTILE, OZ_WTILE, &w_full[stage]);
+                bulk_g2s(sW + (size_t)stage * S * OZ_WTILE, wsrc, S * OZ_WTILE, &w_full[stage]);
+                tr.mark(2000 + u);
             }
         }
     } else if (warp == 8) {
@@ -216,9 +219,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             const uint64_t xd0 = umma_desc(sX, 128, OZ_KC * 8), wd0 = umma_desc(sW, 128, OZ_KC * 8);
             for (int u = 0; u < units; ++u) {
                 const int kc = u / nct, stage = u % OZ_WSTAGES, set = u & 1;
+                tr.mark(3000 + u);
                 if (u % nct == 0) mbar_wait(&x_full, (unsigned)(kc & 1));
                 mbar_wait(&w_full[stage], (unsigned)((u / OZ_WSTAGES) & 1));
+                tr.mark(4000 + u);
                 if (u >= 2) mbar_wait(&tm_empty[set], (unsigned)((u / 2 - 1) & 1));   // epilogue drained this accumulator set
+                tr.mark(5000 + u);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint64_t wdu = wd0 + (uint64_t)((stage * S * OZ_WTILE) >> 4);
                 const uint32_t dbase = tmem + set * TM_SET;
@@ -238,6 +244,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 umma_commit(&tm_full[set]);                 // accumulator set ready for the epilogue
                 umma_commit(&w_empty[stage]);               // W stage free once these MMAs have read it
                 if (u % nct == nct - 1) umma_commit(&x_free);
+                tr.mark(6000 + u);
             }
         }
     } else {
@@ -274,8 +281,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                     for (int j = 0; j < 16; j += 2) { const double2 v = *reinterpret_cast<const double2*>(rr + j); add[j] = v.x; add[j + 1] = v.y; }
                 }
             }
-            const double rs = row_ok ? p.rowscale[kc][row] : 0.0;
+            const double rs = row_ok ? (kc == 0 ? p.rowscale[0] : p.rowscale[1])[row] : 0.0;
+            tr.mark(7000 + u);
             mbar_wait(&tm_full[set], (unsigned)((u / 2) & 1));
+            tr.mark(8000 + u);
             asm volatile("tcgen05.fence::after_thread_sync;");
             // Horner over the diagonals. Two neighbouring diagonals are first merged exactly in int32
             // (|acc_dd| <= (dd+1) * 128 * 64 * 64 < 2^23, so acc_dd * 128 + acc_dd+1 < 2^31), then converted with the
@@ -296,6 +305,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             // all TMEM reads of this set are complete: hand it back to the tensor core
             asm volatile("tcgen05.fence::before_thread_sync;");
             mbar_arrive(&tm_empty[set]);
+            tr.mark(9000 + u);
             if (!row_ok) continue;
             double t[16];
             auto to_f64 = [&](int v) {
@@ -396,6 +406,7 @@ cudaError_t launch_ozaki_gemm(const OzGemmArgs& a, int S, cudaStream_t st) {
     p.Xs[0] = a.Xs[0]; p.Xs[1] = a.Xs[1]; p.rowscale[0] = a.rowscale[0]; p.rowscale[1] = a.rowscale[1]; p.Ws = a.Ws; p.colscale = a.colscale; p.bias = a.bias;
     p.Res = a.Res; p.ldres = a.ldres; p.Y = a.Y; p.ldy = a.ldy; p.R = a.R; p.Nout = a.Nout; p.K = a.K;
     p.relu = a.relu; p.epi = a.epi; p.Qh = a.Qh; p.Kh = a.Kh; p.Vh = a.Vh; p.rows0 = a.rows0; p.n0 = a.n0; p.n1 = a.n1;
+    p.trace = g_trace_dev;
     const int row_tiles = (a.R + OZ_BM - 1) / OZ_BM, col_tiles = a.Nout / OZ_BN;
     // the X slice planes are loaded once per (CTA, k chunk): keep all column tiles in one CTA unless that leaves
     // SMs idle

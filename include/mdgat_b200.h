@@ -235,6 +235,10 @@ long long mdgat_launch_count(void);
  * (0,0,0) of the tcgen05 kernels records (tag, clock64) pairs per role (loader, MMA issuer, two epilogue warps):
  * buf[role*2050] = count, then the pairs. tools/trace_tcgen05.py prints the timeline. */
 int mdgat_debug_trace(void* d_buf);
+/* Debug switches for timeline experiments (0 = normal operation). Bit 0: the Ozaki GEMM epilogue skips its global
+ * stores; bit 1: it skips the float64 recombination (results are wrong while 0 or 1 is set); bit 2: the epilogue warps
+ * record timeline marks too (costs registers: their timing is then not that of the production kernel). */
+int mdgat_debug_flags(int flags);
 int mdgat_profile_enable(int on);
 int mdgat_profile_collect(double* ms, long long* launches, long long* segments, int n);
 

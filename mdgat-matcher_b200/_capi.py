@@ -74,6 +74,7 @@ def _load():
         'mdgat_measure_fp64_mixed': (i, [C.POINTER(d), C.POINTER(d)]),
         'mdgat_launch_count': (ll, []),
         'mdgat_debug_trace': (i, [vp]),
+        'mdgat_debug_flags': (i, [i]),
         'mdgat_profile_enable': (i, [i]),
         'mdgat_profile_collect': (i, [C.POINTER(d), C.POINTER(ll), C.POINTER(ll), i]),
     }

@@ -53,7 +53,7 @@ void prof_mark(int stage, cudaStream_t st) {
     g_prof.launches_at.push_back(g_launches.load());
 }
 }  // namespace
-namespace mdgat { void count_launch(int n) { g_launches.fetch_add(n); } long long* g_trace_dev = nullptr; }
+namespace mdgat { void count_launch(int n) { g_launches.fetch_add(n); } long long* g_trace_dev = nullptr; int g_debug_flags = 0; }
 
 namespace {
 
@@ -495,6 +495,8 @@ int mdgat_knn(const double* d_x, const double* d_src, int64_t* d_idx, int B, int
 long long mdgat_launch_count(void) { return g_launches.load(); }
 
 int mdgat_debug_trace(void* d_buf) { mdgat::g_trace_dev = reinterpret_cast<long long*>(d_buf); return MDGAT_OK; }
+
+int mdgat_debug_flags(int flags) { mdgat::g_debug_flags = flags; return MDGAT_OK; }
 
 int mdgat_profile_enable(int on) {
     g_prof.on = on != 0;

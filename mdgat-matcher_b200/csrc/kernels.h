@@ -10,6 +10,7 @@ enum { EPI_PLAIN = 0, EPI_QKV = 1 };
 
 // debug timeline buffer (device pointer, or null), see Tracer in common.cuh
 extern long long* g_trace_dev;
+extern int g_debug_flags;
 
 // every kernel launch of this library is counted (bench.py reports it as gpu_launches)
 void count_launch(int n = 1);

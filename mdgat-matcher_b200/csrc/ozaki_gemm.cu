@@ -29,7 +29,7 @@ namespace mdgat {
 constexpr int OZ_BM = 128, OZ_BN = 32, OZ_KC = 128;
 constexpr int OZ_XTILE = OZ_BM * OZ_KC, OZ_WTILE = OZ_BN * OZ_KC;       // bytes per slice tile
 constexpr int OZ_WSTAGES = 3;                                             // W tile ring
-constexpr int OZ_EPI_THREADS = 256, OZ_THREADS = OZ_EPI_THREADS + 64;     // 8 epilogue warps + MMA warp + loader warp
+constexpr int OZ_EPI_WARPS = 16, OZ_EPI_THREADS = OZ_EPI_WARPS * 32, OZ_THREADS = OZ_EPI_THREADS + 64;   // epilogue warps + MMA warp + loader warp
 constexpr int OZ_MAXN = 384;                                               // widest GEMM (q/k/v stack): scales staged in smem
 
 DEVINL int oz_canon(int r, int k) { return (r >> 3) * (OZ_KC * 8) + (k >> 4) * 128 + (r & 7) * 16 + (k & 15); }
@@ -135,6 +135,7 @@ struct OzParams {
     double *Qh, *Kh, *Vh; int rows0, n0, n1;
     int col_tiles_per_cta;                             // blockIdx.y selects a group of column tiles
     long long* trace;                                  // debug timeline (null = off)
+    int dbg;                                           // debug switches (mdgat_debug_flags)
 };
 
 // One CTA = one 128-row tile x a group of 32-column tiles, warp specialised:
@@ -147,14 +148,14 @@ struct OzParams {
 //                    columns), scales, and -- k chunks being accumulated in float64 through the output buffer, each
 //                    with its own row/column scale -- bias, ReLU, residual or the q/k/v scatter after the last chunk.
 //                    While it works on one accumulator set the tensor core fills the other.
-template <int S>
+template <int S, int EPI, int DBG, bool FULL>
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_constant__ OzParams p) {
     extern __shared__ __align__(128) unsigned char oz_smem[];
     int8_t* sX = reinterpret_cast<int8_t*>(oz_smem);                 // [S][128*128]
     int8_t* sW = sX + (size_t)S * OZ_XTILE;                          // [OZ_WSTAGES][S][32*128]
     __shared__ __align__(8) uint64_t x_full, x_free, w_full[OZ_WSTAGES], w_empty[OZ_WSTAGES], tm_full[2], tm_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ double s_cs[2 * OZ_MAXN], s_bias[OZ_MAXN];             // column scales per k chunk, bias
+    __shared__ __align__(16) double s_cs[2 * OZ_MAXN], s_bias[OZ_MAXN];             // column scales per k chunk, bias
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row_tile = blockIdx.x;
     const int nkc = p.K / OZ_KC;
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
     }
     for (int i = tid; i < nkc * p.Nout; i += OZ_THREADS) s_cs[i] = p.colscale[i];
     for (int i = tid; i < p.Nout; i += OZ_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.0;
-    if (warp == 8) {
+    if (warp == OZ_EPI_WARPS) {
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_s);
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(dst));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -185,29 +186,34 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
     const uint32_t tmem = tmem_base_s;
     constexpr int TM_SET = S * OZ_BN;                                // TMEM columns of one accumulator set
     Tracer tr;
-    tr.init(p.trace, warp == 9 ? 0 : (warp == 8 ? 1 : (warp == 0 ? 2 : 3)), blockIdx.x == 0 && blockIdx.y == 0 && (tid & 31) == 0 && (warp >= 8 || warp == 0 || warp == 4));
+    if (DBG) tr.init(p.trace, warp == OZ_EPI_WARPS + 1 ? 0 : (warp == OZ_EPI_WARPS ? 1 : (warp == 0 ? 2 : 3)), blockIdx.x == 0 && blockIdx.y == 0 && (tid & 31) == 0 && (warp >= OZ_EPI_WARPS || (DBG > 1 && (warp == 0 || warp == 4))));
 
-    if (warp == 9) {
+    if (warp == OZ_EPI_WARPS + 1) {
         // ------------------------------------------------------------------ loader: TMA bulk copies, runs ahead
         if ((tid & 31) == 0 && units > 0) {
+            // (kc, ctl, stage, ring phase) are walked incrementally: a division by the runtime nct costs this single
+            // thread ~100 cycles of dependent instructions per unit
+            int kc = 0, ctl = 0, stage = 0; unsigned wphase = 1;       // wphase: parity of the ring pass before this one
             for (int u = 0; u < units; ++u) {
-                const int kc = u / nct, ct = ct_begin + u % nct, stage = u % OZ_WSTAGES;
-                tr.mark(1000 + u);
-                if (u % nct == 0) {
+                const int ct = ct_begin + ctl;
+                if (DBG) tr.mark(1000 + u);
+                if (ctl == 0) {
                     if (kc > 0) mbar_wait(&x_free, (unsigned)((kc - 1) & 1));        // MMAs of the previous chunk are done with sX
                     mbar_expect_tx(&x_full, S * OZ_XTILE);
                     // the S planes of a row tile are contiguous in global and in shared memory: one bulk copy
                     const int8_t* xsrc = (kc == 0 ? p.Xs[0] : p.Xs[1]) + ((size_t)row_tile * S) * OZ_XTILE;
                     bulk_g2s(sX, xsrc, S * OZ_XTILE, &x_full);
                 }
-                if (u >= OZ_WSTAGES) mbar_wait(&w_empty[stage], (unsigned)((u / OZ_WSTAGES - 1) & 1));
+                if (u >= OZ_WSTAGES) mbar_wait(&w_empty[stage], wphase);
                 mbar_expect_tx(&w_full[stage], S * OZ_WTILE);
                 const int8_t* wsrc = p.Ws + ((size_t)(ct * nkc + kc) * S) * OZ_WTILE;
                 bulk_g2s(sW + (size_t)stage * S * OZ_WTILE, wsrc, S * OZ_WTILE, &w_full[stage]);
-                tr.mark(2000 + u);
+                if (DBG) tr.mark(2000 + u);
+                if (++ctl == nct) { ctl = 0; ++kc; }
+                if (++stage == OZ_WSTAGES) { stage = 0; wphase ^= 1u; }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == OZ_EPI_WARPS) {
         // ------------------------------------------------------------------ MMA issuer: one thread, never waits on loads it issued
         if ((tid & 31) == 0 && units > 0) {
             // Stacked-N issue. The S weight planes of a column tile sit back to back in shared memory, i.e. they form ONE
@@ -217,14 +223,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             // S(S+1)/2 narrow ones. A 128x32x32 MMA takes 45 cycles on this part (operand fetch bound, 16 in
             // theory), a 128xNx32 one N/2 cycles from N = 128 up (tools/ubench/umma_i8_rate.cu).
             const uint64_t xd0 = umma_desc(sX, 128, OZ_KC * 8), wd0 = umma_desc(sW, 128, OZ_KC * 8);
+            int kc = 0, ctl = 0, stage = 0; unsigned wphase = 0;
             for (int u = 0; u < units; ++u) {
-                const int kc = u / nct, stage = u % OZ_WSTAGES, set = u & 1;
-                tr.mark(3000 + u);
-                if (u % nct == 0) mbar_wait(&x_full, (unsigned)(kc & 1));
-                mbar_wait(&w_full[stage], (unsigned)((u / OZ_WSTAGES) & 1));
-                tr.mark(4000 + u);
+                const int set = u & 1;
+                if (DBG) tr.mark(3000 + u);
+                if (ctl == 0) mbar_wait(&x_full, (unsigned)(kc & 1));
+                mbar_wait(&w_full[stage], wphase);
+                if (DBG) tr.mark(4000 + u);
                 if (u >= 2) mbar_wait(&tm_empty[set], (unsigned)((u / 2 - 1) & 1));   // epilogue drained this accumulator set
-                tr.mark(5000 + u);
+                if (DBG) tr.mark(5000 + u);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint64_t wdu = wd0 + (uint64_t)((stage * S * OZ_WTILE) >> 4);
                 const uint32_t dbase = tmem + set * TM_SET;
@@ -243,118 +250,165 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 }
                 umma_commit(&tm_full[set]);                 // accumulator set ready for the epilogue
                 umma_commit(&w_empty[stage]);               // W stage free once these MMAs have read it
-                if (u % nct == nct - 1) umma_commit(&x_free);
-                tr.mark(6000 + u);
+                if (ctl == nct - 1) umma_commit(&x_free);
+                if (DBG) tr.mark(6000 + u);
+                if (++ctl == nct) { ctl = 0; ++kc; }
+                if (++stage == OZ_WSTAGES) { stage = 0; wphase ^= 1u; }
             }
         }
     } else {
         // ------------------------------------------------------------------ epilogue warps
-        // warp w reads TMEM lanes 32*(w%4)..: warps w and w+4 share a lane quarter and split the 32 columns of a
-        // unit 16 / 16, so every SM sub-partition has two epilogue warps to overlap latencies.
-        const int lane = tid & 31, quarter = warp & 3, half = warp >> 2;
-        const int row = row_tile * OZ_BM + quarter * 32 + lane;      // output row = TMEM lane
-        const bool row_ok = row < p.R;
-        long long hrow = 0; int npts = 0;
-        if (p.epi == EPI_QKV && row_ok) {
-            if (row < p.rows0) { const int b = row / p.n0; npts = p.n0; hrow = (long long)b * HEADS * p.n0 + (row - b * p.n0); }
-            else { const int r1 = row - p.rows0; const int b = r1 / p.n1; npts = p.n1;
-                   hrow = (long long)p.rows0 * HEADS + (long long)b * HEADS * p.n1 + (r1 - b * p.n1); }
-        }
-        const double MAGIC = 6755399441055744.0;                     // 1.5 * 2^52
-        for (int u = 0; u < units; ++u) {
-            const int kc = u / nct, ct = ct_begin + u % nct, set = u & 1;
-            const int col0 = ct * OZ_BN + half * 16;
-            const bool first = kc == 0, last = kc == nkc - 1;
-            const bool res_first = p.Res && !p.relu;
-            double* dst = p.Y + (long long)row * p.ldy + col0;
-            // operands that come from global memory are requested before the wait on the tensor core
-            double add[16];
+        // 16 warps = 4 per SM sub-partition. Warp w owns TMEM lanes 32*(w%4).. (hardware rule) and columns 8*(w/4)..+7
+        // of every 32-column unit. Accumulators are read with the 16x256b shape, i.e. in MMA C-fragment order: lane t
+        // holds rows t/4 and t/4 + 8 of a 16-lane half and the column pair 2*(t%4), +1 -- so a quad owns 64
+        // contiguous bytes of an output row and a warp-wide double2 access touches 8 rows x 64 B (19.7 B/clk/SM of
+        // store throughput against 9.1 for the thread-per-row shape, tools/ubench/store_patterns.cu).
+        // Register budget: 18 warps cap a thread at 96 registers and every spill is a local-memory load queued behind
+        // the global stores, so the diagonals are fetched in two rounds and neighbouring ones merged in int32 at once.
+        const int lane = tid & 31, quarter = warp & 3, cg = warp >> 2;
+        const int cpair = cg * 8 + (lane & 3) * 2;                   // column pair inside a unit
+        const int rbase = row_tile * OZ_BM + quarter * 32 + (lane >> 2);   // rows rbase + 8 i, i = 0..3
+        int hrow[EPI == EPI_QKV ? 4 : 1], npts[EPI == EPI_QKV ? 4 : 1];      // head-major row of the point, points per set
+        if (EPI == EPI_QKV) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) add[j] = 0.0;
-            if (row_ok && p.epi == EPI_PLAIN) {
-                if (!first) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) { const double2 v = *reinterpret_cast<const double2*>(dst + j); add[j] = v.x; add[j + 1] = v.y; }
-                } else if (res_first) {
-                    const double* rr = p.Res + (long long)row * p.ldres + col0;
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) { const double2 v = *reinterpret_cast<const double2*>(rr + j); add[j] = v.x; add[j + 1] = v.y; }
+            for (int i = 0; i < 4; ++i) {
+                const int row = rbase + 8 * i;
+                hrow[i] = 0; npts[i] = 0;
+                if (FULL || row < p.R) {
+                    if (row < p.rows0) { const int b = row / p.n0; npts[i] = p.n0; hrow[i] = b * HEADS * p.n0 + (row - b * p.n0); }
+                    else { const int r1 = row - p.rows0; const int b = r1 / p.n1; npts[i] = p.n1;
+                           hrow[i] = p.rows0 * HEADS + b * HEADS * p.n1 + (r1 - b * p.n1); }
                 }
             }
-            const double rs = row_ok ? (kc == 0 ? p.rowscale[0] : p.rowscale[1])[row] : 0.0;
-            tr.mark(7000 + u);
-            mbar_wait(&tm_full[set], (unsigned)((u / 2) & 1));
-            tr.mark(8000 + u);
-            asm volatile("tcgen05.fence::after_thread_sync;");
-            // Horner over the diagonals. Two neighbouring diagonals are first merged exactly in int32
-            // (|acc_dd| <= (dd+1) * 128 * 64 * 64 < 2^23, so acc_dd * 128 + acc_dd+1 < 2^31), then converted with the
-            // 2^52 magic constant (integer ALU + one DADD instead of a quarter-rate I2F.F64) and chained in float64.
-            int acc[S][16];
-            const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + set * TM_SET + half * 16;
+        }
+        constexpr int G = (S + 1) / 2;                               // digit groups: S odd: {0}, {1,2}, {3,4}, ..; S even: {0,1}, {2,3}, ..
+        const double MAGIC = 6755399441055744.0;                     // 1.5 * 2^52
+        const bool res_first = p.Res && !p.relu;
+        const bool one_chunk = nkc == 1;
+        const int* s_cs_hi = reinterpret_cast<const int*>(s_cs) + 1; // high words of the column scales (exact powers of two)
+        // element offsets fit 32 bits (checked by the launcher): one IMAD per address instead of 64-bit chains
+        const int yrow = rbase * p.ldy, ystep = 8 * p.ldy, rrow = rbase * p.ldres, rstep = 8 * p.ldres;
+        int kc = 0, ctl = 0;                                         // unit u = (kc, ct_begin + ctl), walked incrementally
+        for (int u = 0; u < units; ++u, ++ctl) {
+            if (ctl == nct) { ctl = 0; ++kc; }
+            const int set = u & 1;
+            const int col0 = (ct_begin + ctl) * OZ_BN + cpair;
+            const bool first = kc == 0, last = kc == nkc - 1;
+            // operands that come from global memory are requested before the wait on the tensor core
+            double2 add[4]; int rsh[4];                              // rsh: high word of the row scale 2^(e-12)
+            const int* rsp = reinterpret_cast<const int*>(kc == 0 ? p.rowscale[0] : p.rowscale[1]) + 1 + 2 * rbase;
+            const double2 bias2 = *reinterpret_cast<const double2*>(s_bias + col0);
 #pragma unroll
-            for (int dd = 0; dd < S; ++dd) {
-                uint32_t r[16];
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                             : "=r"(r[0]),"=r"(r[1]),"=r"(r[2]),"=r"(r[3]),"=r"(r[4]),"=r"(r[5]),"=r"(r[6]),"=r"(r[7]),
-                               "=r"(r[8]),"=r"(r[9]),"=r"(r[10]),"=r"(r[11]),"=r"(r[12]),"=r"(r[13]),"=r"(r[14]),"=r"(r[15])
-                             : "r"(lane_addr + dd * OZ_BN));
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[dd][j] = (int)r[j];
-            }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            // all TMEM reads of this set are complete: hand it back to the tensor core
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            mbar_arrive(&tm_empty[set]);
-            tr.mark(9000 + u);
-            if (!row_ok) continue;
-            double t[16];
-            auto to_f64 = [&](int v) {
-                return __hiloint2double(0x43380000 + (v >> 31), v) - MAGIC;      // exact for any int32
-            };
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                // pairs from the least significant end: (S-2,S-1), (S-4,S-3), ...; with S odd diagonal 0 stays single
-                double h = to_f64(acc[S - 2][j] * 128 + acc[S - 1][j]);
-#pragma unroll
-                for (int dd = S - 4; dd >= 0; dd -= 2) h = fma(h, 0.00006103515625, to_f64(acc[dd][j] * 128 + acc[dd + 1][j]));   // 2^-14
-                if (S & 1) h = fma(h, 0.00006103515625, to_f64(acc[0][j]));   // last pair sits at 2^-14, diagonal 0 at 2^0
-                else h *= 0.0078125;                                          // even S: last pair (0,1) carries acc_0 * 128
-                t[j] = h;
-            }
-            const double* cs = s_cs + kc * p.Nout + col0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) t[j] = fma(t[j] * rs, cs[j], add[j]);
-            if (p.epi == EPI_QKV) {
-                // single k chunk; 32 consecutive output channels = one head of q, k or v (head-major c' = h*32 + d)
-#pragma unroll
-                for (int j = 0; j < 16; ++j) t[j] += s_bias[col0 + j];
-                const int which = col0 >> 7, h = (col0 & 127) >> 5;
-                double* base = which == 0 ? p.Qh : (which == 1 ? p.Kh : p.Vh);
-                double* q = base + (hrow + (long long)h * npts) * (which == 2 ? LDH_V : LDH_QK) + (col0 & 31);
-#pragma unroll
-                for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2*>(q + j) = make_double2(t[j], t[j + 1]);
-                continue;
-            }
-            if (last) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) t[j] += s_bias[col0 + j];
-                if (p.relu) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) t[j] = __double2hiint(t[j]) < 0 ? 0.0 : t[j];
-                    if (p.Res) {        // launcher guarantees Res != Y here when there are several k chunks
-                        const double* rr = p.Res + (long long)row * p.ldres + col0;
-#pragma unroll
-                        for (int j = 0; j < 16; j += 2) { const double2 v = *reinterpret_cast<const double2*>(rr + j); t[j] += v.x; t[j + 1] += v.y; }
+            for (int i = 0; i < 4; ++i) {
+                add[i] = one_chunk ? bias2 : make_double2(0.0, 0.0);
+                rsh[i] = 0;
+                if (FULL || rbase + 8 * i < p.R) {
+                    rsh[i] = rsp[16 * i];
+                    if (EPI == EPI_PLAIN) {
+                        if (!first) add[i] = *reinterpret_cast<const double2*>(p.Y + (yrow + i * ystep + col0));
+                        else if (res_first) {
+                            const double2 v = *reinterpret_cast<const double2*>(p.Res + (rrow + i * rstep + col0));
+                            add[i].x += v.x; add[i].y += v.y;
+                        }
                     }
                 }
             }
+            if (DBG > 1) tr.mark(7000 + u);
+            mbar_wait(&tm_full[set], (unsigned)((u / 2) & 1));
+            if (DBG > 1) tr.mark(8000 + u);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            // m[g][half * 4 + (row & 8 ? 2 : 0) + column]: group g of the diagonals merged exactly in int32
+            // (|acc_dd| <= (dd+1) * 128 * 64 * 64 < 2^23, so acc_dd * 128 + acc_dd+1 < 2^31)
+            int m[G][8];
+            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + set * TM_SET + cg * 8;
+            auto ld_diag = [&](int dd, int half, uint32_t (&r)[4]) {
+                asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr + ((uint32_t)(half * 16) << 16) + dd * OZ_BN));
+            };
+            auto fetch_groups = [&](int g_lo, int g_hi) {            // groups [g_lo, g_hi): one round of TMEM loads
+                uint32_t raw[2][2][2][4];                            // [group][digit][half][4]
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(t[j], t[j + 1]);
+                for (int g = g_lo; g < g_hi; ++g) {
+                    const int d0 = (S & 1) ? 2 * g - 1 : 2 * g;      // first diagonal of the group (-1: group 0 of an odd S is diagonal 0 alone)
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        if (d0 >= 0) ld_diag(d0, half, raw[g - g_lo][0][half]);
+                        ld_diag(d0 + 1, half, raw[g - g_lo][1][half]);
+                    }
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int g = g_lo; g < g_hi; ++g) {
+                    const int d0 = (S & 1) ? 2 * g - 1 : 2 * g;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            m[g][half * 4 + j] = d0 >= 0 ? (int)raw[g - g_lo][0][half][j] * 128 + (int)raw[g - g_lo][1][half][j]
+                                                         : (int)raw[g - g_lo][1][half][j];
+                }
+            };
+            fetch_groups(G - 2 > 0 ? G - 2 : 0, G);                   // the two least significant groups
+            if (G > 2) fetch_groups(0, G - 2);
+            // all TMEM reads of this set are complete: hand it back to the tensor core
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            mbar_arrive(&tm_empty[set]);
+            if (DBG > 1) tr.mark(9000 + u);
+            // Horner over the groups in float64; int32 -> float64 with the 2^52 magic constant (integer ALU + one DADD
+            // instead of a quarter-rate I2F.F64)
+            auto to_f64 = [&](int v) {
+                return __hiloint2double(0x43380000 + (v >> 31), v) - MAGIC;      // exact for any int32
+            };
+            double t[8];
+            if (DBG > 1 && (p.dbg & 2)) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { int x = 0;
+#pragma unroll
+                    for (int g = 0; g < G; ++g) x ^= m[g][j];
+                    t[j] = __hiloint2double(x, x); }
+            } else
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                double h = to_f64(m[G - 1][j]);
+#pragma unroll
+                for (int g = G - 2; g >= 0; --g) h = fma(h, 0.00006103515625, to_f64(m[g][j]));   // 2^-14 per group
+                t[j] = h;                                             // even S: group 0 carries acc_0 * 128, folded into the scale below
+            }
+            // scale 2^(e_row - 12) * 2^(f_col) [* 2^-7] assembled in the exponent field: both factors are exact powers of two
+            const int csh0 = s_cs_hi[2 * (kc * p.Nout + col0)] - ((S & 1) ? 0x3FF00000 : 0x3FF00000 + (7 << 20));
+            const int csh1 = s_cs_hi[2 * (kc * p.Nout + col0 + 1)] - ((S & 1) ? 0x3FF00000 : 0x3FF00000 + (7 << 20));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (!FULL && rbase + 8 * i >= p.R) continue;
+                double2 y;
+                y.x = fma(t[2 * i], __hiloint2double(rsh[i] + csh0, 0), add[i].x);
+                y.y = fma(t[2 * i + 1], __hiloint2double(rsh[i] + csh1, 0), add[i].y);
+                if (DBG > 1 && (p.dbg & 1) && y.x != 1234.5) continue;
+                if (EPI == EPI_QKV) {
+                    // single k chunk; 32 consecutive output channels = one head of q, k or v (head-major c' = h*32 + d)
+                    const int which = col0 >> 7, h = (col0 & 127) >> 5;
+                    double* base = which == 0 ? p.Qh : (which == 1 ? p.Kh : p.Vh);
+                    *reinterpret_cast<double2*>(base + (long long)(hrow[i] + h * npts[i]) * (which == 2 ? LDH_V : LDH_QK) + (col0 & 31)) = y;
+                    continue;
+                }
+                if (last) {
+                    if (!one_chunk) { y.x += bias2.x; y.y += bias2.y; }
+                    if (p.relu) {
+                        y.x = __double2hiint(y.x) < 0 ? 0.0 : y.x;
+                        y.y = __double2hiint(y.y) < 0 ? 0.0 : y.y;
+                        if (p.Res) {        // launcher guarantees Res != Y here when there are several k chunks
+                            const double2 v = *reinterpret_cast<const double2*>(p.Res + (rrow + i * rstep + col0));
+                            y.x += v.x; y.y += v.y;
+                        }
+                    }
+                }
+                *reinterpret_cast<double2*>(p.Y + (yrow + i * ystep + col0)) = y;
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem));
+    if (warp == OZ_EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem));
 }
 
 size_t ozaki_slices_bytes(int R, int K, int S) {
@@ -388,13 +442,26 @@ cudaError_t launch_slice_rows(const double* A0, int ld0, int K0, const double* A
     return e;
 }
 
+template <int S, int EPI, int DBG, bool FULL>
+static cudaError_t ozaki_gemm_tf(const OzParams& p, dim3 grid, cudaStream_t st) {
+    const size_t smem = (size_t)S * (OZ_XTILE + OZ_WSTAGES * OZ_WTILE);
+    cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel<S, EPI, DBG, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ozaki_gemm_kernel<S, EPI, DBG, FULL><<<grid, OZ_THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+template <int S, int EPI, int DBG>
+static cudaError_t ozaki_gemm_te(const OzParams& p, dim3 grid, cudaStream_t st) {
+    // row count a multiple of the tile height (cfg2: 32768 rows): the epilogue drops every row check
+    return (p.R % OZ_BM) == 0 ? ozaki_gemm_tf<S, EPI, DBG, true>(p, grid, st) : ozaki_gemm_tf<S, EPI, DBG, false>(p, grid, st);
+}
 template <int S>
 static cudaError_t ozaki_gemm_t(const OzParams& p, dim3 grid, cudaStream_t st) {
-    const size_t smem = (size_t)S * (OZ_XTILE + OZ_WSTAGES * OZ_WTILE);
-    cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    ozaki_gemm_kernel<S><<<grid, OZ_THREADS, smem, st>>>(p);
-    return cudaGetLastError();
+    // timeline probes / debug switches live in their own instantiations: 1 = loader + MMA thread only (the epilogue
+    // is the production code), 2 = epilogue probes and switches too (costs registers there)
+    if (p.dbg != 0) return p.epi == EPI_QKV ? ozaki_gemm_te<S, EPI_QKV, 2>(p, grid, st) : ozaki_gemm_te<S, EPI_PLAIN, 2>(p, grid, st);
+    if (p.trace != nullptr) return p.epi == EPI_QKV ? ozaki_gemm_te<S, EPI_QKV, 1>(p, grid, st) : ozaki_gemm_te<S, EPI_PLAIN, 1>(p, grid, st);
+    return p.epi == EPI_QKV ? ozaki_gemm_te<S, EPI_QKV, 0>(p, grid, st) : ozaki_gemm_te<S, EPI_PLAIN, 0>(p, grid, st);
 }
 
 cudaError_t launch_ozaki_gemm(const OzGemmArgs& a, int S, cudaStream_t st) {
@@ -402,11 +469,14 @@ cudaError_t launch_ozaki_gemm(const OzGemmArgs& a, int S, cudaStream_t st) {
     if ((a.K != OZ_KC && a.K != 2 * OZ_KC) || (a.Nout % OZ_BN) != 0 || a.Nout > OZ_MAXN) return cudaErrorInvalidValue;
     if (a.relu && a.Res == a.Y && a.Res != nullptr && a.K > OZ_KC) return cudaErrorInvalidValue;   // see res_first
     if (a.epi == EPI_QKV && a.K != OZ_KC) return cudaErrorInvalidValue;
+    // the epilogue addresses Y / Res / the head-major q,k,v rows with 32-bit element offsets
+    const long long rpad = (long long)((a.R + OZ_BM - 1) / OZ_BM) * OZ_BM;
+    if (rpad * (a.ldy > a.ldres ? a.ldy : a.ldres) >= (1ll << 31) || rpad * HEADS * LDH_QK >= (1ll << 31)) return cudaErrorInvalidValue;
     OzParams p;
     p.Xs[0] = a.Xs[0]; p.Xs[1] = a.Xs[1]; p.rowscale[0] = a.rowscale[0]; p.rowscale[1] = a.rowscale[1]; p.Ws = a.Ws; p.colscale = a.colscale; p.bias = a.bias;
     p.Res = a.Res; p.ldres = a.ldres; p.Y = a.Y; p.ldy = a.ldy; p.R = a.R; p.Nout = a.Nout; p.K = a.K;
     p.relu = a.relu; p.epi = a.epi; p.Qh = a.Qh; p.Kh = a.Kh; p.Vh = a.Vh; p.rows0 = a.rows0; p.n0 = a.n0; p.n1 = a.n1;
-    p.trace = g_trace_dev;
+    p.trace = g_trace_dev; p.dbg = g_debug_flags;
     const int row_tiles = (a.R + OZ_BM - 1) / OZ_BM, col_tiles = a.Nout / OZ_BN;
     // the X slice planes are loaded once per (CTA, k chunk): keep all column tiles in one CTA unless that leaves
     // SMs idle

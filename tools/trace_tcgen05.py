@@ -16,14 +16,16 @@ ROLES = ('loader', 'mma', 'epi warp0', 'epi warp4')
 CAP = 1024
 
 
-def run(name, fn):
+def run(name, fn, flags=0, full=True):
     dev = torch.device('cuda:0')
     fn()
     torch.cuda.synchronize()
     buf = torch.zeros(8 * (2 + 2 * CAP), dtype=torch.int64, device=dev)
     _capi.check(_capi.lib.mdgat_debug_trace(buf.data_ptr()))
+    _capi.check(_capi.lib.mdgat_debug_flags(flags))
     fn()
     torch.cuda.synchronize()
+    _capi.check(_capi.lib.mdgat_debug_flags(0))
     _capi.check(_capi.lib.mdgat_debug_trace(None))
     b = buf.cpu().view(8, 2 + 2 * CAP)
     recs = {}
@@ -34,10 +36,10 @@ def run(name, fn):
         recs[role] = rr
         if rr:
             t0 = rr[0][1] if t0 is None else min(t0, rr[0][1])
-    print('==== %s' % name)
+    print('==== %s (debug flags %d)' % (name, flags))
     for role in ROLES:
         rr = recs[role]
-        if not rr:
+        if not rr or not full:
             continue
         print('-- %s (%d records)' % (role, len(rr)))
         prev = None
@@ -55,6 +57,9 @@ def run(name, fn):
     if units:
         print('-- per unit: wait operands | wait tmem | issue | epi: wait mma | drain tmem | math+stores')
         for u in units:
+            if 8000 + u not in epi:
+                print('   u=%2d  %6d %6d %6d' % (u, mma[4000 + u] - mma[3000 + u], mma[5000 + u] - mma[4000 + u], mma[6000 + u] - mma[5000 + u]))
+                continue
             try:
                 nxt = epi.get(7000 + u + 1, None)
                 print('   u=%2d  %6d %6d %6d | %6d %6d %s' % (
@@ -63,7 +68,7 @@ def run(name, fn):
                     '%6d' % (nxt - epi[9000 + u]) if nxt else '     -'))
             except KeyError:
                 pass
-        last = max(c for _, c in recs['epi warp0'])
+        last = max(c for r in recs.values() for _, c in r)
         print('   CTA span (first record -> last epilogue record): %d cycles for %d units = %.0f cycles/unit' %
               (last - t0, len(units), (last - t0) / len(units)))
 
@@ -82,6 +87,9 @@ def main():
     run('plain K=128 N=384 (q/k/v shape)', lambda: ops.linear_i8(x, wqkv))
     run('MLP 256->256 relu (cat[x, msg])', lambda: ops.linear_i8(x, w1, bias=b1, relu=True, x2=m))
     run('MLP 256->128 + residual', lambda: ops.linear_i8(h, w2, residual=x))
+    for flags in (4, 5, 6, 7):
+        run('plain K=128 N=384', lambda: ops.linear_i8(x, wqkv), flags, False)
+        run('MLP 256->256 relu', lambda: ops.linear_i8(x, w1, bias=b1, relu=True, x2=m), flags, False)
 
 
 if __name__ == '__main__':

@@ -21,6 +21,7 @@
 // (8 rows x 16 bytes contiguous, k-chunks adjacent: LBO = 128 B, row groups SBO = 1024 B), so a tile
 // is one contiguous block in global memory and one cp.async.bulk brings it in.
 //   Xs[row_tile][k_chunk][slice][128*128]      Ws[col_tile][k_chunk][slice][64*128]
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -148,7 +149,7 @@ struct OzParams {
 //                    columns), scales, and -- k chunks being accumulated in float64 through the output buffer, each
 //                    with its own row/column scale -- bias, ReLU, residual or the q/k/v scatter after the last chunk.
 //                    While it works on one accumulator set the tensor core fills the other.
-template <int S, int EPI, int DBG, bool FULL>
+template <int S, int EPI, int DBG, bool FULL, int GROUPS>
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_constant__ OzParams p) {
     extern __shared__ __align__(128) unsigned char oz_smem[];
     int8_t* sX = reinterpret_cast<int8_t*>(oz_smem);                 // [S][128*128]
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
 #pragma unroll
         for (int i = 0; i < OZ_WSTAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], OZ_EPI_THREADS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], OZ_EPI_THREADS / GROUPS); }
         mbar_fence_init();
     }
     for (int i = tid; i < nkc * p.Nout; i += OZ_THREADS) s_cs[i] = p.colscale[i];
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             int kc = 0, ctl = 0, stage = 0; unsigned wphase = 1;       // wphase: parity of the ring pass before this one
             for (int u = 0; u < units; ++u) {
                 const int ct = ct_begin + ctl;
-                if (DBG) tr.mark(1000 + u);
+                if (DBG && !(p.dbg & 256)) tr.mark(1000 + u);
                 if (ctl == 0) {
                     if (kc > 0) mbar_wait(&x_free, (unsigned)((kc - 1) & 1));        // MMAs of the previous chunk are done with sX
                     mbar_expect_tx(&x_full, S * OZ_XTILE);
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 mbar_expect_tx(&w_full[stage], S * OZ_WTILE);
                 const int8_t* wsrc = p.Ws + ((size_t)(ct * nkc + kc) * S) * OZ_WTILE;
                 bulk_g2s(sW + (size_t)stage * S * OZ_WTILE, wsrc, S * OZ_WTILE, &w_full[stage]);
-                if (DBG) tr.mark(2000 + u);
+                if (DBG && !(p.dbg & 512)) tr.mark(2000 + u);
                 if (++ctl == nct) { ctl = 0; ++kc; }
                 if (++stage == OZ_WSTAGES) { stage = 0; wphase ^= 1u; }
             }
@@ -226,12 +227,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             int kc = 0, ctl = 0, stage = 0; unsigned wphase = 0;
             for (int u = 0; u < units; ++u) {
                 const int set = u & 1;
-                if (DBG) tr.mark(3000 + u);
+                if (DBG && !(p.dbg & 1024)) tr.mark(3000 + u);
                 if (ctl == 0) mbar_wait(&x_full, (unsigned)(kc & 1));
                 mbar_wait(&w_full[stage], wphase);
-                if (DBG) tr.mark(4000 + u);
+                if (DBG && !(p.dbg & 2048)) tr.mark(4000 + u);
                 if (u >= 2) mbar_wait(&tm_empty[set], (unsigned)((u / 2 - 1) & 1));   // epilogue drained this accumulator set
-                if (DBG) tr.mark(5000 + u);
+                if (DBG && !(p.dbg & 4096)) tr.mark(5000 + u);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint64_t wdu = wd0 + (uint64_t)((stage * S * OZ_WTILE) >> 4);
                 const uint32_t dbase = tmem + set * TM_SET;
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 umma_commit(&tm_full[set]);                 // accumulator set ready for the epilogue
                 umma_commit(&w_empty[stage]);               // W stage free once these MMAs have read it
                 if (ctl == nct - 1) umma_commit(&x_free);
-                if (DBG) tr.mark(6000 + u);
+                if (DBG && !(p.dbg & 8192)) tr.mark(6000 + u);
                 if (++ctl == nct) { ctl = 0; ++kc; }
                 if (++stage == OZ_WSTAGES) { stage = 0; wphase ^= 1u; }
             }
@@ -265,8 +266,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
         // store throughput against 9.1 for the thread-per-row shape, tools/ubench/store_patterns.cu).
         // Register budget: 18 warps cap a thread at 96 registers and every spill is a local-memory load queued behind
         // the global stores, so the diagonals are fetched in two rounds and neighbouring ones merged in int32 at once.
-        const int lane = tid & 31, quarter = warp & 3, cg = warp >> 2;
-        const int cpair = cg * 8 + (lane & 3) * 2;                   // column pair inside a unit
+        // GROUPS == 2: warps 0-7 take the even units (accumulator set 0), warps 8-15 the odd ones (set 1), each warp
+        // covering 16 columns in two passes of 8 -- the two groups are then in different phases (TMEM latency, FP64
+        // math, stores) at any time instead of all 16 warps queueing for the same pipe.
+        constexpr int PASSES = GROUPS;
+        const int lane = tid & 31, grp = GROUPS == 2 ? warp >> 3 : 0, wl = GROUPS == 2 ? warp & 7 : warp;
+        const int quarter = wl & 3, cg0 = (wl >> 2) * PASSES;
         const int rbase = row_tile * OZ_BM + quarter * 32 + (lane >> 2);   // rows rbase + 8 i, i = 0..3
         int hrow[EPI == EPI_QKV ? 4 : 1], npts[EPI == EPI_QKV ? 4 : 1];      // head-major row of the point, points per set
         if (EPI == EPI_QKV) {
@@ -288,22 +293,26 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
         const int* s_cs_hi = reinterpret_cast<const int*>(s_cs) + 1; // high words of the column scales (exact powers of two)
         // element offsets fit 32 bits (checked by the launcher): one IMAD per address instead of 64-bit chains
         const int yrow = rbase * p.ldy, ystep = 8 * p.ldy, rrow = rbase * p.ldres, rstep = 8 * p.ldres;
-        int kc = 0, ctl = 0;                                         // unit u = (kc, ct_begin + ctl), walked incrementally
-        for (int u = 0; u < units; ++u, ++ctl) {
-            if (ctl == nct) { ctl = 0; ++kc; }
+        int kc = 0, ctl = grp;                                       // unit u = (kc, ct_begin + ctl), walked incrementally
+        for (int u = grp; u < units; u += GROUPS, ctl += GROUPS) {
+            while (ctl >= nct) { ctl -= nct; ++kc; }
             const int set = u & 1;
-            const int col0 = (ct_begin + ctl) * OZ_BN + cpair;
             const bool first = kc == 0, last = kc == nkc - 1;
-            // operands that come from global memory are requested before the wait on the tensor core
-            double2 add[4]; int rsh[4];                              // rsh: high word of the row scale 2^(e-12)
+            int rsh[4];                                              // rsh: high word of the row scale 2^(e-12)
             const int* rsp = reinterpret_cast<const int*>(kc == 0 ? p.rowscale[0] : p.rowscale[1]) + 1 + 2 * rbase;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rsh[i] = (FULL || rbase + 8 * i < p.R) ? rsp[16 * i] : 0;
+#pragma unroll
+          for (int pz = 0; pz < PASSES; ++pz) {
+            const int cg = cg0 + pz;
+            const int col0 = (ct_begin + ctl) * OZ_BN + cg * 8 + (lane & 3) * 2;
+            // operands that come from global memory are requested before the wait on the tensor core
+            double2 add[4];
             const double2 bias2 = *reinterpret_cast<const double2*>(s_bias + col0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 add[i] = one_chunk ? bias2 : make_double2(0.0, 0.0);
-                rsh[i] = 0;
                 if (FULL || rbase + 8 * i < p.R) {
-                    rsh[i] = rsp[16 * i];
                     if (EPI == EPI_PLAIN) {
                         if (!first) add[i] = *reinterpret_cast<const double2*>(p.Y + (yrow + i * ystep + col0));
                         else if (res_first) {
@@ -313,10 +322,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                     }
                 }
             }
-            if (DBG > 1) tr.mark(7000 + u);
-            mbar_wait(&tm_full[set], (unsigned)((u / 2) & 1));
-            if (DBG > 1) tr.mark(8000 + u);
-            asm volatile("tcgen05.fence::after_thread_sync;");
+            if (pz == 0) {
+                if (DBG > 1) tr.mark(7000 + u);
+                mbar_wait(&tm_full[set], (unsigned)((u / 2) & 1));
+                if (DBG > 1) tr.mark(8000 + u);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+            }
             // m[g][half * 4 + (row & 8 ? 2 : 0) + column]: group g of the diagonals merged exactly in int32
             // (|acc_dd| <= (dd+1) * 128 * 64 * 64 < 2^23, so acc_dd * 128 + acc_dd+1 < 2^31)
             int m[G][8];
@@ -350,10 +361,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             };
             fetch_groups(G - 2 > 0 ? G - 2 : 0, G);                   // the two least significant groups
             if (G > 2) fetch_groups(0, G - 2);
-            // all TMEM reads of this set are complete: hand it back to the tensor core
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            mbar_arrive(&tm_empty[set]);
-            if (DBG > 1) tr.mark(9000 + u);
+            if (pz == PASSES - 1) {
+                // all TMEM reads of this set are complete: hand it back to the tensor core
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                mbar_arrive(&tm_empty[set]);
+                if (DBG > 1) tr.mark(9000 + u);
+            }
             // Horner over the groups in float64; int32 -> float64 with the 2^52 magic constant (integer ALU + one DADD
             // instead of a quarter-rate I2F.F64)
             auto to_f64 = [&](int v) {
@@ -404,6 +417,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 }
                 *reinterpret_cast<double2*>(p.Y + (yrow + i * ystep + col0)) = y;
             }
+          }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -442,13 +456,22 @@ cudaError_t launch_slice_rows(const double* A0, int ld0, int K0, const double* A
     return e;
 }
 
+template <int S, int EPI, int DBG, bool FULL, int GROUPS>
+static cudaError_t ozaki_gemm_tg(const OzParams& p, dim3 grid, cudaStream_t st) {
+    const size_t smem = (size_t)S * (OZ_XTILE + OZ_WSTAGES * OZ_WTILE);
+    cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel<S, EPI, DBG, FULL, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ozaki_gemm_kernel<S, EPI, DBG, FULL, GROUPS><<<grid, OZ_THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
 template <int S, int EPI, int DBG, bool FULL>
 static cudaError_t ozaki_gemm_tf(const OzParams& p, dim3 grid, cudaStream_t st) {
-    const size_t smem = (size_t)S * (OZ_XTILE + OZ_WSTAGES * OZ_WTILE);
-    cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel<S, EPI, DBG, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    ozaki_gemm_kernel<S, EPI, DBG, FULL><<<grid, OZ_THREADS, smem, st>>>(p);
-    return cudaGetLastError();
+    // MDGAT_OZ_GROUPS=1|2 (read once): epilogue organisation, see the kernel
+    static const int groups = [] { const char* e = getenv("MDGAT_OZ_GROUPS"); return e && e[0] == '1' ? 1 : 2; }();
+    // two groups need the k chunks of a column tile in the same group (the partial sum is read back by the thread
+    // that wrote it): one chunk, or an even number of column tiles per CTA
+    const bool ok2 = p.K == OZ_KC || (p.col_tiles_per_cta % 2) == 0;
+    return groups == 2 && ok2 ? ozaki_gemm_tg<S, EPI, DBG, FULL, 2>(p, grid, st) : ozaki_gemm_tg<S, EPI, DBG, FULL, 1>(p, grid, st);
 }
 template <int S, int EPI, int DBG>
 static cudaError_t ozaki_gemm_te(const OzParams& p, dim3 grid, cudaStream_t st) {
@@ -459,7 +482,7 @@ template <int S>
 static cudaError_t ozaki_gemm_t(const OzParams& p, dim3 grid, cudaStream_t st) {
     // timeline probes / debug switches live in their own instantiations: 1 = loader + MMA thread only (the epilogue
     // is the production code), 2 = epilogue probes and switches too (costs registers there)
-    if (p.dbg != 0) return p.epi == EPI_QKV ? ozaki_gemm_te<S, EPI_QKV, 2>(p, grid, st) : ozaki_gemm_te<S, EPI_PLAIN, 2>(p, grid, st);
+    if ((p.dbg & 255) != 0) return p.epi == EPI_QKV ? ozaki_gemm_te<S, EPI_QKV, 2>(p, grid, st) : ozaki_gemm_te<S, EPI_PLAIN, 2>(p, grid, st);
     if (p.trace != nullptr) return p.epi == EPI_QKV ? ozaki_gemm_te<S, EPI_QKV, 1>(p, grid, st) : ozaki_gemm_te<S, EPI_PLAIN, 1>(p, grid, st);
     return p.epi == EPI_QKV ? ozaki_gemm_te<S, EPI_QKV, 0>(p, grid, st) : ozaki_gemm_te<S, EPI_PLAIN, 0>(p, grid, st);
 }

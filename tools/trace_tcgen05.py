@@ -87,7 +87,11 @@ def main():
     run('plain K=128 N=384 (q/k/v shape)', lambda: ops.linear_i8(x, wqkv))
     run('MLP 256->256 relu (cat[x, msg])', lambda: ops.linear_i8(x, w1, bias=b1, relu=True, x2=m))
     run('MLP 256->128 + residual', lambda: ops.linear_i8(h, w2, residual=x))
-    for flags in (4, 5, 6, 7):
+    # bits 8..13 switch off the loader / MMA-thread marks 1000..6000: fewer probes, less perturbation
+    only6000 = (1 + 2 + 4 + 8 + 16) << 8
+    for flags in (only6000, only6000 + 1, only6000 + 2, only6000 + 3):
+        run('plain K=128 N=384', lambda: ops.linear_i8(x, wqkv), flags, True)
+    for flags in ():
         run('plain K=128 N=384', lambda: ops.linear_i8(x, wqkv), flags, False)
         run('MLP 256->256 relu', lambda: ops.linear_i8(x, w1, bias=b1, relu=True, x2=m), flags, False)
 

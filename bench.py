@@ -297,12 +297,39 @@ def main():
     per_step = {s: v['ms'] / args.steps for s, v in stages.items()}
     dominant = max(('gemm', 'attn_full'), key=lambda s: per_step[s])
     seg = stages[dominant]
-    achieved = stage_flops[dominant] / (per_step[dominant] * 1e-3) / 1e12
-    roofline = {
-        'bound': 'tensor', 'kernel': {'gemm': 'gemm_f64_kernel (DMMA.8x8x4)', 'attn_full': 'attn_full_kernel (DMMA.8x8x4)'}[dominant],
-        'achieved': achieved, 'peak': dmma_peak, 'unit': 'TFLOP/s', 'frac': achieved / dmma_peak, 'traffic': None,
-        'peak_source': 'fp64 DMMA issue-loop microbenchmark run in this process (MEASURED_PEAKS.json has no fp64 entry; '
-                       'the path computes in float64 for parity, tcgen05 has no f64 kind)',
+    i8 = {'gemm': args.gemm == 'tcgen05_i8', 'attn_full': args.attention == 'tcgen05_i8'}[dominant]
+    fp64_equiv = stage_flops[dominant] / (per_step[dominant] * 1e-3) / 1e12
+    if i8:
+        # The dominant kernel runs on the int8 tensor pipe: its algorithmic work is the exact digit-plane products
+        # (DESIGN.md 4.1 / 4.3), 2 operations per int8 multiply-add; the ceiling is the kind::i8 issue rate measured
+        # in this process. The float64 FLOPs those products stand for are reported next to it.
+        S = 7
+        R = B * 2 * N
+        i8_ops = {'gemm': 2 * L * (S * (S + 1) // 2) * 2.0 * R * (384 * 128 + 256 * 256 + 128 * 256),
+               'attn_full': (2 * L - n_topk) * (28 + 3 + 27) * 2.0 * N * N * 32 * 4 * 2 * B}[dominant]
+        i8_peak = ops.measure_i8_peak()
+        achieved = i8_ops / (per_step[dominant] * 1e-3) / 1e12
+        roofline = {
+            'bound': 'tensor',
+            'kernel': {'gemm': 'ozaki_gemm_kernel (tcgen05.mma.kind::i8, 28 exact digit-plane products per float64 GEMM)',
+                       'attn_full': 'attn_i8_kernel (tcgen05.mma.kind::i8, 58 exact digit-plane products per float64 Q K^T + P V)'}[dominant],
+            'achieved': achieved, 'peak': i8_peak, 'unit': 'TFLOP/s', 'frac': achieved / i8_peak, 'traffic': None,
+            'op_kind': 'int8 tensor operations (2 per multiply-add) of the digit-plane products issued per step',
+            'peak_source': 'tcgen05.mma kind::i8 issue-rate microbenchmark run in this process (128x256x32 MMAs from shared memory); '
+                           'MEASURED_PEAKS.json carries HBM and bf16 figures only',
+            'fp64_equivalent': {'achieved_tflops': fp64_equiv, 'fp64_dmma_peak_tflops': dmma_peak, 'ratio_to_fp64_pipe': fp64_equiv / dmma_peak,
+                                'note': 'algorithmic float64 FLOPs of the stage (SURVEY 8d) over its device time, against the DMMA ceiling '
+                                        'the reference arithmetic would be bound by'},
+            'algorithmic_ops_per_step': i8_ops,
+        }
+    else:
+        roofline = {
+            'bound': 'tensor', 'kernel': {'gemm': 'gemm_f64_kernel (DMMA.8x8x4)', 'attn_full': 'attn_full_kernel (DMMA.8x8x4)'}[dominant],
+            'achieved': fp64_equiv, 'peak': dmma_peak, 'unit': 'TFLOP/s', 'frac': fp64_equiv / dmma_peak, 'traffic': None,
+            'peak_source': 'fp64 DMMA issue-loop microbenchmark run in this process (MEASURED_PEAKS.json has no fp64 entry; '
+                           'the path computes in float64 for parity, tcgen05 has no f64 kind)',
+        }
+    roofline.update({
         'dfma_peak_tflops': dfma_peak,
         'launches_per_step': seg['launches'] / args.steps,
         'avg_launch_ms': seg['ms'] / max(seg['launches'], 1),
@@ -310,8 +337,8 @@ def main():
         'measured_peaks_file': measured,
         'stage_ms_per_step': per_step,
         'stage_share': {s: per_step[s] / max(sum(per_step.values()), 1e-9) for s in per_step},
-        'all_fp64_tflops': (lin_f + attn_f) * B / ((per_step['gemm'] + per_step['attn_full'] + per_step['attn_topk']) * 1e-3) / 1e12,
-    }
+        'all_fp64_tflops': (lin_f + attn_f) * B / ((per_step['gemm'] + per_step['attn_full'] + per_step['attn_topk'] + per_step.get('slice', 0.0)) * 1e-3) / 1e12,
+    })
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:

@@ -216,6 +216,9 @@ int mdgat_measure_fp64_peak(double* tflops_dmma, double* tflops_dfma);
  * tflops_dfma must have room for 2 doubles: [1] receives the DMMA rate of a register-tiled 4x4
  * outer-product loop at 16 warps/SM (the GEMM inner loop without its memory traffic). */
 int mdgat_measure_fp64_mixed(double* tflops_dmma, double* tflops_dfma);
+/* Issue-rate ceiling of tcgen05.mma kind::i8 on this device: one CTA per SM issues 128x256x32 MMAs on operands
+ * resident in shared memory; result in int8 tera-operations (2 per multiply-add) per second. */
+int mdgat_measure_i8_peak(double* tops);
 
 /* ---- instrumentation (no reference counterpart; the reference has no tracing) ----
  * mdgat_launch_count: kernels launched by this library since load.
@@ -229,7 +232,8 @@ int mdgat_measure_fp64_mixed(double* tflops_dmma, double* tflops_dfma);
 #define MDGAT_STAGE_ATTN_TOPK 3   /* logits GEMM + selection/softmax/sparse PV */
 #define MDGAT_STAGE_SINKHORN 4
 #define MDGAT_STAGE_MATCH 5
-#define MDGAT_STAGE_COUNT 6
+#define MDGAT_STAGE_SLICE 6       /* digit-plane slicers of the tcgen05 engines */
+#define MDGAT_STAGE_COUNT 7
 long long mdgat_launch_count(void);
 /* Debug timeline: d_buf = NULL (default, off) or a zeroed device buffer of 8 roles x (2 + 2*1024) int64. While set, CTA
  * (0,0,0) of the tcgen05 kernels records (tag, clock64) pairs per role (loader, MMA issuer, two epilogue warps):

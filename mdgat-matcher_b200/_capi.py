@@ -72,6 +72,7 @@ def _load():
         'mdgat_register_pairs': (i, [vp, vp, i, vp, vp, vp, i, i, i, vp, vp, vp]),
         'mdgat_measure_fp64_peak': (i, [C.POINTER(d), C.POINTER(d)]),
         'mdgat_measure_fp64_mixed': (i, [C.POINTER(d), C.POINTER(d)]),
+        'mdgat_measure_i8_peak': (i, [C.POINTER(d)]),
         'mdgat_launch_count': (ll, []),
         'mdgat_debug_trace': (i, [vp]),
         'mdgat_debug_flags': (i, [i]),
@@ -88,7 +89,7 @@ def _load():
 lib, EXPORTS = _load()
 
 
-STAGES = ('encode', 'gemm', 'attn_full', 'attn_topk', 'sinkhorn', 'match')
+STAGES = ('encode', 'gemm', 'attn_full', 'attn_topk', 'sinkhorn', 'match', 'slice')
 
 
 def profile_collect():

@@ -251,32 +251,62 @@ struct __align__(16) KeptEntry { double p; int col; int pad; };
 
 // VPT = values per lane (M <= 32*VPT). Dynamic shared memory: per warp `topk` KeptEntry
 // (kept logit -> probability, column), then the 64-entry exp table.
-template <int VPT>
-__global__ void __launch_bounds__(32 * TK_WARPS, VPT == 16 ? 3 : 1)
+//
+// SMEM_V = false: one warp per row, 8 rows per CTA; the sparse P.V gathers its k value rows from global memory
+//                 (L2): 32 KB per query row, 2.1 GB per side at cfg2 -- the L2 read bandwidth is the bound.
+// SMEM_V = true : one CTA (16 warps) per (b, h); the whole value matrix of the head (M x 34 doubles, 136 KB at
+//                 M = 512) is brought in by ONE TMA bulk copy and every warp walks query rows i = warp, warp + 16, ..
+//                 gathering from shared memory. The logits row of the next query is requested before the P.V of
+//                 the current one. L2 traffic for V drops from 2.1 GB to 18 MB per side; the bound becomes the
+//                 shared-memory read of k x 256 B per row.
+constexpr int TKS_WARPS = 24;
+template <int VPT, bool SMEM_V>
+__global__ void __launch_bounds__(SMEM_V ? 32 * TKS_WARPS : 32 * TK_WARPS, (SMEM_V || VPT != 16) ? 1 : 3)
 topk_softmax_pv_kernel(const double* __restrict__ S, const double* __restrict__ V, double* __restrict__ Out,
                        int ldo, int N, int M, int topk, long long total_rows) {
     extern __shared__ __align__(16) unsigned char tk_smem[];
+    constexpr int WARPS = SMEM_V ? TKS_WARPS : TK_WARPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     KeptEntry* kept = reinterpret_cast<KeptEntry*>(tk_smem) + (size_t)warp * topk;
-    double* etab = reinterpret_cast<double*>(tk_smem + (size_t)TK_WARPS * topk * sizeof(KeptEntry));
+    double* etab = reinterpret_cast<double*>(tk_smem + (size_t)WARPS * topk * sizeof(KeptEntry));
+    double* sV = etab + 64;                                               // SMEM_V: [M][LDH_V]
+    __shared__ __align__(8) uint64_t v_bar;
     exp_table_to_shared(etab);
-    __syncthreads();
-    const long long g = (long long)blockIdx.x * TK_WARPS + warp;          // row in (B,4,N) order
-    if (g >= total_rows) return;
-    const long long bh = g / N;
-    const int i = (int)(g - bh * N);
+    long long bh; int i;
+    if (SMEM_V) {
+        bh = blockIdx.x; i = warp;
+        if (threadIdx.x == 0) { mbar_init(&v_bar, 1); mbar_fence_init(); }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned bytes = (unsigned)((size_t)M * LDH_V * sizeof(double));
+            mbar_expect_tx(&v_bar, bytes);
+            bulk_g2s(sV, V + bh * (long long)M * LDH_V, bytes, &v_bar);
+        }
+    } else {
+        __syncthreads();
+        const long long g0 = (long long)blockIdx.x * TK_WARPS + warp;      // row in (B,4,N) order
+        if (g0 >= total_rows) return;
+        bh = g0 / N;
+        i = (int)(g0 - bh * N);
+    }
     const int b = (int)(bh / HEADS), h = (int)(bh - (long long)b * HEADS);
-    const double* srow = S + g * (long long)M;
-    const double* Vbh = V + bh * (long long)M * LDH_V;
-
+    const double* Vbh = SMEM_V ? sV : V + bh * (long long)M * LDH_V;
+    auto load_row = [&](int row, double (&dst)[VPT]) {
+        const double* srow = S + (bh * N + row) * (long long)M;
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+            const int j = lane + 32 * v;
+            dst[v] = j < M ? srow[j] : -INFINITY;          // padding never passes a ">= finite" test
+        }
+    };
     double s[VPT];
+    if (i < N) load_row(i, s);
+    bool v_ready = !SMEM_V;
+  for (; i < N; i += WARPS) {
     double mx = -INFINITY, mn = INFINITY;
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
-        const int j = lane + 32 * v;
-        const bool ok = j < M;
-        s[v] = ok ? srow[j] : -INFINITY;                  // padding never passes a ">= finite" test
-        if (ok) { mx = fmax(mx, s[v]); mn = fmin(mn, s[v]); }
+        if (lane + 32 * v < M) { mx = fmax(mx, s[v]); mn = fmin(mn, s[v]); }
     }
     mx = warp_max_d(mx);
     mn = -warp_max_d(-mn);
@@ -285,16 +315,24 @@ topk_softmax_pv_kernel(const double* __restrict__ S, const double* __restrict__ 
     double thr = mn;
     bool exact = topk >= M;
     if (!exact) {
+        // bracket [lo, hi] with count(>= lo) = clo > k > chi = count(>= hi) (chi taken as 1 at the maximum); even steps
+        // place the probe by linear interpolation of the counts (3-4 probes on smooth rows), odd steps bisect, so the
+        // bracket at least halves every two probes
         double lo = mn, hi = mx;
-        for (int step = 0; step < 48; ++step) {
-            const double mid = lo + 0.5 * (hi - lo);
+        int clo = M, chi = 1;
+        for (int step = 0; step < 96; ++step) {
+            double mid = lo + 0.5 * (hi - lo);
             if (!(mid > lo && mid < hi)) break;           // interval collapsed: ties or adjacent doubles
+            if ((step & 1) == 0) {
+                const double guess = lo + (hi - lo) * ((double)(clo - topk) / (double)(clo - chi));
+                if (guess > lo && guess < hi) mid = guess;
+            }
             int c = 0;
 #pragma unroll
             for (int v = 0; v < VPT; ++v) c += (s[v] >= mid) ? 1 : 0;
             c = __reduce_add_sync(0xffffffffu, c);
             if (c == topk) { thr = mid; exact = true; break; }
-            if (c > topk) lo = mid; else hi = mid;
+            if (c > topk) { lo = mid; clo = c; } else { hi = mid; chi = c; }
         }
     }
     unsigned long long sel = 0ull;                        // bit v: keep s[v]
@@ -360,6 +398,8 @@ topk_softmax_pv_kernel(const double* __restrict__ S, const double* __restrict__ 
         base += __popc(tm);
     }
     __syncwarp();
+    // the logits of this warp's next row travel while the P.V below runs
+    if (SMEM_V && i + WARPS < N) load_row(i + WARPS, s);
     // softmax over the kept k (mdgat.py:206-207); the row maximum is always among them
     double sum = 0.0;
     for (int t = lane; t < topk; t += 32) {
@@ -369,29 +409,56 @@ topk_softmax_pv_kernel(const double* __restrict__ S, const double* __restrict__ 
     }
     sum = warp_sum_d(sum);
     __syncwarp();
-    // sparse P.V: lane = channel d of this head; only k of the M value rows are read
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    const double* vl = Vbh + lane;
-    int t = 0;
-    for (; t + 4 <= topk; t += 4) {
-        const KeptEntry e0 = kept[t], e1 = kept[t + 1], e2 = kept[t + 2], e3 = kept[t + 3];
-        a0 = fma(e0.p, __ldg(vl + e0.col * LDH_V), a0);
-        a1 = fma(e1.p, __ldg(vl + e1.col * LDH_V), a1);
-        a2 = fma(e2.p, __ldg(vl + e2.col * LDH_V), a2);
-        a3 = fma(e3.p, __ldg(vl + e3.col * LDH_V), a3);
+    if (!v_ready) { mbar_wait(&v_bar, 0); v_ready = true; }
+    // sparse P.V: only k of the M value rows are read. The two half-warps take the kept entries of even / odd position,
+    // a lane the channel pair (2 l, 2 l + 1): one 16-byte read of the entry and one of the value row per two FMAs
+    // (half the instructions of the lane-per-channel form); the halves are combined with two shuffles.
+    const int hw = lane >> 4;
+    const double* vl = Vbh + 2 * (lane & 15);
+    auto vload = [&](int col) -> double2 {
+        const double2* q = reinterpret_cast<const double2*>(vl + col * LDH_V);
+        return SMEM_V ? *q : __ldg(q);
+    };
+    double2 a0 = make_double2(0.0, 0.0), a1 = a0;
+    int t = hw;
+    for (; t + 2 < topk; t += 4) {
+        const KeptEntry e0 = kept[t], e1 = kept[t + 2];
+        const double2 v0 = vload(e0.col), v1 = vload(e1.col);
+        a0.x = fma(e0.p, v0.x, a0.x); a0.y = fma(e0.p, v0.y, a0.y);
+        a1.x = fma(e1.p, v1.x, a1.x); a1.y = fma(e1.p, v1.y, a1.y);
     }
-    for (; t < topk; ++t) a0 = fma(kept[t].p, __ldg(vl + kept[t].col * LDH_V), a0);
-    Out[((long long)b * N + i) * ldo + h * HDIM + lane] = ((a0 + a1) + (a2 + a3)) / sum;
+    if (t < topk) {
+        const KeptEntry e0 = kept[t];
+        const double2 v0 = vload(e0.col);
+        a0.x = fma(e0.p, v0.x, a0.x); a0.y = fma(e0.p, v0.y, a0.y);
+    }
+    a0.x += a1.x; a0.y += a1.y;
+    a0.x += shfl_xor_d(a0.x, 16); a0.y += shfl_xor_d(a0.y, 16);
+    if (hw == 0)
+        *reinterpret_cast<double2*>(Out + ((long long)b * N + i) * ldo + h * HDIM + 2 * lane) = make_double2(a0.x / sum, a0.y / sum);
+    __syncwarp();                                        // kept[] is rewritten by the next row
+    if (!SMEM_V) break;
+  }
 }
 
 template <int VPT>
 static cudaError_t launch_topk_t(const double* S, const double* V, double* Out, int ldo, int N, int M, int topk,
                                  long long rows, cudaStream_t st) {
+    // value matrix of a head resident in shared memory when it fits next to the kept lists (M = 512, k = 128: 169 KB)
+    const size_t smem_v = (size_t)TKS_WARPS * topk * sizeof(KeptEntry) + 64 * sizeof(double) + (size_t)M * LDH_V * sizeof(double);
+    if constexpr (VPT == 16) {
+        if (smem_v <= 200 * 1024 && N >= TKS_WARPS) {
+            cudaError_t e = cudaFuncSetAttribute(topk_softmax_pv_kernel<VPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v);
+            if (e != cudaSuccess) return e;
+            topk_softmax_pv_kernel<VPT, true><<<(unsigned)(rows / N), 32 * TKS_WARPS, smem_v, st>>>(S, V, Out, ldo, N, M, topk, rows);
+            return cudaSuccess;
+        }
+    }
     const size_t smem = (size_t)TK_WARPS * topk * sizeof(KeptEntry) + 64 * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(topk_softmax_pv_kernel<VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(topk_softmax_pv_kernel<VPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((rows + TK_WARPS - 1) / TK_WARPS);
-    topk_softmax_pv_kernel<VPT><<<grid, 32 * TK_WARPS, smem, st>>>(S, V, Out, ldo, N, M, topk, rows);
+    topk_softmax_pv_kernel<VPT, false><<<grid, 32 * TK_WARPS, smem, st>>>(S, V, Out, ldo, N, M, topk, rows);
     return cudaSuccess;
 }
 

@@ -27,7 +27,7 @@ using namespace mdgat;
 
 // ---- launch counter and per-stage device timers (CUDA events on the caller's stream) ----
 namespace {
-enum { ST_ENCODE = 0, ST_GEMM, ST_ATTN_FULL, ST_ATTN_TOPK, ST_SINKHORN, ST_MATCH, ST_COUNT };
+enum { ST_ENCODE = 0, ST_GEMM, ST_ATTN_FULL, ST_ATTN_TOPK, ST_SINKHORN, ST_MATCH, ST_SLICE, ST_COUNT };
 struct Profiler {
     bool on = false;
     std::vector<cudaEvent_t> ev;       // ev[i] opens segment i; the last event closes the last segment
@@ -283,9 +283,10 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
         const size_t slice_tile = (size_t)S8 * 32 * 128;                // bytes of one (column tile, k chunk) of W slices
         const unsigned char* Li8 = i8 ? reinterpret_cast<const unsigned char*>(d_weights_i8) + (size_t)l * (slice_tile * 36 + 1152 * 8) : nullptr;
         const double* cs8 = i8 ? reinterpret_cast<const double*>(Li8 + slice_tile * 36) : nullptr;
-        prof_mark(ST_GEMM, st);
+        prof_mark(i8 ? ST_SLICE : ST_GEMM, st);
         if (i8) {
             MDGAT_CUDA_OK(launch_slice_rows(w.X, LDX, DMODEL, nullptr, 0, 0, R, S8, w.xsX, w.rsX, st));
+            prof_mark(ST_GEMM, st);
             OzGemmArgs a;
             memset(&a, 0, sizeof(a));
             a.Xs[0] = w.xsX; a.rowscale[0] = w.rsX; a.Ws = reinterpret_cast<const int8_t*>(Li8); a.colscale = cs8;
@@ -300,7 +301,7 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
             p.Qh = w.Qh; p.Kh = w.Kh; p.Vh = w.Vh; p.rows0 = R0; p.n0 = N; p.n1 = M;
             MDGAT_CUDA_OK(launch_gemm(p, EPI_QKV, 1, st));
         }
-        prof_mark(k > 0 ? ST_ATTN_TOPK : ST_ATTN_FULL, st);
+        prof_mark(ai8 ? ST_SLICE : (k > 0 ? ST_ATTN_TOPK : ST_ATTN_FULL), st);
         // messages: side 0 reads side (cross ? 1 : 0), side 1 the other way round (mdgat.py:263-266)
         AttnSides ps;
         ps.Q[0] = Q0; ps.K[0] = cross ? K1 : K0; ps.V[0] = cross ? V1 : V0; ps.Out[0] = w.Msg; ps.N[0] = N; ps.M[0] = cross ? M : N;
@@ -310,13 +311,14 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
             // of side s (self) or 1 - s (cross)
             MDGAT_CUDA_OK(launch_attn_i8_slice(Q0, K0, V0, w.ai[0], B, st));
             MDGAT_CUDA_OK(launch_attn_i8_slice(Q1, K1, V1, w.ai[1], B, st));
+            prof_mark(k > 0 ? ST_ATTN_TOPK : ST_ATTN_FULL, st);
             const AttnI8Side qd[2] = {w.ai[0], w.ai[1]};
             const AttnI8Side kvd[2] = {cross ? w.ai[1] : w.ai[0], cross ? w.ai[0] : w.ai[1]};
             MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st, qd, kvd));
         } else {
             MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st));
         }
-        prof_mark(ST_GEMM, st);
+        prof_mark(i8 ? ST_SLICE : ST_GEMM, st);
         // the merge conv (mdgat.py:237) is folded into the first MLP conv by the weight packer
         // mlp(cat[x, message]) : 256 -> 256 (BN folded, ReLU) -> 128, then the residual (mdgat.py:248, :274)
         if (i8) {
@@ -324,10 +326,13 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
             memset(&a, 0, sizeof(a));
             // k chunk 0 = x (its slice planes are the ones the q/k/v projection used), k chunk 1 = message
             MDGAT_CUDA_OK(launch_slice_rows(w.Msg, LDX, DMODEL, nullptr, 0, 0, R, S8, w.xsM, w.rsM, st));
+            prof_mark(ST_GEMM, st);
             a.Xs[0] = w.xsX; a.rowscale[0] = w.rsX; a.Xs[1] = w.xsM; a.rowscale[1] = w.rsM; a.Ws = reinterpret_cast<const int8_t*>(Li8 + slice_tile * 12); a.colscale = cs8 + 384;
             a.bias = Wt + lo.b1; a.Y = w.Hd; a.ldy = LDHID; a.R = R; a.Nout = 2 * DMODEL; a.K = 2 * DMODEL; a.relu = 1; a.epi = EPI_PLAIN;
             MDGAT_CUDA_OK(launch_ozaki_gemm(a, S8, st));
+            prof_mark(ST_SLICE, st);
             MDGAT_CUDA_OK(launch_slice_rows(w.Hd, LDHID, 2 * DMODEL, nullptr, 0, 0, R, S8, w.xsH, w.rsH, st));
+            prof_mark(ST_GEMM, st);
             a.Xs[0] = w.xsH; a.rowscale[0] = w.rsH; a.Xs[1] = w.xsH + ozaki_slices_bytes(R, 128, S8); a.rowscale[1] = w.rsH + (size_t)((R + 127) / 128 * 128);
             a.Ws = reinterpret_cast<const int8_t*>(Li8 + slice_tile * 28); a.colscale = cs8 + 896;
             a.bias = Wt + lo.b2; a.Res = w.X; a.ldres = LDX; a.Y = w.X; a.ldy = LDX; a.Nout = DMODEL; a.relu = 0;
@@ -337,6 +342,7 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
             MDGAT_CUDA_OK(linear(w.Hd, LDHID, 2 * DMODEL, nullptr, 0, 0, Wt + lo.w2, 2 * DMODEL, Wt + lo.b2, w.X, LDX, w.X, LDX, R, DMODEL, 1.0, 0, st));
         }
     }
+    prof_mark(ST_GEMM, st);
     // final_proj (mdgat.py:397) and scores = mdesc0^T mdesc1 / sqrt(128) (:430-431) into the couplings
     MDGAT_CUDA_OK(linear(w.X, LDX, DMODEL, nullptr, 0, 0, Wt + lay.wf, DMODEL, Wt + lay.bf, nullptr, 0, w.MD, LDX, R, DMODEL, 1.0, 0, st));
     MDGAT_CUDA_OK(gemm_nt(w.MD, LDX, (long long)N * LDX, w.MD + (size_t)R0 * LDX, LDX, (long long)M * LDX,
@@ -544,6 +550,11 @@ int mdgat_register_pairs(const void* d_kpts0, const void* d_kpts1, int kp_dtype,
 int mdgat_measure_fp64_mixed(double* tflops_dmma, double* tflops_dfma) {
     MDGAT_CUDA_OK(measure_fp64_mixed(tflops_dmma, tflops_dfma));
     MDGAT_CUDA_OK(measure_dmma_tiled(tflops_dfma + 1));
+    return MDGAT_OK;
+}
+
+int mdgat_measure_i8_peak(double* tops) {
+    MDGAT_CUDA_OK(measure_i8_peak(tops));
     return MDGAT_OK;
 }
 

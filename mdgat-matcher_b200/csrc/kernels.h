@@ -86,6 +86,7 @@ size_t ozaki_slices_bytes(int R, int K, int S);
 cudaError_t launch_slice_rows(const double* A0, int ld0, int K0, const double* A1, int ld1, int K1, int R, int S,
                               int8_t* Xs, double* rowscale, cudaStream_t st);
 cudaError_t launch_ozaki_gemm(const OzGemmArgs& a, int S, cudaStream_t st);
+cudaError_t measure_i8_peak(double* tops);
 
 // float64-faithful attention on tcgen05 int8 tensor cores (digit planes of q/k/v, exact int32 accumulation in
 // TMEM), see attention_i8.cu. One AttnI8Side holds the digit planes of ONE side's q, k and v head vectors.

@@ -85,9 +85,13 @@ slice_rows_kernel(const double* __restrict__ A0, int ld0, int K0, const double* 
         uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            const double d = rint(x[i]);
+            // rint() and the double -> int conversion both run on the quarter-rate conversion pipe; adding 1.5 * 2^52
+            // rounds to the nearest integer (ties to even, like rint) on the FP64 pipe and leaves the integer in the
+            // low mantissa word
+            const double m = x[i] + 6755399441055744.0;
+            const double d = m - 6755399441055744.0;
             x[i] = (x[i] - d) * 128.0;
-            w[i >> 2] |= (uint32_t)(uint8_t)(int8_t)(int)d << (8 * (i & 3));
+            w[i >> 2] |= ((uint32_t)__double2loint(m) & 0xffu) << (8 * (i & 3));
         }
         *reinterpret_cast<uint4*>(base + (size_t)s * OZ_XTILE) = make_uint4(w[0], w[1], w[2], w[3]);
     }
@@ -423,6 +427,69 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (warp == OZ_EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Issue-rate ceiling of kind::i8 (roofline denominator of the tcgen05 engines, measured live by bench.py): one CTA
+// per SM, one thread issues 128x256x32 MMAs back to back on operands resident in shared memory.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) i8_peak_kernel(int iters) {
+    extern __shared__ __align__(128) unsigned char pk_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (128 + 256) * 128 / 4; i += 128) reinterpret_cast<uint32_t*>(pk_smem)[i] = 0x01010101u * (i & 3);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_s);
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(dst));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t da0 = umma_desc(pk_smem, 128, 1024), db0 = umma_desc(pk_smem + 16384, 128, 1024);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int kk = j & 3;
+                umma_i8<true>(tmem, da0 + (uint64_t)((kk * 256) >> 4), db0 + (uint64_t)((kk * 256) >> 4), idesc);
+            }
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem));
+}
+
+cudaError_t measure_i8_peak(double* tops) {
+    int dev = 0, sms = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    const size_t smem = (128 + 256) * 128;
+    if ((e = cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    const int iters = 2000;
+    float ms = 0.f;
+    for (int rep = 0; rep < 2; ++rep) {         // first rep warms up
+        cudaEventRecord(t0);
+        i8_peak_kernel<<<sms, 128, smem>>>(iters);
+        cudaEventRecord(t1);
+        if ((e = cudaEventSynchronize(t1)) != cudaSuccess) break;
+        cudaEventElapsedTime(&ms, t0, t1);
+    }
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    if (e != cudaSuccess) return e;
+    *tops = (double)sms * iters * 16.0 * 2.0 * 128 * 256 * 32 / (ms * 1e-3) / 1e12;
+    return cudaGetLastError();
 }
 
 size_t ozaki_slices_bytes(int R, int K, int S) {

@@ -195,6 +195,13 @@ def measure_fp64_peak():
     return a.value, b.value
 
 
+def measure_i8_peak():
+    """Issue-rate ceiling of tcgen05.mma kind::i8 in TOP/s (2 operations per multiply-add)."""
+    a = ctypes.c_double()
+    _capi.check(_capi.lib.mdgat_measure_i8_peak(ctypes.byref(a)))
+    return a.value
+
+
 def measure_fp64_mixed():
     """(DMMA TF/s in a DMMA+DFMA mix, DFMA TF/s in the mix, DMMA TF/s of a register-tiled 4x4 loop)."""
     a, b = ctypes.c_double(), (ctypes.c_double * 2)()

@@ -172,7 +172,7 @@ def main():
     ap.add_argument('--sinkhorn', type=int, default=100)
     ap.add_argument('--cpu-pairs', type=int, default=0, help='pairs in the CPU baseline sample (0 = auto)')
     ap.add_argument('--gemm', default='tcgen05_i8', choices=['tcgen05_i8', 'dmma'], help='engine of the per-layer projections')
-    ap.add_argument('--attention', default='tcgen05_i8', choices=['tcgen05_i8', 'dmma'], help='engine of Q K^T / P V')
+    ap.add_argument('--attention', default='tcgen05_i8', choices=['tcgen05_i8', 'tcgen05_i8_all', 'dmma'], help='engine of Q K^T / P V')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-eager', action='store_true', help='skip the eager-PyTorch fp64 GPU timing of the same math')
     args = ap.parse_args()
@@ -297,7 +297,7 @@ def main():
     per_step = {s: v['ms'] / args.steps for s, v in stages.items()}
     dominant = max(('gemm', 'attn_full'), key=lambda s: per_step[s])
     seg = stages[dominant]
-    i8 = {'gemm': args.gemm == 'tcgen05_i8', 'attn_full': args.attention == 'tcgen05_i8'}[dominant]
+    i8 = {'gemm': args.gemm == 'tcgen05_i8', 'attn_full': args.attention != 'dmma'}[dominant]
     fp64_equiv = stage_flops[dominant] / (per_step[dominant] * 1e-3) / 1e12
     if i8:
         # The dominant kernel runs on the int8 tensor pipe: its algorithmic work is the exact digit-plane products

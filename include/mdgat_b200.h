@@ -44,7 +44,9 @@ extern "C" {
 
 /* attention engines (full-softmax layers and the logits of the dynamic layers) */
 #define MDGAT_ATTN_DMMA_F64 0     /* flash attention on DMMA (FP64 pipe) */
-#define MDGAT_ATTN_TCGEN05_I8 1   /* float64-faithful digit products on tcgen05.mma kind::i8: Q K^T and P V in TMEM */
+#define MDGAT_ATTN_TCGEN05_I8 1   /* float64-faithful digit products on tcgen05.mma kind::i8: Q K^T and P V in TMEM (full-attention
+                                   * layers; the dense logits of the top-k layers come from the DMMA kernel, which is faster there) */
+#define MDGAT_ATTN_TCGEN05_I8_ALL 2   /* the same, top-k layers included */
 
 /* input element types */
 #define MDGAT_F32 0

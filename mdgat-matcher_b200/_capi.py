@@ -14,7 +14,7 @@ MATCH_DUSTBIN, MATCH_THRESHOLD = 0, 1
 LOSS_NONE, LOSS_TRIPLET = 0, 1
 F32, F64 = 0, 1
 GEMM_DMMA_F64, GEMM_TCGEN05_I8 = 0, 1
-ATTN_DMMA_F64, ATTN_TCGEN05_I8 = 0, 1
+ATTN_DMMA_F64, ATTN_TCGEN05_I8, ATTN_TCGEN05_I8_ALL = 0, 1, 2
 LDX = 132
 LDH_QK, LDH_V = 36, 34
 

@@ -164,25 +164,26 @@ slice_qk_kernel(const double* __restrict__ Qh, const double* __restrict__ Kh, At
 // channel. One CTA per (b, h); lane = channel. vscale[c] = 2^(e_c - 13): with p^ = p 2^47 and the digit
 // weights, message = vscale * Horner(P V diagonals) / (sum_j p^_j 2^-47).
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int SV_WARPS = 16;     // one CTA per (b, h) (128 CTAs at cfg2): 16 warps keep enough loads in flight per SM
+__global__ void __launch_bounds__(32 * SV_WARPS)
 slice_v_kernel(const double* __restrict__ Vh, AttnI8Side o) {
-    __shared__ double s_max[8][32];
+    __shared__ double s_max[SV_WARPS][32];
     const int n = o.n, npad = (n + AI_BN - 1) / AI_BN * AI_BN;
     const int bh = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double* V = Vh + (long long)bh * n * LDH_V;
     double mx = 0.0;
-    for (int j = warp; j < n; j += 8) mx = fmax(mx, fabs(V[(long long)j * LDH_V + lane]));
+    for (int j = warp; j < n; j += SV_WARPS) mx = fmax(mx, fabs(V[(long long)j * LDH_V + lane]));
     s_max[warp][lane] = mx;
     __syncthreads();
 #pragma unroll
-    for (int w = 0; w < 8; ++w) mx = fmax(mx, s_max[w][lane]);
+    for (int w = 0; w < SV_WARPS; ++w) mx = fmax(mx, s_max[w][lane]);
     int e = 0;
     if (mx > 0.0) frexp(mx, &e);
     e = max(-AI_EXP_LIMIT, min(AI_EXP_LIMIT, e));
     if (warp == 0) o.vscale[(size_t)bh * 32 + lane] = pow2i(e - 13);
     const double sc = pow2i(54 - e);
     // unit = 16 consecutive keypoints: 16 bytes per plane and channel
-    for (int unit = warp; unit < npad / 16; unit += 8) {
+    for (int unit = warp; unit < npad / 16; unit += SV_WARPS) {
         const int j0 = unit * 16;
         double x[16];
 #pragma unroll
@@ -545,7 +546,7 @@ cudaError_t launch_attn_i8_slice(const double* Qh, const double* Kh, const doubl
         count_launch();
     }
     if (Vh) {
-        slice_v_kernel<<<B * HEADS, 256, 0, st>>>(Vh, o);
+        slice_v_kernel<<<B * HEADS, 32 * SV_WARPS, 0, st>>>(Vh, o);
         count_launch();
     }
     return cudaGetLastError();

@@ -225,7 +225,7 @@ size_t mdgat_weight_blob_doubles(int L) { return BlobLayout(L).total; }
 size_t mdgat_forward_workspace_bytes(const mdgat_forward_cfg* cfg) {
     bool need = false;
     for (int i = 0; i < 2 * cfg->L; ++i) need = need || (cfg->layer_k && cfg->layer_k[i] > 0);
-    const bool ai = cfg->attn_mode == MDGAT_ATTN_TCGEN05_I8 && attn_i8_supported(cfg->N, cfg->M) && attn_i8_supported(cfg->M, cfg->N);
+    const bool ai = (cfg->attn_mode == MDGAT_ATTN_TCGEN05_I8 || cfg->attn_mode == MDGAT_ATTN_TCGEN05_I8_ALL) && attn_i8_supported(cfg->N, cfg->M) && attn_i8_supported(cfg->M, cfg->N);
     return carve(nullptr, cfg->B, cfg->N, cfg->M, need, cfg->gemm_mode == MDGAT_GEMM_TCGEN05_I8 ? cfg->gemm_slices : 0, ai).bytes;
 }
 
@@ -255,8 +255,8 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
     const bool i8 = cfg->gemm_mode == MDGAT_GEMM_TCGEN05_I8;
     const int S8 = cfg->gemm_slices;
     MDGAT_REQUIRE(!i8 || (d_weights_i8 != nullptr && S8 >= 6 && S8 <= 7), "tcgen05 int8 GEMM mode needs the sliced weight blob and 6 or 7 slices");
-    const bool ai8 = cfg->attn_mode == MDGAT_ATTN_TCGEN05_I8 && attn_i8_supported(N, M) && attn_i8_supported(M, N);
-    Workspace w = carve(reinterpret_cast<char*>(d_workspace), B, N, M, need, i8 ? S8 : 0, ai8);
+    const bool ai8_any = (cfg->attn_mode == MDGAT_ATTN_TCGEN05_I8 || cfg->attn_mode == MDGAT_ATTN_TCGEN05_I8_ALL) && attn_i8_supported(N, M) && attn_i8_supported(M, N);
+    Workspace w = carve(reinterpret_cast<char*>(d_workspace), B, N, M, need, i8 ? S8 : 0, ai8_any);
     if (w.bytes > workspace_bytes) {
         mdgat_host::set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
         return MDGAT_ERR_WORKSPACE;
@@ -277,6 +277,9 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
         const LayerOffsets lo = lay.layer(l);
         const bool cross = (l & 1) != 0;                  // names = ['self','cross']*L (mdgat.py:353)
         const int k = cfg->layer_k[l];
+        // top-k layers only need the dense logits: the DMMA flash pipeline produces them faster than the digit-plane
+        // route (no slicing pass, no Horner per logit) unless the caller asks for tcgen05 everywhere
+        const bool ai8 = ai8_any && (k <= 0 || cfg->attn_mode == MDGAT_ATTN_TCGEN05_I8_ALL);
         // q/k/v of both sides with the shared layer weights (mdgat.py:227-232, :270)
         // int8 blob of layer l: [qkv: 12 col tiles x 1 k chunk][mlp0: 8 x 2][mlp3: 4 x 2] slice tiles, then the column
         // scales qkv[384] mlp0[2][256] mlp3[2][128]

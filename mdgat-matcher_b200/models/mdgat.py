@@ -229,11 +229,12 @@ class MDGAT(nn.Module):
         return mode, int(self.config.get('gemm_slices', 7))
 
     def attention_engine(self):
-        """config['attention']: 'tcgen05_i8' (default; Q K^T and P V as exact int8 digit products in TMEM)
-        or 'dmma' (flash attention on the FP64 pipe)."""
+        """config['attention']: 'tcgen05_i8' (default; Q K^T and P V of the full-attention layers as exact int8
+        digit products in TMEM, dense logits of the top-k layers from the DMMA kernel), 'tcgen05_i8_all' (top-k
+        layers on tcgen05 too) or 'dmma' (flash attention on the FP64 pipe)."""
         mode = self.config.get('attention', 'tcgen05_i8')
-        if mode not in ('tcgen05_i8', 'dmma'):
-            raise ValueError("config['attention'] must be 'tcgen05_i8' or 'dmma'")
+        if mode not in ('tcgen05_i8', 'tcgen05_i8_all', 'dmma'):
+            raise ValueError("config['attention'] must be 'tcgen05_i8', 'tcgen05_i8_all' or 'dmma'")
         return mode
 
     def packed_weights_i8(self, slices):
@@ -336,7 +337,8 @@ class MDGAT(nn.Module):
                 write_Z=int(write_Z),
                 gemm_mode=_capi.GEMM_TCGEN05_I8 if gemm_mode == 'tcgen05_i8' else _capi.GEMM_DMMA_F64,
                 gemm_slices=gemm_slices,
-                attn_mode=_capi.ATTN_TCGEN05_I8 if self.attention_engine() == 'tcgen05_i8' else _capi.ATTN_DMMA_F64)
+                attn_mode={'tcgen05_i8': _capi.ATTN_TCGEN05_I8, 'tcgen05_i8_all': _capi.ATTN_TCGEN05_I8_ALL,
+                           'dmma': _capi.ATTN_DMMA_F64}[self.attention_engine()])
             need = _capi.lib.mdgat_forward_workspace_bytes(ctypes.byref(cfg))
             ws = self._workspace
             if ws is None or ws.device != dev or ws.numel() < need:

@@ -271,7 +271,7 @@ E2E = ['cfg1_seeded_L4_n128', 'ckpt_L9_n512_T100', 'ckpt_L9_ragged_gap', 'ckpt_L
        'seeded_L9_n512', 'ckpt_L9_duplicates', 'ckpt_L9_sgloss_mutual', 'ckpt_L9_n2048', 'ckpt_L9_n512_b8']
 
 
-@pytest.mark.parametrize('gemm,attention', [('tcgen05_i8', 'tcgen05_i8'), ('tcgen05_i8', 'dmma'), ('dmma', 'dmma')])
+@pytest.mark.parametrize('gemm,attention', [('tcgen05_i8', 'tcgen05_i8'), ('tcgen05_i8', 'tcgen05_i8_all'), ('tcgen05_i8', 'dmma'), ('dmma', 'dmma')])
 @pytest.mark.parametrize('name', E2E)
 def test_forward_matches_reference_golden(dev, name, gemm, attention):
     rec = load_golden(name)

@@ -11,6 +11,7 @@
 //    (b, h, query) row over dense logits produced by the batched GEMM, softmax over the kept
 //    k, and a sparse P.V (only k of M value rows are touched). Ties at the k-th logit are
 //    resolved towards the lowest index, so exactly k entries are kept (torch.topk semantics).
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -447,7 +448,8 @@ static cudaError_t launch_topk_t(const double* S, const double* V, double* Out, 
     // value matrix of a head resident in shared memory when it fits next to the kept lists (M = 512, k = 128: 169 KB)
     const size_t smem_v = (size_t)TKS_WARPS * topk * sizeof(KeptEntry) + 64 * sizeof(double) + (size_t)M * LDH_V * sizeof(double);
     if constexpr (VPT == 16) {
-        if (smem_v <= 200 * 1024 && N >= TKS_WARPS) {
+        static const bool smem_variant = [] { const char* e = getenv("MDGAT_TOPK_SMEMV"); return !(e && e[0] == '0'); }();
+        if (smem_variant && smem_v <= 200 * 1024 && N >= TKS_WARPS) {
             cudaError_t e = cudaFuncSetAttribute(topk_softmax_pv_kernel<VPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v);
             if (e != cudaSuccess) return e;
             topk_softmax_pv_kernel<VPT, true><<<(unsigned)(rows / N), 32 * TKS_WARPS, smem_v, st>>>(S, V, Out, ldo, N, M, topk, rows);

@@ -28,6 +28,7 @@
 // instructions) against 80 in the DMMA kernel; digit handling runs on the integer pipe.
 // LOGITS mode (dynamic layers) stops after the Horner pass and stores the scaled logits for the exact
 // top-k selection kernel.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -42,7 +43,10 @@ constexpr int AI_KPLANE = AI_BN * 32;      // bytes of one K (or V^T) digit plan
 constexpr int AI_PPLANE = AI_BM * AI_BN;   // bytes of one P digit plane
 constexpr int AI_STAGES = 3;               // K/V tile ring
 constexpr int AI_STAGE_BYTES = 2 * AI_S * AI_KPLANE;
-constexpr int AI_EPI_THREADS = 256, AI_THREADS = AI_EPI_THREADS + 64;
+// epilogue organisation: CW = columns of a 32-column tile per warp (16: 8 epilogue warps, 8: 16 epilogue warps = 4 per SM
+// sub-partition); the MMA and loader warps follow the epilogue warps
+constexpr int ai_epi_threads(int cw) { return 128 * (32 / cw); }
+constexpr int ai_threads(int cw) { return ai_epi_threads(cw) + 64; }
 constexpr int AI_TM_S = 0;                 // TMEM columns: logits diagonals [0, 224)
 constexpr int AI_TM_O = AI_S * AI_BN;      //               P V diagonals   [224, 448); pass 1 borrows [224, 352)
 constexpr int AI_EXP_LIMIT = 60;           // |exponent| clamp of the digit scales (values beyond 2^60 are out of range)
@@ -220,10 +224,16 @@ DEVINL void ai_ld16(uint32_t taddr, int (&r)[16]) {
                    "=r"(r[8]),"=r"(r[9]),"=r"(r[10]),"=r"(r[11]),"=r"(r[12]),"=r"(r[13]),"=r"(r[14]),"=r"(r[15])
                  : "r"(taddr));
 }
+DEVINL void ai_ld8(uint32_t taddr, int (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]),"=r"(r[1]),"=r"(r[2]),"=r"(r[3]),"=r"(r[4]),"=r"(r[5]),"=r"(r[6]),"=r"(r[7]) : "r"(taddr));
+}
+DEVINL void ai_ldw(uint32_t taddr, int (&r)[16]) { ai_ld16(taddr, r); }
+DEVINL void ai_ldw(uint32_t taddr, int (&r)[8]) { ai_ld8(taddr, r); }
 DEVINL void ai_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 DEVINL void ai_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 DEVINL void ai_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }       // the 8 epilogue warps only
+template <int THREADS> DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, %0;" :: "n"(THREADS) : "memory"); }   // the epilogue warps only
 DEVINL double int_to_f64(int v) {                                                    // exact, integer ALU + one DADD
     return __hiloint2double(0x43380000 + (v >> 31), v) - 6755399441055744.0;
 }
@@ -244,8 +254,10 @@ struct AttnI8Params {
 //   warp 8 lane 0   MMA issuer
 //   warps 0..7      epilogue: thread = query row (TMEM lane = 32 * (warp % 4) + lane), warps w and w + 4 split the
 //                   32 columns of a tile 16 / 16
-template <bool LOGITS>
-__global__ void __launch_bounds__(AI_THREADS, 1) attn_i8_kernel(const __grid_constant__ AttnI8Params p) {
+// (CW = 16; with CW = 8 there are 16 epilogue warps, four per lane quarter with 8 columns each, then the MMA and loader warps)
+template <bool LOGITS, int CW>
+__global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid_constant__ AttnI8Params p) {
+    constexpr int AI_EPI_THREADS = ai_epi_threads(CW), EPI_WARPS = AI_EPI_THREADS / 32, NCG = 32 / CW;
     extern __shared__ __align__(128) unsigned char ai_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int side = (int)blockIdx.z >= p.B ? 1 : 0;
@@ -265,8 +277,8 @@ __global__ void __launch_bounds__(AI_THREADS, 1) attn_i8_kernel(const __grid_con
     float* s_ksf = reinterpret_cast<float*>(s_ksd + Mpad);                        // [Mpad]
     float* s_ktm = s_ksf + Mpad;                                                  // [T] (padded to 4)
     double* etab = reinterpret_cast<double*>(s_ktm + ((T + 3) & ~3));             // [64]
-    double* s_xd = etab + 64;                                                     // [2][128] row exchange between column halves
-    unsigned long long* s_xu = reinterpret_cast<unsigned long long*>(s_xd + 256); // [2][128]
+    double* s_xd = etab + 64;                                                     // [4][128] row exchange between column groups
+    unsigned long long* s_xu = reinterpret_cast<unsigned long long*>(s_xd + 512); // [4][128]
 
     __shared__ __align__(8) uint64_t q_full, kv_full[AI_STAGES], kv_empty[AI_STAGES], s1_full[2], s1_empty[2],
         s_full, s_empty, p_full[2], p_empty[2], o_full;
@@ -285,7 +297,7 @@ __global__ void __launch_bounds__(AI_THREADS, 1) attn_i8_kernel(const __grid_con
         mbar_fence_init();
     }
     exp_table_to_shared(etab);
-    if (warp == 8) {
+    if (warp == EPI_WARPS) {
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_s);
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(dst));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -298,7 +310,7 @@ __global__ void __launch_bounds__(AI_THREADS, 1) attn_i8_kernel(const __grid_con
     const int8_t* gK = Kd.Ks + (size_t)bh * T * (AI_S * AI_KPLANE);
     const int8_t* gV = Kd.Vs + (size_t)bh * T * (AI_S * AI_KPLANE);
 
-    if (warp == 9) {
+    if (warp == EPI_WARPS + 1) {
         // ------------------------------------------------------------------ loader
         if (lane == 0) {
             const int8_t* gQ = Qd.Qs + ((size_t)bh * (Npad / AI_BM) + qt) * (AI_S * AI_QPLANE);
@@ -327,7 +339,7 @@ __global__ void __launch_bounds__(AI_THREADS, 1) attn_i8_kernel(const __grid_con
                     bulk_g2s(sKV + stage * AI_STAGE_BYTES + AI_S * AI_KPLANE, gV + (size_t)jt * (AI_S * AI_KPLANE), AI_S * AI_KPLANE, &kv_full[stage]);
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == EPI_WARPS) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint64_t qd0 = ai_desc(sQ), kd0 = ai_desc(sKV), pd0 = ai_desc(sP);
@@ -385,7 +397,7 @@ __global__ void __launch_bounds__(AI_THREADS, 1) attn_i8_kernel(const __grid_con
         }
     } else {
         // ------------------------------------------------------------------ epilogue warps
-        const int quarter = warp & 3, half = warp >> 2;
+        const int quarter = warp & 3, cgi = warp >> 2, c0 = cgi * CW;   // columns c0 .. c0 + CW - 1 of every 32-column tile
         const int rloc = quarter * 32 + lane;                     // TMEM lane = row inside the query tile
         const int row = qt * AI_BM + rloc;
         const bool row_ok = row < N;
@@ -400,17 +412,17 @@ __global__ void __launch_bounds__(AI_THREADS, 1) attn_i8_kernel(const __grid_con
                 const int buf = jt & 1;
                 mbar_wait(&s1_full[buf], (unsigned)((jt >> 1) & 1));
                 ai_fence_after();
-                int a0[16], a1[16];
-                ai_ld16(tlane + AI_TM_O + buf * 64 + half * 16, a0);
-                ai_ld16(tlane + AI_TM_O + buf * 64 + 32 + half * 16, a1);
+                int a0[CW], a1[CW];
+                ai_ldw(tlane + AI_TM_O + buf * 64 + c0, a0);
+                ai_ldw(tlane + AI_TM_O + buf * 64 + 32 + c0, a1);
                 ai_ld_wait();
                 ai_fence_before();
                 mbar_arrive(&s1_empty[buf]);
-                const float* kf = s_ksf + jt * AI_BN + half * 16;
+                const float* kf = s_ksf + jt * AI_BN + c0;
                 kmax = fmaxf(kmax, s_ktm[jt]);
-                const int jbase = jt * AI_BN + half * 16;
+                const int jbase = jt * AI_BN + c0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
+                for (int j = 0; j < CW; ++j) {
                     const float v = (float)(a0[j] * 256 + a1[j]) * kf[j];        // units 2^(e_i - 20)
                     if (jbase + j < M) amax = fmaxf(amax, v);
                 }
@@ -419,25 +431,27 @@ __global__ void __launch_bounds__(AI_THREADS, 1) attn_i8_kernel(const __grid_con
             const double lead = (double)amax * 0.00390625 * r_i;
             double c = lead + fabs(lead) * 4.76837158203125e-07 + 24.2 * (double)kmax * r_i;
             if (!(amax > -INFINITY)) c = -INFINITY;                               // this half saw only padding columns
-            s_xd[half * 128 + rloc] = c;
-            epi_bar_sync();
-            c_i = fmax(c, s_xd[(half ^ 1) * 128 + rloc]);
+            s_xd[cgi * 128 + rloc] = c;
+            epi_bar_sync<AI_EPI_THREADS>();
+            c_i = c;
+#pragma unroll
+            for (int g = 0; g < NCG; ++g) c_i = fmax(c_i, s_xd[g * 128 + rloc]);
         }
         unsigned long long rsum = 0ull;
         for (int jt = 0; jt < T; ++jt) {
             mbar_wait(&s_full, (unsigned)(jt & 1));
             ai_fence_after();
-            int acc[AI_S][16];
+            int acc[AI_S][CW];
 #pragma unroll
-            for (int dd = 0; dd < AI_S; ++dd) ai_ld16(tlane + AI_TM_S + dd * AI_BN + half * 16, acc[dd]);
+            for (int dd = 0; dd < AI_S; ++dd) ai_ldw(tlane + AI_TM_S + dd * AI_BN + c0, acc[dd]);
             ai_ld_wait();
             ai_fence_before();
             mbar_arrive(&s_empty);
-            const int jbase = jt * AI_BN + half * 16;
+            const int jbase = jt * AI_BN + c0;
             const double* ks = s_ksd + jbase;
-            double z[16];
+            double z[CW];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < CW; ++j) {
                 // |acc_dd| <= 7 * 32 * 2^14 < 2^22: two neighbouring diagonals merge exactly in int32
                 double hsum = int_to_f64(acc[5][j] * 256 + acc[6][j]);
                 hsum = fma(hsum, 1.52587890625e-05, int_to_f64(acc[3][j] * 256 + acc[4][j]));
@@ -448,39 +462,39 @@ __global__ void __launch_bounds__(AI_THREADS, 1) attn_i8_kernel(const __grid_con
             if (LOGITS) {
                 if (row_ok) {
                     double* dst = p.Out[side] + ((long long)bh * N + row) * (long long)M + jbase;
-                    if (jbase + 16 <= M && (M & 1) == 0) {
+                    if (jbase + CW <= M && (M & 1) == 0) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(z[j] * r_i, z[j + 1] * r_i);
+                        for (int j = 0; j < CW; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(z[j] * r_i, z[j + 1] * r_i);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) if (jbase + j < M) dst[j] = z[j] * r_i;
+                        for (int j = 0; j < CW; ++j) if (jbase + j < M) dst[j] = z[j] * r_i;
                     }
                 }
                 continue;
             }
-            uint32_t lo[16], hi[16];
+            uint32_t lo[CW], hi[CW];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < CW; ++j) {
                 const double pj = exp_fast_neg(fma(z[j], r_i, -c_i), etab);      // <= 1
                 const double pm = fma(pj, 140737488355328.0, 6755399441055744.0);   // p 2^47 rounded into the mantissa
                 lo[j] = (uint32_t)__double2loint(pm);
                 hi[j] = (uint32_t)__double2hiint(pm) & 0xffffu;                  // bits 32..47 of p^
             }
-            if (jbase + 16 > M) {
+            if (jbase + CW > M) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) if (jbase + j >= M) { lo[j] = 0u; hi[j] = 0u; }
+                for (int j = 0; j < CW; ++j) if (jbase + j >= M) { lo[j] = 0u; hi[j] = 0u; }
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) rsum += ((unsigned long long)hi[j] << 32) | lo[j];
+            for (int j = 0; j < CW; ++j) rsum += ((unsigned long long)hi[j] << 32) | lo[j];
             const int buf = jt & 1;
             if (jt >= 2) mbar_wait(&p_empty[buf], (unsigned)(((jt >> 1) - 1) & 1));   // P V of tile jt - 2 has read this buffer
-            uint8_t* pdst = sP + buf * (AI_SP * AI_PPLANE) + canon32(rloc, half);
+            uint8_t* pdst = sP + buf * (AI_SP * AI_PPLANE) + canon32(rloc, c0 >> 4) + (c0 & 15);
 #pragma unroll
             for (int a = 0; a < AI_SP; ++a) {
                 const int byte = AI_SP - 1 - a;                                  // plane 0 = most significant byte
-                uint32_t w[4];
+                uint32_t w[CW / 4];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < CW / 4; ++g) {
                     uint32_t x0, x1, x2, x3;
                     if (byte < 4) { x0 = lo[4 * g]; x1 = lo[4 * g + 1]; x2 = lo[4 * g + 2]; x3 = lo[4 * g + 3]; }
                     else { x0 = hi[4 * g]; x1 = hi[4 * g + 1]; x2 = hi[4 * g + 2]; x3 = hi[4 * g + 3]; }
@@ -488,47 +502,50 @@ __global__ void __launch_bounds__(AI_THREADS, 1) attn_i8_kernel(const __grid_con
                     const uint32_t t01 = __byte_perm(x0, x1, sel), t23 = __byte_perm(x2, x3, sel);
                     w[g] = __byte_perm(t01, t23, 0x5410);
                 }
-                *reinterpret_cast<uint4*>(pdst + a * AI_PPLANE) = make_uint4(w[0], w[1], w[2], w[3]);
+                if constexpr (CW == 16) *reinterpret_cast<uint4*>(pdst + a * AI_PPLANE) = make_uint4(w[0], w[1], w[2], w[3]);
+                else *reinterpret_cast<uint2*>(pdst + a * AI_PPLANE) = make_uint2(w[0], w[1]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy stores -> tensor core reads
             mbar_arrive(&p_full[buf]);
         }
         if (!LOGITS) {
-            s_xu[half * 128 + rloc] = rsum;
+            s_xu[cgi * 128 + rloc] = rsum;
             mbar_wait(&o_full, 0);
             ai_fence_after();
-            epi_bar_sync();
-            const unsigned long long tot = rsum + s_xu[(half ^ 1) * 128 + rloc];
-            const double inv = 140737488355328.0 / (double)tot;                 // 1 / (sum p^ 2^-47)
-            const double* vs = Kd.vscale + (size_t)bh * 32 + half * 16;
-            double outv[16];
+            epi_bar_sync<AI_EPI_THREADS>();
+            unsigned long long tot = 0ull;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) outv[j] = 0.0;
+            for (int g = 0; g < NCG; ++g) tot += s_xu[g * 128 + rloc];
+            const double inv = 140737488355328.0 / (double)tot;                 // 1 / (sum p^ 2^-47)
+            const double* vs = Kd.vscale + (size_t)bh * 32 + c0;
+            double outv[CW];
+#pragma unroll
+            for (int j = 0; j < CW; ++j) outv[j] = 0.0;
 #pragma unroll
             for (int dd = AI_S - 1; dd >= 0; --dd) {
-                int o[16];
-                ai_ld16(tlane + AI_TM_O + dd * 32 + half * 16, o);
+                int o[CW];
+                ai_ldw(tlane + AI_TM_O + dd * 32 + c0, o);
                 ai_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) outv[j] = fma(outv[j], 0.00390625, int_to_f64(o[j]));
+                for (int j = 0; j < CW; ++j) outv[j] = fma(outv[j], 0.00390625, int_to_f64(o[j]));
             }
             if (row_ok) {
-                double* dst = p.Out[side] + ((long long)b * N + row) * p.ldo + h * HDIM + half * 16;
+                double* dst = p.Out[side] + ((long long)b * N + row) * p.ldo + h * HDIM + c0;
 #pragma unroll
-                for (int j = 0; j < 16; j += 2)
+                for (int j = 0; j < CW; j += 2)
                     *reinterpret_cast<double2*>(dst + j) = make_double2(outv[j] * vs[j] * inv, outv[j + 1] * vs[j + 1] * inv);
             }
         }
     }
     ai_fence_before();
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem));
+    if (warp == EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem));
 }
 
 static size_t attn_i8_smem(int M) {
     const int T = (M + AI_BN - 1) / AI_BN, Mpad = T * AI_BN;
     return (size_t)AI_S * AI_QPLANE + (size_t)AI_STAGES * AI_STAGE_BYTES + 2 * AI_SP * AI_PPLANE +
-           (size_t)Mpad * 12 + (size_t)((T + 3) & ~3) * 4 + 64 * 8 + 256 * 8 + 256 * 8;
+           (size_t)Mpad * 12 + (size_t)((T + 3) & ~3) * 4 + 64 * 8 + 512 * 8 + 512 * 8;
 }
 
 bool attn_i8_supported(int N, int M) { return N > 0 && M > 0 && attn_i8_smem(M) <= 200 * 1024; }
@@ -569,13 +586,17 @@ cudaError_t launch_attn_i8(const AttnI8Side* q, const AttnI8Side* kv, double* co
     const size_t smem = attn_i8_smem(mmax);
     dim3 grid((nmax + AI_BM - 1) / AI_BM, HEADS, nsides * B);
     cudaError_t e;
-    if (logits_only) {
-        if ((e = cudaFuncSetAttribute(attn_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        attn_i8_kernel<true><<<grid, AI_THREADS, smem, st>>>(p);
-    } else {
-        if ((e = cudaFuncSetAttribute(attn_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        attn_i8_kernel<false><<<grid, AI_THREADS, smem, st>>>(p);
-    }
+    // MDGAT_ATTN_CW=16|8 (read once): columns of a key tile per epilogue warp, i.e. 8 or 16 epilogue warps
+    static const int cw = [] { const char* v = getenv("MDGAT_ATTN_CW"); return v && v[0] == '1' ? 16 : 8; }();
+    auto go = [&](auto kern, int threads) -> cudaError_t {
+        cudaError_t r = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (r != cudaSuccess) return r;
+        kern<<<grid, threads, smem, st>>>(p);
+        return cudaSuccess;
+    };
+    if (logits_only) e = cw == 16 ? go(attn_i8_kernel<true, 16>, ai_threads(16)) : go(attn_i8_kernel<true, 8>, ai_threads(8));
+    else e = cw == 16 ? go(attn_i8_kernel<false, 16>, ai_threads(16)) : go(attn_i8_kernel<false, 8>, ai_threads(8));
+    if (e != cudaSuccess) return e;
     count_launch();
     return cudaGetLastError();
 }

@@ -109,15 +109,16 @@ DEVINL void digits16(const double* x, double sc, uint32_t (&w)[AI_S][4]) {
 // qscale = 2^(e-12) / sqrt(32)   (row factor of the logits, 1/sqrt(d) of mdgat.py:192 included)
 // kscale = 2^f (double and float copies), ktilemax = largest kscale of a 32-row tile
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-slice_qk_kernel(const double* __restrict__ Qh, const double* __restrict__ Kh, AttnI8Side o, int B, int nqb) {
-    const bool isq = (int)blockIdx.x < nqb;
+// blk128 / t128: index of the 128-row block and the thread inside it (the stand-alone kernel maps them to blockIdx /
+// threadIdx, the fused per-layer kernel packs four of them into a 512-thread CTA)
+DEVINL void slice_qk_body(const double* __restrict__ Qh, const double* __restrict__ Kh, const AttnI8Side& o, int nqb, int blk128, int t128) {
+    const bool isq = blk128 < nqb;
     const int n = o.n;
     const int npad = isq ? (n + AI_BM - 1) / AI_BM * AI_BM : (n + AI_BN - 1) / AI_BN * AI_BN;
     const int bpb = (npad + 127) / 128;                              // blocks per (b, h)
-    const int blk = isq ? blockIdx.x : blockIdx.x - nqb;
+    const int blk = isq ? blk128 : blk128 - nqb;
     const int bh = blk / bpb;
-    const int i = (blk - bh * bpb) * 128 + threadIdx.x;              // padded row inside (b, h)
+    const int i = (blk - bh * bpb) * 128 + t128;                     // padded row inside (b, h)
     if (i >= npad) return;                                           // K only; whole warps (npad multiple of 32)
     const double* src = (isq ? Qh : Kh) + ((long long)bh * n + i) * LDH_QK;
     double x[32];
@@ -150,7 +151,7 @@ slice_qk_kernel(const double* __restrict__ Qh, const double* __restrict__ Kh, At
         float tm = kf;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, off));
-        if ((threadIdx.x & 31) == 0) o.ktilemax[(size_t)bh * (((npad / AI_BN) + 3) & ~3) + (i >> 5)] = tm;
+        if ((t128 & 31) == 0) o.ktilemax[(size_t)bh * (((npad / AI_BN) + 3) & ~3) + (i >> 5)] = tm;
     }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -162,6 +163,11 @@ slice_qk_kernel(const double* __restrict__ Qh, const double* __restrict__ Kh, At
     }
 }
 
+__global__ void __launch_bounds__(128)
+slice_qk_kernel(const double* __restrict__ Qh, const double* __restrict__ Kh, AttnI8Side o, int B, int nqb) {
+    slice_qk_body(Qh, Kh, o, nqb, (int)blockIdx.x, (int)threadIdx.x);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Digits of V, transposed: the P V product contracts over source keypoints, so the B operand is V^T
 // (32 channel rows x 32 keypoints of K per tile) and all keypoints of a (b, h) share one exponent per
@@ -169,11 +175,10 @@ slice_qk_kernel(const double* __restrict__ Qh, const double* __restrict__ Kh, At
 // weights, message = vscale * Horner(P V diagonals) / (sum_j p^_j 2^-47).
 // ---------------------------------------------------------------------------------------------------
 constexpr int SV_WARPS = 16;     // one CTA per (b, h) (128 CTAs at cfg2): 16 warps keep enough loads in flight per SM
-__global__ void __launch_bounds__(32 * SV_WARPS)
-slice_v_kernel(const double* __restrict__ Vh, AttnI8Side o) {
+DEVINL void slice_v_body(const double* __restrict__ Vh, const AttnI8Side& o, int bh) {
     __shared__ double s_max[SV_WARPS][32];
     const int n = o.n, npad = (n + AI_BN - 1) / AI_BN * AI_BN;
-    const int bh = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double* V = Vh + (long long)bh * n * LDH_V;
     double mx = 0.0;
     for (int j = warp; j < n; j += SV_WARPS) mx = fmax(mx, fabs(V[(long long)j * LDH_V + lane]));
@@ -198,6 +203,26 @@ slice_v_kernel(const double* __restrict__ Vh, AttnI8Side o) {
 #pragma unroll
         for (int s = 0; s < AI_S; ++s)
             *reinterpret_cast<uint4*>(dst + (size_t)s * AI_KPLANE) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+    }
+}
+
+__global__ void __launch_bounds__(32 * SV_WARPS)
+slice_v_kernel(const double* __restrict__ Vh, AttnI8Side o) { slice_v_body(Vh, o, (int)blockIdx.x); }
+
+// Both sides of a layer in ONE launch (the forward path): 512-thread CTAs, [q/k blocks of side 0 | v blocks of side 0 |
+// q/k blocks of side 1 | v blocks of side 1]; a q/k CTA holds four 128-row blocks.
+struct SliceSide { const double *Qh, *Kh, *Vh; AttnI8Side o; int nqb, nkb, qk_ctas, v_ctas; };
+__global__ void __launch_bounds__(32 * SV_WARPS)
+slice_sides_kernel(const __grid_constant__ SliceSide s0, const __grid_constant__ SliceSide s1) {
+    int blk = blockIdx.x;
+    const bool second = blk >= s0.qk_ctas + s0.v_ctas;
+    const SliceSide& sd = second ? s1 : s0;
+    if (second) blk -= s0.qk_ctas + s0.v_ctas;
+    if (blk < sd.qk_ctas) {
+        const int blk128 = blk * 4 + ((int)threadIdx.x >> 7);
+        if (blk128 < sd.nqb + sd.nkb) slice_qk_body(sd.Qh, sd.Kh, sd.o, sd.nqb, blk128, (int)threadIdx.x & 127);
+    } else {
+        slice_v_body(sd.Vh, sd.o, blk - sd.qk_ctas);
     }
 }
 
@@ -567,6 +592,26 @@ cudaError_t launch_attn_i8_slice(const double* Qh, const double* Kh, const doubl
         count_launch();
     }
     return cudaGetLastError();
+}
+
+cudaError_t launch_attn_i8_slice_sides(const double* const* Qh, const double* const* Kh, const double* const* Vh, const AttnI8Side* o,
+                                       int B, cudaStream_t st) {
+    static_assert(SV_WARPS == 16, "a q/k CTA of the fused slicer holds four 128-row blocks");
+    SliceSide sd[2];
+    for (int s = 0; s < 2; ++s) {
+        const int n = o[s].n;
+        sd[s].Qh = Qh[s]; sd[s].Kh = Kh[s]; sd[s].Vh = Vh[s]; sd[s].o = o[s];
+        sd[s].nqb = B * HEADS * ((n + AI_BM - 1) / AI_BM);
+        sd[s].nkb = B * HEADS * ((pad_to(n, AI_BN) + 127) / 128);
+        sd[s].qk_ctas = (sd[s].nqb + sd[s].nkb + 3) / 4;
+        sd[s].v_ctas = B * HEADS;
+    }
+    if (B <= 0 || o[0].n <= 0 || o[1].n <= 0) return cudaSuccess;
+    const int grid = sd[0].qk_ctas + sd[0].v_ctas + sd[1].qk_ctas + sd[1].v_ctas;
+    slice_sides_kernel<<<grid, 32 * SV_WARPS, 0, st>>>(sd[0], sd[1]);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) count_launch();
+    return e;
 }
 
 // q[s] / kv[s]: digit planes of the query side and of the source side of grid side s; Out[s]: messages (rows x ldo),

@@ -312,8 +312,12 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
         if (ai8) {
             // digit planes of this layer's q, k, v (both sides), then the tcgen05 kernel: side s reads the k / v planes
             // of side s (self) or 1 - s (cross)
-            MDGAT_CUDA_OK(launch_attn_i8_slice(Q0, K0, V0, w.ai[0], B, st));
-            MDGAT_CUDA_OK(launch_attn_i8_slice(Q1, K1, V1, w.ai[1], B, st));
+            const double* const qs[2] = {Q0, Q1}; const double* const ks[2] = {K0, K1}; const double* const vs[2] = {V0, V1};
+            if (N > 0 && M > 0) { MDGAT_CUDA_OK(launch_attn_i8_slice_sides(qs, ks, vs, w.ai, B, st)); }
+            else {
+                MDGAT_CUDA_OK(launch_attn_i8_slice(Q0, K0, V0, w.ai[0], B, st));
+                MDGAT_CUDA_OK(launch_attn_i8_slice(Q1, K1, V1, w.ai[1], B, st));
+            }
             prof_mark(k > 0 ? ST_ATTN_TOPK : ST_ATTN_FULL, st);
             const AttnI8Side qd[2] = {w.ai[0], w.ai[1]};
             const AttnI8Side kvd[2] = {cross ? w.ai[1] : w.ai[0], cross ? w.ai[0] : w.ai[1]};

@@ -100,6 +100,9 @@ size_t attn_i8_side_bytes(int B, int n);
 AttnI8Side attn_i8_carve(void* base, int B, int n);
 bool attn_i8_supported(int N, int M);
 cudaError_t launch_attn_i8_slice(const double* Qh, const double* Kh, const double* Vh, const AttnI8Side& o, int B, cudaStream_t st);
+// both sides of a layer (index 0 / 1) in one launch
+cudaError_t launch_attn_i8_slice_sides(const double* const* Qh, const double* const* Kh, const double* const* Vh, const AttnI8Side* o,
+                                       int B, cudaStream_t st);
 cudaError_t launch_attn_i8(const AttnI8Side* q, const AttnI8Side* kv, double* const* Out, int B, int nsides, int ldo,
                            bool logits_only, cudaStream_t st);
 

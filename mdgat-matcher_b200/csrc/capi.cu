@@ -273,6 +273,11 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
     const double* K0 = w.Kh; const double* K1 = w.Kh + (size_t)R0 * HEADS * LDH_QK;
     const double* V0 = w.Vh; const double* V1 = w.Vh + (size_t)R0 * HEADS * LDH_V;
 
+    // MDGAT_FUSE_SLICE=1: the per-layer GEMMs cut their own outputs into digit planes when one CTA owns whole rows
+    // (R >= 148 row tiles). Bit-identical results; measured slower on B200 (slice stage -1.04 ms, GEMM stage +1.14 ms:
+    // the FP64-bound slicing tail runs while the CTA's tensor pipe idles), so the stand-alone launches stay the default.
+    static const bool fuse_env = [] { const char* e = getenv("MDGAT_FUSE_SLICE"); return e && e[0] == '1'; }();
+    const bool fuse_slice = i8 && fuse_env && ozaki_gemm_can_slice(R, DMODEL);
     for (int l = 0; l < 2 * L; ++l) {
         const LayerOffsets lo = lay.layer(l);
         const bool cross = (l & 1) != 0;                  // names = ['self','cross']*L (mdgat.py:353)
@@ -286,9 +291,10 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
         const size_t slice_tile = (size_t)S8 * 32 * 128;                // bytes of one (column tile, k chunk) of W slices
         const unsigned char* Li8 = i8 ? reinterpret_cast<const unsigned char*>(d_weights_i8) + (size_t)l * (slice_tile * 36 + 1152 * 8) : nullptr;
         const double* cs8 = i8 ? reinterpret_cast<const double*>(Li8 + slice_tile * 36) : nullptr;
-        prof_mark(i8 ? ST_SLICE : ST_GEMM, st);
+        prof_mark(i8 && !(fuse_slice && l > 0) ? ST_SLICE : ST_GEMM, st);
         if (i8) {
-            MDGAT_CUDA_OK(launch_slice_rows(w.X, LDX, DMODEL, nullptr, 0, 0, R, S8, w.xsX, w.rsX, st));
+            // digit planes of the residual stream: cut by the previous layer's last GEMM when it can (fuse_slice)
+            if (!(fuse_slice && l > 0)) MDGAT_CUDA_OK(launch_slice_rows(w.X, LDX, DMODEL, nullptr, 0, 0, R, S8, w.xsX, w.rsX, st));
             prof_mark(ST_GEMM, st);
             OzGemmArgs a;
             memset(&a, 0, sizeof(a));
@@ -336,13 +342,18 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
             prof_mark(ST_GEMM, st);
             a.Xs[0] = w.xsX; a.rowscale[0] = w.rsX; a.Xs[1] = w.xsM; a.rowscale[1] = w.rsM; a.Ws = reinterpret_cast<const int8_t*>(Li8 + slice_tile * 12); a.colscale = cs8 + 384;
             a.bias = Wt + lo.b1; a.Y = w.Hd; a.ldy = LDHID; a.R = R; a.Nout = 2 * DMODEL; a.K = 2 * DMODEL; a.relu = 1; a.epi = EPI_PLAIN;
+            if (fuse_slice) { a.slice_out = w.xsH; a.slice_scale = w.rsH; }       // the GEMM cuts its own output for the next one
             MDGAT_CUDA_OK(launch_ozaki_gemm(a, S8, st));
-            prof_mark(ST_SLICE, st);
-            MDGAT_CUDA_OK(launch_slice_rows(w.Hd, LDHID, 2 * DMODEL, nullptr, 0, 0, R, S8, w.xsH, w.rsH, st));
-            prof_mark(ST_GEMM, st);
+            a.slice_out = nullptr; a.slice_scale = nullptr;
+            if (!fuse_slice) {
+                prof_mark(ST_SLICE, st);
+                MDGAT_CUDA_OK(launch_slice_rows(w.Hd, LDHID, 2 * DMODEL, nullptr, 0, 0, R, S8, w.xsH, w.rsH, st));
+                prof_mark(ST_GEMM, st);
+            }
             a.Xs[0] = w.xsH; a.rowscale[0] = w.rsH; a.Xs[1] = w.xsH + ozaki_slices_bytes(R, 128, S8); a.rowscale[1] = w.rsH + (size_t)((R + 127) / 128 * 128);
             a.Ws = reinterpret_cast<const int8_t*>(Li8 + slice_tile * 28); a.colscale = cs8 + 896;
             a.bias = Wt + lo.b2; a.Res = w.X; a.ldres = LDX; a.Y = w.X; a.ldy = LDX; a.Nout = DMODEL; a.relu = 0;
+            if (fuse_slice && l + 1 < 2 * L) { a.slice_out = w.xsX; a.slice_scale = w.rsX; }   // planes of x for the next layer
             MDGAT_CUDA_OK(launch_ozaki_gemm(a, S8, st));
         } else {
             MDGAT_CUDA_OK(linear(w.X, LDX, DMODEL, w.Msg, LDX, DMODEL, Wt + lo.w1, 2 * DMODEL, Wt + lo.b1, nullptr, 0, w.Hd, LDHID, R, 2 * DMODEL, 1.0, 1, st));

@@ -80,8 +80,10 @@ struct OzGemmArgs {
     double* Y; int ldy;
     int R, Nout, K, relu, epi;
     double *Qh, *Kh, *Vh; int rows0, n0, n1;
+    int8_t* slice_out; double* slice_scale;       // optional: digit planes + row scales of Y for the next GEMM (ozaki_gemm_can_slice)
 };
 size_t ozaki_slices_bytes(int R, int K, int S);
+bool ozaki_gemm_can_slice(int R, int Nout);
 // chunk c (128 columns) of the input goes to Xs + c * ozaki_slices_bytes(R, 128, S) and rowscale + c * Rpad
 cudaError_t launch_slice_rows(const double* A0, int ld0, int K0, const double* A1, int ld1, int K1, int R, int S,
                               int8_t* Xs, double* rowscale, cudaStream_t st);

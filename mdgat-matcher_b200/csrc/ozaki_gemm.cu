@@ -42,6 +42,50 @@ DEVINL double pow2d(int e) { return __longlong_as_double((long long)(1023 + e) <
 // chunk's exponent. Input = concat of up to two row-major float64 buffers (K0 + K1 columns, multiples
 // of 128). rowscale[kchunk][Rpad] = 2^(e - 12).
 // ---------------------------------------------------------------------------------------------------
+// x: 16 consecutive k (group kt) of padded row r; the 8 lanes holding a (row, 128-column chunk) must be an aligned
+// group of 8 lanes of a fully active warp
+template <int S>
+DEVINL void slice_group(double (&x)[16], long long r, int kt, int Rpad, int8_t* Xs, double* rowscale, size_t chunk_stride) {
+    const int k0 = kt * 16;
+    double mx = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mx = fmax(mx, fabs(x[i]));
+    // maximum over the 8 lanes that share this (row, 128-column chunk)
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+    int e = 0;
+    if (mx > 0.0) frexp(mx, &e);                         // mx = m * 2^e, m in [0.5, 1)  ->  |x| < 2^e
+    e = max(-900, min(900, e));
+    const int tile = (int)(r / OZ_BM), rr = (int)(r % OZ_BM);
+    const int kchunk = k0 / OZ_KC, kk = k0 % OZ_KC;
+    if ((kt & 7) == 0) rowscale[(size_t)kchunk * Rpad + r] = pow2d(e - 12);
+    // Digits. With t = x * 2^(6-e) the most-significant-first cascade d_1 = rint(t), d_2 = rint((t - d_1) * 128), ..
+    // telescopes: d_s = q_s - 128 q_(s-1) with q_s = rint(t * 128^(s-1)) (every step of the cascade is exact). Each q_s
+    // is ONE FMA -- x * (2^(6-e) 128^(s-1)) + 1.5 * 2^52 leaves rint(.) in the low mantissa word (|q_s| < 2^48; only its
+    // low 32 bits are needed because |d_s| <= 64) -- and the difference runs on the integer pipe: 7 FP64 instructions per
+    // element instead of 28 (the slicer was FP64-bound), rint() / F2I never touch the quarter-rate conversion pipe.
+    int8_t* base = Xs + (size_t)kchunk * chunk_stride + ((size_t)tile * S) * OZ_XTILE + oz_canon(rr, kk);
+    int qprev[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) qprev[i] = 0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const double cs = pow2d(6 - e + 7 * s);              // 6 - e + 7 s <= 6 + 900 + 42 < 1023
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int q = __double2loint(fma(x[i], cs, 6755399441055744.0));
+            const int d = q - (qprev[i] << 7);
+            qprev[i] = q;
+            w[i >> 2] |= ((uint32_t)d & 0xffu) << (8 * (i & 3));
+        }
+        *reinterpret_cast<uint4*>(base + (size_t)s * OZ_XTILE) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// (A software-pipelined grid-stride variant -- two CTAs per SM, the next task's loads in flight during the current one --
+// was measured 5 % slower than this one-task-per-thread form.)
 template <int S>
 __global__ void __launch_bounds__(256)
 slice_rows_kernel(const double* __restrict__ A0, int ld0, int K0, const double* __restrict__ A1, int ld1, int K1,
@@ -62,39 +106,7 @@ slice_rows_kernel(const double* __restrict__ A0, int ld0, int K0, const double* 
 #pragma unroll
         for (int i = 0; i < 16; ++i) x[i] = 0.0;
     }
-    double mx = 0.0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) mx = fmax(mx, fabs(x[i]));
-    // maximum over the 8 lanes that share this (row, 128-column chunk)
-    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-    int e = 0;
-    if (mx > 0.0) frexp(mx, &e);                         // mx = m * 2^e, m in [0.5, 1)  ->  |x| < 2^e
-    e = max(-900, min(900, e));
-    const int tile = (int)(r / OZ_BM), rr = (int)(r % OZ_BM);
-    const int kchunk = k0 / OZ_KC, kk = k0 % OZ_KC;
-    if ((kt & 7) == 0) rowscale[(size_t)kchunk * Rpad + r] = pow2d(e - 12);
-    // digits: t = x * 2^(6-e); d = rint(t); t = (t - d) * 2^7; ...
-    const double sc = pow2d(6 - e);
-    int8_t* base = Xs + (size_t)kchunk * chunk_stride + ((size_t)tile * S) * OZ_XTILE + oz_canon(rr, kk);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] *= sc;
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-        uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            // rint() and the double -> int conversion both run on the quarter-rate conversion pipe; adding 1.5 * 2^52
-            // rounds to the nearest integer (ties to even, like rint) on the FP64 pipe and leaves the integer in the
-            // low mantissa word
-            const double m = x[i] + 6755399441055744.0;
-            const double d = m - 6755399441055744.0;
-            x[i] = (x[i] - d) * 128.0;
-            w[i >> 2] |= ((uint32_t)__double2loint(m) & 0xffu) << (8 * (i & 3));
-        }
-        *reinterpret_cast<uint4*>(base + (size_t)s * OZ_XTILE) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
+    slice_group<S>(x, r, kt, Rpad, Xs, rowscale, chunk_stride);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -139,6 +151,9 @@ struct OzParams {
     int epi;                                           // EPI_PLAIN / EPI_QKV
     double *Qh, *Kh, *Vh; int rows0, n0, n1;
     int col_tiles_per_cta;                             // blockIdx.y selects a group of column tiles
+    // fused slicing of the output (EPI_PLAIN, CTA owns whole rows of Y): the digit planes of this CTA's 128 x Nout tile of Y,
+    // i.e. the operand of the next GEMM, in the layout launch_slice_rows() writes; null = off
+    int8_t* slice_out; double* slice_scale; unsigned long long slice_chunk_stride;
     long long* trace;                                  // debug timeline (null = off)
     int dbg;                                           // debug switches (mdgat_debug_flags)
 };
@@ -423,6 +438,27 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             }
           }
         }
+        if (EPI == EPI_PLAIN && p.slice_out != nullptr) {
+            // Tail: the digit planes of this CTA's rows of Y for the next GEMM. The rows were written by other warps of
+            // this CTA: the named barrier orders those stores before the loads below (same SM, coherent L1).
+            asm volatile("bar.sync 1, %0;" :: "n"(OZ_EPI_THREADS) : "memory");
+            const int tpr = p.Nout / 16;                                 // 16-wide groups per row
+            const double* Yc = p.Y;                                      // plain loads: Y was written in this kernel
+            for (int task = tid; task < OZ_BM * tpr; task += OZ_EPI_THREADS) {
+                const int rr = task / tpr, kt = task - rr * tpr;
+                const long long r = (long long)row_tile * OZ_BM + rr;
+                double x[16];
+                if (r < p.R) {
+                    const double* src = Yc + r * p.ldy + kt * 16;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) { const double2 v = *reinterpret_cast<const double2*>(src + i); x[i] = v.x; x[i + 1] = v.y; }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) x[i] = 0.0;
+                }
+                slice_group<S>(x, r, kt, Rpad, p.slice_out, p.slice_scale, (size_t)p.slice_chunk_stride);
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
@@ -491,6 +527,9 @@ cudaError_t measure_i8_peak(double* tops) {
     *tops = (double)sms * iters * 16.0 * 2.0 * 128 * 256 * 32 / (ms * 1e-3) / 1e12;
     return cudaGetLastError();
 }
+
+// the GEMM can cut its own output into digit planes when one CTA owns whole rows of Y (no column split)
+bool ozaki_gemm_can_slice(int R, int Nout) { return (R + OZ_BM - 1) / OZ_BM >= 148 && (Nout % OZ_KC) == 0; }
 
 size_t ozaki_slices_bytes(int R, int K, int S) {
     const size_t rt = (size_t)((R + OZ_BM - 1) / OZ_BM);
@@ -567,6 +606,7 @@ cudaError_t launch_ozaki_gemm(const OzGemmArgs& a, int S, cudaStream_t st) {
     p.Res = a.Res; p.ldres = a.ldres; p.Y = a.Y; p.ldy = a.ldy; p.R = a.R; p.Nout = a.Nout; p.K = a.K;
     p.relu = a.relu; p.epi = a.epi; p.Qh = a.Qh; p.Kh = a.Kh; p.Vh = a.Vh; p.rows0 = a.rows0; p.n0 = a.n0; p.n1 = a.n1;
     p.trace = g_trace_dev; p.dbg = g_debug_flags;
+    p.slice_out = a.slice_out; p.slice_scale = a.slice_scale; p.slice_chunk_stride = ozaki_slices_bytes(a.R, OZ_KC, S);
     const int row_tiles = (a.R + OZ_BM - 1) / OZ_BM, col_tiles = a.Nout / OZ_BN;
     // the X slice planes are loaded once per (CTA, k chunk): keep all column tiles in one CTA unless that leaves
     // SMs idle
@@ -574,6 +614,7 @@ cudaError_t launch_ozaki_gemm(const OzGemmArgs& a, int S, cudaStream_t st) {
     while (row_tiles * groups < 148 && groups < col_tiles) ++groups;
     p.col_tiles_per_cta = (col_tiles + groups - 1) / groups;
     dim3 grid(row_tiles, (col_tiles + p.col_tiles_per_cta - 1) / p.col_tiles_per_cta);
+    if (a.slice_out != nullptr && (grid.y != 1 || a.epi != EPI_PLAIN || (a.Nout % OZ_KC) != 0)) return cudaErrorInvalidValue;   // see ozaki_gemm_can_slice
     cudaError_t e;
     switch (S) {
         case 6: e = ozaki_gemm_t<6>(p, grid, st); break;

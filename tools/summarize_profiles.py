@@ -1,0 +1,109 @@
+"""Turns the ncu outputs of tools/gpu_round.sh (gpurun_out/) into the tracked summaries under profiles/.
+
+  python tools/summarize_profiles.py <tag>      # e.g. r1_final
+Reads gpurun_out/launches_final.csv (gpu__time_duration.sum per launch), the --set full reports
+prof_{attn_i8,oz,misc}_final.ncu-rep (through `ncu -i ... --page raw --csv`) and bench_final*.json.
+"""
+import collections
+import csv
+import io
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, 'gpurun_out')
+METRICS = [
+    ('gpu__time_duration.sum', 'duration'),
+    ('launch__grid_size', 'grid'),
+    ('launch__registers_per_thread', 'regs'),
+    ('sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active', 'IMMA pipe %'),
+    ('sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'FP64 pipe %'),
+    ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue slots %'),
+    ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps active %'),
+    ('dram__bytes_read.sum', 'DRAM read'),
+    ('dram__bytes_write.sum', 'DRAM write'),
+    ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'DRAM throughput %'),
+    ('lts__throughput.avg.pct_of_peak_sustained_elapsed', 'L2 throughput %'),
+    ('lts__t_sector_hit_rate.pct', 'L2 hit %'),
+    ('smsp__inst_executed.sum', 'warp instructions'),
+]
+
+
+def launch_table(path, forwards):
+    lines = [l for l in open(path) if not l.startswith('==')]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        if row.get('Metric Name') != 'gpu__time_duration.sum':
+            continue
+        k = row['Kernel Name']
+        if 'mdgat' not in k:
+            continue
+        v = float(row['Metric Value'].replace(',', ''))
+        v = {'ns': v / 1000, 'us': v, 'ms': v * 1000}[row['Metric Unit']]
+        a = agg.setdefault(k.split('(')[0][-60:], [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for k, a in agg.items() if 'peak_kernel' not in k)
+    out = ['| kernel | launches / forward | us / forward | avg us | share |', '|---|---|---|---|---|']
+    for k, a in agg.items():
+        if 'peak_kernel' in k:
+            continue
+        out.append('| `%s` | %.1f | %.1f | %.1f | %.3f |' % (k, a[0] / forwards, a[1] / forwards, a[1] / a[0], a[1] / tot))
+    out.append('')
+    out.append('Sum over the path kernels: %.1f us per forward (serialised, cold-cache launches; compare shares).' % (tot / forwards))
+    return '\n'.join(out), agg
+
+
+def ncu_table(rep):
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    out = ['| kernel | ' + ' | '.join(n for _, n in METRICS) + ' |', '|---|' + '---|' * len(METRICS)]
+    for r in rows[2:]:
+        cells = []
+        for m, _ in METRICS:
+            if m in ix:
+                v, u = r[ix[m]], units[ix[m]]
+                try:
+                    v = '%.1f' % float(v) if '.' in v else v
+                except ValueError:
+                    pass
+                cells.append((v + ' ' + u).strip())
+            else:
+                cells.append('-')
+        out.append('| `%s` | ' % r[ix['Kernel Name']][:48] + ' | '.join(cells) + ' |')
+    return '\n'.join(out)
+
+
+def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else 'r1_final'
+    bench = json.loads(open(os.path.join(OUT, 'bench_final.json')).read().strip().splitlines()[-1])
+    ref = json.loads(open(os.path.join(OUT, 'bench_final_ref.json')).read().strip().splitlines()[-1])
+    json.dump(bench, open(os.path.join(ROOT, 'profiles', tag + '_bench.json'), 'w'), indent=1)
+    json.dump(ref, open(os.path.join(ROOT, 'profiles', tag + '_bench_reference_arm.json'), 'w'), indent=1)
+    # the launch list covers warm-up + timed + e2e forwards of `bench.py --steps 2 --warmup 1`: count them by a once-per-forward kernel
+    table, agg = launch_table(os.path.join(OUT, 'launches_final.csv'), 1)
+    forwards = [a[0] for k, a in agg.items() if 'pack_inputs_kernel' in k][0]
+    table, _ = launch_table(os.path.join(OUT, 'launches_final.csv'), forwards)
+    md = ['# %s -- ncu launch list and top-kernel captures (cfg2: B=32, N=M=512, L=9, T=100, one B200)' % tag, '',
+          'Commands: see `tools/gpu_round.sh` (launch list: `ncu --metrics gpu__time_duration.sum --clock-control none` on',
+          '`bench.py --steps 2 --warmup 1`; captures: `ncu --set full --clock-control none --import-source on -k <kernel>`).', '',
+          'Bench of the same build (`%s_bench.json`): **%.1f pairs/s** resident, %.1f pairs/s end to end, CPU port %.2f pairs/s on %d threads,'
+          % (tag, bench['value'], bench['e2e']['value'], bench['cpu_baseline']['value'], bench['cpu_baseline']['cores']),
+          'eager PyTorch fp64 restatement on the same GPU %.1f pairs/s.' % bench['gpu_eager_port']['pairs_per_s'], '',
+          'Live stage times (CUDA events on the launch stream, ms per forward): `%s`' % json.dumps({k: round(v, 3) for k, v in bench['roofline']['stage_ms_per_step'].items()}), '',
+          '## Launch list (%d forwards in the capture)' % forwards, '', table, '']
+    for name, title in (('prof_attn_i8_final', 'attention (tcgen05 int8 digit products)'), ('prof_oz_final', 'Ozaki GEMM (q/k/v, MLP 256->256, MLP 256->128)'),
+                        ('prof_misc_final', 'slicer / DMMA logits / top-k / Sinkhorn')):
+        rep = os.path.join(OUT, name + '.ncu-rep')
+        if os.path.isfile(rep):
+            md += ['## ncu --set full: %s' % title, '', ncu_table(rep), '']
+    open(os.path.join(ROOT, 'profiles', tag + '_ncu_summary.md'), 'w').write('\n'.join(md))
+    print('\n'.join(md)[:3000])
+
+
+if __name__ == '__main__':
+    main()

@@ -121,17 +121,13 @@ DEVINL void slice_qk_body(const double* __restrict__ Qh, const double* __restric
     const int i = (blk - bh * bpb) * 128 + t128;                     // padded row inside (b, h)
     if (i >= npad) return;                                           // K only; whole warps (npad multiple of 32)
     const double* src = (isq ? Qh : Kh) + ((long long)bh * n + i) * LDH_QK;
-    double x[32];
+    // the row is read twice (maximum, then 16 values at a time for the digits; the second read hits L1): 16 instead of
+    // 32 live doubles keep the fused slicer at two 512-thread CTAs per SM
+    double mx = 0.0;
     if (i < n) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) { const double2 v = *reinterpret_cast<const double2*>(src + c); x[c] = v.x; x[c + 1] = v.y; }
-    } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) x[c] = 0.0;
+        for (int c = 0; c < 32; c += 2) { const double2 v = *reinterpret_cast<const double2*>(src + c); mx = fmax(mx, fmax(fabs(v.x), fabs(v.y))); }
     }
-    double mx = 0.0;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) mx = fmax(mx, fabs(x[c]));
     int e = 0;
     if (mx > 0.0) frexp(mx, &e);                                     // |x| < 2^e
     e = max(-AI_EXP_LIMIT, min(AI_EXP_LIMIT, e));
@@ -155,8 +151,16 @@ DEVINL void slice_qk_body(const double* __restrict__ Qh, const double* __restric
     }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
+        double x[16];
+        if (i < n) {
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) { const double2 v = *reinterpret_cast<const double2*>(src + half * 16 + c); x[c] = v.x; x[c + 1] = v.y; }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) x[c] = 0.0;
+        }
         uint32_t w[AI_S][4];
-        digits16(x + half * 16, sc, w);
+        digits16(x, sc, w);
 #pragma unroll
         for (int s = 0; s < AI_S; ++s)
             *reinterpret_cast<uint4*>(dst + (size_t)s * plane + half * 128) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
@@ -212,7 +216,7 @@ slice_v_kernel(const double* __restrict__ Vh, AttnI8Side o) { slice_v_body(Vh, o
 // Both sides of a layer in ONE launch (the forward path): 512-thread CTAs, [q/k blocks of side 0 | v blocks of side 0 |
 // q/k blocks of side 1 | v blocks of side 1]; a q/k CTA holds four 128-row blocks.
 struct SliceSide { const double *Qh, *Kh, *Vh; AttnI8Side o; int nqb, nkb, qk_ctas, v_ctas; };
-__global__ void __launch_bounds__(32 * SV_WARPS)
+__global__ void __launch_bounds__(32 * SV_WARPS, 2)
 slice_sides_kernel(const __grid_constant__ SliceSide s0, const __grid_constant__ SliceSide s1) {
     int blk = blockIdx.x;
     const bool second = blk >= s0.qk_ctas + s0.v_ctas;

@@ -66,28 +66,26 @@ DEVINL void slice_group(double (&x)[16], long long r, int kt, int Rpad, int8_t* 
     // low 32 bits are needed because |d_s| <= 64) -- and the difference runs on the integer pipe: 7 FP64 instructions per
     // element instead of 28 (the slicer was FP64-bound), rint() / F2I never touch the quarter-rate conversion pipe.
     int8_t* base = Xs + (size_t)kchunk * chunk_stride + ((size_t)tile * S) * OZ_XTILE + oz_canon(rr, kk);
-    int qprev[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) qprev[i] = 0;
-#pragma unroll
+    // q_(s-1) is recomputed rather than kept (one more FMA per digit; 16 registers less: four CTAs per SM instead of
+    // three -- the slicer is bound by the loads it keeps in flight, not by FP64 work)
+#pragma unroll 1
     for (int s = 0; s < S; ++s) {
         const double cs = pow2d(6 - e + 7 * s);              // 6 - e + 7 s <= 6 + 900 + 42 < 1023
+        const double cp = pow2d(6 - e + 7 * (s > 0 ? s - 1 : 0));
         uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int q = __double2loint(fma(x[i], cs, 6755399441055744.0));
-            const int d = q - (qprev[i] << 7);
-            qprev[i] = q;
+            const int qp = s > 0 ? __double2loint(fma(x[i], cp, 6755399441055744.0)) : 0;
+            const int d = q - (qp << 7);
             w[i >> 2] |= ((uint32_t)d & 0xffu) << (8 * (i & 3));
         }
         *reinterpret_cast<uint4*>(base + (size_t)s * OZ_XTILE) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
-// (A software-pipelined grid-stride variant -- two CTAs per SM, the next task's loads in flight during the current one --
-// was measured 5 % slower than this one-task-per-thread form.)
 template <int S>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 slice_rows_kernel(const double* __restrict__ A0, int ld0, int K0, const double* __restrict__ A1, int ld1, int K1,
                   int R, int8_t* __restrict__ Xs, double* __restrict__ rowscale, size_t chunk_stride) {
     const int K = K0 + K1, tpr = K / 16;                 // threads per row

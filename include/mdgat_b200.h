@@ -243,7 +243,9 @@ long long mdgat_launch_count(void);
 int mdgat_debug_trace(void* d_buf);
 /* Debug switches for timeline experiments (0 = normal operation). Bit 0: the Ozaki GEMM epilogue skips its global
  * stores; bit 1: it skips the float64 recombination (results are wrong while 0 or 1 is set); bit 2: the epilogue warps
- * record timeline marks too (costs registers: their timing is then not that of the production kernel). */
+ * record timeline marks too (costs registers: their timing is then not that of the production kernel).
+ * Bit 16 (0x10000, results unchanged): mdgat_forward lets the per-layer GEMMs cut their own outputs into digit planes
+ * (same as MDGAT_FUSE_SLICE=1 in the environment). */
 int mdgat_debug_flags(int flags);
 int mdgat_profile_enable(int on);
 int mdgat_profile_collect(double* ms, long long* launches, long long* segments, int n);

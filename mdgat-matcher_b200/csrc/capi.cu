@@ -277,7 +277,7 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
     // (R >= 148 row tiles). Bit-identical results; measured slower on B200 (slice stage -1.04 ms, GEMM stage +1.14 ms:
     // the FP64-bound slicing tail runs while the CTA's tensor pipe idles), so the stand-alone launches stay the default.
     static const bool fuse_env = [] { const char* e = getenv("MDGAT_FUSE_SLICE"); return e && e[0] == '1'; }();
-    const bool fuse_slice = i8 && fuse_env && ozaki_gemm_can_slice(R, DMODEL);
+    const bool fuse_slice = i8 && (fuse_env || (g_debug_flags & 0x10000) != 0) && ozaki_gemm_can_slice(R, DMODEL);   // bit 16: same switch, per call (tests)
     for (int l = 0; l < 2 * L; ++l) {
         const LayerOffsets lo = lay.layer(l);
         const bool cross = (l & 1) != 0;                  // names = ['self','cross']*L (mdgat.py:353)

@@ -362,6 +362,31 @@ def test_cfg2_full_size_properties(dev):
     assert torch.equal(outp['matching_scores1'], out['matching_scores1'][perm])
 
 
+def test_fused_output_slicing_is_bit_identical(dev):
+    """The GEMM-tail slicer (debug flag 0x10000 / MDGAT_FUSE_SLICE=1) must reproduce the stand-alone slicing launches
+    bit for bit: same digits, same exact int32 products. Needs R >= 148 row tiles, i.e. the cfg2 batch."""
+    from mdgat_matcher_b200 import synth, _capi
+    from mdgat_matcher_b200.models.mdgat import MDGAT
+    from oracle.ref_loader import net_config
+    cfg = net_config(L=9, sinkhorn_iterations=20)
+    net = MDGAT(cfg)
+    net.load_state_dict(synth.seeded_state_dict(9, 0))
+    net = net.double().eval().to(dev)
+    data = synth.make_batch(11, 32, 512)
+    outs = []
+    for flags in (0, 0x10000):
+        _capi.check(_capi.lib.mdgat_debug_flags(flags))
+        try:
+            out = net({k: v.clone().to(dev) for k, v in data.items()})
+            torch.cuda.synchronize()
+        finally:
+            _capi.check(_capi.lib.mdgat_debug_flags(0))
+        outs.append({k: out[k].cpu() for k in ('matches0', 'matches1', 'matching_scores0', 'matching_scores1', 'loss')})
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+    assert int((outs[0]['matches0'] >= 0).sum()) > 0
+
+
 # ----------------------------------------------------------------------------- test.py-style plumbing
 
 def test_reference_eval_loop_plumbing(dev):

@@ -156,16 +156,19 @@ struct OzParams {
     int dbg;                                           // debug switches (mdgat_debug_flags)
 };
 
-// One CTA = one 128-row tile x a group of 32-column tiles, warp specialised:
-//   warp 4, lane 0   producer + MMA issuer. For every k chunk it brings in the S slice planes of X (they stay for
-//                    all column tiles of the chunk), then walks the column tiles: W planes arrive through a 3-deep
-//                    ring of TMA bulk copies, the S(S+1)/2 slice products are issued into one of TWO TMEM accumulator
-//                    sets (S diagonals x 32 columns each), and tcgen05.commit hands the set to the epilogue and the
-//                    W stage back to the ring.
-//   warps 0..3       epilogue: thread = output row = TMEM lane. Horner over the diagonals (7 tcgen05.ld per 32
-//                    columns), scales, and -- k chunks being accumulated in float64 through the output buffer, each
-//                    with its own row/column scale -- bias, ReLU, residual or the q/k/v scatter after the last chunk.
-//                    While it works on one accumulator set the tensor core fills the other.
+// One CTA = one 128-row tile x a group of 32-column tiles (all of them when there are >= 148 row tiles), 18 warps:
+//   warp 17, lane 0  loader. For every k chunk one TMA bulk copy brings in the S slice planes of X (they stay for all
+//                    column tiles of the chunk); W planes arrive through a 3-deep ring of bulk copies.
+//   warp 16, lane 0  MMA issuer: per unit (k chunk, column tile) the S(S+1)/2 slice products as S stacked-N instructions
+//                    per k step into one of TWO TMEM accumulator sets (S diagonals x 32 columns each); tcgen05.commit
+//                    hands the set to the epilogue and the W stage back to the ring.
+//   warps 0..15      epilogue (see the comment there): TMEM -> int32 merges -> float64 Horner -> scales; k chunks are
+//                    accumulated in float64 through the output buffer, each with its own row/column scale; bias, ReLU,
+//                    residual or the q/k/v scatter after the last chunk. While one accumulator set is drained the
+//                    tensor core fills the other.
+// Template switches: EPI (plain / q,k,v scatter), DBG (0 production, 1 timeline probes in the loader + MMA threads,
+// 2 probes and debug switches in the epilogue too), FULL (row count a multiple of 128: no row checks), GROUPS (1: all
+// 16 epilogue warps on every unit, 2: warps 0-7 on even units / set 0, warps 8-15 on odd units / set 1).
 template <int S, int EPI, int DBG, bool FULL, int GROUPS>
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_constant__ OzParams p) {
     extern __shared__ __align__(128) unsigned char oz_smem[];

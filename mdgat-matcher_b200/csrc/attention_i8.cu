@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
 
     if (warp == EPI_WARPS + 1) {
         // ------------------------------------------------------------------ loader
-        if (lane == 0) {
+        if (elect_one()) {
             const int8_t* gQ = Qd.Qs + ((size_t)bh * (Npad / AI_BM) + qt) * (AI_S * AI_QPLANE);
             const unsigned sc_bytes = (unsigned)(Mpad * 8 + Mpad * 4 + ((T + 3) & ~3) * 4);
             mbar_expect_tx(&q_full, AI_S * AI_QPLANE + sc_bytes);
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
         }
     } else if (warp == EPI_WARPS) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {
             const uint64_t qd0 = ai_desc(sQ), kd0 = ai_desc(sKV), pd0 = ai_desc(sP);
             mbar_wait(&q_full, 0);
             int u = 0;

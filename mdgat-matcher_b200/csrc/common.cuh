@@ -71,6 +71,15 @@ DEVINL void bulk_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar
                  :: "r"(d), "l"(gmem), "r"(bytes), "r"(b) : "memory");
 }
 
+// One lane of a converged warp. Single-thread roles (TMA producer, tcgen05.mma issuer) must be entered through this and not
+// through `lane == 0`: with a lane test the compiler wraps every uniform-datapath instruction (UTCIMMA, UBLKCP, ..) in
+// its own ELECT / BRA.U.ANY retry loop (11 instructions between two MMAs instead of 2-4).
+DEVINL bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- timeline probe (debug): one CTA records (tag, clock64) pairs per role into a global buffer set with
 // mdgat_debug_trace() and handed to the kernels as a parameter; a null buffer (the default) costs one predicate per probe.
 constexpr int TRACE_CAP = 1024;                 // records per role

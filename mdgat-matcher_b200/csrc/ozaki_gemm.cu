@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
 
     if (warp == OZ_EPI_WARPS + 1) {
         // ------------------------------------------------------------------ loader: TMA bulk copies, runs ahead
-        if ((tid & 31) == 0 && units > 0) {
+        if (elect_one() && units > 0) {
             // (kc, ctl, stage, ring phase) are walked incrementally: a division by the runtime nct costs this single
             // thread ~100 cycles of dependent instructions per unit
             int kc = 0, ctl = 0, stage = 0; unsigned wphase = 1;       // wphase: parity of the ring pass before this one
@@ -236,7 +236,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
         }
     } else if (warp == OZ_EPI_WARPS) {
         // ------------------------------------------------------------------ MMA issuer: one thread, never waits on loads it issued
-        if ((tid & 31) == 0 && units > 0) {
+        // (elected with elect.sync: with a `lane == 0` test the compiler wraps every tcgen05.mma in its own
+        // ELECT / BRA.U.ANY retry loop -- 11 instructions between two MMAs instead of 4)
+        if (elect_one() && units > 0) {
             // Stacked-N issue. The S weight planes of a column tile sit back to back in shared memory, i.e. they form ONE
             // K-major operand of S*32 rows. Multiplying activation plane s by planes 0..S-1-s in a single MMA of
             // N = (S-s)*32 and writing it 32*s columns into the accumulator set drops product (s, t) onto diagonal

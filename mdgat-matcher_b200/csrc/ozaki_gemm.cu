@@ -149,6 +149,8 @@ struct OzParams {
     int epi;                                           // EPI_PLAIN / EPI_QKV
     double *Qh, *Kh, *Vh; int rows0, n0, n1;
     int col_tiles_per_cta;                             // blockIdx.y selects a group of column tiles
+    int items_per_cta;                                 // > 0: persistent mode, CTA c walks the (row tile, column tile) items
+                                                       // [c * items_per_cta, (c + 1) * items_per_cta) in row-major order
     // fused slicing of the output (EPI_PLAIN, CTA owns whole rows of Y): the digit planes of this CTA's 128 x Nout tile of Y,
     // i.e. the operand of the next GEMM, in the layout launch_slice_rows() writes; null = off
     int8_t* slice_out; double* slice_scale; unsigned long long slice_chunk_stride;
@@ -178,13 +180,22 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) double s_cs[2 * OZ_MAXN], s_bias[OZ_MAXN];             // column scales per k chunk, bias
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int row_tile = blockIdx.x;
     const int nkc = p.K / OZ_KC;
     const int Rpad = ((p.R + OZ_BM - 1) / OZ_BM) * OZ_BM;
-    const int ct_begin = blockIdx.y * p.col_tiles_per_cta;
-    const int ct_end = min(p.Nout / OZ_BN, ct_begin + p.col_tiles_per_cta);
-    const int nct = ct_end - ct_begin;
-    const int units = nkc * nct;                                     // unit u = (kc = u / nct, ct = ct_begin + u % nct)
+    // Work of this CTA: a range of (row tile, column tile) items in row-major order, cut into segments that stay inside
+    // one row tile. Classic mode: one segment (row tile blockIdx.x, column tiles of group blockIdx.y). Persistent mode
+    // (one CTA per SM, items_per_cta > 0): up to three segments, which balances the SMs when the row tiles are not a
+    // multiple of the SM count (256 row tiles on 148 SMs: 2 waves of which the second is 73 % full).
+    const int nct_all = p.Nout / OZ_BN;
+    int item_begin, item_end;
+    if (p.items_per_cta > 0) {
+        item_begin = blockIdx.x * p.items_per_cta;
+        item_end = min(((p.R + OZ_BM - 1) / OZ_BM) * nct_all, item_begin + p.items_per_cta);
+    } else {
+        const int cb = blockIdx.y * p.col_tiles_per_cta;
+        item_begin = blockIdx.x * nct_all + cb;
+        item_end = blockIdx.x * nct_all + min(nct_all, cb + p.col_tiles_per_cta);
+    }
 
     if (tid == 0) {
         mbar_init(&x_full, 1); mbar_init(&x_free, 1);
@@ -211,34 +222,42 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
 
     if (warp == OZ_EPI_WARPS + 1) {
         // ------------------------------------------------------------------ loader: TMA bulk copies, runs ahead
-        if (elect_one() && units > 0) {
+        if (elect_one()) {
             // (kc, ctl, stage, ring phase) are walked incrementally: a division by the runtime nct costs this single
-            // thread ~100 cycles of dependent instructions per unit
-            int kc = 0, ctl = 0, stage = 0; unsigned wphase = 1;       // wphase: parity of the ring pass before this one
-            for (int u = 0; u < units; ++u) {
-                const int ct = ct_begin + ctl;
-                if (DBG && !(p.dbg & 256)) tr.mark(1000 + u);
-                if (ctl == 0) {
-                    if (kc > 0) mbar_wait(&x_free, (unsigned)((kc - 1) & 1));        // MMAs of the previous chunk are done with sX
-                    mbar_expect_tx(&x_full, S * OZ_XTILE);
-                    // the S planes of a row tile are contiguous in global and in shared memory: one bulk copy
-                    const int8_t* xsrc = (kc == 0 ? p.Xs[0] : p.Xs[1]) + ((size_t)row_tile * S) * OZ_XTILE;
-                    bulk_g2s(sX, xsrc, S * OZ_XTILE, &x_full);
+            // thread ~100 cycles of dependent instructions per unit. ug / xl count units and X chunk loads over all
+            // segments of the CTA (barrier phases run on).
+            int stage = 0, ug = 0, xl = 0; unsigned wphase = 1;       // wphase: parity of the ring pass before this one
+            for (int it = item_begin; it < item_end;) {
+                const int row_tile = it / nct_all, ct_begin = it - row_tile * nct_all;
+                const int nct = min(nct_all - ct_begin, item_end - it), units = nkc * nct;
+                it += nct;
+                int kc = 0, ctl = 0;
+                for (int u = 0; u < units; ++u, ++ug) {
+                    const int ct = ct_begin + ctl;
+                    if (DBG && !(p.dbg & 256)) tr.mark(1000 + ug);
+                    if (ctl == 0) {
+                        if (xl > 0) mbar_wait(&x_free, (unsigned)((xl - 1) & 1));    // MMAs of the previous chunk are done with sX
+                        ++xl;
+                        mbar_expect_tx(&x_full, S * OZ_XTILE);
+                        // the S planes of a row tile are contiguous in global and in shared memory: one bulk copy
+                        const int8_t* xsrc = (kc == 0 ? p.Xs[0] : p.Xs[1]) + ((size_t)row_tile * S) * OZ_XTILE;
+                        bulk_g2s(sX, xsrc, S * OZ_XTILE, &x_full);
+                    }
+                    if (ug >= OZ_WSTAGES) mbar_wait(&w_empty[stage], wphase);
+                    mbar_expect_tx(&w_full[stage], S * OZ_WTILE);
+                    const int8_t* wsrc = p.Ws + ((size_t)(ct * nkc + kc) * S) * OZ_WTILE;
+                    bulk_g2s(sW + (size_t)stage * S * OZ_WTILE, wsrc, S * OZ_WTILE, &w_full[stage]);
+                    if (DBG && !(p.dbg & 512)) tr.mark(2000 + ug);
+                    if (++ctl == nct) { ctl = 0; ++kc; }
+                    if (++stage == OZ_WSTAGES) { stage = 0; wphase ^= 1u; }
                 }
-                if (u >= OZ_WSTAGES) mbar_wait(&w_empty[stage], wphase);
-                mbar_expect_tx(&w_full[stage], S * OZ_WTILE);
-                const int8_t* wsrc = p.Ws + ((size_t)(ct * nkc + kc) * S) * OZ_WTILE;
-                bulk_g2s(sW + (size_t)stage * S * OZ_WTILE, wsrc, S * OZ_WTILE, &w_full[stage]);
-                if (DBG && !(p.dbg & 512)) tr.mark(2000 + u);
-                if (++ctl == nct) { ctl = 0; ++kc; }
-                if (++stage == OZ_WSTAGES) { stage = 0; wphase ^= 1u; }
             }
         }
     } else if (warp == OZ_EPI_WARPS) {
         // ------------------------------------------------------------------ MMA issuer: one thread, never waits on loads it issued
         // (elected with elect.sync: with a `lane == 0` test the compiler wraps every tcgen05.mma in its own
         // ELECT / BRA.U.ANY retry loop -- 11 instructions between two MMAs instead of 4)
-        if (elect_one() && units > 0) {
+        if (elect_one()) {
             // Stacked-N issue. The S weight planes of a column tile sit back to back in shared memory, i.e. they form ONE
             // K-major operand of S*32 rows. Multiplying activation plane s by planes 0..S-1-s in a single MMA of
             // N = (S-s)*32 and writing it 32*s columns into the accumulator set drops product (s, t) onto diagonal
@@ -246,11 +265,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             // S(S+1)/2 narrow ones. A 128x32x32 MMA takes 45 cycles on this part (operand fetch bound, 16 in
             // theory), a 128xNx32 one N/2 cycles from N = 128 up (tools/ubench/umma_i8_rate.cu).
             const uint64_t xd0 = umma_desc(sX, 128, OZ_KC * 8), wd0 = umma_desc(sW, 128, OZ_KC * 8);
-            int kc = 0, ctl = 0, stage = 0; unsigned wphase = 0;
-            for (int u = 0; u < units; ++u) {
+            int stage = 0, ug = 0, xl = 0; unsigned wphase = 0;
+            for (int it = item_begin; it < item_end;) {
+              const int ct_begin = it % nct_all;
+              const int nct = min(nct_all - ct_begin, item_end - it), units = nkc * nct;
+              it += nct;
+              int ctl = 0;
+              for (int uu = 0; uu < units; ++uu, ++ug) {
+                const int u = ug;                                    // global unit index of this CTA
                 const int set = u & 1;
                 if (DBG && !(p.dbg & 1024)) tr.mark(3000 + u);
-                if (ctl == 0) mbar_wait(&x_full, (unsigned)(kc & 1));
+                if (ctl == 0) { mbar_wait(&x_full, (unsigned)(xl & 1)); ++xl; }
                 mbar_wait(&w_full[stage], wphase);
                 if (DBG && !(p.dbg & 2048)) tr.mark(4000 + u);
                 if (u >= 2) mbar_wait(&tm_empty[set], (unsigned)((u / 2 - 1) & 1));   // epilogue drained this accumulator set
@@ -275,8 +300,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 umma_commit(&w_empty[stage]);               // W stage free once these MMAs have read it
                 if (ctl == nct - 1) umma_commit(&x_free);
                 if (DBG && !(p.dbg & 8192)) tr.mark(6000 + u);
-                if (++ctl == nct) { ctl = 0; ++kc; }
+                if (++ctl == nct) ctl = 0;
                 if (++stage == OZ_WSTAGES) { stage = 0; wphase ^= 1u; }
+              }
             }
         }
     } else {
@@ -294,6 +320,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
         constexpr int PASSES = GROUPS;
         const int lane = tid & 31, grp = GROUPS == 2 ? warp >> 3 : 0, wl = GROUPS == 2 ? warp & 7 : warp;
         const int quarter = wl & 3, cg0 = (wl >> 2) * PASSES;
+        constexpr int G = (S + 1) / 2;                               // digit groups: S odd: {0}, {1,2}, {3,4}, ..; S even: {0,1}, {2,3}, ..
+        const double MAGIC = 6755399441055744.0;                     // 1.5 * 2^52
+        const bool res_first = p.Res && !p.relu;
+        const bool one_chunk = nkc == 1;
+        const int* s_cs_hi = reinterpret_cast<const int*>(s_cs) + 1; // high words of the column scales (exact powers of two)
+        int ug_base = 0;                                             // units of the segments before this one (accumulator set / phase)
+      for (int it = item_begin; it < item_end;) {
+        const int row_tile = it / nct_all, ct_begin = it - row_tile * nct_all;
+        const int nct = min(nct_all - ct_begin, item_end - it), units = nkc * nct;
+        it += nct;
         const int rbase = row_tile * OZ_BM + quarter * 32 + (lane >> 2);   // rows rbase + 8 i, i = 0..3
         int hrow[EPI == EPI_QKV ? 4 : 1], npts[EPI == EPI_QKV ? 4 : 1];      // head-major row of the point, points per set
         if (EPI == EPI_QKV) {
@@ -308,16 +344,14 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 }
             }
         }
-        constexpr int G = (S + 1) / 2;                               // digit groups: S odd: {0}, {1,2}, {3,4}, ..; S even: {0,1}, {2,3}, ..
-        const double MAGIC = 6755399441055744.0;                     // 1.5 * 2^52
-        const bool res_first = p.Res && !p.relu;
-        const bool one_chunk = nkc == 1;
-        const int* s_cs_hi = reinterpret_cast<const int*>(s_cs) + 1; // high words of the column scales (exact powers of two)
         // element offsets fit 32 bits (checked by the launcher): one IMAD per address instead of 64-bit chains
         const int yrow = rbase * p.ldy, ystep = 8 * p.ldy, rrow = rbase * p.ldres, rstep = 8 * p.ldres;
-        int kc = 0, ctl = grp;                                       // unit u = (kc, ct_begin + ctl), walked incrementally
-        for (int u = grp; u < units; u += GROUPS, ctl += GROUPS) {
+        // this group's units of the segment: those whose CTA-wide index ug_base + us has the group's parity
+        const int us0 = GROUPS == 2 ? ((grp - ug_base) & 1) : 0;
+        int kc = 0, ctl = us0;                                       // unit (kc, ct_begin + ctl), walked incrementally
+        for (int us = us0; us < units; us += GROUPS, ctl += GROUPS) {
             while (ctl >= nct) { ctl -= nct; ++kc; }
+            const int u = ug_base + us;                              // CTA-wide unit index
             const int set = u & 1;
             const bool first = kc == 0, last = kc == nkc - 1;
             int rsh[4];                                              // rsh: high word of the row scale 2^(e-12)
@@ -441,7 +475,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             }
           }
         }
+        ug_base += units;
+      }
         if (EPI == EPI_PLAIN && p.slice_out != nullptr) {
+            const int row_tile = blockIdx.x;                         // classic mode only (checked by the launcher)
             // Tail: the digit planes of this CTA's rows of Y for the next GEMM. The rows were written by other warps of
             // this CTA: the named barrier orders those stores before the loads below (same SM, coherent L1).
             asm volatile("bar.sync 1, %0;" :: "n"(OZ_EPI_THREADS) : "memory");
@@ -579,7 +616,9 @@ static cudaError_t ozaki_gemm_tf(const OzParams& p, dim3 grid, cudaStream_t st) 
     static const int groups = [] { const char* e = getenv("MDGAT_OZ_GROUPS"); return e && e[0] == '1' ? 1 : 2; }();
     // two groups need the k chunks of a column tile in the same group (the partial sum is read back by the thread
     // that wrote it): one chunk, or an even number of column tiles per CTA
-    const bool ok2 = p.K == OZ_KC || (p.col_tiles_per_cta % 2) == 0;
+    // (persistent mode: every segment of a CTA has an even number of column tiles iff items_per_cta and the column
+    // tile count are even)
+    const bool ok2 = p.K == OZ_KC || ((p.col_tiles_per_cta % 2) == 0 && (p.items_per_cta % 2) == 0);
     return groups == 2 && ok2 ? ozaki_gemm_tg<S, EPI, DBG, FULL, 2>(p, grid, st) : ozaki_gemm_tg<S, EPI, DBG, FULL, 1>(p, grid, st);
 }
 template <int S, int EPI, int DBG>
@@ -618,6 +657,16 @@ cudaError_t launch_ozaki_gemm(const OzGemmArgs& a, int S, cudaStream_t st) {
     p.col_tiles_per_cta = (col_tiles + groups - 1) / groups;
     dim3 grid(row_tiles, (col_tiles + p.col_tiles_per_cta - 1) / p.col_tiles_per_cta);
     if (a.slice_out != nullptr && (grid.y != 1 || a.epi != EPI_PLAIN || (a.Nout % OZ_KC) != 0)) return cudaErrorInvalidValue;   // see ozaki_gemm_can_slice
+    // Persistent mode: more row tiles than SMs but not a multiple of them -> one CTA per SM walks an equal share of the
+    // (row tile, column tile) items (MDGAT_OZ_PERSISTENT=0 keeps one CTA per row tile).
+    p.items_per_cta = 0;
+    static const bool persistent_env = [] { const char* e = getenv("MDGAT_OZ_PERSISTENT"); return !(e && e[0] == '0'); }();
+    static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+    if (persistent_env && grid.y == 1 && row_tiles > sms && (row_tiles % sms) != 0 && a.slice_out == nullptr) {
+        const int total = row_tiles * col_tiles;
+        p.items_per_cta = (total + sms - 1) / sms;
+        grid = dim3((total + p.items_per_cta - 1) / p.items_per_cta, 1);
+    }
     cudaError_t e;
     switch (S) {
         case 6: e = ozaki_gemm_t<6>(p, grid, st); break;

@@ -176,7 +176,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
     extern __shared__ __align__(128) unsigned char oz_smem[];
     int8_t* sX = reinterpret_cast<int8_t*>(oz_smem);                 // [S][128*128]
     int8_t* sW = sX + (size_t)S * OZ_XTILE;                          // [OZ_WSTAGES][S][32*128]
-    __shared__ __align__(8) uint64_t x_full, x_free, w_full[OZ_WSTAGES], w_empty[OZ_WSTAGES], tm_full[2], tm_empty[2];
+    // x_full / x_free are per slice plane: the first unit of a k chunk starts on plane 0 while planes 1.. are still in
+    // flight, and the last unit hands the planes back one by one so that the next chunk's reload overlaps its MMAs
+    __shared__ __align__(8) uint64_t x_full[S], x_free[S], w_full[OZ_WSTAGES], w_empty[OZ_WSTAGES], tm_full[2], tm_empty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) double s_cs[2 * OZ_MAXN], s_bias[OZ_MAXN];             // column scales per k chunk, bias
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -198,7 +200,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
     }
 
     if (tid == 0) {
-        mbar_init(&x_full, 1); mbar_init(&x_free, 1);
+#pragma unroll
+        for (int i = 0; i < S; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_free[i], 1); }
 #pragma unroll
         for (int i = 0; i < OZ_WSTAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
 #pragma unroll
@@ -235,18 +238,21 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 for (int u = 0; u < units; ++u, ++ug) {
                     const int ct = ct_begin + ctl;
                     if (DBG && !(p.dbg & 256)) tr.mark(1000 + ug);
-                    if (ctl == 0) {
-                        if (xl > 0) mbar_wait(&x_free, (unsigned)((xl - 1) & 1));    // MMAs of the previous chunk are done with sX
-                        ++xl;
-                        mbar_expect_tx(&x_full, S * OZ_XTILE);
-                        // the S planes of a row tile are contiguous in global and in shared memory: one bulk copy
-                        const int8_t* xsrc = (kc == 0 ? p.Xs[0] : p.Xs[1]) + ((size_t)row_tile * S) * OZ_XTILE;
-                        bulk_g2s(sX, xsrc, S * OZ_XTILE, &x_full);
-                    }
+                    // the W tile first: the X planes below may have to wait for the previous chunk's last MMAs
                     if (ug >= OZ_WSTAGES) mbar_wait(&w_empty[stage], wphase);
                     mbar_expect_tx(&w_full[stage], S * OZ_WTILE);
                     const int8_t* wsrc = p.Ws + ((size_t)(ct * nkc + kc) * S) * OZ_WTILE;
                     bulk_g2s(sW + (size_t)stage * S * OZ_WTILE, wsrc, S * OZ_WTILE, &w_full[stage]);
+                    if (ctl == 0) {
+                        const int8_t* xsrc = (kc == 0 ? p.Xs[0] : p.Xs[1]) + ((size_t)row_tile * S) * OZ_XTILE;
+#pragma unroll
+                        for (int sp = 0; sp < S; ++sp) {
+                            if (xl > 0) mbar_wait(&x_free[sp], (unsigned)((xl - 1) & 1));   // last MMA reading this plane is done
+                            mbar_expect_tx(&x_full[sp], OZ_XTILE);
+                            bulk_g2s(sX + (size_t)sp * OZ_XTILE, xsrc + (size_t)sp * OZ_XTILE, OZ_XTILE, &x_full[sp]);
+                        }
+                        ++xl;
+                    }
                     if (DBG && !(p.dbg & 512)) tr.mark(2000 + ug);
                     if (++ctl == nct) { ctl = 0; ++kc; }
                     if (++stage == OZ_WSTAGES) { stage = 0; wphase ^= 1u; }
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 const int u = ug;                                    // global unit index of this CTA
                 const int set = u & 1;
                 if (DBG && !(p.dbg & 1024)) tr.mark(3000 + u);
-                if (ctl == 0) { mbar_wait(&x_full, (unsigned)(xl & 1)); ++xl; }
+                const bool first_of_chunk = ctl == 0, last_of_chunk = ctl == nct - 1;
                 mbar_wait(&w_full[stage], wphase);
                 if (DBG && !(p.dbg & 2048)) tr.mark(4000 + u);
                 if (u >= 2) mbar_wait(&tm_empty[set], (unsigned)((u / 2 - 1) & 1));   // epilogue drained this accumulator set
@@ -283,22 +289,35 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint64_t wdu = wd0 + (uint64_t)((stage * S * OZ_WTILE) >> 4);
                 const uint32_t dbase = tmem + set * TM_SET;
-#pragma unroll
-                for (int kk = 0; kk < OZ_KC / 32; ++kk) {
+                // D = s32, A = B = signed int8, both K-major, M = 128, N = (S - s) * 32
+                auto issue = [&](int s, int kk) {
+                    constexpr uint32_t ibase = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
+                    const uint32_t idesc = ibase | ((uint32_t)(((S - s) * OZ_BN) >> 3) << 17);
+                    const uint64_t da = xd0 + (uint64_t)((s * OZ_XTILE + kk * 256) >> 4);
+                    const uint64_t db = wdu + (uint64_t)((kk * 256) >> 4);
+                    if (s > 0 || kk > 0) umma_i8<true>(dbase + s * OZ_BN, da, db, idesc);
+                    else umma_i8<false>(dbase, da, db, idesc);
+                };
+                if (first_of_chunk || last_of_chunk) {
+                    // plane-major order: plane s is needed only once planes < s are done (first unit of a chunk: the
+                    // planes arrive one after the other) and is handed back as soon as its four k steps are issued
+                    // (last unit: the loader refills it while the remaining planes are multiplied)
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
-                        // D = s32, A = B = signed int8, both K-major, M = 128, N = (S - s) * 32
-                        constexpr uint32_t ibase = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
-                        const uint32_t idesc = ibase | ((uint32_t)(((S - s) * OZ_BN) >> 3) << 17);
-                        const uint64_t da = xd0 + (uint64_t)((s * OZ_XTILE + kk * 256) >> 4);
-                        const uint64_t db = wdu + (uint64_t)((kk * 256) >> 4);
-                        if (s > 0 || kk > 0) umma_i8<true>(dbase + s * OZ_BN, da, db, idesc);
-                        else umma_i8<false>(dbase, da, db, idesc);
+                        if (first_of_chunk) mbar_wait(&x_full[s], (unsigned)(xl & 1));
+#pragma unroll
+                        for (int kk = 0; kk < OZ_KC / 32; ++kk) issue(s, kk);
+                        if (last_of_chunk) umma_commit(&x_free[s]);
                     }
+                    if (first_of_chunk) ++xl;
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < OZ_KC / 32; ++kk)
+#pragma unroll
+                        for (int s = 0; s < S; ++s) issue(s, kk);
                 }
                 umma_commit(&tm_full[set]);                 // accumulator set ready for the epilogue
                 umma_commit(&w_empty[stage]);               // W stage free once these MMAs have read it
-                if (ctl == nct - 1) umma_commit(&x_free);
                 if (DBG && !(p.dbg & 8192)) tr.mark(6000 + u);
                 if (++ctl == nct) ctl = 0;
                 if (++stage == OZ_WSTAGES) { stage = 0; wphase ^= 1u; }

@@ -85,7 +85,7 @@ DEVINL void slice_group(double (&x)[16], long long r, int kt, int Rpad, int8_t* 
 }
 
 template <int S>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(128, 8)
 slice_rows_kernel(const double* __restrict__ A0, int ld0, int K0, const double* __restrict__ A1, int ld1, int K1,
                   int R, int8_t* __restrict__ Xs, double* __restrict__ rowscale, size_t chunk_stride) {
     const int K = K0 + K1, tpr = K / 16;                 // threads per row
@@ -601,7 +601,7 @@ static cudaError_t slice_rows_t(const double* A0, int ld0, int K0, const double*
     const int K = K0 + K1;
     const long long Rpad = (long long)((R + OZ_BM - 1) / OZ_BM) * OZ_BM;
     const long long threads = Rpad * (K / 16);
-    slice_rows_kernel<S><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale, chunk_stride);
+    slice_rows_kernel<S><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale, chunk_stride);
     return cudaGetLastError();
 }
 

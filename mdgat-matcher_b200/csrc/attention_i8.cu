@@ -305,8 +305,8 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
     double* s_ksd = reinterpret_cast<double*>(sP + 2 * AI_SP * AI_PPLANE);        // [Mpad]
     float* s_ksf = reinterpret_cast<float*>(s_ksd + Mpad);                        // [Mpad]
     float* s_ktm = s_ksf + Mpad;                                                  // [T] (padded to 4)
-    double* etab = reinterpret_cast<double*>(s_ktm + ((T + 3) & ~3));             // [64]
-    double* s_xd = etab + 64;                                                     // [4][128] row exchange between column groups
+    double* etab = reinterpret_cast<double*>(s_ktm + ((T + 3) & ~3));             // [256] 2^(j/256)
+    double* s_xd = etab + 256;                                                     // [4][128] row exchange between column groups
     unsigned long long* s_xu = reinterpret_cast<unsigned long long*>(s_xd + 512); // [4][128]
 
     __shared__ __align__(8) uint64_t q_full, kv_full[AI_STAGES], kv_empty[AI_STAGES], s1_full[2], s1_empty[2],
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
         mbar_init(&s_full, 1); mbar_init(&s_empty, AI_EPI_THREADS); mbar_init(&o_full, 1);
         mbar_fence_init();
     }
-    exp_table_to_shared(etab);
+    exp_table256_to_shared(etab);
     if (warp == EPI_WARPS) {
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_s);
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(dst));
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
             uint32_t lo[CW], hi[CW];
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
-                const double pj = exp_fast_neg(fma(z[j], r_i, -c_i), etab);      // <= 1
+                const double pj = exp_neg_abs47(fma(z[j], r_i, -c_i), etab);     // <= 1
                 const double pm = fma(pj, 140737488355328.0, 6755399441055744.0);   // p 2^47 rounded into the mantissa
                 lo[j] = (uint32_t)__double2loint(pm);
                 hi[j] = (uint32_t)__double2hiint(pm) & 0xffffu;                  // bits 32..47 of p^
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
 static size_t attn_i8_smem(int M) {
     const int T = (M + AI_BN - 1) / AI_BN, Mpad = T * AI_BN;
     return (size_t)AI_S * AI_QPLANE + (size_t)AI_STAGES * AI_STAGE_BYTES + 2 * AI_SP * AI_PPLANE +
-           (size_t)Mpad * 12 + (size_t)((T + 3) & ~3) * 4 + 64 * 8 + 512 * 8 + 512 * 8;
+           (size_t)Mpad * 12 + (size_t)((T + 3) & ~3) * 4 + 256 * 8 + 512 * 8 + 512 * 8;
 }
 
 bool attn_i8_supported(int N, int M) { return N > 0 && M > 0 && attn_i8_smem(M) <= 200 * 1024; }

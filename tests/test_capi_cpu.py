@@ -132,3 +132,43 @@ def test_eval_forward_refuses_cpu_tensors_and_train_path_matches_oracle():
     out = net({k: v.clone() for k, v in data.items()})
     out['loss'].backward()
     assert net.final_proj.weight.grad is not None and torch.isfinite(net.final_proj.weight.grad).all()
+
+
+def test_slice_weight_digit_planes_are_exact_and_in_layout():
+    """packing.slice_weight (operand of the tcgen05 int8 GEMM, csrc/ozaki_gemm.cu): digits |g| <= 64, 2^f * sum_s g_s 2^(1-7s)
+    reproduces every weight to 2^-49 of its row-chunk maximum, colscale is an exact power of two, and the bytes sit in the
+    UMMA canonical no-swizzle K-major order [col tile][k chunk][slice][(r/8)*1024 + (k/16)*128 + (r%8)*16 + k%16]."""
+    from mdgat_matcher_b200 import packing
+    g = torch.Generator().manual_seed(3)
+    nout, k, S = 64, 256, 7
+    w = torch.randn(nout, k, generator=g, dtype=torch.float64) * torch.exp(torch.randn(nout, 1, generator=g, dtype=torch.float64) * 3)
+    w[5] = 0.0                                                     # an all-zero row keeps scale 1 and zero digits
+    w[:, ::9] *= 1e-7
+    planes, cs = packing.slice_weight(w, S)
+    assert planes.dtype == torch.int8 and planes.numel() == (nout // 32) * (k // 128) * S * 32 * 128
+    assert cs.shape == (k // 128, nout)
+    m, e = torch.frexp(cs)
+    assert torch.all(m == 0.5), 'colscale must be a power of two'
+    d = planes.reshape(nout // 32, k // 128, S, 4, 8, 8, 16).to(torch.float64)      # [ct][kc][s][r/8][k/16][r%8][k%16]
+    assert float(d.abs().max()) <= 64
+    d = d.permute(0, 3, 5, 1, 4, 6, 2).reshape(nout, k, S)                            # [row][k][s]
+    weights = torch.tensor([2.0 ** (1 - 7 * (s + 1)) for s in range(S)], dtype=torch.float64)
+    scale = cs.t().repeat_interleave(128, dim=1)                                     # [row][k]
+    rec = (d * weights).sum(-1) * scale
+    rowmax = w.reshape(nout, k // 128, 128).abs().amax(-1).repeat_interleave(128, dim=1)
+    err = (rec - w).abs()
+    assert torch.all(err <= rowmax * 2.0 ** -48 + 0.0), float((err / rowmax.clamp_min(1e-300)).max())
+    assert float(rec[5].abs().max()) == 0.0
+
+
+def test_i8_blob_layout_matches_the_forward_offsets():
+    """pack_state_dict_i8: per layer 36 slice tiles (12 q/k/v + 16 MLP conv 0 + 8 MLP conv 3, k chunks included) followed by
+    1152 column scales -- the offsets mdgat_forward() hard-codes (capi.cu)."""
+    from mdgat_matcher_b200 import packing, synth
+    L, S = 2, 7
+    blob = packing.pack_state_dict_i8(synth.seeded_state_dict(L, 0), L, S)
+    per_layer = S * 32 * 128 * 36 + 1152 * 8
+    assert blob.dtype == torch.uint8 and blob.numel() == 2 * L * per_layer == 2 * L * packing.i8_layer_bytes(S)
+    cs = blob[S * 32 * 128 * 36: per_layer].view(torch.float64)
+    m, _ = torch.frexp(cs)
+    assert torch.all(m == 0.5)

@@ -387,6 +387,22 @@ def test_fused_output_slicing_is_bit_identical(dev):
     assert int((outs[0]['matches0'] >= 0).sum()) > 0
 
 
+def test_persistent_gemm_schedule_is_bit_identical(dev, tmp_path):
+    """One CTA per SM walking several row-tile segments (MDGAT_OZ_PERSISTENT=1, default) against one CTA per row tile
+    (=0) at 640 row tiles: the schedules must agree bit for bit. The switch is read once per process, hence two runs."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = []
+    for v in ('0', '1'):
+        f = str(tmp_path / ('p%s.npz' % v))
+        env = dict(os.environ, MDGAT_OZ_PERSISTENT=v)
+        subprocess.run([sys.executable, os.path.join(root, 'tools', 'check_persistent.py'), f, '20', '2048'], check=True, env=env, timeout=600)
+        files.append(np.load(f))
+    for k in files[0].files:
+        assert np.array_equal(files[0][k], files[1][k]), k
+    assert int((files[0]['matches0'] >= 0).sum()) > 0
+
+
 # ----------------------------------------------------------------------------- test.py-style plumbing
 
 def test_reference_eval_loop_plumbing(dev):

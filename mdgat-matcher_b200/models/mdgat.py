@@ -6,17 +6,74 @@ shipped checkpoint loads with strict=True through DataParallel), and forward(dic
 returns matches0/1 (int64, -1 = unmatched), matching_scores0/1 (float64) and loss.
 
 eval mode  -> hand-written CUDA path through the C ABI (include/mdgat_b200.h); CUDA tensors
-              only, no CPU or eager fallback.
+              only, no CPU or eager fallback. Its outputs carry no autograd graph (the reference's
+              scripts run eval under torch.no_grad(): test.py:182, train.py:263); for eval-mode
+              calls that must be differentiable (frozen-BatchNorm fine-tuning) construct the module
+              with config['eval_autograd'] = True, which routes them through the torch path below
+              whenever autograd is enabled.
 train mode -> a differentiable torch restatement (train.py needs autograd and batch-statistics
               BatchNorm); same math, library kernels.
 """
 import ctypes
+import threading
 from copy import deepcopy
 
 import torch
 from torch import nn
 
 from .. import packing, losses
+
+
+class _PackedWeights:
+    """Packed-weight cache of one MDGAT module, shared BY REFERENCE with its nn.DataParallel replicas (a replica is a
+    shallow copy of the module, /root/reference/test.py:158, train.py:196).
+
+    The blobs are built on the host (packing.py) from the SOURCE module's parameters and copied to each device once per
+    weight version. A replica never packs: DataParallel hands it freshly broadcast parameter copies on every forward
+    (equal to the source's by construction, with new storage each time, and -- when autograd is on -- not even
+    registered as parameters), so it asks this cache for the blob of its device instead."""
+
+    def __init__(self):
+        self.lock = threading.Lock()          # DataParallel runs the replicas' forwards on threads
+        self.key = None
+        self.host = None                      # float64 CPU blob
+        self.host_i8 = {}                     # slices -> uint8 CPU blob
+        self.dev = {}                         # (device, 'f64' | slices) -> device tensor
+
+    def invalidate(self):
+        with self.lock:
+            self.key, self.host, self.host_i8, self.dev = None, None, {}, {}
+
+    def refresh(self, module):
+        """Re-keys against the source module's parameters; drops everything when they changed."""
+        key = module._weights_key()
+        with self.lock:
+            if key != self.key:
+                self.key, self.host, self.host_i8, self.dev = key, None, {}, {}
+
+    def blob(self, module, device, slices=None):
+        """Device blob (float64 blob for slices=None, else the int8 digit-plane blob); `module` supplies the state dict
+        when the host copy has to be (re)built, i.e. it must be the source module the first time."""
+        tag = (torch.device(device), 'f64' if slices is None else int(slices))
+        with self.lock:
+            t = self.dev.get(tag)
+            if t is not None:
+                return t
+            host = self.host if slices is None else self.host_i8.get(int(slices))
+            if host is None:
+                sd = module.state_dict(keep_vars=True)
+                if 'bin_score' not in sd:
+                    raise RuntimeError('mdgat-matcher_b200: this DataParallel replica was asked to pack weights before '
+                                       'its source module did; call the source module (or net.module.packed_weights()) first')
+                with torch.no_grad():
+                    if slices is None:
+                        host = self.host = packing.pack_state_dict(sd, module.config['L'])
+                    else:
+                        host = self.host_i8[int(slices)] = packing.pack_state_dict_i8(sd, module.config['L'], int(slices))
+            t = host.to(tag[0])
+            self.dev[tag] = t
+            return t
+
 
 _DESCRIPTORS_OUT_OF_SCOPE = ('pointnet', 'pointnetmsg', 'FPFH_gloabal', 'FPFH_only')
 
@@ -197,9 +254,9 @@ class MDGAT(nn.Module):
         self.mutual_check = config['mutual_check']
         self.triplet_loss_gamma = config['triplet_loss_gamma']
         self.train_step = config['train_step']
-        self._packed = None          # (key, blob)
-        self._packed_i8 = None       # (key, slices, int8 blob) for the tcgen05 GEMM mode
-        self._workspace = None       # uint8 tensor
+        self._pack_cache = _PackedWeights()     # shared by reference with DataParallel replicas
+        self._is_replica = False
+        self._workspaces = {}                   # device -> uint8 tensor (shared dict: one workspace per device)
         self._layer_k = None
 
     # ------------------------------------------------------------------ packed-weight cache
@@ -209,16 +266,44 @@ class MDGAT(nn.Module):
             key.append((t.data_ptr(), t._version, t.dtype))
         return tuple(key)
 
-    def packed_weights(self):
-        """float64 blob on the parameters' device, rebuilt only when a parameter changed
+    def invalidate_packed(self):
+        """Forget the packed weight blobs. The cache is keyed on (storage pointer, version counter, dtype) of every
+        parameter and buffer, which catches optimizer steps, load_state_dict, .to() / .double() and in-place tensor ops,
+        but NOT writes made through `param.data` (that view has its own version counter): after
+        `p.data.mul_()`-style edits call this method. load_state_dict() and the train() -> eval() transition call it."""
+        self._pack_cache.invalidate()
+
+    def load_state_dict(self, *args, **kwargs):
+        res = super().load_state_dict(*args, **kwargs)
+        self.invalidate_packed()
+        return res
+
+    def train(self, mode=True):
+        if self.training and not mode:
+            self.invalidate_packed()
+        return super().train(mode)
+
+    def _replicate_for_data_parallel(self):
+        # called on the SOURCE module by torch.nn.parallel.replicate(), once per replica and forward: bring the shared
+        # cache up to date here, because the replicas cannot (see _PackedWeights)
+        self._pack_cache.refresh(self)
+        self.packed_weights(device='cpu')
+        mode, slices = self.gemm_engine()
+        if mode == 'tcgen05_i8':
+            self.packed_weights_i8(slices, device='cpu')
+        replica = super()._replicate_for_data_parallel()
+        replica._is_replica = True
+        return replica
+
+    def _param_device(self):
+        return self.final_proj.weight.device if isinstance(self.final_proj.weight, torch.Tensor) else torch.device('cpu')
+
+    def packed_weights(self, device=None):
+        """float64 blob on `device` (default: the parameters' device), rebuilt only when a parameter changed
         (test.py calls net.double() before every batch; that keeps storage and version)."""
-        key = self._weights_key()
-        if self._packed is None or self._packed[0] != key:
-            sd = {k: v for k, v in self.state_dict(keep_vars=True).items()}
-            with torch.no_grad():
-                blob = packing.pack_state_dict(sd, self.config['L'])
-            self._packed = (key, blob)
-        return self._packed[1]
+        if not self._is_replica:
+            self._pack_cache.refresh(self)
+        return self._pack_cache.blob(self, self._param_device() if device is None else device)
 
     def gemm_engine(self):
         """config['gemm']: 'tcgen05_i8' (float64-faithful Ozaki splitting on the int8 tensor cores, default)
@@ -237,14 +322,10 @@ class MDGAT(nn.Module):
             raise ValueError("config['attention'] must be 'tcgen05_i8', 'tcgen05_i8_all' or 'dmma'")
         return mode
 
-    def packed_weights_i8(self, slices):
-        key = (self._weights_key(), slices)
-        if self._packed_i8 is None or self._packed_i8[0] != key:
-            sd = {k: v for k, v in self.state_dict(keep_vars=True).items()}
-            with torch.no_grad():
-                blob = packing.pack_state_dict_i8(sd, self.config['L'], slices)
-            self._packed_i8 = (key, blob)
-        return self._packed_i8[1]
+    def packed_weights_i8(self, slices, device=None):
+        if not self._is_replica:
+            self._pack_cache.refresh(self)
+        return self._pack_cache.blob(self, self._param_device() if device is None else device, slices)
 
     # ------------------------------------------------------------------ forward
     def _gt(self, data):
@@ -262,7 +343,10 @@ class MDGAT(nn.Module):
                 'matching_scores1': k1.new_zeros(shape1)[0],
                 'skip_train': True,
             }
-        if self.training:
+        if self.loss_method not in ('triplet_loss', 'gap_loss', 'superglue'):
+            # the reference falls off the end of its if / elif chain (mdgat.py:486-603)
+            raise UnboundLocalError("local variable 'loss' referenced before assignment (unknown loss_method %r)" % (self.loss_method,))
+        if self.training or (self.config.get('eval_autograd', False) and torch.is_grad_enabled()):
             return self._forward_torch(data)
         return self._forward_cuda(data)
 
@@ -294,11 +378,11 @@ class MDGAT(nn.Module):
             sc = [prep(data['scores0']), prep(data['scores1'])]
             if sc[0].dtype != sc[1].dtype:
                 sc = [t.double() for t in sc]
-            blob = self.packed_weights()
+            if not self._is_replica and self._param_device() != dev:
+                raise RuntimeError('module parameters live on %s but inputs on %s' % (self._param_device(), dev))
+            blob = self.packed_weights(dev)
             gemm_mode, gemm_slices = self.gemm_engine()
-            blob_i8 = self.packed_weights_i8(gemm_slices) if gemm_mode == 'tcgen05_i8' else None
-            if blob.device != dev:
-                raise RuntimeError('module parameters live on %s but inputs on %s' % (blob.device, dev))
+            blob_i8 = self.packed_weights_i8(gemm_slices, dev) if gemm_mode == 'tcgen05_i8' else None
 
             loss_mode = _capi.LOSS_NONE
             gt0 = gt1 = None
@@ -340,10 +424,10 @@ class MDGAT(nn.Module):
                 attn_mode={'tcgen05_i8': _capi.ATTN_TCGEN05_I8, 'tcgen05_i8_all': _capi.ATTN_TCGEN05_I8_ALL,
                            'dmma': _capi.ATTN_DMMA_F64}[self.attention_engine()])
             need = _capi.lib.mdgat_forward_workspace_bytes(ctypes.byref(cfg))
-            ws = self._workspace
-            if ws is None or ws.device != dev or ws.numel() < need:
+            ws = self._workspaces.get(dev)
+            if ws is None or ws.numel() < need:
                 ws = torch.empty(need, dtype=torch.uint8, device=dev)
-                self._workspace = ws
+                self._workspaces[dev] = ws
             fin = _capi.ForwardIn(tens[0].data_ptr(), tens[1].data_ptr(), tens[2].data_ptr(), tens[3].data_ptr(),
                                   sc[0].data_ptr(), sc[1].data_ptr(),
                                   gt0.data_ptr() if gt0 is not None else None,

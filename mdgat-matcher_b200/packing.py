@@ -15,6 +15,10 @@
 
 All arithmetic is done in float64 on whatever the parameters currently hold, so calling the
 module as test.py does (fp32 module -> load_state_dict -> .double()) yields fp64(fp32(ckpt)).
+
+Packing runs on the HOST: the state dict is copied to the CPU once (plain device-to-host copies, no kernels), folded
+and tiled there, and the finished blob travels to the GPU in one copy. The weights change once per checkpoint load,
+so this is off the hot path, and the device never sees the ~1000 tiny library launches an on-device packer costs.
 """
 import torch
 
@@ -72,9 +76,15 @@ def _fold_bn(w, b, sd, name):
     return w * s[:, None], (b - mean) * s + beta
 
 
+def host_state_dict(sd):
+    """The tensors of a state dict as float64 CPU tensors (integer buffers are dropped: nothing here reads them)."""
+    return {k: v.detach().to(device='cpu', dtype=torch.float64) for k, v in sd.items() if v.is_floating_point()}
+
+
 def pack_state_dict(sd, L):
-    """sd: mapping name -> tensor (no 'module.' prefix). Returns a contiguous 1-D float64 tensor."""
-    dev = sd['bin_score'].device
+    """sd: mapping name -> tensor (no 'module.' prefix). Returns a contiguous 1-D float64 CPU tensor."""
+    sd = host_state_dict(sd)
+    dev = torch.device('cpu')
     parts = []
 
     def mlp(prefix, n_conv, pad_in=None):
@@ -152,8 +162,9 @@ def i8_layer_bytes(S):
 def pack_state_dict_i8(sd, L, S=7):
     """Int8-sliced copy of the per-layer GEMM weights (q/k/v stack, folded MLP conv 0, MLP conv 3) for the
     tcgen05 path: per layer [qkv slices | mlp0 slices | mlp3 slices | colscale qkv(384) mlp0(256) mlp3(128)]
-    as one uint8 tensor (colscale per (k chunk, column): qkv 384, mlp0 2x256, mlp3 2x128). Built from exactly the same float64 matrices pack_state_dict() stores."""
-    dev = sd['bin_score'].device
+    as one uint8 CPU tensor (colscale per (k chunk, column): qkv 384, mlp0 2x256, mlp3 2x128). Built from exactly the same float64 matrices pack_state_dict() stores."""
+    sd = host_state_dict(sd)
+    dev = torch.device('cpu')
     perm = _head_major_perm(dev)
     chunks = []
     for l in range(2 * L):

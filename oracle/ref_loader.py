@@ -18,7 +18,19 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get('MDGAT_REFERENCE_ROOT', '/root/reference')
+def _reference_root():
+    # /root/reference in the build container; on the GPU box the byte-identical copy oracle/build_ref.py placed under
+    # oracle/_ref/reference (git-ignored build output that travels with the snapshot)
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.environ.get('MDGAT_REFERENCE_ROOT', '/root/reference')
+    if not os.path.isfile(os.path.join(root, 'models', 'mdgat.py')):
+        alt = os.path.join(here, '_ref', 'reference')
+        if os.path.isfile(os.path.join(alt, 'models', 'mdgat.py')):
+            return alt
+    return root
+
+
+REFERENCE_ROOT = _reference_root()
 CHECKPOINT = os.path.join(REFERENCE_ROOT, 'pre-trained', 'best_model.pth')
 
 DEFAULT_K = [128, None, 128, None, 64, None, 64, None]      # test.py:83
@@ -115,14 +127,23 @@ def build_reference_net(cfg, weights='checkpoint', seed=0, target='cpu'):
     net = mod.MDGAT(cfg)                                  # fp32 params (test.py:156)
     net = torch.nn.DataParallel(net)                      # test.py:158
     if isinstance(weights, str) and weights == 'checkpoint':
-        ck = torch.load(CHECKPOINT, map_location='cpu', weights_only=True)
-        net.load_state_dict(ck['net'])                    # fp64 -> fp32 copy (test.py:159)
+        if os.path.isfile(CHECKPOINT):
+            ck = torch.load(CHECKPOINT, map_location='cpu', weights_only=True)
+            net.load_state_dict(ck['net'])                # fp64 -> fp32 copy (test.py:159)
+        else:
+            # GPU box: the 71 MB checkpoint did not travel; oracle/_ref/best_model_fp32.npz holds exactly the fp32
+            # values that copy produces
+            from oracle.build_ref import load_checkpoint_state_dict
+            sd = load_checkpoint_state_dict()
+            if sd is None:
+                raise FileNotFoundError('neither %s nor oracle/_ref/best_model_fp32.npz exists' % CHECKPOINT)
+            net.load_state_dict({'module.' + k: torch.from_numpy(v) for k, v in sd.items()})
     elif isinstance(weights, str) and weights == 'seeded':
-        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-        from oracle.synth import make_matchy
-        make_matchy(net.module, seed)
+        pass                                              # torch.manual_seed(seed) default initialisation
     else:
         net.load_state_dict(weights)
+    if str(target) != 'cpu':
+        net.to(torch.device(target))                      # test.py:172
     net.double().eval()                                   # test.py:193
     zcap = {}
     orig = mod.log_optimal_transport

@@ -172,3 +172,64 @@ def test_i8_blob_layout_matches_the_forward_offsets():
     cs = blob[S * 32 * 128 * 36: per_layer].view(torch.float64)
     m, _ = torch.frexp(cs)
     assert torch.all(m == 0.5)
+
+
+def test_packed_weight_cache_invalidation_and_dataparallel_replicas():
+    """The packed-weight cache: keyed on (storage, version, dtype), explicit invalidate_packed() for `.data` edits,
+    dropped by load_state_dict(); DataParallel replicas share the source module's cache by reference and never pack
+    themselves (their parameters are per-forward broadcast copies, not even registered when autograd is on)."""
+    from mdgat_matcher_b200.models.mdgat import MDGAT
+    from mdgat_matcher_b200 import synth
+    from conftest import case_cfg
+    cfg = case_cfg({'L': 2, 'T': 10, 'k': [16, None]})
+    sd = synth.seeded_state_dict(2, 5)
+    net = MDGAT(cfg)
+    net.load_state_dict(sd)
+    net.double().eval()
+    b0 = net.packed_weights()
+    assert b0.device.type == 'cpu' and net.packed_weights() is b0
+    net.double()                                              # test.py:193 every iteration: no repack
+    assert net.packed_weights() is b0
+    bin_at = b0.numel() - 4
+    # writes through .data bypass the version counter: documented, remedied by invalidate_packed()
+    net.bin_score.data.fill_(3.0)
+    assert net.packed_weights() is b0
+    net.invalidate_packed()
+    b1 = net.packed_weights()
+    assert b1 is not b0 and float(b1[bin_at]) == 3.0
+    with torch.no_grad():
+        net.bin_score.add_(1.0)                               # ordinary in-place update: seen by the key
+    assert float(net.packed_weights()[bin_at]) == 4.0
+    net.load_state_dict(sd)                                   # always invalidates
+    assert float(net.packed_weights()[bin_at]) == float(sd['bin_score'])
+    i8 = net.packed_weights_i8(7)
+    assert i8.dtype == torch.uint8 and net.packed_weights_i8(7) is i8
+    # what torch.nn.parallel.replicate() does with autograd enabled: a shallow copy without registered parameters
+    rep = net._replicate_for_data_parallel()
+    rep._parameters.clear()
+    assert rep._is_replica and not net._is_replica and 'bin_score' not in rep.state_dict()
+    assert rep.packed_weights(torch.device('cpu')) is net.packed_weights()
+    assert rep.packed_weights_i8(7, torch.device('cpu')) is i8
+    assert rep._workspaces is net._workspaces
+
+
+def test_forward_routing_unknown_loss_and_eval_autograd():
+    from mdgat_matcher_b200.models.mdgat import MDGAT
+    from mdgat_matcher_b200 import synth
+    from conftest import case_cfg
+    cfg = case_cfg({'L': 2, 'T': 10, 'k': [16, None]})
+    sd = synth.seeded_state_dict(2, 5)
+    data = synth.make_batch(2, 2, 48)
+    bad = MDGAT({**cfg, 'loss_method': 'nope'})
+    with pytest.raises(UnboundLocalError):                    # what falling off mdgat.py:486-603 raises
+        bad.double().eval()({k: v.clone() for k, v in data.items()})
+    # eval-mode call that must be differentiable (frozen-BatchNorm fine-tuning): opt-in torch path, CPU tensors fine
+    net = MDGAT({**cfg, 'eval_autograd': True})
+    net.load_state_dict(sd)
+    net.double().eval()
+    out = net({k: v.clone() for k, v in data.items()})
+    assert out['loss'].requires_grad
+    out['loss'].backward()
+    assert net.final_proj.weight.grad is not None and float(net.final_proj.weight.grad.abs().sum()) > 0
+    with torch.no_grad(), pytest.raises(RuntimeError, match='CUDA'):
+        net({k: v.clone() for k, v in data.items()})          # autograd off: the CUDA path, which refuses CPU tensors

@@ -22,12 +22,13 @@ def _worker(rank, world, port, q):
     from mdgat_matcher_b200 import dist as D
     D.init_process_group('gloo')
     n = 7                                              # ragged: 4 + 3
-    full = {'keypoints0': torch.arange(n * 5 * 3, dtype=torch.float64).reshape(n, 5, 3), 'tag': 'x'}
+    # 'calib' has as many rows as there are pairs but is shared, not per pair: it must not be sliced
+    full = {'keypoints0': torch.arange(n * 5 * 3, dtype=torch.float64).reshape(n, 5, 3), 'tag': 'x', 'calib': torch.eye(n)}
     mine = D.shard_batch(full)
     lo, hi = D.shard_bounds(n, rank, world)
-    assert mine['keypoints0'].shape[0] == hi - lo and mine['tag'] == 'x'
+    assert mine['keypoints0'].shape[0] == hi - lo and mine['tag'] == 'x' and mine['calib'].shape == (n, n)
     out = {'matches0': (mine['keypoints0'][:, :, 0] * 2).long(), 'matching_scores0': mine['keypoints0'][:, :, 1]}
-    g = D.all_gather_outputs(out, keys=('matches0', 'matching_scores0'))
+    g = D.all_gather_outputs(out, keys=('matches0', 'matching_scores0'), n_total=n)
     loss = D.all_reduce_mean_loss(torch.tensor(float(rank + 1), dtype=torch.float64), hi - lo)
     q.put((rank, g['matches0'], g['matching_scores0'], float(loss)))
     torch.distributed.destroy_process_group()

@@ -247,7 +247,7 @@ def test_encoder_vs_oracle(dev):
     sd_t = synth.seeded_state_dict(4, 0)
     sd = O.state_dict_to_numpy(sd_t)
     data = synth.make_batch(3, 2, 100, 77)
-    blob = packing.pack_state_dict({k: v.to(dev) for k, v in sd_t.items()}, 4)
+    blob = packing.pack_state_dict(sd_t, 4).to(dev)
     d0, d1 = ops.encode(blob, {k: v.to(dev) for k, v in data.items()})
     w0 = O.descriptor_encoder(sd, data['descriptors0'].numpy()) + O.keypoint_encoder(sd, data['keypoints0'].numpy(), data['scores0'].numpy())
     w1 = O.descriptor_encoder(sd, data['descriptors1'].numpy()) + O.keypoint_encoder(sd, data['keypoints1'].numpy(), data['scores1'].numpy())
@@ -427,7 +427,7 @@ def test_reference_eval_loop_plumbing(dev):
         m0 = data['matches0'].cpu().detach().numpy()
         assert np.array_equal(m0, rec['matches0'])
         assert np.abs(data['matching_scores0'].cpu().numpy() - rec['matching_scores0']).max() <= 1e-7
-        blobs.append(net.module._packed[1].data_ptr())
+        blobs.append(net.module.packed_weights().data_ptr())
     assert len(set(blobs)) == 1, 'packed weights were rebuilt although no parameter changed'
     # a parameter update invalidates the cache
     with torch.no_grad():

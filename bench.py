@@ -2,13 +2,14 @@
 """bench.py -- keypoint-pairs/s of the MDGAT forward hot path on B200 (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
-    python bench.py --impl reference ...                      (CPU arm: the oracle port on host cores)
+    python bench.py --impl reference ...                      (CPU arm: the unmodified reference under torch on the host cores)
 
 One "step" = one forward of MDGAT over one batch of synthetic pairs: encoder -> 18 GNN layers
 (full / top-k attention) -> score matrix -> 100 log-Sinkhorn iterations -> match extraction +
 triplet loss. Workload at every N: BASELINE.json configs[1] per GPU (batch 32, 2x512 keypoints,
-33-dim descriptors, L=9, T=100); ranks process independent batches (weak scaling, no data-path
-collective); the per-rank results are all-gathered once after the timed region.
+33-dim descriptors, L=9, T=100); ranks process independent batches (weak scaling); the per-rank
+match results are all-gathered once per step INSIDE both timed regions (one packed NCCL
+all_gather_into_tensor, no host synchronisation).
 
 Prints ONE JSON line (rank 0). `value` = pairs/s with inputs resident in HBM; `e2e` = the same
 through MDGAT.forward() with pinned HOST inputs (H2D + D2H inside the timed region).
@@ -35,6 +36,26 @@ def net_config(L, T):
     return {'sinkhorn_iterations': T, 'match_threshold': 0.2, 'lr': 1e-4, 'loss_method': 'triplet_loss',
             'k': list(DEFAULT_K), 'descriptor': 'FPFH', 'mutual_check': False, 'triplet_loss_gamma': 0.5,
             'train_step': 3, 'L': L}
+
+
+def workload_name(B, N, L, T):
+    """Names the BASELINE.json config the arguments correspond to."""
+    shape = 'batch %d per GPU, 2x%d keypoints, 33-dim desc, %d MDGAT layers (L=%d), %d Sinkhorn iters' % (B, N, L, L, T)
+    if (B, N, L, T) == (32, 512, 9, 100):
+        return 'cfg2: ' + shape
+    if (B, N, L, T) == (32, 2048, 9, 100):
+        return 'cfg4: ' + shape
+    if (B, N, L, T) == (1, 128, 4, 20):
+        return 'cfg1: ' + shape
+    return 'custom: ' + shape
+
+
+def workload_config(B, N, L, T, world):
+    """The `config` object of the JSON line; both arms (b200 and reference) print the same one."""
+    return {'workload': workload_name(B, N, L, T), 'batch_per_gpu': B, 'N': N, 'M': N, 'L': L, 'sinkhorn_iterations': T,
+            'k': [k or 0 for k in DEFAULT_K], 'loss_method': 'triplet_loss',
+            'parallelism': 'batch sharded over %d rank(s); one all_gather_into_tensor of the match results per step when ranks > 1' % world,
+            'l2': 'per-step working set (activations + q/k/v digit planes + logits scratch, ~0.6 GB at cfg2) exceeds the 126 MB L2'}
 
 
 def load_weights(L):
@@ -106,58 +127,105 @@ class ClockSampler(threading.Thread):
                 'samples': len(self.samples)}
 
 
-def cpu_port_pairs_per_s(cfg, sd_np, N, M, pairs, threads, seed=123):
-    """Times the oracle port (numpy float64 restatement of the reference) on `pairs` pairs."""
-    from oracle import mdgat_oracle as O
+def reference_cpu_net(L, T):
+    """(net, description): the UNMODIFIED reference module (oracle/_ref/reference/models/mdgat.py, a byte-identical copy
+    of /root/reference/models/mdgat.py placed there by oracle/build_ref.py; or /root/reference itself in the build
+    container), fp64, test.py load order, run on the host through oracle/ref_loader.py's torch-name shim for the
+    hard-coded torch.device('cuda') of mdgat.py:200. None when neither tree exists."""
+    from oracle import ref_loader as RL
+    if not RL.reference_available():
+        return None, 'reference tree not available'
+    cfg = RL.net_config(L=L, sinkhorn_iterations=T)
+    if L == 9 and (os.path.isfile(PRETRAINED) or os.path.isfile(RL.CHECKPOINT)):
+        net, mod, zcap = RL.build_reference_net(cfg, 'checkpoint')
+        return net, 'pre-trained checkpoint weights (fp64(fp32), test.py load order)'
     from mdgat_matcher_b200 import synth
-    data = synth.make_batch(seed, pairs, N, M)
+    sd = synth.seeded_state_dict(L, 0)
+    net, mod, zcap = RL.build_reference_net(cfg, {'module.' + k: v for k, v in sd.items()})
+    return net, 'seeded random-init weights'
+
+
+def reference_cpu_time(net, data, pairs):
+    """Seconds of one reference forward over the first `pairs` pairs of `data` (host tensors)."""
+    from oracle import ref_loader as RL
+    d = {k: v[:pairs] for k, v in data.items()}
     t0 = time.perf_counter()
-    O.forward_threaded(sd_np, data, cfg, threads)
-    dt = time.perf_counter() - t0
-    return pairs / dt, dt
+    RL.run_reference(net, d)
+    return time.perf_counter() - t0
+
+
+def pick_sample_pairs(per_pair_s, batch, steps, budget_s):
+    """Largest of batch, batch/2, batch/4, .. whose `steps` forwards fit the time budget (at least 1)."""
+    pairs = batch
+    while pairs > 1 and per_pair_s * pairs * steps > budget_s:
+        pairs //= 2
+    return max(pairs, 1)
 
 
 def run_reference_arm(args, rank):
-    """--impl reference: the reference's own CPU implementation of the path. The reference tree
-    does not exist on the GPU box, so this is the oracle port (oracle/mdgat_oracle.py, pinned to
-    the unmodified reference by tests/golden), one pair per host thread."""
+    """--impl reference: the reference's own implementation of the path on the host cores -- the unmodified
+    models/mdgat.py under torch with every host thread. Each step is one forward over a
+    bounded sample of the batch: the full batch when K steps of it fit ~4 minutes, else a power-of-two fraction."""
     if rank != 0:
         return
-    from oracle import mdgat_oracle as O
+    from mdgat_matcher_b200 import synth
     threads = os.cpu_count() or 1
-    try:
-        from threadpoolctl import threadpool_limits
-        limiter = threadpool_limits(limits=1)       # one BLAS thread per pair-task
-    except Exception:
-        limiter = None
-    cfg = net_config(args.layers, args.sinkhorn)
-    sd, wdesc = load_weights(args.layers)
-    sd_np = O.state_dict_to_numpy(sd)
-    pairs = args.cpu_pairs if args.cpu_pairs > 0 else max(threads, 8)
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_port_pairs_per_s(cfg, sd_np, args.n, args.n, min(pairs, threads), threads)
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        cpu_port_pairs_per_s(cfg, sd_np, args.n, args.n, pairs, threads, seed=200 + s)
-    dt = time.perf_counter() - t0
+    torch.set_num_threads(threads)
+    B, N, L, T = args.batch, args.n, args.layers, args.sinkhorn
+    net, wdesc = reference_cpu_net(L, T)
+    kind = 'reference'
+    if net is None:
+        raise SystemExit('bench.py --impl reference: oracle/_ref/reference is missing; run `python __graft_entry__.py build` '
+                         'where /root/reference exists (the snapshot carries oracle/_ref to the GPU box)')
+    data = synth.make_batch(1000, B, N)
+    with torch.no_grad():
+        probe = min(4, B)
+        reference_cpu_time(net, data, probe)                       # first call: thread pool, allocator
+        per_pair = reference_cpu_time(net, data, probe) / probe
+        pairs = args.cpu_pairs if args.cpu_pairs > 0 else pick_sample_pairs(per_pair, B, args.steps + 1, args.cpu_budget)
+        for _ in range(args.warmup):
+            reference_cpu_time(net, data, pairs if _ == 0 else probe)
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            reference_cpu_time(net, data, pairs)
+        dt = time.perf_counter() - t0
     value = pairs * args.steps / dt
+    sample = ('%d steps x one forward over %d of the %d pairs (N=M=%d, L=%d, T=%d), unmodified reference models/mdgat.py, torch %s, '
+              '%d threads' % (args.steps, pairs, B, N, L, T, torch.__version__, threads))
     line = {
         'impl': 'reference', 'metric': 'keypoint-pairs/sec', 'value': value, 'unit': 'pairs/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic in-distribution keypoint pairs; ' + wdesc,
-        'config': {'workload': 'cfg2: batch 32, 2x512 keypoints, 33-dim desc, 9 MDGAT layers (L=9), 100 Sinkhorn iters',
-                   'N': args.n, 'L': args.layers, 'sinkhorn_iterations': args.sinkhorn,
-                   'step': '%d pairs per step (bounded sample of the batch-32 workload)' % pairs},
-        'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
-                         'sample': '%d steps x %d pairs of N=M=%d, L=%d, T=%d, one pair per thread' %
-                                   (args.steps, pairs, args.n, args.layers, args.sinkhorn)},
+        'data': 'synthetic in-distribution keypoint pairs (SURVEY 8d generator); ' + wdesc,
+        'config': workload_config(B, N, L, T, 1),
+        'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': threads, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
-    if limiter is not None:
-        limiter.restore_original_limits() if hasattr(limiter, 'restore_original_limits') else None
+
+
+def digit_products(S, SP):
+    """int8 plane products per float64 contraction: GEMM / Q K^T keep the pairs s + t <= S - 1; pass 1 of the attention
+    kernel multiplies the 3 leading pairs; P V keeps a + t <= S - 1 for the SP planes of P."""
+    return S * (S + 1) // 2, 3, SP * S - SP * (SP - 1) // 2
+
+
+def sweep_parity(out, seed, B, N, L, T):
+    """Compares this run's outputs with the stored outputs of the UNMODIFIED reference for the same seeded batch
+    (tests/golden/sweep, oracle/gen_sweep.py), when that batch is the one being timed."""
+    path = os.path.join(ROOT, 'tests', 'golden', 'sweep', 'cfg2_s%d_b%d.npz' % (seed, B))
+    if (N, L, T) != (512, 9, 100) or not os.path.isfile(path):
+        return None
+    ref = np.load(path)
+    flips, errs = 0, []
+    for side in ('0', '1'):
+        flips += int((out['matches' + side].cpu().numpy() != ref['matches' + side].astype(np.int64)).sum())
+        errs.append(np.abs(out['matching_scores' + side].cpu().numpy() - ref['matching_scores' + side]).ravel())
+    e = np.concatenate(errs)
+    return {'against': 'unmodified reference outputs for the timed batch (tests/golden/sweep/%s)' % os.path.basename(path),
+            'rows': int(e.size), 'index_flips': flips, 'max_score_err': float(e.max()), 'p99_score_err': float(np.quantile(e, 0.99)),
+            'loss_err': abs(float(out['loss']) - float(ref['loss'])), 'bar': 'indices exact, scores <= 1e-4'}
 
 
 def main():
@@ -170,11 +238,15 @@ def main():
     ap.add_argument('--n', type=int, default=512, help='keypoints per set')
     ap.add_argument('--layers', type=int, default=9, help='L (2L GNN layers)')
     ap.add_argument('--sinkhorn', type=int, default=100)
-    ap.add_argument('--cpu-pairs', type=int, default=0, help='pairs in the CPU baseline sample (0 = auto)')
+    ap.add_argument('--cpu-pairs', type=int, default=0, help='pairs per step of the CPU reference (0 = auto)')
+    ap.add_argument('--cpu-budget', type=float, default=240.0, help='seconds the --impl reference run may take')
     ap.add_argument('--gemm', default='tcgen05_i8', choices=['tcgen05_i8', 'dmma'], help='engine of the per-layer projections')
     ap.add_argument('--attention', default='tcgen05_i8', choices=['tcgen05_i8', 'tcgen05_i8_all', 'dmma'], help='engine of Q K^T / P V')
+    ap.add_argument('--precision', default=None, choices=['sweep', 'exact'],
+                    help="digit planes: 'sweep' = the smallest counts that pass the 131 k-row parity sweep (module default), 'exact' = 7/7/6")
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-eager', action='store_true', help='skip the eager-PyTorch fp64 GPU timing of the same math')
+    ap.add_argument('--no-eager', action='store_true', help='skip the eager-GPU timing of the unmodified reference')
+    ap.add_argument('--no-latency', action='store_true', help='skip the batch-1 latency measurement')
     args = ap.parse_args()
 
     # NCCL prints its version banner on STDOUT at level VERSION; this script owes the driver ONE json line
@@ -201,21 +273,30 @@ def main():
     B, N, L, T = args.batch, args.n, args.layers, args.sinkhorn
     cfg = net_config(L, T)
     cfg['gemm'], cfg['attention'] = args.gemm, args.attention
+    if args.precision:
+        cfg['precision'] = args.precision
     sd, wdesc = load_weights(L)
     net = MDGAT(cfg)
     net.load_state_dict(sd)
     net = net.double().eval().to(dev)
+    planes = net.digit_planes()                                   # (gemm S, attention S, attention SP)
 
-    host = synth.make_batch(1000 + rank, B, N)                    # every rank its own pairs
+    seed = 1000 + rank
+    host = synth.make_batch(seed, B, N)                           # every rank its own pairs
     host = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
     out_keys = ('matches0', 'matches1', 'matching_scores0', 'matching_scores1', 'loss')
 
+    @torch.no_grad()
     def step_resident():
         d = dict(resident)
         d['gt_matches0'] = resident['gt_matches0'].clone()      # forward rewrites gt in place (mdgat.py:519)
         d['gt_matches1'] = resident['gt_matches1'].clone()
-        return net(d)
+        o = net(d)
+        if world > 1:
+            # the one collective of the path, every step: all ranks' match results
+            o['gathered'] = mdist.all_gather_outputs(o)
+        return o
 
     # End-to-end step as a pipelined caller drives it (a loader that prefetches, a consumer that reads the results of
     # step i-1 while step i runs): the pinned host inputs of step i+1 travel on a copy stream during step i, the results
@@ -241,6 +322,7 @@ def main():
             done[(i - 1) % 2].synchronize()
             e2e_state['consumed'] += float(host_out[(i - 1) % 2]['loss'])
 
+    @torch.no_grad()
     def step_e2e():
         i = e2e_state['i']
         if not e2e_state['primed']:
@@ -248,6 +330,8 @@ def main():
             e2e_state['primed'] = True
         torch.cuda.current_stream().wait_event(slot_ready[i % 2])
         o = net(slots[i % 2])
+        if world > 1:
+            o['gathered'] = mdist.all_gather_outputs(o)
         for k in out_keys:
             if k not in host_out[i % 2]:
                 host_out[i % 2][k] = torch.empty(o[k].shape, dtype=o[k].dtype).pin_memory()
@@ -283,7 +367,7 @@ def main():
     launches = _capi.lib.mdgat_launch_count() - l0
 
     # ---------------- per-stage device times: a separate pass of the same K steps with the stage events switched on
-    # (≈230 cudaEventRecord calls per forward cost ≈0.5 ms per step, so they stay out of the timed region above)
+    # (~230 cudaEventRecord calls per forward cost ~0.5 ms per step, so they stay out of the timed region above)
     _capi.lib.mdgat_profile_enable(1)
     for _ in range(args.steps):
         step_resident()
@@ -307,9 +391,7 @@ def main():
     t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        # the one collective of the path: gather every rank's match results
-        gathered = mdist.all_gather_outputs({k: out[k] for k in out_keys[:4]})
-        assert gathered['matches0'].shape[0] == B * world
+        assert out['gathered']['matches0'].shape[0] == B * world
     ms_total, e2e_ms = float(t[0]), float(t[1])
 
     if rank != 0:
@@ -321,6 +403,12 @@ def main():
     e2e_value = pairs_total / (e2e_ms * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = sum(v.numel() * v.element_size() for v in host_out[0].values())
+    config = workload_config(B, N, L, T, world)
+    config['digit_planes'] = {'gemm': planes[0], 'attention_qkv': planes[1], 'attention_p': planes[2],
+                              'note': 'int8 planes per float64 operand; chosen on the 131 k-row sweep against the unmodified reference (DESIGN.md 2)'}
+    if world > 1:
+        config['collective'] = {'op': 'all_gather_into_tensor (NCCL)', 'per_step': 1, 'inside_timed_region': True,
+                                'bytes_per_rank_per_step': int(B * 2 * (N + N) * 8)}
 
     # ---------------- roofline of the dominant stage (device time from CUDA events on the launch stream)
     lin_f, attn_f = flops_per_pair(N, N, L)
@@ -340,16 +428,17 @@ def main():
         # The dominant kernel runs on the int8 tensor pipe: its algorithmic work is the exact digit-plane products
         # (DESIGN.md 4.1 / 4.3), 2 operations per int8 multiply-add; the ceiling is the kind::i8 issue rate measured
         # in this process. The float64 FLOPs those products stand for are reported next to it.
-        S = 7
         R = B * 2 * N
-        i8_ops = {'gemm': 2 * L * (S * (S + 1) // 2) * 2.0 * R * (384 * 128 + 256 * 256 + 128 * 256),
-               'attn_full': (2 * L - n_topk) * (28 + 3 + 27) * 2.0 * N * N * 32 * 4 * 2 * B}[dominant]
+        gq, _, _ = digit_products(planes[0], planes[2])
+        qk, p1, pv = digit_products(planes[1], planes[2])
+        i8_ops = {'gemm': 2 * L * gq * 2.0 * R * (384 * 128 + 256 * 256 + 128 * 256),
+                  'attn_full': (2 * L - n_topk) * (qk + p1 + pv) * 2.0 * N * N * 32 * 4 * 2 * B}[dominant]
         i8_peak = ops.measure_i8_peak()
         achieved = i8_ops / (per_step[dominant] * 1e-3) / 1e12
         roofline = {
             'bound': 'tensor',
-            'kernel': {'gemm': 'ozaki_gemm_kernel (tcgen05.mma.kind::i8, 28 exact digit-plane products per float64 GEMM)',
-                       'attn_full': 'attn_i8_kernel (tcgen05.mma.kind::i8, 58 exact digit-plane products per float64 Q K^T + P V)'}[dominant],
+            'kernel': {'gemm': 'ozaki_gemm_kernel (tcgen05.mma.kind::i8, %d exact digit-plane products per float64 GEMM)' % gq,
+                       'attn_full': 'attn_i8_kernel (tcgen05.mma.kind::i8, %d exact digit-plane products per float64 Q K^T + P V)' % (qk + p1 + pv)}[dominant],
             'achieved': achieved, 'peak': i8_peak, 'unit': 'TFLOP/s', 'frac': achieved / i8_peak, 'traffic': None,
             'op_kind': 'int8 tensor operations (2 per multiply-add) of the digit-plane products issued per step',
             'peak_source': 'tcgen05.mma kind::i8 issue-rate microbenchmark run in this process (128x256x32 MMAs from shared memory); '
@@ -377,70 +466,134 @@ def main():
         'all_fp64_tflops': (lin_f + attn_f) * B / ((per_step['gemm'] + per_step['attn_full'] + per_step['attn_topk'] + per_step.get('slice', 0.0)) * 1e-3) / 1e12,
     })
 
+    parity = sweep_parity(out, seed, B, N, L, T)
+
+    # ---------------- the reference's own CPU path, bounded sample (the unmodified models/mdgat.py under torch)
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        from oracle import mdgat_oracle as O
         threads = os.cpu_count() or 1
-        try:
-            from threadpoolctl import threadpool_limits
-            threadpool_limits(limits=1)
-        except Exception:
-            pass
-        pairs = args.cpu_pairs if args.cpu_pairs > 0 else max(threads, 8)
-        v, dt = cpu_port_pairs_per_s(cfg, O.state_dict_to_numpy(sd), N, N, pairs, threads)
-        cpu_baseline = {'value': v, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
-                        'sample': '%d pairs of N=M=%d, L=%d, T=%d (%.1f s), one pair per host thread' % (pairs, N, L, T, dt)}
+        torch.set_num_threads(threads)
+        ref_net, _ = reference_cpu_net(L, T)
+        if ref_net is not None:
+            cpu_data = {k: v.clone() for k, v in host.items()}
+            with torch.no_grad():
+                probe = min(2, B)
+                reference_cpu_time(ref_net, cpu_data, probe)
+                per_pair = reference_cpu_time(ref_net, cpu_data, probe) / probe
+                pairs = args.cpu_pairs if args.cpu_pairs > 0 else pick_sample_pairs(per_pair, B, 1, 20.0)
+                dt = reference_cpu_time(ref_net, cpu_data, pairs)
+            cpu_baseline = {'value': pairs / dt, 'unit': 'pairs/s', 'cores': threads, 'kind': 'reference',
+                            'sample': 'one forward over %d of the %d timed pairs (N=M=%d, L=%d, T=%d; %.1f s), unmodified reference '
+                                      'models/mdgat.py under torch %s on %d host threads' % (pairs, B, N, L, T, dt, torch.__version__, threads)}
+            del ref_net
+        else:
+            cpu_baseline = {'value': None, 'unit': 'pairs/s', 'cores': threads, 'kind': 'reference',
+                            'sample': 'unavailable: oracle/_ref/reference missing (run __graft_entry__.build() where /root/reference exists)'}
 
-    # the reference's own op sequence (einsum / softmax / topk / scatter / logsumexp, fp64) as eager PyTorch on
-    # this GPU: the drop-in's differentiable path in eval mode. Context for the >=10x north-star target; the
-    # reference tree itself is not on the GPU box.
+    # ---------------- the reference's own eager-GPU path: the UNMODIFIED models/mdgat.py on this GPU, fp64, same inputs
+    # (the denominator of the >= 10x north-star target). No shim is needed on a CUDA box.
     eager = None
     if not args.no_eager and world == 1:
         try:
+            from oracle import ref_loader as RL
+            if not RL.reference_available():
+                raise FileNotFoundError('oracle/_ref/reference missing')
+            rcfg = RL.net_config(L=L, sinkhorn_iterations=T)
+            if L == 9:
+                rnet, rmod, zcap = RL.build_reference_net(rcfg, 'checkpoint', target=dev)
+            else:
+                rnet, rmod, zcap = RL.build_reference_net(rcfg, {'module.' + k: v for k, v in sd.items()}, target=dev)
+            rmodule = rnet.module                                    # the MDGAT module itself (DataParallel would replicate over every visible GPU)
             with torch.no_grad():
                 def step_eager():
                     d = dict(resident)
                     d['gt_matches0'] = resident['gt_matches0'].clone()
                     d['gt_matches1'] = resident['gt_matches1'].clone()
-                    return net._forward_torch(d)
-                oe = step_eager()
-                torch.cuda.synchronize()
-                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                g0.record()
+                    return rmodule(d)
                 for _ in range(3):
                     oe = step_eager()
-                g1.record()
                 torch.cuda.synchronize()
-                ems = g0.elapsed_time(g1) / 3
-            eager = {'ms_per_step': ems, 'pairs_per_s': B / (ems * 1e-3), 'speedup_of_value': value / (B / (ems * 1e-3)),
+                times = []
+                for _ in range(10):
+                    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    g0.record()
+                    oe = step_eager()
+                    g1.record()
+                    torch.cuda.synchronize()
+                    times.append(g0.elapsed_time(g1))
+            ems = float(np.median(times))
+            eager = {'ms_per_step': ems, 'min_ms_per_step': float(min(times)), 'pairs_per_s': B / (ems * 1e-3),
+                     'speedup_of_value': value / (B / (ems * 1e-3)), 'speedup_of_e2e': e2e_value / (B / (ems * 1e-3)),
                      'matches_equal': bool(torch.equal(oe['matches0'], out['matches0']) and torch.equal(oe['matches1'], out['matches1'])),
-                     'max_score_diff': float((oe['matching_scores0'] - out['matching_scores0']).abs().max()),
-                     'what': 'eager PyTorch fp64 restatement of the reference op sequence (MDGAT._forward_torch, eval mode), same inputs'}
-            del oe
+                     'max_score_diff': float(max((oe['matching_scores0'] - out['matching_scores0']).abs().max(),
+                                                 (oe['matching_scores1'] - out['matching_scores1']).abs().max())),
+                     'peak_memory_gb': torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+                     'what': 'UNMODIFIED reference models/mdgat.py (MDGAT.forward, eval, fp64, checkpoint weights in test.py load order) as eager '
+                             'PyTorch %s on this GPU, same resident inputs, 3 warm-up + 10 timed forwards, median (CUDA events)' % torch.__version__}
+            del oe, rnet, rmodule
             torch.cuda.empty_cache()
-        except Exception as e:          # e.g. out of memory on the dense prob tensors
-            eager = {'error': repr(e)[:200]}
+        except Exception as e:          # e.g. out of memory on the retained attn.prob tensors at N = 2048
+            eager = {'error': repr(e)[:300]}
+
+    # ---------------- single-call latency at the KITTI-like shape (batch 1, 2 x 256 keypoints, T = 20: cfg5's step)
+    latency = None
+    if not args.no_latency and world == 1:
+        latency = batch1_latency(dev, sd, L)
 
     line = {
         'metric': 'keypoint-pairs/sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic in-distribution keypoint pairs (SURVEY 8d generator); ' + wdesc,
-        'config': {'workload': 'cfg2: batch 32 per GPU, 2x512 keypoints, 33-dim desc, 9 MDGAT layers (L=9), 100 Sinkhorn iters',
-                   'batch_per_gpu': B, 'N': N, 'M': N, 'L': L, 'sinkhorn_iterations': T, 'k': [k or 0 for k in DEFAULT_K],
-                   'loss_method': 'triplet_loss', 'parallelism': 'batch sharded over %d rank(s), no data-path collective' % world,
-                   'l2': 'per-step working set (activations + q/k/v + logits scratch, ~0.6 GB) exceeds the 126 MB L2'},
+        'config': config,
         'e2e': {'value': e2e_value, 'unit': 'pairs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_ms / args.steps},
         'gpu_launches': int(launches),
         'clocks': sampler.summary(),
         'roofline': roofline,
         'cpu_baseline': cpu_baseline,
-        'gpu_eager_port': eager,
+        'parity': parity,
+        'gpu_eager_reference': eager,
+        'latency_batch1': latency,
         'candidate_correspondences_per_s': value * N * N,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def batch1_latency(dev, sd, L):
+    """Milliseconds of ONE MDGAT.forward call at batch 1, 2 x 256 keypoints, T = 20 (the per-step shape of
+    test_registration_metric.py, BASELINE config 5): plain launches, and replayed from a captured CUDA graph."""
+    from mdgat_matcher_b200 import synth
+    from mdgat_matcher_b200.models.mdgat import MDGAT
+    try:
+        res = {}
+        data = {k: v.to(dev) for k, v in synth.make_batch(77, 1, 256).items()}
+        for graph in (False, True):
+            cfg = net_config(L, 20)
+            cfg['cuda_graph'] = graph
+            net = MDGAT(cfg)
+            net.load_state_dict(sd)
+            net = net.double().eval().to(dev)
+            with torch.no_grad():
+                def call():
+                    d = dict(data)
+                    d['gt_matches0'], d['gt_matches1'] = data['gt_matches0'].clone(), data['gt_matches1'].clone()
+                    return net(d)
+                for _ in range(5):
+                    o = call()
+                torch.cuda.synchronize()
+                times = []
+                for _ in range(30):
+                    t0 = time.perf_counter()
+                    o = call()
+                    float(o['loss'])                                  # the caller reads a result: device -> host, synchronises
+                    times.append((time.perf_counter() - t0) * 1e3)
+            res['graph' if graph else 'launches'] = {'median_ms': float(np.median(times)), 'min_ms': float(min(times))}
+        res['shape'] = 'batch 1, 2x256 keypoints, L=%d, T=20; wall clock of forward() + reading the loss on the host' % L
+        return res
+    except Exception as e:
+        return {'error': repr(e)[:300]}
 
 
 if __name__ == '__main__':

@@ -87,8 +87,13 @@ typedef struct {
     int score_dtype;          /* element type of scores0/1 (the reference does not cast them) */
     int write_Z;              /* also materialise Z (B,N+1,M+1) into d_Z (debug / other losses) */
     int gemm_mode;            /* MDGAT_GEMM_* */
-    int gemm_slices;          /* int8 slices per operand in MDGAT_GEMM_TCGEN05_I8 mode (6 or 7; 7 = 49 bits) */
+    int gemm_slices;          /* int8 digit planes (7 bits each) per GEMM operand in MDGAT_GEMM_TCGEN05_I8 mode: 4..7.
+                                 5 (35 bits) is the smallest count that passes the 131 k-row parity sweep against the
+                                 unmodified reference (0 index flips, score error <= 7e-8); 7 = 49 bits ("exact") */
     int attn_mode;            /* MDGAT_ATTN_* (tcgen05 needs N, M <= 4096; larger sets use the DMMA kernel) */
+    int attn_slices;          /* int8 digit planes (8 bits each) of q, k, v in the tcgen05 attention: 4..7 (0 = 7) */
+    int attn_p_slices;        /* byte planes of the softmax probabilities: (attn_slices, attn_p_slices) must be one of
+                                 (4,3) (4,4) (5,4) (6,5) (7,6); 0 = attn_slices - 1 */
 } mdgat_forward_cfg;
 
 typedef struct {
@@ -159,10 +164,12 @@ int mdgat_attention_f64(const double* d_Q, const double* d_K, const double* d_V,
 
 /* Same contract on the tcgen05 int8 tensor cores (attention_i8.cu): q, k, v are cut into base-256 digit planes on
  * the device, Q K^T and P V are exact int32 digit products in TMEM, recombined in float64.
- * d_scratch: mdgat_attention_i8_scratch_bytes(B, N, M) bytes. Requires N, M <= 4096. */
-size_t mdgat_attention_i8_scratch_bytes(int B, int N, int M);
+ * d_scratch: mdgat_attention_i8_scratch_bytes(B, N, M) bytes. Requires N, M <= 4096. slices / p_slices: digit planes of
+ * q, k, v / of the probabilities, as mdgat_forward_cfg.attn_slices / attn_p_slices. */
+size_t mdgat_attention_i8_scratch_bytes(int B, int N, int M);   /* sized for 7 planes, enough for any setting */
 int mdgat_attention_i8(const double* d_Q, const double* d_K, const double* d_V, double* d_Out, int ldo,
-                       int B, int N, int M, int topk, double* d_logits, void* d_scratch, void* stream);
+                       int B, int N, int M, int topk, double* d_logits, void* d_scratch, int slices, int p_slices,
+                       void* stream);
 
 /* log_optimal_transport (mdgat.py:279-308) on couplings already holding scores in [:N,:M]:
  * fills the dustbin row/column with bin_score (read from d_bin_score), runs `iters`

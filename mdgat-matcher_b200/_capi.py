@@ -25,7 +25,8 @@ class ForwardCfg(C.Structure):
                 ('match_mode', C.c_int), ('mutual_check', C.c_int), ('match_threshold', C.c_double),
                 ('loss_mode', C.c_int), ('triplet_gamma', C.c_double),
                 ('in_dtype', C.c_int), ('score_dtype', C.c_int), ('write_Z', C.c_int),
-                ('gemm_mode', C.c_int), ('gemm_slices', C.c_int), ('attn_mode', C.c_int)]
+                ('gemm_mode', C.c_int), ('gemm_slices', C.c_int), ('attn_mode', C.c_int),
+                ('attn_slices', C.c_int), ('attn_p_slices', C.c_int)]
 
 
 class ForwardIn(C.Structure):
@@ -61,7 +62,7 @@ def _load():
         'mdgat_encode': (i, [C.POINTER(ForwardIn), i, i, i, i, i, vp, vp, vp, vp]),
         'mdgat_attention_f64': (i, [vp, vp, vp, vp, i, i, i, i, i, vp, vp]),
         'mdgat_attention_i8_scratch_bytes': (sz, [i, i, i]),
-        'mdgat_attention_i8': (i, [vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp]),
+        'mdgat_attention_i8': (i, [vp, vp, vp, vp, i, i, i, i, i, vp, vp, i, i, vp]),
         'mdgat_sinkhorn_scratch_doubles': (sz, [i, i, i]),
         'mdgat_sinkhorn_read_status': (i, [vp, i, i, i, C.POINTER(i), C.POINTER(i)]),
         'mdgat_sinkhorn_f64': (i, [vp, vp, vp, vp, i, i, i, i, vp, vp]),

@@ -27,6 +27,10 @@ using namespace mdgat;
 
 // ---- launch counter and per-stage device timers (CUDA events on the caller's stream) ----
 namespace {
+// digit planes of the tcgen05 attention: (q/k/v planes, probability planes) from the cfg, 0 = defaults
+inline int attn_planes(const mdgat_forward_cfg* cfg) { return cfg->attn_slices > 0 ? cfg->attn_slices : 7; }
+inline int attn_p_planes(const mdgat_forward_cfg* cfg) { return cfg->attn_p_slices > 0 ? cfg->attn_p_slices : attn_planes(cfg) - 1; }
+inline bool attn_planes_ok(int S, int SP) { return (S == 4 && (SP == 3 || SP == 4)) || (S >= 5 && S <= 7 && SP == S - 1); }
 enum { ST_ENCODE = 0, ST_GEMM, ST_ATTN_FULL, ST_ATTN_TOPK, ST_SINKHORN, ST_MATCH, ST_SLICE, ST_COUNT };
 struct Profiler {
     bool on = false;
@@ -99,7 +103,7 @@ struct Workspace {
 };
 
 // Carves the workspace; with base == nullptr only computes the size.
-Workspace carve(char* base, int B, int N, int M, bool need_logits, int i8_slices = 0, bool attn_i8 = false) {
+Workspace carve(char* base, int B, int N, int M, bool need_logits, int i8_slices = 0, int attn_i8 = 0) {
     Workspace w;
     const size_t R = (size_t)B * N + (size_t)B * M;
     size_t off = 0;
@@ -135,8 +139,8 @@ Workspace carve(char* base, int B, int N, int M, bool need_logits, int i8_slices
     w.xsH = reinterpret_cast<int8_t*>(take(2 * chunk8));
     for (int s = 0; s < 2; ++s) {
         const int n = s == 0 ? N : M;
-        void* p = take(attn_i8 ? attn_i8_side_bytes(B, n) / 8 : 0);
-        if (attn_i8 && base) w.ai[s] = attn_i8_carve(p, B, n);
+        void* p = take(attn_i8 ? attn_i8_side_bytes(B, n, attn_i8) / 8 : 0);
+        if (attn_i8 && base) w.ai[s] = attn_i8_carve(p, B, n, attn_i8);
     }
     w.bytes = off;
     return w;
@@ -168,12 +172,12 @@ cudaError_t gemm_nt(const double* X, int ldx, long long sX, const double* W, int
 // Messages of one GNN layer. nsides = 2: side 0 and side 1 in the same launches.
 // qd / kvd != nullptr: tcgen05 engine; the digit planes of the query / source side of each grid side are already cut.
 cudaError_t attention_layer(const AttnSides& ps, int B, int nsides, int ldo, int topk, double* S, cudaStream_t st,
-                            const AttnI8Side* qd = nullptr, const AttnI8Side* kvd = nullptr) {
+                            const AttnI8Side* qd = nullptr, const AttnI8Side* kvd = nullptr, int SP = 0) {
     if (qd) {
-        if (topk <= 0) return launch_attn_i8(qd, kvd, ps.Out, B, nsides, ldo, false, st);
+        if (topk <= 0) return launch_attn_i8(qd, kvd, ps.Out, B, nsides, ldo, false, SP, st);
         double* lg[2]; double* sp = S;
         for (int s = 0; s < nsides; ++s) { lg[s] = sp; sp += (size_t)B * HEADS * ps.N[s] * ps.M[s]; }
-        cudaError_t e = launch_attn_i8(qd, kvd, lg, B, nsides, 0, true, st);
+        cudaError_t e = launch_attn_i8(qd, kvd, lg, B, nsides, 0, true, SP, st);
         if (e != cudaSuccess) return e;
         for (int s = 0; s < nsides; ++s) {
             e = launch_topk_softmax_pv(lg[s], ps.V[s], ps.Out[s], ldo, B, ps.N[s], ps.M[s], topk, st);
@@ -218,7 +222,7 @@ cudaError_t encode(const mdgat_forward_in* in, int B, int N, int M, int in_dtype
 extern "C" {
 
 const char* mdgat_last_error(void) { return mdgat_host::g_err; }
-int mdgat_abi_version(void) { return 1; }
+int mdgat_abi_version(void) { return 2; }
 
 size_t mdgat_weight_blob_doubles(int L) { return BlobLayout(L).total; }
 
@@ -226,7 +230,7 @@ size_t mdgat_forward_workspace_bytes(const mdgat_forward_cfg* cfg) {
     bool need = false;
     for (int i = 0; i < 2 * cfg->L; ++i) need = need || (cfg->layer_k && cfg->layer_k[i] > 0);
     const bool ai = (cfg->attn_mode == MDGAT_ATTN_TCGEN05_I8 || cfg->attn_mode == MDGAT_ATTN_TCGEN05_I8_ALL) && attn_i8_supported(cfg->N, cfg->M) && attn_i8_supported(cfg->M, cfg->N);
-    return carve(nullptr, cfg->B, cfg->N, cfg->M, need, cfg->gemm_mode == MDGAT_GEMM_TCGEN05_I8 ? cfg->gemm_slices : 0, ai).bytes;
+    return carve(nullptr, cfg->B, cfg->N, cfg->M, need, cfg->gemm_mode == MDGAT_GEMM_TCGEN05_I8 ? cfg->gemm_slices : 0, ai ? attn_planes(cfg) : 0).bytes;
 }
 
 int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const void* d_weights_i8,
@@ -254,9 +258,11 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
     }
     const bool i8 = cfg->gemm_mode == MDGAT_GEMM_TCGEN05_I8;
     const int S8 = cfg->gemm_slices;
-    MDGAT_REQUIRE(!i8 || (d_weights_i8 != nullptr && S8 >= 6 && S8 <= 7), "tcgen05 int8 GEMM mode needs the sliced weight blob and 6 or 7 slices");
+    MDGAT_REQUIRE(!i8 || (d_weights_i8 != nullptr && S8 >= 4 && S8 <= 7), "tcgen05 int8 GEMM mode needs the sliced weight blob and 4..7 slices (got %d)", S8);
     const bool ai8_any = (cfg->attn_mode == MDGAT_ATTN_TCGEN05_I8 || cfg->attn_mode == MDGAT_ATTN_TCGEN05_I8_ALL) && attn_i8_supported(N, M) && attn_i8_supported(M, N);
-    Workspace w = carve(reinterpret_cast<char*>(d_workspace), B, N, M, need, i8 ? S8 : 0, ai8_any);
+    const int AS = attn_planes(cfg), ASP = attn_p_planes(cfg);
+    MDGAT_REQUIRE(!ai8_any || attn_planes_ok(AS, ASP), "tcgen05 attention: unsupported digit planes (attn_slices %d, attn_p_slices %d)", AS, ASP);
+    Workspace w = carve(reinterpret_cast<char*>(d_workspace), B, N, M, need, i8 ? S8 : 0, ai8_any ? AS : 0);
     if (w.bytes > workspace_bytes) {
         mdgat_host::set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
         return MDGAT_ERR_WORKSPACE;
@@ -327,7 +333,7 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
             prof_mark(k > 0 ? ST_ATTN_TOPK : ST_ATTN_FULL, st);
             const AttnI8Side qd[2] = {w.ai[0], w.ai[1]};
             const AttnI8Side kvd[2] = {cross ? w.ai[1] : w.ai[0], cross ? w.ai[0] : w.ai[1]};
-            MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st, qd, kvd));
+            MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st, qd, kvd, ASP));
         } else {
             MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st));
         }
@@ -401,7 +407,7 @@ int mdgat_linear_i8(const double* d_X0, int ldx0, int K0, const double* d_X1, in
                     double* d_Y, int ldy, int R, int Nout, int relu, int slices, void* d_scratch, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int K = K0 + (d_X1 ? K1 : 0);
-    MDGAT_REQUIRE(slices >= 6 && slices <= 7, "mdgat_linear_i8: 6 or 7 slices");
+    MDGAT_REQUIRE(slices >= 4 && slices <= 7, "mdgat_linear_i8: 4..7 slices");
     MDGAT_REQUIRE((K0 % 128) == 0 && (K == 128 || K == 256) && (Nout % 32) == 0 && Nout <= 384, "mdgat_linear_i8: K0 multiple of 128, K in {128,256}, Nout multiple of 32 and <= 384");
     MDGAT_REQUIRE((ldx0 % 2) == 0 && (ldy % 2) == 0, "mdgat_linear_i8: even leading dimensions");
     MDGAT_REQUIRE(!(relu && d_Res == d_Y && d_Res && K > 128), "mdgat_linear_i8: in-place residual with ReLU needs K == 128");
@@ -449,24 +455,27 @@ int mdgat_attention_f64(const double* d_Q, const double* d_K, const double* d_V,
     return MDGAT_OK;
 }
 
-size_t mdgat_attention_i8_scratch_bytes(int B, int N, int M) { return attn_i8_side_bytes(B, N) + attn_i8_side_bytes(B, M); }
+size_t mdgat_attention_i8_scratch_bytes(int B, int N, int M) { return attn_i8_side_bytes(B, N, 7) + attn_i8_side_bytes(B, M, 7); }
 
 int mdgat_attention_i8(const double* d_Q, const double* d_K, const double* d_V, double* d_Out, int ldo,
-                       int B, int N, int M, int topk, double* d_logits, void* d_scratch, void* stream) {
+                       int B, int N, int M, int topk, double* d_logits, void* d_scratch, int slices, int p_slices,
+                       void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int AS = slices > 0 ? slices : 7, ASP = p_slices > 0 ? p_slices : AS - 1;
+    MDGAT_REQUIRE(attn_planes_ok(AS, ASP), "mdgat_attention_i8: unsupported digit planes (slices %d, p_slices %d)", AS, ASP);
     MDGAT_REQUIRE(topk <= M, "selected index k out of range (k=%d, M=%d)", topk, M);
     MDGAT_REQUIRE(topk <= 0 || (d_logits != nullptr && M <= 2048), "mdgat_attention_i8: top-k needs a logits scratch and M <= 2048");
     MDGAT_REQUIRE((ldo % 2) == 0 && d_scratch != nullptr, "mdgat_attention_i8: ldo must be even, scratch required");
     MDGAT_REQUIRE(attn_i8_supported(N, M), "mdgat_attention_i8: M = %d source keypoints exceed the shared-memory budget", M);
     // query planes from Q of the N-point set, source planes from K and V of the M-point set
-    AttnI8Side qs = attn_i8_carve(d_scratch, B, N);
-    AttnI8Side ks = attn_i8_carve(reinterpret_cast<char*>(d_scratch) + attn_i8_side_bytes(B, N), B, M);
+    AttnI8Side qs = attn_i8_carve(d_scratch, B, N, AS);
+    AttnI8Side ks = attn_i8_carve(reinterpret_cast<char*>(d_scratch) + attn_i8_side_bytes(B, N, AS), B, M, AS);
     MDGAT_CUDA_OK(launch_attn_i8_slice(d_Q, nullptr, nullptr, qs, B, st));
     MDGAT_CUDA_OK(launch_attn_i8_slice(nullptr, d_K, d_V, ks, B, st));
     AttnSides ps;
     memset(&ps, 0, sizeof(ps));
     ps.Q[0] = d_Q; ps.K[0] = d_K; ps.V[0] = d_V; ps.Out[0] = d_Out; ps.N[0] = N; ps.M[0] = M;
-    MDGAT_CUDA_OK(attention_layer(ps, B, 1, ldo, topk, d_logits, st, &qs, &ks));
+    MDGAT_CUDA_OK(attention_layer(ps, B, 1, ldo, topk, d_logits, st, &qs, &ks, ASP));
     return MDGAT_OK;
 }
 

@@ -97,16 +97,18 @@ struct AttnI8Side {
     double *qscale, *kscale, *vscale;     // per query row, per source row, per (b, h, channel)
     float *kscale_f, *ktilemax;           // fp32 copy of kscale, largest kscale per source tile
     int n;                                // keypoints of this side
+    int S;                                // digit planes per operand (4..7)
 };
-size_t attn_i8_side_bytes(int B, int n);
-AttnI8Side attn_i8_carve(void* base, int B, int n);
+size_t attn_i8_side_bytes(int B, int n, int S);
+AttnI8Side attn_i8_carve(void* base, int B, int n, int S);
 bool attn_i8_supported(int N, int M);
 cudaError_t launch_attn_i8_slice(const double* Qh, const double* Kh, const double* Vh, const AttnI8Side& o, int B, cudaStream_t st);
 // both sides of a layer (index 0 / 1) in one launch
 cudaError_t launch_attn_i8_slice_sides(const double* const* Qh, const double* const* Kh, const double* const* Vh, const AttnI8Side* o,
                                        int B, cudaStream_t st);
+// SP: byte planes of the probabilities; supported (S, SP): (4,3) (4,4) (5,4) (6,5) (7,6)
 cudaError_t launch_attn_i8(const AttnI8Side* q, const AttnI8Side* kv, double* const* Out, int B, int nsides, int ldo,
-                           bool logits_only, cudaStream_t st);
+                           bool logits_only, int SP, cudaStream_t st);
 
 // Batched Kabsch registration + match statistics (one CTA per pair)
 cudaError_t launch_register_pairs(const void* kpts0, const void* kpts1, int kp_dtype, const int64_t* matches0,

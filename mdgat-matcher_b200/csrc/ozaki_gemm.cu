@@ -613,6 +613,8 @@ cudaError_t launch_slice_rows(const double* A0, int ld0, int K0, const double* A
     cudaError_t e;
     const size_t chunk_stride = ozaki_slices_bytes(R, OZ_KC, S);     // chunk c of the input goes to Xs + c * chunk_stride
     switch (S) {
+        case 4: e = slice_rows_t<4>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale, chunk_stride, st); break;
+        case 5: e = slice_rows_t<5>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale, chunk_stride, st); break;
         case 6: e = slice_rows_t<6>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale, chunk_stride, st); break;
         case 7: e = slice_rows_t<7>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale, chunk_stride, st); break;
         default: return cudaErrorInvalidValue;
@@ -688,6 +690,8 @@ cudaError_t launch_ozaki_gemm(const OzGemmArgs& a, int S, cudaStream_t st) {
     }
     cudaError_t e;
     switch (S) {
+        case 4: e = ozaki_gemm_t<4>(p, grid, st); break;
+        case 5: e = ozaki_gemm_t<5>(p, grid, st); break;
         case 6: e = ozaki_gemm_t<6>(p, grid, st); break;
         case 7: e = ozaki_gemm_t<7>(p, grid, st); break;
         default: return cudaErrorInvalidValue;

@@ -257,6 +257,7 @@ class MDGAT(nn.Module):
         self._pack_cache = _PackedWeights()     # shared by reference with DataParallel replicas
         self._is_replica = False
         self._workspaces = {}                   # device -> uint8 tensor (shared dict: one workspace per device)
+        self._graphs = {}                       # config['cuda_graph']: captured forward per (shape, weights, workspace)
         self._layer_k = None
 
     # ------------------------------------------------------------------ packed-weight cache
@@ -266,12 +267,16 @@ class MDGAT(nn.Module):
             key.append((t.data_ptr(), t._version, t.dtype))
         return tuple(key)
 
+    def invalidate_graphs(self):
+        self._graphs.clear()
+
     def invalidate_packed(self):
         """Forget the packed weight blobs. The cache is keyed on (storage pointer, version counter, dtype) of every
         parameter and buffer, which catches optimizer steps, load_state_dict, .to() / .double() and in-place tensor ops,
         but NOT writes made through `param.data` (that view has its own version counter): after
         `p.data.mul_()`-style edits call this method. load_state_dict() and the train() -> eval() transition call it."""
         self._pack_cache.invalidate()
+        self._graphs.clear()
 
     def load_state_dict(self, *args, **kwargs):
         res = super().load_state_dict(*args, **kwargs)
@@ -305,13 +310,31 @@ class MDGAT(nn.Module):
             self._pack_cache.refresh(self)
         return self._pack_cache.blob(self, self._param_device() if device is None else device)
 
+    # int8 digit planes per float64 operand: (GEMM operands, attention q/k/v, attention probabilities).
+    # 'sweep': the smallest counts with 0 index flips and score error <= 7e-8 (bar: 1e-4) on the 131 k-row sweep against
+    # the unmodified reference (tests/golden/sweep, tests/test_gpu_sweep.py); one plane less on any
+    # operand breaks the 1e-5 margin (tools/precision_model.py). 'exact': float64-faithful to ~1e-13.
+    PRECISIONS = {'sweep': (5, 5, 4), 'exact': (7, 7, 6)}
+
+    def digit_planes(self):
+        """(gemm_slices, attn_slices, attn_p_slices) from config['precision'] ('sweep' default | 'exact'), each
+        overridable by the config key of the same name."""
+        name = self.config.get('precision', 'sweep')
+        if name not in self.PRECISIONS:
+            raise ValueError("config['precision'] must be one of %s" % sorted(self.PRECISIONS))
+        g, a, sp = self.PRECISIONS[name]
+        g = int(self.config.get('gemm_slices', g))
+        a = int(self.config.get('attn_slices', a))
+        sp = int(self.config.get('attn_p_slices', min(sp, a) if a == 4 else a - 1))
+        return g, a, sp
+
     def gemm_engine(self):
-        """config['gemm']: 'tcgen05_i8' (float64-faithful Ozaki splitting on the int8 tensor cores, default)
-        or 'dmma' (FP64 pipe); config['gemm_slices']: int8 digit planes per operand (6 or 7, default 7)."""
+        """config['gemm']: 'tcgen05_i8' (Ozaki splitting on the int8 tensor cores, default) or 'dmma' (FP64 pipe);
+        the number of int8 digit planes per operand comes from digit_planes()."""
         mode = self.config.get('gemm', 'tcgen05_i8')
         if mode not in ('tcgen05_i8', 'dmma'):
             raise ValueError("config['gemm'] must be 'tcgen05_i8' or 'dmma'")
-        return mode, int(self.config.get('gemm_slices', 7))
+        return mode, self.digit_planes()[0]
 
     def attention_engine(self):
         """config['attention']: 'tcgen05_i8' (default; Q K^T and P V of the full-attention layers as exact int8
@@ -402,15 +425,8 @@ class MDGAT(nn.Module):
                 gt0_t, gt1_t = self._gt(data)
             write_Z = self.loss_method in ('gap_loss', 'superglue') or bool(self.config.get('return_assignment', False))
 
-            matches0 = torch.empty((B, N), dtype=torch.int64, device=dev)
-            matches1 = torch.empty((B, M), dtype=torch.int64, device=dev)
-            ms0 = torch.empty((B, N), dtype=torch.float64, device=dev)
-            ms1 = torch.empty((B, M), dtype=torch.float64, device=dev)
-            loss = torch.zeros((), dtype=torch.float64, device=dev)
-            nvalid = torch.zeros((), dtype=torch.int32, device=dev)
-            Z = torch.empty((B, N + 1, M + 1), dtype=torch.float64, device=dev) if write_Z else None
-
             karr = (ctypes.c_int * len(sched))(*sched)
+            planes = self.digit_planes()
             cfg = _capi.ForwardCfg(
                 B=B, N=N, M=M, L=L, sinkhorn_iters=int(self.config['sinkhorn_iterations']), layer_k=karr,
                 match_mode=_capi.MATCH_THRESHOLD if self.loss_method == 'superglue' else _capi.MATCH_DUSTBIN,
@@ -422,22 +438,71 @@ class MDGAT(nn.Module):
                 gemm_mode=_capi.GEMM_TCGEN05_I8 if gemm_mode == 'tcgen05_i8' else _capi.GEMM_DMMA_F64,
                 gemm_slices=gemm_slices,
                 attn_mode={'tcgen05_i8': _capi.ATTN_TCGEN05_I8, 'tcgen05_i8_all': _capi.ATTN_TCGEN05_I8_ALL,
-                           'dmma': _capi.ATTN_DMMA_F64}[self.attention_engine()])
+                           'dmma': _capi.ATTN_DMMA_F64}[self.attention_engine()],
+                attn_slices=planes[1], attn_p_slices=planes[2])
             need = _capi.lib.mdgat_forward_workspace_bytes(ctypes.byref(cfg))
             ws = self._workspaces.get(dev)
             if ws is None or ws.numel() < need:
                 ws = torch.empty(need, dtype=torch.uint8, device=dev)
                 self._workspaces[dev] = ws
-            fin = _capi.ForwardIn(tens[0].data_ptr(), tens[1].data_ptr(), tens[2].data_ptr(), tens[3].data_ptr(),
-                                  sc[0].data_ptr(), sc[1].data_ptr(),
-                                  gt0.data_ptr() if gt0 is not None else None,
-                                  gt1.data_ptr() if gt1 is not None else None)
-            fout = _capi.ForwardOut(matches0.data_ptr(), matches1.data_ptr(), ms0.data_ptr(), ms1.data_ptr(),
-                                    loss.data_ptr(), nvalid.data_ptr(), Z.data_ptr() if Z is not None else None)
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            _capi.check(_capi.lib.mdgat_forward(ctypes.byref(cfg), blob.data_ptr(),
-                                                blob_i8.data_ptr() if blob_i8 is not None else None, ctypes.byref(fin),
-                                                ctypes.byref(fout), ws.data_ptr(), ws.numel(), stream))
+
+            def new_outputs():
+                # one buffer: [matches0 | matches1 | scores0 | scores1 | loss | valid count], carved into typed views
+                n0, n1 = B * N, B * M
+                ob = torch.zeros(2 * (n0 + n1) + 2, dtype=torch.int64, device=dev)
+                return ob, (ob[:n0].view(B, N), ob[n0:n0 + n1].view(B, M),
+                            ob[n0 + n1:2 * n0 + n1].view(torch.float64).view(B, N),
+                            ob[2 * n0 + n1:2 * (n0 + n1)].view(torch.float64).view(B, M),
+                            ob[2 * (n0 + n1):2 * (n0 + n1) + 1].view(torch.float64).reshape(()),
+                            ob[2 * (n0 + n1) + 1:].view(torch.int32)[0])
+
+            def launch(ins, outs, Zt):
+                fin = _capi.ForwardIn(*[t.data_ptr() if t is not None else None for t in ins])
+                fout = _capi.ForwardOut(outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(),
+                                        outs[4].data_ptr(), outs[5].data_ptr(), Zt.data_ptr() if Zt is not None else None)
+                _capi.check(_capi.lib.mdgat_forward(ctypes.byref(cfg), blob.data_ptr(),
+                                                    blob_i8.data_ptr() if blob_i8 is not None else None, ctypes.byref(fin),
+                                                    ctypes.byref(fout), ws.data_ptr(), ws.numel(),
+                                                    torch.cuda.current_stream(dev).cuda_stream))
+
+            ins = tens + sc + [gt0, gt1]
+            Z = torch.empty((B, N + 1, M + 1), dtype=torch.float64, device=dev) if write_Z else None
+            if self.config.get('cuda_graph', False) and not write_Z:
+                # config['cuda_graph']: the fixed launch sequence of one forward (about 150 kernels) is captured once per
+                # (shape, dtypes, weights, workspace) and replayed; the inputs are copied into the graph's static buffers
+                # and the results out of them, so the caller sees fresh tensors as with plain launches
+                key = (dev, B, N, M, in_dtype, sc[0].dtype, loss_mode, tuple(sched), tuple(planes), gemm_mode,
+                       self.attention_engine(), int(self.config['sinkhorn_iterations']), bool(self.mutual_check),
+                       blob.data_ptr(), blob_i8.data_ptr() if blob_i8 is not None else 0, ws.data_ptr())
+                ent = self._graphs.get(key)
+                if ent is None:
+                    static_in = [torch.empty_like(t) if t is not None else None for t in ins]
+                    ob, outs = new_outputs()
+                    for a, b_ in zip(static_in, ins):
+                        if a is not None:
+                            a.copy_(b_)
+                    side = torch.cuda.Stream(device=dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        launch(static_in, outs, None)              # plain run first: lazy one-time initialisation stays out of the capture
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        launch(static_in, outs, None)
+                    ent = (graph, [a for a in static_in if a is not None], ob, ws, blob, blob_i8)
+                    self._graphs[key] = ent
+                torch._foreach_copy_(ent[1], [t for t in ins if t is not None])
+                ent[0].replay()
+                n0, n1 = B * N, B * M
+                res = ent[2].clone()
+                matches0, matches1 = res[:n0].view(B, N), res[n0:n0 + n1].view(B, M)
+                ms0 = res[n0 + n1:2 * n0 + n1].view(torch.float64).view(B, N)
+                ms1 = res[2 * n0 + n1:2 * (n0 + n1)].view(torch.float64).view(B, M)
+                loss = res[2 * (n0 + n1):2 * (n0 + n1) + 1].view(torch.float64).reshape(())
+                nvalid = res[2 * (n0 + n1) + 1:].view(torch.int32)[0]
+            else:
+                _, (matches0, matches1, ms0, ms1, loss, nvalid) = new_outputs()
+                launch(ins, (matches0, matches1, ms0, ms1, loss, nvalid), Z)
             if self.loss_method == 'gap_loss':
                 loss = losses.gap_loss(Z, gt0_t.long(), gt1_t.long(), self.triplet_loss_gamma)
             elif self.loss_method == 'superglue':

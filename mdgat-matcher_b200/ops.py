@@ -69,7 +69,7 @@ def to_head_major(t, ld):
     return out.contiguous()
 
 
-def attention(q, k, v, topk=None, engine='dmma'):
+def attention(q, k, v, topk=None, engine='dmma', slices=7, p_slices=0):
     """q (B,128,N), k/v (B,128,M) in the reference's channel layout. Returns the message
     (B,128,N) in the reference layout (what attention()/dynamic_attention() return after
     .view(B, 128, N), mdgat.py:229-237 before the merge conv)."""
@@ -85,7 +85,7 @@ def attention(q, k, v, topk=None, engine='dmma'):
             scratch = torch.empty(_capi.lib.mdgat_attention_i8_scratch_bytes(B, N, M), dtype=torch.uint8, device=q.device)
             _capi.check(_capi.lib.mdgat_attention_i8(qh.data_ptr(), kh.data_ptr(), vh.data_ptr(), out.data_ptr(), LDX,
                                                      B, N, M, kk, logits.data_ptr() if logits is not None else None,
-                                                     scratch.data_ptr(), _stream(q.device)))
+                                                     scratch.data_ptr(), int(slices), int(p_slices), _stream(q.device)))
         elif engine == 'dmma':
             _capi.check(_capi.lib.mdgat_attention_f64(qh.data_ptr(), kh.data_ptr(), vh.data_ptr(), out.data_ptr(), LDX,
                                                       B, N, M, kk, logits.data_ptr() if logits is not None else None,

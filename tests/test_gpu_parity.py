@@ -51,10 +51,12 @@ def test_linear_concat_inputs(dev):
     assert np.abs(got - want).max() < 1e-11
 
 
-@pytest.mark.parametrize('R,K,Nout,slices', [(128, 128, 64, 7), (1000, 128, 384, 7), (333, 256, 256, 7), (4096, 256, 128, 7), (500, 128, 128, 6)])
+@pytest.mark.parametrize('R,K,Nout,slices', [(128, 128, 64, 7), (1000, 128, 384, 7), (333, 256, 256, 7), (4096, 256, 128, 7), (500, 128, 128, 6),
+                                             (1000, 128, 384, 5), (4096, 256, 128, 5), (333, 256, 256, 4)])
 def test_linear_i8_tensor_core_gemm_is_float64_faithful(dev, R, K, Nout, slices):
     """tcgen05 int8 (Ozaki) GEMM against a float64 numpy product: error relative to |x|max |w|max sqrt(K)
-    must be at float64 rounding level for 7-8 slices (2^-42 class for 6)."""
+    must be at float64 rounding level for 7 slices and scales with 2^-7 per slice below that (6: 2^-42 class,
+    5 -- the sweep default -- 2^-35 class, 4: 2^-28 class)."""
     from mdgat_matcher_b200 import ops
     rng = np.random.default_rng(R + K + Nout)
     x = rng.normal(size=(R, K)) * np.exp(rng.normal(size=(R, 1)) * 2)       # rows of very different scale
@@ -66,7 +68,7 @@ def test_linear_i8_tensor_core_gemm_is_float64_faithful(dev, R, K, Nout, slices)
     got = ops.linear_i8(_t(x, dev), _t(w, dev), _t(b, dev), relu=True, residual=_t(res, dev), slices=slices).cpu().numpy()
     scale = np.abs(x).max(1, keepdims=True) * np.abs(w).max(1)[None, :] * np.sqrt(K)
     err = np.abs(got - want) / scale
-    assert err.max() < {6: 2e-11, 7: 2e-13}[slices], err.max()
+    assert err.max() < {4: 4e-7, 5: 3e-9, 6: 2e-11, 7: 2e-13}[slices], err.max()
 
 
 def test_linear_i8_concat_and_zero_rows(dev):
@@ -102,6 +104,21 @@ def test_attention_full_vs_oracle(dev, N, M, engine):
     want, _ = O.attention(q.reshape(2, 32, 4, N), k.reshape(2, 32, 4, M), v.reshape(2, 32, 4, M))
     got = ops.attention(_t(q, dev), _t(k, dev), _t(v, dev), engine=engine).cpu().numpy()
     assert np.abs(got - want.reshape(2, 128, N)).max() < ENGINE_TOL[engine]
+
+
+@pytest.mark.parametrize('slices,p_slices,tol', [(5, 4, 2e-8), (6, 5, 1e-10), (4, 4, 5e-6), (4, 3, 2e-5)])
+@pytest.mark.parametrize('N,M', [(128, 128), (200, 77), (513, 300), (33, 17)])
+def test_attention_i8_reduced_planes_vs_oracle(dev, N, M, slices, p_slices, tol):
+    """The reduced digit-plane settings of the tcgen05 attention (5 / 4 = the sweep default): error scales with
+    2^-8 per plane; messages are convex combinations of |v| <= ~4, so the bounds are absolute."""
+    from mdgat_matcher_b200 import ops
+    from oracle import mdgat_oracle as O
+    rng = np.random.default_rng(N * 7 + M)
+    q = rng.normal(size=(2, 128, N)) * 3; k = rng.normal(size=(2, 128, M)) * 3; v = rng.normal(size=(2, 128, M))
+    want, _ = O.attention(q.reshape(2, 32, 4, N), k.reshape(2, 32, 4, M), v.reshape(2, 32, 4, M))
+    got = ops.attention(_t(q, dev), _t(k, dev), _t(v, dev), engine='tcgen05_i8', slices=slices, p_slices=p_slices).cpu().numpy()
+    err = np.abs(got - want.reshape(2, 128, N)).max()
+    assert err < tol, err
 
 
 def test_attention_i8_wide_dynamic_range(dev):
@@ -271,12 +288,21 @@ E2E = ['cfg1_seeded_L4_n128', 'ckpt_L9_n512_T100', 'ckpt_L9_ragged_gap', 'ckpt_L
        'seeded_L9_n512', 'ckpt_L9_duplicates', 'ckpt_L9_sgloss_mutual', 'ckpt_L9_n2048', 'ckpt_L9_n512_b8']
 
 
-@pytest.mark.parametrize('gemm,attention', [('tcgen05_i8', 'tcgen05_i8'), ('tcgen05_i8', 'tcgen05_i8_all'), ('tcgen05_i8', 'dmma'), ('dmma', 'dmma')])
+# (gemm engine, attention engine, precision): 'sweep' = 5/5/4 digit planes (the default), 'exact' = 7/7/6
+ENGINES = [('tcgen05_i8', 'tcgen05_i8', 'sweep'), ('tcgen05_i8', 'tcgen05_i8_all', 'sweep'),
+           ('tcgen05_i8', 'tcgen05_i8', 'exact'), ('tcgen05_i8', 'tcgen05_i8_all', 'exact'),
+           ('tcgen05_i8', 'dmma', 'exact'), ('dmma', 'dmma', 'exact')]
+
+
+@pytest.mark.parametrize('gemm,attention,precision', ENGINES)
 @pytest.mark.parametrize('name', E2E)
-def test_forward_matches_reference_golden(dev, name, gemm, attention):
+def test_forward_matches_reference_golden(dev, name, gemm, attention, precision):
     rec = load_golden(name)
     case = rec['case']
-    net = _build_module(case, dev, extra={'return_assignment': True, 'gemm': gemm, 'attention': attention})
+    net = _build_module(case, dev, extra={'return_assignment': True, 'gemm': gemm, 'attention': attention, 'precision': precision})
+    # the float64-faithful setting must stay at float64 noise; the sweep setting (35 / 39-bit operands) is held to
+    # 1e-6, a hundred times below the bar (its measured worst case on the 131 k-row sweep is 7e-8)
+    tol_s, tol_z = (1e-7, 1e-6) if precision == 'exact' else (1e-6, 5e-5)
     data = {k: _t(v, dev) for k, v in golden_inputs(rec).items()}
     out = net(data)
     torch.cuda.synchronize()
@@ -286,13 +312,13 @@ def test_forward_matches_reference_golden(dev, name, gemm, attention):
     e0 = np.abs(out['matching_scores0'].cpu().numpy() - rec['matching_scores0']).max()
     e1 = np.abs(out['matching_scores1'].cpu().numpy() - rec['matching_scores1']).max()
     assert max(e0, e1) <= SCORE_TOL
-    assert max(e0, e1) <= 1e-7, 'float64 path drifted: %g' % max(e0, e1)
+    assert max(e0, e1) <= tol_s, '%s path drifted: %g' % (precision, max(e0, e1))
     Z = out['assignment'].cpu().numpy()
     if 'Z' in rec:
-        assert np.abs(Z - rec['Z']).max() <= 1e-6
-    assert np.abs(Z[:, :-1, :].max(2) - rec['Z_rowmax']).max() <= 1e-6
+        assert np.abs(Z - rec['Z']).max() <= tol_z
+    assert np.abs(Z[:, :-1, :].max(2) - rec['Z_rowmax']).max() <= tol_z
     if out['loss'] is not None:
-        assert np.allclose(out['loss'].cpu().numpy(), rec['loss'], rtol=0, atol=1e-6)
+        assert np.allclose(out['loss'].cpu().numpy(), rec['loss'], rtol=0, atol=max(tol_s, 1e-6))
     # the reference rewrites gt_matches in place (mdgat.py:519-520)
     if case.get('loss_method', 'triplet_loss') != 'superglue':
         assert int((data['gt_matches0'] == -1).sum()) == 0
@@ -306,7 +332,7 @@ def test_superglue_module_is_full_attention_mdgat(dev):
     data['match0'], data['match1'] = data.pop('gt_matches0'), data.pop('gt_matches1')
     out = net(data)
     assert np.array_equal(out['matches0'].cpu().numpy(), rec['matches0'])
-    assert np.abs(out['matching_scores0'].cpu().numpy() - rec['matching_scores0']).max() <= 1e-7
+    assert np.abs(out['matching_scores0'].cpu().numpy() - rec['matching_scores0']).max() <= 1e-6
 
 
 def test_k_larger_than_M_raises_and_empty_returns(dev):
@@ -341,7 +367,7 @@ def test_cfg2_full_size_properties(dev):
     m0 = out['matches0'].cpu().numpy()
     # (1) the first eight pairs are the golden batch: batch elements are independent
     assert np.array_equal(m0[:8], rec['matches0'])
-    assert np.abs(out['matching_scores0'].cpu().numpy()[:8] - rec['matching_scores0']).max() <= 1e-7
+    assert np.abs(out['matching_scores0'].cpu().numpy()[:8] - rec['matching_scores0']).max() <= 1e-6
     # (2) shard equivalence: two half batches reproduce the full batch bit for bit (multi-GPU sharding relies on it)
     halves = [net({k: v[i:i + 16].clone() for k, v in data.items()}) for i in (0, 16)]
     for key in ('matches0', 'matches1', 'matching_scores0', 'matching_scores1'):
@@ -426,7 +452,7 @@ def test_reference_eval_loop_plumbing(dev):
         data = net(pred)
         m0 = data['matches0'].cpu().detach().numpy()
         assert np.array_equal(m0, rec['matches0'])
-        assert np.abs(data['matching_scores0'].cpu().numpy() - rec['matching_scores0']).max() <= 1e-7
+        assert np.abs(data['matching_scores0'].cpu().numpy() - rec['matching_scores0']).max() <= 1e-6
         blobs.append(net.module.packed_weights().data_ptr())
     assert len(set(blobs)) == 1, 'packed weights were rebuilt although no parameter changed'
     # a parameter update invalidates the cache

@@ -235,8 +235,32 @@ def compare(out, ref):
     return res
 
 
+def run_golden(names, configs):
+    """The same comparison on the committed golden cases of tests/golden (other shapes, weights, k lists)."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from conftest import load_golden, golden_inputs, case_weights
+    for name in names:
+        rec = load_golden(name)
+        case = rec['case']
+        sd = {k: torch.from_numpy(np.asarray(v)) for k, v in case_weights(case).items()}
+        data = {k: torch.from_numpy(v) for k, v in golden_inputs(rec).items()}
+        k_list = case.get('k', DEFAULT_K)
+        if case.get('loss_method') == 'superglue':
+            print(json.dumps({'case': name, 'skipped': 'threshold match variant not modelled'}))
+            continue
+        ref = {k: rec[k] for k in ('matches0', 'matches1', 'matching_scores0', 'matching_scores1', 'Z_rowmax')}
+        for cs in configs:
+            t = time.time()
+            with torch.no_grad():
+                out = forward_model(sd, data, case['L'], case['T'], k_list, parse_config(cs))
+            r = compare(out, ref)
+            r.update(case=name, config=cs, seconds=round(time.time() - t, 1))
+            print(json.dumps(r), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument('--golden', nargs='+', default=None, help='golden case names (tests/golden) instead of sweep cases')
     ap.add_argument('--cases', nargs='+', default=['sweep_s100_b16'])
     ap.add_argument('--configs', nargs='+', default=['7/7/6', '5/5/4', '4/4/3'])
     ap.add_argument('--pairs', type=int, default=0, help='only the first n pairs of each case (0 = all)')
@@ -244,6 +268,9 @@ def main():
     args = ap.parse_args()
     if args.threads:
         torch.set_num_threads(args.threads)
+    if args.golden:
+        run_golden(args.golden, args.configs)
+        return
     sd_np = load_checkpoint_state_dict()
     sd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd_np.items()}
     for cname in args.cases:

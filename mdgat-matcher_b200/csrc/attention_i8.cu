@@ -44,7 +44,7 @@ constexpr int AI_STAGES = 3;               // K/V tile ring
 // sub-partition); the MMA and loader warps follow the epilogue warps
 constexpr int ai_epi_threads(int cw) { return 128 * (32 / cw); }
 constexpr int ai_threads(int cw) { return ai_epi_threads(cw) + 64; }
-constexpr int AI_CVT_DEFAULT = 1;          // int32 -> float64 conversion of the epilogue (int_to_f64)
+constexpr int AI_CVT_DEFAULT = 0;          // int32 -> float64 conversion of the epilogue (int_to_f64)
 constexpr int AI_EXP_LIMIT = 60;           // |exponent| clamp of the digit scales (values beyond 2^60 are out of range)
 
 size_t attn_i8_q_bytes(int B, int n, int S) { return (size_t)B * HEADS * ((n + AI_BM - 1) / AI_BM) * S * AI_QPLANE; }
@@ -267,7 +267,7 @@ DEVINL void ai_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;
 DEVINL void ai_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 template <int THREADS> DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, %0;" :: "n"(THREADS) : "memory"); }   // the epilogue warps only
 // int32 -> float64, exact. CVT selects the instruction mix (the epilogue is issue-bound, the three pipes are not):
-//   0  sign bit flipped into the low mantissa word of 2^52 (LOP3 + a MOV for the high word), minus 2^52 + 2^31 (DADD)
+//   0  (default) sign bit flipped into the low mantissa word of 2^52 (LOP3 + a MOV for the high word), minus 2^52 + 2^31 (DADD)
 //   1  I2F.F64.S32: one instruction on the conversion pipe (16 lanes / clk / SM), nothing on the FP64 pipe
 //   2  the bit pattern of 2^52 + 2^31 + v built by 64-bit integer multiply-adds (IMAD.WIDE), minus 2^52 + 2^31 (DADD)
 constexpr long long AI_MAGIC_BITS = 0x4330000080000000LL;      // 2^52 + 2^31 as a double
@@ -299,9 +299,11 @@ DEVINL constexpr uint32_t ai_idesc(int n, bool a_signed) {
 
 // sum_dd acc[dd][j] 256^(-dd), times 256 when S is even (the caller folds 2^-8 into the row factor): the diagonals are
 // merged in pairs exactly in int32 (|acc_dd| <= S * 32 * 2^14 < 2^22) from the least significant end, then Horner in float64
-template <int S, int CW, int CVT>
+// CVT == 3: the least significant pair through I2F (conversion pipe), the others through the 2^52 constant (ALU + FP64 pipe)
+template <int S, int CW, int CVTX>
 DEVINL double ai_recombine(const int (&acc)[S][CW], int j) {
-    double h = pair_to_f64<CVT>(acc[S - 2][j], acc[S - 1][j]);
+    constexpr int CVT = CVTX == 3 ? 0 : CVTX;
+    double h = pair_to_f64<CVTX == 3 ? 1 : CVT>(acc[S - 2][j], acc[S - 1][j]);
 #pragma unroll
     for (int d = S - 4; d >= (S & 1); d -= 2) h = fma(h, 1.52587890625e-05, pair_to_f64<CVT>(acc[d][j], acc[d + 1][j]));
     if (S & 1) h = fma(h, 1.52587890625e-05, int_to_f64<CVT>(acc[0][j]));
@@ -312,25 +314,28 @@ DEVINL double ai_recombine(const int (&acc)[S][CW], int j) {
 // 256-entry table 2^(j/256), |r| <= ln2/512: the cubic is good to 1.4e-13 relative (SP <= 4: 32-bit probabilities), the
 // quartic to 4e-17 (SP > 4); one correctly rounded ln2/256 suffices under the FMA. The power of two, the 2^(8 SP - 1)
 // scale and the underflow clamp are one integer add into the exponent field; results below 1/2 round to 0.
-// tbl_s32: shared-window address of the table, 2 KB aligned (entry address = base | (n mod 256) * 8: one LOP3).
+// Table of 2^(j/E): E = 16 entries for SP <= 4 -- 128 bytes, one entry per bank pair, so the 32 random lookups of a warp
+// never conflict (a 256-entry table costs ~9 shared-memory wavefronts per warp instead of 2); |r| <= ln2/32 and the quartic
+// is good to 4e-11 relative, a fifth of the last probability bit. SP > 4 (float64-faithful mode): 256 entries, |r| <= ln2/512,
+// quartic good to 4e-17. tbl_s32: shared-window address of the table, aligned to its size (entry address = base | index * 8).
 template <int SP>
 DEVINL void ai_exp_fixed(double x, uint32_t tbl_s32, uint32_t& lo, uint32_t& hi) {
+    constexpr int E = SP > 4 ? 256 : 16, EL = SP > 4 ? 8 : 4;
     const double MAGIC = 6755399441055744.0;                // 1.5 * 2^52: rint() in the low mantissa bits
-    // n + 256 (8 SP - 1) in the low mantissa word: the 2^(8 SP - 1) scale rides along in the exponent part n >> 8
-    const double MAGIC_N = MAGIC + 256.0 * (8 * SP - 1);
-    const double tn = fma(x, EXP_INV_LN2_256, MAGIC_N);
+    // n + E (8 SP - 1) in the low mantissa word: the 2^(8 SP - 1) scale rides along in the exponent part n >> EL
+    const double MAGIC_N = MAGIC + (double)E * (8 * SP - 1);
+    const double tn = fma(x, EXP_INV_LN2_256 * (E / 256.0), MAGIC_N);
     const int n = __double2loint(tn);
     const double nd = tn - MAGIC_N;
-    const double r = fma(nd, -EXP_LN2_256, x);
+    const double r = fma(nd, -EXP_LN2_256 * (256.0 / E), x);
     const double r2 = r * r;
-    double q;
-    if (SP > 4) { q = fma(r, 1.0 / 24.0, 1.0 / 6.0); q = fma(q, r, 0.5); }
-    else q = fma(r, 1.0 / 6.0, 0.5);
+    double q = fma(r, 1.0 / 24.0, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
     const double pl = fma(r2, q, r);                         // e^r - 1
     double t;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(tbl_s32 | (((uint32_t)n << 3) & 0x7f8u)));
-    const double y = fma(t, pl, t);                          // in (0.99, 2.01)
-    const int m = max(n >> 8, -9);                           // exp(x) 2^(8 SP - 1) < 2^-9 rounds to 0 like anything smaller
+    asm("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(tbl_s32 | (((uint32_t)n << 3) & (uint32_t)(8 * E - 8))));
+    const double y = fma(t, pl, t);                          // in (0.97, 2.05)
+    const int m = max(n >> EL, -9);                          // exp(x) 2^(8 SP - 1) < 2^-9 rounds to 0 like anything smaller
     const double ys = __hiloint2double(__double2hiint(y) + (m << 20), __double2loint(y));
     const double pm = ys + MAGIC;
     lo = (uint32_t)__double2loint(pm);
@@ -355,7 +360,10 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
     constexpr int AI_EPI_THREADS = ai_epi_threads(CW), EPI_WARPS = AI_EPI_THREADS / 32, NCG = 32 / CW;
     constexpr int NSBUF = (3 * S * AI_BN <= 512) ? 2 : 1;
     constexpr int TM_S = 0;                               // TMEM columns: NSBUF sets of S logits diagonals
-    constexpr int TM_O = NSBUF * S * AI_BN;               //               S P V diagonals; pass 1 borrows the first 128 columns
+    constexpr int TM_O = NSBUF * S * AI_BN;               //               S P V diagonals
+    // pass 1 borrows four 64-column buffers: two at the start of the P V region, two at the start of the LAST logits set
+    // (the first Q K^T product into that set waits for the end of pass 1)
+    constexpr int TM_P1_LO = TM_O, TM_P1_HI = TM_S + (NSBUF - 1) * S * AI_BN;
     constexpr int STAGE_BYTES = 2 * S * AI_KPLANE;
     static_assert(SP <= S && SP >= 3 && SP <= 6 && S * AI_BN >= 128 && TM_O + S * AI_BN <= 512, "plane counts");
     extern __shared__ __align__(128) unsigned char ai_smem[];
@@ -384,7 +392,7 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
     double* s_xd = reinterpret_cast<double*>(s_ktm + ((T + 3) & ~3));             // [4][128] row exchange between column groups
     unsigned long long* s_xu = reinterpret_cast<unsigned long long*>(s_xd + 512); // [4][128]
 
-    __shared__ __align__(8) uint64_t q_full, kv_full[AI_STAGES], kv_empty[AI_STAGES], s1_full[2], s1_empty[2],
+    __shared__ __align__(8) uint64_t q_full, kv_full[AI_STAGES], kv_empty[AI_STAGES], s1_full[4], s1_empty[4], p1_done,
         s_full[NSBUF], s_empty[NSBUF], p_full[2], p_empty[2], o_full;
     __shared__ uint32_t tmem_base_s;
 
@@ -393,16 +401,16 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
 #pragma unroll
         for (int i = 0; i < AI_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&s1_full[i], 1); mbar_init(&s1_empty[i], AI_EPI_THREADS);
-            mbar_init(&p_full[i], AI_EPI_THREADS); mbar_init(&p_empty[i], 1);
-        }
+        for (int i = 0; i < 4; ++i) { mbar_init(&s1_full[i], 1); mbar_init(&s1_empty[i], AI_EPI_THREADS); }
+        mbar_init(&p1_done, AI_EPI_THREADS);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { mbar_init(&p_full[i], AI_EPI_THREADS); mbar_init(&p_empty[i], 1); }
 #pragma unroll
         for (int i = 0; i < NSBUF; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], AI_EPI_THREADS); }
         mbar_init(&o_full, 1);
         mbar_fence_init();
     }
-    exp_table256_to_shared(etab);
+    for (int i = tid; i < (SP > 4 ? 256 : 16); i += ai_threads(CW)) etab[i] = g_exp2_table256[SP > 4 ? i : 16 * i];
     if (warp == EPI_WARPS) {
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_s);
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(dst));
@@ -453,12 +461,12 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
             int u = 0;
             if (!LOGITS) {
                 for (int jt = 0; jt < T; ++jt, ++u) {
-                    const int stage = u % AI_STAGES, buf = jt & 1;
+                    const int stage = u % AI_STAGES, buf = jt & 3;
                     mbar_wait(&kv_full[stage], (unsigned)((u / AI_STAGES) & 1));
-                    if (jt >= 2) mbar_wait(&s1_empty[buf], (unsigned)(((jt >> 1) - 1) & 1));
+                    if (jt >= 4) mbar_wait(&s1_empty[buf], (unsigned)(((jt >> 2) - 1) & 1));
                     ai_fence_after();
                     const uint64_t kd = kd0 + (uint64_t)((stage * STAGE_BYTES) >> 4);
-                    const uint32_t d = tmem + TM_O + buf * 64;
+                    const uint32_t d = tmem + (buf < 2 ? TM_P1_LO + buf * 64 : TM_P1_HI + (buf - 2) * 64);
                     // diagonal 0 = D0 G0, diagonal 1 = D0 G1 + D1 G0
                     ai_mma(d, qd0, kd, ai_idesc(64, true), false);
                     ai_mma(d + 32, qd0 + (uint64_t)(AI_QPLANE >> 4), kd, ai_idesc(32, true), true);
@@ -470,6 +478,7 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
             auto qk_tile = [&](int jt, int stage) {
                 const int sb = jt % NSBUF, use = jt / NSBUF;
                 if (use >= 1) mbar_wait(&s_empty[sb], (unsigned)((use - 1) & 1));      // the epilogue has read the previous tile of this set
+                else if (!LOGITS && sb == NSBUF - 1) mbar_wait(&p1_done, 0);          // pass 1 borrowed the start of this set
                 ai_fence_after();
                 const uint64_t kd = kd0 + (uint64_t)((stage * STAGE_BYTES) >> 4);
 #pragma unroll
@@ -515,16 +524,17 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
         if (!LOGITS) {
             // ---- pass 1: c_i >= max_j z_ij from the two leading diagonals
             float amax = -INFINITY, kmax = 0.f;
-            for (int jt = 0; jt < T; ++jt) {
-                const int buf = jt & 1;
-                mbar_wait(&s1_full[buf], (unsigned)((jt >> 1) & 1));
+            // two tiles per trip: the TMEM loads of the second are in flight while the first is reduced (registers of an
+            // asynchronous load are scoreboarded; tcgen05.wait::ld is only needed before the buffers are handed back)
+            auto p1_load = [&](int jt, int (&a0)[CW], int (&a1)[CW]) {
+                const int buf = jt & 3;
+                mbar_wait(&s1_full[buf], (unsigned)((jt >> 2) & 1));
                 ai_fence_after();
-                int a0[CW], a1[CW];
-                ai_ldw(tlane + TM_O + buf * 64 + c0, a0);
-                ai_ldw(tlane + TM_O + buf * 64 + 32 + c0, a1);
-                ai_ld_wait();
-                ai_fence_before();
-                mbar_arrive(&s1_empty[buf]);
+                const uint32_t col = buf < 2 ? TM_P1_LO + buf * 64 : TM_P1_HI + (buf - 2) * 64;
+                ai_ldw(tlane + col + c0, a0);
+                ai_ldw(tlane + col + 32 + c0, a1);
+            };
+            auto p1_use = [&](int jt, const int (&a0)[CW], const int (&a1)[CW]) {
                 const float* kf = s_ksf + jt * AI_BN + c0;
                 kmax = fmaxf(kmax, s_ktm[jt]);
                 const int jbase = jt * AI_BN + c0;
@@ -538,7 +548,20 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
                         if (jbase + j < M) amax = fmaxf(amax, v);
                     }
                 }
+            };
+            for (int jt = 0; jt < T; jt += 2) {
+                int a0[CW], a1[CW], b0[CW], b1[CW];
+                const bool two = jt + 1 < T;
+                p1_load(jt, a0, a1);
+                if (two) p1_load(jt + 1, b0, b1);
+                p1_use(jt, a0, a1);
+                if (two) p1_use(jt + 1, b0, b1);
+                ai_ld_wait();
+                ai_fence_before();
+                mbar_arrive(&s1_empty[jt & 3]);
+                if (two) mbar_arrive(&s1_empty[(jt + 1) & 3]);
             }
+            mbar_arrive(&p1_done);
             // |dropped digits| <= 24.1 * 2^(e_i + f_j - 12); fp32 rounding of the leading part <= 2^-23 relative
             const double lead = (double)amax * 0.00390625 * r_i;
             double c = lead + fabs(lead) * 4.76837158203125e-07 + 24.2 * (double)kmax * r_i;
@@ -552,21 +575,29 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
         uint32_t bsum[SP];                                         // byte sums of this thread's p^ per plane (DP4A), exact
 #pragma unroll
         for (int a = 0; a < SP; ++a) bsum[a] = 0u;
-        for (int jt = 0; jt < T; ++jt) {
+        // The accumulator loads of tile jt + 1 are issued before the exponentials of tile jt and collected after them: the
+        // TMEM latency hides behind ~250 instructions, and the registers they land in are dead in between.
+        int acc[S][CW];
+        double z[CW];
+        auto s_load = [&](int jt) {
             const int sb = jt % NSBUF;
             mbar_wait(&s_full[sb], (unsigned)((jt / NSBUF) & 1));
             ai_fence_after();
-            int acc[S][CW];
 #pragma unroll
             for (int dd = 0; dd < S; ++dd) ai_ldw(tlane + TM_S + sb * (S * AI_BN) + dd * AI_BN + c0, acc[dd]);
+        };
+        auto s_collect = [&](int jt) {
             ai_ld_wait();
             ai_fence_before();
-            mbar_arrive(&s_empty[sb]);
-            const int jbase = jt * AI_BN + c0;
-            const double* ks = s_ksd + jbase;
-            double z[CW];
+            mbar_arrive(&s_empty[jt % NSBUF]);
+            const double* ks = s_ksd + jt * AI_BN + c0;
 #pragma unroll
             for (int j = 0; j < CW; ++j) z[j] = ai_recombine<S, CW, CVT>(acc, j) * ks[j];   // exact: ks is a power of two
+        };
+        s_load(0);
+        s_collect(0);
+        for (int jt = 0; jt < T; ++jt) {
+            const int jbase = jt * AI_BN + c0;
             if (LOGITS) {
                 if (row_ok) {
                     double* dst = p.Out[side] + ((long long)bh * N + row) * (long long)M + jbase;
@@ -578,8 +609,10 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
                         for (int j = 0; j < CW; ++j) if (jbase + j < M) dst[j] = z[j] * r_z;
                     }
                 }
+                if (jt + 1 < T) { s_load(jt + 1); s_collect(jt + 1); }
                 continue;
             }
+            if (NSBUF == 2 && jt + 1 < T) s_load(jt + 1);            // one accumulator set: tile jt + 1 is still being multiplied
             uint32_t lo[CW], hi[SP > 4 ? CW : 1];
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
@@ -619,6 +652,10 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy stores -> tensor core reads
             mbar_arrive(&p_full[buf]);
+            if (jt + 1 < T) {
+                if (NSBUF == 1) s_load(jt + 1);
+                s_collect(jt + 1);
+            }
         }
         if (!LOGITS) {
             unsigned long long rsum = 0ull;
@@ -758,14 +795,15 @@ cudaError_t launch_attn_i8(const AttnI8Side* q, const AttnI8Side* kv, double* co
     static const int cw = [] { const char* v = getenv("MDGAT_ATTN_CW"); return v && v[0] == '1' ? 16 : 8; }();
     // MDGAT_ATTN_CVT=0|1|2 (read once): int32 -> float64 conversion of the epilogue, see int_to_f64(); the sweep setting
     // (5, 4) is built in all three variants, the others with the default
-    static const int cvt = [] { const char* v = getenv("MDGAT_ATTN_CVT"); return v && v[0] >= '0' && v[0] <= '2' ? v[0] - '0' : AI_CVT_DEFAULT; }();
+    static const int cvt = [] { const char* v = getenv("MDGAT_ATTN_CVT"); return v && v[0] >= '0' && v[0] <= '3' ? v[0] - '0' : AI_CVT_DEFAULT; }();
     cudaError_t e;
     switch (S * 10 + SP) {
         case 43: e = attn_i8_go<4, 3, AI_CVT_DEFAULT>(p, grid, smem, logits_only, cw, st); break;
         case 44: e = attn_i8_go<4, 4, AI_CVT_DEFAULT>(p, grid, smem, logits_only, cw, st); break;
         case 54: e = cvt == 0 ? attn_i8_go<5, 4, 0>(p, grid, smem, logits_only, cw, st)
                    : cvt == 1 ? attn_i8_go<5, 4, 1>(p, grid, smem, logits_only, cw, st)
-                              : attn_i8_go<5, 4, 2>(p, grid, smem, logits_only, cw, st); break;
+                   : cvt == 2 ? attn_i8_go<5, 4, 2>(p, grid, smem, logits_only, cw, st)
+                              : attn_i8_go<5, 4, 3>(p, grid, smem, logits_only, cw, st); break;
         case 65: e = attn_i8_go<6, 5, AI_CVT_DEFAULT>(p, grid, smem, logits_only, cw, st); break;
         case 76: e = attn_i8_go<7, 6, AI_CVT_DEFAULT>(p, grid, smem, logits_only, cw, st); break;
         default: return cudaErrorInvalidValue;

@@ -161,6 +161,11 @@ def build_reference_net(cfg, weights='checkpoint', seed=0, target='cpu'):
 def run_reference(net, data):
     """forward() mutates gt_matches in place (mdgat.py:519-520); hand it copies."""
     d = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in data.items()}
+    # With a GPU visible, DataParallel.forward scatters its inputs to cuda:0 even when the wrapped module lives on the
+    # CPU; the CPU oracle / baseline therefore calls the wrapped (unmodified) MDGAT module directly.
+    call = net
+    if isinstance(net, torch.nn.DataParallel) and next(net.parameters()).device.type == 'cpu':
+        call = net.module
     with torch.no_grad():
-        out = net(d)
+        out = call(d)
     return out

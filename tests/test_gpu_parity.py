@@ -2,11 +2,13 @@
 oracle (oracle/mdgat_oracle.py) and the golden vectors produced by the unmodified reference.
 Bar: match indices bit-exact, scores within 1e-4 (BASELINE.json north_star); the float64
 kernels are in practice held to 1e-9."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, golden_inputs, case_cfg, case_weights
+from conftest import load_golden, golden_inputs, case_cfg, case_weights, GOLDEN
 
 pytestmark = pytest.mark.gpu
 
@@ -106,7 +108,7 @@ def test_attention_full_vs_oracle(dev, N, M, engine):
     assert np.abs(got - want.reshape(2, 128, N)).max() < ENGINE_TOL[engine]
 
 
-@pytest.mark.parametrize('slices,p_slices,tol', [(5, 4, 2e-8), (6, 5, 1e-10), (4, 4, 5e-6), (4, 3, 2e-5)])
+@pytest.mark.parametrize('slices,p_slices,tol', [(5, 4, 5e-8), (6, 5, 5e-10), (4, 4, 1e-5), (4, 3, 5e-5)])
 @pytest.mark.parametrize('N,M', [(128, 128), (200, 77), (513, 300), (33, 17)])
 def test_attention_i8_reduced_planes_vs_oracle(dev, N, M, slices, p_slices, tol):
     """The reduced digit-plane settings of the tcgen05 attention (5 / 4 = the sweep default): error scales with
@@ -461,6 +463,42 @@ def test_reference_eval_loop_plumbing(dev):
     pred = {k: torch.from_numpy(v).cuda() for k, v in golden_inputs(rec).items()}
     data = net(pred)
     assert not np.array_equal(data['matching_scores0'].cpu().numpy(), rec['matching_scores0'])
+
+
+# ----------------------------------------------------------------------------- pins: kernels against reference outputs
+
+def test_knn_kernel_vs_reference_outputs(dev):
+    """mdgat_knn / get_graph_feature against outputs of the UNMODIFIED models/mdgat.py:8-32 (oracle/gen_pins.py)."""
+    from mdgat_matcher_b200 import ops
+    z = np.load(os.path.join(GOLDEN, 'pins_knn_registration.npz'))
+    for i in range(4):
+        x, src, k = z['knn%d_x' % i], z['knn%d_src' % i], int(z['knn%d_k' % i])
+        assert np.array_equal(ops.knn(_t(x, dev), _t(src, dev), k).cpu().numpy(), z['knn%d_idx' % i]), i
+        assert np.array_equal(ops.get_graph_feature(_t(x, dev), _t(src, dev), k).cpu().numpy(), z['knn%d_adj' % i].astype(np.int64)), i
+
+
+def test_register_pairs_kernel_vs_reference_outputs(dev):
+    """mdgat_register_pairs against outputs of the UNMODIFIED utils_test.calculate_error2 / solve_icp: the matched sets
+    of the fixture are embedded in keypoint arrays through a matches0 vector."""
+    from mdgat_matcher_b200 import ops
+    z = np.load(os.path.join(GOLDEN, 'pins_knn_registration.npz'))
+    rng = np.random.default_rng(3)
+    for i in range(5):
+        mk0, mk1, T_gt = z['reg%d_mkpts0' % i], z['reg%d_mkpts1' % i], z['reg%d_T_gt' % i]
+        n = len(mk0)
+        N, M = n + 9, n + 5
+        kp0, kp1 = rng.normal(size=(N, 3)) * 10, rng.normal(size=(M, 3)) * 10
+        rows = np.sort(rng.permutation(N)[:n])                   # matched rows of set 0, in order (as kpts0[valid] selects them)
+        cols = rng.permutation(M)[:n]
+        kp0[rows], kp1[cols] = mk0, mk1
+        m0 = np.full(N, -1, dtype=np.int64)
+        m0[rows] = cols
+        T, st = ops.register_pairs(_t(kp0[None], dev), _t(kp1[None], dev), torch.from_numpy(m0[None]).to(dev),
+                                   T_gt=_t(T_gt[None], dev))
+        assert np.abs(T[0].cpu().numpy() - z['reg%d_T' % i]).max() < 1e-9, i
+        assert abs(float(st['rte'][0]) - float(z['reg%d_rte' % i])) < 1e-9
+        assert abs(float(st['rre'][0]) - float(z['reg%d_rre' % i])) < 1e-6
+        assert int(st['n_valid'][0]) == n
 
 
 # ----------------------------------------------------------------------------- output side (f-4)

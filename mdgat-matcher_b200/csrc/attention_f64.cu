@@ -442,6 +442,119 @@ topk_softmax_pv_kernel(const double* __restrict__ S, const double* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Exact top-k THRESHOLD of every logits row, for the tcgen05 top-k attention (attention_i8.cu, TOPK mode): the masked
+// softmax . V of dynamic_attention() (mdgat.py:196-210) then runs on the tensor cores as a full attention whose
+// probabilities outside the kept set are zero. One warp per (b, h, query) row, two rows per warp in flight.
+// Per row: thr and jlast such that the kept set is { j : z_j > thr  or  (z_j == thr and j <= jlast) } -- exactly k
+// entries, ties at the k-th value resolved towards the lowest index (torch.topk keeps exactly k; which of several equal
+// logits it keeps is unspecified, duplicated keypoints give identical value rows so the message does not depend on it)
+// -- and the exact row maximum (the softmax shift: the kept set always contains it).
+// The comparison is on the float64 logits bit for bit as the LOGITS mode of attn_i8_kernel stored them; the TOPK mode
+// recomputes them with the same instruction sequence, so the two kernels agree on every entry.
+// ------------------------------------------------------------------------------------------
+template <int VPT>
+__global__ void __launch_bounds__(32 * TK_WARPS)
+topk_threshold_kernel(const double* __restrict__ S, double* __restrict__ thr_out, int* __restrict__ jlast_out,
+                      double* __restrict__ max_out, int M, int topk, long long total_rows) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row = (long long)blockIdx.x * TK_WARPS + warp;
+    if (row >= total_rows) return;
+    const double* srow = S + row * (long long)M;
+    double s[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+        const int j = lane + 32 * v;
+        s[v] = j < M ? srow[j] : -INFINITY;                 // padding never passes a ">= finite" test
+    }
+    double mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+        if (lane + 32 * v < M) { mx = fmax(mx, s[v]); mn = fmin(mn, s[v]); }
+    }
+    mx = warp_max_d(mx);
+    mn = -warp_max_d(-mn);
+    double thr = mn;
+    int jlast = 0x7fffffff;
+    bool exact = topk >= M;
+    if (!exact) {
+        // bracket [lo, hi] with count(>= lo) = clo > k > chi = count(>= hi); even steps place the probe by linear
+        // interpolation of the counts, odd steps bisect (see topk_softmax_pv_kernel)
+        double lo = mn, hi = mx;
+        int clo = M, chi = 1;
+        for (int step = 0; step < 96; ++step) {
+            double mid = lo + 0.5 * (hi - lo);
+            if (!(mid > lo && mid < hi)) break;             // interval collapsed: ties or adjacent doubles
+            if ((step & 1) == 0) {
+                const double guess = lo + (hi - lo) * ((double)(clo - topk) / (double)(clo - chi));
+                if (guess > lo && guess < hi) mid = guess;
+            }
+            int c = 0;
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) c += (s[v] >= mid) ? 1 : 0;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c == topk) { thr = mid; exact = true; break; }
+            if (c > topk) { lo = mid; clo = c; } else { hi = mid; chi = c; }
+        }
+    }
+    if (!exact) {
+        // ties at the k-th value (or adjacent doubles): most-significant-bit-first search on the order-preserving
+        // integer image, then the index of the last tied entry to keep
+        auto keyof = [&](int v) -> unsigned long long { return (lane + 32 * v) < M ? order_key(s[v]) : 0ull; };
+        const unsigned long long kmax = order_key(mx), kmin = order_key(mn);
+        const unsigned long long diff = kmax ^ kmin;
+        unsigned long long prefix = kmax;
+        bool found = false;
+        if (diff != 0ull) {
+            const int top = 63 - __clzll((long long)diff);
+            prefix = (top == 63) ? 0ull : (kmax >> (top + 1)) << (top + 1);
+            for (int bit = top; bit >= 0; --bit) {
+                const unsigned long long cand = prefix | (1ull << bit);
+                int c = 0;
+#pragma unroll
+                for (int v = 0; v < VPT; ++v) c += (keyof(v) >= cand) ? 1 : 0;
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (c >= topk) {
+                    prefix = cand;
+                    if (c == topk) { found = true; break; }
+                }
+            }
+        }
+        // the double whose key is `prefix`: z >= thr  <=>  key(z) >= prefix
+        thr = __longlong_as_double((long long)((prefix >> 63) ? (prefix ^ 0x8000000000000000ull) : ~prefix));
+        if (!found) {
+            int gt = 0;
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) gt += (keyof(v) > prefix) ? 1 : 0;
+            gt = __reduce_add_sync(0xffffffffu, gt);
+            const int need = topk - gt;                     // tied entries to keep, lowest index first
+            int seen = 0, jl = -1;
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) {
+                const bool eq = keyof(v) == prefix;
+                const unsigned em = __ballot_sync(0xffffffffu, eq);
+                if (eq && seen + __popc(em & ((1u << lane) - 1u)) == need - 1) jl = lane + 32 * v;
+                seen += __popc(em);
+            }
+            jlast = __reduce_max_sync(0xffffffffu, jl);
+        }
+    }
+    if (lane == 0) { thr_out[row] = thr; jlast_out[row] = jlast; max_out[row] = mx; }
+}
+
+cudaError_t launch_topk_threshold(const double* S, double* thr, int* jlast, double* rmax, int B, int N, int M, int topk,
+                                  cudaStream_t st) {
+    if (B <= 0 || N <= 0) return cudaSuccess;
+    const long long rows = (long long)B * HEADS * N;
+    const unsigned grid = (unsigned)((rows + TK_WARPS - 1) / TK_WARPS);
+    if (M <= 512) topk_threshold_kernel<16><<<grid, 32 * TK_WARPS, 0, st>>>(S, thr, jlast, rmax, M, topk, rows);
+    else if (M <= 1024) topk_threshold_kernel<32><<<grid, 32 * TK_WARPS, 0, st>>>(S, thr, jlast, rmax, M, topk, rows);
+    else if (M <= 2048) topk_threshold_kernel<64><<<grid, 32 * TK_WARPS, 0, st>>>(S, thr, jlast, rmax, M, topk, rows);
+    else return cudaErrorInvalidValue;
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <int VPT>
 static cudaError_t launch_topk_t(const double* S, const double* V, double* Out, int ldo, int N, int M, int topk,
                                  long long rows, cudaStream_t st) {

@@ -39,7 +39,7 @@ constexpr int AI_BN = 32;                  // source keypoints per tile
 constexpr int AI_QPLANE = AI_BM * 32;      // bytes of one Q digit plane of a query tile
 constexpr int AI_KPLANE = AI_BN * 32;      // bytes of one K (or V^T) digit plane of a source tile
 constexpr int AI_PPLANE = AI_BM * AI_BN;   // bytes of one P digit plane
-constexpr int AI_STAGES = 3;               // K/V tile ring
+constexpr int AI_STAGES = 4;               // K/V tile ring (the logits run two tiles ahead of P V)
 // epilogue organisation: CW = columns of a 32-column tile per warp (16: 8 epilogue warps, 8: 16 epilogue warps = 4 per SM
 // sub-partition); the MMA and loader warps follow the epilogue warps
 constexpr int ai_epi_threads(int cw) { return 128 * (32 / cw); }
@@ -346,6 +346,7 @@ struct AttnI8Params {
     AttnI8Side q[2];             // digit planes of the QUERY side of grid side s
     AttnI8Side kv[2];            // digit planes of its SOURCE side
     double* Out[2];              // messages (rows x ldo) or, LOGITS, dense (B,4,N,M) logits
+    AttnI8TopK tk;               // TOPK: per-row threshold / last tied column / maximum (launch_topk_threshold)
     int B, ldo;
 };
 
@@ -355,8 +356,12 @@ struct AttnI8Params {
 //   the others              epilogue: thread = query row (TMEM lane = 32 * (warp % 4) + lane); the 32 / CW warps that share
 //                           a lane quarter split the 32 columns of a tile (CW = 8: 16 epilogue warps, CW = 16: 8)
 // S digit planes of q, k, v; SP byte planes of P. NSBUF accumulator sets for Q K^T (2 when TMEM has room: S <= 5).
-template <int S, int SP, bool LOGITS, int CW, int CVT>
+// MODE: AI_MODE_FULL (pass 1 + pass 2), AI_MODE_LOGITS (the scaled logits are stored, nothing else), AI_MODE_TOPK (no pass 1:
+// the exact row maximum and the top-k threshold come from topk_threshold_kernel; probabilities outside the kept set are 0,
+// which turns dynamic_attention() of mdgat.py:196-210 into the same tensor-core P V as the full layers).
+template <int S, int SP, int MODE, int CW, int CVT>
 __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid_constant__ AttnI8Params p) {
+    constexpr bool LOGITS = MODE == AI_MODE_LOGITS, TOPK = MODE == AI_MODE_TOPK, PASS1 = MODE == AI_MODE_FULL;
     constexpr int AI_EPI_THREADS = ai_epi_threads(CW), EPI_WARPS = AI_EPI_THREADS / 32, NCG = 32 / CW;
     constexpr int NSBUF = (3 * S * AI_BN <= 512) ? 2 : 1;
     constexpr int TM_S = 0;                               // TMEM columns: NSBUF sets of S logits diagonals
@@ -365,6 +370,7 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
     // (the first Q K^T product into that set waits for the end of pass 1)
     constexpr int TM_P1_LO = TM_O, TM_P1_HI = TM_S + (NSBUF - 1) * S * AI_BN;
     constexpr int STAGE_BYTES = 2 * S * AI_KPLANE;
+    constexpr int P1G = STAGE_BYTES / (2 * AI_KPLANE);    // pass-1 tiles per ring stage (S: their two leading K planes fill a stage)
     static_assert(SP <= S && SP >= 3 && SP <= 6 && S * AI_BN >= 128 && TM_O + S * AI_BN <= 512, "plane counts");
     extern __shared__ __align__(128) unsigned char ai_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -435,13 +441,17 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
             bulk_g2s(s_ksd, Kd.kscale + (size_t)bh * Mpad, Mpad * 8, &q_full);
             bulk_g2s(s_ksf, Kd.kscale_f + (size_t)bh * Mpad, Mpad * 4, &q_full);
             bulk_g2s(s_ktm, Kd.ktilemax + (size_t)bh * ((T + 3) & ~3), ((T + 3) & ~3) * 4, &q_full);
+            // Ring units: in pass 1 a unit is a GROUP of up to P1G tiles (only the two leading K planes of each, 2 KB per
+            // tile: one barrier round trip per tile would leave the ring, not the epilogue, as the bound of pass 1);
+            // in pass 2 a unit is one tile (its S planes of K and of V^T).
             int u = 0;
-            if (!LOGITS) {
-                for (int jt = 0; jt < T; ++jt, ++u) {               // pass 1: the two leading K planes
-                    const int stage = u % AI_STAGES;
+            if (PASS1) {
+                for (int g0 = 0; g0 < T; g0 += P1G, ++u) {
+                    const int stage = u % AI_STAGES, nt = min(P1G, T - g0);
                     if (u >= AI_STAGES) mbar_wait(&kv_empty[stage], (unsigned)((u / AI_STAGES - 1) & 1));
-                    mbar_expect_tx(&kv_full[stage], 2 * AI_KPLANE);
-                    bulk_g2s(sKV + stage * STAGE_BYTES, gK + (size_t)jt * (S * AI_KPLANE), 2 * AI_KPLANE, &kv_full[stage]);
+                    mbar_expect_tx(&kv_full[stage], nt * 2 * AI_KPLANE);
+                    for (int i = 0; i < nt; ++i)
+                        bulk_g2s(sKV + stage * STAGE_BYTES + i * 2 * AI_KPLANE, gK + (size_t)(g0 + i) * (S * AI_KPLANE), 2 * AI_KPLANE, &kv_full[stage]);
                 }
             }
             for (int jt = 0; jt < T; ++jt, ++u) {
@@ -459,26 +469,32 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
             const uint64_t qd0 = ai_desc(sQ), kd0 = ai_desc(sKV), pd0 = ai_desc(sP);
             mbar_wait(&q_full, 0);
             int u = 0;
-            if (!LOGITS) {
-                for (int jt = 0; jt < T; ++jt, ++u) {
-                    const int stage = u % AI_STAGES, buf = jt & 3;
+            if (PASS1) {
+                for (int g0 = 0; g0 < T; g0 += P1G, ++u) {
+                    const int stage = u % AI_STAGES, nt = min(P1G, T - g0);
                     mbar_wait(&kv_full[stage], (unsigned)((u / AI_STAGES) & 1));
-                    if (jt >= 4) mbar_wait(&s1_empty[buf], (unsigned)(((jt >> 2) - 1) & 1));
-                    ai_fence_after();
-                    const uint64_t kd = kd0 + (uint64_t)((stage * STAGE_BYTES) >> 4);
-                    const uint32_t d = tmem + (buf < 2 ? TM_P1_LO + buf * 64 : TM_P1_HI + (buf - 2) * 64);
-                    // diagonal 0 = D0 G0, diagonal 1 = D0 G1 + D1 G0
-                    ai_mma(d, qd0, kd, ai_idesc(64, true), false);
-                    ai_mma(d + 32, qd0 + (uint64_t)(AI_QPLANE >> 4), kd, ai_idesc(32, true), true);
-                    ai_commit(&s1_full[buf]);
+                    for (int i = 0; i < nt; ++i) {
+                        const int jt = g0 + i, buf = jt & 3;
+                        if (jt >= 4) mbar_wait(&s1_empty[buf], (unsigned)(((jt >> 2) - 1) & 1));
+                        ai_fence_after();
+                        const uint64_t kd = kd0 + (uint64_t)((stage * STAGE_BYTES + i * 2 * AI_KPLANE) >> 4);
+                        const uint32_t d = tmem + (buf < 2 ? TM_P1_LO + buf * 64 : TM_P1_HI + (buf - 2) * 64);
+                        // diagonal 0 = D0 G0, diagonal 1 = D0 G1 + D1 G0
+                        ai_mma(d, qd0, kd, ai_idesc(64, true), false);
+                        ai_mma(d + 32, qd0 + (uint64_t)(AI_QPLANE >> 4), kd, ai_idesc(32, true), true);
+                        ai_commit(&s1_full[buf]);
+                    }
                     ai_commit(&kv_empty[stage]);
                 }
             }
+            const int u0 = u;                                        // ring unit of pass-2 tile 0
             // Q K^T of tile jt into accumulator set jt % NSBUF (its (jt / NSBUF)-th use)
-            auto qk_tile = [&](int jt, int stage) {
+            auto qk_tile = [&](int jt) {
+                const int uu = u0 + jt, stage = uu % AI_STAGES;
+                mbar_wait(&kv_full[stage], (unsigned)((uu / AI_STAGES) & 1));
                 const int sb = jt % NSBUF, use = jt / NSBUF;
                 if (use >= 1) mbar_wait(&s_empty[sb], (unsigned)((use - 1) & 1));      // the epilogue has read the previous tile of this set
-                else if (!LOGITS && sb == NSBUF - 1) mbar_wait(&p1_done, 0);          // pass 1 borrowed the start of this set
+                else if (PASS1 && sb == NSBUF - 1) mbar_wait(&p1_done, 0);          // pass 1 borrowed the start of this set
                 ai_fence_after();
                 const uint64_t kd = kd0 + (uint64_t)((stage * STAGE_BYTES) >> 4);
 #pragma unroll
@@ -486,15 +502,12 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
                     ai_mma(tmem + TM_S + sb * (S * AI_BN) + s * AI_BN, qd0 + (uint64_t)((s * AI_QPLANE) >> 4), kd, ai_idesc((S - s) * AI_BN, true), s > 0);
                 ai_commit(&s_full[sb]);
             };
-            mbar_wait(&kv_full[u % AI_STAGES], (unsigned)((u / AI_STAGES) & 1));
-            qk_tile(0, u % AI_STAGES);
-            for (int jt = 0; jt < T; ++jt, ++u) {
-                const int stage = u % AI_STAGES;
-                if (jt + 1 < T) {
-                    const int nst = (u + 1) % AI_STAGES;
-                    mbar_wait(&kv_full[nst], (unsigned)(((u + 1) / AI_STAGES) & 1));
-                    qk_tile(jt + 1, nst);
-                }
+            // The logits run NSBUF tiles ahead of P V: the epilogue asks for the accumulators of tile jt + 1 before it starts
+            // the exponentials of tile jt, and P V of tile jt can only be issued once those exponentials are done.
+            for (int t = 0; t < NSBUF && t < T; ++t) qk_tile(t);
+            for (int jt = 0; jt < T; ++jt) {
+                const int stage = (u0 + jt) % AI_STAGES;
+                if (jt + NSBUF < T) qk_tile(jt + NSBUF);
                 if (!LOGITS) {
                     const int buf = jt & 1;
                     mbar_wait(&p_full[buf], (unsigned)((jt >> 1) & 1));
@@ -520,8 +533,15 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
         mbar_wait(&q_full, 0);                                     // key scales are in shared memory
         const double r_i = Qd.qscale[(size_t)bh * Npad + row];     // 2^(e_i - 12) / sqrt(32); 0 for padded rows
         const double r_z = (S & 1) ? r_i : r_i * 0.00390625;       // even S: ai_recombine() returns 256 x the sum
-        double c_i = 0.0;
-        if (!LOGITS) {
+        double c_i = 0.0, t_i = 0.0;
+        int jl_i = 0;
+        if (TOPK) {
+            const long long grow = (long long)bh * N + row;
+            c_i = row_ok ? p.tk.rmax[side][grow] : 0.0;                         // exact row maximum: p <= 1 with no slack
+            t_i = row_ok ? p.tk.thr[side][grow] : INFINITY;                     // padded rows keep nothing
+            jl_i = row_ok ? p.tk.jlast[side][grow] : -1;
+        }
+        if (PASS1) {
             // ---- pass 1: c_i >= max_j z_ij from the two leading diagonals
             float amax = -INFINITY, kmax = 0.f;
             // two tiles per trip: the TMEM loads of the second are in flight while the first is reduced (registers of an
@@ -603,10 +623,10 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
                     double* dst = p.Out[side] + ((long long)bh * N + row) * (long long)M + jbase;
                     if (jbase + CW <= M && (M & 1) == 0) {
 #pragma unroll
-                        for (int j = 0; j < CW; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(z[j] * r_z, z[j + 1] * r_z);
+                        for (int j = 0; j < CW; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(__dmul_rn(z[j], r_z), __dmul_rn(z[j + 1], r_z));
                     } else {
 #pragma unroll
-                        for (int j = 0; j < CW; ++j) if (jbase + j < M) dst[j] = z[j] * r_z;
+                        for (int j = 0; j < CW; ++j) if (jbase + j < M) dst[j] = __dmul_rn(z[j], r_z);
                     }
                 }
                 if (jt + 1 < T) { s_load(jt + 1); s_collect(jt + 1); }
@@ -617,7 +637,16 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
                 uint32_t h32;
-                ai_exp_fixed<SP>(fma(z[j], r_z, -c_i), etab_s32, lo[j], h32);        // p^ = rint(exp(z - c_i) 2^(8 SP - 1)), p <= 1
+                if (TOPK) {
+                    // the scaled logit exactly as LOGITS mode stored it (one rounded product), compared with the row's
+                    // threshold; ties at the threshold are kept up to column jl_i
+                    const double zz = __dmul_rn(z[j], r_z);
+                    const bool keep = zz > t_i || (zz == t_i && jbase + j <= jl_i);
+                    ai_exp_fixed<SP>(zz - c_i, etab_s32, lo[j], h32);
+                    if (!keep) { lo[j] = 0u; h32 = 0u; }
+                } else {
+                    ai_exp_fixed<SP>(fma(z[j], r_z, -c_i), etab_s32, lo[j], h32);    // p^ = rint(exp(z - c_i) 2^(8 SP - 1)), p <= 1
+                }
                 if (SP > 4) hi[j] = h32;
             }
             if (jbase + CW > M) {
@@ -762,22 +791,30 @@ cudaError_t launch_attn_i8_slice_sides(const double* const* Qh, const double* co
 }
 
 template <int S, int SP, int CVT>
-static cudaError_t attn_i8_go(const AttnI8Params& p, dim3 grid, size_t smem, bool logits_only, int cw, cudaStream_t st) {
+static cudaError_t attn_i8_go(const AttnI8Params& p, dim3 grid, size_t smem, int mode, int cw, cudaStream_t st) {
     auto go = [&](auto kern, int threads) -> cudaError_t {
         cudaError_t r = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (r != cudaSuccess) return r;
         kern<<<grid, threads, smem, st>>>(p);
         return cudaSuccess;
     };
-    if (logits_only) return cw == 16 ? go(attn_i8_kernel<S, SP, true, 16, CVT>, ai_threads(16)) : go(attn_i8_kernel<S, SP, true, 8, CVT>, ai_threads(8));
-    return cw == 16 ? go(attn_i8_kernel<S, SP, false, 16, CVT>, ai_threads(16)) : go(attn_i8_kernel<S, SP, false, 8, CVT>, ai_threads(8));
+    if (mode == AI_MODE_LOGITS) return cw == 16 ? go(attn_i8_kernel<S, SP, AI_MODE_LOGITS, 16, CVT>, ai_threads(16)) : go(attn_i8_kernel<S, SP, AI_MODE_LOGITS, 8, CVT>, ai_threads(8));
+    if (mode == AI_MODE_TOPK) return cw == 16 ? go(attn_i8_kernel<S, SP, AI_MODE_TOPK, 16, CVT>, ai_threads(16)) : go(attn_i8_kernel<S, SP, AI_MODE_TOPK, 8, CVT>, ai_threads(8));
+    return cw == 16 ? go(attn_i8_kernel<S, SP, AI_MODE_FULL, 16, CVT>, ai_threads(16)) : go(attn_i8_kernel<S, SP, AI_MODE_FULL, 8, CVT>, ai_threads(8));
 }
 
 // q[s] / kv[s]: digit planes of the query side and of the source side of grid side s; Out[s]: messages (rows x ldo),
-// or with logits_only the dense scaled logits (B,4,N,M) of that side. SP: byte planes of P (S = 4: 3 or 4, 5: 4, 6: 5, 7: 6).
+// or in AI_MODE_LOGITS the dense scaled logits (B,4,N,M) of that side. SP: byte planes of P (S = 4: 3 or 4, 5: 4, 6: 5, 7: 6).
 cudaError_t launch_attn_i8(const AttnI8Side* q, const AttnI8Side* kv, double* const* Out, int B, int nsides, int ldo,
-                           bool logits_only, int SP, cudaStream_t st) {
+                           int mode, const AttnI8TopK* tk, int SP, cudaStream_t st) {
     AttnI8Params p;
+    if (mode == AI_MODE_TOPK) {
+        if (tk == nullptr) return cudaErrorInvalidValue;
+        p.tk = *tk;
+        if (nsides < 2) { p.tk.thr[1] = tk->thr[0]; p.tk.jlast[1] = tk->jlast[0]; p.tk.rmax[1] = tk->rmax[0]; }
+    } else {
+        p.tk = AttnI8TopK{{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    }
     int nmax = 0, mmax = 0;
     const int S = q[0].S;
     for (int s = 0; s < 2; ++s) {
@@ -798,14 +835,14 @@ cudaError_t launch_attn_i8(const AttnI8Side* q, const AttnI8Side* kv, double* co
     static const int cvt = [] { const char* v = getenv("MDGAT_ATTN_CVT"); return v && v[0] >= '0' && v[0] <= '3' ? v[0] - '0' : AI_CVT_DEFAULT; }();
     cudaError_t e;
     switch (S * 10 + SP) {
-        case 43: e = attn_i8_go<4, 3, AI_CVT_DEFAULT>(p, grid, smem, logits_only, cw, st); break;
-        case 44: e = attn_i8_go<4, 4, AI_CVT_DEFAULT>(p, grid, smem, logits_only, cw, st); break;
-        case 54: e = cvt == 0 ? attn_i8_go<5, 4, 0>(p, grid, smem, logits_only, cw, st)
-                   : cvt == 1 ? attn_i8_go<5, 4, 1>(p, grid, smem, logits_only, cw, st)
-                   : cvt == 2 ? attn_i8_go<5, 4, 2>(p, grid, smem, logits_only, cw, st)
-                              : attn_i8_go<5, 4, 3>(p, grid, smem, logits_only, cw, st); break;
-        case 65: e = attn_i8_go<6, 5, AI_CVT_DEFAULT>(p, grid, smem, logits_only, cw, st); break;
-        case 76: e = attn_i8_go<7, 6, AI_CVT_DEFAULT>(p, grid, smem, logits_only, cw, st); break;
+        case 43: e = attn_i8_go<4, 3, AI_CVT_DEFAULT>(p, grid, smem, mode, cw, st); break;
+        case 44: e = attn_i8_go<4, 4, AI_CVT_DEFAULT>(p, grid, smem, mode, cw, st); break;
+        case 54: e = cvt == 0 ? attn_i8_go<5, 4, 0>(p, grid, smem, mode, cw, st)
+                   : cvt == 1 ? attn_i8_go<5, 4, 1>(p, grid, smem, mode, cw, st)
+                   : cvt == 2 ? attn_i8_go<5, 4, 2>(p, grid, smem, mode, cw, st)
+                              : attn_i8_go<5, 4, 3>(p, grid, smem, mode, cw, st); break;
+        case 65: e = attn_i8_go<6, 5, AI_CVT_DEFAULT>(p, grid, smem, mode, cw, st); break;
+        case 76: e = attn_i8_go<7, 6, AI_CVT_DEFAULT>(p, grid, smem, mode, cw, st); break;
         default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;

@@ -97,6 +97,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Workspace {
     double *X, *Xk, *Xd, *Qh, *Kh, *Vh, *Msg, *Mg, *Hd, *MD, *S, *C, *u, *v, *mscratch, *skscratch;
+    double *tkthr, *tkmax; int* tkjl;                   // tcgen05 top-k layers: per (b, h, row) threshold, maximum, last tied column
     double *rsX, *rsM, *rsH; int8_t *xsX, *xsM, *xsH;   // tcgen05 path: int8 slice planes + row scales of X, Msg, Hd (2 chunks)
     AttnI8Side ai[2];                                   // tcgen05 attention: digit planes of q/k/v of side 0 / side 1
     size_t bytes;
@@ -129,6 +130,9 @@ Workspace carve(char* base, int B, int N, int M, bool need_logits, int i8_slices
     w.v = take((size_t)B * (M + 1));
     w.mscratch = take(4 * R + 8);
     w.skscratch = take(sinkhorn_scratch_doubles(B, N, M));
+    w.tkthr = take(need_logits && attn_i8 ? R * HEADS : 0);
+    w.tkmax = take(need_logits && attn_i8 ? R * HEADS : 0);
+    w.tkjl = reinterpret_cast<int*>(take(need_logits && attn_i8 ? (R * HEADS + 1) / 2 : 0));
     const size_t Rpad = (R + 127) / 128 * 128;
     w.rsX = take(i8_slices ? Rpad : 0);
     w.rsM = take(i8_slices ? Rpad : 0);
@@ -171,19 +175,36 @@ cudaError_t gemm_nt(const double* X, int ldx, long long sX, const double* W, int
 
 // Messages of one GNN layer. nsides = 2: side 0 and side 1 in the same launches.
 // qd / kvd != nullptr: tcgen05 engine; the digit planes of the query / source side of each grid side are already cut.
+// tk: scratch of the tcgen05 top-k path (threshold / maximum / last tied column per (b, h, row) of every side)
+struct TopKScratch { double* thr; double* rmax; int* jlast; };
 cudaError_t attention_layer(const AttnSides& ps, int B, int nsides, int ldo, int topk, double* S, cudaStream_t st,
-                            const AttnI8Side* qd = nullptr, const AttnI8Side* kvd = nullptr, int SP = 0) {
+                            const AttnI8Side* qd = nullptr, const AttnI8Side* kvd = nullptr, int SP = 0,
+                            const TopKScratch* tks = nullptr) {
     if (qd) {
-        if (topk <= 0) return launch_attn_i8(qd, kvd, ps.Out, B, nsides, ldo, false, SP, st);
+        if (topk <= 0) return launch_attn_i8(qd, kvd, ps.Out, B, nsides, ldo, AI_MODE_FULL, nullptr, SP, st);
+        // dynamic_attention() (mdgat.py:196-210) on the tensor cores: dense logits (digit-plane Q K^T, stored), the exact
+        // top-k threshold of every row, then the same kernel again as a masked softmax . V that recomputes the logits bit
+        // for bit and zeroes the probabilities outside the kept set
         double* lg[2]; double* sp = S;
         for (int s = 0; s < nsides; ++s) { lg[s] = sp; sp += (size_t)B * HEADS * ps.N[s] * ps.M[s]; }
-        cudaError_t e = launch_attn_i8(qd, kvd, lg, B, nsides, 0, true, SP, st);
+        cudaError_t e = launch_attn_i8(qd, kvd, lg, B, nsides, 0, AI_MODE_LOGITS, nullptr, SP, st);
         if (e != cudaSuccess) return e;
-        for (int s = 0; s < nsides; ++s) {
-            e = launch_topk_softmax_pv(lg[s], ps.V[s], ps.Out[s], ldo, B, ps.N[s], ps.M[s], topk, st);
-            if (e != cudaSuccess) return e;
+        if (tks == nullptr) {
+            for (int s = 0; s < nsides; ++s) {
+                e = launch_topk_softmax_pv(lg[s], ps.V[s], ps.Out[s], ldo, B, ps.N[s], ps.M[s], topk, st);
+                if (e != cudaSuccess) return e;
+            }
+            return cudaSuccess;
         }
-        return cudaSuccess;
+        AttnI8TopK tk;
+        size_t off = 0;
+        for (int s = 0; s < nsides; ++s) {
+            tk.thr[s] = tks->thr + off; tk.rmax[s] = tks->rmax + off; tk.jlast[s] = tks->jlast + off;
+            e = launch_topk_threshold(lg[s], tks->thr + off, tks->jlast + off, tks->rmax + off, B, ps.N[s], ps.M[s], topk, st);
+            if (e != cudaSuccess) return e;
+            off += (size_t)B * HEADS * ps.N[s];
+        }
+        return launch_attn_i8(qd, kvd, ps.Out, B, nsides, ldo, AI_MODE_TOPK, &tk, SP, st);
     }
     if (topk <= 0) return launch_attention_full(ps, B, nsides, ldo, st);
     // dense logits q.k / sqrt(32) for every (b, h) (mdgat.py:201), then exact-k selection per row
@@ -333,7 +354,8 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
             prof_mark(k > 0 ? ST_ATTN_TOPK : ST_ATTN_FULL, st);
             const AttnI8Side qd[2] = {w.ai[0], w.ai[1]};
             const AttnI8Side kvd[2] = {cross ? w.ai[1] : w.ai[0], cross ? w.ai[0] : w.ai[1]};
-            MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st, qd, kvd, ASP));
+            const TopKScratch tks = {w.tkthr, w.tkmax, w.tkjl};
+            MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st, qd, kvd, ASP, &tks));
         } else {
             MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st));
         }
@@ -455,7 +477,10 @@ int mdgat_attention_f64(const double* d_Q, const double* d_K, const double* d_V,
     return MDGAT_OK;
 }
 
-size_t mdgat_attention_i8_scratch_bytes(int B, int N, int M) { return attn_i8_side_bytes(B, N, 7) + attn_i8_side_bytes(B, M, 7); }
+size_t mdgat_attention_i8_scratch_bytes(int B, int N, int M) {
+    // digit planes of both sets (sized for 7 planes) + the top-k scratch: threshold, maximum (doubles), last tied column (int) per (b, h, row)
+    return attn_i8_side_bytes(B, N, 7) + attn_i8_side_bytes(B, M, 7) + (size_t)B * HEADS * N * 20 + 256;
+}
 
 int mdgat_attention_i8(const double* d_Q, const double* d_K, const double* d_V, double* d_Out, int ldo,
                        int B, int N, int M, int topk, double* d_logits, void* d_scratch, int slices, int p_slices,
@@ -475,7 +500,10 @@ int mdgat_attention_i8(const double* d_Q, const double* d_K, const double* d_V, 
     AttnSides ps;
     memset(&ps, 0, sizeof(ps));
     ps.Q[0] = d_Q; ps.K[0] = d_K; ps.V[0] = d_V; ps.Out[0] = d_Out; ps.N[0] = N; ps.M[0] = M;
-    MDGAT_CUDA_OK(attention_layer(ps, B, 1, ldo, topk, d_logits, st, &qs, &ks, ASP));
+    char* tkb = reinterpret_cast<char*>(d_scratch) + attn_i8_side_bytes(B, N, 7) + attn_i8_side_bytes(B, M, 7);
+    const size_t rows = (size_t)B * HEADS * N;
+    const TopKScratch tks = {reinterpret_cast<double*>(tkb), reinterpret_cast<double*>(tkb) + rows, reinterpret_cast<int*>(tkb + rows * 16)};
+    MDGAT_CUDA_OK(attention_layer(ps, B, 1, ldo, topk, d_logits, st, &qs, &ks, ASP, &tks));
     return MDGAT_OK;
 }
 

@@ -45,6 +45,10 @@ cudaError_t launch_attention_logits(const AttnSides& ps, int B, int nsides, cuda
 cudaError_t launch_topk_softmax_pv(const double* S, const double* V, double* Out, int ldo,
                                    int B, int N, int M, int topk, cudaStream_t st);
 
+// Exact top-k threshold per logits row (B,4,N,M): kept set = { z > thr or (z == thr and column <= jlast) }, plus the row maximum
+cudaError_t launch_topk_threshold(const double* S, double* thr, int* jlast, double* rmax, int B, int N, int M, int topk,
+                                  cudaStream_t st);
+
 // Encoder input staging: Xk (R x 4) = [x,y,z,score], Xd (R x 36) = [33 desc | 0 0 0]
 cudaError_t launch_pack_inputs(const void* kpts0, const void* kpts1, const void* desc0, const void* desc1,
                                const void* sc0, const void* sc1, int in_dtype, int score_dtype,
@@ -107,8 +111,12 @@ cudaError_t launch_attn_i8_slice(const double* Qh, const double* Kh, const doubl
 cudaError_t launch_attn_i8_slice_sides(const double* const* Qh, const double* const* Kh, const double* const* Vh, const AttnI8Side* o,
                                        int B, cudaStream_t st);
 // SP: byte planes of the probabilities; supported (S, SP): (4,3) (4,4) (5,4) (6,5) (7,6)
+// mode: AI_MODE_FULL softmax over all sources; AI_MODE_LOGITS store the dense scaled logits (B,4,N,M) into Out;
+// AI_MODE_TOPK softmax over the kept set described by tk (from launch_topk_threshold on the logits of AI_MODE_LOGITS)
+enum { AI_MODE_FULL = 0, AI_MODE_LOGITS = 1, AI_MODE_TOPK = 2 };
+struct AttnI8TopK { const double* thr[2]; const int* jlast[2]; const double* rmax[2]; };   // per side, rows in (B,4,N) order
 cudaError_t launch_attn_i8(const AttnI8Side* q, const AttnI8Side* kv, double* const* Out, int B, int nsides, int ldo,
-                           bool logits_only, int SP, cudaStream_t st);
+                           int mode, const AttnI8TopK* tk, int SP, cudaStream_t st);
 
 // Batched Kabsch registration + match statistics (one CTA per pair)
 cudaError_t launch_register_pairs(const void* kpts0, const void* kpts1, int kp_dtype, const int64_t* matches0,

@@ -84,10 +84,16 @@ def read_calib(train_path, seq):
     return calib                       # the last 12-value line (Tr), as the reference's loop leaves it
 
 
-def write_synthetic_sequence(root, seq=10, frames=12, n_kpts=256, n_landmarks=3000, seed=0, step=2.0):
+def write_synthetic_sequence(root, seq=10, frames=12, n_kpts=256, n_landmarks=3000, seed=0, step=2.0, saliency_scale=1.0):
     """Creates <root>/{poses,calib,preprocess,keypoints}: a straight-ish drive past a static landmark
     field; every frame sees the n_kpts nearest landmarks in its own LiDAR frame with small noise, so
-    consecutive frames share most keypoints. Returns the directory names the scripts' flags expect."""
+    consecutive frames share most keypoints. Returns the directory names the scripts' flags expect.
+
+    Saliency is written as 32 +- 10 (times saliency_scale): the loader's optional keypoint-count fix-up keeps only
+    saliency > 10 (load_data.py:180-211). The pre-trained matcher saw saliencies around 0.32 and keypoint clouds about
+    18 m wide: with saliency_scale = 0.01, a sparse field (n_landmarks ~ 1.5 n_kpts) and
+    step <= 1 m it registers these synthetic pairs (>= 95 % of its matches correct); with the dense default field the
+    clouds are a few metres wide, far from its training distribution, and it finds no correct match."""
     rng = np.random.default_rng(seed)
     g = torch.Generator().manual_seed(seed)
     calib = np.array([[4.276802385584e-04, -9.999672484946e-01, -8.084491683471e-03, -1.198459927713e-02],
@@ -113,7 +119,7 @@ def write_synthetic_sequence(root, seq=10, frames=12, n_kpts=256, n_landmarks=30
         near = np.argsort(np.linalg.norm(local, axis=1))[:n_kpts]
         near = near[rng.permutation(len(near))]
         write_keypoint_bin(os.path.join(kp_dir, '%02d' % seq, '%06d.bin' % f),
-                           local[near] + rng.normal(0, 0.03, (len(near), 3)), score[near],
+                           local[near] + rng.normal(0, 0.03, (len(near), 3)), score[near] * saliency_scale,
                            desc[near] * (1 + 0.05 * rng.normal(size=(len(near), 33))))
     os.makedirs(os.path.join(root, 'poses'), exist_ok=True)
     with open(os.path.join(root, 'poses', '%02d.txt' % seq), 'w') as fh:

@@ -144,6 +144,8 @@ def build_reference_net(cfg, weights='checkpoint', seed=0, target='cpu'):
         net.load_state_dict(weights)
     if str(target) != 'cpu':
         net.to(torch.device(target))                      # test.py:172
+    else:
+        net.module.to('cpu')                              # DataParallel.__init__ moves the module to cuda:0 when exactly one GPU is visible
     net.double().eval()                                   # test.py:193
     zcap = {}
     orig = mod.log_optimal_transport

@@ -43,7 +43,8 @@ def test_registration_metric_script_runs_unchanged_and_agrees(tmp_path):
     if ckpt is None:
         pytest.skip('oracle/_ref/best_model_fp32.npz missing')
     frames, n = 14, 256
-    dirs = kitti_io.write_synthetic_sequence(str(tmp_path / 'KITTI'), seq=10, frames=frames, n_kpts=n, n_landmarks=3000, seed=7)
+    dirs = kitti_io.write_synthetic_sequence(str(tmp_path / 'KITTI'), seq=10, frames=frames, n_kpts=n, n_landmarks=400, seed=7,
+                                             step=1.0, saliency_scale=0.01)
 
     # ---- the unchanged script, through the launcher (one visible GPU: DataParallel then calls the module directly)
     env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES=os.environ.get('CUDA_VISIBLE_DEVICES', '0').split(',')[0])
@@ -52,14 +53,17 @@ def test_registration_metric_script_runs_unchanged_and_agrees(tmp_path):
            '--resume_model', ckpt, '--max_keypoints', str(n)]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=900)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
-    per_pair = {}
+    per_pair, failed = {}, set()
     for line in r.stdout.splitlines():
         m = re.match(r'idx(\d+), rep ([\d.]+), inlier (\d+), precision\(inlier ratio\) ([\d.]+), recall ([\d.]+), '
                      r'fp_rate ([\d.]+), tp_rate ([\d.]+), RTE ([\d.]+), RRE ([\d.]+)', line)
         if m:
             per_pair[int(m.group(1))] = [float(x) for x in m.groups()[1:]]
+        m = re.match(r'idx(\d+), rep ([\d.]+), registration fail', line)
+        if m:
+            failed.add(int(m.group(1)))
     summary = [l for l in r.stdout.splitlines() if '||' in l and not l.startswith('repeat')]
-    assert len(per_pair) == frames - 3 and len(summary) == 1, r.stdout[-3000:]
+    assert len(per_pair) + len(failed) == frames - 3 and len(summary) == 1, r.stdout[-3000:]
     s = [float(x) for x in re.findall(r'[-\d.]+(?:e-?\d+)?|nan', summary[0])]
 
     # ---- this package's own pipeline on the same pairs
@@ -81,11 +85,12 @@ def test_registration_metric_script_runs_unchanged_and_agrees(tmp_path):
             prec = g['tp'] / g['n_valid'] if g['n_valid'] > 0 else 0.0
             recall = g['tp'] / g['n_valid_gt'] if g['n_valid'] > 0 else 0.0
             fp_rate, tp_rate = g['fp'] / (g['fp'] + g['tn']), g['tp'] / (g['tp'] + g['fn'])
-            want = per_pair[pb.pairs[i][0]]
             got = [rep, g['tp'], prec, recall, fp_rate, tp_rate, g['rte'], g['rre']]
-            for a, b in zip(got, want):
-                assert abs(a - b) <= 0.00051, (i, got, want)              # the script prints three decimals
             ok = g['rte'] < 2 and g['rre'] < np.pi / 180 * 5
+            assert ok == (pb.pairs[i][0] in per_pair), (i, got)          # the script prints metrics only for registered pairs
+            if ok:
+                for a, b in zip(got, per_pair[pb.pairs[i][0]]):
+                    assert abs(a - b) <= 0.00051, (i, got, per_pair[pb.pairs[i][0]])      # three printed decimals
             acc['rr'].append(1.0 if ok else 0.0)
             for k, v in zip(('rep', 'inlier', 'prec', 'recall', 'fp', 'tp'), got[:6]):
                 acc[k].append(v)

@@ -68,7 +68,7 @@ AttnI8Side attn_i8_carve(void* base, int B, int n, int S) {
     s.Ks = reinterpret_cast<int8_t*>(p); p += attn_i8_kv_bytes(B, n, S);
     s.Vs = reinterpret_cast<int8_t*>(p); p += attn_i8_kv_bytes(B, n, S);
     s.qscale = reinterpret_cast<double*>(p); p += rq * 8;
-    s.kscale = reinterpret_cast<double*>(p); p += rk * 8;
+    s.kexp = reinterpret_cast<int*>(p); p += rk * 8;                 // rk * 4 used
     s.vscale = reinterpret_cast<double*>(p); p += (size_t)B * HEADS * 32 * 8;
     s.kscale_f = reinterpret_cast<float*>(p); p += rk * 4;
     s.ktilemax = reinterpret_cast<float*>(p);
@@ -105,7 +105,7 @@ DEVINL void digits16(const double* x, double sc, uint32_t (&w)[S][4]) {
 // Digits of the q and k rows. One thread per (b, h, padded row); blocks [0, nqb) cut Q (query tiles of 128
 // rows), the rest cut K (4 source tiles of 32 rows per block).
 // qscale = 2^(e-12) / sqrt(32)   (row factor of the logits, 1/sqrt(d) of mdgat.py:192 included)
-// kscale = 2^f (double and float copies), ktilemax = largest kscale of a 32-row tile
+// kexp = f << 20 (added to the exponent field of the row factor: 2^f), kscale_f = 2^f as float, ktilemax = largest kscale_f of a 32-row tile
 // ---------------------------------------------------------------------------------------------------
 // blk128 / t128: index of the 128-row block and the thread inside it (the stand-alone kernel maps them to blockIdx /
 // threadIdx, the fused per-layer kernel packs four of them into a 512-thread CTA)
@@ -141,7 +141,7 @@ DEVINL void slice_qk_body(const double* __restrict__ Qh, const double* __restric
         dst = o.Ks + ((size_t)bh * (npad / AI_BN) + (i >> 5)) * (S * AI_KPLANE) + canon32(i & 31, 0);
         plane = AI_KPLANE;
         const float kf = i < n ? __int_as_float((127 + e) << 23) : 0.f;
-        o.kscale[(size_t)bh * npad + i] = i < n ? pow2i(e) : 0.0;
+        o.kexp[(size_t)bh * npad + i] = i < n ? e * (1 << 20) : 0;
         o.kscale_f[(size_t)bh * npad + i] = kf;
         float tm = kf;
 #pragma unroll
@@ -300,9 +300,28 @@ DEVINL constexpr uint32_t ai_idesc(int n, bool a_signed) {
 // sum_dd acc[dd][j] 256^(-dd), times 256 when S is even (the caller folds 2^-8 into the row factor): the diagonals are
 // merged in pairs exactly in int32 (|acc_dd| <= S * 32 * 2^14 < 2^22) from the least significant end, then Horner in float64
 // CVT == 3: the least significant pair through I2F (conversion pipe), the others through the 2^52 constant (ALU + FP64 pipe)
+// CVT == 4 (S <= 6): all diagonals merged into ONE 64-bit integer (|sum| < 2^63: S = 5 needs 54 bits) by integer
+//           multiply-adds, then a single I2F.F64.S64 -- no FP64-pipe instruction at all; the result is 2^(16 (S-1)/2) times
+//           the Horner value (ai_recombine_scale), which the caller folds into the row factor
+template <int S, int CVT> constexpr double ai_recombine_scale() {
+    return (CVT == 4 && S <= 6) ? 1.0 / (double)(1ull << (16 * ((S - 1) / 2))) : 1.0;
+}
 template <int S, int CW, int CVTX>
 DEVINL double ai_recombine(const int (&acc)[S][CW], int j) {
-    constexpr int CVT = CVTX == 3 ? 0 : CVTX;
+    if constexpr (CVTX == 4 && S <= 6) {
+        long long t = (long long)(acc[S - 2][j] * 256 + acc[S - 1][j]);
+        int sh = 16;
+#pragma unroll
+        for (int d = S - 4; d >= (S & 1); d -= 2) {
+            const int g = acc[d][j] * 256 + acc[d + 1][j];
+            if (sh == 16) asm("mad.wide.s32 %0, %1, 65536, %0;" : "+l"(t) : "r"(g));
+            else t += (long long)g << sh;
+            sh += 16;
+        }
+        if (S & 1) t += (long long)acc[0][j] << sh;
+        return __ll2double_rn(t);
+    }
+    constexpr int CVT = (CVTX == 3 || CVTX == 4) ? 0 : CVTX;
     double h = pair_to_f64<CVTX == 3 ? 1 : CVT>(acc[S - 2][j], acc[S - 1][j]);
 #pragma unroll
     for (int d = S - 4; d >= (S & 1); d -= 2) h = fma(h, 1.52587890625e-05, pair_to_f64<CVT>(acc[d][j], acc[d + 1][j]));
@@ -392,8 +411,8 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
     int8_t* sQ = reinterpret_cast<int8_t*>(smem_al + 2048);                       // [S][4096]
     int8_t* sKV = sQ + S * AI_QPLANE;                                             // [stage][K S planes | V S planes]
     uint8_t* sP = reinterpret_cast<uint8_t*>(sKV + AI_STAGES * STAGE_BYTES);      // [2][SP][4096]
-    double* s_ksd = reinterpret_cast<double*>(sP + 2 * SP * AI_PPLANE);           // [Mpad]
-    float* s_ksf = reinterpret_cast<float*>(s_ksd + Mpad);                        // [Mpad]
+    int* s_kex = reinterpret_cast<int*>(sP + 2 * SP * AI_PPLANE);                 // [Mpad] key exponents << 20
+    float* s_ksf = reinterpret_cast<float*>(s_kex + Mpad);                        // [Mpad]
     float* s_ktm = s_ksf + Mpad;                                                  // [T] (padded to 4)
     double* s_xd = reinterpret_cast<double*>(s_ktm + ((T + 3) & ~3));             // [4][128] row exchange between column groups
     unsigned long long* s_xu = reinterpret_cast<unsigned long long*>(s_xd + 512); // [4][128]
@@ -434,11 +453,11 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
         // ------------------------------------------------------------------ loader
         if (elect_one()) {
             const int8_t* gQ = Qd.Qs + ((size_t)bh * (Npad / AI_BM) + qt) * (S * AI_QPLANE);
-            const unsigned sc_bytes = (unsigned)(Mpad * 8 + Mpad * 4 + ((T + 3) & ~3) * 4);
+            const unsigned sc_bytes = (unsigned)(Mpad * 4 + Mpad * 4 + ((T + 3) & ~3) * 4);
             mbar_expect_tx(&q_full, S * AI_QPLANE + sc_bytes);
 #pragma unroll
             for (int s = 0; s < S; ++s) bulk_g2s(sQ + s * AI_QPLANE, gQ + (size_t)s * AI_QPLANE, AI_QPLANE, &q_full);
-            bulk_g2s(s_ksd, Kd.kscale + (size_t)bh * Mpad, Mpad * 8, &q_full);
+            bulk_g2s(s_kex, Kd.kexp + (size_t)bh * Mpad, Mpad * 4, &q_full);
             bulk_g2s(s_ksf, Kd.kscale_f + (size_t)bh * Mpad, Mpad * 4, &q_full);
             bulk_g2s(s_ktm, Kd.ktilemax + (size_t)bh * ((T + 3) & ~3), ((T + 3) & ~3) * 4, &q_full);
             // Ring units: in pass 1 a unit is a GROUP of up to P1G tiles (only the two leading K planes of each, 2 KB per
@@ -532,7 +551,9 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
         const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
         mbar_wait(&q_full, 0);                                     // key scales are in shared memory
         const double r_i = Qd.qscale[(size_t)bh * Npad + row];     // 2^(e_i - 12) / sqrt(32); 0 for padded rows
-        const double r_z = (S & 1) ? r_i : r_i * 0.00390625;       // even S: ai_recombine() returns 256 x the sum
+        // row factor of the recombined integer: even S: ai_recombine() returns 256 x the sum; CVT 4: 2^(16 (S-1)/2) x
+        const double r_z = ((S & 1) ? r_i : r_i * 0.00390625) * ai_recombine_scale<S, CVT>();
+        const int r_zh = __double2hiint(r_z), r_zl = __double2loint(r_z);
         double c_i = 0.0, t_i = 0.0;
         int jl_i = 0;
         if (TOPK) {
@@ -610,23 +631,29 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
             ai_ld_wait();
             ai_fence_before();
             mbar_arrive(&s_empty[jt % NSBUF]);
-            const double* ks = s_ksd + jt * AI_BN + c0;
 #pragma unroll
-            for (int j = 0; j < CW; ++j) z[j] = ai_recombine<S, CW, CVT>(acc, j) * ks[j];   // exact: ks is a power of two
+            for (int j = 0; j < CW; ++j) z[j] = ai_recombine<S, CW, CVT>(acc, j);           // the integer Q K^T in units of the row / key scales
         };
         s_load(0);
         s_collect(0);
         for (int jt = 0; jt < T; ++jt) {
             const int jbase = jt * AI_BN + c0;
+            // row factor x key scale 2^f_j: the key exponent is added into the exponent field of r_z (integer pipe)
+            double rk[CW];
+            {
+                const int* kx = s_kex + jbase;
+#pragma unroll
+                for (int j = 0; j < CW; ++j) rk[j] = __hiloint2double(r_zh + kx[j], r_zl);
+            }
             if (LOGITS) {
                 if (row_ok) {
                     double* dst = p.Out[side] + ((long long)bh * N + row) * (long long)M + jbase;
                     if (jbase + CW <= M && (M & 1) == 0) {
 #pragma unroll
-                        for (int j = 0; j < CW; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(__dmul_rn(z[j], r_z), __dmul_rn(z[j + 1], r_z));
+                        for (int j = 0; j < CW; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(__dmul_rn(z[j], rk[j]), __dmul_rn(z[j + 1], rk[j + 1]));
                     } else {
 #pragma unroll
-                        for (int j = 0; j < CW; ++j) if (jbase + j < M) dst[j] = __dmul_rn(z[j], r_z);
+                        for (int j = 0; j < CW; ++j) if (jbase + j < M) dst[j] = __dmul_rn(z[j], rk[j]);
                     }
                 }
                 if (jt + 1 < T) { s_load(jt + 1); s_collect(jt + 1); }
@@ -640,12 +667,12 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
                 if (TOPK) {
                     // the scaled logit exactly as LOGITS mode stored it (one rounded product), compared with the row's
                     // threshold; ties at the threshold are kept up to column jl_i
-                    const double zz = __dmul_rn(z[j], r_z);
+                    const double zz = __dmul_rn(z[j], rk[j]);
                     const bool keep = zz > t_i || (zz == t_i && jbase + j <= jl_i);
                     ai_exp_fixed<SP>(zz - c_i, etab_s32, lo[j], h32);
                     if (!keep) { lo[j] = 0u; h32 = 0u; }
                 } else {
-                    ai_exp_fixed<SP>(fma(z[j], r_z, -c_i), etab_s32, lo[j], h32);    // p^ = rint(exp(z - c_i) 2^(8 SP - 1)), p <= 1
+                    ai_exp_fixed<SP>(fma(z[j], rk[j], -c_i), etab_s32, lo[j], h32);    // p^ = rint(exp(z - c_i) 2^(8 SP - 1)), p <= 1
                 }
                 if (SP > 4) hi[j] = h32;
             }
@@ -726,7 +753,7 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
 static size_t attn_i8_smem(int M, int S, int SP) {
     const int T = (M + AI_BN - 1) / AI_BN, Mpad = T * AI_BN;
     return (size_t)S * AI_QPLANE + (size_t)AI_STAGES * 2 * S * AI_KPLANE + 2 * SP * AI_PPLANE +
-           (size_t)Mpad * 12 + (size_t)((T + 3) & ~3) * 4 + 2 * 2048 + 512 * 8 + 512 * 8;     // table + its alignment slack
+           (size_t)Mpad * 8 + (size_t)((T + 3) & ~3) * 4 + 2 * 2048 + 512 * 8 + 512 * 8;     // table + its alignment slack
 }
 
 // the planes of one query tile plus the per-key scales of ALL M sources must fit in shared memory (sized for S = 7, SP = 6 so
@@ -832,7 +859,7 @@ cudaError_t launch_attn_i8(const AttnI8Side* q, const AttnI8Side* kv, double* co
     static const int cw = [] { const char* v = getenv("MDGAT_ATTN_CW"); return v && v[0] == '1' ? 16 : 8; }();
     // MDGAT_ATTN_CVT=0|1|2 (read once): int32 -> float64 conversion of the epilogue, see int_to_f64(); the sweep setting
     // (5, 4) is built in all three variants, the others with the default
-    static const int cvt = [] { const char* v = getenv("MDGAT_ATTN_CVT"); return v && v[0] >= '0' && v[0] <= '3' ? v[0] - '0' : AI_CVT_DEFAULT; }();
+    static const int cvt = [] { const char* v = getenv("MDGAT_ATTN_CVT"); return v && v[0] >= '0' && v[0] <= '4' ? v[0] - '0' : AI_CVT_DEFAULT; }();
     cudaError_t e;
     switch (S * 10 + SP) {
         case 43: e = attn_i8_go<4, 3, AI_CVT_DEFAULT>(p, grid, smem, mode, cw, st); break;
@@ -840,7 +867,8 @@ cudaError_t launch_attn_i8(const AttnI8Side* q, const AttnI8Side* kv, double* co
         case 54: e = cvt == 0 ? attn_i8_go<5, 4, 0>(p, grid, smem, mode, cw, st)
                    : cvt == 1 ? attn_i8_go<5, 4, 1>(p, grid, smem, mode, cw, st)
                    : cvt == 2 ? attn_i8_go<5, 4, 2>(p, grid, smem, mode, cw, st)
-                              : attn_i8_go<5, 4, 3>(p, grid, smem, mode, cw, st); break;
+                   : cvt == 3 ? attn_i8_go<5, 4, 3>(p, grid, smem, mode, cw, st)
+                              : attn_i8_go<5, 4, 4>(p, grid, smem, mode, cw, st); break;
         case 65: e = attn_i8_go<6, 5, AI_CVT_DEFAULT>(p, grid, smem, mode, cw, st); break;
         case 76: e = attn_i8_go<7, 6, AI_CVT_DEFAULT>(p, grid, smem, mode, cw, st); break;
         default: return cudaErrorInvalidValue;

@@ -98,7 +98,8 @@ cudaError_t measure_i8_peak(double* tops);
 // TMEM), see attention_i8.cu. One AttnI8Side holds the digit planes of ONE side's q, k and v head vectors.
 struct AttnI8Side {
     int8_t *Qs, *Ks, *Vs;                 // Q planes per 128-row query tile, K / V^T planes per 32-row source tile
-    double *qscale, *kscale, *vscale;     // per query row, per source row, per (b, h, channel)
+    double *qscale, *vscale;              // per query row, per (b, h, channel)
+    int* kexp;                            // per source row: exponent of its scale, shifted into the float64 exponent field
     float *kscale_f, *ktilemax;           // fp32 copy of kscale, largest kscale per source tile
     int n;                                // keypoints of this side
     int S;                                // digit planes per operand (4..7)

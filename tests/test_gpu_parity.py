@@ -483,7 +483,7 @@ def test_register_pairs_kernel_vs_reference_outputs(dev):
     from mdgat_matcher_b200 import ops
     z = np.load(os.path.join(GOLDEN, 'pins_knn_registration.npz'))
     rng = np.random.default_rng(3)
-    for i in (0, 1, 2, 4):          # case 3 is exactly planar: the sign of its null singular vector is LAPACK's choice, not defined
+    for i in (0, 1, 2):             # cases 3 (exactly planar) and 4 (three points) are rank deficient: the null singular vector's sign is LAPACK's choice
         mk0, mk1, T_gt = z['reg%d_mkpts0' % i], z['reg%d_mkpts1' % i], z['reg%d_T_gt' % i]
         n = len(mk0)
         N, M = n + 9, n + 5

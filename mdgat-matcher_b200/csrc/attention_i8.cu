@@ -44,7 +44,7 @@ constexpr int AI_STAGES = 4;               // K/V tile ring (the logits run two 
 // sub-partition); the MMA and loader warps follow the epilogue warps
 constexpr int ai_epi_threads(int cw) { return 128 * (32 / cw); }
 constexpr int ai_threads(int cw) { return ai_epi_threads(cw) + 64; }
-constexpr int AI_CVT_DEFAULT = 0;          // int32 -> float64 conversion of the epilogue (int_to_f64)
+constexpr int AI_CVT_DEFAULT = 4;          // int32 -> float64 conversion of the epilogue (int_to_f64)
 constexpr int AI_EXP_LIMIT = 60;           // |exponent| clamp of the digit scales (values beyond 2^60 are out of range)
 
 size_t attn_i8_q_bytes(int B, int n, int S) { return (size_t)B * HEADS * ((n + AI_BM - 1) / AI_BM) * S * AI_QPLANE; }
@@ -109,8 +109,15 @@ DEVINL void digits16(const double* x, double sc, uint32_t (&w)[S][4]) {
 // ---------------------------------------------------------------------------------------------------
 // blk128 / t128: index of the 128-row block and the thread inside it (the stand-alone kernel maps them to blockIdx /
 // threadIdx, the fused per-layer kernel packs four of them into a 512-thread CTA)
-template <int S>
-DEVINL void slice_qk_body(const double* __restrict__ Qh, const double* __restrict__ Kh, const AttnI8Side& o, int nqb, int blk128, int t128) {
+// STAGED (the forward path): every thread first brings ITS row (256 bytes) into shared memory with one TMA bulk copy, at a
+// 272-byte pitch (16 bytes past a multiple of 128: the LDS.128 of 32 consecutive rows are conflict-free). Read straight
+// from global memory, a warp's 16-byte loads sit 288 bytes apart -- 32 cache lines per instruction, 48 of them per row --
+// and the kernel was bound by the L1 wavefront pipe (53 % busy, lg_throttle its largest stall). stage: this warp's 32 x 272
+// bytes; bar: this warp's mbarrier (initialised by the caller, one arrival).
+constexpr int SQ_PITCH = 272;
+template <int S, bool STAGED>
+DEVINL void slice_qk_body(const double* __restrict__ Qh, const double* __restrict__ Kh, const AttnI8Side& o, int nqb, int blk128, int t128,
+                          unsigned char* stage = nullptr, uint64_t* bar = nullptr) {
     const bool isq = blk128 < nqb;
     const int n = o.n;
     const int npad = isq ? (n + AI_BM - 1) / AI_BM * AI_BM : (n + AI_BN - 1) / AI_BN * AI_BN;
@@ -120,12 +127,33 @@ DEVINL void slice_qk_body(const double* __restrict__ Qh, const double* __restric
     const int i = (blk - bh * bpb) * 128 + t128;                     // padded row inside (b, h)
     if (i >= npad) return;                                           // K only; whole warps (npad multiple of 32)
     const double* src = (isq ? Qh : Kh) + ((long long)bh * n + i) * LDH_QK;
+    if (STAGED) {
+        const unsigned have = __ballot_sync(0xffffffffu, i < n);
+        if (have) {
+            if ((t128 & 31) == 0) mbar_expect_tx(bar, (unsigned)__popc(have) * 256u);
+            __syncwarp();
+            unsigned char* mine = stage + (t128 & 31) * SQ_PITCH;
+            if (i < n) bulk_g2s(mine, src, 256, bar);
+            mbar_wait(bar, 0);
+            src = reinterpret_cast<const double*>(mine);
+        }
+    }
+    // 16-byte read of the row at element c: LDS from the staged copy, else a global load
+    const uint32_t src_s32 = STAGED ? (uint32_t)__cvta_generic_to_shared(src) : 0u;
+    auto ld2 = [&](int c) -> double2 {
+        if (STAGED) {
+            double2 v;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(src_s32 + (uint32_t)c * 8u));
+            return v;
+        }
+        return *reinterpret_cast<const double2*>(src + c);
+    };
     // the row is read twice (maximum, then 16 values at a time for the digits; the second read hits L1): 16 instead of
     // 32 live doubles keep the fused slicer at two 512-thread CTAs per SM
     double mx = 0.0;
     if (i < n) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) { const double2 v = *reinterpret_cast<const double2*>(src + c); mx = fmax(mx, fmax(fabs(v.x), fabs(v.y))); }
+        for (int c = 0; c < 32; c += 2) { const double2 v = ld2(c); mx = fmax(mx, fmax(fabs(v.x), fabs(v.y))); }
     }
     int e = 0;
     if (mx > 0.0) frexp(mx, &e);                                     // |x| < 2^e
@@ -153,7 +181,7 @@ DEVINL void slice_qk_body(const double* __restrict__ Qh, const double* __restric
         double x[16];
         if (i < n) {
 #pragma unroll
-            for (int c = 0; c < 16; c += 2) { const double2 v = *reinterpret_cast<const double2*>(src + half * 16 + c); x[c] = v.x; x[c + 1] = v.y; }
+            for (int c = 0; c < 16; c += 2) { const double2 v = ld2(half * 16 + c); x[c] = v.x; x[c + 1] = v.y; }
         } else {
 #pragma unroll
             for (int c = 0; c < 16; ++c) x[c] = 0.0;
@@ -169,7 +197,7 @@ DEVINL void slice_qk_body(const double* __restrict__ Qh, const double* __restric
 template <int S>
 __global__ void __launch_bounds__(128)
 slice_qk_kernel(const double* __restrict__ Qh, const double* __restrict__ Kh, AttnI8Side o, int B, int nqb) {
-    slice_qk_body<S>(Qh, Kh, o, nqb, (int)blockIdx.x, (int)threadIdx.x);
+    slice_qk_body<S, false>(Qh, Kh, o, nqb, (int)blockIdx.x, (int)threadIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -215,22 +243,32 @@ template <int S>
 __global__ void __launch_bounds__(32 * SV_WARPS)
 slice_v_kernel(const double* __restrict__ Vh, AttnI8Side o) { slice_v_body<S>(Vh, o, (int)blockIdx.x); }
 
-// Both sides of a layer in ONE launch (the forward path): 512-thread CTAs, [q/k blocks of side 0 | v blocks of side 0 |
-// q/k blocks of side 1 | v blocks of side 1]; a q/k CTA holds four 128-row blocks.
+// The forward path: both sides of a layer in TWO launches -- the q / k rows (128-thread CTAs, one 128-row block each, rows
+// staged through shared memory) and the v channels (512-thread CTAs, one per (b, h)).
 struct SliceSide { const double *Qh, *Kh, *Vh; AttnI8Side o; int nqb, nkb, qk_ctas, v_ctas; };
 template <int S>
-__global__ void __launch_bounds__(32 * SV_WARPS, 2)
-slice_sides_kernel(const __grid_constant__ SliceSide s0, const __grid_constant__ SliceSide s1) {
+__global__ void __launch_bounds__(128, 6)
+slice_qk_sides_kernel(const __grid_constant__ SliceSide s0, const __grid_constant__ SliceSide s1) {
+    extern __shared__ __align__(128) unsigned char sq_smem[];           // [4 warps][32 rows][272 B]
+    __shared__ __align__(8) uint64_t bars[4];
+    const int warp = (int)threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) mbar_init(&bars[warp], 1);
+    mbar_fence_init();
+    __syncthreads();
     int blk = blockIdx.x;
-    const bool second = blk >= s0.qk_ctas + s0.v_ctas;
+    const bool second = blk >= s0.nqb + s0.nkb;
     const SliceSide& sd = second ? s1 : s0;
-    if (second) blk -= s0.qk_ctas + s0.v_ctas;
-    if (blk < sd.qk_ctas) {
-        const int blk128 = blk * 4 + ((int)threadIdx.x >> 7);
-        if (blk128 < sd.nqb + sd.nkb) slice_qk_body<S>(sd.Qh, sd.Kh, sd.o, sd.nqb, blk128, (int)threadIdx.x & 127);
-    } else {
-        slice_v_body<S>(sd.Vh, sd.o, blk - sd.qk_ctas);
-    }
+    if (second) blk -= s0.nqb + s0.nkb;
+    slice_qk_body<S, true>(sd.Qh, sd.Kh, sd.o, sd.nqb, blk, (int)threadIdx.x, sq_smem + warp * 32 * SQ_PITCH, &bars[warp]);
+}
+template <int S>
+__global__ void __launch_bounds__(32 * SV_WARPS, 2)
+slice_v_sides_kernel(const __grid_constant__ SliceSide s0, const __grid_constant__ SliceSide s1) {
+    int blk = blockIdx.x;
+    const bool second = blk >= s0.v_ctas;
+    const SliceSide& sd = second ? s1 : s0;
+    if (second) blk -= s0.v_ctas;
+    slice_v_body<S>(sd.Vh, sd.o, blk);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -267,7 +305,7 @@ DEVINL void ai_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;
 DEVINL void ai_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 template <int THREADS> DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, %0;" :: "n"(THREADS) : "memory"); }   // the epilogue warps only
 // int32 -> float64, exact. CVT selects the instruction mix (the epilogue is issue-bound, the three pipes are not):
-//   0  (default) sign bit flipped into the low mantissa word of 2^52 (LOP3 + a MOV for the high word), minus 2^52 + 2^31 (DADD)
+//   0  sign bit flipped into the low mantissa word of 2^52 (LOP3 + a MOV for the high word), minus 2^52 + 2^31 (DADD)
 //   1  I2F.F64.S32: one instruction on the conversion pipe (16 lanes / clk / SM), nothing on the FP64 pipe
 //   2  the bit pattern of 2^52 + 2^31 + v built by 64-bit integer multiply-adds (IMAD.WIDE), minus 2^52 + 2^31 (DADD)
 constexpr long long AI_MAGIC_BITS = 0x4330000080000000LL;      // 2^52 + 2^31 as a double
@@ -416,6 +454,7 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
     float* s_ktm = s_ksf + Mpad;                                                  // [T] (padded to 4)
     double* s_xd = reinterpret_cast<double*>(s_ktm + ((T + 3) & ~3));             // [4][128] row exchange between column groups
     unsigned long long* s_xu = reinterpret_cast<unsigned long long*>(s_xd + 512); // [4][128]
+    double* s_lg = reinterpret_cast<double*>(s_xu + 512);                          // LOGITS: [128][33] staging tile (coalesced stores)
 
     __shared__ __align__(8) uint64_t q_full, kv_full[AI_STAGES], kv_empty[AI_STAGES], s1_full[4], s1_empty[4], p1_done,
         s_full[NSBUF], s_empty[NSBUF], p_full[2], p_empty[2], o_full;
@@ -646,17 +685,33 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
                 for (int j = 0; j < CW; ++j) rk[j] = __hiloint2double(r_zh + kx[j], r_zl);
             }
             if (LOGITS) {
-                if (row_ok) {
-                    double* dst = p.Out[side] + ((long long)bh * N + row) * (long long)M + jbase;
-                    if (jbase + CW <= M && (M & 1) == 0) {
+                // A thread owns 64 bytes of ITS row: stored from here a warp would touch 32 rows per instruction (9 B / clk / SM,
+                // the kernel would be store-bound at 2.3 TB/s). The tile goes through shared memory instead and leaves as
+                // 256-byte row segments, two rows per warp instruction.
+                if (jt > 0) epi_bar_sync<AI_EPI_THREADS>();                      // the previous tile has been read out
 #pragma unroll
-                        for (int j = 0; j < CW; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(__dmul_rn(z[j], rk[j]), __dmul_rn(z[j + 1], rk[j + 1]));
-                    } else {
+                for (int j = 0; j < CW; ++j) s_lg[rloc * 33 + c0 + j] = __dmul_rn(z[j], rk[j]);
+                if (jt + 1 < T) s_load(jt + 1);
+                epi_bar_sync<AI_EPI_THREADS>();
+                {
+                    const int tile0 = jt * AI_BN, cc = (lane & 15) * 2;
+                    const bool pair_ok = (M & 1) == 0;
 #pragma unroll
-                        for (int j = 0; j < CW; ++j) if (jbase + j < M) dst[j] = __dmul_rn(z[j], rk[j]);
+                    for (int it = 0; it < 64 / EPI_WARPS; ++it) {
+                        const int r = (warp * (64 / EPI_WARPS) + it) * 2 + (lane >> 4);
+                        const int grow = qt * AI_BM + r;
+                        const double v0 = s_lg[r * 33 + cc], v1 = s_lg[r * 33 + cc + 1];
+                        if (grow < N) {
+                            double* dst = p.Out[side] + ((long long)bh * N + grow) * (long long)M + tile0 + cc;
+                            if (pair_ok && tile0 + cc + 1 < M) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+                            else {
+                                if (tile0 + cc < M) dst[0] = v0;
+                                if (tile0 + cc + 1 < M) dst[1] = v1;
+                            }
+                        }
                     }
                 }
-                if (jt + 1 < T) { s_load(jt + 1); s_collect(jt + 1); }
+                if (jt + 1 < T) s_collect(jt + 1);
                 continue;
             }
             if (NSBUF == 2 && jt + 1 < T) s_load(jt + 1);            // one accumulator set: tile jt + 1 is still being multiplied
@@ -753,7 +808,7 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
 static size_t attn_i8_smem(int M, int S, int SP) {
     const int T = (M + AI_BN - 1) / AI_BN, Mpad = T * AI_BN;
     return (size_t)S * AI_QPLANE + (size_t)AI_STAGES * 2 * S * AI_KPLANE + 2 * SP * AI_PPLANE +
-           (size_t)Mpad * 8 + (size_t)((T + 3) & ~3) * 4 + 2 * 2048 + 512 * 8 + 512 * 8;     // table + its alignment slack
+           (size_t)Mpad * 8 + (size_t)((T + 3) & ~3) * 4 + 2 * 2048 + 512 * 8 + 512 * 8 + 128 * 33 * 8;     // table + its alignment slack, LOGITS staging tile
 }
 
 // the planes of one query tile plus the per-key scales of ALL M sources must fit in shared memory (sized for S = 7, SP = 6 so
@@ -804,16 +859,24 @@ cudaError_t launch_attn_i8_slice_sides(const double* const* Qh, const double* co
     }
     if (B <= 0 || o[0].n <= 0 || o[1].n <= 0) return cudaSuccess;
     if (o[0].S != o[1].S) return cudaErrorInvalidValue;
-    const int grid = sd[0].qk_ctas + sd[0].v_ctas + sd[1].qk_ctas + sd[1].v_ctas;
+    const int grid_qk = sd[0].nqb + sd[0].nkb + sd[1].nqb + sd[1].nkb, grid_v = sd[0].v_ctas + sd[1].v_ctas;
+    const size_t smem_qk = 4 * 32 * SQ_PITCH;
+    auto go = [&](auto kqk, auto kv) -> cudaError_t {
+        cudaError_t r = cudaFuncSetAttribute(kqk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_qk);
+        if (r != cudaSuccess) return r;
+        kqk<<<grid_qk, 128, smem_qk, st>>>(sd[0], sd[1]);
+        kv<<<grid_v, 32 * SV_WARPS, 0, st>>>(sd[0], sd[1]);
+        return cudaGetLastError();
+    };
+    cudaError_t e;
     switch (o[0].S) {
-        case 4: slice_sides_kernel<4><<<grid, 32 * SV_WARPS, 0, st>>>(sd[0], sd[1]); break;
-        case 5: slice_sides_kernel<5><<<grid, 32 * SV_WARPS, 0, st>>>(sd[0], sd[1]); break;
-        case 6: slice_sides_kernel<6><<<grid, 32 * SV_WARPS, 0, st>>>(sd[0], sd[1]); break;
-        case 7: slice_sides_kernel<7><<<grid, 32 * SV_WARPS, 0, st>>>(sd[0], sd[1]); break;
+        case 4: e = go(slice_qk_sides_kernel<4>, slice_v_sides_kernel<4>); break;
+        case 5: e = go(slice_qk_sides_kernel<5>, slice_v_sides_kernel<5>); break;
+        case 6: e = go(slice_qk_sides_kernel<6>, slice_v_sides_kernel<6>); break;
+        case 7: e = go(slice_qk_sides_kernel<7>, slice_v_sides_kernel<7>); break;
         default: return cudaErrorInvalidValue;
     }
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) count_launch();
+    if (e == cudaSuccess) count_launch(2);
     return e;
 }
 

@@ -108,6 +108,80 @@ slice_rows_kernel(const double* __restrict__ A0, int ld0, int K0, const double* 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// The forward path's slicer. slice_rows_kernel above gives every thread 128 contiguous bytes of a row, so each of its
+// load instructions touches 32 different cache lines and each plane store half-fills eight: the kernel sat at 65-80 % of
+// the L1 wavefront pipe and a third of the HBM rate (ncu, profiles/r2_*). Here a CTA owns 64 rows x one 128-column chunk:
+// the 64 row segments (1 KB each, contiguous) arrive by TMA bulk copies into shared memory with a 1040-byte row pitch
+// (16 bytes past a multiple of 128: the 8 x LDS.128 of a warp whose lanes are 32 consecutive rows are conflict-free),
+// thread (row, kt) cuts 16 consecutive k, the chunk maximum of a row is combined across the 8 warps that share it through
+// shared memory, and a warp's 16-byte plane stores fall on 4 full 128-byte lines (8 rows x 16 bytes are contiguous in the
+// core-matrix layout). Same digits, same layout, bit for bit.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SL_ROWS = 64, SL_PITCH = 1040, SL_THREADS = 512;
+template <int S>
+__global__ void __launch_bounds__(SL_THREADS, 2)
+slice_rows_tiled_kernel(const double* __restrict__ A0, int ld0, int K0, const double* __restrict__ A1, int ld1,
+                        int R, int8_t* __restrict__ Xs, double* __restrict__ rowscale, size_t chunk_stride) {
+    extern __shared__ __align__(128) unsigned char sl_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    double* s_mx = reinterpret_cast<double*>(sl_smem + SL_ROWS * SL_PITCH);          // [8][64]
+    const int tid = threadIdx.x, rl = tid & 63, kt = tid >> 6;
+    const int kchunk = blockIdx.y, k0 = kchunk * OZ_KC;
+    const long long row0 = (long long)blockIdx.x * SL_ROWS, r = row0 + rl;
+    const int Rpad = ((R + OZ_BM - 1) / OZ_BM) * OZ_BM;
+    const int nvalid = (int)max(0ll, min((long long)SL_ROWS, (long long)R - row0));
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid < 32 && nvalid > 0) {
+        if (tid == 0) mbar_expect_tx(&bar, (unsigned)nvalid * 1024u);
+        __syncwarp();
+        for (int rr = tid; rr < nvalid; rr += 32) {
+            const double* src = k0 < K0 ? A0 + (row0 + rr) * ld0 + k0 : A1 + (row0 + rr) * ld1 + (k0 - K0);
+            bulk_g2s(sl_smem + rr * SL_PITCH, src, 1024, &bar);
+        }
+    }
+    double x[16];
+    if (nvalid > 0) mbar_wait(&bar, 0);
+    if (rl < nvalid) {
+        const double* srow = reinterpret_cast<const double*>(sl_smem + rl * SL_PITCH + kt * 128);
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) { const double2 v = *reinterpret_cast<const double2*>(srow + i); x[i] = v.x; x[i + 1] = v.y; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = 0.0;
+    }
+    double mx = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mx = fmax(mx, fabs(x[i]));
+    s_mx[kt * SL_ROWS + rl] = mx;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mx = fmax(mx, s_mx[q * SL_ROWS + rl]);
+    int e = 0;
+    if (mx > 0.0) frexp(mx, &e);                         // mx = m * 2^e, m in [0.5, 1)  ->  |x| < 2^e
+    e = max(-900, min(900, e));
+    if (r >= Rpad) return;
+    if (kt == 0) rowscale[(size_t)kchunk * Rpad + r] = pow2d(e - 12);
+    const int tile = (int)(r / OZ_BM), rr = (int)(r % OZ_BM);
+    int8_t* base = Xs + (size_t)kchunk * chunk_stride + ((size_t)tile * S) * OZ_XTILE + oz_canon(rr, kt * 16);
+    // digits as in slice_group(): d_s = q_s - 128 q_(s-1), q_s = rint(x 2^(6-e) 128^s) read out of the mantissa
+#pragma unroll 1
+    for (int s = 0; s < S; ++s) {
+        const double cs = pow2d(6 - e + 7 * s);
+        const double cp = pow2d(6 - e + 7 * (s > 0 ? s - 1 : 0));
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int q = __double2loint(fma(x[i], cs, 6755399441055744.0));
+            const int qp = s > 0 ? __double2loint(fma(x[i], cp, 6755399441055744.0)) : 0;
+            const int d = q - (qp << 7);
+            w[i >> 2] |= ((uint32_t)d & 0xffu) << (8 * (i & 3));
+        }
+        *reinterpret_cast<uint4*>(base + (size_t)s * OZ_XTILE) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // tcgen05 helpers (raw PTX)
 // ---------------------------------------------------------------------------------------------------
 DEVINL uint64_t umma_desc(const void* smem, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -448,12 +522,30 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 return __hiloint2double(0x43380000 + (v >> 31), v) - MAGIC;      // exact for any int32
             };
             double t[8];
+            // S <= 6: the merged groups fit ONE 64-bit integer (S = 5: 23 + 28 = 51 bits), combined by integer multiply-adds and
+            // converted once (I2F.F64.S64) -- one conversion-pipe instruction instead of G DADDs and G - 1 DFMAs on the FP64 pipe,
+            // which the epilogue warps were queueing for (math-pipe throttle was their second largest stall). The value is
+            // 2^(14 (G - 1)) times the Horner sum; the factor goes into the exponent assembly below.
+            constexpr bool I64 = S <= 6;
+            constexpr int HSHIFT = I64 ? 14 * (G - 1) : 0;
             if (DBG > 1 && (p.dbg & 2)) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { int x = 0;
 #pragma unroll
                     for (int g = 0; g < G; ++g) x ^= m[g][j];
                     t[j] = __hiloint2double(x, x); }
+            } else if (I64) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    long long v = (long long)m[G - 1][j];
+#pragma unroll
+                    for (int g = G - 2; g >= 0; --g) {
+                        if (g == G - 2) asm("mad.wide.s32 %0, %1, 16384, %0;" : "+l"(v) : "r"(m[g][j]));
+                        else if (g == G - 3) asm("mad.wide.s32 %0, %1, 268435456, %0;" : "+l"(v) : "r"(m[g][j]));
+                        else v += (long long)m[g][j] << (14 * (G - 1 - g));
+                    }
+                    t[j] = __ll2double_rn(v);
+                }
             } else
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -463,8 +555,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 t[j] = h;                                             // even S: group 0 carries acc_0 * 128, folded into the scale below
             }
             // scale 2^(e_row - 12) * 2^(f_col) [* 2^-7] assembled in the exponent field: both factors are exact powers of two
-            const int csh0 = s_cs_hi[2 * (kc * p.Nout + col0)] - ((S & 1) ? 0x3FF00000 : 0x3FF00000 + (7 << 20));
-            const int csh1 = s_cs_hi[2 * (kc * p.Nout + col0 + 1)] - ((S & 1) ? 0x3FF00000 : 0x3FF00000 + (7 << 20));
+            const int csh0 = s_cs_hi[2 * (kc * p.Nout + col0)] - (0x3FF00000 + ((((S & 1) ? 0 : 7) + HSHIFT) << 20));
+            const int csh1 = s_cs_hi[2 * (kc * p.Nout + col0 + 1)] - (0x3FF00000 + ((((S & 1) ? 0 : 7) + HSHIFT) << 20));
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (!FULL && rbase + 8 * i >= p.R) continue;
@@ -600,6 +692,18 @@ static cudaError_t slice_rows_t(const double* A0, int ld0, int K0, const double*
                                 int8_t* Xs, double* rowscale, size_t chunk_stride, cudaStream_t st) {
     const int K = K0 + K1;
     const long long Rpad = (long long)((R + OZ_BM - 1) / OZ_BM) * OZ_BM;
+    // MDGAT_SLICE_TILED=0 (read once) falls back to the thread-per-128-bytes kernel; the tiled one needs 16-byte aligned rows
+    static const bool tiled = [] { const char* e = getenv("MDGAT_SLICE_TILED"); return !(e && e[0] == '0'); }();
+    const bool aligned = (ld0 % 2) == 0 && (reinterpret_cast<uintptr_t>(A0) % 16) == 0 &&
+                         (A1 == nullptr || ((ld1 % 2) == 0 && (reinterpret_cast<uintptr_t>(A1) % 16) == 0));
+    if (tiled && aligned) {
+        const size_t smem = (size_t)SL_ROWS * SL_PITCH + 8 * SL_ROWS * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(slice_rows_tiled_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        dim3 grid((unsigned)(Rpad / SL_ROWS), (unsigned)(K / OZ_KC));
+        slice_rows_tiled_kernel<S><<<grid, SL_THREADS, smem, st>>>(A0, ld0, K0, A1, ld1, R, Xs, rowscale, chunk_stride);
+        return cudaGetLastError();
+    }
     const long long threads = Rpad * (K / 16);
     slice_rows_kernel<S><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale, chunk_stride);
     return cudaGetLastError();

@@ -83,9 +83,39 @@ DEVINL double pow2i(int e) { return __longlong_as_double((long long)(1023 + e) <
 // the two 16-byte K halves 128 B apart (LBO), 8-row groups 256 B apart (SBO)
 DEVINL int canon32(int r, int khalf) { return (r >> 3) * 256 + khalf * 128 + (r & 7) * 16; }
 
-// S balanced base-256 digits of 16 values -> w[plane][4] (16 bytes per plane, plane 0 = most significant)
+// S balanced base-256 digits of 16 values -> w[plane][4] (16 bytes per plane, plane 0 = most significant).
+// I = rint(x sc), |I| <= 65.5 * 256^(S-1). Adding the bias B = 0x80 in every byte position makes I + B non-negative, and the
+// balanced digits are then simply its bytes with the top bit flipped (sum (u_s - 128) 256^k = I, no carries). For S <= 6 the
+// biased integer fits the mantissa: ONE fma(x, sc, 1.5 * 2^52 + B) leaves it in the low mantissa bits -- one FP64 instruction,
+// two LOP3 and a 4x4 byte transpose per value instead of a 64-bit conversion and a shift / subtract chain per digit.
 template <int S>
 DEVINL void digits16(const double* x, double sc, uint32_t (&w)[S][4]) {
+    if constexpr (S <= 6) {
+        constexpr unsigned long long BIAS = S == 4 ? 0x80808080ull : (S == 5 ? 0x8080808080ull : 0x808080808080ull);
+        const double magic = 6755399441055744.0 + (double)BIAS;        // exact: BIAS < 2^48
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint32_t lo[4], hi[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double u = fma(x[4 * g + i], sc, magic);
+                lo[i] = (uint32_t)__double2loint(u) ^ 0x80808080u;          // bytes 0..3: digits S-1 .. S-4
+                hi[i] = (uint32_t)__double2hiint(u) ^ 0x8080u;              // bytes 0..1: digits S-5, S-6 (bits 32..47 of the integer)
+            }
+            const uint32_t a0 = __byte_perm(lo[0], lo[1], 0x5140), a1 = __byte_perm(lo[0], lo[1], 0x7362);
+            const uint32_t b0 = __byte_perm(lo[2], lo[3], 0x5140), b1 = __byte_perm(lo[2], lo[3], 0x7362);
+            w[S - 1][g] = __byte_perm(a0, b0, 0x5410);
+            w[S - 2][g] = __byte_perm(a0, b0, 0x7632);
+            w[S - 3][g] = __byte_perm(a1, b1, 0x5410);
+            w[S - 4][g] = __byte_perm(a1, b1, 0x7632);
+            if (S > 4) {
+                const uint32_t c0 = __byte_perm(hi[0], hi[1], 0x5140), d0 = __byte_perm(hi[2], hi[3], 0x5140);
+                w[S > 4 ? S - 5 : 0][g] = __byte_perm(c0, d0, 0x5410);
+                if (S > 5) w[S > 5 ? S - 6 : 0][g] = __byte_perm(c0, d0, 0x7632);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int s = 0; s < S; ++s) { w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u; }
 #pragma unroll

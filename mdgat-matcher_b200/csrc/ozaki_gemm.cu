@@ -117,67 +117,81 @@ slice_rows_kernel(const double* __restrict__ A0, int ld0, int K0, const double* 
 // shared memory, and a warp's 16-byte plane stores fall on 4 full 128-byte lines (8 rows x 16 bytes are contiguous in the
 // core-matrix layout). Same digits, same layout, bit for bit.
 // ---------------------------------------------------------------------------------------------------
-constexpr int SL_ROWS = 64, SL_PITCH = 1040, SL_THREADS = 512;
+constexpr int SL_ROWS = 32, SL_PITCH = 1040, SL_THREADS = 256, SL_STAGES = 2;
+// Persistent: the CTAs (three per SM) walk the (row tile, k chunk) tiles round robin through a two-stage ring -- the rows of
+// the next tile travel while the current one is cut -- so neither the HBM latency of a tile nor the last partial wave of a
+// one-tile-per-CTA grid (1.73 waves at cfg2) is exposed.
 template <int S>
-__global__ void __launch_bounds__(SL_THREADS, 2)
+__global__ void __launch_bounds__(SL_THREADS, 3)
 slice_rows_tiled_kernel(const double* __restrict__ A0, int ld0, int K0, const double* __restrict__ A1, int ld1,
-                        int R, int8_t* __restrict__ Xs, double* __restrict__ rowscale, size_t chunk_stride) {
-    extern __shared__ __align__(128) unsigned char sl_smem[];
-    __shared__ __align__(8) uint64_t bar;
-    double* s_mx = reinterpret_cast<double*>(sl_smem + SL_ROWS * SL_PITCH);          // [8][64]
-    const int tid = threadIdx.x, rl = tid & 63, kt = tid >> 6;
-    const int kchunk = blockIdx.y, k0 = kchunk * OZ_KC;
-    const long long row0 = (long long)blockIdx.x * SL_ROWS, r = row0 + rl;
+                        int R, int nchunks, int8_t* __restrict__ Xs, double* __restrict__ rowscale, size_t chunk_stride) {
+    extern __shared__ __align__(128) unsigned char sl_smem[];                        // [stage][32 rows][1040 B] | s_mx[8][32]
+    __shared__ __align__(8) uint64_t full[SL_STAGES];
+    double* s_mx = reinterpret_cast<double*>(sl_smem + SL_STAGES * SL_ROWS * SL_PITCH);
+    const int tid = threadIdx.x, rl = tid & 31, kt = tid >> 5;
     const int Rpad = ((R + OZ_BM - 1) / OZ_BM) * OZ_BM;
-    const int nvalid = (int)max(0ll, min((long long)SL_ROWS, (long long)R - row0));
-    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    const int ntiles = (Rpad / SL_ROWS) * nchunks;
+    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
     __syncthreads();
-    if (tid < 32 && nvalid > 0) {
-        if (tid == 0) mbar_expect_tx(&bar, (unsigned)nvalid * 1024u);
+    // tile t = (row tile t / nchunks, k chunk t % nchunks); warp 0 issues the row copies of a tile (one per lane)
+    auto issue = [&](int t, int stage) {
+        const long long row0 = (long long)(t / nchunks) * SL_ROWS;
+        const int k0 = (t % nchunks) * OZ_KC;
+        const int nvalid = (int)max(0ll, min((long long)SL_ROWS, (long long)R - row0));
+        if (rl == 0) mbar_expect_tx(&full[stage], (unsigned)nvalid * 1024u);       // nvalid == 0: a plain arrival
         __syncwarp();
-        for (int rr = tid; rr < nvalid; rr += 32) {
-            const double* src = k0 < K0 ? A0 + (row0 + rr) * ld0 + k0 : A1 + (row0 + rr) * ld1 + (k0 - K0);
-            bulk_g2s(sl_smem + rr * SL_PITCH, src, 1024, &bar);
+        if (rl < nvalid) {
+            const double* src = k0 < K0 ? A0 + (row0 + rl) * ld0 + k0 : A1 + (row0 + rl) * ld1 + (k0 - K0);
+            bulk_g2s(sl_smem + (stage * SL_ROWS + rl) * SL_PITCH, src, 1024, &full[stage]);
         }
-    }
-    double x[16];
-    if (nvalid > 0) mbar_wait(&bar, 0);
-    if (rl < nvalid) {
-        const double* srow = reinterpret_cast<const double*>(sl_smem + rl * SL_PITCH + kt * 128);
+    };
+    int t = blockIdx.x;
+    if (kt == 0 && t < ntiles) issue(t, 0);
+    for (int it = 0; t < ntiles; t += gridDim.x, ++it) {
+        const int stage = it & 1;
+        if (kt == 0 && t + (int)gridDim.x < ntiles) issue(t + gridDim.x, stage ^ 1);   // that buffer was released by the barrier below
+        const long long row0 = (long long)(t / nchunks) * SL_ROWS, r = row0 + rl;
+        const int kchunk = t % nchunks;
+        const int nvalid = (int)max(0ll, min((long long)SL_ROWS, (long long)R - row0));
+        mbar_wait(&full[stage], (unsigned)((it >> 1) & 1));
+        double x[16];
+        if (rl < nvalid) {
+            const double* srow = reinterpret_cast<const double*>(sl_smem + (stage * SL_ROWS + rl) * SL_PITCH + kt * 128);
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) { const double2 v = *reinterpret_cast<const double2*>(srow + i); x[i] = v.x; x[i + 1] = v.y; }
-    } else {
+            for (int i = 0; i < 16; i += 2) { const double2 v = *reinterpret_cast<const double2*>(srow + i); x[i] = v.x; x[i + 1] = v.y; }
+        } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = 0.0;
-    }
-    double mx = 0.0;
+            for (int i = 0; i < 16; ++i) x[i] = 0.0;
+        }
+        double mx = 0.0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) mx = fmax(mx, fabs(x[i]));
-    s_mx[kt * SL_ROWS + rl] = mx;
-    __syncthreads();
+        for (int i = 0; i < 16; ++i) mx = fmax(mx, fabs(x[i]));
+        s_mx[kt * SL_ROWS + rl] = mx;
+        __syncthreads();                                     // chunk maxima visible; everybody has read its part of the stage
 #pragma unroll
-    for (int q = 0; q < 8; ++q) mx = fmax(mx, s_mx[q * SL_ROWS + rl]);
-    int e = 0;
-    if (mx > 0.0) frexp(mx, &e);                         // mx = m * 2^e, m in [0.5, 1)  ->  |x| < 2^e
-    e = max(-900, min(900, e));
-    if (r >= Rpad) return;
-    if (kt == 0) rowscale[(size_t)kchunk * Rpad + r] = pow2d(e - 12);
-    const int tile = (int)(r / OZ_BM), rr = (int)(r % OZ_BM);
-    int8_t* base = Xs + (size_t)kchunk * chunk_stride + ((size_t)tile * S) * OZ_XTILE + oz_canon(rr, kt * 16);
-    // digits as in slice_group(): d_s = q_s - 128 q_(s-1), q_s = rint(x 2^(6-e) 128^s) read out of the mantissa
+        for (int q = 0; q < 8; ++q) mx = fmax(mx, s_mx[q * SL_ROWS + rl]);
+        int e = 0;
+        if (mx > 0.0) frexp(mx, &e);                         // mx = m * 2^e, m in [0.5, 1)  ->  |x| < 2^e
+        e = max(-900, min(900, e));
+        if (kt == 0) rowscale[(size_t)kchunk * Rpad + r] = pow2d(e - 12);
+        const int tile = (int)(r / OZ_BM), rr = (int)(r % OZ_BM);
+        int8_t* base = Xs + (size_t)kchunk * chunk_stride + ((size_t)tile * S) * OZ_XTILE + oz_canon(rr, kt * 16);
+        // digits as in slice_group(): d_s = q_s - 128 q_(s-1), q_s = rint(x 2^(6-e) 128^s) read out of the mantissa
 #pragma unroll 1
-    for (int s = 0; s < S; ++s) {
-        const double cs = pow2d(6 - e + 7 * s);
-        const double cp = pow2d(6 - e + 7 * (s > 0 ? s - 1 : 0));
-        uint32_t w[4] = {0, 0, 0, 0};
+        for (int s = 0; s < S; ++s) {
+            const double cs = pow2d(6 - e + 7 * s);
+            const double cp = pow2d(6 - e + 7 * (s > 0 ? s - 1 : 0));
+            uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int q = __double2loint(fma(x[i], cs, 6755399441055744.0));
-            const int qp = s > 0 ? __double2loint(fma(x[i], cp, 6755399441055744.0)) : 0;
-            const int d = q - (qp << 7);
-            w[i >> 2] |= ((uint32_t)d & 0xffu) << (8 * (i & 3));
+            for (int i = 0; i < 16; ++i) {
+                const int q = __double2loint(fma(x[i], cs, 6755399441055744.0));
+                const int qp = s > 0 ? __double2loint(fma(x[i], cp, 6755399441055744.0)) : 0;
+                const int d = q - (qp << 7);
+                w[i >> 2] |= ((uint32_t)d & 0xffu) << (8 * (i & 3));
+            }
+            *reinterpret_cast<uint4*>(base + (size_t)s * OZ_XTILE) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        *reinterpret_cast<uint4*>(base + (size_t)s * OZ_XTILE) = make_uint4(w[0], w[1], w[2], w[3]);
+        __syncthreads();                                     // s_mx is rewritten by the next tile
     }
 }
 
@@ -697,11 +711,13 @@ static cudaError_t slice_rows_t(const double* A0, int ld0, int K0, const double*
     const bool aligned = (ld0 % 2) == 0 && (reinterpret_cast<uintptr_t>(A0) % 16) == 0 &&
                          (A1 == nullptr || ((ld1 % 2) == 0 && (reinterpret_cast<uintptr_t>(A1) % 16) == 0));
     if (tiled && aligned) {
-        const size_t smem = (size_t)SL_ROWS * SL_PITCH + 8 * SL_ROWS * sizeof(double);
+        const size_t smem = (size_t)SL_STAGES * SL_ROWS * SL_PITCH + 8 * SL_ROWS * sizeof(double);
         cudaError_t e = cudaFuncSetAttribute(slice_rows_tiled_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        dim3 grid((unsigned)(Rpad / SL_ROWS), (unsigned)(K / OZ_KC));
-        slice_rows_tiled_kernel<S><<<grid, SL_THREADS, smem, st>>>(A0, ld0, K0, A1, ld1, R, Xs, rowscale, chunk_stride);
+        static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+        const long long ntiles = (Rpad / SL_ROWS) * (K / OZ_KC);
+        const unsigned grid = (unsigned)(ntiles < 3ll * sms ? ntiles : 3ll * sms);
+        slice_rows_tiled_kernel<S><<<grid, SL_THREADS, smem, st>>>(A0, ld0, K0, A1, ld1, R, K / OZ_KC, Xs, rowscale, chunk_stride);
         return cudaGetLastError();
     }
     const long long threads = Rpad * (K / 16);

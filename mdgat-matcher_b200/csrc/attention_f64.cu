@@ -30,6 +30,8 @@ attn_full_kernel(AttnSides ps, int B, int ldo, double scale) {
     double* Vs = smem + A_STAGES * A_BN * LDH_QK;        // [stage][A_BN][LDH_V]
     double* etab = Vs + A_STAGES * A_BN * LDH_V;         // [64] 2^(j/64)
     exp_table_to_shared(etab);
+    pdl_wait();
+    pdl_trigger();
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // blockIdx.z = side * B + b: both sides of a GNN layer (they share the layer weights and are
@@ -217,10 +219,10 @@ static cudaError_t launch_attn(const AttnSides& ps, int B, int nsides, int ldo, 
     cudaError_t e;
     if (logits_only) {
         if ((e = cudaFuncSetAttribute(attn_full_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM)) != cudaSuccess) return e;
-        attn_full_kernel<true><<<grid, A_THREADS, A_SMEM, st>>>(ps, B, ldo, scale);
+        if ((e = launch_pdl(attn_full_kernel<true>, grid, dim3(A_THREADS), A_SMEM, st, ps, B, ldo, scale)) != cudaSuccess) return e;
     } else {
         if ((e = cudaFuncSetAttribute(attn_full_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM)) != cudaSuccess) return e;
-        attn_full_kernel<false><<<grid, A_THREADS, A_SMEM, st>>>(ps, B, ldo, scale);
+        if ((e = launch_pdl(attn_full_kernel<false>, grid, dim3(A_THREADS), A_SMEM, st, ps, B, ldo, scale)) != cudaSuccess) return e;
     }
     count_launch();
     return cudaGetLastError();
@@ -236,48 +238,273 @@ cudaError_t launch_attention_logits(const AttnSides& ps, int B, int nsides, cuda
 }
 
 // ------------------------------------------------------------------------------------------
-// Exact top-k + softmax + sparse PV. One warp per (b, h, query) row; lane l holds logits
-// j = l + 32 v. The k-th largest value is found by a most-significant-bit-first search on
-// the order-preserving integer image of the doubles (at most 64 counting rounds, stops as
-// soon as a candidate threshold keeps exactly k entries).
+// Exact top-k + softmax + sparse PV (dynamic_attention(), mdgat.py:196-210). One warp per (b, h, query) row; lane l
+// holds logits j = l + 32 v.
+//
+// Selection of exactly k entries, ties at the k-th value towards the lowest index:
+//   1. bounds lo_b <= z_j <= hi_b of the row from the HIGH WORDS of the doubles alone (order-preserving 32-bit keys,
+//      IMNMX + one REDUX each: no FP64 compare, no FP64 shuffle);
+//   2. every logit is mapped to one of NB = 16 VPT equal-width bins by ONE fma whose result is read out of the mantissa
+//      (u = rint(256 t), t = (z - lo_b) (NB-1)/(hi_b - lo_b) + 1/4, bin = u >> 8). The map is monotone, so an entry in a
+//      higher bin is strictly larger than any entry in a lower one. A per-warp histogram in shared memory (one atomic
+//      add per logit) and a suffix scan (NB / 32 bins per lane) give the bin b* that holds the k-th largest value and
+//      the number of entries above it;
+//   3. entries above b* are kept (lane counts, one warp scan, predicated stores: deterministic order); the handful of
+//      entries INSIDE b* (M / NB x a density factor: 2-6 at M = 512) go to a list and are ranked exactly against each
+//      other -- (value descending, column ascending) -- the best k - above of them are kept.
+// ~250 instructions per row against ~1000 for the probe-and-count search this replaces (96 dependent FP64 compare /
+// reduce rounds in the worst case). Rows the fast path cannot take -- all logits equal, a boundary bin with more than
+// TK_LMAX entries (many exactly tied logits: duplicated keypoints, load_data.py:198-201), k >= M, non-finite bounds --
+// go through topk_select_exact(): most-significant-bit-first search on the order-preserving 64-bit image.
 // ------------------------------------------------------------------------------------------
 DEVINL unsigned long long order_key(double x) {
     unsigned long long bits = (unsigned long long)__double_as_longlong(x);
     return (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
 }
+DEVINL int order_key32(int hi) { return hi ^ ((hi >> 31) & 0x7fffffff); }      // signed order of the high words; an involution
 
 constexpr int TK_WARPS = 8;
+constexpr int TK_LMAX = 64;                  // capacity of the boundary-bin list
+constexpr double TK_MAGIC = 26388279066624.0;  // 1.5 * 2^44: the low mantissa word of MAGIC + t is rint(256 t) for 0 <= t < 2^24
 
 struct __align__(16) KeptEntry { double p; int col; int pad; };
 
-// VPT = values per lane (M <= 32*VPT). Dynamic shared memory: per warp `topk` KeptEntry
-// (kept logit -> probability, column), then the 64-entry exp table.
+// The slow, always-correct selection (cold path): reloads the row, finds the k-th largest order key bit by bit, keeps
+// everything above it and the lowest-index ties. Writes exactly min(k, M) entries to kept[] in column order.
+template <int VPT>
+__device__ __noinline__ void topk_select_exact(const double* __restrict__ srow, int M, int topk, int lane, KeptEntry* kept) {
+    unsigned long long key[VPT];                 // 0 for padding: below every real key (real keys have a bit set)
+    unsigned long long kmax = 0ull, kmin = ~0ull;
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+        const int j = lane + 32 * v;
+        key[v] = j < M ? order_key(srow[j]) : 0ull;
+        if (j < M) { kmax = key[v] > kmax ? key[v] : kmax; kmin = key[v] < kmin ? key[v] : kmin; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, kmax, o), b = __shfl_xor_sync(0xffffffffu, kmin, o);
+        kmax = a > kmax ? a : kmax; kmin = b < kmin ? b : kmin;
+    }
+    unsigned long long prefix = kmin;            // k >= M: everything real is kept
+    bool found = topk >= M;
+    if (!found) {
+        const unsigned long long diff = kmax ^ kmin;
+        prefix = kmax;
+        if (diff != 0ull) {
+            const int top = 63 - __clzll((long long)diff);
+            prefix = (top == 63) ? 0ull : (kmax >> (top + 1)) << (top + 1);
+            for (int bit = top; bit >= 0; --bit) {
+                const unsigned long long cand = prefix | (1ull << bit);
+                int c = 0;
+#pragma unroll
+                for (int v = 0; v < VPT; ++v) c += (key[v] >= cand) ? 1 : 0;
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (c >= topk) {
+                    prefix = cand;
+                    if (c == topk) { found = true; break; }
+                }
+            }
+        }
+    }
+    int gt = 0;
+    if (!found) {
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) gt += (key[v] > prefix) ? 1 : 0;
+        gt = __reduce_add_sync(0xffffffffu, gt);
+    }
+    const int need = topk - gt;                  // tied entries to keep, lowest index first
+    int seen = 0, base = 0;
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+        const unsigned long long kv = key[v];
+        bool take;
+        if (found) {
+            take = kv >= prefix && kv != 0ull;
+        } else {
+            const bool eq = kv == prefix;
+            const unsigned em = __ballot_sync(0xffffffffu, eq);
+            take = (kv > prefix) || (eq && (seen + __popc(em & ((1u << lane) - 1u))) < need);
+            seen += __popc(em);
+        }
+        const unsigned tm = __ballot_sync(0xffffffffu, take);
+        if (take) {
+            const unsigned long long bits = (kv >> 63) ? (kv ^ 0x8000000000000000ull) : ~kv;
+            KeptEntry e; e.p = __longlong_as_double((long long)bits); e.col = lane + 32 * v; e.pad = 0;
+            kept[base + __popc(tm & ((1u << lane) - 1u))] = e;
+        }
+        base += __popc(tm);
+    }
+    __syncwarp();
+}
+
+// The fast selection described above. s[]: the row (padding = -inf). Returns false when the row must take the exact
+// path (nothing useful has been written then). hist aliases the start of kept[] (NB counters), alist is the warp's
+// boundary-bin list. hi_b (>= every logit, within 2^-20 relative of the maximum) is the softmax shift.
+template <int VPT>
+DEVINL bool topk_select_fast(const double (&s)[VPT], int M, int topk, int lane, KeptEntry* kept, KeptEntry* alist,
+                             double& hi_b) {
+    constexpr int NB = 16 * VPT, BPL = NB / 32;
+    constexpr bool KEEP_U = VPT <= 16;           // the 32-bit bin keys stay in registers when there is room
+    unsigned* hist = reinterpret_cast<unsigned*>(kept);
+#pragma unroll
+    for (int q = 0; q < BPL / 4; ++q) reinterpret_cast<uint4*>(hist)[lane + 32 * q] = make_uint4(0u, 0u, 0u, 0u);
+    int kmax = (int)0x80000000, kmin = 0x7fffffff;
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+        const int key = order_key32(__double2hiint(s[v]));
+        kmax = max(kmax, key);
+        kmin = min(kmin, (lane + 32 * v) < M ? key : 0x7fffffff);
+    }
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    const int hmax = order_key32(kmax), hmin = order_key32(kmin);
+    hi_b = __hiloint2double(hmax, hmax < 0 ? 0 : -1);
+    const double lo_b = __hiloint2double(hmin, hmin < 0 ? -1 : 0);
+    const double range = hi_b - lo_b;
+    const double scale = (double)(NB - 1) / range;
+    // |lo_b| scale < 2^40 keeps MAGIC + 1/4 - lo_b scale on the 2^-8 grid of MAGIC (NaN / Inf bounds fail the test too)
+    if (!(range > 0.0 && fmax(fabs(lo_b), fabs(hi_b)) * scale < 1.0e12) || topk >= M) return false;
+    const double off = (TK_MAGIC + 0.25) - lo_b * scale;
+    auto ukey = [&](int v) -> unsigned { return (unsigned)__double2loint(fma(s[v], scale, off)); };   // -inf -> 0
+    unsigned u[KEEP_U ? VPT : 1];
+    __syncwarp();
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+        const unsigned uv = ukey(v);
+        if (KEEP_U) u[v] = uv;
+        atomicAdd(hist + ((uv >> 8) & (unsigned)(NB - 1)), 1u);
+    }
+    __syncwarp();
+    // suffix scan from the top bin: lane l owns bins [BPL l, BPL (l + 1))
+    unsigned h[BPL];
+#pragma unroll
+    for (int q = 0; q < BPL / 4; ++q) {
+        const uint4 t = reinterpret_cast<const uint4*>(hist)[lane * (BPL / 4) + q];
+        h[4 * q] = t.x; h[4 * q + 1] = t.y; h[4 * q + 2] = t.z; h[4 * q + 3] = t.w;
+    }
+    int tot = 0;
+#pragma unroll
+    for (int b = 0; b < BPL; ++b) tot += (int)h[b];
+    int suf = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_down_sync(0xffffffffu, suf, o);
+        if (lane + o < 32) suf += t;
+    }
+    const int above_lane = suf - tot;
+    const bool mine = above_lane < topk && topk <= suf;      // exactly one lane (1 <= k <= M <= total count)
+    int bstar = 0, above = 0;
+    if (mine) {
+        int c = above_lane;
+        bool done = false;
+#pragma unroll
+        for (int b = BPL - 1; b >= 0; --b) {
+            if (!done) {
+                if (c + (int)h[b] >= topk) { bstar = lane * BPL + b; above = c; done = true; }
+                else c += (int)h[b];
+            }
+        }
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+    bstar = __shfl_sync(0xffffffffu, bstar, src);
+    above = __shfl_sync(0xffffffffu, above, src);
+    // padding has u = 0 and every real entry u >= 62 (t >= 1/4 - rounding), so a lower limit of at least 1 keeps the
+    // padding out of the boundary list without a column test
+    const unsigned t_hi = (unsigned)(bstar + 1) << 8, t_lo = max((unsigned)bstar << 8, 1u);
+    // entries above the boundary bin: per-lane count, exclusive warp scan, predicated stores (lane-major order). The
+    // histogram is dead (every lane passed the shuffles above after reading its bins), kept[] may be overwritten.
+    // Entries INSIDE the boundary bin are rare (L of them per row): one ballot per v finds them, and only a non-empty
+    // ballot (warp-uniform branch) does any work; list positions follow (v, lane), so the list is deterministic.
+    int cnt = 0, L = 0;
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+        const unsigned uv = KEEP_U ? u[v] : ukey(v);
+        if (uv >= t_hi) ++cnt;
+        const bool amb = uv < t_hi && uv >= t_lo;
+        const unsigned am = __ballot_sync(0xffffffffu, amb);
+        if (am != 0u) {
+            const int q = L + __popc(am & ((1u << lane) - 1u));
+            if (amb && q < TK_LMAX) { KeptEntry e; e.p = s[v]; e.col = lane + 32 * v; e.pad = 0; alist[q] = e; }
+            L += __popc(am);
+        }
+    }
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    KeptEntry* dst = kept + (inc - cnt);
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+        const unsigned uv = KEEP_U ? u[v] : ukey(v);
+        if (uv >= t_hi) {
+            KeptEntry e; e.p = s[v]; e.col = lane + 32 * v; e.pad = 0;
+            *dst++ = e;
+        }
+    }
+    __syncwarp();
+    if (L > TK_LMAX) return false;
+    // exact rank inside the boundary bin: (value descending, column ascending) is a strict total order, so the ranks
+    // are a permutation of 0 .. L-1 and the entries of rank < need land on distinct slots
+    const int need = topk - above;
+    for (int t = lane; t < L; t += 32) {
+        const KeptEntry et = alist[t];
+        int rank = 0;
+        for (int q = 0; q < L; ++q) {
+            const KeptEntry eq = alist[q];
+            rank += (eq.p > et.p || (eq.p == et.p && eq.col < et.col)) ? 1 : 0;
+        }
+        if (rank < need) kept[above + rank] = et;
+    }
+    __syncwarp();
+    return true;
+}
+
+// VPT = values per lane (M <= 32*VPT). Dynamic shared memory: per warp max(topk, 4 VPT) KeptEntry (kept logit ->
+// probability, column; its first 64 VPT bytes double as the selection histogram), per warp TK_LMAX boundary-bin
+// entries, then the 64-entry exp table.
 //
 // SMEM_V = false: one warp per row, 8 rows per CTA; the sparse P.V gathers its k value rows from global memory
 //                 (L2): 32 KB per query row, 2.1 GB per side at cfg2 -- the L2 read bandwidth is the bound.
-// SMEM_V = true : one CTA (16 warps) per (b, h); the whole value matrix of the head (M x 34 doubles, 136 KB at
-//                 M = 512) is brought in by ONE TMA bulk copy and every warp walks query rows i = warp, warp + 16, ..
-//                 gathering from shared memory. The logits row of the next query is requested before the P.V of
-//                 the current one. L2 traffic for V drops from 2.1 GB to 18 MB per side; the bound becomes the
-//                 shared-memory read of k x 256 B per row.
+// SMEM_V = true : a CTA (24 warps) owns 1 / nsplit of the query rows of one (side, b, h) (grid = (b h, nsplit, side):
+//                 nsplit is chosen so that the CTA count fills whole waves of the 148 SMs); the whole value matrix
+//                 of the head (M x 34 doubles, 136 KB at M = 512) is brought in by ONE TMA bulk copy and every warp
+//                 walks query rows i = r0 + warp, r0 + warp + 24, .. gathering from shared memory. The logits row of
+//                 the next query is requested before the P.V of the current one.
 constexpr int TKS_WARPS = 24;
+struct TopkSides { const double* S[2]; const double* V[2]; double* Out[2]; int N[2], M[2]; };
+DEVINL constexpr int tk_kept_entries(int topk, int vpt) { return topk > 4 * vpt ? topk : 4 * vpt; }
+
 template <int VPT, bool SMEM_V>
 __global__ void __launch_bounds__(SMEM_V ? 32 * TKS_WARPS : 32 * TK_WARPS, (SMEM_V || VPT != 16) ? 1 : 3)
-topk_softmax_pv_kernel(const double* __restrict__ S, const double* __restrict__ V, double* __restrict__ Out,
-                       int ldo, int N, int M, int topk, long long total_rows) {
+topk_softmax_pv_kernel(const __grid_constant__ TopkSides ps, int ldo, int topk, int nbh) {
     extern __shared__ __align__(16) unsigned char tk_smem[];
     constexpr int WARPS = SMEM_V ? TKS_WARPS : TK_WARPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    KeptEntry* kept = reinterpret_cast<KeptEntry*>(tk_smem) + (size_t)warp * topk;
-    double* etab = reinterpret_cast<double*>(tk_smem + (size_t)WARPS * topk * sizeof(KeptEntry));
+    const int side = blockIdx.z;
+    const int N = ps.N[side], M = ps.M[side];
+    const double* __restrict__ S = ps.S[side];
+    const double* __restrict__ V = ps.V[side];
+    double* __restrict__ Out = ps.Out[side];
+    const int KS = tk_kept_entries(topk, VPT);
+    KeptEntry* kept = reinterpret_cast<KeptEntry*>(tk_smem) + (size_t)warp * KS;
+    KeptEntry* alist = reinterpret_cast<KeptEntry*>(tk_smem) + (size_t)WARPS * KS + (size_t)warp * TK_LMAX;
+    double* etab = reinterpret_cast<double*>(reinterpret_cast<KeptEntry*>(tk_smem) + (size_t)WARPS * (KS + TK_LMAX));
     double* sV = etab + 64;                                               // SMEM_V: [M][LDH_V]
     __shared__ __align__(8) uint64_t v_bar;
     exp_table_to_shared(etab);
-    long long bh; int i;
+    long long bh; int i, iend;
     if (SMEM_V) {
-        bh = blockIdx.x; i = warp;
+        bh = blockIdx.x;
+        const int per = (N + (int)gridDim.y - 1) / (int)gridDim.y;
+        i = (int)blockIdx.y * per + warp;
+        iend = min(N, ((int)blockIdx.y + 1) * per);
         if (threadIdx.x == 0) { mbar_init(&v_bar, 1); mbar_fence_init(); }
         __syncthreads();
+        pdl_wait();
+        pdl_trigger();
         if (threadIdx.x == 0) {
             const unsigned bytes = (unsigned)((size_t)M * LDH_V * sizeof(double));
             mbar_expect_tx(&v_bar, bytes);
@@ -285,10 +512,13 @@ topk_softmax_pv_kernel(const double* __restrict__ S, const double* __restrict__ 
         }
     } else {
         __syncthreads();
+        pdl_wait();
+        pdl_trigger();
         const long long g0 = (long long)blockIdx.x * TK_WARPS + warp;      // row in (B,4,N) order
-        if (g0 >= total_rows) return;
         bh = g0 / N;
         i = (int)(g0 - bh * N);
+        iend = N;
+        if (bh >= nbh) return;                                             // past the last row of this side (whole warps)
     }
     const int b = (int)(bh / HEADS), h = (int)(bh - (long long)b * HEADS);
     const double* Vbh = SMEM_V ? sV : V + bh * (long long)M * LDH_V;
@@ -297,113 +527,22 @@ topk_softmax_pv_kernel(const double* __restrict__ S, const double* __restrict__ 
 #pragma unroll
         for (int v = 0; v < VPT; ++v) {
             const int j = lane + 32 * v;
-            dst[v] = j < M ? srow[j] : -INFINITY;          // padding never passes a ">= finite" test
+            dst[v] = j < M ? srow[j] : -INFINITY;          // padding: bin 0, never kept
         }
     };
     double s[VPT];
-    if (i < N) load_row(i, s);
+    if (i < iend) load_row(i, s);
     bool v_ready = !SMEM_V;
-  for (; i < N; i += WARPS) {
-    double mx = -INFINITY, mn = INFINITY;
-#pragma unroll
-    for (int v = 0; v < VPT; ++v) {
-        if (lane + 32 * v < M) { mx = fmax(mx, s[v]); mn = fmin(mn, s[v]); }
-    }
-    mx = warp_max_d(mx);
-    mn = -warp_max_d(-mn);
-
-    // ---- fast path: bisect the VALUE interval [mn, mx] until a threshold keeps exactly k
-    double thr = mn;
-    bool exact = topk >= M;
-    if (!exact) {
-        // bracket [lo, hi] with count(>= lo) = clo > k > chi = count(>= hi) (chi taken as 1 at the maximum); even steps
-        // place the probe by linear interpolation of the counts (3-4 probes on smooth rows), odd steps bisect, so the
-        // bracket at least halves every two probes
-        double lo = mn, hi = mx;
-        int clo = M, chi = 1;
-        for (int step = 0; step < 96; ++step) {
-            double mid = lo + 0.5 * (hi - lo);
-            if (!(mid > lo && mid < hi)) break;           // interval collapsed: ties or adjacent doubles
-            if ((step & 1) == 0) {
-                const double guess = lo + (hi - lo) * ((double)(clo - topk) / (double)(clo - chi));
-                if (guess > lo && guess < hi) mid = guess;
-            }
-            int c = 0;
-#pragma unroll
-            for (int v = 0; v < VPT; ++v) c += (s[v] >= mid) ? 1 : 0;
-            c = __reduce_add_sync(0xffffffffu, c);
-            if (c == topk) { thr = mid; exact = true; break; }
-            if (c > topk) { lo = mid; clo = c; } else { hi = mid; chi = c; }
-        }
-    }
-    unsigned long long sel = 0ull;                        // bit v: keep s[v]
-    if (exact) {
-#pragma unroll
-        for (int v = 0; v < VPT; ++v) sel |= (unsigned long long)(s[v] >= thr && (lane + 32 * v) < M) << v;
-    } else {
-        // ---- exact path for ties at the k-th value: most-significant-bit-first search on the
-        // order-preserving integer image of the doubles, then lowest-index tie-break
-        auto keyof = [&](int v) -> unsigned long long { return (lane + 32 * v) < M ? order_key(s[v]) : 0ull; };
-        const unsigned long long kmax = order_key(mx), kmin = order_key(mn);
-        const unsigned long long diff = kmax ^ kmin;
-        unsigned long long prefix = kmax;
-        bool found = false;
-        if (diff != 0ull) {
-            const int top = 63 - __clzll((long long)diff);
-            prefix = (top == 63) ? 0ull : (kmax >> (top + 1)) << (top + 1);
-            for (int bit = top; bit >= 0; --bit) {
-                const unsigned long long cand = prefix | (1ull << bit);
-                int c = 0;
-#pragma unroll
-                for (int v = 0; v < VPT; ++v) c += (keyof(v) >= cand) ? 1 : 0;
-                c = __reduce_add_sync(0xffffffffu, c);
-                if (c >= topk) {
-                    prefix = cand;
-                    if (c == topk) { found = true; break; }
-                }
-            }
-        }
-        int gt = 0;
-        if (!found) {
-#pragma unroll
-            for (int v = 0; v < VPT; ++v) gt += (keyof(v) > prefix) ? 1 : 0;
-            gt = __reduce_add_sync(0xffffffffu, gt);
-        }
-        const int need = topk - gt;                       // tied entries to keep, lowest index first
-        int seen = 0;
-#pragma unroll
-        for (int v = 0; v < VPT; ++v) {
-            const unsigned long long kv = keyof(v);
-            bool take;
-            if (found) {
-                take = kv >= prefix && kv != 0ull;
-            } else {
-                const bool eq = kv == prefix;
-                const unsigned em = __ballot_sync(0xffffffffu, eq);
-                take = (kv > prefix) || (eq && (seen + __popc(em & ((1u << lane) - 1u))) < need);
-                seen += __popc(em);
-            }
-            sel |= (unsigned long long)take << v;
-        }
-    }
-    // ---- compaction of the kept (logit, column) pairs
-    int base = 0;
-#pragma unroll
-    for (int v = 0; v < VPT; ++v) {
-        const bool take = (sel >> v) & 1ull;
-        const unsigned tm = __ballot_sync(0xffffffffu, take);
-        if (take) {
-            KeptEntry e; e.p = s[v]; e.col = lane + 32 * v; e.pad = 0;
-            kept[base + __popc(tm & ((1u << lane) - 1u))] = e;
-        }
-        base += __popc(tm);
-    }
-    __syncwarp();
+  for (; i < iend; i += WARPS) {
+    double mx;
+    if (!topk_select_fast<VPT>(s, M, topk, lane, kept, alist, mx))
+        topk_select_exact<VPT>(S + (bh * N + i) * (long long)M, M, topk, lane, kept);
+    const int nk = min(topk, M);
     // the logits of this warp's next row travel while the P.V below runs
-    if (SMEM_V && i + WARPS < N) load_row(i + WARPS, s);
-    // softmax over the kept k (mdgat.py:206-207); the row maximum is always among them
+    if (SMEM_V && i + WARPS < iend) load_row(i + WARPS, s);
+    // softmax over the kept k (mdgat.py:206-207), shifted by the upper bound of the row maximum
     double sum = 0.0;
-    for (int t = lane; t < topk; t += 32) {
+    for (int t = lane; t < nk; t += 32) {
         const double e = exp_fast_neg(kept[t].p - mx, etab);
         kept[t].p = e;
         sum += e;
@@ -422,13 +561,13 @@ topk_softmax_pv_kernel(const double* __restrict__ S, const double* __restrict__ 
     };
     double2 a0 = make_double2(0.0, 0.0), a1 = a0;
     int t = hw;
-    for (; t + 2 < topk; t += 4) {
+    for (; t + 2 < nk; t += 4) {
         const KeptEntry e0 = kept[t], e1 = kept[t + 2];
         const double2 v0 = vload(e0.col), v1 = vload(e1.col);
         a0.x = fma(e0.p, v0.x, a0.x); a0.y = fma(e0.p, v0.y, a0.y);
         a1.x = fma(e1.p, v1.x, a1.x); a1.y = fma(e1.p, v1.y, a1.y);
     }
-    if (t < topk) {
+    if (t < nk) {
         const KeptEntry e0 = kept[t];
         const double2 v0 = vload(e0.col);
         a0.x = fma(e0.p, v0.x, a0.x); a0.y = fma(e0.p, v0.y, a0.y);
@@ -555,40 +694,71 @@ cudaError_t launch_topk_threshold(const double* S, double* thr, int* jlast, doub
     return cudaGetLastError();
 }
 
+static size_t topk_smem_bytes(int warps, int topk, int vpt, int m_smem_v) {
+    return ((size_t)warps * (tk_kept_entries(topk, vpt) + TK_LMAX)) * sizeof(KeptEntry) + 64 * sizeof(double) +
+           (size_t)m_smem_v * LDH_V * sizeof(double);
+}
+
 template <int VPT>
-static cudaError_t launch_topk_t(const double* S, const double* V, double* Out, int ldo, int N, int M, int topk,
-                                 long long rows, cudaStream_t st) {
-    // value matrix of a head resident in shared memory when it fits next to the kept lists (M = 512, k = 128: 169 KB)
-    const size_t smem_v = (size_t)TKS_WARPS * topk * sizeof(KeptEntry) + 64 * sizeof(double) + (size_t)M * LDH_V * sizeof(double);
+static cudaError_t launch_topk_t(const TopkSides& ps, int nsides, int ldo, int B, int topk, cudaStream_t st) {
+    const int nbh = B * HEADS;
+    int nmax = 0, nmin = 1 << 30, mmax = 0;
+    for (int s = 0; s < nsides; ++s) { nmax = ps.N[s] > nmax ? ps.N[s] : nmax; nmin = ps.N[s] < nmin ? ps.N[s] : nmin; mmax = ps.M[s] > mmax ? ps.M[s] : mmax; }
+    // value matrix of a head resident in shared memory when it fits next to the kept lists (M = 512, k = 128: 209 KB)
+    const size_t smem_v = topk_smem_bytes(TKS_WARPS, topk, VPT, mmax);
     if constexpr (VPT == 16) {
         static const bool smem_variant = [] { const char* e = getenv("MDGAT_TOPK_SMEMV"); return !(e && e[0] == '0'); }();
-        if (smem_variant && smem_v <= 200 * 1024 && N >= TKS_WARPS) {
+        if (smem_variant && smem_v <= 227 * 1024 && nmin >= TKS_WARPS) {
             cudaError_t e = cudaFuncSetAttribute(topk_softmax_pv_kernel<VPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v);
             if (e != cudaSuccess) return e;
-            topk_softmax_pv_kernel<VPT, true><<<(unsigned)(rows / N), 32 * TKS_WARPS, smem_v, st>>>(S, V, Out, ldo, N, M, topk, rows);
-            return cudaSuccess;
+            // rows of a (side, b, h) over nsplit CTAs: the split that needs the fewest (fractional) waves of 148 CTAs; every
+            // extra CTA reloads the value matrix, so ties go to the smaller split
+            static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n > 0 ? n : 148; }();
+            static const int split_env = [] { const char* e = getenv("MDGAT_TOPK_SPLIT"); return e ? atoi(e) : 0; }();
+            int nsplit = 1; double best = 1e30;
+            for (int ns = 1; ns <= 8; ns *= 2) {
+                if (nmin / ns < TKS_WARPS) break;
+                const long long ctas = (long long)nsides * nbh * ns;
+                const double cost = (double)((ctas + sms - 1) / sms) / ns + 0.02 * ns;
+                if (cost < best - 1e-9) { best = cost; nsplit = ns; }
+            }
+            if (split_env > 0 && nmin / split_env >= 1) nsplit = split_env;
+            return launch_pdl(topk_softmax_pv_kernel<VPT, true>, dim3((unsigned)nbh, (unsigned)nsplit, (unsigned)nsides), dim3(32 * TKS_WARPS), smem_v, st, ps, ldo, topk, nbh);
         }
     }
-    const size_t smem = (size_t)TK_WARPS * topk * sizeof(KeptEntry) + 64 * sizeof(double);
+    const size_t smem = topk_smem_bytes(TK_WARPS, topk, VPT, 0);
     cudaError_t e = cudaFuncSetAttribute(topk_softmax_pv_kernel<VPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const unsigned grid = (unsigned)((rows + TK_WARPS - 1) / TK_WARPS);
-    topk_softmax_pv_kernel<VPT, false><<<grid, 32 * TK_WARPS, smem, st>>>(S, V, Out, ldo, N, M, topk, rows);
-    return cudaSuccess;
+    const unsigned grid = (unsigned)(((long long)nbh * nmax + TK_WARPS - 1) / TK_WARPS);
+    return launch_pdl(topk_softmax_pv_kernel<VPT, false>, dim3(grid, 1, (unsigned)nsides), dim3(32 * TK_WARPS), smem, st, ps, ldo, topk, nbh);
+}
+
+// both sides of a layer in one launch (S[s]: dense logits (B,4,N[s],M[s]); V[s]: head-major values of the source side)
+cudaError_t launch_topk_softmax_pv_sides(const double* const* S, const double* const* V, double* const* Out, int ldo,
+                                         int B, const int* N, const int* M, int nsides, int topk, cudaStream_t st) {
+    if (B <= 0 || nsides <= 0) return cudaSuccess;
+    TopkSides ps;
+    int mmax = 0;
+    for (int s = 0; s < 2; ++s) {
+        const int t = s < nsides ? s : 0;
+        ps.S[s] = S[t]; ps.V[s] = V[t]; ps.Out[s] = Out[t]; ps.N[s] = N[t]; ps.M[s] = M[t];
+        if (N[t] <= 0 || M[t] <= 0) return cudaErrorInvalidValue;
+        mmax = M[t] > mmax ? M[t] : mmax;
+    }
+    cudaError_t e;
+    if (mmax <= 512) e = launch_topk_t<16>(ps, nsides, ldo, B, topk, st);
+    else if (mmax <= 1024) e = launch_topk_t<32>(ps, nsides, ldo, B, topk, st);
+    else if (mmax <= 2048) e = launch_topk_t<64>(ps, nsides, ldo, B, topk, st);
+    else return cudaErrorInvalidValue;
+    if (e != cudaSuccess) return e;
+    count_launch();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_topk_softmax_pv(const double* S, const double* V, double* Out, int ldo,
                                    int B, int N, int M, int topk, cudaStream_t st) {
     if (B <= 0 || N <= 0) return cudaSuccess;
-    const long long rows = (long long)B * HEADS * N;
-    cudaError_t e;
-    if (M <= 512) e = launch_topk_t<16>(S, V, Out, ldo, N, M, topk, rows, st);
-    else if (M <= 1024) e = launch_topk_t<32>(S, V, Out, ldo, N, M, topk, rows, st);
-    else if (M <= 2048) e = launch_topk_t<64>(S, V, Out, ldo, N, M, topk, rows, st);
-    else return cudaErrorInvalidValue;
-    if (e != cudaSuccess) return e;
-    count_launch();
-    return cudaGetLastError();
+    return launch_topk_softmax_pv_sides(&S, &V, &Out, ldo, B, &N, &M, 1, topk, st);
 }
 
 }  // namespace mdgat

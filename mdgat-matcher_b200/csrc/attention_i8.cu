@@ -285,6 +285,8 @@ slice_qk_sides_kernel(const __grid_constant__ SliceSide s0, const __grid_constan
     if ((threadIdx.x & 31) == 0) mbar_init(&bars[warp], 1);
     mbar_fence_init();
     __syncthreads();
+    pdl_wait();
+    pdl_trigger();
     int blk = blockIdx.x;
     const bool second = blk >= s0.nqb + s0.nkb;
     const SliceSide& sd = second ? s1 : s0;
@@ -294,6 +296,8 @@ slice_qk_sides_kernel(const __grid_constant__ SliceSide s0, const __grid_constan
 template <int S>
 __global__ void __launch_bounds__(32 * SV_WARPS, 2)
 slice_v_sides_kernel(const __grid_constant__ SliceSide s0, const __grid_constant__ SliceSide s1) {
+    pdl_wait();
+    pdl_trigger();
     int blk = blockIdx.x;
     const bool second = blk >= s0.v_ctas;
     const SliceSide& sd = second ? s1 : s0;
@@ -514,6 +518,8 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
     __syncthreads();
     ai_fence_after();
     const uint32_t tmem = tmem_base_s;
+    pdl_wait();                                            // barriers, TMEM and the table are set up while the slicers drain
+    pdl_trigger();
 
     const int8_t* gK = Kd.Ks + (size_t)bh * T * (S * AI_KPLANE);
     const int8_t* gV = Kd.Vs + (size_t)bh * T * (S * AI_KPLANE);
@@ -894,9 +900,9 @@ cudaError_t launch_attn_i8_slice_sides(const double* const* Qh, const double* co
     auto go = [&](auto kqk, auto kv) -> cudaError_t {
         cudaError_t r = cudaFuncSetAttribute(kqk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_qk);
         if (r != cudaSuccess) return r;
-        kqk<<<grid_qk, 128, smem_qk, st>>>(sd[0], sd[1]);
-        kv<<<grid_v, 32 * SV_WARPS, 0, st>>>(sd[0], sd[1]);
-        return cudaGetLastError();
+        r = launch_pdl(kqk, dim3(grid_qk), dim3(128), smem_qk, st, sd[0], sd[1]);
+        if (r != cudaSuccess) return r;
+        return launch_pdl(kv, dim3(grid_v), dim3(32 * SV_WARPS), 0, st, sd[0], sd[1]);
     };
     cudaError_t e;
     switch (o[0].S) {
@@ -915,8 +921,7 @@ static cudaError_t attn_i8_go(const AttnI8Params& p, dim3 grid, size_t smem, int
     auto go = [&](auto kern, int threads) -> cudaError_t {
         cudaError_t r = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (r != cudaSuccess) return r;
-        kern<<<grid, threads, smem, st>>>(p);
-        return cudaSuccess;
+        return launch_pdl(kern, grid, dim3(threads), smem, st, p);
     };
     if (mode == AI_MODE_LOGITS) return cw == 16 ? go(attn_i8_kernel<S, SP, AI_MODE_LOGITS, 16, CVT>, ai_threads(16)) : go(attn_i8_kernel<S, SP, AI_MODE_LOGITS, 8, CVT>, ai_threads(8));
     if (mode == AI_MODE_TOPK) return cw == 16 ? go(attn_i8_kernel<S, SP, AI_MODE_TOPK, 16, CVT>, ai_threads(16)) : go(attn_i8_kernel<S, SP, AI_MODE_TOPK, 8, CVT>, ai_threads(8));

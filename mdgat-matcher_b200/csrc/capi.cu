@@ -57,6 +57,7 @@ void prof_mark(int stage, cudaStream_t st) {
     g_prof.launches_at.push_back(g_launches.load());
 }
 }  // namespace
+namespace mdgat { bool pdl_enabled() { static const bool on = [] { const char* e = getenv("MDGAT_PDL"); return !(e && e[0] == '0'); }(); return on; } }
 namespace mdgat { void count_launch(int n) { g_launches.fetch_add(n); } long long* g_trace_dev = nullptr; int g_debug_flags = 0; }
 
 namespace {
@@ -190,11 +191,7 @@ cudaError_t attention_layer(const AttnSides& ps, int B, int nsides, int ldo, int
         cudaError_t e = launch_attn_i8(qd, kvd, lg, B, nsides, 0, AI_MODE_LOGITS, nullptr, SP, st);
         if (e != cudaSuccess) return e;
         if (tks == nullptr) {
-            for (int s = 0; s < nsides; ++s) {
-                e = launch_topk_softmax_pv(lg[s], ps.V[s], ps.Out[s], ldo, B, ps.N[s], ps.M[s], topk, st);
-                if (e != cudaSuccess) return e;
-            }
-            return cudaSuccess;
+            return launch_topk_softmax_pv_sides(lg, ps.V, ps.Out, ldo, B, ps.N, ps.M, nsides, topk, st);
         }
         AttnI8TopK tk;
         size_t off = 0;
@@ -213,11 +210,7 @@ cudaError_t attention_layer(const AttnSides& ps, int B, int nsides, int ldo, int
     for (int s = 0; s < nsides; ++s) { lg.Out[s] = sp; sp += (size_t)B * HEADS * ps.N[s] * ps.M[s]; }
     cudaError_t e = launch_attention_logits(lg, B, nsides, st);
     if (e != cudaSuccess) return e;
-    for (int s = 0; s < nsides; ++s) {
-        e = launch_topk_softmax_pv(lg.Out[s], ps.V[s], ps.Out[s], ldo, B, ps.N[s], ps.M[s], topk, st);
-        if (e != cudaSuccess) return e;
-    }
-    return cudaSuccess;
+    return launch_topk_softmax_pv_sides(lg.Out, ps.V, ps.Out, ldo, B, ps.N, ps.M, nsides, topk, st);
 }
 
 cudaError_t encode(const mdgat_forward_in* in, int B, int N, int M, int in_dtype, int score_dtype,

@@ -93,6 +93,14 @@ struct Tracer {
     }
 };
 
+// ---- programmatic dependent launch (PDL). A kernel launched through launch_pdl() may become resident while the kernel
+// before it in the stream is still draining: everything up to pdl_wait() (barrier / TMEM set-up, tables from constant
+// data) overlaps that tail. pdl_wait() returns once the preceding kernel has completed and its writes are visible; no
+// global memory the forward pass produces may be read or written before it. pdl_trigger() lets the NEXT kernel in the
+// stream start its own prologue; it is issued right after the wait, so at most one grid is parked at a time.
+DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 DEVINL double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 DEVINL double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
@@ -171,6 +179,22 @@ DEVINL double exp_neg_abs47(double x, const double* tbl) {
 namespace mdgat_host {
 void set_error(const char* fmt, ...);
 }
+
+// ---- host side of PDL: launch with the programmatic-stream-serialization attribute (MDGAT_PDL=0 switches it off; the
+// kernels' griddepcontrol instructions are no-ops then). Only kernels that call pdl_wait() may be launched this way.
+namespace mdgat {
+bool pdl_enabled();                                        // capi.cu
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+}  // namespace mdgat
 #define MDGAT_CUDA_OK(expr)                                                              \
     do {                                                                                 \
         cudaError_t _e = (expr);                                                         \

@@ -49,6 +49,8 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_f64_kernel(GemmParams p, in
     const int row_begin = blockIdx.x * rows_per_stripe;
     const int row_end = min(p.R, row_begin + rows_per_stripe);
     if (row_begin >= row_end) return;
+    pdl_wait();
+    pdl_trigger();
     const int ntiles = (row_end - row_begin + BM - 1) / BM;
     const int nk = (p.K + G_BK - 1) / G_BK;
     const int total = ntiles * nk;
@@ -184,8 +186,7 @@ static cudaError_t launch_inst(const GemmParams& p, dim3 grid, int rps, cudaStre
     // per-device attribute; set on every launch (cheap) so multi-device processes stay correct
     cudaError_t e = cudaFuncSetAttribute(gemm_f64_kernel<MI, EPI, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    gemm_f64_kernel<MI, EPI, WT><<<grid, G_THREADS, smem, st>>>(p, rps);
-    return cudaSuccess;
+    return launch_pdl(gemm_f64_kernel<MI, EPI, WT>, grid, dim3(G_THREADS), smem, st, p, rps);
 }
 
 template <int MI>

@@ -44,6 +44,9 @@ cudaError_t launch_attention_logits(const AttnSides& ps, int B, int nsides, cuda
 // Exact top-k selection + softmax + sparse P.V from materialised logits S (B,4,N,M).
 cudaError_t launch_topk_softmax_pv(const double* S, const double* V, double* Out, int ldo,
                                    int B, int N, int M, int topk, cudaStream_t st);
+// both sides of a layer in ONE launch (S[s]: dense logits (B,4,N[s],M[s]) of side s, V[s]: its head-major source values)
+cudaError_t launch_topk_softmax_pv_sides(const double* const* S, const double* const* V, double* const* Out, int ldo,
+                                         int B, const int* N, const int* M, int nsides, int topk, cudaStream_t st);
 
 // Exact top-k threshold per logits row (B,4,N,M): kept set = { z > thr or (z == thr and column <= jlast) }, plus the row maximum
 cudaError_t launch_topk_threshold(const double* S, double* thr, int* jlast, double* rmax, int B, int N, int M, int topk,

@@ -133,6 +133,8 @@ slice_rows_tiled_kernel(const double* __restrict__ A0, int ld0, int K0, const do
     const int ntiles = (Rpad / SL_ROWS) * nchunks;
     if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
     __syncthreads();
+    pdl_wait();
+    pdl_trigger();
     // tile t = (row tile t / nchunks, k chunk t % nchunks); warp 0 issues the row copies of a tile (one per lane)
     auto issue = [&](int t, int stage) {
         const long long row0 = (long long)(t / nchunks) * SL_ROWS;
@@ -307,6 +309,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = tmem_base_s;
+    pdl_wait();                                                      // up to here only weights (scales, bias) were read
+    pdl_trigger();
     constexpr int TM_SET = S * OZ_BN;                                // TMEM columns of one accumulator set
     Tracer tr;
     if (DBG) tr.init(p.trace, warp == OZ_EPI_WARPS + 1 ? 0 : (warp == OZ_EPI_WARPS ? 1 : (warp == 0 ? 2 : 3)), blockIdx.x == 0 && blockIdx.y == 0 && (tid & 31) == 0 && (warp >= OZ_EPI_WARPS || (DBG > 1 && (warp == 0 || warp == 4))));
@@ -717,8 +721,7 @@ static cudaError_t slice_rows_t(const double* A0, int ld0, int K0, const double*
         static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
         const long long ntiles = (Rpad / SL_ROWS) * (K / OZ_KC);
         const unsigned grid = (unsigned)(ntiles < 3ll * sms ? ntiles : 3ll * sms);
-        slice_rows_tiled_kernel<S><<<grid, SL_THREADS, smem, st>>>(A0, ld0, K0, A1, ld1, R, K / OZ_KC, Xs, rowscale, chunk_stride);
-        return cudaGetLastError();
+        return launch_pdl(slice_rows_tiled_kernel<S>, dim3(grid), dim3(SL_THREADS), smem, st, A0, ld0, K0, A1, ld1, R, K / OZ_KC, Xs, rowscale, chunk_stride);
     }
     const long long threads = Rpad * (K / 16);
     slice_rows_kernel<S><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale, chunk_stride);
@@ -748,8 +751,7 @@ static cudaError_t ozaki_gemm_tg(const OzParams& p, dim3 grid, cudaStream_t st) 
     const size_t smem = (size_t)S * (OZ_XTILE + OZ_WSTAGES * OZ_WTILE);
     cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel<S, EPI, DBG, FULL, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    ozaki_gemm_kernel<S, EPI, DBG, FULL, GROUPS><<<grid, OZ_THREADS, smem, st>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(ozaki_gemm_kernel<S, EPI, DBG, FULL, GROUPS>, grid, dim3(OZ_THREADS), smem, st, p);
 }
 template <int S, int EPI, int DBG, bool FULL>
 static cudaError_t ozaki_gemm_tf(const OzParams& p, dim3 grid, cudaStream_t st) {

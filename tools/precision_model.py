@@ -38,10 +38,14 @@ def frexp_exp(mx):
     return torch.where(mx > 0, e, torch.zeros_like(e)).to(torch.float64)
 
 
+GEMM_CHUNK = [128]          # columns that share one digit scale per row (128 = the kernels' k chunk; 0 = the whole row)
+
+
 def gemm_planes(x, S):
     """x [R, K] (K multiple of 128) -> (planes [S][R, K], trunc [S+1][R, K]) in value units; trunc[j] = first j planes."""
     R, K = x.shape
-    xc = x.reshape(R, K // 128, 128)
+    ch = GEMM_CHUNK[0] or K
+    xc = x.reshape(R, K // ch, ch)
     e = frexp_exp(xc.abs().amax(dim=2, keepdim=True))
     t = xc * torch.exp2(6.0 - e)
     unit = torch.exp2(e - 6.0)
@@ -272,9 +276,11 @@ def main():
     ap.add_argument('--configs', nargs='+', default=['7/7/6', '5/5/4', '4/4/3'])
     ap.add_argument('--pairs', type=int, default=0, help='only the first n pairs of each case (0 = all)')
     ap.add_argument('--threads', type=int, default=0)
+    ap.add_argument('--gemm-chunk', type=int, default=128, help='columns sharing one digit scale per row (0 = whole row)')
     args = ap.parse_args()
     if args.threads:
         torch.set_num_threads(args.threads)
+    GEMM_CHUNK[0] = args.gemm_chunk
     if args.golden:
         run_golden(args.golden, args.configs)
         return

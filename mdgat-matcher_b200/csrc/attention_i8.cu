@@ -438,6 +438,7 @@ struct AttnI8Params {
     AttnI8Side kv[2];            // digit planes of its SOURCE side
     double* Out[2];              // messages (rows x ldo) or, LOGITS, dense (B,4,N,M) logits
     AttnI8TopK tk;               // TOPK: per-row threshold / last tied column / maximum (launch_topk_threshold)
+    AttnI8MsgPlanes mp;          // Xs != nullptr: messages as GEMM digit planes instead of float64 rows
     int B, ldo;
 };
 
@@ -493,6 +494,7 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
     __shared__ __align__(8) uint64_t q_full, kv_full[AI_STAGES], kv_empty[AI_STAGES], s1_full[4], s1_empty[4], p1_done,
         s_full[NSBUF], s_empty[NSBUF], p_full[2], p_empty[2], o_full;
     __shared__ uint32_t tmem_base_s;
+    __shared__ int s_vexp[4];                                 // message planes: largest exponent word of the head's value scales
 
     if (tid == 0) {
         mbar_init(&q_full, 1);
@@ -624,6 +626,12 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
         const int row = qt * AI_BM + rloc;
         const bool row_ok = row < N;
         const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
+        if (!LOGITS && p.mp.Xs != nullptr && warp < 4) {
+            // vscale = 2^(e_c - 13) of the 4 x 32 value channels of this pair: the largest exponent bounds every message entry
+            const int hi = __double2hiint(Kd.vscale[(size_t)b * (HEADS * 32) + tid]);
+            const int mx = __reduce_max_sync(0xffffffffu, hi);
+            if (lane == 0) s_vexp[warp] = mx;                      // read after the epilogue barrier at the end
+        }
         mbar_wait(&q_full, 0);                                     // key scales are in shared memory
         const double r_i = Qd.qscale[(size_t)bh * Npad + row];     // 2^(e_i - 12) / sqrt(32); 0 for padded rows
         // row factor of the recombined integer: even S: ai_recombine() returns 256 x the sum; CVT 4: 2^(16 (S-1)/2) x
@@ -828,7 +836,40 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
 #pragma unroll
                 for (int j = 0; j < CW; ++j) outv[j] = fma(outv[j], 0.00390625, int_to_f64<0>(o[j]));
             }
-            if (row_ok) {
+            if (p.mp.Xs != nullptr) {
+                // The message row as the digit planes of the next GEMM's A operand (slice_rows_kernel's format: x = 2^e sum_s
+                // d_s 2^(1-7s), |d_s| <= 64, d_s = q_s - 128 q_(s-1), q_s = rint(x 2^(6-e) 128^s) read out of the mantissa).
+                // e = exponent bound of the pair's source values instead of the row maximum of the message: |message| <=
+                // max |v| because the probabilities are a convex combination -- no second pass over the 128 columns (4 CTAs).
+                const int e = (max(max(s_vexp[0], s_vexp[1]), max(s_vexp[2], s_vexp[3])) >> 20) - 1023 + 13;
+                const long long r = p.mp.row0[side] + (long long)b * N + row;
+                const int kcol = h * HDIM + c0;
+                int8_t* dst = p.mp.Xs + ((size_t)(r >> 7) * p.mp.S) * (128 * 128) +
+                              (((int)(r & 127) >> 3) * 1024 + (kcol >> 4) * 128 + ((int)(r & 7)) * 16 + (kcol & 15));
+                double x[CW];
+                int qp[CW];
+#pragma unroll
+                for (int j = 0; j < CW; ++j) { x[j] = outv[j] * vs[j] * inv; qp[j] = 0; }
+#pragma unroll 1
+                for (int s = 0; s < p.mp.S; ++s) {
+                    const double cs = pow2i(6 - e + 7 * s);
+                    uint32_t w[CW / 4];
+#pragma unroll
+                    for (int g = 0; g < CW / 4; ++g) w[g] = 0u;
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) {
+                        const int q = __double2loint(fma(x[j], cs, 6755399441055744.0));
+                        const int d = q - (qp[j] << 7);
+                        qp[j] = q;
+                        w[j >> 2] |= ((uint32_t)d & 0xffu) << (8 * (j & 3));
+                    }
+                    if (row_ok) {
+                        if constexpr (CW == 16) *reinterpret_cast<uint4*>(dst + (size_t)s * (128 * 128)) = make_uint4(w[0], w[1], w[2], w[3]);
+                        else *reinterpret_cast<uint2*>(dst + (size_t)s * (128 * 128)) = make_uint2(w[0], w[1]);
+                    }
+                }
+                if (row_ok && h == 0 && cgi == 0) p.mp.rowscale[r] = pow2i(e - 12);
+            } else if (row_ok) {
                 double* dst = p.Out[side] + ((long long)b * N + row) * p.ldo + h * HDIM + c0;
 #pragma unroll
                 for (int j = 0; j < CW; j += 2)
@@ -931,8 +972,14 @@ static cudaError_t attn_i8_go(const AttnI8Params& p, dim3 grid, size_t smem, int
 // q[s] / kv[s]: digit planes of the query side and of the source side of grid side s; Out[s]: messages (rows x ldo),
 // or in AI_MODE_LOGITS the dense scaled logits (B,4,N,M) of that side. SP: byte planes of P (S = 4: 3 or 4, 5: 4, 6: 5, 7: 6).
 cudaError_t launch_attn_i8(const AttnI8Side* q, const AttnI8Side* kv, double* const* Out, int B, int nsides, int ldo,
-                           int mode, const AttnI8TopK* tk, int SP, cudaStream_t st) {
+                           int mode, const AttnI8TopK* tk, int SP, cudaStream_t st, const AttnI8MsgPlanes* mp) {
     AttnI8Params p;
+    if (mp != nullptr && mode != AI_MODE_LOGITS) {
+        if (mp->Xs == nullptr || mp->rowscale == nullptr || mp->S < 1 || mp->S > 7) return cudaErrorInvalidValue;
+        p.mp = *mp;
+    } else {
+        p.mp = AttnI8MsgPlanes{nullptr, nullptr, 0, {0, 0}};
+    }
     if (mode == AI_MODE_TOPK) {
         if (tk == nullptr) return cudaErrorInvalidValue;
         p.tk = *tk;

@@ -180,9 +180,13 @@ cudaError_t gemm_nt(const double* X, int ldx, long long sX, const double* W, int
 struct TopKScratch { double* thr; double* rmax; int* jlast; };
 cudaError_t attention_layer(const AttnSides& ps, int B, int nsides, int ldo, int topk, double* S, cudaStream_t st,
                             const AttnI8Side* qd = nullptr, const AttnI8Side* kvd = nullptr, int SP = 0,
-                            const TopKScratch* tks = nullptr) {
+                            const TopKScratch* tks = nullptr, const AttnI8MsgPlanes* mp = nullptr, bool* planes_written = nullptr) {
+    if (planes_written) *planes_written = false;
     if (qd) {
-        if (topk <= 0) return launch_attn_i8(qd, kvd, ps.Out, B, nsides, ldo, AI_MODE_FULL, nullptr, SP, st);
+        if (topk <= 0) {
+            if (planes_written) *planes_written = mp != nullptr;
+            return launch_attn_i8(qd, kvd, ps.Out, B, nsides, ldo, AI_MODE_FULL, nullptr, SP, st, mp);
+        }
         // dynamic_attention() (mdgat.py:196-210) on the tensor cores: dense logits (digit-plane Q K^T, stored), the exact
         // top-k threshold of every row, then the same kernel again as a masked softmax . V that recomputes the logits bit
         // for bit and zeroes the probabilities outside the kept set
@@ -201,7 +205,8 @@ cudaError_t attention_layer(const AttnSides& ps, int B, int nsides, int ldo, int
             if (e != cudaSuccess) return e;
             off += (size_t)B * HEADS * ps.N[s];
         }
-        return launch_attn_i8(qd, kvd, ps.Out, B, nsides, ldo, AI_MODE_TOPK, &tk, SP, st);
+        if (planes_written) *planes_written = mp != nullptr;
+        return launch_attn_i8(qd, kvd, ps.Out, B, nsides, ldo, AI_MODE_TOPK, &tk, SP, st, mp);
     }
     if (topk <= 0) return launch_attention_full(ps, B, nsides, ldo, st);
     // dense logits q.k / sqrt(32) for every (b, h) (mdgat.py:201), then exact-k selection per row
@@ -331,6 +336,7 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
             MDGAT_CUDA_OK(launch_gemm(p, EPI_QKV, 1, st));
         }
         prof_mark(ai8 ? ST_SLICE : (k > 0 ? ST_ATTN_TOPK : ST_ATTN_FULL), st);
+        bool msg_planes = false;                          // the attention kernel wrote the message digit planes itself
         // messages: side 0 reads side (cross ? 1 : 0), side 1 the other way round (mdgat.py:263-266)
         AttnSides ps;
         ps.Q[0] = Q0; ps.K[0] = cross ? K1 : K0; ps.V[0] = cross ? V1 : V0; ps.Out[0] = w.Msg; ps.N[0] = N; ps.M[0] = cross ? M : N;
@@ -348,7 +354,11 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
             const AttnI8Side qd[2] = {w.ai[0], w.ai[1]};
             const AttnI8Side kvd[2] = {cross ? w.ai[1] : w.ai[0], cross ? w.ai[0] : w.ai[1]};
             const TopKScratch tks = {w.tkthr, w.tkmax, w.tkjl};
-            MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st, qd, kvd, ASP, &tks));
+            // with the tcgen05 GEMM engine the messages leave the attention kernel as the digit planes of the MLP's second
+            // k chunk (MDGAT_MSG_PLANES=0: float64 rows + the stand-alone slicer, as for the DMMA attention engine)
+            static const bool msg_planes_env = [] { const char* e = getenv("MDGAT_MSG_PLANES"); return !(e && e[0] == '0'); }();
+            const AttnI8MsgPlanes mpl = {w.xsM, w.rsM, S8, {0, (long long)R0}};
+            MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st, qd, kvd, ASP, &tks, (i8 && msg_planes_env) ? &mpl : nullptr, &msg_planes));
         } else {
             MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st));
         }
@@ -359,7 +369,7 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
             OzGemmArgs a;
             memset(&a, 0, sizeof(a));
             // k chunk 0 = x (its slice planes are the ones the q/k/v projection used), k chunk 1 = message
-            MDGAT_CUDA_OK(launch_slice_rows(w.Msg, LDX, DMODEL, nullptr, 0, 0, R, S8, w.xsM, w.rsM, st));
+            if (!msg_planes) MDGAT_CUDA_OK(launch_slice_rows(w.Msg, LDX, DMODEL, nullptr, 0, 0, R, S8, w.xsM, w.rsM, st));
             prof_mark(ST_GEMM, st);
             a.Xs[0] = w.xsX; a.rowscale[0] = w.rsX; a.Xs[1] = w.xsM; a.rowscale[1] = w.rsM; a.Ws = reinterpret_cast<const int8_t*>(Li8 + slice_tile * 12); a.colscale = cs8 + 384;
             a.bias = Wt + lo.b1; a.Y = w.Hd; a.ldy = LDHID; a.R = R; a.Nout = 2 * DMODEL; a.K = 2 * DMODEL; a.relu = 1; a.epi = EPI_PLAIN;

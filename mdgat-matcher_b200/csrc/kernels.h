@@ -119,8 +119,13 @@ cudaError_t launch_attn_i8_slice_sides(const double* const* Qh, const double* co
 // AI_MODE_TOPK softmax over the kept set described by tk (from launch_topk_threshold on the logits of AI_MODE_LOGITS)
 enum { AI_MODE_FULL = 0, AI_MODE_LOGITS = 1, AI_MODE_TOPK = 2 };
 struct AttnI8TopK { const double* thr[2]; const int* jlast[2]; const double* rmax[2]; };   // per side, rows in (B,4,N) order
+// mp != nullptr (AI_MODE_FULL / AI_MODE_TOPK): the messages leave the kernel as the int8 digit planes the next GEMM
+// reads (ozaki_gemm.cu operand layout, S planes, rows row0[s] + b * N[s] + i) instead of float64 rows; the digit scale
+// of a row is the per-pair bound 2^e >= max |v| of its source values (a message is a convex combination of them),
+// rowscale = 2^(e - 12). Out is not written then.
+struct AttnI8MsgPlanes { int8_t* Xs; double* rowscale; int S; long long row0[2]; };
 cudaError_t launch_attn_i8(const AttnI8Side* q, const AttnI8Side* kv, double* const* Out, int B, int nsides, int ldo,
-                           int mode, const AttnI8TopK* tk, int SP, cudaStream_t st);
+                           int mode, const AttnI8TopK* tk, int SP, cudaStream_t st, const AttnI8MsgPlanes* mp = nullptr);
 
 // Batched Kabsch registration + match statistics (one CTA per pair)
 cudaError_t launch_register_pairs(const void* kpts0, const void* kpts1, int kp_dtype, const int64_t* matches0,

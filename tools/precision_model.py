@@ -39,14 +39,18 @@ def frexp_exp(mx):
 
 
 GEMM_CHUNK = [128]          # columns that share one digit scale per row (128 = the kernels' k chunk; 0 = the whole row)
+MSG_VBOUND = [False]        # message planes of the full-attention layers cut with the per-pair bound max |v| instead of the row maximum
 
 
-def gemm_planes(x, S):
-    """x [R, K] (K multiple of 128) -> (planes [S][R, K], trunc [S+1][R, K]) in value units; trunc[j] = first j planes."""
+def gemm_planes(x, S, e_min=None):
+    """x [R, K] (K multiple of 128) -> (planes [S][R, K], trunc [S+1][R, K]) in value units; trunc[j] = first j planes.
+    e_min [R, chunks, 1]: lower limit of the chunk exponents (-inf where the row maximum decides)."""
     R, K = x.shape
     ch = GEMM_CHUNK[0] or K
     xc = x.reshape(R, K // ch, ch)
     e = frexp_exp(xc.abs().amax(dim=2, keepdim=True))
+    if e_min is not None:
+        e = torch.maximum(e, e_min)
     t = xc * torch.exp2(6.0 - e)
     unit = torch.exp2(e - 6.0)
     trunc = [torch.zeros_like(x)]
@@ -57,11 +61,11 @@ def gemm_planes(x, S):
     return planes, trunc
 
 
-def gemm_emul(x, w, S):
+def gemm_emul(x, w, S, e_min=None):
     """x [R, K] @ w[Nout, K]^T with S digit planes per operand, pairs s + t <= S - 1 (0-based); S == 0: exact float64."""
     if S == 0:
         return x @ w.t()
-    px, _ = gemm_planes(x, S)
+    px, _ = gemm_planes(x, S, e_min)
     _, tw = gemm_planes(w, S)
     y = px[0] @ tw[S].t()
     for s in range(1, S):
@@ -178,6 +182,7 @@ def forward_model(sd, data, L, T, k_list, prec):
         q1, k1, v1 = (heads(qkv[R0:, i * 128:(i + 1) * 128], M) for i in range(3))
         cross = l % 2 == 1
         msgs = []
+        ebs = []
         for (q, k, v) in ((q0, k1 if cross else k0, v1 if cross else v0), (q1, k0 if cross else k1, v0 if cross else v1)):
             kk = sched[l]
             if kk > 0:
@@ -192,13 +197,18 @@ def forward_model(sd, data, L, T, k_list, prec):
                 o = attn_emul(q, k, v, aS, aSP)
             n = o.shape[2]
             msgs.append(o.permute(0, 2, 3, 1).reshape(B * n, 128))        # back to c = d*4 + h
+            eb = frexp_exp(v.abs().amax(dim=(1, 2, 3)))                   # per pair: |message| <= max |v| < 2^eb
+            if not (MSG_VBOUND[0] and kk == 0):
+                eb = torch.full_like(eb, -1e9)
+            ebs.append(eb[:, None].expand(B, n).reshape(B * n))
         msg = torch.cat(msgs, 0)
+        e_min = torch.stack([torch.full_like(torch.cat(ebs, 0), -1e9), torch.cat(ebs, 0)], 1)[:, :, None]
         wm, bm = conv(sd, p + 'attn.merge')
         w1, b1 = conv(sd, p + 'mlp.0')
         w1, b1 = fold_bn(w1, b1, sd, p + 'mlp.1')
         w1f = torch.cat([w1[:, :128], w1[:, 128:] @ wm], 1)
         b1f = b1 + w1[:, 128:] @ bm
-        h = torch.relu(gemm_emul(torch.cat([X, msg], 1), w1f, gS) + b1f)
+        h = torch.relu(gemm_emul(torch.cat([X, msg], 1), w1f, gS, e_min if GEMM_CHUNK[0] == 128 else None) + b1f)
         w2, b2 = conv(sd, p + 'mlp.3')
         X = X + gemm_emul(h, w2, gS) + b2
     wf, bf = conv(sd, 'final_proj')
@@ -276,11 +286,13 @@ def main():
     ap.add_argument('--configs', nargs='+', default=['7/7/6', '5/5/4', '4/4/3'])
     ap.add_argument('--pairs', type=int, default=0, help='only the first n pairs of each case (0 = all)')
     ap.add_argument('--threads', type=int, default=0)
+    ap.add_argument('--msg-vbound', action='store_true', help='message planes of full-attention layers scaled by the per-pair bound max |v|')
     ap.add_argument('--gemm-chunk', type=int, default=128, help='columns sharing one digit scale per row (0 = whole row)')
     args = ap.parse_args()
     if args.threads:
         torch.set_num_threads(args.threads)
     GEMM_CHUNK[0] = args.gemm_chunk
+    MSG_VBOUND[0] = args.msg_vbound
     if args.golden:
         run_golden(args.golden, args.configs)
         return

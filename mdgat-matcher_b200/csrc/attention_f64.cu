@@ -267,10 +267,14 @@ constexpr int TK_WARPS = 8;
 constexpr int TK_LMAX = 64;                  // capacity of the boundary-bin list
 constexpr double TK_MAGIC = 26388279066624.0;  // 1.5 * 2^44: the low mantissa word of MAGIC + t is rint(256 t) for 0 <= t < 2^24
 
-struct __align__(16) KeptEntry { double p; int col; int pad; };
+// A kept entry: logit (later probability) and the BYTE offset of its value row inside the head's value matrix
+// (column * LDH_V * 8). 16-byte slots, but the P.V loop reads the two fields with an 8- and a 4-byte broadcast load
+// (one shared-memory wavefront each; a 16-byte load of the struct costs four).
+struct __align__(16) KeptEntry { double p; int voff; int pad; };
+constexpr int TK_VROW = LDH_V * 8;           // bytes of a value row
 
 // The slow, always-correct selection (cold path): reloads the row, finds the k-th largest order key bit by bit, keeps
-// everything above it and the lowest-index ties. Writes exactly min(k, M) entries to kept[] in column order.
+// everything above it and the lowest-index ties. Writes exactly min(k, M) entries in column order.
 template <int VPT>
 __device__ __noinline__ void topk_select_exact(const double* __restrict__ srow, int M, int topk, int lane, KeptEntry* kept) {
     unsigned long long key[VPT];                 // 0 for padding: below every real key (real keys have a bit set)
@@ -330,7 +334,7 @@ __device__ __noinline__ void topk_select_exact(const double* __restrict__ srow, 
         const unsigned tm = __ballot_sync(0xffffffffu, take);
         if (take) {
             const unsigned long long bits = (kv >> 63) ? (kv ^ 0x8000000000000000ull) : ~kv;
-            KeptEntry e; e.p = __longlong_as_double((long long)bits); e.col = lane + 32 * v; e.pad = 0;
+            KeptEntry e; e.p = __longlong_as_double((long long)bits); e.voff = (lane + 32 * v) * TK_VROW; e.pad = 0;
             kept[base + __popc(tm & ((1u << lane) - 1u))] = e;
         }
         base += __popc(tm);
@@ -338,15 +342,16 @@ __device__ __noinline__ void topk_select_exact(const double* __restrict__ srow, 
     __syncwarp();
 }
 
-// The fast selection described above. s[]: the row (padding = -inf). Returns false when the row must take the exact
-// path (nothing useful has been written then). hist aliases the start of kept[] (NB counters), alist is the warp's
+// The fast selection described above. s[]: the row (padding = -inf; FULLROW: M == 32 VPT, no padding). Returns false
+// when the row must take the exact path (nothing useful has been written then). The histogram aliases the start of
+// kept[] (NB counters; kept is aligned to 4 NB bytes so that a counter address is base | offset), alist is the warp's
 // boundary-bin list. hi_b (>= every logit, within 2^-20 relative of the maximum) is the softmax shift.
-template <int VPT>
-DEVINL bool topk_select_fast(const double (&s)[VPT], int M, int topk, int lane, KeptEntry* kept, KeptEntry* alist,
-                             double& hi_b) {
+template <int VPT, bool FULLROW>
+DEVINL bool topk_select_fast(const double (&s)[VPT], int M, int topk, int lane, KeptEntry* kept, KeptEntry* alist, double& hi_b) {
     constexpr int NB = 16 * VPT, BPL = NB / 32;
-    constexpr bool KEEP_U = VPT <= 16;           // the 32-bit bin keys stay in registers when there is room
+    constexpr bool KEEP_U = false;               // the 32-bit bin keys are recomputed (one fma) rather than kept: registers
     unsigned* hist = reinterpret_cast<unsigned*>(kept);
+    const uint32_t kept_s = (uint32_t)__cvta_generic_to_shared(kept), alist_s = (uint32_t)__cvta_generic_to_shared(alist);
 #pragma unroll
     for (int q = 0; q < BPL / 4; ++q) reinterpret_cast<uint4*>(hist)[lane + 32 * q] = make_uint4(0u, 0u, 0u, 0u);
     int kmax = (int)0x80000000, kmin = 0x7fffffff;
@@ -354,7 +359,7 @@ DEVINL bool topk_select_fast(const double (&s)[VPT], int M, int topk, int lane, 
     for (int v = 0; v < VPT; ++v) {
         const int key = order_key32(__double2hiint(s[v]));
         kmax = max(kmax, key);
-        kmin = min(kmin, (lane + 32 * v) < M ? key : 0x7fffffff);
+        kmin = min(kmin, (FULLROW || (lane + 32 * v) < M) ? key : 0x7fffffff);
     }
     kmax = __reduce_max_sync(0xffffffffu, kmax);
     kmin = __reduce_min_sync(0xffffffffu, kmin);
@@ -362,9 +367,11 @@ DEVINL bool topk_select_fast(const double (&s)[VPT], int M, int topk, int lane, 
     hi_b = __hiloint2double(hmax, hmax < 0 ? 0 : -1);
     const double lo_b = __hiloint2double(hmin, hmin < 0 ? -1 : 0);
     const double range = hi_b - lo_b;
-    const double scale = (double)(NB - 1) / range;
-    // |lo_b| scale < 2^40 keeps MAGIC + 1/4 - lo_b scale on the 2^-8 grid of MAGIC (NaN / Inf bounds fail the test too)
-    if (!(range > 0.0 && fmax(fabs(lo_b), fabs(hi_b)) * scale < 1.0e12) || topk >= M) return false;
+    // a little less than (NB - 1) / range, in float32 with the reciprocal rounded down (any smaller positive scale keeps
+    // the bins inside [0, NB)): a handful of instructions instead of a float64 division
+    const double scale = (double)(__frcp_rd(__double2float_ru(range)) * ((float)(NB - 1) * 0.99999f));
+    // |lo_b| scale < 2^40 keeps MAGIC + 1/4 - lo_b scale on the 2^-8 grid of MAGIC (NaN / Inf bounds fail the tests too)
+    if (!(range > 1.0e-30 && range < 1.0e30 && fmax(fabs(lo_b), fabs(hi_b)) * scale < 1.0e12) || topk >= M) return false;
     const double off = (TK_MAGIC + 0.25) - lo_b * scale;
     auto ukey = [&](int v) -> unsigned { return (unsigned)__double2loint(fma(s[v], scale, off)); };   // -inf -> 0
     unsigned u[KEEP_U ? VPT : 1];
@@ -373,7 +380,9 @@ DEVINL bool topk_select_fast(const double (&s)[VPT], int M, int topk, int lane, 
     for (int v = 0; v < VPT; ++v) {
         const unsigned uv = ukey(v);
         if (KEEP_U) u[v] = uv;
-        atomicAdd(hist + ((uv >> 8) & (unsigned)(NB - 1)), 1u);
+        // counter address = base | 4 * bin (the base is aligned to the size of the histogram)
+        const uint32_t addr = kept_s | ((uv >> 6) & (unsigned)(4 * NB - 4));
+        asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(addr) : "memory");
     }
     __syncwarp();
     // suffix scan from the top bin: lane l owns bins [BPL l, BPL (l + 1))
@@ -383,9 +392,11 @@ DEVINL bool topk_select_fast(const double (&s)[VPT], int M, int topk, int lane, 
         const uint4 t = reinterpret_cast<const uint4*>(hist)[lane * (BPL / 4) + q];
         h[4 * q] = t.x; h[4 * q + 1] = t.y; h[4 * q + 2] = t.z; h[4 * q + 3] = t.w;
     }
-    int tot = 0;
+    int sfx[BPL + 1];                                        // sfx[b] = entries of this lane's bins b .. BPL-1
+    sfx[BPL] = 0;
 #pragma unroll
-    for (int b = 0; b < BPL; ++b) tot += (int)h[b];
+    for (int b = BPL - 1; b >= 0; --b) sfx[b] = sfx[b + 1] + (int)h[b];
+    const int tot = sfx[0];
     int suf = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -394,40 +405,31 @@ DEVINL bool topk_select_fast(const double (&s)[VPT], int M, int topk, int lane, 
     }
     const int above_lane = suf - tot;
     const bool mine = above_lane < topk && topk <= suf;      // exactly one lane (1 <= k <= M <= total count)
-    int bstar = 0, above = 0;
-    if (mine) {
-        int c = above_lane;
-        bool done = false;
+    // inside the owning lane: b* = number of bins b >= 1 whose suffix (from b up) still reaches k
+    // (walking down from the top bin: the last suffix that does not reach k is the count above b*)
+    int nb = 0, abv = above_lane;
 #pragma unroll
-        for (int b = BPL - 1; b >= 0; --b) {
-            if (!done) {
-                if (c + (int)h[b] >= topk) { bstar = lane * BPL + b; above = c; done = true; }
-                else c += (int)h[b];
-            }
-        }
+    for (int b = BPL - 1; b >= 1; --b) {
+        const int c = above_lane + sfx[b];
+        nb += (c >= topk) ? 1 : 0;
+        abv = (c >= topk) ? abv : c;
     }
     const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
-    bstar = __shfl_sync(0xffffffffu, bstar, src);
-    above = __shfl_sync(0xffffffffu, above, src);
+    const int bstar = __shfl_sync(0xffffffffu, lane * BPL + nb, src);
+    const int above = __shfl_sync(0xffffffffu, abv, src);
     // padding has u = 0 and every real entry u >= 62 (t >= 1/4 - rounding), so a lower limit of at least 1 keeps the
     // padding out of the boundary list without a column test
     const unsigned t_hi = (unsigned)(bstar + 1) << 8, t_lo = max((unsigned)bstar << 8, 1u);
-    // entries above the boundary bin: per-lane count, exclusive warp scan, predicated stores (lane-major order). The
-    // histogram is dead (every lane passed the shuffles above after reading its bins), kept[] may be overwritten.
-    // Entries INSIDE the boundary bin are rare (L of them per row): one ballot per v finds them, and only a non-empty
-    // ballot (warp-uniform branch) does any work; list positions follow (v, lane), so the list is deterministic.
-    int cnt = 0, L = 0;
+    // One counting pass (entries above / inside the boundary bin per lane, packed into one word), one warp scan, one
+    // write pass: the entries above go to kept[] in (lane, v) order, the few inside to the boundary list. Both passes
+    // are straight predicated code -- written as PTX so that they stay free of per-element branches. The histogram is
+    // dead (every lane passed the shuffles above after reading its bins): kept[] may be overwritten.
+    int cnt = 0;                                             // low half: above, high half: inside
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
         const unsigned uv = KEEP_U ? u[v] : ukey(v);
-        if (uv >= t_hi) ++cnt;
-        const bool amb = uv < t_hi && uv >= t_lo;
-        const unsigned am = __ballot_sync(0xffffffffu, amb);
-        if (am != 0u) {
-            const int q = L + __popc(am & ((1u << lane) - 1u));
-            if (amb && q < TK_LMAX) { KeptEntry e; e.p = s[v]; e.col = lane + 32 * v; e.pad = 0; alist[q] = e; }
-            L += __popc(am);
-        }
+        asm("{\n.reg .pred p, q;\nsetp.ge.u32 p, %1, %2;\nsetp.ge.and.u32 q, %1, %3, !p;\n@p add.s32 %0, %0, 1;\n@q add.s32 %0, %0, 65536;\n}"
+            : "+r"(cnt) : "r"(uv), "r"(t_hi), "r"(t_lo));
     }
     int inc = cnt;
 #pragma unroll
@@ -435,17 +437,21 @@ DEVINL bool topk_select_fast(const double (&s)[VPT], int M, int topk, int lane, 
         const int t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
     }
-    KeptEntry* dst = kept + (inc - cnt);
+    const int L = __shfl_sync(0xffffffffu, inc, 31) >> 16;
+    if (L > TK_LMAX) return false;
+    uint32_t kp = kept_s + (uint32_t)((inc - cnt) & 0xffff) * 16u, ap = alist_s + (uint32_t)((inc - cnt) >> 16) * 16u;
+    const int voff0 = lane * TK_VROW;
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
         const unsigned uv = KEEP_U ? u[v] : ukey(v);
-        if (uv >= t_hi) {
-            KeptEntry e; e.p = s[v]; e.col = lane + 32 * v; e.pad = 0;
-            *dst++ = e;
-        }
+        // one 16-byte store per kept entry: {logit, row offset}
+        asm volatile("{\n.reg .pred p, q;\n.reg .b64 t, x;\nsetp.ge.u32 p, %2, %3;\nsetp.ge.and.u32 q, %2, %4, !p;\n"
+                     "cvt.u64.u32 t, %6;\nmov.b64 x, %5;\n"
+                     "@p st.shared.v2.b64 [%0], {x, t};\n@p add.u32 %0, %0, 16;\n"
+                     "@q st.shared.v2.b64 [%1], {x, t};\n@q add.u32 %1, %1, 16;\n}"
+                     : "+r"(kp), "+r"(ap) : "r"(uv), "r"(t_hi), "r"(t_lo), "d"(s[v]), "r"(voff0 + v * (32 * TK_VROW)) : "memory");
     }
     __syncwarp();
-    if (L > TK_LMAX) return false;
     // exact rank inside the boundary bin: (value descending, column ascending) is a strict total order, so the ranks
     // are a permutation of 0 .. L-1 and the entries of rank < need land on distinct slots
     const int need = topk - above;
@@ -454,7 +460,7 @@ DEVINL bool topk_select_fast(const double (&s)[VPT], int M, int topk, int lane, 
         int rank = 0;
         for (int q = 0; q < L; ++q) {
             const KeptEntry eq = alist[q];
-            rank += (eq.p > et.p || (eq.p == et.p && eq.col < et.col)) ? 1 : 0;
+            rank += (eq.p > et.p || (eq.p == et.p && eq.voff < et.voff)) ? 1 : 0;
         }
         if (rank < need) kept[above + rank] = et;
     }
@@ -462,9 +468,9 @@ DEVINL bool topk_select_fast(const double (&s)[VPT], int M, int topk, int lane, 
     return true;
 }
 
-// VPT = values per lane (M <= 32*VPT). Dynamic shared memory: per warp max(topk, 4 VPT) KeptEntry (kept logit ->
-// probability, column; its first 64 VPT bytes double as the selection histogram), per warp TK_LMAX boundary-bin
-// entries, then the 64-entry exp table.
+// VPT = values per lane (M <= 32*VPT). Dynamic shared memory (aligned to 4 NB bytes): per warp max(topk, 4 VPT)
+// KeptEntry rounded up to a multiple of 4 VPT (its first 64 VPT bytes double as the selection histogram), per warp
+// TK_LMAX boundary-bin entries, then the 64-entry exp table.
 //
 // SMEM_V = false: one warp per row, 8 rows per CTA; the sparse P.V gathers its k value rows from global memory
 //                 (L2): 32 KB per query row, 2.1 GB per side at cfg2 -- the L2 read bandwidth is the bound.
@@ -473,15 +479,18 @@ DEVINL bool topk_select_fast(const double (&s)[VPT], int M, int topk, int lane, 
 //                 of the head (M x 34 doubles, 136 KB at M = 512) is brought in by ONE TMA bulk copy and every warp
 //                 walks query rows i = r0 + warp, r0 + warp + 24, .. gathering from shared memory. The logits row of
 //                 the next query is requested before the P.V of the current one.
-constexpr int TKS_WARPS = 24;
+constexpr int TKS_WARPS = 20;
 struct TopkSides { const double* S[2]; const double* V[2]; double* Out[2]; int N[2], M[2]; };
-DEVINL constexpr int tk_kept_entries(int topk, int vpt) { return topk > 4 * vpt ? topk : 4 * vpt; }
+DEVINL constexpr int tk_kept_entries(int topk, int vpt) { return (topk + 4 * vpt - 1) / (4 * vpt) * (4 * vpt); }
 
-template <int VPT, bool SMEM_V>
+template <int VPT, bool SMEM_V, bool FULLROW>
 __global__ void __launch_bounds__(SMEM_V ? 32 * TKS_WARPS : 32 * TK_WARPS, (SMEM_V || VPT != 16) ? 1 : 3)
 topk_softmax_pv_kernel(const __grid_constant__ TopkSides ps, int ldo, int topk, int nbh) {
-    extern __shared__ __align__(16) unsigned char tk_smem[];
+    extern __shared__ __align__(16) unsigned char tk_smem_raw[];
     constexpr int WARPS = SMEM_V ? TKS_WARPS : TK_WARPS;
+    constexpr uint32_t HB = 64 * VPT;                                      // bytes of the histogram = alignment of a kept list
+    const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(tk_smem_raw);
+    unsigned char* tk_smem = tk_smem_raw + (((raw_s + HB - 1) & ~(HB - 1)) - raw_s);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int side = blockIdx.z;
     const int N = ps.N[side], M = ps.M[side];
@@ -521,21 +530,38 @@ topk_softmax_pv_kernel(const __grid_constant__ TopkSides ps, int ldo, int topk, 
         if (bh >= nbh) return;                                             // past the last row of this side (whole warps)
     }
     const int b = (int)(bh / HEADS), h = (int)(bh - (long long)b * HEADS);
-    const double* Vbh = SMEM_V ? sV : V + bh * (long long)M * LDH_V;
     auto load_row = [&](int row, double (&dst)[VPT]) {
         const double* srow = S + (bh * N + row) * (long long)M;
 #pragma unroll
         for (int v = 0; v < VPT; ++v) {
             const int j = lane + 32 * v;
-            dst[v] = j < M ? srow[j] : -INFINITY;          // padding: bin 0, never kept
+            dst[v] = (FULLROW || j < M) ? srow[j] : -INFINITY;          // padding: bin 0, never kept
         }
     };
     double s[VPT];
     if (i < iend) load_row(i, s);
     bool v_ready = !SMEM_V;
+    // P.V lane roles: quarter-warp qw takes the kept entries t = qw (mod 4); lane cl of it the channels 2cl, 2cl+1,
+    // 16+2cl, 17+2cl -- its two 16-byte reads of a value row fall on two contiguous 128-byte runs per quarter-warp
+    const int qw = lane >> 3, cl = lane & 7;
+    const uint32_t kq_s = (uint32_t)__cvta_generic_to_shared(kept) + (uint32_t)qw * 16u;         // entry qw + 4 n at kq_s + 64 n
+    const uint32_t vq_s = (uint32_t)__cvta_generic_to_shared(sV) + (uint32_t)cl * 16u;
+    const char* vq_g = reinterpret_cast<const char*>(V + bh * (long long)M * LDH_V) + cl * 16;
+    // entry n of this quarter-warp: probability, then the four values of its row (shared-window loads, or L2 gathers)
+    auto entry = [&](int n, double& pr, double2& x0, double2& x1) {
+        int voff;
+        asm volatile("ld.shared.f64 %0, [%2];\n ld.shared.b32 %1, [%2+8];" : "=d"(pr), "=r"(voff) : "r"(kq_s + (uint32_t)n * 64u));
+        if (SMEM_V) {
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%4];\n ld.shared.v2.f64 {%2, %3}, [%4+128];"
+                         : "=d"(x0.x), "=d"(x0.y), "=d"(x1.x), "=d"(x1.y) : "r"(vq_s + (uint32_t)voff));
+        } else {
+            x0 = __ldg(reinterpret_cast<const double2*>(vq_g + voff));
+            x1 = __ldg(reinterpret_cast<const double2*>(vq_g + voff + 128));
+        }
+    };
   for (; i < iend; i += WARPS) {
     double mx;
-    if (!topk_select_fast<VPT>(s, M, topk, lane, kept, alist, mx))
+    if (!topk_select_fast<VPT, FULLROW>(s, M, topk, lane, kept, alist, mx))
         topk_select_exact<VPT>(S + (bh * N + i) * (long long)M, M, topk, lane, kept);
     const int nk = min(topk, M);
     // the logits of this warp's next row travel while the P.V below runs
@@ -550,32 +576,36 @@ topk_softmax_pv_kernel(const __grid_constant__ TopkSides ps, int ldo, int topk, 
     sum = warp_sum_d(sum);
     __syncwarp();
     if (!v_ready) { mbar_wait(&v_bar, 0); v_ready = true; }
-    // sparse P.V: only k of the M value rows are read. The two half-warps take the kept entries of even / odd position,
-    // a lane the channel pair (2 l, 2 l + 1): one 16-byte read of the entry and one of the value row per two FMAs
-    // (half the instructions of the lane-per-channel form); the halves are combined with two shuffles.
-    const int hw = lane >> 4;
-    const double* vl = Vbh + 2 * (lane & 15);
-    auto vload = [&](int col) -> double2 {
-        const double2* q = reinterpret_cast<const double2*>(vl + col * LDH_V);
-        return SMEM_V ? *q : __ldg(q);
-    };
-    double2 a0 = make_double2(0.0, 0.0), a1 = a0;
-    int t = hw;
-    for (; t + 2 < nk; t += 4) {
-        const KeptEntry e0 = kept[t], e1 = kept[t + 2];
-        const double2 v0 = vload(e0.col), v1 = vload(e1.col);
-        a0.x = fma(e0.p, v0.x, a0.x); a0.y = fma(e0.p, v0.y, a0.y);
-        a1.x = fma(e1.p, v1.x, a1.x); a1.y = fma(e1.p, v1.y, a1.y);
+    // sparse P.V: only k of the M value rows are read; per entry one 8-byte and one 4-byte broadcast read (probability,
+    // row offset) and 256 bytes of the value row; four entries per trip of the warp, two trips in flight
+    double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0;
+    const int nq = (nk - qw + 3) >> 2;                   // entries of this quarter-warp
+    int n = 0;
+#pragma unroll 2
+    for (; n + 1 < nq; n += 2) {
+        double p0, p1; double2 x00, x01, x10, x11;
+        entry(n, p0, x00, x01);
+        entry(n + 1, p1, x10, x11);
+        a0.x = fma(p0, x00.x, a0.x); a0.y = fma(p0, x00.y, a0.y); a1.x = fma(p0, x01.x, a1.x); a1.y = fma(p0, x01.y, a1.y);
+        b0.x = fma(p1, x10.x, b0.x); b0.y = fma(p1, x10.y, b0.y); b1.x = fma(p1, x11.x, b1.x); b1.y = fma(p1, x11.y, b1.y);
     }
-    if (t < nk) {
-        const KeptEntry e0 = kept[t];
-        const double2 v0 = vload(e0.col);
-        a0.x = fma(e0.p, v0.x, a0.x); a0.y = fma(e0.p, v0.y, a0.y);
+    if (n < nq) {
+        double p0; double2 x00, x01;
+        entry(n, p0, x00, x01);
+        a0.x = fma(p0, x00.x, a0.x); a0.y = fma(p0, x00.y, a0.y); a1.x = fma(p0, x01.x, a1.x); a1.y = fma(p0, x01.y, a1.y);
     }
-    a0.x += a1.x; a0.y += a1.y;
-    a0.x += shfl_xor_d(a0.x, 16); a0.y += shfl_xor_d(a0.y, 16);
-    if (hw == 0)
-        *reinterpret_cast<double2*>(Out + ((long long)b * N + i) * ldo + h * HDIM + 2 * lane) = make_double2(a0.x / sum, a0.y / sum);
+    a0.x += b0.x; a0.y += b0.y; a1.x += b1.x; a1.y += b1.y;
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1) {
+        a0.x += shfl_xor_d(a0.x, o); a0.y += shfl_xor_d(a0.y, o);
+        a1.x += shfl_xor_d(a1.x, o); a1.y += shfl_xor_d(a1.y, o);
+    }
+    if (qw == 0) {
+        const double inv = 1.0 / sum;
+        double* dst = Out + ((long long)b * N + i) * ldo + h * HDIM + 2 * cl;
+        *reinterpret_cast<double2*>(dst) = make_double2(a0.x * inv, a0.y * inv);
+        *reinterpret_cast<double2*>(dst + 16) = make_double2(a1.x * inv, a1.y * inv);
+    }
     __syncwarp();                                        // kept[] is rewritten by the next row
     if (!SMEM_V) break;
   }
@@ -696,20 +726,18 @@ cudaError_t launch_topk_threshold(const double* S, double* thr, int* jlast, doub
 
 static size_t topk_smem_bytes(int warps, int topk, int vpt, int m_smem_v) {
     return ((size_t)warps * (tk_kept_entries(topk, vpt) + TK_LMAX)) * sizeof(KeptEntry) + 64 * sizeof(double) +
-           (size_t)m_smem_v * LDH_V * sizeof(double);
+           (size_t)m_smem_v * LDH_V * sizeof(double) + 64 * vpt;            // + alignment slack of the kept lists
 }
 
-template <int VPT>
-static cudaError_t launch_topk_t(const TopkSides& ps, int nsides, int ldo, int B, int topk, cudaStream_t st) {
+template <int VPT, bool FULLROW>
+static cudaError_t launch_topk_tf(const TopkSides& ps, int nsides, int ldo, int B, int topk, int nmax, int nmin, int mmax, cudaStream_t st) {
     const int nbh = B * HEADS;
-    int nmax = 0, nmin = 1 << 30, mmax = 0;
-    for (int s = 0; s < nsides; ++s) { nmax = ps.N[s] > nmax ? ps.N[s] : nmax; nmin = ps.N[s] < nmin ? ps.N[s] : nmin; mmax = ps.M[s] > mmax ? ps.M[s] : mmax; }
-    // value matrix of a head resident in shared memory when it fits next to the kept lists (M = 512, k = 128: 209 KB)
+    // value matrix of a head resident in shared memory when it fits next to the kept lists (M = 512, k = 128: 197 KB)
     const size_t smem_v = topk_smem_bytes(TKS_WARPS, topk, VPT, mmax);
     if constexpr (VPT == 16) {
         static const bool smem_variant = [] { const char* e = getenv("MDGAT_TOPK_SMEMV"); return !(e && e[0] == '0'); }();
         if (smem_variant && smem_v <= 227 * 1024 && nmin >= TKS_WARPS) {
-            cudaError_t e = cudaFuncSetAttribute(topk_softmax_pv_kernel<VPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v);
+            cudaError_t e = cudaFuncSetAttribute(topk_softmax_pv_kernel<VPT, true, FULLROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v);
             if (e != cudaSuccess) return e;
             // rows of a (side, b, h) over nsplit CTAs: the split that needs the fewest (fractional) waves of 148 CTAs; every
             // extra CTA reloads the value matrix, so ties go to the smaller split
@@ -723,14 +751,26 @@ static cudaError_t launch_topk_t(const TopkSides& ps, int nsides, int ldo, int B
                 if (cost < best - 1e-9) { best = cost; nsplit = ns; }
             }
             if (split_env > 0 && nmin / split_env >= 1) nsplit = split_env;
-            return launch_pdl(topk_softmax_pv_kernel<VPT, true>, dim3((unsigned)nbh, (unsigned)nsplit, (unsigned)nsides), dim3(32 * TKS_WARPS), smem_v, st, ps, ldo, topk, nbh);
+            return launch_pdl(topk_softmax_pv_kernel<VPT, true, FULLROW>, dim3((unsigned)nbh, (unsigned)nsplit, (unsigned)nsides), dim3(32 * TKS_WARPS), smem_v, st, ps, ldo, topk, nbh);
         }
     }
     const size_t smem = topk_smem_bytes(TK_WARPS, topk, VPT, 0);
-    cudaError_t e = cudaFuncSetAttribute(topk_softmax_pv_kernel<VPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(topk_softmax_pv_kernel<VPT, false, FULLROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)(((long long)nbh * nmax + TK_WARPS - 1) / TK_WARPS);
-    return launch_pdl(topk_softmax_pv_kernel<VPT, false>, dim3(grid, 1, (unsigned)nsides), dim3(32 * TK_WARPS), smem, st, ps, ldo, topk, nbh);
+    return launch_pdl(topk_softmax_pv_kernel<VPT, false, FULLROW>, dim3(grid, 1, (unsigned)nsides), dim3(32 * TK_WARPS), smem, st, ps, ldo, topk, nbh);
+}
+
+template <int VPT>
+static cudaError_t launch_topk_t(const TopkSides& ps, int nsides, int ldo, int B, int topk, cudaStream_t st) {
+    int nmax = 0, nmin = 1 << 30, mmax = 0;
+    bool full = true;                                        // every side has exactly 32 VPT sources: no padding tests
+    for (int s = 0; s < nsides; ++s) {
+        nmax = ps.N[s] > nmax ? ps.N[s] : nmax; nmin = ps.N[s] < nmin ? ps.N[s] : nmin; mmax = ps.M[s] > mmax ? ps.M[s] : mmax;
+        full = full && ps.M[s] == 32 * VPT;
+    }
+    return full ? launch_topk_tf<VPT, true>(ps, nsides, ldo, B, topk, nmax, nmin, mmax, st)
+                : launch_topk_tf<VPT, false>(ps, nsides, ldo, B, topk, nmax, nmin, mmax, st);
 }
 
 // both sides of a layer in one launch (S[s]: dense logits (B,4,N[s],M[s]); V[s]: head-major values of the source side)

@@ -36,7 +36,9 @@ extern "C" {
 
 /* loss variants computed on the device (mdgat.py:486-594) */
 #define MDGAT_LOSS_NONE 0
-#define MDGAT_LOSS_TRIPLET 1     /* mdgat.py:512-546 (test.py default) */
+#define MDGAT_LOSS_TRIPLET 1     /* mdgat.py:512-546 (test.py default): d_loss = 1 double, the batch mean */
+#define MDGAT_LOSS_GAP 2         /* mdgat.py:547-594 (train.py default): d_loss = B doubles, one per pair; any N, M */
+#define MDGAT_LOSS_SUPERGLUE 3   /* mdgat.py:487-511: d_loss = 1 double; gt with -1 = unmatched (NOT remapped); N == M */
 
 /* GEMM engines for the per-layer projections (q/k/v, MLP) */
 #define MDGAT_GEMM_DMMA_F64 0     /* mma.sync.m8n8k4.f64 (DMMA) on the FP64 pipe */
@@ -103,8 +105,8 @@ typedef struct {
     const void* d_desc1;      /* (B,M,33) */
     const void* d_scores0;    /* (B,N) */
     const void* d_scores1;    /* (B,M) */
-    const int16_t* d_gt0;     /* (B,N) int16, "no match" already mapped to M (mdgat.py:519) or NULL */
-    const int16_t* d_gt1;     /* (B,M) int16, "no match" already mapped to N, or NULL */
+    const int16_t* d_gt0;     /* (B,N) int16, "no match" = M (mdgat.py:519) or -1 (both accepted; SUPERGLUE needs -1), or NULL */
+    const int16_t* d_gt1;     /* (B,M) int16, "no match" = N or -1, or NULL */
 } mdgat_forward_in;
 
 typedef struct {
@@ -112,7 +114,7 @@ typedef struct {
     int64_t* d_matches1;      /* (B,M) */
     double* d_mscores0;       /* (B,N) */
     double* d_mscores1;       /* (B,M) */
-    double* d_loss;           /* 1 double: mean triplet loss (if loss_mode) */
+    double* d_loss;           /* loss_mode TRIPLET / SUPERGLUE: 1 double; GAP: B doubles (one per pair); untouched for NONE */
     int* d_nvalid0;           /* 1 int: number of valid matches0 (the reference branches on it, mdgat.py:465) */
     double* d_Z;              /* (B,N+1,M+1) or NULL unless write_Z */
 } mdgat_forward_out;
@@ -157,8 +159,10 @@ int mdgat_encode(const mdgat_forward_in* in, int B, int N, int M, int in_dtype, 
 
 /* Multi-head attention message for one side (mdgat.py:190-194 / 196-210), head-major inputs:
  * d_Q (B,4,N,36), d_K (B,4,M,36), d_V (B,4,M,34). topk == 0 -> softmax over all M,
- * else exactly-k selection (lowest index wins ties). d_logits: scratch (B,4,N,M) doubles,
- * needed only when topk > 0. Output rows (B*N) x ldo, column h*32+d. */
+ * else exactly-k selection (lowest index wins ties). d_logits: scratch of
+ * mdgat_attention_f64_scratch_doubles(B, N, M) doubles (the dense (B,4,N,M) logits or the ring of the one-kernel
+ * variant, whichever is larger), needed only when topk > 0. Output rows (B*N) x ldo, column h*32+d. */
+size_t mdgat_attention_f64_scratch_doubles(int B, int N, int M);
 int mdgat_attention_f64(const double* d_Q, const double* d_K, const double* d_V, double* d_Out, int ldo,
                         int B, int N, int M, int topk, double* d_logits, void* stream);
 
@@ -186,7 +190,7 @@ int mdgat_sinkhorn_read_status(const double* d_scratch, int B, int N, int M, int
 int mdgat_sinkhorn_f64(double* d_couplings, const double* d_bin_score, double* d_u, double* d_v,
                        int B, int N, int M, int iters, double* d_scratch, void* stream);
 
-/* Match extraction + optional triplet loss from (couplings, u, v) (mdgat.py:442-483,512-546). */
+/* Match extraction + optional loss (MDGAT_LOSS_*) from (couplings, u, v) (mdgat.py:442-483, 487-594); Z is never formed. */
 int mdgat_match_extract(const double* d_couplings, const double* d_u, const double* d_v,
                         int B, int N, int M, int match_mode, int mutual_check, double match_threshold,
                         int loss_mode, double gamma, const int16_t* d_gt0, const int16_t* d_gt1,

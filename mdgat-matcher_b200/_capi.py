@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libmdgat_b200.so')
 
 MDGAT_OK = 0
 MATCH_DUSTBIN, MATCH_THRESHOLD = 0, 1
-LOSS_NONE, LOSS_TRIPLET = 0, 1
+LOSS_NONE, LOSS_TRIPLET, LOSS_GAP, LOSS_SUPERGLUE = 0, 1, 2, 3
 F32, F64 = 0, 1
 GEMM_DMMA_F64, GEMM_TCGEN05_I8 = 0, 1
 ATTN_DMMA_F64, ATTN_TCGEN05_I8, ATTN_TCGEN05_I8_ALL = 0, 1, 2
@@ -60,6 +60,7 @@ def _load():
         'mdgat_gemm_nt_f64': (i, [vp, i, ll, vp, i, ll, vp, i, ll, i, i, i, i, d, vp]),
         'mdgat_encode_scratch_doubles': (sz, [i]),
         'mdgat_encode': (i, [C.POINTER(ForwardIn), i, i, i, i, i, vp, vp, vp, vp]),
+        'mdgat_attention_f64_scratch_doubles': (sz, [i, i, i]),
         'mdgat_attention_f64': (i, [vp, vp, vp, vp, i, i, i, i, i, vp, vp]),
         'mdgat_attention_i8_scratch_bytes': (sz, [i, i, i]),
         'mdgat_attention_i8': (i, [vp, vp, vp, vp, i, i, i, i, i, vp, vp, i, i, vp]),

@@ -19,16 +19,18 @@ namespace mdgat {
 
 constexpr int A_BM = 64, A_BN = 64, A_THREADS = 128, A_STAGES = 2;
 constexpr size_t A_SMEM = ((size_t)A_STAGES * A_BN * (LDH_QK + LDH_V) + 64) * sizeof(double);
+// logits only: no V stages (the table keeps its place behind the K stages), so four or five CTAs fit an SM
+constexpr size_t A_SMEM_LOGITS = ((size_t)A_STAGES * A_BN * LDH_QK + 64) * sizeof(double);
 
 // LOGITS_ONLY = true: the same Q K^T pipeline, but the scaled logits are written to Out as a dense
 // (B,4,N,M) tensor (ldo = M) for the exact top-k selection below; no softmax, V is not read.
 template <bool LOGITS_ONLY>
-__global__ void __launch_bounds__(A_THREADS, 3)
+__global__ void __launch_bounds__(A_THREADS, LOGITS_ONLY ? 4 : 3)
 attn_full_kernel(AttnSides ps, int B, int ldo, double scale) {
     extern __shared__ __align__(16) double smem[];
     double* Ks = smem;                                   // [stage][A_BN][LDH_QK]
-    double* Vs = smem + A_STAGES * A_BN * LDH_QK;        // [stage][A_BN][LDH_V]
-    double* etab = Vs + A_STAGES * A_BN * LDH_V;         // [64] 2^(j/64)
+    double* Vs = smem + A_STAGES * A_BN * LDH_QK;        // [stage][A_BN][LDH_V] (absent with LOGITS_ONLY)
+    double* etab = Vs + (LOGITS_ONLY ? 0 : A_STAGES * A_BN * LDH_V);         // [64] 2^(j/64)
     exp_table_to_shared(etab);
     pdl_wait();
     pdl_trigger();
@@ -218,8 +220,8 @@ static cudaError_t launch_attn(const AttnSides& ps, int B, int nsides, int ldo, 
     const double scale = 1.0 / sqrt((double)HDIM);
     cudaError_t e;
     if (logits_only) {
-        if ((e = cudaFuncSetAttribute(attn_full_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM)) != cudaSuccess) return e;
-        if ((e = launch_pdl(attn_full_kernel<true>, grid, dim3(A_THREADS), A_SMEM, st, ps, B, ldo, scale)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(attn_full_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM_LOGITS)) != cudaSuccess) return e;
+        if ((e = launch_pdl(attn_full_kernel<true>, grid, dim3(A_THREADS), A_SMEM_LOGITS, st, ps, B, ldo, scale)) != cudaSuccess) return e;
     } else {
         if ((e = cudaFuncSetAttribute(attn_full_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM)) != cudaSuccess) return e;
         if ((e = launch_pdl(attn_full_kernel<false>, grid, dim3(A_THREADS), A_SMEM, st, ps, B, ldo, scale)) != cudaSuccess) return e;
@@ -468,6 +470,67 @@ DEVINL bool topk_select_fast(const double (&s)[VPT], int M, int topk, int lane, 
     return true;
 }
 
+// softmax numerators of the kept entries of a row (mdgat.py:206-207), shifted by mx >= every kept logit; returns their sum
+DEVINL double topk_softmax_kept(KeptEntry* kept, int nk, double mx, const double* etab, int lane) {
+    double sum = 0.0;
+    for (int t = lane; t < nk; t += 32) {
+        const double e = exp_fast_neg(kept[t].p - mx, etab);
+        kept[t].p = e;
+        sum += e;
+    }
+    sum = warp_sum_d(sum);
+    __syncwarp();
+    return sum;
+}
+
+// Sparse P.V of one query row and the store of its 32 message channels (dst: channel 0 of this head in the row).
+// Lane roles: quarter-warp qw takes the kept entries t = qw (mod 4); lane cl of it the channels 2cl, 2cl+1, 16+2cl,
+// 17+2cl -- its two 16-byte reads of a value row fall on two contiguous 128-byte runs per quarter-warp. Per entry one
+// 8-byte and one 4-byte broadcast read (probability, row offset) and 256 bytes of the value row; four entries per trip
+// of the warp, two trips in flight. kq_s: shared address of kept[qw]; vq_s / vq_g: value matrix + 16 cl bytes.
+template <bool SMEM_V>
+DEVINL void topk_pv_store(uint32_t kq_s, uint32_t vq_s, const char* vq_g, int nk, double sum, int lane, double* dst) {
+    const int qw = lane >> 3, cl = lane & 7;
+    auto entry = [&](int n, double& pr, double2& x0, double2& x1) {
+        int voff;
+        asm volatile("ld.shared.f64 %0, [%2];\n ld.shared.b32 %1, [%2+8];" : "=d"(pr), "=r"(voff) : "r"(kq_s + (uint32_t)n * 64u));
+        if (SMEM_V) {
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%4];\n ld.shared.v2.f64 {%2, %3}, [%4+128];"
+                         : "=d"(x0.x), "=d"(x0.y), "=d"(x1.x), "=d"(x1.y) : "r"(vq_s + (uint32_t)voff));
+        } else {
+            x0 = __ldg(reinterpret_cast<const double2*>(vq_g + voff));
+            x1 = __ldg(reinterpret_cast<const double2*>(vq_g + voff + 128));
+        }
+    };
+    double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0;
+    const int nq = (nk - qw + 3) >> 2;                   // entries of this quarter-warp
+    int n = 0;
+#pragma unroll 2
+    for (; n + 1 < nq; n += 2) {
+        double p0, p1; double2 x00, x01, x10, x11;
+        entry(n, p0, x00, x01);
+        entry(n + 1, p1, x10, x11);
+        a0.x = fma(p0, x00.x, a0.x); a0.y = fma(p0, x00.y, a0.y); a1.x = fma(p0, x01.x, a1.x); a1.y = fma(p0, x01.y, a1.y);
+        b0.x = fma(p1, x10.x, b0.x); b0.y = fma(p1, x10.y, b0.y); b1.x = fma(p1, x11.x, b1.x); b1.y = fma(p1, x11.y, b1.y);
+    }
+    if (n < nq) {
+        double p0; double2 x00, x01;
+        entry(n, p0, x00, x01);
+        a0.x = fma(p0, x00.x, a0.x); a0.y = fma(p0, x00.y, a0.y); a1.x = fma(p0, x01.x, a1.x); a1.y = fma(p0, x01.y, a1.y);
+    }
+    a0.x += b0.x; a0.y += b0.y; a1.x += b1.x; a1.y += b1.y;
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1) {
+        a0.x += shfl_xor_d(a0.x, o); a0.y += shfl_xor_d(a0.y, o);
+        a1.x += shfl_xor_d(a1.x, o); a1.y += shfl_xor_d(a1.y, o);
+    }
+    if (qw == 0) {
+        const double inv = 1.0 / sum;
+        *reinterpret_cast<double2*>(dst + 2 * cl) = make_double2(a0.x * inv, a0.y * inv);
+        *reinterpret_cast<double2*>(dst + 16 + 2 * cl) = make_double2(a1.x * inv, a1.y * inv);
+    }
+}
+
 // VPT = values per lane (M <= 32*VPT). Dynamic shared memory (aligned to 4 NB bytes): per warp max(topk, 4 VPT)
 // KeptEntry rounded up to a multiple of 4 VPT (its first 64 VPT bytes double as the selection histogram), per warp
 // TK_LMAX boundary-bin entries, then the 64-entry exp table.
@@ -547,18 +610,7 @@ topk_softmax_pv_kernel(const __grid_constant__ TopkSides ps, int ldo, int topk, 
     const uint32_t kq_s = (uint32_t)__cvta_generic_to_shared(kept) + (uint32_t)qw * 16u;         // entry qw + 4 n at kq_s + 64 n
     const uint32_t vq_s = (uint32_t)__cvta_generic_to_shared(sV) + (uint32_t)cl * 16u;
     const char* vq_g = reinterpret_cast<const char*>(V + bh * (long long)M * LDH_V) + cl * 16;
-    // entry n of this quarter-warp: probability, then the four values of its row (shared-window loads, or L2 gathers)
-    auto entry = [&](int n, double& pr, double2& x0, double2& x1) {
-        int voff;
-        asm volatile("ld.shared.f64 %0, [%2];\n ld.shared.b32 %1, [%2+8];" : "=d"(pr), "=r"(voff) : "r"(kq_s + (uint32_t)n * 64u));
-        if (SMEM_V) {
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%4];\n ld.shared.v2.f64 {%2, %3}, [%4+128];"
-                         : "=d"(x0.x), "=d"(x0.y), "=d"(x1.x), "=d"(x1.y) : "r"(vq_s + (uint32_t)voff));
-        } else {
-            x0 = __ldg(reinterpret_cast<const double2*>(vq_g + voff));
-            x1 = __ldg(reinterpret_cast<const double2*>(vq_g + voff + 128));
-        }
-    };
+    (void)qw;
   for (; i < iend; i += WARPS) {
     double mx;
     if (!topk_select_fast<VPT, FULLROW>(s, M, topk, lane, kept, alist, mx))
@@ -566,49 +618,310 @@ topk_softmax_pv_kernel(const __grid_constant__ TopkSides ps, int ldo, int topk, 
     const int nk = min(topk, M);
     // the logits of this warp's next row travel while the P.V below runs
     if (SMEM_V && i + WARPS < iend) load_row(i + WARPS, s);
-    // softmax over the kept k (mdgat.py:206-207), shifted by the upper bound of the row maximum
-    double sum = 0.0;
-    for (int t = lane; t < nk; t += 32) {
-        const double e = exp_fast_neg(kept[t].p - mx, etab);
-        kept[t].p = e;
-        sum += e;
-    }
-    sum = warp_sum_d(sum);
-    __syncwarp();
+    const double sum = topk_softmax_kept(kept, nk, mx, etab, lane);
     if (!v_ready) { mbar_wait(&v_bar, 0); v_ready = true; }
-    // sparse P.V: only k of the M value rows are read; per entry one 8-byte and one 4-byte broadcast read (probability,
-    // row offset) and 256 bytes of the value row; four entries per trip of the warp, two trips in flight
-    double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0;
-    const int nq = (nk - qw + 3) >> 2;                   // entries of this quarter-warp
-    int n = 0;
-#pragma unroll 2
-    for (; n + 1 < nq; n += 2) {
-        double p0, p1; double2 x00, x01, x10, x11;
-        entry(n, p0, x00, x01);
-        entry(n + 1, p1, x10, x11);
-        a0.x = fma(p0, x00.x, a0.x); a0.y = fma(p0, x00.y, a0.y); a1.x = fma(p0, x01.x, a1.x); a1.y = fma(p0, x01.y, a1.y);
-        b0.x = fma(p1, x10.x, b0.x); b0.y = fma(p1, x10.y, b0.y); b1.x = fma(p1, x11.x, b1.x); b1.y = fma(p1, x11.y, b1.y);
-    }
-    if (n < nq) {
-        double p0; double2 x00, x01;
-        entry(n, p0, x00, x01);
-        a0.x = fma(p0, x00.x, a0.x); a0.y = fma(p0, x00.y, a0.y); a1.x = fma(p0, x01.x, a1.x); a1.y = fma(p0, x01.y, a1.y);
-    }
-    a0.x += b0.x; a0.y += b0.y; a1.x += b1.x; a1.y += b1.y;
-#pragma unroll
-    for (int o = 8; o < 32; o <<= 1) {
-        a0.x += shfl_xor_d(a0.x, o); a0.y += shfl_xor_d(a0.y, o);
-        a1.x += shfl_xor_d(a1.x, o); a1.y += shfl_xor_d(a1.y, o);
-    }
-    if (qw == 0) {
-        const double inv = 1.0 / sum;
-        double* dst = Out + ((long long)b * N + i) * ldo + h * HDIM + 2 * cl;
-        *reinterpret_cast<double2*>(dst) = make_double2(a0.x * inv, a0.y * inv);
-        *reinterpret_cast<double2*>(dst + 16) = make_double2(a1.x * inv, a1.y * inv);
-    }
+    topk_pv_store<SMEM_V>(kq_s, vq_s, vq_g, nk, sum, lane, Out + ((long long)b * N + i) * ldo + h * HDIM);
     __syncwarp();                                        // kept[] is rewritten by the next row
     if (!SMEM_V) break;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// dynamic_attention() in ONE kernel: the dense logits never travel to HBM.
+//
+// The two-kernel route above writes the (B,4,N,M) float64 logits (537 MB per layer at cfg2) and reads them back: the
+// logits kernel is bound by the HBM WRITE rate (2.8 TB/s, not by its DMMAs), the selection kernel by the shared-memory
+// wavefronts of its value gathers -- the FP64 pipe idles there. Here both run in the same persistent CTA (one per SM):
+//   warps 0-15   consumers: exact top-k selection + softmax + sparse P.V, one query row per warp (code shared with
+//                topk_softmax_pv_kernel)
+//   warps 16-19  producers: Q K^T / sqrt(32) of 16-row groups on DMMA.8x8x4 (one producer warp per SM sub-partition),
+//                K arriving in 64-key chunks by TMA bulk copies; a finished group (16 rows x M logits) goes to a
+//                slot of the CTA's private ring in global memory
+//   warp 20      loader: the K chunk ring and the head's value matrix (one bulk copy per (side, b, h))
+// The ring (8 slots x 16 rows x M doubles = 512 KB per CTA, 76 MB for 148 CTAs) is rewritten every few microseconds
+// and stays in the 126 MB L2: the consumers read it with ld.global.cg. A CTA walks a contiguous range of the work
+// items (side, b, h, row split), so the value matrix is reloaded only when (side, b, h) changes.
+// ------------------------------------------------------------------------------------------
+constexpr int TF_CONS = 16, TF_PROD = 4, TF_THREADS = 32 * (TF_CONS + TF_PROD), TF_GROUP = 16, TF_SLOTS = 8, TF_KC = 64;
+struct TopkFusedParams {
+    const double* Q[2]; const double* K[2]; const double* V[2]; double* Out[2];
+    int N[2], M[2];
+    double* ring;                 // [gridDim.x][TF_SLOTS][TF_GROUP][ldS]
+    int ldS, ldo, topk, nbh, nsplit, per, items, items_side0, slots;   // slots <= TF_SLOTS ring slots in use
+    double scale;
+};
+
+template <bool FULLROW>
+__global__ void __launch_bounds__(TF_THREADS, 1) topk_fused_kernel(const __grid_constant__ TopkFusedParams p) {
+    constexpr int VPT = 16;
+    extern __shared__ __align__(16) unsigned char tf_smem_raw[];
+    constexpr uint32_t HB = 64 * VPT;
+    const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(tf_smem_raw);
+    unsigned char* smem = tf_smem_raw + (((raw_s + HB - 1) & ~(HB - 1)) - raw_s);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int KS = tk_kept_entries(p.topk, VPT);
+    KeptEntry* kept_all = reinterpret_cast<KeptEntry*>(smem);
+    KeptEntry* alist_all = kept_all + (size_t)TF_CONS * KS;
+    double* etab = reinterpret_cast<double*>(alist_all + (size_t)TF_CONS * TK_LMAX);
+    double* sK = etab + 64;                                            // [2][TF_KC][LDH_QK]
+    double* sV = sK + 2 * TF_KC * LDH_QK;                              // [M][LDH_V]
+    __shared__ __align__(8) uint64_t k_full[2], k_empty[2], v_full, slot_full[TF_SLOTS], slot_free[TF_SLOTS];
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], TF_PROD); }
+        mbar_init(&v_full, 1);
+        for (int i = 0; i < TF_SLOTS; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_free[i], TF_CONS); }
+        mbar_fence_init();
+    }
+    exp_table_to_shared(etab);
+    __syncthreads();
+    pdl_wait();
+    pdl_trigger();
+    // contiguous item range of this CTA; item = ((side * nbh + bh) * nsplit + split)
+    const int it0 = (int)(((long long)p.items * blockIdx.x) / gridDim.x), it1 = (int)(((long long)p.items * (blockIdx.x + 1)) / gridDim.x);
+    double* ring = p.ring + (size_t)blockIdx.x * p.slots * TF_GROUP * p.ldS;
+    auto decode = [&](int it, int& side, int& bh, int& r0, int& r1) {
+        side = it >= p.items_side0 ? 1 : 0;
+        const int q = it - side * p.items_side0;
+        bh = q / p.nsplit;
+        const int sp = q - bh * p.nsplit;
+        r0 = sp * p.per;
+        r1 = min(p.N[side], r0 + p.per);
+    };
+
+    if (warp >= TF_CONS) {
+        // ------------------------------------------------------------------ producers: logits of 16-row groups
+        const int pw = warp - TF_CONS, qr = lane >> 2, qc = lane & 3;
+        const bool loader = pw == 0 && elect_one();          // one lane of producer warp 0 also feeds the K chunk ring
+        // the loader walks the chunk sequence (item, pass, chunk) one chunk ahead of the compute loop below
+        int l_it = it0, l_ps = 0, l_c = 0, l_q = 0;
+        auto load_next = [&]() {                              // issues the load of chunk l_q (if any is left)
+            int side, bh, r0, r1;
+            for (;; ++l_it) {                                 // items past the end of the shorter side are empty
+                if (l_it >= it1) return;
+                decode(l_it, side, bh, r0, r1);
+                if (r1 > r0) break;
+            }
+            const int M = p.M[side];
+            const int groups = (r1 - r0 + TF_GROUP - 1) / TF_GROUP, passes = (groups + TF_PROD - 1) / TF_PROD;
+            const int nch = (M + TF_KC - 1) / TF_KC;
+            const int st = l_q & 1;
+            if (l_q >= 2) mbar_wait(&k_empty[st], (unsigned)(((l_q >> 1) - 1) & 1));
+            const int rows = min(TF_KC, M - l_c * TF_KC);
+            const unsigned bytes = (unsigned)(rows * LDH_QK * sizeof(double));
+            mbar_expect_tx(&k_full[st], bytes);
+            bulk_g2s(sK + st * TF_KC * LDH_QK, p.K[side] + ((long long)bh * M + (long long)l_c * TF_KC) * LDH_QK, bytes, &k_full[st]);
+            ++l_q;
+            if (++l_c == nch) { l_c = 0; if (++l_ps == passes) { l_ps = 0; ++l_it; } }
+        };
+        if (loader) load_next();
+        int kq = 0, uses[2] = {0, 0};                       // uses[j]: how often this warp has filled slot pw + 4 j
+        for (int it = it0; it < it1; ++it) {
+            int side, bh, r0, r1;
+            decode(it, side, bh, r0, r1);
+            if (r1 <= r0) continue;
+            const int N = p.N[side], M = p.M[side];
+            const int groups = (r1 - r0 + TF_GROUP - 1) / TF_GROUP, passes = (groups + TF_PROD - 1) / TF_PROD;
+            const int nch = (M + TF_KC - 1) / TF_KC;
+            const double* Qbh = p.Q[side] + (long long)bh * N * LDH_QK;
+            for (int ps = 0; ps < passes; ++ps) {
+                const int g = ps * TF_PROD + pw;            // group of this warp in this pass (slot g)
+                const bool active = g < groups;
+                double qa[2][8];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int row = r0 + g * TF_GROUP + mt * 8 + qr;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) qa[mt][ks] = (active && row < N) ? Qbh[(long long)row * LDH_QK + ks * 4 + qc] : 0.0;
+                }
+                if (active) {
+                    const int use = uses[ps & 1];           // at most two passes per item (8 slots of 16 rows)
+                    if (use > 0) mbar_wait(&slot_free[g], (unsigned)((use - 1) & 1));
+                }
+                double* out = ring + (size_t)(active ? g : 0) * TF_GROUP * p.ldS;
+                for (int c = 0; c < nch; ++c, ++kq) {
+                    const int st = kq & 1;
+                    if (loader) load_next();                 // chunk kq + 1 travels while chunk kq is multiplied
+                    mbar_wait(&k_full[st], (unsigned)((kq >> 1) & 1));
+                    if (active) {
+                        const double* ks_ = sK + st * TF_KC * LDH_QK;
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            double acc[2][4][2];
+#pragma unroll
+                            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                                for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+                                for (int nt = 0; nt < 4; ++nt) {
+                                    const double bfrag = ks_[(half * 32 + nt * 8 + qr) * LDH_QK + ks * 4 + qc];
+                                    dmma884(acc[0][nt][0], acc[0][nt][1], qa[0][ks], bfrag);
+                                    dmma884(acc[1][nt][0], acc[1][nt][1], qa[1][ks], bfrag);
+                                }
+                            }
+#pragma unroll
+                            for (int mt = 0; mt < 2; ++mt) {
+                                double* orow = out + (size_t)(mt * 8 + qr) * p.ldS;
+#pragma unroll
+                                for (int nt = 0; nt < 4; ++nt) {
+                                    const int col = c * TF_KC + half * 32 + nt * 8 + 2 * qc;
+                                    const double y0 = acc[mt][nt][0] * p.scale, y1 = acc[mt][nt][1] * p.scale;
+                                    if (col + 1 < p.ldS) *reinterpret_cast<double2*>(orow + col) = make_double2(y0, y1);
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&k_empty[st]);
+                }
+                if (active) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&slot_full[g]);      // release: the group's logits are visible to the consumers
+                    ++uses[ps & 1];
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ consumers
+        KeptEntry* kept = kept_all + (size_t)warp * KS;
+        KeptEntry* alist = alist_all + (size_t)warp * TK_LMAX;
+        const int qw = lane >> 3, cl = lane & 7;
+        const uint32_t kq_s = (uint32_t)__cvta_generic_to_shared(kept) + (uint32_t)qw * 16u;
+        const uint32_t vq_s = (uint32_t)__cvta_generic_to_shared(sV) + (uint32_t)cl * 16u;
+        int uses[TF_SLOTS];
+#pragma unroll
+        for (int i = 0; i < TF_SLOTS; ++i) uses[i] = 0;
+        int prev_side = -1, prev_bh = -1;
+        unsigned vphase = 0;
+        for (int it = it0; it < it1; ++it) {
+            int side, bh, r0, r1;
+            decode(it, side, bh, r0, r1);
+            if (r1 <= r0) continue;
+            const int N = p.N[side], M = p.M[side];
+            const int b = bh / HEADS, h = bh - b * HEADS;
+            const int groups = (r1 - r0 + TF_GROUP - 1) / TF_GROUP;
+            // the head's value matrix: reloaded when (side, b, h) changes, once every consumer is done with the previous item
+            if (side != prev_side || bh != prev_bh) {
+                asm volatile("bar.sync 1, %0;" :: "n"(32 * TF_CONS) : "memory");
+                if (warp == 0 && elect_one()) {
+                    const unsigned bytes = (unsigned)((size_t)M * LDH_V * sizeof(double));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic reads of the old matrix before the async write
+                    mbar_expect_tx(&v_full, bytes);
+                    bulk_g2s(sV, p.V[side] + (long long)bh * M * LDH_V, bytes, &v_full);
+                }
+                mbar_wait(&v_full, vphase);
+                vphase ^= 1u;
+                prev_side = side; prev_bh = bh;
+            }
+#pragma unroll
+            for (int g = 0; g < TF_SLOTS; ++g) {
+                if (g < groups) {
+                    mbar_wait(&slot_full[g], (unsigned)(uses[g] & 1));
+                    ++uses[g];
+                    const int row = r0 + g * TF_GROUP + warp;
+                    if (row < r1) {
+                        const double* srow = ring + ((size_t)g * TF_GROUP + warp) * p.ldS;
+                        double s[VPT];
+#pragma unroll
+                        for (int v = 0; v < VPT; ++v) {
+                            const int j = lane + 32 * v;
+                            s[v] = (FULLROW || j < M) ? __ldcg(srow + j) : -INFINITY;
+                        }
+                        double mx;
+                        if (!topk_select_fast<VPT, FULLROW>(s, M, p.topk, lane, kept, alist, mx))
+                            topk_select_exact<VPT>(srow, M, p.topk, lane, kept);
+                        const int nk = min(p.topk, M);
+                        const double sum = topk_softmax_kept(kept, nk, mx, etab, lane);
+                        topk_pv_store<true>(kq_s, vq_s, nullptr, nk, sum, lane, p.Out[side] + ((long long)b * N + row) * p.ldo + h * HDIM);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&slot_free[g]);
+                }
+            }
+        }
+    }
+}
+
+static size_t topk_fused_smem(int topk, int mmax) {
+    return ((size_t)TF_CONS * (tk_kept_entries(topk, 16) + TK_LMAX)) * sizeof(KeptEntry) + 64 * sizeof(double) +
+           (size_t)2 * TF_KC * LDH_QK * sizeof(double) + (size_t)mmax * LDH_V * sizeof(double) + 64 * 16;
+}
+
+static int tf_sms() {
+    static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n > 0 ? n : 148; }();
+    return sms;
+}
+// items and ring geometry shared by the sizing function and the launcher
+// ring slots in use (MDGAT_TOPK_SLOTS = 4 | 8): 8 double-buffers the four producers, 4 halves the ring (38 MB for 148 CTAs at M = 512)
+static int tf_slots() {
+    static const int n = [] { const char* e = getenv("MDGAT_TOPK_SLOTS"); return e && e[0] == '4' ? 4 : TF_SLOTS; }();
+    return n;
+}
+static void tf_geometry(int nmax, int mmax, int& nsplit, int& per, int& ldS) {
+    const int ns0 = (nmax + tf_slots() * TF_GROUP - 1) / (tf_slots() * TF_GROUP);
+    per = ((nmax + ns0 - 1) / ns0 + TF_GROUP - 1) / TF_GROUP * TF_GROUP;
+    nsplit = (nmax + per - 1) / per;
+    ldS = (mmax + 1) & ~1;
+}
+// ring scratch (doubles) that covers every top-k layer of a forward on B pairs of N x M keypoints (self and cross layers)
+size_t topk_fused_ring_doubles(int B, int N, int M) {
+    const int big = N > M ? N : M;
+    int nsplit, per, ldS;
+    tf_geometry(big, big, nsplit, per, ldS);
+    const long long items = 2ll * B * HEADS * nsplit;
+    const long long grid = items < tf_sms() ? items : tf_sms();
+    return (size_t)grid * tf_slots() * TF_GROUP * ldS;
+}
+// exact ring need of one launch
+size_t topk_fused_ring_need(const AttnSides& ps, int B, int nsides) {
+    int nmax = 0, mmax = 0;
+    for (int s = 0; s < nsides; ++s) { nmax = ps.N[s] > nmax ? ps.N[s] : nmax; mmax = ps.M[s] > mmax ? ps.M[s] : mmax; }
+    int nsplit, per, ldS;
+    tf_geometry(nmax, mmax, nsplit, per, ldS);
+    const long long items = (long long)nsides * B * HEADS * nsplit;
+    const long long grid = items < tf_sms() ? items : tf_sms();
+    return (size_t)grid * tf_slots() * TF_GROUP * ldS;
+}
+bool topk_fused_supported(int nsides, const int* N, const int* M, int topk) {
+    int mmax = 0, nmin = 1 << 30;
+    for (int s = 0; s < nsides; ++s) { mmax = M[s] > mmax ? M[s] : mmax; nmin = N[s] < nmin ? N[s] : nmin; }
+    return mmax <= 512 && nmin >= 1 && topk >= 1 && topk_fused_smem(topk, mmax) <= 227 * 1024;
+}
+
+cudaError_t launch_topk_fused(const AttnSides& ps, int B, int nsides, int ldo, int topk, double* ring, size_t ring_doubles, cudaStream_t st) {
+    const int sms = tf_sms();
+    TopkFusedParams p;
+    int mmax = 0, nmax = 0;
+    bool full = true;
+    for (int s = 0; s < 2; ++s) {
+        const int t = s < nsides ? s : 0;
+        p.Q[s] = ps.Q[t]; p.K[s] = ps.K[t]; p.V[s] = ps.V[t]; p.Out[s] = ps.Out[t]; p.N[s] = ps.N[t]; p.M[s] = ps.M[t];
+        mmax = ps.M[t] > mmax ? ps.M[t] : mmax; nmax = ps.N[t] > nmax ? ps.N[t] : nmax;
+        full = full && ps.M[t] == 512;
+    }
+    if (!topk_fused_supported(nsides, ps.N, ps.M, topk)) return cudaErrorInvalidValue;
+    p.ring = ring; p.ldo = ldo; p.topk = topk; p.nbh = B * HEADS;
+    // rows of a (side, b, h) per item: at most 8 groups of 16 (the ring), a multiple of 16
+    tf_geometry(nmax, mmax, p.nsplit, p.per, p.ldS);
+    p.items_side0 = p.nbh * p.nsplit;
+    p.items = nsides * p.items_side0;
+    p.scale = 1.0 / sqrt((double)HDIM);
+    const size_t smem = topk_fused_smem(topk, mmax);
+    const int grid = p.items < sms ? p.items : sms;
+    p.slots = tf_slots();
+    if ((size_t)grid * p.slots * TF_GROUP * p.ldS > ring_doubles) return cudaErrorInvalidValue;
+    cudaError_t e;
+    if (full) {
+        if ((e = cudaFuncSetAttribute(topk_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        e = launch_pdl(topk_fused_kernel<true>, dim3(grid), dim3(TF_THREADS), smem, st, p);
+    } else {
+        if ((e = cudaFuncSetAttribute(topk_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        e = launch_pdl(topk_fused_kernel<false>, dim3(grid), dim3(TF_THREADS), smem, st, p);
+    }
+    if (e != cudaSuccess) return e;
+    count_launch();
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------

@@ -101,7 +101,7 @@ struct Workspace {
     double *tkthr, *tkmax; int* tkjl;                   // tcgen05 top-k layers: per (b, h, row) threshold, maximum, last tied column
     double *rsX, *rsM, *rsH; int8_t *xsX, *xsM, *xsH;   // tcgen05 path: int8 slice planes + row scales of X, Msg, Hd (2 chunks)
     AttnI8Side ai[2];                                   // tcgen05 attention: digit planes of q/k/v of side 0 / side 1
-    size_t bytes;
+    size_t bytes, S_doubles;
 };
 
 // Carves the workspace; with base == nullptr only computes the size.
@@ -124,8 +124,13 @@ Workspace carve(char* base, int B, int N, int M, bool need_logits, int i8_slices
     w.Mg = take(R * LDX);
     w.Hd = take(R * LDHID);
     w.MD = take(R * LDX);
-    // logits of both sides at once: self layers need N*N + M*M, cross layers 2*N*M (never more)
-    w.S = take(need_logits ? (size_t)B * HEADS * ((size_t)N * N + (size_t)M * M) : 0);
+    // logits of both sides at once: self layers need N*N + M*M, cross layers 2*N*M (never more); the fused top-k kernel
+    // uses the same buffer as its ring
+    {
+        const size_t dense = (size_t)B * HEADS * ((size_t)N * N + (size_t)M * M), ringd = topk_fused_ring_doubles(B, N, M);
+        w.S_doubles = need_logits ? (dense > ringd ? dense : ringd) : 0;
+        w.S = take(w.S_doubles);
+    }
     w.C = take((size_t)B * (N + 1) * (M + 1));
     w.u = take((size_t)B * (N + 1));
     w.v = take((size_t)B * (M + 1));
@@ -180,7 +185,8 @@ cudaError_t gemm_nt(const double* X, int ldx, long long sX, const double* W, int
 struct TopKScratch { double* thr; double* rmax; int* jlast; };
 cudaError_t attention_layer(const AttnSides& ps, int B, int nsides, int ldo, int topk, double* S, cudaStream_t st,
                             const AttnI8Side* qd = nullptr, const AttnI8Side* kvd = nullptr, int SP = 0,
-                            const TopKScratch* tks = nullptr, const AttnI8MsgPlanes* mp = nullptr, bool* planes_written = nullptr) {
+                            const TopKScratch* tks = nullptr, const AttnI8MsgPlanes* mp = nullptr, bool* planes_written = nullptr,
+                            size_t S_doubles = 0) {
     if (planes_written) *planes_written = false;
     if (qd) {
         if (topk <= 0) {
@@ -209,6 +215,11 @@ cudaError_t attention_layer(const AttnSides& ps, int B, int nsides, int ldo, int
         return launch_attn_i8(qd, kvd, ps.Out, B, nsides, ldo, AI_MODE_TOPK, &tk, SP, st, mp);
     }
     if (topk <= 0) return launch_attention_full(ps, B, nsides, ldo, st);
+    // MDGAT_TOPK_FUSED=1 (or debug flag bit 17, per call, for the tests): one persistent kernel whose logits go through a
+    // per-CTA ring instead of the dense scratch. Parity-green but measured slower than the two launches below
+    static const bool fused_env = [] { const char* e = getenv("MDGAT_TOPK_FUSED"); return e && e[0] == '1'; }();
+    if ((fused_env || (g_debug_flags & 0x20000) != 0) && topk_fused_supported(nsides, ps.N, ps.M, topk) && S_doubles >= topk_fused_ring_need(ps, B, nsides))
+        return launch_topk_fused(ps, B, nsides, ldo, topk, S, S_doubles, st);
     // dense logits q.k / sqrt(32) for every (b, h) (mdgat.py:201), then exact-k selection per row
     AttnSides lg = ps;
     double* sp = S;
@@ -269,6 +280,15 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
             MDGAT_REQUIRE(k <= N && k <= M, "selected index k out of range (layer %d: k=%d, N=%d, M=%d)", i, k, N, M);
             MDGAT_REQUIRE(N <= 2048 && M <= 2048, "top-k attention supports at most 2048 source keypoints (N=%d, M=%d)", N, M);
         }
+    }
+    MDGAT_REQUIRE(cfg->loss_mode >= MDGAT_LOSS_NONE && cfg->loss_mode <= MDGAT_LOSS_SUPERGLUE, "mdgat_forward: unknown loss_mode %d", cfg->loss_mode);
+    if (cfg->loss_mode == MDGAT_LOSS_GAP) {
+        MDGAT_REQUIRE(in->d_gt0 && in->d_gt1, "gap loss needs gt_matches0/1");
+        MDGAT_REQUIRE(cfg->match_mode == MDGAT_MATCH_DUSTBIN, "gap loss is defined on the dustbin match variant");
+    }
+    if (cfg->loss_mode == MDGAT_LOSS_SUPERGLUE) {
+        MDGAT_REQUIRE(in->d_gt0 && in->d_gt1, "superglue loss needs gt_matches0/1");
+        MDGAT_REQUIRE(N == M, "superglue loss needs N == M (the reference indexes an N-shaped mask with M, mdgat.py:501)");
     }
     if (cfg->loss_mode == MDGAT_LOSS_TRIPLET) {
         MDGAT_REQUIRE(in->d_gt0 && in->d_gt1, "triplet loss needs gt_matches0/1");
@@ -360,7 +380,7 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
             const AttnI8MsgPlanes mpl = {w.xsM, w.rsM, S8, {0, (long long)R0}};
             MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st, qd, kvd, ASP, &tks, (i8 && msg_planes_env) ? &mpl : nullptr, &msg_planes));
         } else {
-            MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st));
+            MDGAT_CUDA_OK(attention_layer(ps, B, 2, LDX, k, w.S, st, nullptr, nullptr, 0, nullptr, nullptr, nullptr, w.S_doubles));
         }
         prof_mark(i8 ? ST_SLICE : ST_GEMM, st);
         // the merge conv (mdgat.py:237) is folded into the first MLP conv by the weight packer
@@ -468,6 +488,15 @@ int mdgat_encode(const mdgat_forward_in* in, int B, int N, int M, int in_dtype, 
     return MDGAT_OK;
 }
 
+size_t mdgat_attention_f64_scratch_doubles(int B, int N, int M) {
+    if (B < 1 || N < 1 || M < 1) return 0;
+    AttnSides ps;
+    memset(&ps, 0, sizeof(ps));
+    ps.N[0] = N; ps.M[0] = M;
+    const size_t dense = (size_t)B * HEADS * N * M, ring = topk_fused_ring_need(ps, B, 1);
+    return dense > ring ? dense : ring;
+}
+
 int mdgat_attention_f64(const double* d_Q, const double* d_K, const double* d_V, double* d_Out, int ldo,
                         int B, int N, int M, int topk, double* d_logits, void* stream) {
     MDGAT_REQUIRE(topk <= M, "selected index k out of range (k=%d, M=%d)", topk, M);
@@ -476,7 +505,8 @@ int mdgat_attention_f64(const double* d_Q, const double* d_K, const double* d_V,
     AttnSides ps;
     memset(&ps, 0, sizeof(ps));
     ps.Q[0] = d_Q; ps.K[0] = d_K; ps.V[0] = d_V; ps.Out[0] = d_Out; ps.N[0] = N; ps.M[0] = M;
-    MDGAT_CUDA_OK(attention_layer(ps, B, 1, ldo, topk, d_logits, reinterpret_cast<cudaStream_t>(stream)));
+    MDGAT_CUDA_OK(attention_layer(ps, B, 1, ldo, topk, d_logits, reinterpret_cast<cudaStream_t>(stream), nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                                  mdgat_attention_f64_scratch_doubles(B, N, M)));
     return MDGAT_OK;
 }
 
@@ -536,8 +566,11 @@ int mdgat_match_extract(const double* d_couplings, const double* d_u, const doub
                         int match_mode, int mutual_check, double match_threshold, int loss_mode, double gamma,
                         const int16_t* d_gt0, const int16_t* d_gt1, const mdgat_forward_out* out,
                         double* d_scratch, void* stream) {
-    MDGAT_REQUIRE(loss_mode == MDGAT_LOSS_NONE || (d_gt0 && d_gt1 && N == M && match_mode == MDGAT_MATCH_DUSTBIN),
+    MDGAT_REQUIRE(loss_mode >= MDGAT_LOSS_NONE && loss_mode <= MDGAT_LOSS_SUPERGLUE, "mdgat_match_extract: unknown loss_mode %d", loss_mode);
+    MDGAT_REQUIRE(loss_mode != MDGAT_LOSS_TRIPLET || (d_gt0 && d_gt1 && N == M && match_mode == MDGAT_MATCH_DUSTBIN),
                   "mdgat_match_extract: triplet loss needs gt, N == M and the dustbin variant");
+    MDGAT_REQUIRE(loss_mode != MDGAT_LOSS_GAP || (d_gt0 && d_gt1 && match_mode == MDGAT_MATCH_DUSTBIN), "mdgat_match_extract: gap loss needs gt and the dustbin variant");
+    MDGAT_REQUIRE(loss_mode != MDGAT_LOSS_SUPERGLUE || (d_gt0 && d_gt1 && N == M), "mdgat_match_extract: superglue loss needs gt and N == M");
     MatchParams mp;
     memset(&mp, 0, sizeof(mp));
     mp.C = d_couplings; mp.u = d_u; mp.v = d_v; mp.B = B; mp.N = N; mp.M = M;

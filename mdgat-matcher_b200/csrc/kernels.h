@@ -44,6 +44,13 @@ cudaError_t launch_attention_logits(const AttnSides& ps, int B, int nsides, cuda
 // Exact top-k selection + softmax + sparse P.V from materialised logits S (B,4,N,M).
 cudaError_t launch_topk_softmax_pv(const double* S, const double* V, double* Out, int ldo,
                                    int B, int N, int M, int topk, cudaStream_t st);
+// dynamic_attention() in one persistent kernel (DMMA logits producers + selection / P.V consumers per CTA): ring = scratch of
+// at least topk_fused_ring_doubles(B, N, M) doubles; topk_fused_supported() says whether the shape qualifies (else the
+// two launches above / below run)
+size_t topk_fused_ring_doubles(int B, int N, int M);
+size_t topk_fused_ring_need(const AttnSides& ps, int B, int nsides);
+bool topk_fused_supported(int nsides, const int* N, const int* M, int topk);
+cudaError_t launch_topk_fused(const AttnSides& ps, int B, int nsides, int ldo, int topk, double* ring, size_t ring_doubles, cudaStream_t st);
 // both sides of a layer in ONE launch (S[s]: dense logits (B,4,N[s],M[s]) of side s, V[s]: its head-major source values)
 cudaError_t launch_topk_softmax_pv_sides(const double* const* S, const double* const* V, double* const* Out, int ldo,
                                          int B, const int* N, const int* M, int nsides, int topk, cudaStream_t st);

@@ -1,6 +1,7 @@
-// Match extraction and the triplet loss, straight from (couplings, u, v) without writing Z.
+// Match extraction and the three losses, straight from (couplings, u, v) without writing Z.
 // Restates /root/reference/models/mdgat.py:442-483 (both the dustbin-arg-max variant used by
-// loss_method != 'superglue' and the thresholded variant) and :512-546 (triplet_loss).
+// loss_method != 'superglue' and the thresholded variant), :512-546 (triplet_loss), :547-594 (gap_loss) and
+// :487-511 ('superglue' loss).
 //
 // Z_ij = ((C_ij + u_i) + v_j) - norm is evaluated in the reference's association order so
 // that exact ties (duplicated keypoints, load_data.py:198-201) tie here as well; arg-max
@@ -175,6 +176,136 @@ mean_kernel(const double* __restrict__ terms, long long n, double* __restrict__ 
     if (threadIdx.x == 0) *out = red[0] / (double)n;
 }
 
+// ------------------------------------------------------------------------------------------
+// gap_loss (mdgat.py:547-594) and the 'superglue' loss (mdgat.py:487-511) straight from (C, u, v): Z is not written.
+//
+// Direction pc0 -> pc1 of gap_loss is row-aligned: row i has one positive (column gt0_i) and M negatives, and the
+// reference's boolean-mask gathers keep their order. Direction pc1 -> pc0 is NOT: `scores[:,:,:-1][pos_match].view(b,m)`
+// and `[neg_match].view(b,n,m)` flatten the (N+1) x M block ROW-major, so the M positives arrive sorted by (gt1_j, j) and the
+// N M negatives are the non-positive entries in row-major order, cut into N rows of M (mdgat.py:580-584). Entry t of that
+// list is the block entry e = t + #{k : p_k - k <= t}, p_0 < p_1 < ... the row-major positions of the positives. The kernels
+// below reproduce exactly that pairing (it misaligns positives and negatives whenever gt1 is not sorted; the drop-in's
+// contract is the reference's observable value, not the intended formula).
+// clamp(x, min=0) of torch keeps NaN; fmax() would not.
+// ------------------------------------------------------------------------------------------
+DEVINL double clamp_min0(double x) { return x > 0.0 ? x : (x != x ? x : 0.0); }
+DEVINL double z_at(const MatchParams& p, int b, int i, int j, double norm) {
+    const int C1 = p.M + 1, R1 = p.N + 1;
+    return ((p.C[((long long)b * R1 + i) * C1 + j] + p.u[(long long)b * R1 + i]) + p.v[(long long)b * C1 + j]) - norm;
+}
+
+// one warp per row i < N: rowterm = 2 log(sum_{j != gt0_i} max(0, nle(z_pos) - nle(z_ij) + gamma) + 1)
+__global__ void __launch_bounds__(256)
+gap_rows_kernel(MatchParams p, double norm, double* __restrict__ rowterm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, i = blockIdx.x * 8 + warp;
+    if (i >= p.N) return;
+    int pos = p.gt0[(long long)b * p.N + i]; if (pos < 0) pos = p.M;            // mdgat.py:554
+    const double apos = neglogexp(z_at(p, b, i, pos, norm));
+    double s = 0.0;
+    for (int j = lane; j <= p.M; j += 32)
+        if (j != pos) s += clamp_min0(apos - neglogexp(z_at(p, b, i, j, norm)) + p.gamma);
+    s = warp_sum_d(s);
+    if (lane == 0) rowterm[(long long)b * p.N + i] = 2.0 * log(s + 1.0);
+}
+
+// one CTA per pair: the positives of the (N+1) x M block in row-major order. q[k] = p_k - k, posval[k] = nle(z at p_k)
+__global__ void __launch_bounds__(512)
+gap_sort_kernel(MatchParams p, double norm, int* __restrict__ q, double* __restrict__ posval) {
+    extern __shared__ int16_t g_gt[];
+    const int b = blockIdx.x, N = p.N, M = p.M;
+    for (int j = threadIdx.x; j < M; j += blockDim.x) { int g = p.gt1[(long long)b * M + j]; if (g < 0) g = N; g_gt[j] = (int16_t)g; }   // mdgat.py:555
+    __syncthreads();
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+        const int g = g_gt[j];
+        int rank = 0;
+        for (int t = 0; t < M; ++t) { const int o = g_gt[t]; rank += (o < g || (o == g && t < j)) ? 1 : 0; }
+        q[(long long)b * M + rank] = g * M + j - rank;
+        posval[(long long)b * M + rank] = neglogexp(z_at(p, b, g, j, norm));
+    }
+}
+
+// colterm[c] = 2 log(sum_r max(0, posval[c] - nle(neg[r][c]) + gamma) + 1), neg[r][c] = entry r M + c of the negative list
+constexpr int GP_TY = 16;
+__global__ void __launch_bounds__(32 * GP_TY)
+gap_cols_kernel(MatchParams p, double norm, const int* __restrict__ q, const double* __restrict__ posval, double* __restrict__ colterm) {
+    extern __shared__ int g_q[];                           // [M]
+    __shared__ double red[GP_TY][33];
+    const int tx = threadIdx.x, ty = threadIdx.y, N = p.N, M = p.M;
+    const int b = blockIdx.y, c = blockIdx.x * 32 + tx;
+    for (int t = ty * 32 + tx; t < M; t += 32 * GP_TY) g_q[t] = q[(long long)b * M + t];
+    __syncthreads();
+    double s = 0.0;
+    if (c < M) {
+        const double apos = posval[(long long)b * M + c];
+        for (int r = ty; r < N; r += GP_TY) {
+            const int t = r * M + c;
+            int lo = 0, hi = M;                              // k = #{k : q_k <= t} (q is non-decreasing)
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (g_q[mid] <= t) lo = mid + 1; else hi = mid; }
+            const int e = t + lo, i = e / M, j = e - i * M;
+            s += clamp_min0(apos - neglogexp(z_at(p, b, i, j, norm)) + p.gamma);
+        }
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < M) {
+#pragma unroll
+        for (int k = 1; k < GP_TY; ++k) s += red[k][tx];
+        colterm[(long long)b * M + c] = 2.0 * log(s + 1.0);
+    }
+}
+
+// fixed-tree sum of n values by one CTA of 256 threads (every thread returns the total)
+DEVINL double block_sum_256(const double* x, int n, double* red) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += x[i];
+    __syncthreads();                                        // red may still be read from a previous call
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    return red[0];
+}
+
+// loss[b] = (mean_i rowterm + mean_c colterm) / 2 (mdgat.py:569, 592-594): one value per pair
+__global__ void __launch_bounds__(256)
+gap_final_kernel(const double* __restrict__ rowterm, const double* __restrict__ colterm, int N, int M, double* __restrict__ loss) {
+    __shared__ double red[256];
+    const int b = blockIdx.x;
+    const double l0 = block_sum_256(rowterm + (long long)b * N, N, red) / (double)N;
+    const double l1 = block_sum_256(colterm + (long long)b * M, M, red) / (double)M;
+    if (threadIdx.x == 0) loss[b] = (l0 + l1) * 0.5;
+}
+
+// 'superglue' loss, per pair: (-sum_i z[i][gt0_i] - sum_{j: gt1_j = -1} z[N][j]) / (#{j: gt1_j = -1} + M); gt = -1 addresses the
+// dustbin column / row as a negative index does in the reference (mdgat.py:493-509). N == M (the caller checks it).
+__global__ void __launch_bounds__(256)
+superglue_loss_kernel(MatchParams p, double norm, double* __restrict__ perpair) {
+    __shared__ double red[256];
+    __shared__ int cnt[256];
+    const int b = blockIdx.x, N = p.N, M = p.M;
+    double tp = 0.0, tn = 0.0;
+    int xx = 0;
+    for (int i = threadIdx.x; i < N; i += 256) {
+        int g = p.gt0[(long long)b * N + i]; if (g < 0) g += M + 1;
+        tp += z_at(p, b, i, g, norm);
+    }
+    for (int j = threadIdx.x; j < M; j += 256)
+        if (p.gt1[(long long)b * M + j] == -1) { tn += z_at(p, b, N, j, norm); ++xx; }
+    red[threadIdx.x] = tp; cnt[threadIdx.x] = xx;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) { red[threadIdx.x] += red[threadIdx.x + o]; cnt[threadIdx.x] += cnt[threadIdx.x + o]; } __syncthreads(); }
+    const double tps = red[0];
+    const int xs = cnt[0];
+    __syncthreads();
+    red[threadIdx.x] = tn;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) perpair[b] = (-tps - red[0]) / (double)(xs + M);
+}
+
 __global__ void __launch_bounds__(256)
 write_Z_kernel(const double* __restrict__ C, const double* __restrict__ u, const double* __restrict__ v,
                double* __restrict__ Z, int N, int M, double norm, long long total) {
@@ -212,6 +343,23 @@ cudaError_t launch_match_extract(const MatchParams& p, cudaStream_t st) {
     match_finalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p, norm, rv1, rv2, ri1, ri2, cv1, cv2, ci1, ci2, terms);
     count_launch(3);
     if (p.loss_mode == MDGAT_LOSS_TRIPLET) { mean_kernel<<<1, 1024, 0, st>>>(terms, tot, p.loss); count_launch(); }
+    if (p.loss_mode == MDGAT_LOSS_GAP) {
+        // after match_finalize the second-best buffers are free: positives' order (q, posval) lives there
+        int* q = ci2;
+        double* posval = cv2;
+        double* rowterm = terms;
+        double* colterm = terms + nrow;
+        gap_rows_kernel<<<rgrid, 256, 0, st>>>(p, norm, rowterm);
+        gap_sort_kernel<<<B, 512, (size_t)M * sizeof(int16_t), st>>>(p, norm, q, posval);
+        gap_cols_kernel<<<cgrid, dim3(32, GP_TY), (size_t)M * sizeof(int), st>>>(p, norm, q, posval, colterm);
+        gap_final_kernel<<<B, 256, 0, st>>>(rowterm, colterm, N, M, p.loss);
+        count_launch(4);
+    }
+    if (p.loss_mode == MDGAT_LOSS_SUPERGLUE) {
+        superglue_loss_kernel<<<B, 256, 0, st>>>(p, norm, terms);
+        mean_kernel<<<1, 1024, 0, st>>>(terms, B, p.loss);
+        count_launch(2);
+    }
     if (p.Z) {
         const long long total = (long long)B * (N + 1) * (M + 1);
         write_Z_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.C, p.u, p.v, p.Z, N, M, norm, total);

@@ -419,11 +419,20 @@ class MDGAT(nn.Module):
                     if N != M:
                         raise IndexError('triplet_loss needs N == M (mdgat.py:537)')
                     loss_mode = _capi.LOSS_TRIPLET
-                    gt0 = gt0_t.to(torch.int16).contiguous()
-                    gt1 = gt1_t.to(torch.int16).contiguous()
+                else:
+                    loss_mode = _capi.LOSS_GAP                    # one value per pair (mdgat.py:592-594)
+                gt0 = gt0_t.to(torch.int16).contiguous()
+                gt1 = gt1_t.to(torch.int16).contiguous()
             elif self.loss_method == 'superglue' and have_gt:
                 gt0_t, gt1_t = self._gt(data)
-            write_Z = self.loss_method in ('gap_loss', 'superglue') or bool(self.config.get('return_assignment', False))
+                if N != M:
+                    raise IndexError('superglue loss needs N == M (mdgat.py:501 indexes an N-shaped mask with M)')
+                loss_mode = _capi.LOSS_SUPERGLUE                  # -1 stays -1: it addresses the dustbin (mdgat.py:493-503)
+                gt0 = gt0_t.to(torch.int16).contiguous()
+                gt1 = gt1_t.to(torch.int16).contiguous()
+            # all three losses and both match variants read (couplings, u, v): Z is only formed when the caller asks for it
+            write_Z = bool(self.config.get('return_assignment', False))
+            nloss = B if loss_mode == _capi.LOSS_GAP else 1
 
             karr = (ctypes.c_int * len(sched))(*sched)
             planes = self.digit_planes()
@@ -447,14 +456,19 @@ class MDGAT(nn.Module):
                 self._workspaces[dev] = ws
 
             def new_outputs():
-                # one buffer: [matches0 | matches1 | scores0 | scores1 | loss | valid count], carved into typed views
+                # one buffer: [matches0 | matches1 | scores0 | scores1 | loss (1, or B for gap_loss) | valid count], carved into typed views
+                ob = torch.zeros(2 * (B * N + B * M) + nloss + 1, dtype=torch.int64, device=dev)
+                return ob, carve(ob)
+
+            def carve(ob):
                 n0, n1 = B * N, B * M
-                ob = torch.zeros(2 * (n0 + n1) + 2, dtype=torch.int64, device=dev)
-                return ob, (ob[:n0].view(B, N), ob[n0:n0 + n1].view(B, M),
-                            ob[n0 + n1:2 * n0 + n1].view(torch.float64).view(B, N),
-                            ob[2 * n0 + n1:2 * (n0 + n1)].view(torch.float64).view(B, M),
-                            ob[2 * (n0 + n1):2 * (n0 + n1) + 1].view(torch.float64).reshape(()),
-                            ob[2 * (n0 + n1) + 1:].view(torch.int32)[0])
+                e = 2 * (n0 + n1)
+                lv = ob[e:e + nloss].view(torch.float64)
+                return (ob[:n0].view(B, N), ob[n0:n0 + n1].view(B, M),
+                        ob[n0 + n1:2 * n0 + n1].view(torch.float64).view(B, N),
+                        ob[2 * n0 + n1:e].view(torch.float64).view(B, M),
+                        lv if loss_mode == _capi.LOSS_GAP else lv.reshape(()),
+                        ob[e + nloss:].view(torch.int32)[0])
 
             def launch(ins, outs, Zt):
                 fin = _capi.ForwardIn(*[t.data_ptr() if t is not None else None for t in ins])
@@ -493,20 +507,12 @@ class MDGAT(nn.Module):
                     self._graphs[key] = ent
                 torch._foreach_copy_(ent[1], [t for t in ins if t is not None])
                 ent[0].replay()
-                n0, n1 = B * N, B * M
-                res = ent[2].clone()
-                matches0, matches1 = res[:n0].view(B, N), res[n0:n0 + n1].view(B, M)
-                ms0 = res[n0 + n1:2 * n0 + n1].view(torch.float64).view(B, N)
-                ms1 = res[2 * n0 + n1:2 * (n0 + n1)].view(torch.float64).view(B, M)
-                loss = res[2 * (n0 + n1):2 * (n0 + n1) + 1].view(torch.float64).reshape(())
-                nvalid = res[2 * (n0 + n1) + 1:].view(torch.int32)[0]
+                matches0, matches1, ms0, ms1, loss, nvalid = carve(ent[2].clone())
             else:
                 _, (matches0, matches1, ms0, ms1, loss, nvalid) = new_outputs()
                 launch(ins, (matches0, matches1, ms0, ms1, loss, nvalid), Z)
-            if self.loss_method == 'gap_loss':
-                loss = losses.gap_loss(Z, gt0_t.long(), gt1_t.long(), self.triplet_loss_gamma)
-            elif self.loss_method == 'superglue':
-                loss = losses.superglue_loss(Z, gt0_t, gt1_t) if have_gt else None
+            if loss_mode == _capi.LOSS_NONE:
+                loss = None
             if self.config.get('strict_degenerate_dtypes', False) and self.loss_method != 'superglue' \
                     and int(nvalid.item()) == 0:
                 # the reference returns int64 zeros when nothing is valid (mdgat.py:465-467)

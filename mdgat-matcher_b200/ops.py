@@ -79,7 +79,7 @@ def attention(q, k, v, topk=None, engine='dmma', slices=7, p_slices=0):
     qh, kh, vh = to_head_major(q, LDH_QK), to_head_major(k, LDH_QK), to_head_major(v, LDH_V)
     out = torch.empty((B * N, LDX), dtype=torch.float64, device=q.device)
     kk = 0 if topk is None else int(topk)
-    logits = torch.empty((B, 4, N, M), dtype=torch.float64, device=q.device) if kk > 0 else None
+    logits = torch.empty(max(B * 4 * N * M, _capi.lib.mdgat_attention_f64_scratch_doubles(B, N, M)), dtype=torch.float64, device=q.device) if kk > 0 else None
     with torch.cuda.device(q.device):
         if engine == 'tcgen05_i8':
             scratch = torch.empty(_capi.lib.mdgat_attention_i8_scratch_bytes(B, N, M), dtype=torch.uint8, device=q.device)
@@ -121,6 +121,8 @@ def sinkhorn(scores, bin_score, iters, fused=True, return_status=False):
 
 def match_extract(C, u, v, loss_method='triplet_loss', mutual_check=False, match_threshold=0.2,
                   gt0=None, gt1=None, gamma=0.5, want_Z=False):
+    """Match extraction (mdgat.py:442-483) and, with gt given, the loss of `loss_method` (mdgat.py:487-594) from the
+    Sinkhorn outputs; 'loss' is a scalar, or (B,) for gap_loss. gt: -1 = no match (triplet / gap also accept M / N)."""
     _need_cuda(C)
     dev = C.device
     B, N, M = C.shape[0], C.shape[1] - 1, C.shape[2] - 1
@@ -128,11 +130,13 @@ def match_extract(C, u, v, loss_method='triplet_loss', mutual_check=False, match
     m1 = torch.empty((B, M), dtype=torch.int64, device=dev)
     s0 = torch.empty((B, N), dtype=torch.float64, device=dev)
     s1 = torch.empty((B, M), dtype=torch.float64, device=dev)
-    loss = torch.zeros((), dtype=torch.float64, device=dev)
+    loss_mode = _capi.LOSS_NONE
+    if gt0 is not None:
+        loss_mode = {'triplet_loss': _capi.LOSS_TRIPLET, 'gap_loss': _capi.LOSS_GAP, 'superglue': _capi.LOSS_SUPERGLUE}[loss_method]
+    loss = torch.zeros((B,) if loss_mode == _capi.LOSS_GAP else (), dtype=torch.float64, device=dev)
     nvalid = torch.zeros((), dtype=torch.int32, device=dev)
     Z = torch.empty_like(C) if want_Z else None
     scratch = torch.empty(_capi.lib.mdgat_match_scratch_doubles(B, N, M), dtype=torch.float64, device=dev)
-    loss_mode = _capi.LOSS_TRIPLET if (loss_method == 'triplet_loss' and gt0 is not None) else _capi.LOSS_NONE
     g0 = gt0.to(torch.int16).contiguous() if gt0 is not None else None
     g1 = gt1.to(torch.int16).contiguous() if gt1 is not None else None
     fout = _capi.ForwardOut(m0.data_ptr(), m1.data_ptr(), s0.data_ptr(), s1.data_ptr(), loss.data_ptr(),

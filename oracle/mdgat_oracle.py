@@ -279,6 +279,21 @@ def gap_loss(Z, gt0, gt1, gamma):
     return (l0 + l1) / 2
 
 
+def superglue_loss(Z, gt0, gt1):
+    """'superglue' loss branch (:487-511); gt arrays keep -1 for "no match", which indexes the dustbin column / row as a
+    negative index does upstream (:493, :503). Needs n == m (:501 masks an (b, n) index tensor with a (b, m) mask)."""
+    b, n = gt0.shape
+    m = gt1.shape[1]
+    if n != m:
+        raise IndexError('superglue loss needs N == M')
+    bi = np.arange(b)[:, None]
+    tp = Z[bi, np.arange(n)[None], gt0].sum(axis=1)                    # :494-495
+    inv = gt1 == -1                                                    # :498-499
+    xx = inv.sum(axis=1)
+    tn = np.array([Z[i, -1, :m][inv[i]].sum() for i in range(b)])      # :501-509: rows gt1 = -1 -> last row
+    return np.mean((-tp - tn) / (xx + m))                              # :510
+
+
 def knn(x, src, k):
     """knn() (:8-15): x (B,3,n), src (B,3,m) -> indices (B,n,k) of the k nearest sources."""
     inner = -2 * np.matmul(x.transpose(0, 2, 1), src)
@@ -359,6 +374,8 @@ def forward(sd, data, cfg, trace=None):
             out['loss'] = triplet_loss(Z, gt0, gt1, gamma)
         else:
             out['loss'] = gap_loss(Z, gt0, gt1, gamma)
+    elif 'gt_matches0' in data and cfg['loss_method'] == 'superglue':
+        out['loss'] = superglue_loss(Z, _np(data['gt_matches0']).astype(np.int64), _np(data['gt_matches1']).astype(np.int64))
     return out
 
 

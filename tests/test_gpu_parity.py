@@ -168,6 +168,31 @@ def test_attention_topk_exact_ties(dev, engine):
     assert np.abs(got - want.reshape(1, 128, N)).max() < ENGINE_TOL[engine]
 
 
+@pytest.mark.parametrize('N,M,topk', [(128, 128, 128), (200, 300, 128), (512, 512, 64), (130, 77, 64), (64, 160, 64)])
+def test_attention_topk_fused_kernel(dev, N, M, topk):
+    """dynamic_attention() in one persistent kernel (debug flag 0x20000 / MDGAT_TOPK_FUSED=1: DMMA logits producers and
+    selection consumers share a per-CTA ring) against the oracle and, bit for bit, against the two-launch default; the
+    last shape has an exact twin for every column (ties at the k-th value)."""
+    from mdgat_matcher_b200 import ops, _capi
+    from oracle import mdgat_oracle as O
+    rng = np.random.default_rng(3 * N + M + topk)
+    q = rng.normal(size=(3, 128, N)) * 2; k = rng.normal(size=(3, 128, M)) * 2; v = rng.normal(size=(3, 128, M))
+    if M == 160:
+        k[:, :, 80:] = k[:, :, :80]; v[:, :, 80:] = v[:, :, :80]
+    want, _ = O.dynamic_attention(q.reshape(3, 32, 4, N), k.reshape(3, 32, 4, M), v.reshape(3, 32, 4, M), topk)
+    ref = ops.attention(_t(q, dev), _t(k, dev), _t(v, dev), topk=topk, engine='dmma')
+    _capi.check(_capi.lib.mdgat_debug_flags(0x20000))
+    try:
+        n0 = _capi.lib.mdgat_launch_count()
+        got = ops.attention(_t(q, dev), _t(k, dev), _t(v, dev), topk=topk, engine='dmma')
+        torch.cuda.synchronize()
+        assert _capi.lib.mdgat_launch_count() - n0 == 1            # the one-kernel variant ran (two launches otherwise)
+    finally:
+        _capi.check(_capi.lib.mdgat_debug_flags(0))
+    assert np.abs(got.cpu().numpy() - want.reshape(3, 128, N)).max() < ENGINE_TOL['dmma']
+    assert torch.equal(got, ref)
+
+
 def test_attention_topk_k_out_of_range(dev):
     from mdgat_matcher_b200 import ops, _capi
     q = torch.zeros((1, 128, 16), device=dev, dtype=torch.float64)
@@ -247,6 +272,45 @@ def test_match_extract_vs_oracle(dev, loss_method, mutual):
     if loss_method == 'triplet_loss':
         g0 = np.where(gt0 < 0, M, gt0).astype(np.int64); g1 = np.where(gt1 < 0, N, gt1).astype(np.int64)
         assert abs(float(got['loss'].item()) - O.triplet_loss(Z, g0, g1, 0.5)) < 1e-12
+
+
+@pytest.mark.parametrize('N,M', [(150, 150), (200, 77), (64, 300)])
+def test_gap_loss_on_device_vs_oracle(dev, N, M):
+    """gap_loss (mdgat.py:547-594) from (couplings, u, v), Z never formed: one value per pair, including the reference's
+    row-major pairing of positives and negatives in the pc1 -> pc0 direction (visible whenever gt1 is not sorted)."""
+    from mdgat_matcher_b200 import ops
+    from oracle import mdgat_oracle as O
+    rng = np.random.default_rng(N + 3 * M)
+    B = 3
+    scores = rng.normal(size=(B, N, M)) * 4
+    C, u, v = ops.sinkhorn(_t(scores, dev), 1.0, 30)
+    gt0 = rng.integers(-1, M, size=(B, N)).astype(np.int16)
+    gt1 = rng.integers(-1, N, size=(B, M)).astype(np.int16)
+    gt1[0] = -1                                              # a pair with no match at all: every positive in the dustbin row
+    got = ops.match_extract(C, u, v, 'gap_loss', False, 0.2, _t(gt0, dev), _t(gt1, dev), 0.5, want_Z=True)
+    Z = got['Z'].cpu().numpy()
+    g0 = np.where(gt0 < 0, M, gt0).astype(np.int64); g1 = np.where(gt1 < 0, N, gt1).astype(np.int64)
+    want = O.gap_loss(Z, g0, g1, 0.5)
+    assert got['loss'].shape == (B,)
+    assert np.abs(got['loss'].cpu().numpy() - want).max() < 1e-11
+    # the already remapped form (what MDGAT.forward passes after mdgat.py:554-555) gives the same bits
+    again = ops.match_extract(C, u, v, 'gap_loss', False, 0.2, _t(g0.astype(np.int16), dev), _t(g1.astype(np.int16), dev), 0.5)
+    assert torch.equal(again['loss'], got['loss'])
+
+
+def test_superglue_loss_on_device_vs_oracle(dev):
+    from mdgat_matcher_b200 import ops
+    from oracle import mdgat_oracle as O
+    rng = np.random.default_rng(21)
+    B, N = 4, 130
+    scores = rng.normal(size=(B, N, N)) * 3
+    C, u, v = ops.sinkhorn(_t(scores, dev), 1.3, 25)
+    gt0 = rng.integers(-1, N, size=(B, N)).astype(np.int16)
+    gt1 = rng.integers(-1, N, size=(B, N)).astype(np.int16)
+    gt1[1] = -1; gt1[2] = 5
+    got = ops.match_extract(C, u, v, 'superglue', True, 0.2, _t(gt0, dev), _t(gt1, dev), 0.5, want_Z=True)
+    want = O.superglue_loss(got['Z'].cpu().numpy(), gt0.astype(np.int64), gt1.astype(np.int64))
+    assert abs(float(got['loss'].item()) - want) < 1e-12
 
 
 def test_knn_vs_oracle(dev):

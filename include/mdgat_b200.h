@@ -96,6 +96,8 @@ typedef struct {
     int attn_slices;          /* int8 digit planes (8 bits each) of q, k, v in the tcgen05 attention: 4..7 (0 = 7) */
     int attn_p_slices;        /* byte planes of the softmax probabilities: (attn_slices, attn_p_slices) must be one of
                                  (4,3) (4,4) (5,4) (6,5) (7,6); 0 = attn_slices - 1 */
+    int sinkhorn_k32;         /* 1: the Sinkhorn kernel matrix exp(C_ij - max_j C_ij) is STORED in float32 (every sum,
+                                 division and potential stays float64; potentials move by O(1e-7)); 0: float64 storage */
 } mdgat_forward_cfg;
 
 typedef struct {
@@ -189,6 +191,9 @@ size_t mdgat_sinkhorn_scratch_doubles(int B, int N, int M);
 int mdgat_sinkhorn_read_status(const double* d_scratch, int B, int N, int M, int* h_flags, int* h_iters);
 int mdgat_sinkhorn_f64(double* d_couplings, const double* d_bin_score, double* d_u, double* d_v,
                        int B, int N, int M, int iters, double* d_scratch, void* stream);
+/* Same contract (d_scratch required) with the kernel matrix stored in float32, float64 arithmetic (mdgat_forward_cfg.sinkhorn_k32). */
+int mdgat_sinkhorn_f64_k32(double* d_couplings, const double* d_bin_score, double* d_u, double* d_v,
+                           int B, int N, int M, int iters, double* d_scratch, void* stream);
 
 /* Match extraction + optional loss (MDGAT_LOSS_*) from (couplings, u, v) (mdgat.py:442-483, 487-594); Z is never formed. */
 int mdgat_match_extract(const double* d_couplings, const double* d_u, const double* d_v,

@@ -26,7 +26,7 @@ class ForwardCfg(C.Structure):
                 ('loss_mode', C.c_int), ('triplet_gamma', C.c_double),
                 ('in_dtype', C.c_int), ('score_dtype', C.c_int), ('write_Z', C.c_int),
                 ('gemm_mode', C.c_int), ('gemm_slices', C.c_int), ('attn_mode', C.c_int),
-                ('attn_slices', C.c_int), ('attn_p_slices', C.c_int)]
+                ('attn_slices', C.c_int), ('attn_p_slices', C.c_int), ('sinkhorn_k32', C.c_int)]
 
 
 class ForwardIn(C.Structure):
@@ -67,6 +67,7 @@ def _load():
         'mdgat_sinkhorn_scratch_doubles': (sz, [i, i, i]),
         'mdgat_sinkhorn_read_status': (i, [vp, i, i, i, C.POINTER(i), C.POINTER(i)]),
         'mdgat_sinkhorn_f64': (i, [vp, vp, vp, vp, i, i, i, i, vp, vp]),
+        'mdgat_sinkhorn_f64_k32': (i, [vp, vp, vp, vp, i, i, i, i, vp, vp]),
         'mdgat_match_scratch_doubles': (sz, [i, i, i]),
         'mdgat_match_extract': (i, [vp, vp, vp, i, i, i, i, i, d, i, d, vp, vp, C.POINTER(ForwardOut), vp, vp]),
         'mdgat_knn': (i, [vp, vp, vp, i, i, i, i, vp]),

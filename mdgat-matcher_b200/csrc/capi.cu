@@ -101,6 +101,7 @@ struct Workspace {
     double *tkthr, *tkmax; int* tkjl;                   // tcgen05 top-k layers: per (b, h, row) threshold, maximum, last tied column
     double *rsX, *rsM, *rsH; int8_t *xsX, *xsM, *xsH;   // tcgen05 path: int8 slice planes + row scales of X, Msg, Hd (2 chunks)
     AttnI8Side ai[2];                                   // tcgen05 attention: digit planes of q/k/v of side 0 / side 1
+    int* bad;                                          // per pair: non-finite input seen
     size_t bytes, S_doubles;
 };
 
@@ -135,6 +136,7 @@ Workspace carve(char* base, int B, int N, int M, bool need_logits, int i8_slices
     w.u = take((size_t)B * (N + 1));
     w.v = take((size_t)B * (M + 1));
     w.mscratch = take(4 * R + 8);
+    w.bad = reinterpret_cast<int*>(take((size_t)(B + 1) / 2 + 1));
     w.skscratch = take(sinkhorn_scratch_doubles(B, N, M));
     w.tkthr = take(need_logits && attn_i8 ? R * HEADS : 0);
     w.tkmax = take(need_logits && attn_i8 ? R * HEADS : 0);
@@ -231,10 +233,10 @@ cudaError_t attention_layer(const AttnSides& ps, int B, int nsides, int ldo, int
 
 cudaError_t encode(const mdgat_forward_in* in, int B, int N, int M, int in_dtype, int score_dtype,
                    const double* Wt, const BlobLayout& lay, double* X, double* Xk, double* Xd,
-                   double* T0, double* T1, double* T2, int ldt2, cudaStream_t st) {
+                   double* T0, double* T1, double* T2, int ldt2, cudaStream_t st, int* bad = nullptr) {
     const int R = B * N + B * M;
     cudaError_t e = launch_pack_inputs(in->d_kpts0, in->d_kpts1, in->d_desc0, in->d_desc1, in->d_scores0,
-                                       in->d_scores1, in_dtype, score_dtype, B, N, M, Xk, Xd, st);
+                                       in->d_scores1, in_dtype, score_dtype, B, N, M, Xk, Xd, bad, st);
     if (e != cudaSuccess) return e;
     // KeypointEncoder: 4 -> 32 -> 64 -> 128 -> 128 (mdgat.py:181), BN folded, ReLU on the first three
     if ((e = linear(Xk, 4, 4, nullptr, 0, 0, Wt + lay.kenc.w[0], 4, Wt + lay.kenc.b[0], nullptr, 0, T0, LDX, R, 32, 1.0, 1, st))) return e;
@@ -252,7 +254,7 @@ cudaError_t encode(const mdgat_forward_in* in, int B, int N, int M, int in_dtype
 extern "C" {
 
 const char* mdgat_last_error(void) { return mdgat_host::g_err; }
-int mdgat_abi_version(void) { return 2; }
+int mdgat_abi_version(void) { return 3; }
 
 size_t mdgat_weight_blob_doubles(int L) { return BlobLayout(L).total; }
 
@@ -311,7 +313,7 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
     const int R0 = B * N, R1 = B * M, R = R0 + R1;
 
     prof_mark(ST_ENCODE, st);
-    MDGAT_CUDA_OK(encode(in, B, N, M, cfg->in_dtype, cfg->score_dtype, Wt, lay, w.X, w.Xk, w.Xd, w.Msg, w.Mg, w.Hd, LDHID, st));
+    MDGAT_CUDA_OK(encode(in, B, N, M, cfg->in_dtype, cfg->score_dtype, Wt, lay, w.X, w.Xk, w.Xd, w.Msg, w.Mg, w.Hd, LDHID, st, w.bad));
 
     // head-major buffers: side 0 occupies the first R0*4 rows, side 1 the rest
     const double* Q0 = w.Qh; const double* Q1 = w.Qh + (size_t)R0 * HEADS * LDH_QK;
@@ -418,7 +420,7 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
                           w.C, M + 1, (long long)(N + 1) * (M + 1), N, M, DMODEL, B, 1.0 / sqrt((double)DMODEL), st));
     prof_mark(ST_SINKHORN, st);
     MDGAT_CUDA_OK(launch_fill_dustbin(w.C, Wt + lay.bin, B, N, M, st));
-    MDGAT_CUDA_OK(launch_sinkhorn_fused(w.C, w.u, w.v, w.skscratch, B, N, M, cfg->sinkhorn_iters, st));
+    MDGAT_CUDA_OK(launch_sinkhorn_fused(w.C, w.u, w.v, w.skscratch, B, N, M, cfg->sinkhorn_iters, st, cfg->sinkhorn_k32 != 0));
     prof_mark(ST_MATCH, st);
 
     MatchParams mp;
@@ -428,7 +430,7 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
     mp.loss_mode = cfg->loss_mode; mp.gamma = cfg->triplet_gamma; mp.gt0 = in->d_gt0; mp.gt1 = in->d_gt1;
     mp.matches0 = out->d_matches0; mp.matches1 = out->d_matches1; mp.ms0 = out->d_mscores0; mp.ms1 = out->d_mscores1;
     mp.loss = out->d_loss; mp.nvalid0 = out->d_nvalid0; mp.Z = cfg->write_Z ? out->d_Z : nullptr;
-    mp.scratch = w.mscratch;
+    mp.scratch = w.mscratch; mp.bad = w.bad;
     MDGAT_CUDA_OK(launch_match_extract(mp, st));
     prof_mark(ST_COUNT, st);
     return MDGAT_OK;
@@ -557,6 +559,16 @@ int mdgat_sinkhorn_f64(double* d_couplings, const double* d_bin_score, double* d
     MDGAT_CUDA_OK(launch_fill_dustbin(d_couplings, d_bin_score, B, N, M, st));
     if (d_scratch) MDGAT_CUDA_OK(launch_sinkhorn_fused(d_couplings, d_u, d_v, d_scratch, B, N, M, iters, st));
     else MDGAT_CUDA_OK(launch_sinkhorn(d_couplings, d_u, d_v, B, N, M, iters, st));
+    return MDGAT_OK;
+}
+
+int mdgat_sinkhorn_f64_k32(double* d_couplings, const double* d_bin_score, double* d_u, double* d_v,
+                       int B, int N, int M, int iters, double* d_scratch, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    MDGAT_REQUIRE(B > 0 && N > 0 && M > 0 && iters >= 0, "mdgat_sinkhorn_f64_k32: bad shape");
+    MDGAT_CUDA_OK(launch_fill_dustbin(d_couplings, d_bin_score, B, N, M, st));
+    MDGAT_REQUIRE(d_scratch != nullptr, "mdgat_sinkhorn_f64_k32: the fused kernel needs its scratch (mdgat_sinkhorn_scratch_doubles)");
+    MDGAT_CUDA_OK(launch_sinkhorn_fused(d_couplings, d_u, d_v, d_scratch, B, N, M, iters, st, true));
     return MDGAT_OK;
 }
 

@@ -62,15 +62,16 @@ cudaError_t launch_topk_threshold(const double* S, double* thr, int* jlast, doub
 // Encoder input staging: Xk (R x 4) = [x,y,z,score], Xd (R x 36) = [33 desc | 0 0 0]
 cudaError_t launch_pack_inputs(const void* kpts0, const void* kpts1, const void* desc0, const void* desc1,
                                const void* sc0, const void* sc1, int in_dtype, int score_dtype,
-                               int B, int N, int M, double* Xk, double* Xd, cudaStream_t st);
+                               int B, int N, int M, double* Xk, double* Xd, int* bad, cudaStream_t st);
 
 // Sinkhorn (general, global-memory resident couplings)
 cudaError_t launch_fill_dustbin(double* C, const double* bin_score, int B, int N, int M, cudaStream_t st);
 cudaError_t launch_sinkhorn(const double* C, double* u, double* v, int B, int N, int M, int iters, cudaStream_t st);
 // Fused: one launch, one 8-CTA cluster per pair, kernel matrix in distributed shared memory.
 size_t sinkhorn_scratch_doubles(int B, int N, int M);
+// k32: kernel matrix stored in float32 (sums and potentials in float64), see sinkhorn_fused32_kernel
 cudaError_t launch_sinkhorn_fused(const double* C, double* u, double* v, double* scratch, int B, int N, int M,
-                                  int iters, cudaStream_t st);
+                                  int iters, cudaStream_t st, bool k32 = false);
 
 struct MatchParams {
     const double* C; const double* u; const double* v;
@@ -81,6 +82,7 @@ struct MatchParams {
     int64_t* matches0; int64_t* matches1; double* ms0; double* ms1;
     double* loss; int* nvalid0; double* Z;
     double* scratch;
+    const int* bad;                 // per pair: an input was NaN / Inf (launch_pack_inputs), or nullptr
 };
 cudaError_t launch_match_extract(const MatchParams& p, cudaStream_t st);
 

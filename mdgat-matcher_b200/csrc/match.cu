@@ -89,6 +89,25 @@ match_finalize_kernel(MatchParams p, double norm,
     const long long nrow = (long long)p.B * N, ncol = (long long)p.B * M;
     if (t >= nrow + ncol) return;
     const bool thr_mode = p.match_mode == MDGAT_MATCH_THRESHOLD;
+    if (p.bad != nullptr) {
+        // A pair with a NaN / Inf input has an all-NaN assignment matrix in the reference: max() returns NaN with index 0 for
+        // every row and column, so (mdgat.py:442-483) the dustbin variant reports match 0 everywhere with score NaN (with the
+        // mutual check only row / column 0 is mutual, the other scores are 0), the threshold variant rejects everything
+        // (NaN > threshold is false; with the mutual check score NaN at index 0), and every loss is NaN.
+        const bool row = t < nrow;
+        const long long c = row ? t : t - nrow;
+        const int b = (int)(c / (row ? N : M)), i = (int)(c - (long long)b * (row ? N : M));
+        if (p.bad[b]) {
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            int64_t* mo = row ? p.matches0 : p.matches1;
+            double* so = row ? p.ms0 : p.ms1;
+            mo[c] = thr_mode ? (int64_t)-1 : (int64_t)0;
+            so[c] = thr_mode ? ((p.mutual_check && i == 0) ? nan : 0.0) : ((!p.mutual_check || i == 0) ? nan : 0.0);
+            if (row && !thr_mode) atomicAdd(p.nvalid0, 1);
+            if (p.loss_mode == MDGAT_LOSS_TRIPLET) terms[(long long)b * (N + M) + (row ? 0 : N) + i] = nan;
+            return;
+        }
+    }
     if (t < nrow) {
         const int b = (int)(t / N), i = (int)(t - (long long)b * N);
         const int idx = ri1[t];
@@ -271,9 +290,11 @@ DEVINL double block_sum_256(const double* x, int n, double* red) {
 
 // loss[b] = (mean_i rowterm + mean_c colterm) / 2 (mdgat.py:569, 592-594): one value per pair
 __global__ void __launch_bounds__(256)
-gap_final_kernel(const double* __restrict__ rowterm, const double* __restrict__ colterm, int N, int M, double* __restrict__ loss) {
+gap_final_kernel(const double* __restrict__ rowterm, const double* __restrict__ colterm, int N, int M, double* __restrict__ loss,
+                 const int* __restrict__ bad) {
     __shared__ double red[256];
     const int b = blockIdx.x;
+    if (bad != nullptr && bad[b]) { if (threadIdx.x == 0) loss[b] = __longlong_as_double(0x7ff8000000000000LL); return; }
     const double l0 = block_sum_256(rowterm + (long long)b * N, N, red) / (double)N;
     const double l1 = block_sum_256(colterm + (long long)b * M, M, red) / (double)M;
     if (threadIdx.x == 0) loss[b] = (l0 + l1) * 0.5;
@@ -303,7 +324,7 @@ superglue_loss_kernel(MatchParams p, double norm, double* __restrict__ perpair) 
     red[threadIdx.x] = tn;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
-    if (threadIdx.x == 0) perpair[b] = (-tps - red[0]) / (double)(xs + M);
+    if (threadIdx.x == 0) perpair[b] = (p.bad != nullptr && p.bad[b]) ? __longlong_as_double(0x7ff8000000000000LL) : (-tps - red[0]) / (double)(xs + M);
 }
 
 __global__ void __launch_bounds__(256)
@@ -352,7 +373,7 @@ cudaError_t launch_match_extract(const MatchParams& p, cudaStream_t st) {
         gap_rows_kernel<<<rgrid, 256, 0, st>>>(p, norm, rowterm);
         gap_sort_kernel<<<B, 512, (size_t)M * sizeof(int16_t), st>>>(p, norm, q, posval);
         gap_cols_kernel<<<cgrid, dim3(32, GP_TY), (size_t)M * sizeof(int), st>>>(p, norm, q, posval, colterm);
-        gap_final_kernel<<<B, 256, 0, st>>>(rowterm, colterm, N, M, p.loss);
+        gap_final_kernel<<<B, 256, 0, st>>>(rowterm, colterm, N, M, p.loss, p.bad);
         count_launch(4);
     }
     if (p.loss_mode == MDGAT_LOSS_SUPERGLUE) {

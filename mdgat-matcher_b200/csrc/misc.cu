@@ -16,30 +16,39 @@ DEVINL double load_as_f64(const void* p, long long i, int dtype) {
 __global__ void __launch_bounds__(256)
 pack_inputs_kernel(const void* kp0, const void* kp1, const void* de0, const void* de1,
                    const void* sc0, const void* sc1, int in_dtype, int score_dtype,
-                   long long rows0, long long rows, double* __restrict__ Xk, double* __restrict__ Xd) {
+                   long long rows0, long long rows, int N, int M, double* __restrict__ Xk, double* __restrict__ Xd,
+                   int* __restrict__ bad) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long r = t / 40;
     const int c = (int)(t - r * 40);
     if (r >= rows) return;
     const bool s1 = r >= rows0;
     const long long rr = s1 ? r - rows0 : r;
-    if (c < 36) {
-        Xd[r * 36 + c] = c < MDGAT_DESC_IN ? load_as_f64(s1 ? de1 : de0, rr * MDGAT_DESC_IN + c, in_dtype) : 0.0;
-    } else {
-        const int k = c - 36;
-        Xk[r * 4 + k] = k < 3 ? load_as_f64(s1 ? kp1 : kp0, rr * 3 + k, in_dtype)
-                              : load_as_f64(s1 ? sc1 : sc0, rr, score_dtype);
-    }
+    const int k = c - 36;
+    double x;
+    if (c < 36) x = c < MDGAT_DESC_IN ? load_as_f64(s1 ? de1 : de0, rr * MDGAT_DESC_IN + c, in_dtype) : 0.0;
+    else x = k < 3 ? load_as_f64(s1 ? kp1 : kp0, rr * 3 + k, in_dtype) : load_as_f64(s1 ? sc1 : sc0, rr, score_dtype);
+    // A NaN / Inf input (e.g. a zero-norm FPFH row, load_data.py:290) turns the whole pair into NaN in the reference after
+    // two layers. The integer digit planes cannot carry a NaN and the selection kernels assume ordered logits, so the pair
+    // is flagged here, computed on a zero in place of the bad value, and match extraction emits what the reference's
+    // all-NaN assignment matrix yields (match.cu). bad == nullptr (mdgat_encode): values pass through unchanged.
+    if (bad != nullptr && !(fabs(x) <= 1.79769313486231570815e308)) { atomicOr(bad + (int)(rr / (s1 ? M : N)), 1); x = 0.0; }
+    if (c < 36) Xd[r * 36 + c] = x;
+    else Xk[r * 4 + k] = x;
 }
 
 cudaError_t launch_pack_inputs(const void* kpts0, const void* kpts1, const void* desc0, const void* desc1,
                                const void* sc0, const void* sc1, int in_dtype, int score_dtype,
-                               int B, int N, int M, double* Xk, double* Xd, cudaStream_t st) {
+                               int B, int N, int M, double* Xk, double* Xd, int* bad, cudaStream_t st) {
     const long long rows0 = (long long)B * N, rows = rows0 + (long long)B * M;
     if (rows == 0) return cudaSuccess;
+    if (bad != nullptr) {
+        const cudaError_t e = cudaMemsetAsync(bad, 0, sizeof(int) * (size_t)B, st);
+        if (e != cudaSuccess) return e;
+    }
     const long long total = rows * 40;
     pack_inputs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(kpts0, kpts1, desc0, desc1, sc0, sc1,
-                                                                      in_dtype, score_dtype, rows0, rows, Xk, Xd);
+                                                                      in_dtype, score_dtype, rows0, rows, N, M, Xk, Xd, bad);
     count_launch();
     return cudaGetLastError();
 }

@@ -315,6 +315,195 @@ sinkhorn_fused_kernel(const double* __restrict__ C, double* __restrict__ Kg, dou
         for (int j = tid; j < C1; j += SKF_THREADS) v_out[(long long)b * C1 + j] = iters > 0 ? log(bs[j]) : 0.0;
 }
 
+// ------------------------------------------------------------------------------------------
+// The same scaling iteration with the kernel matrix STORED in float32 and every sum, division and potential in float64.
+//
+// The fused kernel above is bound by the shared-memory wavefronts of its two sweeps over K per iteration (ncu: 6400
+// wavefronts per iteration and CTA against 8250 cycles). K_ij = exp(C_ij - c_i) in (e^-80, 1] rounded to float32 (relative
+// error <= 2^-24) is the exact kernel of the couplings C'_ij = C_ij + log(1 + d_ij), |d_ij| <= 6e-8, and the Sinkhorn map is
+// non-expansive in the log domain, so u and v move by O(1e-7): three orders of magnitude inside the 1e-4 score bar, and
+// SURVEY.md 7.3 measured the whole tail as float32-safe. Exact ties stay exact ties (equal doubles round to equal floats).
+// A float row is 2 KB at M = 512: all 65 rows of a CTA fit in shared memory (no register tier), half the wavefronts per
+// sweep; at N = 2048 the rows that stream from L2 / HBM are half the bytes. float -> double runs on the integer pipe
+// (two IMADs build the double's words; cvt.f64.f32 would sit on the 16-lane conversion pipe), valid for normal positive
+// floats -- guaranteed by the range bound SK32_MAX_RANGE, pairs beyond it go to the log-domain fallback like before.
+// config['precision'] = 'exact' keeps the float64 kernel matrix.
+// ------------------------------------------------------------------------------------------
+constexpr double SK32_MAX_RANGE = 80.0;
+DEVINL double f32bits_to_f64(uint32_t f) {
+    uint32_t hi;
+    asm("mad.hi.u32 %0, %1, 0x20000000, 0x38000000;" : "=r"(hi) : "r"(f));     // (f >> 3) + ((1023 - 127) << 20)
+    return __hiloint2double((int)hi, (int)(f << 29));
+}
+
+__global__ void __launch_bounds__(SKF_THREADS, 1)
+sinkhorn_fused32_kernel(const double* __restrict__ C, float* __restrict__ Kg, double* __restrict__ u_out,
+                        double* __restrict__ v_out, int* __restrict__ flags, int N, int M, int iters,
+                        int RS, int rows_smem, int ldk) {
+    extern __shared__ __align__(16) double sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    const int b = blockIdx.x / SKF_CLUSTER;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int R1 = N + 1, C1 = M + 1;
+    const double mu_reg = 1.0 / (double)(N + M), mu_bin = (double)M / (double)(N + M);
+    const double nu_reg = mu_reg, nu_bin = (double)N / (double)(N + M);
+
+    const int ldv = (C1 + 1) & ~1, RSp = (RS + 3) & ~3;
+    double* bs = sm;                        // [ldv]    b_j
+    double* part = bs + ldv;                // [2][ldv] column partials of this CTA (peers read them)
+    double* as = part + 2 * ldv;            // [RSp]    a_i of own rows
+    double* cmx = as + RSp;                 // [RSp]    row maxima of C
+    double* kd = cmx + RSp;                 // [RSp]    K of the dustbin column (float64: one scalar per row)
+    int* chg = reinterpret_cast<int*>(kd + RSp);                    // [8] "changed" flags of the cluster
+    uint32_t* Ks = reinterpret_cast<uint32_t*>(kd + RSp + 4);       // [rows_smem][ldk] float bit patterns
+
+    const int r0 = crank * RS;
+    const int nrows = max(0, min(RS, R1 - r0));
+    const int n_smem = min(nrows, rows_smem);
+    const double* Cb = C + (long long)b * R1 * C1;
+    uint32_t* Kb = reinterpret_cast<uint32_t*>(Kg) + (long long)b * R1 * ldk;
+    const int Me = M & ~1;                   // columns taken two at a time; an odd last column separately
+
+    // ---- setup: row maxima, range check, K rows
+    for (int r = tid; r < RSp; r += SKF_THREADS) { as[r] = 0.0; kd[r] = 0.0; cmx[r] = 0.0; }
+    __syncthreads();
+    int bad = 0;
+    for (int r = warp; r < nrows; r += SKF_WARPS) {
+        const double* crow = Cb + (long long)(r0 + r) * C1;
+        double mx = -INFINITY, mn = INFINITY;
+        for (int j = lane; j < C1; j += 32) { const double c = crow[j]; mx = fmax(mx, c); mn = fmin(mn, c); }
+        mx = warp_max_d(mx);
+        mn = -warp_max_d(-mn);
+        if (!(mx - mn < SK32_MAX_RANGE)) bad = 1;          // also catches NaN / inf
+        uint32_t* krow = r < n_smem ? Ks + (size_t)r * ldk : Kb + (long long)(r0 + r) * ldk;
+        for (int j = lane; j < M; j += 32) krow[j] = __float_as_uint(__double2float_rn(exp(crow[j] - mx)));
+        if (lane == 0) { cmx[r] = mx; kd[r] = exp(crow[M] - mx); }
+    }
+    if (bad && lane == 0) atomicOr(flags + b, 1);
+    for (int j = tid; j < ldv; j += SKF_THREADS) bs[j] = j < C1 ? 1.0 : 0.0;      // v = 0 before the first row pass
+    __syncthreads();
+
+    int it_done = 0;
+    for (int it = 0; it < iters; ++it) {
+        const int buf = it & 1;
+        const double bM = bs[M];
+        // ---- row sums s_r = sum_j K_rj b_j, then a_r = mu_r / s_r: a warp takes four rows at a time, a lane two columns
+        for (int rb = warp * 4; rb < nrows; rb += SKF_WARPS * 4) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            if (rb + 3 < n_smem) {
+                const uint32_t* k0 = Ks + (size_t)rb * ldk;
+#pragma unroll 4
+                for (int j = 2 * lane; j < Me; j += 64) {
+                    const double2 bj = *reinterpret_cast<const double2*>(bs + j);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint2 k = *reinterpret_cast<const uint2*>(k0 + (size_t)q * ldk + j);
+                        acc[q] = fma(f32bits_to_f64(k.x), bj.x, acc[q]);
+                        acc[q] = fma(f32bits_to_f64(k.y), bj.y, acc[q]);
+                    }
+                }
+                if (Me < M && lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q] = fma(f32bits_to_f64(k0[(size_t)q * ldk + Me]), bs[Me], acc[q]);
+                }
+            } else {
+                const uint32_t* kr[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = min(rb + q, nrows - 1);
+                    kr[q] = r < n_smem ? Ks + (size_t)r * ldk : Kb + (long long)(r0 + r) * ldk;
+                }
+#pragma unroll 2
+                for (int j = 2 * lane; j < Me; j += 64) {
+                    const double2 bj = *reinterpret_cast<const double2*>(bs + j);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint2 k = *reinterpret_cast<const uint2*>(kr[q] + j);
+                        acc[q] = fma(f32bits_to_f64(k.x), bj.x, acc[q]);
+                        acc[q] = fma(f32bits_to_f64(k.y), bj.y, acc[q]);
+                    }
+                }
+                if (Me < M && lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q] = fma(f32bits_to_f64(kr[q][Me]), bs[Me], acc[q]);
+                }
+            }
+            warp_transpose_sum<4>(acc, lane);
+            const int r = rb + (lane >> 3);
+            if ((lane & 7) == 0 && r < nrows) as[r] = ((r0 + r < N) ? mu_reg : mu_bin) / fma(kd[r], bM, acc[0]);
+        }
+        __syncthreads();
+        // ---- partial column sums over own rows: part_j = sum_r K_rj a_r
+        double* pb = part + buf * ldv;
+        for (int j = tid; j < M; j += SKF_THREADS) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int r = 0;
+            for (; r + 3 < n_smem; r += 4) {
+                const double2 w01 = *reinterpret_cast<const double2*>(as + r);
+                const double2 w23 = *reinterpret_cast<const double2*>(as + r + 2);
+                a0 = fma(f32bits_to_f64(Ks[(size_t)r * ldk + j]), w01.x, a0);
+                a1 = fma(f32bits_to_f64(Ks[(size_t)(r + 1) * ldk + j]), w01.y, a1);
+                a2 = fma(f32bits_to_f64(Ks[(size_t)(r + 2) * ldk + j]), w23.x, a2);
+                a3 = fma(f32bits_to_f64(Ks[(size_t)(r + 3) * ldk + j]), w23.y, a3);
+            }
+            for (; r < n_smem; ++r) a0 = fma(f32bits_to_f64(Ks[(size_t)r * ldk + j]), as[r], a0);
+            for (; r + 3 < nrows; r += 4) {
+                const uint32_t* kp = Kb + (long long)(r0 + r) * ldk + j;
+                const uint32_t k0 = kp[0], k1 = kp[ldk], k2 = kp[2 * (size_t)ldk], k3 = kp[3 * (size_t)ldk];
+                a0 = fma(f32bits_to_f64(k0), as[r], a0);
+                a1 = fma(f32bits_to_f64(k1), as[r + 1], a1);
+                a2 = fma(f32bits_to_f64(k2), as[r + 2], a2);
+                a3 = fma(f32bits_to_f64(k3), as[r + 3], a3);
+            }
+            for (; r < nrows; ++r) a2 = fma(f32bits_to_f64(Kb[(long long)(r0 + r) * ldk + j]), as[r], a2);
+            pb[j] = (a0 + a1) + (a2 + a3);
+        }
+        if (warp == SKF_WARPS - 1) {                    // dustbin column
+            double a = 0.0;
+            for (int r = lane; r < nrows; r += 32) a = fma(kd[r], as[r], a);
+            a = warp_sum_d(a);
+            if (lane == 0) pb[M] = a;
+        }
+        cluster.sync();
+        // ---- reduce-scatter + broadcast through distributed shared memory (as in the float64 kernel)
+        bool changed = false;
+        {
+            const int CS = (C1 + SKF_CLUSTER - 1) / SKF_CLUSTER;
+            const int c0 = crank * CS;
+            const int ncols = max(0, min(CS, C1 - c0));
+            const int src = tid & (SKF_CLUSTER - 1);
+            for (int base = 0; base < ncols * SKF_CLUSTER; base += SKF_THREADS) {
+                const int idx = base + tid;
+                const int j = c0 + (idx >> 3);
+                const bool ok = idx < ncols * SKF_CLUSTER;
+                const double old = ok ? bs[j] : 0.0;
+                double pv = ok ? cluster.map_shared_rank(part, src)[buf * ldv + j] : 0.0;
+                pv += shfl_xor_d(pv, 1);
+                pv += shfl_xor_d(pv, 2);
+                pv += shfl_xor_d(pv, 4);
+                if (ok) {
+                    const double nb = ((j < M) ? nu_reg : nu_bin) / pv;
+                    changed |= (__double_as_longlong(nb) != __double_as_longlong(old));
+                    cluster.map_shared_rank(bs, src)[j] = nb;
+                }
+            }
+        }
+        const int any_local = __syncthreads_or(changed ? 1 : 0);
+        if (tid < SKF_CLUSTER) cluster.map_shared_rank(chg, tid)[crank] = any_local;
+        cluster.sync();
+        ++it_done;
+        int any = 0;
+#pragma unroll
+        for (int c = 0; c < SKF_CLUSTER; ++c) any |= chg[c];
+        if (!any) break;
+    }
+    if (crank == 0 && tid == 0) flags[gridDim.x / SKF_CLUSTER + b] = it_done;
+    for (int r = tid; r < nrows; r += SKF_THREADS) u_out[(long long)b * R1 + r0 + r] = iters > 0 ? log(as[r]) - cmx[r] : 0.0;
+    if (crank == 0)
+        for (int j = tid; j < C1; j += SKF_THREADS) v_out[(long long)b * C1 + j] = iters > 0 ? log(bs[j]) : 0.0;
+}
+
 // Plain log-domain Sinkhorn for flagged pairs: one CTA per pair, exact max subtraction.
 __global__ void __launch_bounds__(1024)
 sinkhorn_safe_kernel(const double* __restrict__ C, double* __restrict__ u, double* __restrict__ v,
@@ -359,8 +548,44 @@ size_t sinkhorn_scratch_doubles(int B, int N, int M) {
     return (size_t)B * (N + 1) * ldk + (size_t)B + 2;      // K scratch + per-pair flags and iteration counts (ints)
 }
 
+// float32 kernel matrix: same scratch (the float rows use half of the K area), same flags / iteration counts behind it
+static cudaError_t launch_sinkhorn_fused32(const double* C, double* u, double* v, double* scratch, int B, int N, int M,
+                                           int iters, cudaStream_t st) {
+    const int R1 = N + 1, C1 = M + 1;
+    const int ldk64 = (M + 1) & ~1, ldk = (M + 3) & ~3, ldv = (C1 + 1) & ~1;
+    const int RS = (R1 + SKF_CLUSTER - 1) / SKF_CLUSTER;
+    float* Kg = reinterpret_cast<float*>(scratch);
+    int* flags = reinterpret_cast<int*>(scratch + (size_t)B * R1 * ldk64);
+    int dev = 0, max_smem = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    const size_t fixed = ((size_t)3 * ldv + 3 * (size_t)((RS + 3) & ~3) + 4) * sizeof(double);
+    if (fixed + 1024 > (size_t)max_smem) return cudaErrorInvalidValue;
+    int rows_smem = (int)(((size_t)max_smem - fixed) / ((size_t)ldk * sizeof(float)));
+    if (rows_smem > RS) rows_smem = RS;
+    const size_t smem = fixed + (size_t)rows_smem * ldk * sizeof(float);
+    if ((e = cudaMemsetAsync(flags, 0, sizeof(int) * 2 * (size_t)B, st)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(sinkhorn_fused32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(SKF_CLUSTER * B);
+    cfg.blockDim = dim3(SKF_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = SKF_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if ((e = cudaLaunchKernelEx(&cfg, sinkhorn_fused32_kernel, C, Kg, u, v, flags, N, M, iters, RS, rows_smem, ldk)) != cudaSuccess) return e;
+    sinkhorn_safe_kernel<<<B, 1024, 0, st>>>(C, u, v, flags, N, M, iters);
+    count_launch(2);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_sinkhorn_fused(const double* C, double* u, double* v, double* scratch, int B, int N, int M,
-                                  int iters, cudaStream_t st) {
+                                  int iters, cudaStream_t st, bool k32) {
+    if (k32) return launch_sinkhorn_fused32(C, u, v, scratch, B, N, M, iters, st);
     const int R1 = N + 1, C1 = M + 1;
     const int ldk = (M + 1) & ~1, ldv = (C1 + 1) & ~1;
     const int RS = (R1 + SKF_CLUSTER - 1) / SKF_CLUSTER;

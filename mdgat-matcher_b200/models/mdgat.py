@@ -328,6 +328,11 @@ class MDGAT(nn.Module):
         sp = int(self.config.get('attn_p_slices', min(sp, a) if a == 4 else a - 1))
         return g, a, sp
 
+    def sinkhorn_k32(self):
+        """Sinkhorn kernel matrix stored in float32 with float64 arithmetic (potentials move by O(1e-7), SURVEY.md 7.3:
+        the tail is float32-safe): on for 'sweep' precision, off for 'exact'; config['sinkhorn_k32'] overrides."""
+        return bool(self.config.get('sinkhorn_k32', self.config.get('precision', 'sweep') == 'sweep'))
+
     def gemm_engine(self):
         """config['gemm']: 'tcgen05_i8' (Ozaki splitting on the int8 tensor cores, default) or 'dmma' (FP64 pipe);
         the number of int8 digit planes per operand comes from digit_planes()."""
@@ -448,7 +453,7 @@ class MDGAT(nn.Module):
                 gemm_slices=gemm_slices,
                 attn_mode={'tcgen05_i8': _capi.ATTN_TCGEN05_I8, 'tcgen05_i8_all': _capi.ATTN_TCGEN05_I8_ALL,
                            'dmma': _capi.ATTN_DMMA_F64}[self.attention_engine()],
-                attn_slices=planes[1], attn_p_slices=planes[2])
+                attn_slices=planes[1], attn_p_slices=planes[2], sinkhorn_k32=int(self.sinkhorn_k32()))
             need = _capi.lib.mdgat_forward_workspace_bytes(ctypes.byref(cfg))
             ws = self._workspaces.get(dev)
             if ws is None or ws.numel() < need:
@@ -486,7 +491,7 @@ class MDGAT(nn.Module):
                 # (shape, dtypes, weights, workspace) and replayed; the inputs are copied into the graph's static buffers
                 # and the results out of them, so the caller sees fresh tensors as with plain launches
                 key = (dev, B, N, M, in_dtype, sc[0].dtype, loss_mode, tuple(sched), tuple(planes), gemm_mode,
-                       self.attention_engine(), int(self.config['sinkhorn_iterations']), bool(self.mutual_check),
+                       self.attention_engine(), int(self.config['sinkhorn_iterations']), bool(self.mutual_check), self.sinkhorn_k32(),
                        blob.data_ptr(), blob_i8.data_ptr() if blob_i8 is not None else 0, ws.data_ptr())
                 ent = self._graphs.get(key)
                 if ent is None:

@@ -96,9 +96,10 @@ def attention(q, k, v, topk=None, engine='dmma', slices=7, p_slices=0):
     return msg.permute(0, 3, 2, 1).reshape(B, 128, N).contiguous()  # channel c = d*4 + h
 
 
-def sinkhorn(scores, bin_score, iters, fused=True, return_status=False):
+def sinkhorn(scores, bin_score, iters, fused=True, return_status=False, k32=False):
     """scores (B,N,M) -> (couplings, u, v) with Z = couplings + u[:, :, None] + v[:, None, :] - norm
-    = log_optimal_transport(scores, bin_score, iters). fused=False uses one launch per half-iteration."""
+    = log_optimal_transport(scores, bin_score, iters). fused=False uses one launch per half-iteration; k32=True stores
+    the kernel matrix exp(C - rowmax) in float32 (float64 arithmetic), the forward's default ('sweep' precision)."""
     _need_cuda(scores)
     B, N, M = scores.shape
     dev = scores.device
@@ -109,9 +110,9 @@ def sinkhorn(scores, bin_score, iters, fused=True, return_status=False):
     alpha = torch.as_tensor(bin_score, dtype=torch.float64, device=dev).reshape(1).contiguous()
     scratch = torch.empty(_capi.lib.mdgat_sinkhorn_scratch_doubles(B, N, M), dtype=torch.float64, device=dev) if fused else None
     with torch.cuda.device(dev):
-        _capi.check(_capi.lib.mdgat_sinkhorn_f64(C.data_ptr(), alpha.data_ptr(), u.data_ptr(), v.data_ptr(),
-                                                 B, N, M, int(iters), scratch.data_ptr() if fused else None,
-                                                 _stream(dev)))
+        fn = _capi.lib.mdgat_sinkhorn_f64_k32 if (k32 and fused) else _capi.lib.mdgat_sinkhorn_f64
+        _capi.check(fn(C.data_ptr(), alpha.data_ptr(), u.data_ptr(), v.data_ptr(),
+                       B, N, M, int(iters), scratch.data_ptr() if fused else None, _stream(dev)))
         if return_status and fused:
             fl, it = (ctypes.c_int * B)(), (ctypes.c_int * B)()
             _capi.check(_capi.lib.mdgat_sinkhorn_read_status(scratch.data_ptr(), B, N, M, fl, it))

@@ -42,6 +42,17 @@ CASES = [
          store_Z=False),
     dict(name='ckpt_L9_n512_b8', weights='checkpoint', L=9, T=100, B=8, N=512, M=512, seed=8,
          store_Z=False),
+    # non-finite inputs (a zero-norm FPFH row becomes NaN in load_data.py:290): 'poke' = (key, pair, row, column or None, value).
+    # The whole pair turns NaN upstream; these pin what match extraction and the losses then report, and that the other
+    # pairs of the batch are untouched
+    dict(name='seeded_L2_nan_triplet', weights='seeded', L=2, T=20, B=3, N=64, M=64, seed=11, k=[16, None, 16, None],
+         store_Z=False, poke=[['descriptors0', 1, 7, 3, 'nan']]),
+    dict(name='seeded_L2_nan_gap_ragged', weights='seeded', L=2, T=20, B=3, N=80, M=64, seed=12, k=[16, None, 16, None],
+         loss_method='gap_loss', store_Z=False, poke=[['keypoints1', 0, 5, 1, 'nan'], ['scores0', 2, 9, None, 'inf']]),
+    dict(name='seeded_L2_nan_sg_mutual', weights='seeded', L=2, T=20, B=3, N=64, M=64, seed=13, k=[16, None, 16, None],
+         loss_method='superglue', mutual_check=True, store_Z=False, poke=[['descriptors1', 2, 0, 0, '-inf']]),
+    dict(name='seeded_L2_nan_sg', weights='seeded', L=2, T=20, B=2, N=64, M=64, seed=14, k=[16, None, 16, None],
+         loss_method='superglue', mutual_check=False, store_Z=False, poke=[['descriptors0', 0, 63, 32, 'nan']]),
 ]
 
 
@@ -57,6 +68,11 @@ def run_case(c):
         weights = 'checkpoint'
     net, mod, zcap = RL.build_reference_net(cfg, weights)
     data = synth.make_batch(c['seed'], c['B'], c['N'], c['M'], duplicates=c.get('duplicates', 0))
+    for key, b, r, col, val in c.get('poke', []):
+        if col is None:
+            data[key][b, r] = float(val)
+        else:
+            data[key][b, r, col] = float(val)
     layers = []
     if c.get('store_layers'):
         def hook(m, inp, out):

@@ -214,6 +214,39 @@ def test_sinkhorn_vs_oracle(dev, N, M, iters, fused):
     assert np.abs(got - want).max() < 1e-10
 
 
+@pytest.mark.parametrize('N,M,iters', [(128, 128, 20), (200, 77, 100), (512, 512, 100), (5, 9, 3), (700, 650, 10), (33, 2048, 30)])
+def test_sinkhorn_float32_kernel_matrix_vs_oracle(dev, N, M, iters):
+    """The forward's default Sinkhorn stores exp(C - rowmax) in float32 and does every sum / division / log in float64:
+    the potentials may move by O(1e-7) (bar for the scores: 1e-4); marginals stay exact to float64 noise relative to the
+    rounded kernel, and exact column ties stay exact ties."""
+    from mdgat_matcher_b200 import ops
+    from oracle import mdgat_oracle as O
+    rng = np.random.default_rng(N + M)
+    scores = rng.normal(size=(3, N, M)) * 3 + 2
+    scores[:, :, M - 1] = scores[:, :, 0]                                  # an exact twin column
+    want = O.log_optimal_transport(scores, 1.977, iters)
+    C, u, v, st = ops.sinkhorn(_t(scores, dev), 1.977, iters, k32=True, return_status=True)
+    assert st['fallback'] == [0, 0, 0]
+    norm = -np.log(N + M)
+    got = (C + u[:, :, None] + v[:, None, :] - norm).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-6
+    assert np.array_equal(got[:, :, M - 1], got[:, :, 0])
+
+
+def test_sinkhorn_float32_kernel_matrix_wide_range_falls_back(dev):
+    """Row range >= 80: exp(C - rowmax) would leave the normal float32 range, the pair is redone in the log domain."""
+    from mdgat_matcher_b200 import ops
+    from oracle import mdgat_oracle as O
+    rng = np.random.default_rng(8)
+    scores = rng.normal(size=(2, 60, 50)) * 2
+    scores[1, 3, 4] = 120.0
+    want = O.log_optimal_transport(scores, 1.0, 25)
+    C, u, v, st = ops.sinkhorn(_t(scores, dev), 1.0, 25, k32=True, return_status=True)
+    assert st['fallback'] == [0, 1]
+    got = (C + u[:, :, None] + v[:, None, :] + np.log(110)).cpu().numpy()
+    assert np.abs(got[0] - want[0]).max() < 1e-6 and np.abs(got[1] - want[1]).max() < 1e-9
+
+
 def test_sinkhorn_early_exit_is_exact(dev):
     """The fused kernel stops once the iterate repeats bit for bit; asking for more iterations than
     that must give bit-identical potentials, and a pair that needs every iteration must run them all."""
@@ -388,6 +421,28 @@ def test_forward_matches_reference_golden(dev, name, gemm, attention, precision)
     # the reference rewrites gt_matches in place (mdgat.py:519-520)
     if case.get('loss_method', 'triplet_loss') != 'superglue':
         assert int((data['gt_matches0'] == -1).sum()) == 0
+
+
+NAN_CASES = ['seeded_L2_nan_triplet', 'seeded_L2_nan_gap_ragged', 'seeded_L2_nan_sg_mutual', 'seeded_L2_nan_sg']
+
+
+@pytest.mark.parametrize('gemm,attention', [('tcgen05_i8', 'tcgen05_i8'), ('tcgen05_i8', 'tcgen05_i8_all'), ('dmma', 'dmma')])
+@pytest.mark.parametrize('name', NAN_CASES)
+def test_nonfinite_inputs_match_reference(dev, name, gemm, attention):
+    """NaN / Inf inputs (zero-norm FPFH rows, load_data.py:290): integer digit planes cannot carry a NaN, so the pair is
+    flagged at the input and match extraction reports what the reference's all-NaN assignment yields -- for every engine;
+    the other pairs of the batch are computed as usual. Fixtures: the unmodified reference on the same poked inputs."""
+    rec = load_golden(name)
+    net = _build_module(rec['case'], dev, extra={'gemm': gemm, 'attention': attention})
+    data = {k: _t(v, dev) for k, v in golden_inputs(rec).items()}
+    out = net(data)
+    torch.cuda.synchronize()
+    assert np.array_equal(out['matches0'].cpu().numpy(), rec['matches0'])
+    assert np.array_equal(out['matches1'].cpu().numpy(), rec['matches1'])
+    assert np.allclose(out['matching_scores0'].cpu().numpy(), rec['matching_scores0'], rtol=0, atol=1e-6, equal_nan=True)
+    assert np.allclose(out['matching_scores1'].cpu().numpy(), rec['matching_scores1'], rtol=0, atol=1e-6, equal_nan=True)
+    assert np.allclose(out['loss'].cpu().numpy(), rec['loss'], rtol=0, atol=1e-6, equal_nan=True)
+    assert np.isnan(rec['matching_scores0']).any() or np.isnan(rec['loss']).any()
 
 
 def test_superglue_module_is_full_attention_mdgat(dev):

@@ -79,28 +79,41 @@ def ncu_table(rep):
 
 
 def main():
+    """python tools/summarize_profiles.py <tag> [<prefix>]: gpurun_out/<prefix>_bench.json, <prefix>_bench_ref.json (optional),
+    <prefix>_launches.csv and every <prefix>_prof_*.ncu-rep -> profiles/<tag>_bench.json, _bench_reference_arm.json, _ncu_summary.md.
+    Without a prefix: the round-1 file names (bench_final.json, launches_final.csv, prof_*_final.ncu-rep)."""
+    import glob
     tag = sys.argv[1] if len(sys.argv) > 1 else 'r1_final'
-    bench = json.loads(open(os.path.join(OUT, 'bench_final.json')).read().strip().splitlines()[-1])
-    ref = json.loads(open(os.path.join(OUT, 'bench_final_ref.json')).read().strip().splitlines()[-1])
+    prefix = sys.argv[2] if len(sys.argv) > 2 else None
+    if prefix:
+        fb, fr, fl = prefix + '_bench.json', prefix + '_bench_ref.json', prefix + '_launches.csv'
+        reps = sorted(glob.glob(os.path.join(OUT, prefix + '_prof_*.ncu-rep')))
+    else:
+        fb, fr, fl = 'bench_final.json', 'bench_final_ref.json', 'launches_final.csv'
+        reps = [os.path.join(OUT, n + '.ncu-rep') for n in ('prof_attn_i8_final', 'prof_oz_final', 'prof_misc_final')]
+    bench = json.loads(open(os.path.join(OUT, fb)).read().strip().splitlines()[-1])
     json.dump(bench, open(os.path.join(ROOT, 'profiles', tag + '_bench.json'), 'w'), indent=1)
-    json.dump(ref, open(os.path.join(ROOT, 'profiles', tag + '_bench_reference_arm.json'), 'w'), indent=1)
+    ref = None
+    if os.path.isfile(os.path.join(OUT, fr)):
+        ref = json.loads(open(os.path.join(OUT, fr)).read().strip().splitlines()[-1])
+        json.dump(ref, open(os.path.join(ROOT, 'profiles', tag + '_bench_reference_arm.json'), 'w'), indent=1)
     # the launch list covers warm-up + timed + e2e forwards of `bench.py --steps 2 --warmup 1`: count them by a once-per-forward kernel
-    table, agg = launch_table(os.path.join(OUT, 'launches_final.csv'), 1)
+    table, agg = launch_table(os.path.join(OUT, fl), 1)
     forwards = [a[0] for k, a in agg.items() if 'pack_inputs_kernel' in k][0]
-    table, _ = launch_table(os.path.join(OUT, 'launches_final.csv'), forwards)
+    table, _ = launch_table(os.path.join(OUT, fl), forwards)
+    cb, eg = bench.get('cpu_baseline'), bench.get('gpu_eager_reference') or bench.get('gpu_eager_port')
     md = ['# %s -- ncu launch list and top-kernel captures (cfg2: B=32, N=M=512, L=9, T=100, one B200)' % tag, '',
-          'Commands: see `tools/gpu_round.sh` (launch list: `ncu --metrics gpu__time_duration.sum --clock-control none` on',
+          'Commands: `tools/gpu_round.sh` (launch list: `ncu --metrics gpu__time_duration.sum --clock-control none` on',
           '`bench.py --steps 2 --warmup 1`; captures: `ncu --set full --clock-control none --import-source on -k <kernel>`).', '',
-          'Bench of the same build (`%s_bench.json`): **%.1f pairs/s** resident, %.1f pairs/s end to end, CPU port %.2f pairs/s on %d threads,'
-          % (tag, bench['value'], bench['e2e']['value'], bench['cpu_baseline']['value'], bench['cpu_baseline']['cores']),
-          'eager PyTorch fp64 restatement on the same GPU %.1f pairs/s.' % bench['gpu_eager_port']['pairs_per_s'], '',
+          'Bench of the same build (`%s_bench.json`): **%.1f pairs/s** resident, %.1f pairs/s end to end%s%s.'
+          % (tag, bench['value'], bench['e2e']['value'],
+             ', CPU %s %.2f pairs/s on %d threads' % (cb['kind'], cb['value'], cb['cores']) if cb else '',
+             ', unmodified reference as eager PyTorch fp64 on the same GPU %.1f pairs/s' % eg['pairs_per_s'] if eg else ''), '',
           'Live stage times (CUDA events on the launch stream, ms per forward): `%s`' % json.dumps({k: round(v, 3) for k, v in bench['roofline']['stage_ms_per_step'].items()}), '',
           '## Launch list (%d forwards in the capture)' % forwards, '', table, '']
-    for name, title in (('prof_attn_i8_final', 'attention (tcgen05 int8 digit products)'), ('prof_oz_final', 'Ozaki GEMM (q/k/v, MLP 256->256, MLP 256->128)'),
-                        ('prof_misc_final', 'slicer / DMMA logits / top-k / Sinkhorn')):
-        rep = os.path.join(OUT, name + '.ncu-rep')
+    for rep in reps:
         if os.path.isfile(rep):
-            md += ['## ncu --set full: %s' % title, '', ncu_table(rep), '']
+            md += ['## ncu --set full: %s' % os.path.basename(rep), '', ncu_table(rep), '']
     open(os.path.join(ROOT, 'profiles', tag + '_ncu_summary.md'), 'w').write('\n'.join(md))
     print('\n'.join(md)[:3000])
 

@@ -9,6 +9,7 @@
 // The assignment matrix Z = C + u + v - norm is never written unless a caller asks for it.
 #include <cooperative_groups.h>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -336,7 +337,8 @@ DEVINL double f32bits_to_f64(uint32_t f) {
     return __hiloint2double((int)hi, (int)(f << 29));
 }
 
-__global__ void __launch_bounds__(SKF_THREADS, 1)
+template <int MINB>
+__global__ void __launch_bounds__(SKF_THREADS, MINB)
 sinkhorn_fused32_kernel(const double* __restrict__ C, float* __restrict__ Kg, double* __restrict__ u_out,
                         double* __restrict__ v_out, int* __restrict__ flags, int N, int M, int iters,
                         int RS, int rows_smem, int ldk) {
@@ -548,7 +550,41 @@ size_t sinkhorn_scratch_doubles(int B, int N, int M) {
     return (size_t)B * (N + 1) * ldk + (size_t)B + 2;      // K scratch + per-pair flags and iteration counts (ints)
 }
 
-// float32 kernel matrix: same scratch (the float rows use half of the K area), same flags / iteration counts behind it
+// float32 kernel matrix: same scratch (the float rows use half of the K area), same flags / iteration counts behind it.
+// Launch shape: one CTA per SM with as many K rows in shared memory as fit (all 65 at N = M = 512). The iteration is bound
+// by its barrier chain (row sums -> CTA barrier -> column partials -> cluster barrier -> exchange -> cluster barrier: 7300
+// cycles per iteration against 2150 shared-memory wavefronts and 2200 issue cycles), and at cfg2 the 32 clusters of 8 need
+// two waves on 148 SMs. MDGAT_SK_CTAS=2 runs the measured-and-rejected alternative: two CTAs per SM (64 registers, 49 of
+// the 65 rows in shared memory, the others read from the L2-resident scratch), all 32 clusters in one wave -- 11 600 cycles
+// per iteration, 1.16 ms against 0.74 ms.
+template <int MINB>
+static cudaError_t sk32_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int B, int RS, int ldk, int ldv, cudaStream_t st,
+                               int& rows_smem, int& clusters) {
+    int dev = 0, max_optin = 0, max_sm = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&max_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev)) != cudaSuccess) return e;
+    const size_t budget = MINB == 1 ? (size_t)max_optin : (size_t)(max_sm / MINB - 1024);      // 1 KB per resident CTA is reserved
+    const size_t fixed = ((size_t)3 * ldv + 3 * (size_t)((RS + 3) & ~3) + 4) * sizeof(double);
+    if (fixed + 1024 > budget) return cudaErrorInvalidValue;
+    rows_smem = (int)((budget - fixed) / ((size_t)ldk * sizeof(float)));
+    if (rows_smem > RS) rows_smem = RS;
+    const size_t smem = fixed + (size_t)rows_smem * ldk * sizeof(float);
+    if ((e = cudaFuncSetAttribute(sinkhorn_fused32_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(SKF_CLUSTER * B);
+    cfg.blockDim = dim3(SKF_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = SKF_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    clusters = 1;
+    if (MINB > 1 && (e = cudaOccupancyMaxActiveClusters(&clusters, sinkhorn_fused32_kernel<MINB>, &cfg)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
 static cudaError_t launch_sinkhorn_fused32(const double* C, double* u, double* v, double* scratch, int B, int N, int M,
                                            int iters, cudaStream_t st) {
     const int R1 = N + 1, C1 = M + 1;
@@ -556,28 +592,21 @@ static cudaError_t launch_sinkhorn_fused32(const double* C, double* u, double* v
     const int RS = (R1 + SKF_CLUSTER - 1) / SKF_CLUSTER;
     float* Kg = reinterpret_cast<float*>(scratch);
     int* flags = reinterpret_cast<int*>(scratch + (size_t)B * R1 * ldk64);
-    int dev = 0, max_smem = 0;
     cudaError_t e;
-    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-    if ((e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
-    const size_t fixed = ((size_t)3 * ldv + 3 * (size_t)((RS + 3) & ~3) + 4) * sizeof(double);
-    if (fixed + 1024 > (size_t)max_smem) return cudaErrorInvalidValue;
-    int rows_smem = (int)(((size_t)max_smem - fixed) / ((size_t)ldk * sizeof(float)));
-    if (rows_smem > RS) rows_smem = RS;
-    const size_t smem = fixed + (size_t)rows_smem * ldk * sizeof(float);
+    cudaLaunchConfig_t cfg1, cfg2;
+    cudaLaunchAttribute attr1[1], attr2[1];
+    int rows1 = 0, rows2 = 0, cl1 = 0, cl2 = 0;
+    static const int force = [] { const char* v = getenv("MDGAT_SK_CTAS"); return v ? atoi(v) : 0; }();
+    bool two = false;
+    if (force == 2) {
+        if (sk32_config<2>(cfg2, attr2, B, RS, ldk, ldv, st, rows2, cl2) == cudaSuccess && cl2 > 0) two = true;
+        else (void)cudaGetLastError();
+    }
+    if (!two && (e = sk32_config<1>(cfg1, attr1, B, RS, ldk, ldv, st, rows1, cl1)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(flags, 0, sizeof(int) * 2 * (size_t)B, st)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(sinkhorn_fused32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(SKF_CLUSTER * B);
-    cfg.blockDim = dim3(SKF_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = SKF_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    if ((e = cudaLaunchKernelEx(&cfg, sinkhorn_fused32_kernel, C, Kg, u, v, flags, N, M, iters, RS, rows_smem, ldk)) != cudaSuccess) return e;
+    if (two) e = cudaLaunchKernelEx(&cfg2, sinkhorn_fused32_kernel<2>, C, Kg, u, v, flags, N, M, iters, RS, rows2, ldk);
+    else e = cudaLaunchKernelEx(&cfg1, sinkhorn_fused32_kernel<1>, C, Kg, u, v, flags, N, M, iters, RS, rows1, ldk);
+    if (e != cudaSuccess) return e;
     sinkhorn_safe_kernel<<<B, 1024, 0, st>>>(C, u, v, flags, N, M, iters);
     count_launch(2);
     return cudaGetLastError();

@@ -404,7 +404,10 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = sum(v.numel() * v.element_size() for v in host_out[0].values())
     config = workload_config(B, N, L, T, world)
+    late = net.digit_planes_late()
     config['digit_planes'] = {'gemm': planes[0], 'attention_qkv': planes[1], 'attention_p': planes[2],
+                              'late_layers': ({'from_layer': late[0], 'gemm': late[1], 'attention_qkv': late[2], 'attention_p': late[3]} if late else None),
+                              'sinkhorn_kernel_matrix': 'float32 storage, float64 arithmetic' if net.sinkhorn_k32() else 'float64',
                               'note': 'int8 planes per float64 operand; chosen on the 131 k-row sweep against the unmodified reference (DESIGN.md 2)'}
     if world > 1:
         config['collective'] = {'op': 'all_gather_into_tensor (NCCL)', 'per_step': 1, 'inside_timed_region': True,
@@ -431,8 +434,15 @@ def main():
         R = B * 2 * N
         gq, _, _ = digit_products(planes[0], planes[2])
         qk, p1, pv = digit_products(planes[1], planes[2])
-        i8_ops = {'gemm': 2 * L * gq * 2.0 * R * (384 * 128 + 256 * 256 + 128 * 256),
-                  'attn_full': (2 * L - n_topk) * (qk + p1 + pv) * 2.0 * N * N * 32 * 4 * 2 * B}[dominant]
+        # digit products summed over the layers (a second plane setting applies from layer late[0] on)
+        gsum = asum = 0
+        for l, kk in enumerate(k_sched):
+            pl = (late[1], late[2], late[3]) if (late and l >= late[0]) else planes
+            gsum += digit_products(pl[0], pl[2])[0]
+            if not kk:
+                asum += sum(digit_products(pl[1], pl[2]))
+        i8_ops = {'gemm': gsum * 2.0 * R * (384 * 128 + 256 * 256 + 128 * 256),
+                  'attn_full': asum * 2.0 * N * N * 32 * 4 * 2 * B}[dominant]
         i8_peak = ops.measure_i8_peak()
         achieved = i8_ops / (per_step[dominant] * 1e-3) / 1e12
         roofline = {

@@ -98,6 +98,12 @@ typedef struct {
                                  (4,3) (4,4) (5,4) (6,5) (7,6); 0 = attn_slices - 1 */
     int sinkhorn_k32;         /* 1: the Sinkhorn kernel matrix exp(C_ij - max_j C_ij) is STORED in float32 (every sum,
                                  division and potential stays float64; potentials move by O(1e-7)); 0: float64 storage */
+    int late_from;            /* > 0: GNN layers late_from .. 2L-1 use the late_* digit-plane counts (never more planes than
+                                 the first setting). Experimental and off by default: 4/4/4 from layer 7 on keeps the match
+                                 indices on the 131 k-row sweep but its worst score error is 6.9e-4. 0: one
+                                 setting for all layers */
+    int late_gemm_slices, late_attn_slices, late_attn_p_slices;
+    const void* d_weights_i8_late;   /* device: the weight digit planes packed with late_gemm_slices (all layers), or NULL */
 } mdgat_forward_cfg;
 
 typedef struct {

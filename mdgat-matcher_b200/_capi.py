@@ -26,7 +26,9 @@ class ForwardCfg(C.Structure):
                 ('loss_mode', C.c_int), ('triplet_gamma', C.c_double),
                 ('in_dtype', C.c_int), ('score_dtype', C.c_int), ('write_Z', C.c_int),
                 ('gemm_mode', C.c_int), ('gemm_slices', C.c_int), ('attn_mode', C.c_int),
-                ('attn_slices', C.c_int), ('attn_p_slices', C.c_int), ('sinkhorn_k32', C.c_int)]
+                ('attn_slices', C.c_int), ('attn_p_slices', C.c_int), ('sinkhorn_k32', C.c_int),
+                ('late_from', C.c_int), ('late_gemm_slices', C.c_int), ('late_attn_slices', C.c_int),
+                ('late_attn_p_slices', C.c_int), ('d_weights_i8_late', C.c_void_p)]
 
 
 class ForwardIn(C.Structure):

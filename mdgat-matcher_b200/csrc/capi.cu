@@ -101,6 +101,7 @@ struct Workspace {
     double *tkthr, *tkmax; int* tkjl;                   // tcgen05 top-k layers: per (b, h, row) threshold, maximum, last tied column
     double *rsX, *rsM, *rsH; int8_t *xsX, *xsM, *xsH;   // tcgen05 path: int8 slice planes + row scales of X, Msg, Hd (2 chunks)
     AttnI8Side ai[2];                                   // tcgen05 attention: digit planes of q/k/v of side 0 / side 1
+    void* ai_base[2];                                   // their memory (re-carved for layers with fewer planes)
     int* bad;                                          // per pair: non-finite input seen
     size_t bytes, S_doubles;
 };
@@ -152,6 +153,7 @@ Workspace carve(char* base, int B, int N, int M, bool need_logits, int i8_slices
     for (int s = 0; s < 2; ++s) {
         const int n = s == 0 ? N : M;
         void* p = take(attn_i8 ? attn_i8_side_bytes(B, n, attn_i8) / 8 : 0);
+        w.ai_base[s] = p;
         if (attn_i8 && base) w.ai[s] = attn_i8_carve(p, B, n, attn_i8);
     }
     w.bytes = off;
@@ -303,6 +305,16 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
     const bool ai8_any = (cfg->attn_mode == MDGAT_ATTN_TCGEN05_I8 || cfg->attn_mode == MDGAT_ATTN_TCGEN05_I8_ALL) && attn_i8_supported(N, M) && attn_i8_supported(M, N);
     const int AS = attn_planes(cfg), ASP = attn_p_planes(cfg);
     MDGAT_REQUIRE(!ai8_any || attn_planes_ok(AS, ASP), "tcgen05 attention: unsupported digit planes (attn_slices %d, attn_p_slices %d)", AS, ASP);
+    // second digit-plane setting from layer late_from on (0: none): never more planes than the first (the workspace is
+    // sized for the first), its own weight blob
+    const int late_from = (cfg->late_from > 0 && cfg->late_from < 2 * L) ? cfg->late_from : 0;
+    const int S8L = late_from ? cfg->late_gemm_slices : S8;
+    const int ASL = late_from && cfg->late_attn_slices > 0 ? cfg->late_attn_slices : AS;
+    const int ASPL = late_from && cfg->late_attn_slices > 0 ? (cfg->late_attn_p_slices > 0 ? cfg->late_attn_p_slices : ASL - 1) : ASP;
+    if (late_from) {
+        MDGAT_REQUIRE(!i8 || (cfg->d_weights_i8_late != nullptr && S8L >= 4 && S8L <= S8), "late layers: need d_weights_i8_late and 4 <= late_gemm_slices <= gemm_slices (got %d)", S8L);
+        MDGAT_REQUIRE(!ai8_any || (attn_planes_ok(ASL, ASPL) && ASL <= AS), "late layers: unsupported attention digit planes (%d, %d)", ASL, ASPL);
+    }
     Workspace w = carve(reinterpret_cast<char*>(d_workspace), B, N, M, need, i8 ? S8 : 0, ai8_any ? AS : 0);
     if (w.bytes > workspace_bytes) {
         mdgat_host::set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
@@ -324,8 +336,19 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
     // (R >= 148 row tiles). Bit-identical results; measured slower on B200 (slice stage -1.04 ms, GEMM stage +1.14 ms:
     // the FP64-bound slicing tail runs while the CTA's tensor pipe idles), so the stand-alone launches stay the default.
     static const bool fuse_env = [] { const char* e = getenv("MDGAT_FUSE_SLICE"); return e && e[0] == '1'; }();
-    const bool fuse_slice = i8 && (fuse_env || (g_debug_flags & 0x10000) != 0) && ozaki_gemm_can_slice(R, DMODEL);   // bit 16: same switch, per call (tests)
+    const bool fuse_slice = i8 && !late_from && (fuse_env || (g_debug_flags & 0x10000) != 0) && ozaki_gemm_can_slice(R, DMODEL);   // bit 16: same switch, per call (tests)
+    AttnI8Side ai_late[2] = {w.ai[0], w.ai[1]};
+    if (late_from && ai8_any && ASL != AS) {
+        ai_late[0] = attn_i8_carve(w.ai_base[0], B, N, ASL);
+        ai_late[1] = attn_i8_carve(w.ai_base[1], B, M, ASL);
+    }
+    const int S8_first = S8, ASP_first = ASP;
+    const void* const d_weights_i8_first = d_weights_i8;
     for (int l = 0; l < 2 * L; ++l) {
+        const bool late = late_from && l >= late_from;
+        const int S8 = late ? S8L : S8_first, ASP = late ? ASPL : ASP_first;          // this layer's digit planes
+        const AttnI8Side* ai = late ? ai_late : w.ai;
+        const void* d_weights_i8 = late ? cfg->d_weights_i8_late : d_weights_i8_first;
         const LayerOffsets lo = lay.layer(l);
         const bool cross = (l & 1) != 0;                  // names = ['self','cross']*L (mdgat.py:353)
         const int k = cfg->layer_k[l];
@@ -367,14 +390,14 @@ int mdgat_forward(const mdgat_forward_cfg* cfg, const double* d_weights, const v
             // digit planes of this layer's q, k, v (both sides), then the tcgen05 kernel: side s reads the k / v planes
             // of side s (self) or 1 - s (cross)
             const double* const qs[2] = {Q0, Q1}; const double* const ks[2] = {K0, K1}; const double* const vs[2] = {V0, V1};
-            if (N > 0 && M > 0) { MDGAT_CUDA_OK(launch_attn_i8_slice_sides(qs, ks, vs, w.ai, B, st)); }
+            if (N > 0 && M > 0) { MDGAT_CUDA_OK(launch_attn_i8_slice_sides(qs, ks, vs, ai, B, st)); }
             else {
-                MDGAT_CUDA_OK(launch_attn_i8_slice(Q0, K0, V0, w.ai[0], B, st));
-                MDGAT_CUDA_OK(launch_attn_i8_slice(Q1, K1, V1, w.ai[1], B, st));
+                MDGAT_CUDA_OK(launch_attn_i8_slice(Q0, K0, V0, ai[0], B, st));
+                MDGAT_CUDA_OK(launch_attn_i8_slice(Q1, K1, V1, ai[1], B, st));
             }
             prof_mark(k > 0 ? ST_ATTN_TOPK : ST_ATTN_FULL, st);
-            const AttnI8Side qd[2] = {w.ai[0], w.ai[1]};
-            const AttnI8Side kvd[2] = {cross ? w.ai[1] : w.ai[0], cross ? w.ai[0] : w.ai[1]};
+            const AttnI8Side qd[2] = {ai[0], ai[1]};
+            const AttnI8Side kvd[2] = {cross ? ai[1] : ai[0], cross ? ai[0] : ai[1]};
             const TopKScratch tks = {w.tkthr, w.tkmax, w.tkjl};
             // with the tcgen05 GEMM engine the messages leave the attention kernel as the digit planes of the MLP's second
             // k chunk (MDGAT_MSG_PLANES=0: float64 rows + the stand-alone slicer, as for the DMMA attention engine)

@@ -296,6 +296,9 @@ class MDGAT(nn.Module):
         mode, slices = self.gemm_engine()
         if mode == 'tcgen05_i8':
             self.packed_weights_i8(slices, device='cpu')
+            late = self.digit_planes_late()
+            if late:
+                self.packed_weights_i8(late[1], device='cpu')
         replica = super()._replicate_for_data_parallel()
         replica._is_replica = True
         return replica
@@ -327,6 +330,33 @@ class MDGAT(nn.Module):
         a = int(self.config.get('attn_slices', a))
         sp = int(self.config.get('attn_p_slices', min(sp, a) if a == 4 else a - 1))
         return g, a, sp
+
+    # A second digit-plane setting for the late layers (mdgat_forward_cfg.late_from) exists and is OFF: measured on the GPU
+    # sweep (131 072 rows), 5/5/4 planes with 4/4/4 from layer 7 on gives 0 index flips but a worst score error of 6.9e-4
+    # (p99 1.3e-6; 4/4/4 in every layer: 2.4e-4 on the same batch, i.e. the tail comes from the late layers, where the
+    # top-k layers 10, 12, 14, 16 sit -- the k list addresses the LAST len(k) layers, mdgat.py:268-272) for 1.6 % more
+    # pairs/s. The CPU model (tools/precision_model.py) had predicted 5e-7 on its 8 192-row sample: the tail events are too
+    # rare for a sample of that size, which is why the GPU sweep is the gate. config['late_planes'] = (first layer, g, a, sp)
+    # switches it on for experiments.
+    LATE_PLANES = {'sweep': None, 'exact': None}
+    LATE_FROM_LAYER = 7
+
+    def digit_planes_late(self, sched=None):
+        """(first layer, gemm_slices, attn_slices, attn_p_slices) of the second digit-plane setting, or None.
+        config['late_planes']: None / False = one setting for all layers, or a (first layer, g, a, sp) tuple; default: the
+        precision's LATE_PLANES from layer LATE_FROM_LAYER on, unless gemm_slices / attn_slices are set explicitly."""
+        if 'late_planes' in self.config:
+            lp = self.config['late_planes']
+            return tuple(int(x) for x in lp) if lp else None
+        if any(k in self.config for k in ('gemm_slices', 'attn_slices', 'attn_p_slices')):
+            return None
+        late = self.LATE_PLANES.get(self.config.get('precision', 'sweep'))
+        if late is None:
+            return None
+        g, a, sp = self.digit_planes()
+        if self.LATE_FROM_LAYER >= 2 * self.config['L'] or late[0] > g or late[1] > a:
+            return None
+        return (self.LATE_FROM_LAYER,) + late
 
     def sinkhorn_k32(self):
         """Sinkhorn kernel matrix stored in float32 with float64 arithmetic (potentials move by O(1e-7), SURVEY.md 7.3:
@@ -441,6 +471,8 @@ class MDGAT(nn.Module):
 
             karr = (ctypes.c_int * len(sched))(*sched)
             planes = self.digit_planes()
+            late = self.digit_planes_late(sched) if (gemm_mode == 'tcgen05_i8' or self.attention_engine() != 'dmma') else None
+            blob_i8_late = self.packed_weights_i8(late[1], dev) if (late and gemm_mode == 'tcgen05_i8') else None
             cfg = _capi.ForwardCfg(
                 B=B, N=N, M=M, L=L, sinkhorn_iters=int(self.config['sinkhorn_iterations']), layer_k=karr,
                 match_mode=_capi.MATCH_THRESHOLD if self.loss_method == 'superglue' else _capi.MATCH_DUSTBIN,
@@ -453,7 +485,10 @@ class MDGAT(nn.Module):
                 gemm_slices=gemm_slices,
                 attn_mode={'tcgen05_i8': _capi.ATTN_TCGEN05_I8, 'tcgen05_i8_all': _capi.ATTN_TCGEN05_I8_ALL,
                            'dmma': _capi.ATTN_DMMA_F64}[self.attention_engine()],
-                attn_slices=planes[1], attn_p_slices=planes[2], sinkhorn_k32=int(self.sinkhorn_k32()))
+                attn_slices=planes[1], attn_p_slices=planes[2], sinkhorn_k32=int(self.sinkhorn_k32()),
+                late_from=late[0] if late else 0, late_gemm_slices=late[1] if late else 0,
+                late_attn_slices=late[2] if late else 0, late_attn_p_slices=late[3] if late else 0,
+                d_weights_i8_late=blob_i8_late.data_ptr() if blob_i8_late is not None else None)
             need = _capi.lib.mdgat_forward_workspace_bytes(ctypes.byref(cfg))
             ws = self._workspaces.get(dev)
             if ws is None or ws.numel() < need:
@@ -490,9 +525,10 @@ class MDGAT(nn.Module):
                 # config['cuda_graph']: the fixed launch sequence of one forward (about 150 kernels) is captured once per
                 # (shape, dtypes, weights, workspace) and replayed; the inputs are copied into the graph's static buffers
                 # and the results out of them, so the caller sees fresh tensors as with plain launches
-                key = (dev, B, N, M, in_dtype, sc[0].dtype, loss_mode, tuple(sched), tuple(planes), gemm_mode,
+                key = (dev, B, N, M, in_dtype, sc[0].dtype, loss_mode, tuple(sched), tuple(planes), late, gemm_mode,
                        self.attention_engine(), int(self.config['sinkhorn_iterations']), bool(self.mutual_check), self.sinkhorn_k32(),
-                       blob.data_ptr(), blob_i8.data_ptr() if blob_i8 is not None else 0, ws.data_ptr())
+                       blob.data_ptr(), blob_i8.data_ptr() if blob_i8 is not None else 0,
+                       blob_i8_late.data_ptr() if blob_i8_late is not None else 0, ws.data_ptr())
                 ent = self._graphs.get(key)
                 if ent is None:
                     static_in = [torch.empty_like(t) if t is not None else None for t in ins]
@@ -508,7 +544,7 @@ class MDGAT(nn.Module):
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
                         launch(static_in, outs, None)
-                    ent = (graph, [a for a in static_in if a is not None], ob, ws, blob, blob_i8)
+                    ent = (graph, [a for a in static_in if a is not None], ob, ws, blob, blob_i8, blob_i8_late)
                     self._graphs[key] = ent
                 torch._foreach_copy_(ent[1], [t for t in ins if t is not None])
                 ent[0].replay()

@@ -601,6 +601,31 @@ def batch1_latency(dev, sd, L):
                     times.append((time.perf_counter() - t0) * 1e3)
             res['graph' if graph else 'launches'] = {'median_ms': float(np.median(times)), 'min_ms': float(min(times))}
         res['shape'] = 'batch 1, 2x256 keypoints, L=%d, T=20; wall clock of forward() + reading the loss on the host' % L
+        # the unmodified reference, eager fp64 on the same GPU, same call
+        try:
+            from oracle import ref_loader as RL
+            if RL.reference_available():
+                rcfg = RL.net_config(L=L, sinkhorn_iterations=20)
+                weights = 'checkpoint' if (L == 9 and (os.path.isfile(PRETRAINED) or os.path.isfile(RL.CHECKPOINT))) else {'module.' + k: v for k, v in sd.items()}
+                rnet, _mod, _z = RL.build_reference_net(rcfg, weights, target=str(dev))
+                with torch.no_grad():
+                    def rcall():
+                        return rnet.module({k: v.clone() for k, v in data.items()})
+                    for _ in range(3):
+                        o = rcall()
+                    torch.cuda.synchronize()
+                    times = []
+                    for _ in range(10):
+                        t0 = time.perf_counter()
+                        o = rcall()
+                        float(o['loss'])
+                        times.append((time.perf_counter() - t0) * 1e3)
+                res['reference_eager'] = {'median_ms': float(np.median(times)), 'min_ms': float(min(times)),
+                                          'what': 'unmodified reference models/mdgat.py, eager PyTorch fp64 on this GPU, same call'}
+                res['speedup_vs_reference_eager'] = res['reference_eager']['median_ms'] / res['launches']['median_ms']
+                del rnet
+        except Exception as e:
+            res['reference_eager'] = {'error': repr(e)[:200]}
         return res
     except Exception as e:
         return {'error': repr(e)[:300]}

@@ -465,6 +465,21 @@ def main():
             'peak_source': 'fp64 DMMA issue-loop microbenchmark run in this process (MEASURED_PEAKS.json has no fp64 entry; '
                            'the path computes in float64 for parity, tcgen05 has no f64 kind)',
         }
+    # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture of this workload
+    # (profiles/r*_traffic.json, written by tools/summarize_profiles.py); next to it the bytes the kernel has to move at least
+    if (B, N, L, T) == (32, 512, 9, 100):
+        import glob
+        tfiles = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_traffic.json')))
+        if tfiles:
+            tj = json.load(open(tfiles[-1]))
+            want = {'gemm': 'ozaki_gemm_kernel' if i8 else 'gemm_f64_kernel', 'attn_full': 'attn_i8_kernel' if i8 else 'attn_full_kernel'}[dominant]
+            hits = [v for k, v in tj['kernels'].items() if want in k]
+            if hits:
+                roofline['traffic'] = sum(h['dram_bytes_per_launch'] * h['launches'] for h in hits) / sum(h['launches'] for h in hits)
+                roofline['traffic_source'] = '%s: %s' % (os.path.basename(tfiles[-1]), tj['source'])
+                if dominant == 'attn_full' and i8:
+                    # digit planes of q, k, v read once and the message planes written once (scales are < 1 %)
+                    roofline['compulsory_bytes_per_launch'] = float(B * 2 * N * 128 * (3 * planes[1] + planes[0]))
     roofline.update({
         'dfma_peak_tflops': dfma_peak,
         'launches_per_step': seg['launches'] / args.steps,

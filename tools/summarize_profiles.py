@@ -78,6 +78,31 @@ def ncu_table(rep):
     return '\n'.join(out)
 
 
+def ncu_traffic(rep):
+    """{kernel name: {'launches', 'dram_bytes_per_launch', 'us_per_launch'}} averaged over the launches captured in `rep`."""
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    mult = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    tmul = {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}
+    out = {}
+    for r in rows[2:]:
+        name = r[ix['Kernel Name']].split('(')[0].replace('void ', '')
+        b = 0.0
+        for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            b += float(r[ix[m]].replace(',', '')) * mult[units[ix[m]]]
+        t = float(r[ix['gpu__time_duration.sum']].replace(',', '')) * tmul[units[ix['gpu__time_duration.sum']]]
+        a = out.setdefault(name, {'launches': 0, 'dram_bytes_per_launch': 0.0, 'us_per_launch': 0.0})
+        a['launches'] += 1
+        a['dram_bytes_per_launch'] += b
+        a['us_per_launch'] += t
+    for a in out.values():
+        a['dram_bytes_per_launch'] /= a['launches']
+        a['us_per_launch'] /= a['launches']
+    return out
+
+
 def main():
     """python tools/summarize_profiles.py <tag> [<prefix>]: gpurun_out/<prefix>_bench.json, <prefix>_bench_ref.json (optional),
     <prefix>_launches.csv and every <prefix>_prof_*.ncu-rep -> profiles/<tag>_bench.json, _bench_reference_arm.json, _ncu_summary.md.
@@ -111,9 +136,16 @@ def main():
              ', unmodified reference as eager PyTorch fp64 on the same GPU %.1f pairs/s' % eg['pairs_per_s'] if eg else ''), '',
           'Live stage times (CUDA events on the launch stream, ms per forward): `%s`' % json.dumps({k: round(v, 3) for k, v in bench['roofline']['stage_ms_per_step'].items()}), '',
           '## Launch list (%d forwards in the capture)' % forwards, '', table, '']
+    traffic = {}
     for rep in reps:
         if os.path.isfile(rep):
             md += ['## ncu --set full: %s' % os.path.basename(rep), '', ncu_table(rep), '']
+            traffic.update(ncu_traffic(rep))
+    if traffic:
+        # per-launch DRAM bytes of each captured kernel (dram__bytes_read.sum + dram__bytes_write.sum): bench.py reports the
+        # dominant kernel's figure as roofline.traffic
+        json.dump({'source': 'ncu --set full --clock-control none captures of `bench.py --steps 1 --warmup 1` (%s)' % ', '.join(os.path.basename(r) for r in reps),
+                   'kernels': traffic}, open(os.path.join(ROOT, 'profiles', tag + '_traffic.json'), 'w'), indent=1)
     open(os.path.join(ROOT, 'profiles', tag + '_ncu_summary.md'), 'w').write('\n'.join(md))
     print('\n'.join(md)[:3000])
 

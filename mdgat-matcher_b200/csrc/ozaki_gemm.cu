@@ -808,6 +808,10 @@ cudaError_t launch_ozaki_gemm(const OzGemmArgs& a, int S, cudaStream_t st) {
     if (persistent_env && grid.y == 1 && row_tiles > sms && (row_tiles % sms) != 0 && a.slice_out == nullptr) {
         const int total = row_tiles * col_tiles;
         p.items_per_cta = (total + sms - 1) / sms;
+        // MDGAT_OZ_EVEN_ITEMS=1: with two k chunks, round the share up to an even count so that the two-group epilogue applies
+        // (256 -> 128 at cfg2: 8 instead of 7 items, 128 instead of 147 CTAs)
+        static const bool even_env = [] { const char* e = getenv("MDGAT_OZ_EVEN_ITEMS"); return e && e[0] == '1'; }();
+        if (even_env && a.K > OZ_KC && (p.items_per_cta & 1) && (col_tiles % 2) == 0) ++p.items_per_cta;
         grid = dim3((total + p.items_per_cta - 1) / p.items_per_cta, 1);
     }
     cudaError_t e;

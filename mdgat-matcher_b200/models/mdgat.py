@@ -16,6 +16,7 @@ train mode -> a differentiable torch restatement (train.py needs autograd and ba
 """
 import ctypes
 import threading
+import warnings
 from copy import deepcopy
 
 import torch
@@ -227,6 +228,7 @@ class MDGAT(nn.Module):
     }
     # keys accepted for the ground-truth matches (SuperGlue upstream reads 'match0/1')
     _gt_keys = ('gt_matches0', 'gt_matches1')
+    _warned_no_grad = False
 
     def __init__(self, config):
         super().__init__()
@@ -406,6 +408,12 @@ class MDGAT(nn.Module):
             raise UnboundLocalError("local variable 'loss' referenced before assignment (unknown loss_method %r)" % (self.loss_method,))
         if self.training or (self.config.get('eval_autograd', False) and torch.is_grad_enabled()):
             return self._forward_torch(data)
+        if torch.is_grad_enabled() and not MDGAT._warned_no_grad and any(p.requires_grad for p in self.parameters()):
+            # the reference is differentiable in eval mode too; its own callers evaluate under torch.no_grad() (test.py:182)
+            MDGAT._warned_no_grad = True
+            warnings.warn("mdgat-matcher_b200: eval-mode forward with autograd enabled returns results WITHOUT a grad_fn (CUDA "
+                          "inference path). Wrap the call in torch.no_grad(), or set config['eval_autograd'] = True to run the "
+                          "differentiable torch path in eval mode.", stacklevel=2)
         return self._forward_cuda(data)
 
     def _forward_cuda(self, data):

@@ -498,7 +498,9 @@ def test_cfg2_full_size_properties(dev):
     norm = -np.log(1024.0)
     col = torch.logsumexp(Z + norm, dim=1)
     want = torch.full_like(col, norm); want[:, -1] = np.log(512.0) + norm
-    assert (col - want).abs().max().item() < 1e-9
+    # (float32-stored kernel matrix: u, v are the exact scaling of a kernel rounded by <= 6e-8 relative, so against the
+    # unrounded couplings the marginals hold to that; with float64 storage to 1e-9)
+    assert (col - want).abs().max().item() < (1e-7 if net.sinkhorn_k32() else 1e-9)
     # (4) matches are consistent with the scores: a valid match has score exp(max) in (0, 1]
     s0 = out['matching_scores0']
     assert bool(((out['matches0'] >= 0) == (s0 > 0)).all()) and float(s0.max()) <= 1.0 + 1e-12

@@ -39,6 +39,7 @@ def frexp_exp(mx):
 
 
 GEMM_CHUNK = [128]          # columns that share one digit scale per row (128 = the kernels' k chunk; 0 = the whole row)
+GEMM_BITS = [7]             # bits per GEMM digit plane (7 = the kernels' base-128 digits; 8: what-if base 256)
 MSG_VBOUND = [False]        # message planes of the full-attention layers cut with the per-pair bound max |v| instead of the row maximum
 
 
@@ -51,11 +52,12 @@ def gemm_planes(x, S, e_min=None):
     e = frexp_exp(xc.abs().amax(dim=2, keepdim=True))
     if e_min is not None:
         e = torch.maximum(e, e_min)
-    t = xc * torch.exp2(6.0 - e)
-    unit = torch.exp2(e - 6.0)
+    b = float(GEMM_BITS[0])
+    t = xc * torch.exp2(b - 1.0 - e)
+    unit = torch.exp2(e - b + 1.0)
     trunc = [torch.zeros_like(x)]
     for j in range(1, S + 1):
-        f = 128.0 ** (j - 1)
+        f = (2.0 ** b) ** (j - 1)
         trunc.append((torch.round(t * f) / f * unit).reshape(R, K))
     planes = [trunc[j + 1] - trunc[j] for j in range(S)]
     return planes, trunc
@@ -287,11 +289,13 @@ def main():
     ap.add_argument('--pairs', type=int, default=0, help='only the first n pairs of each case (0 = all)')
     ap.add_argument('--threads', type=int, default=0)
     ap.add_argument('--msg-vbound', action='store_true', help='message planes of full-attention layers scaled by the per-pair bound max |v|')
+    ap.add_argument('--gemm-bits', type=int, default=7, help='bits per GEMM digit plane (what-if; the kernels use 7)')
     ap.add_argument('--gemm-chunk', type=int, default=128, help='columns sharing one digit scale per row (0 = whole row)')
     args = ap.parse_args()
     if args.threads:
         torch.set_num_threads(args.threads)
     GEMM_CHUNK[0] = args.gemm_chunk
+    GEMM_BITS[0] = args.gemm_bits
     MSG_VBOUND[0] = args.msg_vbound
     if args.golden:
         run_golden(args.golden, args.configs)

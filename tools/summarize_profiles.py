@@ -56,8 +56,16 @@ def launch_table(path, forwards):
     return '\n'.join(out), agg
 
 
+def ncu_raw(rep):
+    """Raw-page CSV of a report: the export made on the GPU box (<name>_raw.csv) when present, else `ncu -i`."""
+    pre = rep[:-len('.ncu-rep')] + '_raw.csv'
+    if os.path.isfile(pre):
+        return open(pre).read()
+    return subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+
+
 def ncu_table(rep):
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    raw = ncu_raw(rep)
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
@@ -80,7 +88,7 @@ def ncu_table(rep):
 
 def ncu_traffic(rep):
     """{kernel name: {'launches', 'dram_bytes_per_launch', 'us_per_launch'}} averaged over the launches captured in `rep`."""
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    raw = ncu_raw(rep)
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
@@ -112,7 +120,9 @@ def main():
     prefix = sys.argv[2] if len(sys.argv) > 2 else None
     if prefix:
         fb, fr, fl = prefix + '_bench.json', prefix + '_bench_ref.json', prefix + '_launches.csv'
-        reps = sorted(glob.glob(os.path.join(OUT, prefix + '_prof_*.ncu-rep')))
+        # a report may have been dropped on the box to fit the copy-back limit: its raw CSV export stands in for it
+        reps = sorted({f[:-len('_raw.csv')] + '.ncu-rep' for f in glob.glob(os.path.join(OUT, prefix + '_prof_*_raw.csv'))} |
+                      set(glob.glob(os.path.join(OUT, prefix + '_prof_*.ncu-rep'))))
     else:
         fb, fr, fl = 'bench_final.json', 'bench_final_ref.json', 'launches_final.csv'
         reps = [os.path.join(OUT, n + '.ncu-rep') for n in ('prof_attn_i8_final', 'prof_oz_final', 'prof_misc_final')]
@@ -138,7 +148,7 @@ def main():
           '## Launch list (%d forwards in the capture)' % forwards, '', table, '']
     traffic = {}
     for rep in reps:
-        if os.path.isfile(rep):
+        if os.path.isfile(rep) or os.path.isfile(rep[:-len('.ncu-rep')] + '_raw.csv'):
             md += ['## ncu --set full: %s' % os.path.basename(rep), '', ncu_table(rep), '']
             traffic.update(ncu_traffic(rep))
     if traffic:

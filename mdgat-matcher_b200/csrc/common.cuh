@@ -50,14 +50,20 @@ DEVINL void mbar_arrive(uint64_t* bar) {
     unsigned s = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(s) : "memory");
 }
+// suspend-time hint of try_wait: the waiting warp sleeps in hardware until the phase completes (wake-up ~60 cycles after the
+// arrive) or the hint expires; without a hint the default time-out is short and a warp waiting for the tensor core re-issues
+// TRYWAIT + BRA half a dozen times per wait, taking issue slots from the three other warps of its scheduler
+#ifndef MBAR_SUSPEND_HINT
+#define MBAR_SUSPEND_HINT 0x989680u
+#endif
 DEVINL bool mbar_try_wait(uint64_t* bar, unsigned parity) {
     unsigned s = (unsigned)__cvta_generic_to_shared(bar), ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(ok) : "r"(s), "r"(parity) : "memory");
+        "}\n" : "=r"(ok) : "r"(s), "r"(parity), "r"(MBAR_SUSPEND_HINT) : "memory");
     return ok != 0;
 }
 DEVINL void mbar_wait(uint64_t* bar, unsigned parity) {

@@ -201,6 +201,17 @@ int mdgat_sinkhorn_f64(double* d_couplings, const double* d_bin_score, double* d
 int mdgat_sinkhorn_f64_k32(double* d_couplings, const double* d_bin_score, double* d_u, double* d_v,
                            int B, int N, int M, int iters, double* d_scratch, void* stream);
 
+/* Training path: hand-written backward of log_optimal_transport (mdgat.py:279-308). d_couplings: the
+ * (B,N+1,M+1) couplings WITH the dustbin row / column filled (what mdgat_sinkhorn_f64 leaves in place), d_gZ = dL/dZ of the
+ * same shape, d_gcouplings (out) = dL/d(couplings) -- the caller takes [:, :N, :M] for the scores and the sum over the dustbin
+ * row and column for bin_score. The iterates are recomputed in scaling form (2 T matrix-vector products), the reverse sweep is
+ * 2 T more and one rank-2T contraction: O(T (N + M)) extra memory per pair where autograd retains 2 T (N+1)(M+1) tensors.
+ * h_ill_conditioned (optional, host): set to 1 when a row of the couplings spans more than 600 and the result is invalid;
+ * reading it synchronises the stream. */
+size_t mdgat_sinkhorn_backward_scratch_doubles(int B, int N, int M, int iters);
+int mdgat_sinkhorn_backward_f64(const double* d_couplings, const double* d_gZ, double* d_gcouplings, int B, int N, int M,
+                                int iters, double* d_scratch, int* h_ill_conditioned, void* stream);
+
 /* Match extraction + optional loss (MDGAT_LOSS_*) from (couplings, u, v) (mdgat.py:442-483, 487-594); Z is never formed. */
 int mdgat_match_extract(const double* d_couplings, const double* d_u, const double* d_v,
                         int B, int N, int M, int match_mode, int mutual_check, double match_threshold,

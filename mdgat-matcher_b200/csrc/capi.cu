@@ -575,6 +575,24 @@ int mdgat_sinkhorn_read_status(const double* d_scratch, int B, int N, int M, int
     return MDGAT_OK;
 }
 
+size_t mdgat_sinkhorn_backward_scratch_doubles(int B, int N, int M, int iters) { return sinkhorn_bwd_scratch_doubles(B, N, M, iters); }
+
+int mdgat_sinkhorn_backward_f64(const double* d_couplings, const double* d_gZ, double* d_gcouplings, int B, int N, int M,
+                                int iters, double* d_scratch, int* h_ill_conditioned, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    MDGAT_REQUIRE(B > 0 && N > 0 && M > 0 && iters >= 0 && d_couplings && d_gZ && d_gcouplings && d_scratch, "mdgat_sinkhorn_backward_f64: bad arguments");
+    MDGAT_CUDA_OK(launch_sinkhorn_backward(d_couplings, d_gZ, d_gcouplings, d_scratch, B, N, M, iters, st));
+    if (h_ill_conditioned) {
+        *h_ill_conditioned = 0;
+        if (iters > 0) {
+            const int* flag = reinterpret_cast<const int*>(d_scratch + (mdgat_sinkhorn_backward_scratch_doubles(B, N, M, iters) - 2));
+            MDGAT_CUDA_OK(cudaMemcpyAsync(h_ill_conditioned, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+            MDGAT_CUDA_OK(cudaStreamSynchronize(st));
+        }
+    }
+    return MDGAT_OK;
+}
+
 int mdgat_sinkhorn_f64(double* d_couplings, const double* d_bin_score, double* d_u, double* d_v,
                        int B, int N, int M, int iters, double* d_scratch, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -73,6 +73,12 @@ size_t sinkhorn_scratch_doubles(int B, int N, int M);
 cudaError_t launch_sinkhorn_fused(const double* C, double* u, double* v, double* scratch, int B, int N, int M,
                                   int iters, cudaStream_t st, bool k32 = false);
 
+// Backward of log_optimal_transport (training path, sinkhorn_bwd.cu): gC = dL/d(couplings) from G = dL/dZ; the int behind the
+// scratch doubles is set when a row of the couplings spans more than 600 (scaling form not representable)
+size_t sinkhorn_bwd_scratch_doubles(int B, int N, int M, int iters);
+cudaError_t launch_sinkhorn_backward(const double* C, const double* G, double* gC, double* scratch, int B, int N, int M,
+                                     int iters, cudaStream_t st);
+
 struct MatchParams {
     const double* C; const double* u; const double* v;
     int B, N, M;

@@ -581,7 +581,13 @@ class MDGAT(nn.Module):
         desc0, desc1 = self.gnn(desc0, desc1, self.k, self.config['L'])
         md0, md1 = self.final_proj(desc0), self.final_proj(desc1)
         scores = torch.einsum('bdn,bdm->bnm', md0, md1) / self.config['descriptor_dim'] ** .5
-        Z = log_optimal_transport(scores, self.bin_score, self.config['sinkhorn_iterations'])
+        if scores.is_cuda and scores.dtype == torch.float64 and self.config.get('cuda_sinkhorn_backward', True):
+            # forward on the fused Sinkhorn kernel, hand-written reverse sweep in backward (csrc/sinkhorn_bwd.cu): nothing
+            # but the couplings is retained, where autograd through the unrolled loop keeps 2 T (B, N+1, M+1) tensors
+            from .. import ops
+            Z = ops.log_optimal_transport(scores, self.bin_score, self.config['sinkhorn_iterations'])
+        else:
+            Z = log_optimal_transport(scores, self.bin_score, self.config['sinkhorn_iterations'])
         m0, m1, ms0, ms1 = extract_matches_torch(Z, self.loss_method, self.mutual_check, self.config['match_threshold'])
         n, m = kpts0.shape[1], kpts1.shape[1]
         loss = None

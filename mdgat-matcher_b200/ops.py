@@ -120,6 +120,57 @@ def sinkhorn(scores, bin_score, iters, fused=True, return_status=False, k32=Fals
     return C, u, v
 
 
+def sinkhorn_backward(couplings, gZ, iters):
+    """dL/d(couplings) (B,N+1,M+1) of Z = log_optimal_transport from dL/dZ, by the hand-written reverse sweep
+    (csrc/sinkhorn_bwd.cu); `couplings` must carry the dustbin row / column (what sinkhorn() returns as its first result)."""
+    _need_cuda(couplings)
+    B, N, M = couplings.shape[0], couplings.shape[1] - 1, couplings.shape[2] - 1
+    dev = couplings.device
+    C = couplings.double().contiguous()
+    G = gZ.double().contiguous()
+    out = torch.empty_like(C)
+    scratch = torch.empty(_capi.lib.mdgat_sinkhorn_backward_scratch_doubles(B, N, M, int(iters)), dtype=torch.float64, device=dev)
+    ill = ctypes.c_int(0)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib.mdgat_sinkhorn_backward_f64(C.data_ptr(), G.data_ptr(), out.data_ptr(), B, N, M, int(iters),
+                                                          scratch.data_ptr(), ctypes.byref(ill), _stream(dev)))
+    if ill.value:
+        raise RuntimeError("mdgat-matcher_b200: a row of the Sinkhorn couplings spans more than 600 -- the scaling-form backward "
+                           "cannot represent it; set config['cuda_sinkhorn_backward'] = False to back-propagate through the "
+                           "unrolled torch iterations instead")
+    return out
+
+
+class LogOptimalTransportFn(torch.autograd.Function):
+    """log_optimal_transport (mdgat.py:279-308) for the training path: forward = the fused float64 Sinkhorn kernel, backward =
+    the hand-written reverse sweep. Nothing but the couplings is kept between the two (autograd through the reference's
+    unrolled loop retains 2 T tensors of shape (B, N+1, M+1))."""
+
+    @staticmethod
+    def forward(ctx, scores, alpha, iters):
+        B, N, M = scores.shape
+        C, u, v = sinkhorn(scores.detach(), alpha.detach(), iters, fused=True, k32=False)
+        ctx.save_for_backward(C)
+        ctx.iters = int(iters)
+        ctx.in_dtype = scores.dtype
+        norm = -math.log(N + M)
+        return C + u[:, :, None] + v[:, None, :] - norm
+
+    @staticmethod
+    def backward(ctx, gZ):
+        C, = ctx.saved_tensors
+        gC = sinkhorn_backward(C, gZ, ctx.iters)
+        N, M = C.shape[1] - 1, C.shape[2] - 1
+        g_scores = gC[:, :N, :M].to(ctx.in_dtype)
+        g_alpha = gC[:, N, :].sum() + gC[:, :N, M].sum()          # every dustbin entry holds alpha (mdgat.py:294-299)
+        return g_scores, g_alpha.reshape(()), None
+
+
+def log_optimal_transport(scores, alpha, iters):
+    """Differentiable Z (B,N+1,M+1) on the CUDA kernels; scores (B,N,M) float64, alpha a 0-dim tensor."""
+    return LogOptimalTransportFn.apply(scores, alpha.reshape(()), int(iters))
+
+
 def match_extract(C, u, v, loss_method='triplet_loss', mutual_check=False, match_threshold=0.2,
                   gt0=None, gt1=None, gamma=0.5, want_Z=False):
     """Match extraction (mdgat.py:442-483) and, with gt given, the loss of `loss_method` (mdgat.py:487-594) from the

@@ -201,6 +201,16 @@ int mdgat_sinkhorn_f64(double* d_couplings, const double* d_bin_score, double* d
 int mdgat_sinkhorn_f64_k32(double* d_couplings, const double* d_bin_score, double* d_u, double* d_v,
                            int B, int N, int M, int iters, double* d_scratch, void* stream);
 
+/* Training path: hand-written backward of attention() / dynamic_attention() (mdgat.py:190-210), one side.
+ * d_Q (B,4,N,36), d_K (B,4,M,36), d_V (B,4,M,34) head-major as for mdgat_attention_f64; d_O = the forward's message and
+ * d_dO = its gradient as (B,4,N,32); outputs d_dQ (B,4,N,32), d_dK, d_dV (B,4,M,32). The probabilities are recomputed tile by
+ * tile (nothing of size N x M is kept from the forward); for topk > 0 the kept set is rebuilt exactly (ties included) from
+ * the dense logits of the forward's own kernel. d_scratch: mdgat_attention_backward_scratch_doubles(B, N, M, topk) doubles. */
+size_t mdgat_attention_backward_scratch_doubles(int B, int N, int M, int topk);
+int mdgat_attention_backward_f64(const double* d_Q, const double* d_K, const double* d_V, const double* d_O, const double* d_dO,
+                                 double* d_dQ, double* d_dK, double* d_dV, int B, int N, int M, int topk, double* d_scratch,
+                                 void* stream);
+
 /* Training path: hand-written backward of log_optimal_transport (mdgat.py:279-308). d_couplings: the
  * (B,N+1,M+1) couplings WITH the dustbin row / column filled (what mdgat_sinkhorn_f64 leaves in place), d_gZ = dL/dZ of the
  * same shape, d_gcouplings (out) = dL/d(couplings) -- the caller takes [:, :N, :M] for the scores and the sum over the dustbin

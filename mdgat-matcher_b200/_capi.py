@@ -69,6 +69,8 @@ def _load():
         'mdgat_sinkhorn_scratch_doubles': (sz, [i, i, i]),
         'mdgat_sinkhorn_read_status': (i, [vp, i, i, i, C.POINTER(i), C.POINTER(i)]),
         'mdgat_sinkhorn_f64': (i, [vp, vp, vp, vp, i, i, i, i, vp, vp]),
+        'mdgat_attention_backward_scratch_doubles': (sz, [i, i, i, i]),
+        'mdgat_attention_backward_f64': (i, [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp]),
         'mdgat_sinkhorn_backward_scratch_doubles': (sz, [i, i, i, i]),
         'mdgat_sinkhorn_backward_f64': (i, [vp, vp, vp, i, i, i, i, vp, C.POINTER(i), vp]),
         'mdgat_sinkhorn_f64_k32': (i, [vp, vp, vp, vp, i, i, i, i, vp, vp]),

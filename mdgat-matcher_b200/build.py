@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 OBJDIR = os.path.join(HERE, 'build')
 LIB = os.path.join(LIBDIR, 'libmdgat_b200.so')
-SOURCES = ['gemm_f64.cu', 'attention_f64.cu', 'sinkhorn.cu', 'sinkhorn_bwd.cu', 'match.cu', 'misc.cu', 'registration.cu', 'prepare.cu', 'ozaki_gemm.cu', 'attention_i8.cu', 'capi.cu']
+SOURCES = ['gemm_f64.cu', 'attention_f64.cu', 'attention_bwd.cu', 'sinkhorn.cu', 'sinkhorn_bwd.cu', 'match.cu', 'misc.cu', 'registration.cu', 'prepare.cu', 'ozaki_gemm.cu', 'attention_i8.cu', 'capi.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']

@@ -575,6 +575,19 @@ int mdgat_sinkhorn_read_status(const double* d_scratch, int B, int N, int M, int
     return MDGAT_OK;
 }
 
+size_t mdgat_attention_backward_scratch_doubles(int B, int N, int M, int topk) { return attention_bwd_scratch_doubles(B, N, M, topk); }
+
+int mdgat_attention_backward_f64(const double* d_Q, const double* d_K, const double* d_V, const double* d_O, const double* d_dO,
+                                 double* d_dQ, double* d_dK, double* d_dV, int B, int N, int M, int topk, double* d_scratch,
+                                 void* stream) {
+    MDGAT_REQUIRE(B > 0 && N > 0 && M > 0 && d_Q && d_K && d_V && d_O && d_dO && d_dQ && d_dK && d_dV && d_scratch, "mdgat_attention_backward_f64: bad arguments");
+    MDGAT_REQUIRE(topk <= M, "selected index k out of range (k=%d, M=%d)", topk, M);
+    MDGAT_REQUIRE(topk <= 0 || M <= 2048, "mdgat_attention_backward_f64: top-k supports at most 2048 sources (M=%d)", M);
+    MDGAT_CUDA_OK(launch_attention_backward(d_Q, d_K, d_V, d_O, d_dO, d_dQ, d_dK, d_dV, B, N, M, topk > 0 ? topk : 0, d_scratch,
+                                            reinterpret_cast<cudaStream_t>(stream)));
+    return MDGAT_OK;
+}
+
 size_t mdgat_sinkhorn_backward_scratch_doubles(int B, int N, int M, int iters) { return sinkhorn_bwd_scratch_doubles(B, N, M, iters); }
 
 int mdgat_sinkhorn_backward_f64(const double* d_couplings, const double* d_gZ, double* d_gcouplings, int B, int N, int M,

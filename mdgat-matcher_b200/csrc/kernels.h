@@ -73,6 +73,13 @@ size_t sinkhorn_scratch_doubles(int B, int N, int M);
 cudaError_t launch_sinkhorn_fused(const double* C, double* u, double* v, double* scratch, int B, int N, int M,
                                   int iters, cudaStream_t st, bool k32 = false);
 
+// Backward of attention() / dynamic_attention() (training path, attention_bwd.cu): head-major Qh, Kh (ld 36), Vh (ld 34), message
+// O and its gradient dO as (B,4,N,32); outputs dQ (B,4,N,32), dK, dV (B,4,M,32)
+size_t attention_bwd_scratch_doubles(int B, int N, int M, int topk);
+cudaError_t launch_attention_backward(const double* Qh, const double* Kh, const double* Vh, const double* O, const double* dO,
+                                      double* dQ, double* dK, double* dV, int B, int N, int M, int topk, double* scratch,
+                                      cudaStream_t st);
+
 // Backward of log_optimal_transport (training path, sinkhorn_bwd.cu): gC = dL/d(couplings) from G = dL/dZ; the int behind the
 // scratch doubles is set when a row of the couplings spans more than 600 (scaling form not representable)
 size_t sinkhorn_bwd_scratch_doubles(int B, int N, int M, int iters);

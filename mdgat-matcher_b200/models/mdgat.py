@@ -119,6 +119,7 @@ class DescriptorEncoder(nn.Module):
 
 class MultiHeadedAttention(nn.Module):
     """q/k/v 1x1 projections, 4 heads with channel c = d*4 + h, full or top-k softmax, merge."""
+    cuda_fn = True          # CUDA tensors in float64: attention forward + hand-written backward kernels (config['cuda_attention_backward'])
 
     def __init__(self, num_heads, d_model):
         super().__init__()
@@ -132,6 +133,11 @@ class MultiHeadedAttention(nn.Module):
         b = x.size(0)
         q, key, val = [f(t).view(b, self.dim, self.num_heads, -1)
                        for f, t in zip(self.proj, (x, source, source))]
+        if self.cuda_fn and x.is_cuda and x.dtype == torch.float64 and self.dim == 32 and self.num_heads == 4:
+            # forward and backward on the CUDA kernels (ops.AttentionFn): the (B,4,N,M) probabilities are never kept
+            from .. import ops
+            msg = ops.attention_autograd(q.reshape(b, 128, -1), key.reshape(b, 128, -1), val.reshape(b, 128, -1), k)
+            return self.merge(msg)
         logits = torch.einsum('bdhn,bdhm->bhnm', q, key) / self.dim ** .5
         if k is None:
             prob = torch.softmax(logits, dim=-1)
@@ -256,6 +262,9 @@ class MDGAT(nn.Module):
         self.mutual_check = config['mutual_check']
         self.triplet_loss_gamma = config['triplet_loss_gamma']
         self.train_step = config['train_step']
+        for m in self.modules():
+            if isinstance(m, MultiHeadedAttention):
+                m.cuda_fn = bool(self.config.get('cuda_attention_backward', True))
         self._pack_cache = _PackedWeights()     # shared by reference with DataParallel replicas
         self._is_replica = False
         self._workspaces = {}                   # device -> uint8 tensor (shared dict: one workspace per device)

@@ -96,6 +96,53 @@ def attention(q, k, v, topk=None, engine='dmma', slices=7, p_slices=0):
     return msg.permute(0, 3, 2, 1).reshape(B, 128, N).contiguous()  # channel c = d*4 + h
 
 
+class AttentionFn(torch.autograd.Function):
+    """attention() / dynamic_attention() of mdgat.py:190-210 for the training path: forward = the CUDA kernels (float64 DMMA
+    flash attention, exact top-k), backward = the hand-written tile-recompute kernels of csrc/attention_bwd.cu. Only q, k, v
+    and the message are kept for backward; autograd through the reference formulation keeps the (B,4,N,M) probabilities."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, topk):
+        _need_cuda(q)
+        B, _, N = q.shape
+        M = k.shape[2]
+        kk = int(topk) if topk else 0
+        qh, kh, vh = to_head_major(q.detach(), LDH_QK), to_head_major(k.detach(), LDH_QK), to_head_major(v.detach(), LDH_V)
+        out = torch.empty((B * N, LDX), dtype=torch.float64, device=q.device)
+        logits = torch.empty(max(B * 4 * N * M, _capi.lib.mdgat_attention_f64_scratch_doubles(B, N, M)), dtype=torch.float64,
+                             device=q.device) if kk > 0 else None
+        with torch.cuda.device(q.device):
+            _capi.check(_capi.lib.mdgat_attention_f64(qh.data_ptr(), kh.data_ptr(), vh.data_ptr(), out.data_ptr(), LDX, B, N, M, kk,
+                                                      logits.data_ptr() if logits is not None else None, _stream(q.device)))
+        oh = out[:, :128].reshape(B, N, 4, 32).permute(0, 2, 1, 3).contiguous()        # (B, h, N, d)
+        ctx.save_for_backward(qh, kh, vh, oh)
+        ctx.kk, ctx.dtypes = kk, (q.dtype, k.dtype, v.dtype)
+        return oh.permute(0, 3, 1, 2).reshape(B, 128, N)                               # channel c = d*4 + h
+
+    @staticmethod
+    def backward(ctx, g):
+        qh, kh, vh, oh = ctx.saved_tensors
+        B, _, N, _ = qh.shape
+        M = kh.shape[2]
+        dev = qh.device
+        doh = g.double().reshape(B, 32, 4, N).permute(0, 2, 3, 1).contiguous()         # (B, h, N, d)
+        dq = torch.empty((B, 4, N, 32), dtype=torch.float64, device=dev)
+        dk = torch.empty((B, 4, M, 32), dtype=torch.float64, device=dev)
+        dv = torch.empty((B, 4, M, 32), dtype=torch.float64, device=dev)
+        scratch = torch.empty(_capi.lib.mdgat_attention_backward_scratch_doubles(B, N, M, ctx.kk), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _capi.check(_capi.lib.mdgat_attention_backward_f64(qh.data_ptr(), kh.data_ptr(), vh.data_ptr(), oh.data_ptr(), doh.data_ptr(),
+                                                               dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, N, M, ctx.kk,
+                                                               scratch.data_ptr(), _stream(dev)))
+        back = lambda t, n, dt: t.permute(0, 3, 1, 2).reshape(B, 128, n).to(dt)
+        return back(dq, N, ctx.dtypes[0]), back(dk, M, ctx.dtypes[1]), back(dv, M, ctx.dtypes[2]), None
+
+
+def attention_autograd(q, k, v, topk=None):
+    """Differentiable message (B,128,N) of attention() / dynamic_attention() on the CUDA kernels (forward and backward)."""
+    return AttentionFn.apply(q, k, v, topk)
+
+
 def sinkhorn(scores, bin_score, iters, fused=True, return_status=False, k32=False):
     """scores (B,N,M) -> (couplings, u, v) with Z = couplings + u[:, :, None] + v[:, None, :] - norm
     = log_optimal_transport(scores, bin_score, iters). fused=False uses one launch per half-iteration; k32=True stores

@@ -288,6 +288,69 @@ def test_sinkhorn_backward_vs_autograd(dev, N, M, iters):
     assert abs(a1.grad.item() - a2.grad.item()) < 1e-9 * max(1.0, abs(a1.grad.item()))
 
 
+def _torch_attention(q, k, v, topk):
+    """attention() / dynamic_attention() as the reference writes them (mdgat.py:190-210), on (B,128,n) inputs."""
+    b = q.shape[0]
+    qh, kh, vh = [t.view(b, 32, 4, -1) for t in (q, k, v)]
+    scores = torch.einsum('bdhn,bdhm->bhnm', qh, kh) / 32 ** .5
+    if topk is None:
+        prob = torch.nn.functional.softmax(scores, dim=-1)
+    else:
+        idx = scores.topk(topk, dim=3, largest=True, sorted=True).indices
+        prob = torch.zeros_like(scores).scatter(3, idx, torch.nn.functional.softmax(scores.gather(3, idx), dim=-1))
+    return torch.einsum('bhnm,bdhm->bdhn', prob, vh).contiguous().view(b, 128, -1)
+
+
+@pytest.mark.parametrize('N,M,topk', [(128, 128, None), (200, 77, None), (64, 300, None), (512, 512, None),
+                                      (128, 128, 64), (200, 300, 128), (96, 1000, 64), (512, 512, 128), (70, 160, 160)])
+def test_attention_backward_vs_autograd(dev, N, M, topk):
+    """Hand-written attention backward (csrc/attention_bwd.cu: tile recompute, exact kept set for the top-k layers) against
+    autograd through the reference formulation: message and the gradients of q, k, v for a random upstream gradient."""
+    from mdgat_matcher_b200 import ops
+    g = torch.Generator().manual_seed(N + 3 * M + (topk or 0))
+    B = 2
+    q = (torch.randn(B, 128, N, generator=g, dtype=torch.float64) * 1.5).to(dev)
+    k = (torch.randn(B, 128, M, generator=g, dtype=torch.float64) * 1.5).to(dev)
+    v = torch.randn(B, 128, M, generator=g, dtype=torch.float64).to(dev)
+    up = torch.randn(B, 128, N, generator=g, dtype=torch.float64).to(dev)
+    a = [t.clone().requires_grad_(True) for t in (q, k, v)]
+    o1 = _torch_attention(*a, topk)
+    (o1 * up).sum().backward()
+    c = [t.clone().requires_grad_(True) for t in (q, k, v)]
+    o2 = ops.attention_autograd(*c, topk)
+    assert (o1 - o2).abs().max().item() < 1e-11
+    (o2 * up).sum().backward()
+    for x, y, name in zip(a, c, 'qkv'):
+        assert (x.grad - y.grad).abs().max().item() < 1e-10 * max(1.0, x.grad.abs().max().item()), name
+
+
+@pytest.mark.parametrize('cfg_key', ['cuda_attention_backward', 'both'])
+def test_train_mode_cuda_attention_matches_torch_path(dev, cfg_key):
+    """train(): attention (and Sinkhorn) forward + hand-written backward on the CUDA kernels against the all-torch path: same
+    loss, same gradient for every parameter (L = 2 with one top-k and one full layer per kind)."""
+    from mdgat_matcher_b200 import synth
+    from mdgat_matcher_b200.models.mdgat import MDGAT
+    from oracle.ref_loader import net_config
+    grads, losses = [], []
+    for cuda in (True, False):
+        cfg = net_config(L=2, sinkhorn_iterations=20, k=[16, None, 16, None])
+        cfg['cuda_attention_backward'] = cuda
+        cfg['cuda_sinkhorn_backward'] = cuda and cfg_key == 'both'
+        net = MDGAT(cfg)
+        net.load_state_dict(synth.seeded_state_dict(2, 0))
+        net = net.double().train().to(dev)
+        data = {k: v.to(dev) for k, v in synth.make_batch(3, 4, 64).items()}
+        out = net(data)
+        out['loss'].backward()
+        losses.append(float(out['loss'].detach()))
+        grads.append({n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None})
+    assert abs(losses[0] - losses[1]) < 1e-10
+    assert set(grads[0]) == set(grads[1])
+    for n in grads[0]:
+        ref = grads[1][n]
+        assert (grads[0][n] - ref).abs().max().item() <= 1e-8 * max(1.0, ref.abs().max().item()), n
+
+
 def test_train_mode_uses_cuda_sinkhorn_and_matches_torch_path(dev):
     """train(): the differentiable torch path with the Sinkhorn stage on the CUDA kernels (forward + hand-written backward)
     gives the same loss and the same parameter gradients as the all-torch path."""
@@ -298,6 +361,7 @@ def test_train_mode_uses_cuda_sinkhorn_and_matches_torch_path(dev):
     for cuda_bwd in (True, False):
         cfg = net_config(L=2, sinkhorn_iterations=20, k=[16, None])
         cfg['cuda_sinkhorn_backward'] = cuda_bwd
+        cfg['cuda_attention_backward'] = False
         torch.manual_seed(0)
         net = MDGAT(cfg)
         net.load_state_dict(synth.seeded_state_dict(2, 0))

@@ -26,9 +26,10 @@ def main():
     sd, _ = load_weights(9)
     data = {k: v.to(dev) for k, v in synth.make_batch(5, B, n).items()}
     res = {'batch': B, 'n': n, 'sinkhorn_iterations': T}
-    for cuda_bwd in (True, False):
+    for name, cuda_attn, cuda_sk in (('cuda_attention+sinkhorn', True, True), ('cuda_sinkhorn', False, True), ('torch', False, False)):
         cfg = net_config(9, T)
-        cfg['cuda_sinkhorn_backward'] = cuda_bwd
+        cfg['cuda_sinkhorn_backward'] = cuda_sk
+        cfg['cuda_attention_backward'] = cuda_attn
         net = MDGAT(cfg)
         net.load_state_dict(sd)
         net = net.double().train().to(dev)
@@ -44,7 +45,7 @@ def main():
             out['loss'].backward()
             torch.cuda.synchronize()
             times.append((time.perf_counter() - t0) * 1e3)
-        res['cuda_sinkhorn' if cuda_bwd else 'torch_sinkhorn'] = {
+        res[name] = {
             'step_ms': round(min(times[1:]), 2), 'peak_gb': round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 3),
             'loss': float(out['loss'].detach())}
         del net, out

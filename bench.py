@@ -457,6 +457,12 @@ def main():
                                 'note': 'algorithmic float64 FLOPs of the stage (SURVEY 8d) over its device time, against the DMMA ceiling '
                                         'the reference arithmetic would be bound by'},
             'algorithmic_ops_per_step': i8_ops,
+            'frac_note': 'frac counts the int8 digit-plane operations the kernel issues, so it falls when a precision setting needs fewer '
+                         'planes: round 1 ran 58 digit products per attention contraction (frac 0.19 at 4.02 ms per forward), this build '
+                         '%d (the stage takes %.2f ms). The kernel is bound by its SIMT epilogue (ncu: issue slots 55 %%, FP64 pipe 20 %%, '
+                         'tensor pipe 14 %%), not by the tensor pipe; fp64_equivalent is the algorithmic float64 rate of SURVEY 8d.'
+                         % (qk + p1 + pv, per_step[dominant]) if dominant == 'attn_full' else
+                         'frac counts the int8 digit-plane operations the kernel issues (15 products per float64 GEMM at 5 planes)',
         }
     else:
         roofline = {

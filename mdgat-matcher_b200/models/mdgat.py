@@ -133,7 +133,8 @@ class MultiHeadedAttention(nn.Module):
         b = x.size(0)
         q, key, val = [f(t).view(b, self.dim, self.num_heads, -1)
                        for f, t in zip(self.proj, (x, source, source))]
-        if self.cuda_fn and x.is_cuda and x.dtype == torch.float64 and self.dim == 32 and self.num_heads == 4:
+        if self.cuda_fn and x.is_cuda and x.dtype == torch.float64 and self.dim == 32 and self.num_heads == 4 \
+                and (k is None or source.shape[-1] <= 2048) and min(x.shape[-1], source.shape[-1]) > 0:
             # forward and backward on the CUDA kernels (ops.AttentionFn): the (B,4,N,M) probabilities are never kept
             from .. import ops
             msg = ops.attention_autograd(q.reshape(b, 128, -1), key.reshape(b, 128, -1), val.reshape(b, 128, -1), k)

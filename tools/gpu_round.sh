@@ -20,7 +20,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 else
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"attn_i8_kernel" -s 6 -c 2 -o gpurun_out/${P}_prof_attn -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-eager --no-latency > gpurun_out/${P}_ncu_attn.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:"ozaki_gemm_kernel" -s 30 -c 3 -o gpurun_out/${P}_prof_gemm -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-eager --no-latency > gpurun_out/${P}_ncu_gemm.log 2>&1
-timeout 600 ncu --set full --clock-control none -k regex:"slice_rows|slice_qk|slice_v|topk_softmax_pv|attn_full_kernel|sinkhorn_fused|gemm_f64" -s 30 -c 14 -o gpurun_out/${P}_prof_misc -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-eager --no-latency > gpurun_out/${P}_ncu_misc.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:"topk_softmax_pv|attn_full_kernel|sinkhorn_fused" -c 5 -o gpurun_out/${P}_prof_topk -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-eager --no-latency > gpurun_out/${P}_ncu_topk.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:"slice_rows|slice_qk|slice_v|gemm_f64" -s 30 -c 10 -o gpurun_out/${P}_prof_misc -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-eager --no-latency > gpurun_out/${P}_ncu_misc.log 2>&1
 for r in gpurun_out/${P}_prof_*.ncu-rep; do ncu -i $r --page raw --csv > ${r%.ncu-rep}_raw.csv 2>/dev/null; done
 ls -la gpurun_out
 # keep the copy-back under 64 MiB: drop the largest report(s) if needed (their raw CSV stays)

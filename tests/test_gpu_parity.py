@@ -587,6 +587,30 @@ def test_superglue_module_is_full_attention_mdgat(dev):
     assert np.abs(out['matching_scores0'].cpu().numpy() - rec['matching_scores0']).max() <= 1e-6
 
 
+@pytest.mark.parametrize('loss_method', ['triplet_loss', 'gap_loss'])
+def test_cuda_graph_replay_is_bit_identical(dev, loss_method):
+    """config['cuda_graph']: the captured launch sequence replayed on new inputs gives exactly what plain launches give
+    (scalar loss and the per-pair gap_loss vector), and a second batch through the same graph is not stale."""
+    from mdgat_matcher_b200 import synth
+    from mdgat_matcher_b200.models.mdgat import MDGAT
+    from oracle.ref_loader import net_config
+    nets = []
+    for graph in (False, True):
+        cfg = net_config(L=4, sinkhorn_iterations=20, loss_method=loss_method)
+        cfg['cuda_graph'] = graph
+        net = MDGAT(cfg)
+        net.load_state_dict(synth.seeded_state_dict(4, 0))
+        nets.append(net.double().eval().to(dev))
+    for seed in (1, 2, 3):                                   # the first call captures, the others replay
+        data = synth.make_batch(seed, 3, 128)
+        outs = [net({k: v.clone().to(dev) for k, v in data.items()}) for net in nets]
+        torch.cuda.synchronize()
+        for key in ('matches0', 'matches1', 'matching_scores0', 'matching_scores1', 'loss'):
+            assert torch.equal(outs[0][key], outs[1][key]), (seed, key)
+        assert outs[1]['loss'].shape == ((3,) if loss_method == 'gap_loss' else ())
+    assert len(nets[1]._graphs) == 1
+
+
 def test_k_larger_than_M_raises_and_empty_returns(dev):
     rec = load_golden('cfg1_seeded_L4_n128')
     net = _build_module(rec['case'], dev)

@@ -28,7 +28,7 @@ REF_COPY = os.path.join(REF_DIR, 'reference')
 REFERENCE_ROOT = os.environ.get('MDGAT_REFERENCE_ROOT', '/root/reference')
 CHECKPOINT = REFERENCE_ROOT + '/pre-trained/best_model.pth'
 REF_FILES = ('models/mdgat.py', 'models/superglue.py', 'models/pointnet/pointnet_util.py',
-             'test.py', 'test_registration_metric.py', 'load_data.py', 'utils/utils_test.py')
+             'test.py', 'test_registration_metric.py', 'train.py', 'load_data.py', 'utils/utils_test.py')
 
 
 def build_weights(force=False):

@@ -106,3 +106,38 @@ def test_registration_metric_script_runs_unchanged_and_agrees(tmp_path):
     for a, b, tol in zip(mine, s, [6e-4, 6e-2, 6e-4, 6e-4, 6e-4, 6e-4, 6e-4, 6e-4, 6e-4, 6e-4]):
         assert abs(a - b) <= tol, (mine, s)
     assert mean['rr'] > 0.5 and mean['prec'] > 0.5, mean                  # the matcher actually registers the synthetic pairs
+
+
+def test_train_script_runs_unchanged_for_one_epoch(tmp_path):
+    """The reference's UNCHANGED train.py (/root/reference/train.py:125-300) for one epoch through the launcher on synthetic
+    KITTI-format sequences (train split 00, 02-07, validation split 09): the training steps run the drop-in's differentiable
+    path (attention and Sinkhorn forward + hand-written backward on the CUDA kernels, gap_loss), the validation pass its CUDA
+    inference path (gap_loss on the device), and the checkpoint the script saves loads back into the drop-in."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from mdgat_matcher_b200 import kitti_io
+    from mdgat_matcher_b200.models.mdgat import MDGAT
+    from oracle.ref_loader import net_config
+    script = _script('train.py')
+    n = 128
+    for seq in (0, 2, 3, 4, 5, 6, 7, 9):
+        # saliency 32 +- 10 as in the real keypoint files: train.py's loader keeps saliency > 10 only (ensure_kpts_num,
+        # load_data.py:180-211) and loops forever on a pair it leaves without keypoints
+        dirs = kitti_io.write_synthetic_sequence(str(tmp_path / 'KITTI'), seq=seq, frames=6, n_kpts=n, n_landmarks=200, seed=20 + seq,
+                                                 step=1.0, saliency_scale=1.0)
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES=os.environ.get('CUDA_VISIBLE_DEVICES', '0').split(',')[0])
+    cmd = [sys.executable, '-m', 'mdgat_matcher_b200.launcher', script,
+           '--train_path', dirs['train_path'], '--txt_path', dirs['txt_path'], '--keypoints_path', dirs['keypoints_path'],
+           '--max_keypoints', str(n), '--batch_size', '2', '--epoch', '1', '--l', '9', '--sinkhorn_iterations', '20']
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    m = re.search(r'Validation loss: ([-\d.naninf]+), epoch_loss: ([-\d.naninf]+)', r.stdout)
+    assert m, r.stdout[-2000:]
+    val_loss, epoch_loss = float(m.group(1)), float(m.group(2))
+    assert np.isfinite(val_loss) and np.isfinite(epoch_loss) and epoch_loss > 0
+    saved = [os.path.join(dp, f) for dp, _, fs in os.walk(str(tmp_path / 'checkpoint')) for f in fs if f.endswith('.pth')]
+    assert len(saved) == 1, saved
+    ck = torch.load(saved[0], map_location='cpu', weights_only=False)
+    net = torch.nn.DataParallel(MDGAT(net_config(L=9, sinkhorn_iterations=20, loss_method='gap_loss')))
+    net.load_state_dict(ck['net'])                                           # strict: the drop-in's parameter names are the reference's
+    assert ck['epoch'] == 1 and abs(ck['loss'] - val_loss) < 1e-3

@@ -375,19 +375,30 @@ class MDGAT(nn.Module):
         the tail is float32-safe): on for 'sweep' precision, off for 'exact'; config['sinkhorn_k32'] overrides."""
         return bool(self.config.get('sinkhorn_k32', self.config.get('precision', 'sweep') == 'sweep'))
 
-    def gemm_engine(self):
-        """config['gemm']: 'tcgen05_i8' (Ozaki splitting on the int8 tensor cores, default) or 'dmma' (FP64 pipe);
-        the number of int8 digit planes per operand comes from digit_planes()."""
-        mode = self.config.get('gemm', 'tcgen05_i8')
+    # Small problems are bound by the per-kernel fixed costs, not by arithmetic: measured on B200 (tools/latency_b1.py, batch 1,
+    # T = 20, ms per forward), R = 512 keypoint rows: 1.85 all-DMMA / 1.86 DMMA GEMM + tcgen05 attention / 2.04 all-tcgen05;
+    # R = 1024: 2.61 / 2.28 / 2.40; R = 2048: 2.69 / 2.28 / 2.19. The unset ('auto') engines follow that.
+    AUTO_DMMA_GEMM_ROWS = 1024
+    AUTO_DMMA_ATTN_ROWS = 512
+
+    def gemm_engine(self, rows=None):
+        """config['gemm']: 'tcgen05_i8' (Ozaki splitting on the int8 tensor cores) or 'dmma' (FP64 pipe); unset: tcgen05_i8
+        except for small problems (`rows` = keypoint rows of the call, see AUTO_DMMA_GEMM_ROWS). The number of int8 digit
+        planes per operand comes from digit_planes()."""
+        mode = self.config.get('gemm')
+        if mode is None:
+            mode = 'dmma' if (rows is not None and rows <= self.AUTO_DMMA_GEMM_ROWS) else 'tcgen05_i8'
         if mode not in ('tcgen05_i8', 'dmma'):
             raise ValueError("config['gemm'] must be 'tcgen05_i8' or 'dmma'")
         return mode, self.digit_planes()[0]
 
-    def attention_engine(self):
-        """config['attention']: 'tcgen05_i8' (default; Q K^T and P V of the full-attention layers as exact int8
-        digit products in TMEM, dense logits of the top-k layers from the DMMA kernel), 'tcgen05_i8_all' (top-k
-        layers on tcgen05 too) or 'dmma' (flash attention on the FP64 pipe)."""
-        mode = self.config.get('attention', 'tcgen05_i8')
+    def attention_engine(self, rows=None):
+        """config['attention']: 'tcgen05_i8' (Q K^T and P V of the full-attention layers as exact int8 digit products in
+        TMEM, dense logits of the top-k layers from the DMMA kernel), 'tcgen05_i8_all' (top-k layers on tcgen05 too) or 'dmma'
+        (flash attention on the FP64 pipe); unset: tcgen05_i8 except for small problems (AUTO_DMMA_ATTN_ROWS)."""
+        mode = self.config.get('attention')
+        if mode is None:
+            mode = 'dmma' if (rows is not None and rows <= self.AUTO_DMMA_ATTN_ROWS) else 'tcgen05_i8'
         if mode not in ('tcgen05_i8', 'tcgen05_i8_all', 'dmma'):
             raise ValueError("config['attention'] must be 'tcgen05_i8', 'tcgen05_i8_all' or 'dmma'")
         return mode
@@ -457,7 +468,9 @@ class MDGAT(nn.Module):
             if not self._is_replica and self._param_device() != dev:
                 raise RuntimeError('module parameters live on %s but inputs on %s' % (self._param_device(), dev))
             blob = self.packed_weights(dev)
-            gemm_mode, gemm_slices = self.gemm_engine()
+            rows = B * (N + M)
+            gemm_mode, gemm_slices = self.gemm_engine(rows)
+            attn_mode = self.attention_engine(rows)
             blob_i8 = self.packed_weights_i8(gemm_slices, dev) if gemm_mode == 'tcgen05_i8' else None
 
             loss_mode = _capi.LOSS_NONE
@@ -489,7 +502,7 @@ class MDGAT(nn.Module):
 
             karr = (ctypes.c_int * len(sched))(*sched)
             planes = self.digit_planes()
-            late = self.digit_planes_late(sched) if (gemm_mode == 'tcgen05_i8' or self.attention_engine() != 'dmma') else None
+            late = self.digit_planes_late(sched) if (gemm_mode == 'tcgen05_i8' or attn_mode != 'dmma') else None
             blob_i8_late = self.packed_weights_i8(late[1], dev) if (late and gemm_mode == 'tcgen05_i8') else None
             cfg = _capi.ForwardCfg(
                 B=B, N=N, M=M, L=L, sinkhorn_iters=int(self.config['sinkhorn_iterations']), layer_k=karr,
@@ -502,7 +515,7 @@ class MDGAT(nn.Module):
                 gemm_mode=_capi.GEMM_TCGEN05_I8 if gemm_mode == 'tcgen05_i8' else _capi.GEMM_DMMA_F64,
                 gemm_slices=gemm_slices,
                 attn_mode={'tcgen05_i8': _capi.ATTN_TCGEN05_I8, 'tcgen05_i8_all': _capi.ATTN_TCGEN05_I8_ALL,
-                           'dmma': _capi.ATTN_DMMA_F64}[self.attention_engine()],
+                           'dmma': _capi.ATTN_DMMA_F64}[attn_mode],
                 attn_slices=planes[1], attn_p_slices=planes[2], sinkhorn_k32=int(self.sinkhorn_k32()),
                 late_from=late[0] if late else 0, late_gemm_slices=late[1] if late else 0,
                 late_attn_slices=late[2] if late else 0, late_attn_p_slices=late[3] if late else 0,
@@ -544,7 +557,7 @@ class MDGAT(nn.Module):
                 # (shape, dtypes, weights, workspace) and replayed; the inputs are copied into the graph's static buffers
                 # and the results out of them, so the caller sees fresh tensors as with plain launches
                 key = (dev, B, N, M, in_dtype, sc[0].dtype, loss_mode, tuple(sched), tuple(planes), late, gemm_mode,
-                       self.attention_engine(), int(self.config['sinkhorn_iterations']), bool(self.mutual_check), self.sinkhorn_k32(),
+                       attn_mode, int(self.config['sinkhorn_iterations']), bool(self.mutual_check), self.sinkhorn_k32(),
                        blob.data_ptr(), blob_i8.data_ptr() if blob_i8 is not None else 0,
                        blob_i8_late.data_ptr() if blob_i8_late is not None else 0, ws.data_ptr())
                 ent = self._graphs.get(key)

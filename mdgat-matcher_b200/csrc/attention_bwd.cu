@@ -7,8 +7,8 @@
 //   D_i = dO_i . O_i,  dP = dO V^T,  dS = P o (dP - D_i),  dQ = dS K / sqrt(32),  dK = dS^T Q / sqrt(32),  dV = P^T dO
 //
 // Two kernels over 64 x 64 tiles of one (b, h): attn_bwd_q_kernel owns 64 query rows (row statistics in a first sweep over
-// the sources, dQ in a second), attn_bwd_kv_kernel owns 64 sources (dK, dV in one sweep over the queries). Plain FP64 FMAs
-// from shared-memory tiles: the training path is not the benchmarked one.
+// the sources, dQ in a second), attn_bwd_kv_kernel owns 64 sources (dK, dV in one sweep over the queries). All tile
+// products run on the FP64 tensor path (DMMA.8x8x4) from shared-memory tiles.
 // Top-k layers: the kept set must be the forward's, ties included, so the logits are not recomputed tile-wise (a different
 // summation order could move an entry across the threshold) but read from the dense logits the forward's own kernel
 // writes (launch_attention_logits) together with the per-row threshold / last tied column of launch_topk_threshold.
@@ -38,48 +38,53 @@ DEVINL void ab_load_tile(double* dst, const double* src, int ld, int r0, int n, 
     }
 }
 
-// this thread's 4 x 4 block (rows ty*4.., columns tx*4..) of A B^T for two 64 x 32 tiles
-DEVINL void ab_mm_nt(const double* A, const double* B, int ty, int tx, double (&acc)[4][4]) {
+// Tile products on the FP64 tensor path (mma.sync.m8n8k4.f64 -> DMMA.8x8x4). Warp w owns rows 8w .. 8w+7 of a tile; in a
+// C fragment lane l holds row 8w + l/4 and the column pair 2 (l%4), 2 (l%4) + 1 of every 8-column block.
+// c[nt][e] = (A B^T)[8w + l/4][8 nt + 2 (l%4) + e] for two 64 x 32 tiles A, B (pitch AB_P)
+DEVINL void ab_dmma_nt(const double* A, const double* B, int warp, int lane, double (&c)[8][2]) {
+    const int qr = lane >> 2, qc = lane & 3;
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int nt = 0; nt < 8; ++nt) c[nt][0] = c[nt][1] = 0.0;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-#pragma unroll 8
-    for (int d = 0; d < 32; ++d) {
-        double x[4], y[4];
+    for (int ks = 0; ks < 8; ++ks) {
+        const double a = A[(8 * warp + qr) * AB_P + ks * 4 + qc];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) x[a] = A[(ty * 4 + a) * AB_P + d];
+        for (int nt = 0; nt < 8; ++nt) dmma884(c[nt][0], c[nt][1], a, B[(nt * 8 + qr) * AB_P + ks * 4 + qc]);
+    }
+}
+// c[nt][e] += sum_k T'[8w + l/4][k] R[k][8 nt + 2 (l%4) + e] over the 64 k of a tile, R a 64 x 32 tile (pitch AB_P) and T' the
+// 64 x 64 tile Tt (pitch AB_PT) read as stored (TRANS = false: T' = Tt) or transposed (TRANS = true: T' = Tt^T)
+template <bool TRANS>
+DEVINL void ab_dmma_acc(const double* Tt, const double* R, int warp, int lane, double (&c)[4][2]) {
+    const int qr = lane >> 2, qc = lane & 3;
+#pragma unroll 4
+    for (int kk = 0; kk < 16; ++kk) {
+        const int k = kk * 4 + qc;
+        const double a = TRANS ? Tt[k * AB_PT + 8 * warp + qr] : Tt[(8 * warp + qr) * AB_PT + k];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) y[b] = B[(tx * 4 + b) * AB_P + d];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = fma(x[a], y[b], acc[a][b]);
+        for (int nt = 0; nt < 4; ++nt) dmma884(c[nt][0], c[nt][1], a, R[k * AB_P + nt * 8 + qr]);
     }
 }
 
-// scaled logits of this thread's 4 x 4 block: recomputed from the Q / K tiles, or read from the dense logits (top-k layers)
-DEVINL void ab_logits(const AttnBwdParams& p, long long bh, const double* Qs, const double* Ks, int i0, int j0, int ty, int tx,
-                      double (&s)[4][4]) {
+// scaled logits in C-fragment order: recomputed from the Q / K tiles, or read from the dense logits (top-k layers)
+DEVINL void ab_logits(const AttnBwdParams& p, long long bh, const double* Qs, const double* Ks, int i0, int j0, int warp, int lane,
+                      double (&s)[8][2]) {
     if (p.S == nullptr) {
-        ab_mm_nt(Qs, Ks, ty, tx, s);
+        ab_dmma_nt(Qs, Ks, warp, lane, s);
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) s[a][b] *= p.scale;
+        for (int nt = 0; nt < 8; ++nt) { s[nt][0] *= p.scale; s[nt][1] *= p.scale; }
     } else {
+        const int i = i0 + 8 * warp + (lane >> 2);
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int i = i0 + ty * 4 + a;
+        for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int j = j0 + tx * 4 + b;
-                s[a][b] = (i < p.N && j < p.M) ? p.S[(bh * p.N + i) * (long long)p.M + j] : 0.0;
+            for (int e = 0; e < 2; ++e) {
+                const int j = j0 + nt * 8 + 2 * (lane & 3) + e;
+                s[nt][e] = (i < p.N && j < p.M) ? p.S[(bh * p.N + i) * (long long)p.M + j] : 0.0;
             }
-        }
     }
 }
-// is source j of query row i in the softmax?
+// is source j of a query row in the softmax?
 DEVINL bool ab_kept(const AttnBwdParams& p, double s, int j, double thr, int jl) {
     if (j >= p.M) return false;
     if (p.S == nullptr) return true;
@@ -93,7 +98,7 @@ __global__ void __launch_bounds__(256) attn_bwd_q_kernel(const AttnBwdParams p) 
     double* Tt = dOs + AB_T * AB_P;                                  // [64][65] dS tile
     double* Dsm = Tt + AB_T * AB_PT; double* Lsm = Dsm + AB_T; double* Thr = Lsm + AB_T;
     __shared__ int Jl[AB_T];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, qr = lane >> 2, qc = lane & 3;
     const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * AB_T;
     const long long bh = (long long)b * HEADS + h;
     const double* Qg = p.Q + bh * p.N * p.ldq;
@@ -114,86 +119,64 @@ __global__ void __launch_bounds__(256) attn_bwd_q_kernel(const AttnBwdParams p) 
         if (i < p.N) p.dvec[bh * p.N + i] = d;
     }
     __syncthreads();
-    // ---- sweep 1: log-sum-exp over the kept set (online maximum; the 16 threads tx of a row group hold the same m, l)
-    double m[4], l[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) { m[a] = -INFINITY; l[a] = 0.0; }
+    const int r = 8 * warp + qr;                                     // this thread's row of the tile (shared by its quad)
+    const double thr = Thr[r]; const int jl = Jl[r];
+    // ---- sweep 1: log-sum-exp over the kept set (online maximum; the four lanes of a quad hold the same m, l)
+    double m = -INFINITY, l = 0.0;
     for (int j0 = 0; j0 < p.M; j0 += AB_T) {
         if (p.S == nullptr) { __syncthreads(); ab_load_tile(Ks, Kg, p.ldq, j0, p.M, tid); __syncthreads(); }
-        double s[4][4];
-        ab_logits(p, bh, Qs, Ks, i0, j0, ty, tx, s);
+        double s[8][2];
+        ab_logits(p, bh, Qs, Ks, i0, j0, warp, lane, s);
+        double mx = -INFINITY;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const double thr = Thr[ty * 4 + a]; const int jl = Jl[ty * 4 + a];
-            double mx = -INFINITY;
+        for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-            for (int bb = 0; bb < 4; ++bb) if (ab_kept(p, s[a][bb], j0 + tx * 4 + bb, thr, jl)) mx = fmax(mx, s[a][bb]);
+            for (int e = 0; e < 2; ++e) if (ab_kept(p, s[nt][e], j0 + nt * 8 + 2 * qc + e, thr, jl)) mx = fmax(mx, s[nt][e]);
+        mx = fmax(mx, shfl_xor_d(mx, 1));
+        mx = fmax(mx, shfl_xor_d(mx, 2));
+        const double mn = fmax(m, mx);
+        double sum = 0.0;
+        if (mn > -INFINITY) {
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) mx = fmax(mx, shfl_xor_d(mx, o));
-            const double mn = fmax(m[a], mx);
-            double sum = 0.0;
-            if (mn > -INFINITY) {
+            for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-                for (int bb = 0; bb < 4; ++bb) if (ab_kept(p, s[a][bb], j0 + tx * 4 + bb, thr, jl)) sum += exp(s[a][bb] - mn);
-            }
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) sum += shfl_xor_d(sum, o);
-            l[a] = (m[a] > -INFINITY ? l[a] * exp(m[a] - mn) : 0.0) + sum;
-            m[a] = mn;
+                for (int e = 0; e < 2; ++e) if (ab_kept(p, s[nt][e], j0 + nt * 8 + 2 * qc + e, thr, jl)) sum += exp(s[nt][e] - mn);
         }
+        sum += shfl_xor_d(sum, 1);
+        sum += shfl_xor_d(sum, 2);
+        l = (m > -INFINITY ? l * exp(m - mn) : 0.0) + sum;
+        m = mn;
     }
-    if (tx == 0) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const double lse = m[a] + log(l[a]);
-            Lsm[ty * 4 + a] = lse;
-            if (i0 + ty * 4 + a < p.N) p.lse[bh * p.N + i0 + ty * 4 + a] = lse;
-        }
-    }
-    __syncthreads();
+    const double lse = m + log(l);
+    if (qc == 0 && i0 + r < p.N) p.lse[bh * p.N + i0 + r] = lse;
+    const double dd = Dsm[r];
     // ---- sweep 2: dQ = sum_j dS_ij K_j
     double dq[4][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) dq[a][0] = dq[a][1] = 0.0;
+    for (int nt = 0; nt < 4; ++nt) dq[nt][0] = dq[nt][1] = 0.0;
     for (int j0 = 0; j0 < p.M; j0 += AB_T) {
         __syncthreads();
         ab_load_tile(Ks, Kg, p.ldq, j0, p.M, tid);
         ab_load_tile(Vs, Vg, p.ldv, j0, p.M, tid);
         __syncthreads();
-        double s[4][4], dp[4][4];
-        ab_logits(p, bh, Qs, Ks, i0, j0, ty, tx, s);
-        ab_mm_nt(dOs, Vs, ty, tx, dp);
+        double s[8][2], dp[8][2];
+        ab_logits(p, bh, Qs, Ks, i0, j0, warp, lane, s);
+        ab_dmma_nt(dOs, Vs, warp, lane, dp);
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int r = ty * 4 + a;
-            const double thr = Thr[r], lse = Lsm[r], dd = Dsm[r]; const int jl = Jl[r];
+        for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-            for (int bb = 0; bb < 4; ++bb) {
-                const bool keep = ab_kept(p, s[a][bb], j0 + tx * 4 + bb, thr, jl);
-                const double pr = keep ? exp(s[a][bb] - lse) : 0.0;
-                Tt[r * AB_PT + tx * 4 + bb] = pr * (dp[a][bb] - dd);
+            for (int e = 0; e < 2; ++e) {
+                const int c = nt * 8 + 2 * qc + e;
+                const double pr = ab_kept(p, s[nt][e], j0 + c, thr, jl) ? exp(s[nt][e] - lse) : 0.0;
+                Tt[r * AB_PT + c] = pr * (dp[nt][e] - dd);
             }
-        }
         __syncthreads();
-#pragma unroll 4
-        for (int c = 0; c < AB_T; ++c) {
-            const double k0 = Ks[c * AB_P + tx * 2], k1 = Ks[c * AB_P + tx * 2 + 1];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const double ds = Tt[(ty * 4 + a) * AB_PT + c];
-                dq[a][0] = fma(ds, k0, dq[a][0]);
-                dq[a][1] = fma(ds, k1, dq[a][1]);
-            }
-        }
+        ab_dmma_acc<false>(Tt, Ks, warp, lane, dq);
     }
+    if (i0 + r < p.N) {
+        double* dst = p.dQ + (bh * p.N + i0 + r) * 32 + 2 * qc;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int i = i0 + ty * 4 + a;
-        if (i < p.N) {
-            double* dst = p.dQ + (bh * p.N + i) * 32 + tx * 2;
-            dst[0] = dq[a][0] * p.scale;
-            dst[1] = dq[a][1] * p.scale;
-        }
+        for (int nt = 0; nt < 4; ++nt) { dst[nt * 8] = dq[nt][0] * p.scale; dst[nt * 8 + 1] = dq[nt][1] * p.scale; }
     }
 }
 
@@ -204,7 +187,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kv_kernel(const AttnBwdParams p)
     double* Tt = dOs + AB_T * AB_P;
     double* Dsm = Tt + AB_T * AB_PT; double* Lsm = Dsm + AB_T; double* Thr = Lsm + AB_T;
     __shared__ int Jl[AB_T];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, qr = lane >> 2, qc = lane & 3;
     const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * AB_T;
     const long long bh = (long long)b * HEADS + h;
     const double* Qg = p.Q + bh * p.N * p.ldq;
@@ -213,10 +196,11 @@ __global__ void __launch_bounds__(256) attn_bwd_kv_kernel(const AttnBwdParams p)
     const double* dOg = p.dO + bh * p.N * 32;
     ab_load_tile(Ks, Kg, p.ldq, j0, p.M, tid);
     ab_load_tile(Vs, Vg, p.ldv, j0, p.M, tid);
-    // this thread's part of dK / dV: sources ty*4.., channels tx*2, tx*2+1
+    // this thread's part of dK / dV: source 8 warp + qr, channels 8 nt + 2 qc, + 1
     double dk[4][2], dv[4][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) dk[a][0] = dk[a][1] = dv[a][0] = dv[a][1] = 0.0;
+    for (int nt = 0; nt < 4; ++nt) dk[nt][0] = dk[nt][1] = dv[nt][0] = dv[nt][1] = 0.0;
+    const int r = 8 * warp + qr;                                     // query row of the logits tile this thread holds
     for (int i0 = 0; i0 < p.N; i0 += AB_T) {
         __syncthreads();
         ab_load_tile(Qs, Qg, p.ldq, i0, p.N, tid);
@@ -230,62 +214,37 @@ __global__ void __launch_bounds__(256) attn_bwd_kv_kernel(const AttnBwdParams p)
             Jl[tid] = (p.S != nullptr && ok) ? p.jlast[bh * p.N + i] : 0x7fffffff;
         }
         __syncthreads();
-        double s[4][4], dp[4][4], pr[4][4];
-        ab_logits(p, bh, Qs, Ks, i0, j0, ty, tx, s);           // rows = queries ty*4.., columns = sources tx*4..
-        ab_mm_nt(dOs, Vs, ty, tx, dp);
+        double s[8][2], dp[8][2], pr[8][2];
+        ab_logits(p, bh, Qs, Ks, i0, j0, warp, lane, s);              // rows = queries, columns = sources
+        ab_dmma_nt(dOs, Vs, warp, lane, dp);
+        const bool rok = i0 + r < p.N;
+        const double thr = Thr[r], lse = Lsm[r], dd = Dsm[r]; const int jl = Jl[r];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int r = ty * 4 + a;
-            const bool rok = i0 + r < p.N;
-            const double thr = Thr[r], lse = Lsm[r]; const int jl = Jl[r];
+        for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-            for (int bb = 0; bb < 4; ++bb) {
-                const bool keep = rok && ab_kept(p, s[a][bb], j0 + tx * 4 + bb, thr, jl);
-                pr[a][bb] = keep ? exp(s[a][bb] - lse) : 0.0;
-                Tt[r * AB_PT + tx * 4 + bb] = pr[a][bb];
+            for (int e = 0; e < 2; ++e) {
+                const int c = nt * 8 + 2 * qc + e;
+                pr[nt][e] = (rok && ab_kept(p, s[nt][e], j0 + c, thr, jl)) ? exp(s[nt][e] - lse) : 0.0;
+                Tt[r * AB_PT + c] = pr[nt][e];
             }
-        }
         __syncthreads();
-        // dV_j += sum_i P_ij dO_i
-#pragma unroll 4
-        for (int q = 0; q < AB_T; ++q) {
-            const double g0 = dOs[q * AB_P + tx * 2], g1 = dOs[q * AB_P + tx * 2 + 1];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const double pp = Tt[q * AB_PT + ty * 4 + a];
-                dv[a][0] = fma(pp, g0, dv[a][0]);
-                dv[a][1] = fma(pp, g1, dv[a][1]);
-            }
-        }
+        ab_dmma_acc<true>(Tt, dOs, warp, lane, dv);                   // dV_j += sum_i P_ij dO_i
         __syncthreads();
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int r = ty * 4 + a;
-            const double dd = Dsm[r];
+        for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-            for (int bb = 0; bb < 4; ++bb) Tt[r * AB_PT + tx * 4 + bb] = pr[a][bb] * (dp[a][bb] - dd);
-        }
+            for (int e = 0; e < 2; ++e) Tt[r * AB_PT + nt * 8 + 2 * qc + e] = pr[nt][e] * (dp[nt][e] - dd);
         __syncthreads();
-        // dK_j += sum_i dS_ij Q_i
-#pragma unroll 4
-        for (int q = 0; q < AB_T; ++q) {
-            const double q0 = Qs[q * AB_P + tx * 2], q1 = Qs[q * AB_P + tx * 2 + 1];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const double ds = Tt[q * AB_PT + ty * 4 + a];
-                dk[a][0] = fma(ds, q0, dk[a][0]);
-                dk[a][1] = fma(ds, q1, dk[a][1]);
-            }
-        }
+        ab_dmma_acc<true>(Tt, Qs, warp, lane, dk);                    // dK_j += sum_i dS_ij Q_i
     }
+    const int j = j0 + 8 * warp + qr;
+    if (j < p.M) {
+        double* dkp = p.dK + (bh * p.M + j) * 32 + 2 * qc;
+        double* dvp = p.dV + (bh * p.M + j) * 32 + 2 * qc;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int j = j0 + ty * 4 + a;
-        if (j < p.M) {
-            double* dkp = p.dK + (bh * p.M + j) * 32 + tx * 2;
-            double* dvp = p.dV + (bh * p.M + j) * 32 + tx * 2;
-            dkp[0] = dk[a][0] * p.scale; dkp[1] = dk[a][1] * p.scale;
-            dvp[0] = dv[a][0]; dvp[1] = dv[a][1];
+        for (int nt = 0; nt < 4; ++nt) {
+            dkp[nt * 8] = dk[nt][0] * p.scale; dkp[nt * 8 + 1] = dk[nt][1] * p.scale;
+            dvp[nt * 8] = dv[nt][0]; dvp[nt * 8 + 1] = dv[nt][1];
         }
     }
 }

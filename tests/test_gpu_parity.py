@@ -247,29 +247,19 @@ def test_sinkhorn_float32_kernel_matrix_wide_range_falls_back(dev):
     assert np.abs(got[0] - want[0]).max() < 1e-6 and np.abs(got[1] - want[1]).max() < 1e-9
 
 
-def _torch_lot(scores, alpha, iters):
-    """log_optimal_transport exactly as the reference writes it (mdgat.py:279-308), for autograd."""
-    b, m, n = scores.shape
-    one = scores.new_tensor(1)
-    ms, ns = (m * one).to(scores), (n * one).to(scores)
-    bins0 = alpha.expand(b, m, 1)
-    bins1 = alpha.expand(b, 1, n)
-    alpha_ = alpha.expand(b, 1, 1)
-    couplings = torch.cat([torch.cat([scores, bins0], -1), torch.cat([bins1, alpha_], -1)], 1)
-    norm = -(ms + ns).log()
-    log_mu = torch.cat([norm.expand(m), ns.log()[None] + norm])[None].expand(b, -1)
-    log_nu = torch.cat([norm.expand(n), ms.log()[None] + norm])[None].expand(b, -1)
-    u, v = torch.zeros_like(log_mu), torch.zeros_like(log_nu)
-    for _ in range(iters):
-        u = log_mu - torch.logsumexp(couplings + v.unsqueeze(1), dim=2)
-        v = log_nu - torch.logsumexp(couplings + u.unsqueeze(2), dim=1)
-    return couplings + u.unsqueeze(2) + v.unsqueeze(1) - norm
+def _reference_module():
+    """The UNMODIFIED reference models/mdgat.py (byte-identical copy under oracle/_ref/reference, or /root/reference in the
+    build container) imported for CUDA: its own functions are what the hand-written backward kernels are checked against."""
+    from oracle import ref_loader as RL
+    if not RL.reference_available():
+        pytest.skip('reference tree not available (oracle/_ref/reference missing)')
+    return RL.load_reference_module('mdgat', 'cuda')
 
 
 @pytest.mark.parametrize('N,M,iters', [(40, 40, 20), (130, 77, 100), (64, 300, 7), (5, 9, 3), (33, 20, 0), (512, 512, 100)])
 def test_sinkhorn_backward_vs_autograd(dev, N, M, iters):
-    """Hand-written reverse sweep of log_optimal_transport (csrc/sinkhorn_bwd.cu) against autograd through the unrolled
-    reference iterations: gradients of the scores and of bin_score for a random upstream gradient."""
+    """Hand-written reverse sweep of log_optimal_transport (csrc/sinkhorn_bwd.cu) against autograd through the unmodified
+    reference's own unrolled iterations: gradients of the scores and of bin_score for a random upstream gradient."""
     from mdgat_matcher_b200 import ops
     g = torch.Generator().manual_seed(N + M + iters)
     B = 2
@@ -277,7 +267,7 @@ def test_sinkhorn_backward_vs_autograd(dev, N, M, iters):
     alpha = torch.tensor(1.3, dtype=torch.float64, device=dev)
     up = torch.randn(B, N + 1, M + 1, generator=g, dtype=torch.float64).to(dev)
     s1, a1 = scores.clone().requires_grad_(True), alpha.clone().requires_grad_(True)
-    Z1 = _torch_lot(s1, a1, iters)
+    Z1 = _reference_module().log_optimal_transport(s1, a1, iters)                 # mdgat.py:288-308, unrolled under autograd
     (Z1 * up).sum().backward()
     s2, a2 = scores.clone().requires_grad_(True), alpha.clone().requires_grad_(True)
     Z2 = ops.log_optimal_transport(s2, a2, iters)
@@ -288,24 +278,22 @@ def test_sinkhorn_backward_vs_autograd(dev, N, M, iters):
     assert abs(a1.grad.item() - a2.grad.item()) < 1e-9 * max(1.0, abs(a1.grad.item()))
 
 
-def _torch_attention(q, k, v, topk):
-    """attention() / dynamic_attention() as the reference writes them (mdgat.py:190-210), on (B,128,n) inputs."""
+def _reference_attention(q, k, v, topk):
+    """attention() / dynamic_attention() of the unmodified reference (mdgat.py:190-210) on (B,128,n) inputs, viewed as
+    MultiHeadedAttention.forward does (mdgat.py:227-232)."""
+    mod = _reference_module()
     b = q.shape[0]
     qh, kh, vh = [t.view(b, 32, 4, -1) for t in (q, k, v)]
-    scores = torch.einsum('bdhn,bdhm->bhnm', qh, kh) / 32 ** .5
-    if topk is None:
-        prob = torch.nn.functional.softmax(scores, dim=-1)
-    else:
-        idx = scores.topk(topk, dim=3, largest=True, sorted=True).indices
-        prob = torch.zeros_like(scores).scatter(3, idx, torch.nn.functional.softmax(scores.gather(3, idx), dim=-1))
-    return torch.einsum('bhnm,bdhm->bdhn', prob, vh).contiguous().view(b, 128, -1)
+    x, _ = mod.attention(qh, kh, vh) if topk is None else mod.dynamic_attention(qh, kh, vh, topk)
+    return x.contiguous().view(b, 128, -1)
 
 
 @pytest.mark.parametrize('N,M,topk', [(128, 128, None), (200, 77, None), (64, 300, None), (512, 512, None),
                                       (128, 128, 64), (200, 300, 128), (96, 1000, 64), (512, 512, 128), (70, 160, 160)])
 def test_attention_backward_vs_autograd(dev, N, M, topk):
     """Hand-written attention backward (csrc/attention_bwd.cu: tile recompute, exact kept set for the top-k layers) against
-    autograd through the reference formulation: message and the gradients of q, k, v for a random upstream gradient."""
+    autograd through the unmodified reference's attention() / dynamic_attention(): message and the gradients of q, k, v for a
+    random upstream gradient."""
     from mdgat_matcher_b200 import ops
     g = torch.Generator().manual_seed(N + 3 * M + (topk or 0))
     B = 2
@@ -314,7 +302,7 @@ def test_attention_backward_vs_autograd(dev, N, M, topk):
     v = torch.randn(B, 128, M, generator=g, dtype=torch.float64).to(dev)
     up = torch.randn(B, 128, N, generator=g, dtype=torch.float64).to(dev)
     a = [t.clone().requires_grad_(True) for t in (q, k, v)]
-    o1 = _torch_attention(*a, topk)
+    o1 = _reference_attention(*a, topk)
     (o1 * up).sum().backward()
     c = [t.clone().requires_grad_(True) for t in (q, k, v)]
     o2 = ops.attention_autograd(*c, topk)

@@ -247,6 +247,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-eager', action='store_true', help='skip the eager-GPU timing of the unmodified reference')
     ap.add_argument('--no-latency', action='store_true', help='skip the batch-1 latency measurement')
+    ap.add_argument('--cuda-graph', action='store_true', help="run the timed forwards with config['cuda_graph'] (captured launch sequence)")
     args = ap.parse_args()
 
     # NCCL prints its version banner on STDOUT at level VERSION; this script owes the driver ONE json line
@@ -275,6 +276,8 @@ def main():
     cfg['gemm'], cfg['attention'] = args.gemm, args.attention
     if args.precision:
         cfg['precision'] = args.precision
+    if args.cuda_graph:
+        cfg['cuda_graph'] = True
     sd, wdesc = load_weights(L)
     net = MDGAT(cfg)
     net.load_state_dict(sd)
@@ -369,9 +372,12 @@ def main():
     # ---------------- per-stage device times: a separate pass of the same K steps with the stage events switched on
     # (~230 cudaEventRecord calls per forward cost ~0.5 ms per step, so they stay out of the timed region above)
     _capi.lib.mdgat_profile_enable(1)
+    graph_on = bool(net.config.get('cuda_graph', False))
+    net.config['cuda_graph'] = False                           # stage events are host-side records: plain launches for this pass
     for _ in range(args.steps):
         step_resident()
     torch.cuda.synchronize()
+    net.config['cuda_graph'] = graph_on
     stages = _capi.profile_collect()
     _capi.lib.mdgat_profile_enable(0)
 

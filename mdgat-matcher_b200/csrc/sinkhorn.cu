@@ -358,10 +358,15 @@ sinkhorn_fused32_kernel(const double* __restrict__ C, float* __restrict__ Kg, do
     double* cmx = as + RSp;                 // [RSp]    row maxima of C
     double* kd = cmx + RSp;                 // [RSp]    K of the dustbin column (float64: one scalar per row)
     int* chg = reinterpret_cast<int*>(kd + RSp);                    // [8] "changed" flags of the cluster
+    __shared__ double s_aN;                                         // a of the dustbin row (every CTA computes the same value)
     uint32_t* Ks = reinterpret_cast<uint32_t*>(kd + RSp + 4);       // [rows_smem][ldk] float bit patterns
 
+    // The dustbin ROW of the couplings is the constant alpha (mdgat.py:294-299), so its kernel row is all ones: its row sum is
+    // the sum of b, its contribution to every column sum is a_N itself -- no storage, and the N real rows split evenly
+    // over the CTAs (512 rows: 64 per CTA = one 4-row round of the 16 warps; with the dustbin row in a slice one warp had a
+    // second round while fifteen waited, 12 % of the kernel's stall samples)
     const int r0 = crank * RS;
-    const int nrows = max(0, min(RS, R1 - r0));
+    const int nrows = max(0, min(RS, N - r0));
     const int n_smem = min(nrows, rows_smem);
     const double* Cb = C + (long long)b * R1 * C1;
     uint32_t* Kb = reinterpret_cast<uint32_t*>(Kg) + (long long)b * R1 * ldk;
@@ -433,7 +438,13 @@ sinkhorn_fused32_kernel(const double* __restrict__ C, float* __restrict__ Kg, do
             }
             warp_transpose_sum<4>(acc, lane);
             const int r = rb + (lane >> 3);
-            if ((lane & 7) == 0 && r < nrows) as[r] = ((r0 + r < N) ? mu_reg : mu_bin) / fma(kd[r], bM, acc[0]);
+            if ((lane & 7) == 0 && r < nrows) as[r] = mu_reg / fma(kd[r], bM, acc[0]);
+        }
+        if (warp == SKF_WARPS - 1) {                    // dustbin row: a_N = mu_N / sum_j b_j (its kernel row is all ones)
+            double sb = 0.0;
+            for (int j = lane; j < C1; j += 32) sb += bs[j];
+            sb = warp_sum_d(sb);
+            if (lane == 0) s_aN = mu_bin / sb;
         }
         __syncthreads();
         // ---- partial column sums over own rows: part_j = sum_r K_rj a_r
@@ -485,7 +496,7 @@ sinkhorn_fused32_kernel(const double* __restrict__ C, float* __restrict__ Kg, do
                 pv += shfl_xor_d(pv, 2);
                 pv += shfl_xor_d(pv, 4);
                 if (ok) {
-                    const double nb = ((j < M) ? nu_reg : nu_bin) / pv;
+                    const double nb = ((j < M) ? nu_reg : nu_bin) / (pv + s_aN);      // + the dustbin row: K_Nj = 1
                     changed |= (__double_as_longlong(nb) != __double_as_longlong(old));
                     cluster.map_shared_rank(bs, src)[j] = nb;
                 }
@@ -502,8 +513,10 @@ sinkhorn_fused32_kernel(const double* __restrict__ C, float* __restrict__ Kg, do
     }
     if (crank == 0 && tid == 0) flags[gridDim.x / SKF_CLUSTER + b] = it_done;
     for (int r = tid; r < nrows; r += SKF_THREADS) u_out[(long long)b * R1 + r0 + r] = iters > 0 ? log(as[r]) - cmx[r] : 0.0;
-    if (crank == 0)
+    if (crank == 0) {
         for (int j = tid; j < C1; j += SKF_THREADS) v_out[(long long)b * C1 + j] = iters > 0 ? log(bs[j]) : 0.0;
+        if (tid == 0) u_out[(long long)b * R1 + N] = iters > 0 ? log(s_aN) - Cb[(long long)N * C1] : 0.0;      // c_N = alpha
+    }
 }
 
 // Plain log-domain Sinkhorn for flagged pairs: one CTA per pair, exact max subtraction.
@@ -589,7 +602,7 @@ static cudaError_t launch_sinkhorn_fused32(const double* C, double* u, double* v
                                            int iters, cudaStream_t st) {
     const int R1 = N + 1, C1 = M + 1;
     const int ldk64 = (M + 1) & ~1, ldk = (M + 3) & ~3, ldv = (C1 + 1) & ~1;
-    const int RS = (R1 + SKF_CLUSTER - 1) / SKF_CLUSTER;
+    const int RS = (N + SKF_CLUSTER - 1) / SKF_CLUSTER;           // real rows per CTA (the dustbin row needs no storage)
     float* Kg = reinterpret_cast<float*>(scratch);
     int* flags = reinterpret_cast<int*>(scratch + (size_t)B * R1 * ldk64);
     cudaError_t e;

@@ -573,7 +573,7 @@ class MDGAT(nn.Module):
                         launch(static_in, outs, None)              # plain run first: lazy one-time initialisation stays out of the capture
                     torch.cuda.current_stream(dev).wait_stream(side)
                     graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
+                    with torch.cuda.graph(graph, capture_error_mode='thread_local'):      # other threads (NCCL watchdog, DataParallel) may call CUDA meanwhile
                         launch(static_in, outs, None)
                     ent = (graph, [a for a in static_in if a is not None], ob, ws, blob, blob_i8, blob_i8_late)
                     self._graphs[key] = ent

@@ -415,6 +415,17 @@ def main():
                               'late_layers': ({'from_layer': late[0], 'gemm': late[1], 'attention_qkv': late[2], 'attention_p': late[3]} if late else None),
                               'sinkhorn_kernel_matrix': 'float32 storage, float64 arithmetic' if net.sinkhorn_k32() else 'float64',
                               'note': 'int8 planes per float64 operand; chosen on the 131 k-row sweep against the unmodified reference (DESIGN.md 2)'}
+    try:
+        sk = net.sinkhorn_status()
+        its = sk['iterations']
+        config['sinkhorn'] = {'iterations_requested': T,
+                              'iterations_run_per_pair': {'min': int(min(its)), 'mean': float(sum(its)) / len(its), 'max': int(max(its))},
+                              'fallback_pairs': int(sum(sk['fallback'])),
+                              'exit_rule': ('no column scaling moved by more than %s relative in one iteration (skipped iterations move a '
+                                            'log-potential by <= (T - t) tol; DESIGN.md 4.6)' % os.environ.get('MDGAT_SK_TOL', '2^-35'))
+                                           if net.sinkhorn_k32() else 'iterate repeats bit for bit'}
+    except Exception as exc:                                  # diagnostic only
+        config['sinkhorn'] = {'status_error': str(exc)}
     if world > 1:
         config['collective'] = {'op': 'all_gather_into_tensor (NCCL)', 'per_step': 1, 'inside_timed_region': True,
                                 'bytes_per_rank_per_step': int(B * 2 * (N + N) * 8)}

@@ -192,9 +192,15 @@ int mdgat_attention_i8(const double* d_Q, const double* d_K, const double* d_V, 
  * uses). d_scratch == NULL: one kernel per half-iteration reading the couplings from L2. */
 size_t mdgat_sinkhorn_scratch_doubles(int B, int N, int M);
 /* After a fused run (synchronises): per pair, whether the pair was redone by the log-domain
- * fallback (h_flags) and how many iterations ran before the iterate repeated bit for bit --
- * the fused kernel stops there, every further iteration being a no-op (h_iters <= iters). */
+ * fallback (h_flags) and how many iterations ran before the fused kernel stopped (h_iters <= iters):
+ * mdgat_sinkhorn_f64 stops once the iterate repeats bit for bit, every further iteration being a no-op;
+ * mdgat_sinkhorn_f64_k32 stops once no column scaling moved by more than 2^-35 relative in an iteration
+ * (the skipped iterations move a log-potential by at most (iters - h_iters) 2^-35; MDGAT_SK_TOL=0 in the
+ * environment restores the bit-for-bit rule). */
 int mdgat_sinkhorn_read_status(const double* d_scratch, int B, int N, int M, int* h_flags, int* h_iters);
+/* The same status for the Sinkhorn stage of the last mdgat_forward() that ran on this workspace with this cfg
+ * (the caller synchronises the forward's stream first). */
+int mdgat_forward_sinkhorn_status(const mdgat_forward_cfg* cfg, const void* d_workspace, int* h_flags, int* h_iters);
 int mdgat_sinkhorn_f64(double* d_couplings, const double* d_bin_score, double* d_u, double* d_v,
                        int B, int N, int M, int iters, double* d_scratch, void* stream);
 /* Same contract (d_scratch required) with the kernel matrix stored in float32, float64 arithmetic (mdgat_forward_cfg.sinkhorn_k32). */

@@ -68,6 +68,7 @@ def _load():
         'mdgat_attention_i8': (i, [vp, vp, vp, vp, i, i, i, i, i, vp, vp, i, i, vp]),
         'mdgat_sinkhorn_scratch_doubles': (sz, [i, i, i]),
         'mdgat_sinkhorn_read_status': (i, [vp, i, i, i, C.POINTER(i), C.POINTER(i)]),
+        'mdgat_forward_sinkhorn_status': (i, [C.POINTER(ForwardCfg), vp, C.POINTER(i), C.POINTER(i)]),
         'mdgat_sinkhorn_f64': (i, [vp, vp, vp, vp, i, i, i, i, vp, vp]),
         'mdgat_attention_backward_scratch_doubles': (sz, [i, i, i, i]),
         'mdgat_attention_backward_f64': (i, [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp]),

@@ -256,7 +256,7 @@ cudaError_t encode(const mdgat_forward_in* in, int B, int N, int M, int in_dtype
 extern "C" {
 
 const char* mdgat_last_error(void) { return mdgat_host::g_err; }
-int mdgat_abi_version(void) { return 3; }
+int mdgat_abi_version(void) { return 4; }
 
 size_t mdgat_weight_blob_doubles(int L) { return BlobLayout(L).total; }
 
@@ -573,6 +573,15 @@ int mdgat_sinkhorn_read_status(const double* d_scratch, int B, int N, int M, int
     MDGAT_CUDA_OK(cudaMemcpy(h_flags, d, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost));
     MDGAT_CUDA_OK(cudaMemcpy(h_iters, d + B, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost));
     return MDGAT_OK;
+}
+
+int mdgat_forward_sinkhorn_status(const mdgat_forward_cfg* cfg, const void* d_workspace, int* h_flags, int* h_iters) {
+    MDGAT_REQUIRE(cfg && d_workspace && h_flags && h_iters, "mdgat_forward_sinkhorn_status: bad arguments");
+    bool need = false;
+    for (int i = 0; i < 2 * cfg->L; ++i) need = need || (cfg->layer_k && cfg->layer_k[i] > 0);
+    // the Sinkhorn scratch lies before every engine-dependent part of the workspace
+    const Workspace w = carve(reinterpret_cast<char*>(const_cast<void*>(d_workspace)), cfg->B, cfg->N, cfg->M, need);
+    return mdgat_sinkhorn_read_status(w.skscratch, cfg->B, cfg->N, cfg->M, h_flags, h_iters);
 }
 
 size_t mdgat_attention_backward_scratch_doubles(int B, int N, int M, int topk) { return attention_bwd_scratch_doubles(B, N, M, topk); }

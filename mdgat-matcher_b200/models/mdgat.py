@@ -583,6 +583,7 @@ class MDGAT(nn.Module):
             else:
                 _, (matches0, matches1, ms0, ms1, loss, nvalid) = new_outputs()
                 launch(ins, (matches0, matches1, ms0, ms1, loss, nvalid), Z)
+            self._last_call = (cfg, karr, ws, dev)                 # for sinkhorn_status()
             if loss_mode == _capi.LOSS_NONE:
                 loss = None
             if self.config.get('strict_degenerate_dtypes', False) and self.loss_method != 'superglue' \
@@ -594,6 +595,20 @@ class MDGAT(nn.Module):
         if self.config.get('return_assignment', False):
             out['assignment'] = Z
         return out
+
+    def sinkhorn_status(self):
+        """Diagnostic for the last eval-mode forward of this module (synchronises the device): per pair, the number of
+        Sinkhorn iterations the fused kernel ran before it stopped (<= config['sinkhorn_iterations'], include/mdgat_b200.h:
+        mdgat_sinkhorn_read_status) and whether the pair was redone by the log-domain fallback."""
+        last = getattr(self, '_last_call', None)
+        if last is None:
+            raise RuntimeError('sinkhorn_status(): no eval-mode forward has run on this module yet')
+        from .. import _capi
+        cfg, _karr, ws, dev = last
+        torch.cuda.synchronize(dev)
+        fl, it = (ctypes.c_int * cfg.B)(), (ctypes.c_int * cfg.B)()
+        _capi.check(_capi.lib.mdgat_forward_sinkhorn_status(ctypes.byref(cfg), ws.data_ptr(), fl, it))
+        return {'iterations': list(it), 'fallback': list(fl)}
 
     def _forward_torch(self, data):
         """Differentiable path for train.py (batch-statistics BatchNorm, autograd)."""

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert set(_capi.EXPORTS) == declared
-    assert _capi.lib.mdgat_abi_version() == 3
+    assert _capi.lib.mdgat_abi_version() == 4
 
 
 def test_error_text_without_gpu():

@@ -247,7 +247,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-eager', action='store_true', help='skip the eager-GPU timing of the unmodified reference')
     ap.add_argument('--no-latency', action='store_true', help='skip the batch-1 latency measurement')
-    ap.add_argument('--cuda-graph', action='store_true', help="run the timed forwards with config['cuda_graph'] (captured launch sequence)")
+    ap.add_argument('--cuda-graph', action='store_true', help="(default) run the timed forwards with config['cuda_graph']: the launch sequence of one forward captured once, replayed per step")
+    ap.add_argument('--no-cuda-graph', action='store_true', help='plain kernel launches (programmatic dependent launch) instead of the captured graph')
     args = ap.parse_args()
 
     # NCCL prints its version banner on STDOUT at level VERSION; this script owes the driver ONE json line
@@ -276,8 +277,7 @@ def main():
     cfg['gemm'], cfg['attention'] = args.gemm, args.attention
     if args.precision:
         cfg['precision'] = args.precision
-    if args.cuda_graph:
-        cfg['cuda_graph'] = True
+    cfg['cuda_graph'] = not args.no_cuda_graph
     sd, wdesc = load_weights(L)
     net = MDGAT(cfg)
     net.load_state_dict(sd)
@@ -415,6 +415,8 @@ def main():
                               'late_layers': ({'from_layer': late[0], 'gemm': late[1], 'attention_qkv': late[2], 'attention_p': late[3]} if late else None),
                               'sinkhorn_kernel_matrix': 'float32 storage, float64 arithmetic' if net.sinkhorn_k32() else 'float64',
                               'note': 'int8 planes per float64 operand; chosen on the 131 k-row sweep against the unmodified reference (DESIGN.md 2)'}
+    config['launch'] = ("config['cuda_graph']: one captured CUDA graph of the forward's kernel sequence replayed per step (inputs copied into its "
+                        "static buffers, results out of them, inside the timed regions)") if cfg['cuda_graph'] else 'plain launches with programmatic dependent launch'
     try:
         sk = net.sinkhorn_status()
         its = sk['iterations']

@@ -272,7 +272,9 @@ int mdgat_measure_fp64_mixed(double* tflops_dmma, double* tflops_dfma);
 int mdgat_measure_i8_peak(double* tops);
 
 /* ---- instrumentation (no reference counterpart; the reference has no tracing) ----
- * mdgat_launch_count: kernels launched by this library since load.
+ * mdgat_launch_count: kernels launched by this library since load. Kernels replayed from a captured CUDA graph are not
+ * launched through the library: the owner of the graph reports them with mdgat_launch_count_add (the number the counter
+ * advanced by during the capture, once per replay).
  * Stage timers: when enabled, mdgat_forward brackets each run of same-stage launches with CUDA
  * events on the caller's stream; mdgat_profile_collect synchronises on the last event and returns
  * accumulated device milliseconds, launch counts and segment counts per stage, in the order
@@ -286,6 +288,7 @@ int mdgat_measure_i8_peak(double* tops);
 #define MDGAT_STAGE_SLICE 6       /* digit-plane slicers of the tcgen05 engines */
 #define MDGAT_STAGE_COUNT 7
 long long mdgat_launch_count(void);
+void mdgat_launch_count_add(long long n);
 /* Debug timeline: d_buf = NULL (default, off) or a zeroed device buffer of 8 roles x (2 + 2*1024) int64. While set, CTA
  * (0,0,0) of the tcgen05 kernels records (tag, clock64) pairs per role (loader, MMA issuer, two epilogue warps):
  * buf[role*2050] = count, then the pairs. tools/trace_tcgen05.py prints the timeline. */

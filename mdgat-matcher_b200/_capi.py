@@ -84,6 +84,7 @@ def _load():
         'mdgat_measure_fp64_mixed': (i, [C.POINTER(d), C.POINTER(d)]),
         'mdgat_measure_i8_peak': (i, [C.POINTER(d)]),
         'mdgat_launch_count': (ll, []),
+        'mdgat_launch_count_add': (None, [ll]),
         'mdgat_debug_trace': (i, [vp]),
         'mdgat_debug_flags': (i, [i]),
         'mdgat_profile_enable': (i, [i]),

@@ -665,6 +665,7 @@ int mdgat_knn(const double* d_x, const double* d_src, int64_t* d_idx, int B, int
 }
 
 long long mdgat_launch_count(void) { return g_launches.load(); }
+void mdgat_launch_count_add(long long n) { g_launches.fetch_add(n); }
 
 int mdgat_debug_trace(void* d_buf) { mdgat::g_trace_dev = reinterpret_cast<long long*>(d_buf); return MDGAT_OK; }
 

@@ -44,8 +44,15 @@ DEVINL double pow2d(int e) { return __longlong_as_double((long long)(1023 + e) <
 // ---------------------------------------------------------------------------------------------------
 // x: 16 consecutive k (group kt) of padded row r; the 8 lanes holding a (row, 128-column chunk) must be an aligned
 // group of 8 lanes of a fully active warp
+template <int S> DEVINL void cut_digits16(const double (&x)[16], int e, int8_t* base);
+// MDGAT_SLICE_ONEFMA (read once; default 1): digits by cut_digits16() -- one FMA per value -- or by the telescoped roundings
+// below (one or two FMAs per digit). Every slicer of a process uses the same rule, so the fused and stand-alone slicers agree.
+static bool slice_onefma() {
+    static const bool v = [] { const char* e = getenv("MDGAT_SLICE_ONEFMA"); return !(e && e[0] == '0'); }();
+    return v;
+}
 template <int S>
-DEVINL void slice_group(double (&x)[16], long long r, int kt, int Rpad, int8_t* Xs, double* rowscale, size_t chunk_stride) {
+DEVINL void slice_group(double (&x)[16], long long r, int kt, int Rpad, int8_t* Xs, double* rowscale, size_t chunk_stride, bool onefma) {
     const int k0 = kt * 16;
     double mx = 0.0;
 #pragma unroll
@@ -66,6 +73,7 @@ DEVINL void slice_group(double (&x)[16], long long r, int kt, int Rpad, int8_t* 
     // low 32 bits are needed because |d_s| <= 64) -- and the difference runs on the integer pipe: 7 FP64 instructions per
     // element instead of 28 (the slicer was FP64-bound), rint() / F2I never touch the quarter-rate conversion pipe.
     int8_t* base = Xs + (size_t)kchunk * chunk_stride + ((size_t)tile * S) * OZ_XTILE + oz_canon(rr, kk);
+    if (onefma) { cut_digits16<S>(x, e, base); return; }
     // q_(s-1) is recomputed rather than kept (one more FMA per digit; 16 registers less: four CTAs per SM instead of
     // three -- the slicer is bound by the loads it keeps in flight, not by FP64 work)
 #pragma unroll 1
@@ -84,10 +92,55 @@ DEVINL void slice_group(double (&x)[16], long long r, int kt, int Rpad, int8_t* 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// All S digits of 16 values from ONE FMA each (the forward path's digit cutter).
+// I = rint(x 2^(6-e) 128^(S-1)), |I| <= 64 * 128^(S-1) because |x| < 2^e. The addend of the FMA is 1.5 * 2^52 + B with
+// B = 64 * sum_k 128^k, so the low mantissa bits hold I + B >= 0, whose base-128 digits u_k in [0, 127] (the leading one in
+// [0, 128]) are balanced digits shifted by 64: d_k = u_k - 64 in [-64, 63] (leading: [-64, 64]), sum_k d_k 128^k = I exactly --
+// the same integer the telescoped roundings of slice_group() represent (x = 2^e sum_s d_s 2^(1-7s), |d_s| <= 64), in another
+// valid digit set. Per plane the 7-bit fields of four values are moved into the bytes of one word (shift + PRMT) and 64 is
+// subtracted from the four bytes at once (carry-free byte add of 0xC0): 1 FP64 + ~2.5 integer instructions per digit where the
+// telescoped form spends 2 FP64 + 3 integer -- the slicer was issue-bound (ncu: 53 instructions per element, issue slots 60 %).
+// ---------------------------------------------------------------------------------------------------
+template <int S>
+DEVINL void cut_digits16(const double (&x)[16], int e, int8_t* base) {
+    static_assert(S >= 1 && S <= 7, "7 S + 1 bits must fit below the 2^51 bit of the rounding constant");
+    constexpr unsigned long long B = 64ull * (((1ull << (7 * S)) - 1ull) / 127ull);
+    const double cs = pow2d(6 - e + 7 * (S - 1));           // 6 - e + 7 (S - 1) <= 6 + 900 + 42 < 1023
+    const double magic = 6755399441055744.0 + (double)B;    // an integer below 2^53: exact
+    uint32_t lo[16], hi[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const double v = fma(x[i], cs, magic);
+        lo[i] = (uint32_t)__double2loint(v);
+        hi[i] = (uint32_t)__double2hiint(v);
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int sh = 7 * (S - 1 - s);                      // plane 0 = most significant digit
+        uint32_t w[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint32_t a[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t l = lo[4 * g + j], h = hi[4 * g + j];
+                a[j] = sh == 0 ? l : (sh + 8 <= 32 ? (l >> sh) : (sh < 32 ? __funnelshift_r(l, h, sh) : (h >> (sh - 32))));
+            }
+            const uint32_t t01 = __byte_perm(a[0], a[1], 0x0040), t23 = __byte_perm(a[2], a[3], 0x0040);
+            const uint32_t u = __byte_perm(t01, t23, 0x5410);                       // byte j = bits sh .. sh + 7 of value 4 g + j
+            const uint32_t t = (u & 0x7f7f7f7fu) + 0x40404040u;                     // + 0xC0 per byte without carries between bytes
+            // leading digit: all eight bits count (u_k up to 128); the others: bit 7 belongs to the next digit
+            w[g] = s == 0 ? (t ^ (~u & 0x80808080u)) : (t ^ 0x80808080u);
+        }
+        *reinterpret_cast<uint4*>(base + (size_t)s * OZ_XTILE) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 template <int S>
 __global__ void __launch_bounds__(128, 8)
 slice_rows_kernel(const double* __restrict__ A0, int ld0, int K0, const double* __restrict__ A1, int ld1, int K1,
-                  int R, int8_t* __restrict__ Xs, double* __restrict__ rowscale, size_t chunk_stride) {
+                  int R, int8_t* __restrict__ Xs, double* __restrict__ rowscale, size_t chunk_stride, bool onefma) {
     const int K = K0 + K1, tpr = K / 16;                 // threads per row
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long r = gid / tpr;
@@ -104,7 +157,7 @@ slice_rows_kernel(const double* __restrict__ A0, int ld0, int K0, const double* 
 #pragma unroll
         for (int i = 0; i < 16; ++i) x[i] = 0.0;
     }
-    slice_group<S>(x, r, kt, Rpad, Xs, rowscale, chunk_stride);
+    slice_group<S>(x, r, kt, Rpad, Xs, rowscale, chunk_stride, onefma);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -121,7 +174,7 @@ constexpr int SL_ROWS = 32, SL_PITCH = 1040, SL_THREADS = 256, SL_STAGES = 2;
 // Persistent: the CTAs (three per SM) walk the (row tile, k chunk) tiles round robin through a two-stage ring -- the rows of
 // the next tile travel while the current one is cut -- so neither the HBM latency of a tile nor the last partial wave of a
 // one-tile-per-CTA grid (1.73 waves at cfg2) is exposed.
-template <int S>
+template <int S, bool ONEFMA>
 __global__ void __launch_bounds__(SL_THREADS, 3)
 slice_rows_tiled_kernel(const double* __restrict__ A0, int ld0, int K0, const double* __restrict__ A1, int ld1,
                         int R, int nchunks, int8_t* __restrict__ Xs, double* __restrict__ rowscale, size_t chunk_stride) {
@@ -178,6 +231,8 @@ slice_rows_tiled_kernel(const double* __restrict__ A0, int ld0, int K0, const do
         if (kt == 0) rowscale[(size_t)kchunk * Rpad + r] = pow2d(e - 12);
         const int tile = (int)(r / OZ_BM), rr = (int)(r % OZ_BM);
         int8_t* base = Xs + (size_t)kchunk * chunk_stride + ((size_t)tile * S) * OZ_XTILE + oz_canon(rr, kt * 16);
+        if constexpr (ONEFMA) cut_digits16<S>(x, e, base);
+        else
         // digits as in slice_group(): d_s = q_s - 128 q_(s-1), q_s = rint(x 2^(6-e) 128^s) read out of the mantissa
 #pragma unroll 1
         for (int s = 0; s < S; ++s) {
@@ -243,7 +298,7 @@ struct OzParams {
                                                        // [c * items_per_cta, (c + 1) * items_per_cta) in row-major order
     // fused slicing of the output (EPI_PLAIN, CTA owns whole rows of Y): the digit planes of this CTA's 128 x Nout tile of Y,
     // i.e. the operand of the next GEMM, in the layout launch_slice_rows() writes; null = off
-    int8_t* slice_out; double* slice_scale; unsigned long long slice_chunk_stride;
+    int8_t* slice_out; double* slice_scale; unsigned long long slice_chunk_stride; int slice_onefma;
     long long* trace;                                  // debug timeline (null = off)
     int dbg;                                           // debug switches (mdgat_debug_flags)
 };
@@ -625,7 +680,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
 #pragma unroll
                     for (int i = 0; i < 16; ++i) x[i] = 0.0;
                 }
-                slice_group<S>(x, r, kt, Rpad, p.slice_out, p.slice_scale, (size_t)p.slice_chunk_stride);
+                slice_group<S>(x, r, kt, Rpad, p.slice_out, p.slice_scale, (size_t)p.slice_chunk_stride, p.slice_onefma != 0);
             }
         }
     }
@@ -716,15 +771,18 @@ static cudaError_t slice_rows_t(const double* A0, int ld0, int K0, const double*
                          (A1 == nullptr || ((ld1 % 2) == 0 && (reinterpret_cast<uintptr_t>(A1) % 16) == 0));
     if (tiled && aligned) {
         const size_t smem = (size_t)SL_STAGES * SL_ROWS * SL_PITCH + 8 * SL_ROWS * sizeof(double);
-        cudaError_t e = cudaFuncSetAttribute(slice_rows_tiled_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const bool one = slice_onefma();
+        cudaError_t e = one ? cudaFuncSetAttribute(slice_rows_tiled_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(slice_rows_tiled_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
         const long long ntiles = (Rpad / SL_ROWS) * (K / OZ_KC);
         const unsigned grid = (unsigned)(ntiles < 3ll * sms ? ntiles : 3ll * sms);
-        return launch_pdl(slice_rows_tiled_kernel<S>, dim3(grid), dim3(SL_THREADS), smem, st, A0, ld0, K0, A1, ld1, R, K / OZ_KC, Xs, rowscale, chunk_stride);
+        if (one) return launch_pdl(slice_rows_tiled_kernel<S, true>, dim3(grid), dim3(SL_THREADS), smem, st, A0, ld0, K0, A1, ld1, R, K / OZ_KC, Xs, rowscale, chunk_stride);
+        return launch_pdl(slice_rows_tiled_kernel<S, false>, dim3(grid), dim3(SL_THREADS), smem, st, A0, ld0, K0, A1, ld1, R, K / OZ_KC, Xs, rowscale, chunk_stride);
     }
     const long long threads = Rpad * (K / 16);
-    slice_rows_kernel<S><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale, chunk_stride);
+    slice_rows_kernel<S><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(A0, ld0, K0, A1, ld1, K1, R, Xs, rowscale, chunk_stride, slice_onefma());
     return cudaGetLastError();
 }
 
@@ -792,6 +850,7 @@ cudaError_t launch_ozaki_gemm(const OzGemmArgs& a, int S, cudaStream_t st) {
     p.relu = a.relu; p.epi = a.epi; p.Qh = a.Qh; p.Kh = a.Kh; p.Vh = a.Vh; p.rows0 = a.rows0; p.n0 = a.n0; p.n1 = a.n1;
     p.trace = g_trace_dev; p.dbg = g_debug_flags;
     p.slice_out = a.slice_out; p.slice_scale = a.slice_scale; p.slice_chunk_stride = ozaki_slices_bytes(a.R, OZ_KC, S);
+    p.slice_onefma = slice_onefma() ? 1 : 0;
     const int row_tiles = (a.R + OZ_BM - 1) / OZ_BM, col_tiles = a.Nout / OZ_BN;
     // the X slice planes are loaded once per (CTA, k chunk): keep all column tiles in one CTA unless that leaves
     // SMs idle

@@ -341,14 +341,15 @@ sinkhorn_fused_kernel(const double* __restrict__ C, double* __restrict__ Kg, dou
 // float64 kernel above) keeps the bit-for-bit exit.
 constexpr double SK32_MAX_RANGE = 80.0;
 constexpr double SK32_EXIT_TOL = 2.9103830456733704e-11;      // 2^-35
+constexpr int SK32_DEFAULT_THREADS = 512;
 DEVINL double f32bits_to_f64(uint32_t f) {
     uint32_t hi;
     asm("mad.hi.u32 %0, %1, 0x20000000, 0x38000000;" : "=r"(hi) : "r"(f));     // (f >> 3) + ((1023 - 127) << 20)
     return __hiloint2double((int)hi, (int)(f << 29));
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(SKF_THREADS, MINB)
+template <int MINB, int NT>
+__global__ void __launch_bounds__(NT, MINB)
 sinkhorn_fused32_kernel(const double* __restrict__ C, float* __restrict__ Kg, double* __restrict__ u_out,
                         double* __restrict__ v_out, int* __restrict__ flags, int N, int M, int iters,
                         int RS, int rows_smem, int ldk, double tol) {
@@ -361,10 +362,15 @@ sinkhorn_fused32_kernel(const double* __restrict__ C, float* __restrict__ Kg, do
     const double mu_reg = 1.0 / (double)(N + M), mu_bin = (double)M / (double)(N + M);
     const double nu_reg = mu_reg, nu_bin = (double)N / (double)(N + M);
 
+    // NT = 512: 16 warps, a warp takes four rows per round, a thread one column over all rows of the CTA.
+    // NT = 1024: 32 warps (64 registers per thread), a warp takes two rows, two threads share a column (half the rows each,
+    // two partial vectors per CTA): the iteration is a chain of dependent phases, more warps shorten every link of it.
+    constexpr int NW = NT / 32, RPW = NT == 512 ? 4 : 2, HALVES = NT / 512, NP = SKF_CLUSTER * HALVES;
+    static_assert(NT == 512 || NT == 1024, "512 or 1024 threads");
     const int ldv = (C1 + 1) & ~1, RSp = (RS + 3) & ~3;
     double* bs = sm;                        // [ldv]    b_j
-    double* part = bs + ldv;                // [2][ldv] column partials of this CTA (peers read them)
-    double* as = part + 2 * ldv;            // [RSp]    a_i of own rows
+    double* part = bs + ldv;                // [2][HALVES][ldv] column partials of this CTA (peers read them)
+    double* as = part + 2 * HALVES * ldv;   // [RSp]    a_i of own rows
     double* cmx = as + RSp;                 // [RSp]    row maxima of C
     double* kd = cmx + RSp;                 // [RSp]    K of the dustbin column (float64: one scalar per row)
     int* chg = reinterpret_cast<int*>(kd + RSp);                    // [8] "changed" flags of the cluster
@@ -383,10 +389,10 @@ sinkhorn_fused32_kernel(const double* __restrict__ C, float* __restrict__ Kg, do
     const int Me = M & ~1;                   // columns taken two at a time; an odd last column separately
 
     // ---- setup: row maxima, range check, K rows
-    for (int r = tid; r < RSp; r += SKF_THREADS) { as[r] = 0.0; kd[r] = 0.0; cmx[r] = 0.0; }
+    for (int r = tid; r < RSp; r += NT) { as[r] = 0.0; kd[r] = 0.0; cmx[r] = 0.0; }
     __syncthreads();
     int bad = 0;
-    for (int r = warp; r < nrows; r += SKF_WARPS) {
+    for (int r = warp; r < nrows; r += NW) {
         const double* crow = Cb + (long long)(r0 + r) * C1;
         double mx = -INFINITY, mn = INFINITY;
         for (int j = lane; j < C1; j += 32) { const double c = crow[j]; mx = fmax(mx, c); mn = fmin(mn, c); }
@@ -398,23 +404,25 @@ sinkhorn_fused32_kernel(const double* __restrict__ C, float* __restrict__ Kg, do
         if (lane == 0) { cmx[r] = mx; kd[r] = exp(crow[M] - mx); }
     }
     if (bad && lane == 0) atomicOr(flags + b, 1);
-    for (int j = tid; j < ldv; j += SKF_THREADS) bs[j] = j < C1 ? 1.0 : 0.0;      // v = 0 before the first row pass
+    for (int j = tid; j < ldv; j += NT) bs[j] = j < C1 ? 1.0 : 0.0;      // v = 0 before the first row pass
     __syncthreads();
 
     int it_done = 0;
     for (int it = 0; it < iters; ++it) {
         const int buf = it & 1;
         const double bM = bs[M];
-        // ---- row sums s_r = sum_j K_rj b_j, then a_r = mu_r / s_r: a warp takes four rows at a time, a lane two columns
-        for (int rb = warp * 4; rb < nrows; rb += SKF_WARPS * 4) {
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            if (rb + 3 < n_smem) {
+        // ---- row sums s_r = sum_j K_rj b_j, then a_r = mu_r / s_r: a warp takes RPW rows at a time, a lane two columns
+        for (int rb = warp * RPW; rb < nrows; rb += NW * RPW) {
+            double acc[RPW];
+#pragma unroll
+            for (int q = 0; q < RPW; ++q) acc[q] = 0.0;
+            if (rb + RPW - 1 < n_smem) {
                 const uint32_t* k0 = Ks + (size_t)rb * ldk;
 #pragma unroll 4
                 for (int j = 2 * lane; j < Me; j += 64) {
                     const double2 bj = *reinterpret_cast<const double2*>(bs + j);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < RPW; ++q) {
                         const uint2 k = *reinterpret_cast<const uint2*>(k0 + (size_t)q * ldk + j);
                         acc[q] = fma(f32bits_to_f64(k.x), bj.x, acc[q]);
                         acc[q] = fma(f32bits_to_f64(k.y), bj.y, acc[q]);
@@ -422,12 +430,12 @@ sinkhorn_fused32_kernel(const double* __restrict__ C, float* __restrict__ Kg, do
                 }
                 if (Me < M && lane == 0) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[q] = fma(f32bits_to_f64(k0[(size_t)q * ldk + Me]), bs[Me], acc[q]);
+                    for (int q = 0; q < RPW; ++q) acc[q] = fma(f32bits_to_f64(k0[(size_t)q * ldk + Me]), bs[Me], acc[q]);
                 }
             } else {
-                const uint32_t* kr[4];
+                const uint32_t* kr[RPW];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < RPW; ++q) {
                     const int r = min(rb + q, nrows - 1);
                     kr[q] = r < n_smem ? Ks + (size_t)r * ldk : Kb + (long long)(r0 + r) * ldk;
                 }
@@ -435,7 +443,7 @@ sinkhorn_fused32_kernel(const double* __restrict__ C, float* __restrict__ Kg, do
                 for (int j = 2 * lane; j < Me; j += 64) {
                     const double2 bj = *reinterpret_cast<const double2*>(bs + j);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < RPW; ++q) {
                         const uint2 k = *reinterpret_cast<const uint2*>(kr[q] + j);
                         acc[q] = fma(f32bits_to_f64(k.x), bj.x, acc[q]);
                         acc[q] = fma(f32bits_to_f64(k.y), bj.y, acc[q]);
@@ -443,50 +451,59 @@ sinkhorn_fused32_kernel(const double* __restrict__ C, float* __restrict__ Kg, do
                 }
                 if (Me < M && lane == 0) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[q] = fma(f32bits_to_f64(kr[q][Me]), bs[Me], acc[q]);
+                    for (int q = 0; q < RPW; ++q) acc[q] = fma(f32bits_to_f64(kr[q][Me]), bs[Me], acc[q]);
                 }
             }
-            warp_transpose_sum<4>(acc, lane);
-            const int r = rb + (lane >> 3);
-            if ((lane & 7) == 0 && r < nrows) as[r] = mu_reg / fma(kd[r], bM, acc[0]);
+            warp_transpose_sum<RPW>(acc, lane);                   // lane l holds the total of row (l / (32 / RPW))
+            const int r = rb + lane / (32 / RPW);
+            if ((lane & (32 / RPW - 1)) == 0 && r < nrows) as[r] = mu_reg / fma(kd[r], bM, acc[0]);
         }
-        if (warp == SKF_WARPS - 1) {                    // dustbin row: a_N = mu_N / sum_j b_j (its kernel row is all ones)
+        if (warp == NW - 1) {                           // dustbin row: a_N = mu_N / sum_j b_j (its kernel row is all ones)
             double sb = 0.0;
             for (int j = lane; j < C1; j += 32) sb += bs[j];
             sb = warp_sum_d(sb);
             if (lane == 0) s_aN = mu_bin / sb;
         }
         __syncthreads();
-        // ---- partial column sums over own rows: part_j = sum_r K_rj a_r
-        double* pb = part + buf * ldv;
-        for (int j = tid; j < M; j += SKF_THREADS) {
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int r = 0;
-            for (; r + 3 < n_smem; r += 4) {
-                const double2 w01 = *reinterpret_cast<const double2*>(as + r);
-                const double2 w23 = *reinterpret_cast<const double2*>(as + r + 2);
-                a0 = fma(f32bits_to_f64(Ks[(size_t)r * ldk + j]), w01.x, a0);
-                a1 = fma(f32bits_to_f64(Ks[(size_t)(r + 1) * ldk + j]), w01.y, a1);
-                a2 = fma(f32bits_to_f64(Ks[(size_t)(r + 2) * ldk + j]), w23.x, a2);
-                a3 = fma(f32bits_to_f64(Ks[(size_t)(r + 3) * ldk + j]), w23.y, a3);
+        // ---- partial column sums over own rows: part_j = sum_r K_rj a_r (NT = 1024: rows [0, rsplit) and [rsplit, nrows) by
+        // the two threads of a column, one partial vector each)
+        double* pb = part + buf * (HALVES * ldv);
+        {
+            const int half = HALVES == 1 ? 0 : (tid >> 9);
+            const int rsplit = HALVES == 1 ? nrows : min(nrows, ((nrows + 1) / 2 + 3) & ~3);
+            const int ra = half == 0 ? 0 : rsplit, rz = (HALVES == 1 || half == 1) ? nrows : rsplit;
+            const int sa = min(ra, n_smem), sz = min(rz, n_smem);       // the part of [ra, rz) that lives in shared memory
+            const int ga = max(ra, n_smem);                              // the rest streams from the L2-resident scratch
+            for (int j = tid & 511; j < M; j += 512) {
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int r = sa;
+                for (; r + 3 < sz; r += 4) {
+                    const double2 w01 = *reinterpret_cast<const double2*>(as + r);
+                    const double2 w23 = *reinterpret_cast<const double2*>(as + r + 2);
+                    a0 = fma(f32bits_to_f64(Ks[(size_t)r * ldk + j]), w01.x, a0);
+                    a1 = fma(f32bits_to_f64(Ks[(size_t)(r + 1) * ldk + j]), w01.y, a1);
+                    a2 = fma(f32bits_to_f64(Ks[(size_t)(r + 2) * ldk + j]), w23.x, a2);
+                    a3 = fma(f32bits_to_f64(Ks[(size_t)(r + 3) * ldk + j]), w23.y, a3);
+                }
+                for (; r < sz; ++r) a0 = fma(f32bits_to_f64(Ks[(size_t)r * ldk + j]), as[r], a0);
+                r = max(r, ga);
+                for (; r + 3 < rz; r += 4) {
+                    const uint32_t* kp = Kb + (long long)(r0 + r) * ldk + j;
+                    const uint32_t k0 = kp[0], k1 = kp[ldk], k2 = kp[2 * (size_t)ldk], k3 = kp[3 * (size_t)ldk];
+                    a0 = fma(f32bits_to_f64(k0), as[r], a0);
+                    a1 = fma(f32bits_to_f64(k1), as[r + 1], a1);
+                    a2 = fma(f32bits_to_f64(k2), as[r + 2], a2);
+                    a3 = fma(f32bits_to_f64(k3), as[r + 3], a3);
+                }
+                for (; r < rz; ++r) a2 = fma(f32bits_to_f64(Kb[(long long)(r0 + r) * ldk + j]), as[r], a2);
+                pb[half * ldv + j] = (a0 + a1) + (a2 + a3);
             }
-            for (; r < n_smem; ++r) a0 = fma(f32bits_to_f64(Ks[(size_t)r * ldk + j]), as[r], a0);
-            for (; r + 3 < nrows; r += 4) {
-                const uint32_t* kp = Kb + (long long)(r0 + r) * ldk + j;
-                const uint32_t k0 = kp[0], k1 = kp[ldk], k2 = kp[2 * (size_t)ldk], k3 = kp[3 * (size_t)ldk];
-                a0 = fma(f32bits_to_f64(k0), as[r], a0);
-                a1 = fma(f32bits_to_f64(k1), as[r + 1], a1);
-                a2 = fma(f32bits_to_f64(k2), as[r + 2], a2);
-                a3 = fma(f32bits_to_f64(k3), as[r + 3], a3);
-            }
-            for (; r < nrows; ++r) a2 = fma(f32bits_to_f64(Kb[(long long)(r0 + r) * ldk + j]), as[r], a2);
-            pb[j] = (a0 + a1) + (a2 + a3);
         }
-        if (warp == SKF_WARPS - 1) {                    // dustbin column
+        if (warp == NW - 1) {                           // dustbin column
             double a = 0.0;
             for (int r = lane; r < nrows; r += 32) a = fma(kd[r], as[r], a);
             a = warp_sum_d(a);
-            if (lane == 0) pb[M] = a;
+            if (lane == 0) { pb[M] = a; if (HALVES == 2) pb[ldv + M] = 0.0; }
         }
         cluster.sync();
         // ---- reduce-scatter + broadcast through distributed shared memory (as in the float64 kernel)
@@ -495,20 +512,21 @@ sinkhorn_fused32_kernel(const double* __restrict__ C, float* __restrict__ Kg, do
             const int CS = (C1 + SKF_CLUSTER - 1) / SKF_CLUSTER;
             const int c0 = crank * CS;
             const int ncols = max(0, min(CS, C1 - c0));
-            const int src = tid & (SKF_CLUSTER - 1);
-            for (int base = 0; base < ncols * SKF_CLUSTER; base += SKF_THREADS) {
+            const int src = tid & (NP - 1);                 // partial vector src: CTA src % 8, half src / 8
+            for (int base = 0; base < ncols * NP; base += NT) {
                 const int idx = base + tid;
-                const int j = c0 + (idx >> 3);
-                const bool ok = idx < ncols * SKF_CLUSTER;
+                const int j = c0 + idx / NP;
+                const bool ok = idx < ncols * NP;
                 const double old = ok ? bs[j] : 0.0;
-                double pv = ok ? cluster.map_shared_rank(part, src)[buf * ldv + j] : 0.0;
+                double pv = ok ? cluster.map_shared_rank(part, src & (SKF_CLUSTER - 1))[(buf * HALVES + (src >> 3)) * ldv + j] : 0.0;
                 pv += shfl_xor_d(pv, 1);
                 pv += shfl_xor_d(pv, 2);
                 pv += shfl_xor_d(pv, 4);
+                if (HALVES == 2) pv += shfl_xor_d(pv, 8);
                 if (ok) {
                     const double nb = ((j < M) ? nu_reg : nu_bin) / (pv + s_aN);      // + the dustbin row: K_Nj = 1
                     changed |= fabs(nb - old) > tol * old;                            // tol = 0: "repeats bit for bit" (b > 0)
-                    cluster.map_shared_rank(bs, src)[j] = nb;
+                    if (src < SKF_CLUSTER) cluster.map_shared_rank(bs, src)[j] = nb;
                 }
             }
         }
@@ -522,9 +540,9 @@ sinkhorn_fused32_kernel(const double* __restrict__ C, float* __restrict__ Kg, do
         if (!any) break;
     }
     if (crank == 0 && tid == 0) flags[gridDim.x / SKF_CLUSTER + b] = it_done;
-    for (int r = tid; r < nrows; r += SKF_THREADS) u_out[(long long)b * R1 + r0 + r] = iters > 0 ? log(as[r]) - cmx[r] : 0.0;
+    for (int r = tid; r < nrows; r += NT) u_out[(long long)b * R1 + r0 + r] = iters > 0 ? log(as[r]) - cmx[r] : 0.0;
     if (crank == 0) {
-        for (int j = tid; j < C1; j += SKF_THREADS) v_out[(long long)b * C1 + j] = iters > 0 ? log(bs[j]) : 0.0;
+        for (int j = tid; j < C1; j += NT) v_out[(long long)b * C1 + j] = iters > 0 ? log(bs[j]) : 0.0;
         if (tid == 0) u_out[(long long)b * R1 + N] = iters > 0 ? log(s_aN) - Cb[(long long)N * C1] : 0.0;      // c_N = alpha
     }
 }
@@ -580,7 +598,7 @@ size_t sinkhorn_scratch_doubles(int B, int N, int M) {
 // two waves on 148 SMs. MDGAT_SK_CTAS=2 runs the measured-and-rejected alternative: two CTAs per SM (64 registers, 49 of
 // the 65 rows in shared memory, the others read from the L2-resident scratch), all 32 clusters in one wave -- 11 600 cycles
 // per iteration, 1.16 ms against 0.74 ms.
-template <int MINB>
+template <int MINB, int NT>
 static cudaError_t sk32_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int B, int RS, int ldk, int ldv, cudaStream_t st,
                                int& rows_smem, int& clusters) {
     int dev = 0, max_optin = 0, max_sm = 0;
@@ -589,22 +607,22 @@ static cudaError_t sk32_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* att
     if ((e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&max_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev)) != cudaSuccess) return e;
     const size_t budget = MINB == 1 ? (size_t)max_optin : (size_t)(max_sm / MINB - 1024);      // 1 KB per resident CTA is reserved
-    const size_t fixed = ((size_t)3 * ldv + 3 * (size_t)((RS + 3) & ~3) + 4) * sizeof(double);
+    const size_t fixed = ((size_t)(1 + 2 * (NT / 512)) * ldv + 3 * (size_t)((RS + 3) & ~3) + 4) * sizeof(double);
     if (fixed + 1024 > budget) return cudaErrorInvalidValue;
     rows_smem = (int)((budget - fixed) / ((size_t)ldk * sizeof(float)));
     if (rows_smem > RS) rows_smem = RS;
     const size_t smem = fixed + (size_t)rows_smem * ldk * sizeof(float);
-    if ((e = cudaFuncSetAttribute(sinkhorn_fused32_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(sinkhorn_fused32_kernel<MINB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(SKF_CLUSTER * B);
-    cfg.blockDim = dim3(SKF_THREADS);
+    cfg.blockDim = dim3(NT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = SKF_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     clusters = 1;
-    if (MINB > 1 && (e = cudaOccupancyMaxActiveClusters(&clusters, sinkhorn_fused32_kernel<MINB>, &cfg)) != cudaSuccess) return e;
+    if (MINB > 1 && (e = cudaOccupancyMaxActiveClusters(&clusters, sinkhorn_fused32_kernel<MINB, NT>, &cfg)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -620,17 +638,22 @@ static cudaError_t launch_sinkhorn_fused32(const double* C, double* u, double* v
     cudaLaunchAttribute attr1[1], attr2[1];
     int rows1 = 0, rows2 = 0, cl1 = 0, cl2 = 0;
     static const int force = [] { const char* v = getenv("MDGAT_SK_CTAS"); return v ? atoi(v) : 0; }();
-    bool two = false;
-    if (force == 2) {
-        if (sk32_config<2>(cfg2, attr2, B, RS, ldk, ldv, st, rows2, cl2) == cudaSuccess && cl2 > 0) two = true;
-        else (void)cudaGetLastError();
-    }
-    if (!two && (e = sk32_config<1>(cfg1, attr1, B, RS, ldk, ldv, st, rows1, cl1)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(flags, 0, sizeof(int) * 2 * (size_t)B, st)) != cudaSuccess) return e;
+    // MDGAT_SK_THREADS: 512 (16 warps, 4 rows per warp round, one thread per column) or 1024 (32 warps, 2 rows, two threads per column)
+    static const int threads = [] { const char* v = getenv("MDGAT_SK_THREADS"); return v ? atoi(v) : SK32_DEFAULT_THREADS; }();
     // Early exit once no b_j moved by more than tol relative (MDGAT_SK_TOL, 0 = "repeats bit for bit"): see the kernel comment
     static const double tol = [] { const char* v = getenv("MDGAT_SK_TOL"); return v ? atof(v) : SK32_EXIT_TOL; }();
-    if (two) e = cudaLaunchKernelEx(&cfg2, sinkhorn_fused32_kernel<2>, C, Kg, u, v, flags, N, M, iters, RS, rows2, ldk, tol);
-    else e = cudaLaunchKernelEx(&cfg1, sinkhorn_fused32_kernel<1>, C, Kg, u, v, flags, N, M, iters, RS, rows1, ldk, tol);
+    bool two = false;
+    if (force == 2) {
+        if (sk32_config<2, 512>(cfg2, attr2, B, RS, ldk, ldv, st, rows2, cl2) == cudaSuccess && cl2 > 0) two = true;
+        else (void)cudaGetLastError();
+    }
+    const bool wide = !two && threads == 1024;
+    if (!two && (e = wide ? sk32_config<1, 1024>(cfg1, attr1, B, RS, ldk, ldv, st, rows1, cl1)
+                          : sk32_config<1, 512>(cfg1, attr1, B, RS, ldk, ldv, st, rows1, cl1)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(flags, 0, sizeof(int) * 2 * (size_t)B, st)) != cudaSuccess) return e;
+    if (two) e = cudaLaunchKernelEx(&cfg2, sinkhorn_fused32_kernel<2, 512>, C, Kg, u, v, flags, N, M, iters, RS, rows2, ldk, tol);
+    else if (wide) e = cudaLaunchKernelEx(&cfg1, sinkhorn_fused32_kernel<1, 1024>, C, Kg, u, v, flags, N, M, iters, RS, rows1, ldk, tol);
+    else e = cudaLaunchKernelEx(&cfg1, sinkhorn_fused32_kernel<1, 512>, C, Kg, u, v, flags, N, M, iters, RS, rows1, ldk, tol);
     if (e != cudaSuccess) return e;
     sinkhorn_safe_kernel<<<B, 1024, 0, st>>>(C, u, v, flags, N, M, iters);
     count_launch(2);

@@ -573,12 +573,16 @@ class MDGAT(nn.Module):
                         launch(static_in, outs, None)              # plain run first: lazy one-time initialisation stays out of the capture
                     torch.cuda.current_stream(dev).wait_stream(side)
                     graph = torch.cuda.CUDAGraph()
+                    n0 = _capi.lib.mdgat_launch_count()
                     with torch.cuda.graph(graph, capture_error_mode='thread_local'):      # other threads (NCCL watchdog, DataParallel) may call CUDA meanwhile
                         launch(static_in, outs, None)
-                    ent = (graph, [a for a in static_in if a is not None], ob, ws, blob, blob_i8, blob_i8_late)
+                    n_kernels = _capi.lib.mdgat_launch_count() - n0                        # kernels of one replay
+                    _capi.lib.mdgat_launch_count_add(-n_kernels)                           # the capture itself ran nothing
+                    ent = (graph, [a for a in static_in if a is not None], ob, ws, blob, blob_i8, blob_i8_late, n_kernels)
                     self._graphs[key] = ent
                 torch._foreach_copy_(ent[1], [t for t in ins if t is not None])
                 ent[0].replay()
+                _capi.lib.mdgat_launch_count_add(ent[7])
                 matches0, matches1, ms0, ms1, loss, nvalid = carve(ent[2].clone())
             else:
                 _, (matches0, matches1, ms0, ms1, loss, nvalid) = new_outputs()

@@ -332,9 +332,10 @@ sinkhorn_fused_kernel(const double* __restrict__ C, double* __restrict__ Kg, dou
 // ------------------------------------------------------------------------------------------
 //
 // Early exit at a tolerance. The reference always runs T iterations (mdgat.py:282-284), but on the network's scores the
-// iteration contracts by ~0.4 per step: after ~25 of the T = 100 iterations no potential moves by 1e-10 any more, the bit-exact
-// fixed point comes at 45-50, and pairs whose last bit oscillates never repeat bit for bit and ran all 100. This kernel
-// stops when every b_j moved by at most tol = 2^-35 relative in one iteration. The per-iteration change of a Sinkhorn
+// iteration contracts by ~0.4 per step: after ~25 of the T = 100 iterations no potential moves by 1e-10 any more, and the
+// bit-for-bit rule of the float64 kernel stopped at 48 iterations on average (cfg2 batch, ncu barrier counts). This kernel
+// stops when every b_j moved by at most tol = 2^-35 relative in one iteration: 19-31 iterations per pair, 26 on average
+// (bench.py reports the counts, config.sinkhorn), 0.74 -> 0.42 ms at cfg2 and 15.2 -> 8.0 ms at cfg4. The per-iteration change of a Sinkhorn
 // iterate does not grow (the map is non-expansive in the log domain), so the T - t iterations that were skipped would have moved
 // a log-potential by at most (T - t) tol <= 3e-9 at T = 100 -- the size of the float32 storage effect above, 1e-4 is the bar.
 // A pair that has not converged keeps iterating up to T exactly like the reference. config['precision'] = 'exact' (the
@@ -592,12 +593,15 @@ size_t sinkhorn_scratch_doubles(int B, int N, int M) {
 }
 
 // float32 kernel matrix: same scratch (the float rows use half of the K area), same flags / iteration counts behind it.
-// Launch shape: one CTA per SM with as many K rows in shared memory as fit (all 65 at N = M = 512). The iteration is bound
-// by its barrier chain (row sums -> CTA barrier -> column partials -> cluster barrier -> exchange -> cluster barrier: 7300
-// cycles per iteration against 2150 shared-memory wavefronts and 2200 issue cycles), and at cfg2 the 32 clusters of 8 need
-// two waves on 148 SMs. MDGAT_SK_CTAS=2 runs the measured-and-rejected alternative: two CTAs per SM (64 registers, 49 of
-// the 65 rows in shared memory, the others read from the L2-resident scratch), all 32 clusters in one wave -- 11 600 cycles
-// per iteration, 1.16 ms against 0.74 ms.
+// Launch shape: one CTA per SM with as many K rows in shared memory as fit (all 64 real rows at N = M = 512). The iteration is
+// bound by its chain of dependent phases (row sums -> CTA barrier -> column partials -> cluster barrier -> exchange -> CTA
+// barrier -> cluster barrier): about 14 600 cycles per iteration (0.42 ms / 2 waves / ~28 iterations of the slowest pair of a
+// wave) against ~4 300 shared-memory wavefronts and ~4 500 issue cycles per scheduler; stall samples of an iteration: 23 % row
+// sweep, 27 % column sweep, 45 % barriers and the exchange. At cfg2 the 32 clusters of 8 need two waves (16 clusters fit the
+// GPCs of 148 SMs). Measured and rejected: MDGAT_SK_CTAS=2, two CTAs per SM (64 registers, 49 of the rows in shared memory,
+// the others read from the L2-resident scratch), all 32 clusters in one wave -- 1.16 ms against 0.74 ms before the tolerance
+// exit; MDGAT_SK_THREADS=1024, 32 warps per CTA (two rows per warp round, two threads per column, 16 partial vectors in the
+// exchange) -- 0.54 ms against 0.42 ms: the barriers and the exchange grow with the warp count faster than the sweeps shrink.
 template <int MINB, int NT>
 static cudaError_t sk32_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int B, int RS, int ldk, int ldv, cudaStream_t st,
                                int& rows_smem, int& clusters) {

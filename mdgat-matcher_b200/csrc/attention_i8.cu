@@ -433,6 +433,37 @@ DEVINL void ai_exp_fixed(double x, uint32_t tbl_s32, uint32_t& lo, uint32_t& hi)
     hi = (uint32_t)__double2hiint(pm) & 0xffffu;
 }
 
+// The same fixed-point exponential with the logit's own multiply-add folded in (FULL mode, SP <= 4; MDGAT_ATTN_CVT=5|6).
+// ai_exp_fixed() is fed x = z rk - c_i (one DFMA) and spends a second DFMA on x E/ln2 + MAGIC. Here the row factor carries
+// E/ln2 (rk16 = rk E/ln2: the key exponent is still one integer add) and the row's bound is rounded UP to a whole number K of
+// ln2/E steps (c_i grows by < ln2/E: 0.06 bit of P at E = 16), so that
+//     tn = z rk16 + (MAGIC_N - K)          low mantissa word: n = rint(z rk16 - K) + E (8 SP - 1), exactly as before
+//     f  = z rk16 - (tn - (MAGIC_N - K))   = (z rk16 - K) - rint(z rk16 - K), |f| <= 1/2, in units of ln2/E
+// and e^(f ln2/E) - 1 is a polynomial in f with the powers of ln2/E folded into its coefficients: 9 FP64 instructions per
+// logit instead of 10 (E = 16, quartic), 8 with the 64-entry table and the cubic (|f ln2/64| <= 0.0054: 3.6e-11 relative, the
+// same fifth of the last probability bit; the larger table costs shared-memory wavefronts, the pipe the epilogue has to spare).
+template <int SP, int E>
+DEVINL void ai_exp_fixed_z(double z, double rk16, double CA, uint32_t tbl_s32, uint32_t& lo) {
+    static_assert(SP <= 4 && (E == 16 || E == 64), "32-bit probabilities only");
+    constexpr int EL = E == 64 ? 6 : 4;
+    constexpr double L = 0.6931471805599453 / E;
+    const double MAGIC = 6755399441055744.0;
+    const double tn = fma(z, rk16, CA);
+    const int n = __double2loint(tn);
+    const double nd = tn - CA;                               // rint(z rk16 - K) + K: exact (integers below 2^53)
+    const double f = fma(z, rk16, -nd);
+    double q = E == 64 ? L * L * L / 6.0 : fma(f, L * L * L * L / 24.0, L * L * L / 6.0);
+    q = fma(q, f, L * L / 2.0);
+    q = fma(q, f, L);
+    const double pl = q * f;                                 // e^(f L) - 1
+    double t;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(tbl_s32 | (((uint32_t)n << 3) & (uint32_t)(8 * E - 8))));
+    const double y = fma(t, pl, t);
+    const int m = max(n >> EL, -9);
+    const double ys = __hiloint2double(__double2hiint(y) + (m << 20), __double2loint(y));
+    lo = (uint32_t)__double2loint(ys + MAGIC);
+}
+
 struct AttnI8Params {
     AttnI8Side q[2];             // digit planes of the QUERY side of grid side s
     AttnI8Side kv[2];            // digit planes of its SOURCE side
@@ -451,8 +482,12 @@ struct AttnI8Params {
 // MODE: AI_MODE_FULL (pass 1 + pass 2), AI_MODE_LOGITS (the scaled logits are stored, nothing else), AI_MODE_TOPK (no pass 1:
 // the exact row maximum and the top-k threshold come from topk_threshold_kernel; probabilities outside the kept set are 0,
 // which turns dynamic_attention() of mdgat.py:196-210 into the same tensor-core P V as the full layers).
-template <int S, int SP, int MODE, int CW, int CVT>
+template <int S, int SP, int MODE, int CW, int CVTX>
 __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid_constant__ AttnI8Params p) {
+    // CVTX 0..4: recombination variant with ai_exp_fixed(); 5 / 6: variant 4 with ai_exp_fixed_z() on 16 / 64 table entries
+    constexpr int CVT = CVTX >= 5 ? 4 : CVTX;
+    constexpr int XE = (CVTX >= 5 && SP <= 4 && MODE == AI_MODE_FULL) ? (CVTX == 6 ? 64 : 16) : 0;     // 0: ai_exp_fixed()
+    constexpr int ETAB = SP > 4 ? 256 : (XE == 64 ? 64 : 16);
     constexpr bool LOGITS = MODE == AI_MODE_LOGITS, TOPK = MODE == AI_MODE_TOPK, PASS1 = MODE == AI_MODE_FULL;
     constexpr int AI_EPI_THREADS = ai_epi_threads(CW), EPI_WARPS = AI_EPI_THREADS / 32, NCG = 32 / CW;
     constexpr int NSBUF = (3 * S * AI_BN <= 512) ? 2 : 1;
@@ -510,7 +545,7 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
         mbar_init(&o_full, 1);
         mbar_fence_init();
     }
-    for (int i = tid; i < (SP > 4 ? 256 : 16); i += ai_threads(CW)) etab[i] = g_exp2_table256[SP > 4 ? i : 16 * i];
+    for (int i = tid; i < ETAB; i += ai_threads(CW)) etab[i] = g_exp2_table256[(256 / ETAB) * i];
     if (warp == EPI_WARPS) {
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_s);
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(dst));
@@ -636,7 +671,9 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
         const double r_i = Qd.qscale[(size_t)bh * Npad + row];     // 2^(e_i - 12) / sqrt(32); 0 for padded rows
         // row factor of the recombined integer: even S: ai_recombine() returns 256 x the sum; CVT 4: 2^(16 (S-1)/2) x
         const double r_z = ((S & 1) ? r_i : r_i * 0.00390625) * ai_recombine_scale<S, CVT>();
-        const int r_zh = __double2hiint(r_z), r_zl = __double2loint(r_z);
+        // XE: the row factor carries E / ln2 (ai_exp_fixed_z)
+        const double r_zx = XE ? r_z * ((double)(XE ? XE : 1) * 1.4426950408889634) : r_z;
+        const int r_zh = __double2hiint(r_zx), r_zl = __double2loint(r_zx);
         double c_i = 0.0, t_i = 0.0;
         int jl_i = 0;
         if (TOPK) {
@@ -695,6 +732,12 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
             c_i = c;
 #pragma unroll
             for (int g = 0; g < NCG; ++g) c_i = fmax(c_i, s_xd[g * 128 + rloc]);
+        }
+        double CA = 0.0;
+        if (XE) {
+            // K = the bound in whole ln2 / E steps, rounded up (the 1e-6 covers the rounding of r_zx); MAGIC_N - K is exact
+            const double K = ceil(fma(c_i, (double)(XE ? XE : 1) * 1.4426950408889634, 1e-6));
+            CA = (6755399441055744.0 + (double)((XE ? XE : 1) * (8 * SP - 1))) - ((K > -1e12 && K < 1e12) ? K : 0.0);
         }
         uint32_t bsum[SP];                                         // byte sums of this thread's p^ per plane (DP4A), exact
 #pragma unroll
@@ -770,6 +813,9 @@ __global__ void __launch_bounds__(ai_threads(CW), 1) attn_i8_kernel(const __grid
                     const bool keep = zz > t_i || (zz == t_i && jbase + j <= jl_i);
                     ai_exp_fixed<SP>(zz - c_i, etab_s32, lo[j], h32);
                     if (!keep) { lo[j] = 0u; h32 = 0u; }
+                } else if constexpr (XE != 0) {
+                    ai_exp_fixed_z<SP <= 4 ? SP : 4, XE ? XE : 16>(z[j], rk[j], CA, etab_s32, lo[j]);
+                    h32 = 0u;
                 } else {
                     ai_exp_fixed<SP>(fma(z[j], rk[j], -c_i), etab_s32, lo[j], h32);    // p^ = rint(exp(z - c_i) 2^(8 SP - 1)), p <= 1
                 }
@@ -1004,7 +1050,7 @@ cudaError_t launch_attn_i8(const AttnI8Side* q, const AttnI8Side* kv, double* co
     static const int cw = [] { const char* v = getenv("MDGAT_ATTN_CW"); return v && v[0] == '1' ? 16 : 8; }();
     // MDGAT_ATTN_CVT=0|1|2 (read once): int32 -> float64 conversion of the epilogue, see int_to_f64(); the sweep setting
     // (5, 4) is built in all three variants, the others with the default
-    static const int cvt = [] { const char* v = getenv("MDGAT_ATTN_CVT"); return v && v[0] >= '0' && v[0] <= '4' ? v[0] - '0' : AI_CVT_DEFAULT; }();
+    static const int cvt = [] { const char* v = getenv("MDGAT_ATTN_CVT"); return v && v[0] >= '0' && v[0] <= '6' ? v[0] - '0' : AI_CVT_DEFAULT; }();
     cudaError_t e;
     switch (S * 10 + SP) {
         case 43: e = attn_i8_go<4, 3, AI_CVT_DEFAULT>(p, grid, smem, mode, cw, st); break;
@@ -1013,6 +1059,8 @@ cudaError_t launch_attn_i8(const AttnI8Side* q, const AttnI8Side* kv, double* co
                    : cvt == 1 ? attn_i8_go<5, 4, 1>(p, grid, smem, mode, cw, st)
                    : cvt == 2 ? attn_i8_go<5, 4, 2>(p, grid, smem, mode, cw, st)
                    : cvt == 3 ? attn_i8_go<5, 4, 3>(p, grid, smem, mode, cw, st)
+                   : cvt == 5 ? attn_i8_go<5, 4, 5>(p, grid, smem, mode, cw, st)
+                   : cvt == 6 ? attn_i8_go<5, 4, 6>(p, grid, smem, mode, cw, st)
                               : attn_i8_go<5, 4, 4>(p, grid, smem, mode, cw, st); break;
         case 65: e = attn_i8_go<6, 5, AI_CVT_DEFAULT>(p, grid, smem, mode, cw, st); break;
         case 76: e = attn_i8_go<7, 6, AI_CVT_DEFAULT>(p, grid, smem, mode, cw, st); break;

@@ -233,6 +233,26 @@ def test_sinkhorn_float32_kernel_matrix_vs_oracle(dev, N, M, iters):
     assert np.array_equal(got[:, :, M - 1], got[:, :, 0])
 
 
+def test_sinkhorn_float32_kernel_matrix_stops_at_tolerance(dev):
+    """The float32-kernel-matrix Sinkhorn stops once no column scaling moved by more than 2^-35 relative in an iteration:
+    never later than the float64 kernel's bit-for-bit rule, the potentials still those of the reference's full loop (the skipped
+    iterations move a log-potential by at most (T - t) 2^-35), and a loop that has not converged runs every iteration."""
+    from mdgat_matcher_b200 import ops
+    from oracle import mdgat_oracle as O
+    rng = np.random.default_rng(4)
+    scores = rng.normal(size=(2, 100, 90)) * 2
+    T = 400
+    want = O.log_optimal_transport(scores, 1.5, T)
+    C, u, v, st32 = ops.sinkhorn(_t(scores, dev), 1.5, T, k32=True, return_status=True)
+    _, _, _, st64 = ops.sinkhorn(_t(scores, dev), 1.5, T, return_status=True)
+    assert st32['fallback'] == [0, 0]
+    assert all(1 <= a <= b < T for a, b in zip(st32['iterations'], st64['iterations'])), (st32, st64)
+    got = (C + u[:, :, None] + v[:, None, :] + np.log(190)).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-6
+    _, _, _, st3 = ops.sinkhorn(_t(scores, dev), 1.5, 3, k32=True, return_status=True)
+    assert st3['iterations'] == [3, 3]
+
+
 def test_sinkhorn_float32_kernel_matrix_wide_range_falls_back(dev):
     """Row range >= 80: exp(C - rowmax) would leave the normal float32 range, the pair is redone in the log domain."""
     from mdgat_matcher_b200 import ops
@@ -540,6 +560,27 @@ def test_forward_matches_reference_golden(dev, name, gemm, attention, precision)
     # the reference rewrites gt_matches in place (mdgat.py:519-520)
     if case.get('loss_method', 'triplet_loss') != 'superglue':
         assert int((data['gt_matches0'] == -1).sum()) == 0
+
+
+def test_module_reports_sinkhorn_iterations(dev):
+    """MDGAT.sinkhorn_status() (mdgat_forward_sinkhorn_status): iterations the Sinkhorn stage of the last forward ran per pair.
+    The network's scores converge long before T = 100 under the default precision; 'exact' stops only at the bit-for-bit
+    fixed point, so it can never stop earlier than the default."""
+    rec = load_golden('ckpt_L9_n512_b8')
+    case = rec['case']
+    its = {}
+    for precision in ('sweep', 'exact'):
+        net = _build_module(case, dev, extra={'precision': precision})
+        with pytest.raises(RuntimeError):
+            net.sinkhorn_status()
+        out = net({k: _t(v, dev) for k, v in golden_inputs(rec).items()})
+        st = net.sinkhorn_status()
+        assert np.array_equal(out['matches0'].cpu().numpy(), rec['matches0'])
+        assert len(st['iterations']) == 8 and st['fallback'] == [0] * 8
+        assert all(1 <= i <= 100 for i in st['iterations'])
+        its[precision] = st['iterations']
+    assert max(its['sweep']) < 100
+    assert all(a <= b for a, b in zip(its['sweep'], its['exact'])), its
 
 
 NAN_CASES = ['seeded_L2_nan_triplet', 'seeded_L2_nan_gap_ragged', 'seeded_L2_nan_sg_mutual', 'seeded_L2_nan_sg']

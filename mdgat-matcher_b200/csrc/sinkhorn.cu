@@ -595,9 +595,10 @@ size_t sinkhorn_scratch_doubles(int B, int N, int M) {
 // float32 kernel matrix: same scratch (the float rows use half of the K area), same flags / iteration counts behind it.
 // Launch shape: one CTA per SM with as many K rows in shared memory as fit (all 64 real rows at N = M = 512). The iteration is
 // bound by its chain of dependent phases (row sums -> CTA barrier -> column partials -> cluster barrier -> exchange -> CTA
-// barrier -> cluster barrier): about 14 600 cycles per iteration (0.42 ms / 2 waves / ~28 iterations of the slowest pair of a
-// wave) against ~4 300 shared-memory wavefronts and ~4 500 issue cycles per scheduler; stall samples of an iteration: 23 % row
-// sweep, 27 % column sweep, 45 % barriers and the exchange. At cfg2 the 32 clusters of 8 need two waves (16 clusters fit the
+// barrier -> cluster barrier): about 12 500 cycles per iteration (ncu capture of the final kernel: 413 us, two waves, ~28
+// iterations of the slowest pair of a wave, 11 % of the samples in the setup) against 4 460 shared-memory wavefronts and ~970
+// warp instructions per warp; stall samples of an iteration: row sweep 23 %, column sweep up to the cluster barrier 40 %,
+// exchange 16 %, second cluster barrier 8 %. At cfg2 the 32 clusters of 8 need two waves (16 clusters fit the
 // GPCs of 148 SMs). Measured and rejected: MDGAT_SK_CTAS=2, two CTAs per SM (64 registers, 49 of the rows in shared memory,
 // the others read from the L2-resident scratch), all 32 clusters in one wave -- 1.16 ms against 0.74 ms before the tolerance
 // exit; MDGAT_SK_THREADS=1024, 32 warps per CTA (two rows per warp round, two threads per column, 16 partial vectors in the

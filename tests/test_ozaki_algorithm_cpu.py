@@ -52,3 +52,54 @@ def test_zero_rows_and_exact_powers_of_two():
     w = np.eye(128)[:8] * 3.0
     got = _ozaki_matmul(x, w, 7)
     assert np.array_equal(got, x @ w.T)
+
+
+# ----------------------------------------------------------------------------- one-FMA digit cutter (cut_digits16, csrc/ozaki_gemm.cu)
+
+def _cut_digits_onefma(x, e, S):
+    """Bit-level model of cut_digits16(): ONE rounded product per value, I = rint(x 2^(6-e) 128^(S-1)), read out of the low
+    mantissa bits of x * c + (1.5 * 2^52 + B), B = 64 * sum_k 128^k; plane s = ((I + B) >> 7 (S-1-s)) & 127 (the leading plane keeps
+    all eight bits), minus 64 -- done on four bytes of a word at once with a carry-free add of 0xC0. Returns int8 digits [S][n]."""
+    B = 64 * (((1 << (7 * S)) - 1) // 127)
+    magic = 6755399441055744.0 + float(B)
+    assert magic == 6755399441055744 + B                                   # the constant is exact
+    v = np.ldexp(x, 6 - e + 7 * (S - 1)) + magic                           # the power-of-two scaling is exact: one rounding, like the FMA
+    bits = v.view(np.uint64)
+    lo, hi = (bits & np.uint64(0xFFFFFFFF)).astype(np.uint64), (bits >> np.uint64(32)).astype(np.uint64)
+    out = []
+    for s in range(S):
+        sh = 7 * (S - 1 - s)
+        if sh == 0:
+            a = lo
+        elif sh + 8 <= 32:
+            a = lo >> np.uint64(sh)
+        elif sh < 32:
+            a = (((hi << np.uint64(32)) | lo) >> np.uint64(sh)) & np.uint64(0xFFFFFFFF)      # funnel shift
+        else:
+            a = hi >> np.uint64(sh - 32)
+        u = a & np.uint64(0xFF)                                            # PRMT picks byte 0 of each value
+        t = (u & np.uint64(0x7F)) + np.uint64(0x40)                        # per byte: no carry into the neighbour (<= 0xBF)
+        b = (t ^ ((~u) & np.uint64(0x80))) if s == 0 else (t ^ np.uint64(0x80))
+        out.append((b & np.uint64(0xFF)).astype(np.uint8).view(np.int8))
+    return np.stack(out)
+
+
+def test_onefma_digits_represent_the_same_integer_as_the_telescoped_ones():
+    rng = np.random.default_rng(3)
+    for S in (4, 5, 6, 7):
+        x = rng.normal(size=(64, 128)) * np.exp(rng.normal(size=(64, 1)) * 3)
+        x[:, ::5] *= 1e-7
+        x[0, :] = 0.0
+        mx = np.abs(x).max(axis=1, keepdims=True)
+        _, e = np.frexp(mx)
+        e = np.where(mx > 0, e, 0)
+        x[1, 0] = np.ldexp(1.0, int(e[1, 0])) * (1 - 2.0 ** -53)           # |x| -> 2^e from below: the leading digit reaches +-64
+        x[2, 0] = -np.ldexp(1.0, int(e[2, 0])) * (1 - 2.0 ** -53)
+        tele, _ = _slice(x, S)
+        one = np.stack([_cut_digits_onefma(x[r], int(e[r, 0]), S) for r in range(x.shape[0])], axis=1).astype(np.int64)
+        assert np.abs(one).max() <= 64
+        w = 128 ** np.arange(S - 1, -1, -1, dtype=np.int64)
+        val_one = np.tensordot(w, one, axes=1)
+        val_tele = np.tensordot(w, tele, axes=1)
+        assert np.array_equal(val_one, val_tele)                           # both digit sets are the integer rint(x 2^(6-e) 128^(S-1))
+        assert np.array_equal(val_one, np.rint(np.ldexp(x, 6 - e + 7 * (S - 1))).astype(np.int64))

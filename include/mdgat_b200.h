@@ -97,7 +97,10 @@ typedef struct {
     int attn_p_slices;        /* byte planes of the softmax probabilities: (attn_slices, attn_p_slices) must be one of
                                  (4,3) (4,4) (5,4) (6,5) (7,6); 0 = attn_slices - 1 */
     int sinkhorn_k32;         /* 1: the Sinkhorn kernel matrix exp(C_ij - max_j C_ij) is STORED in float32 (every sum,
-                                 division and potential stays float64; potentials move by O(1e-7)); 0: float64 storage */
+                                 division and potential stays float64; potentials move by O(1e-7)) and the loop stops once
+                                 no column scaling moved by more than 2^-35 relative in an iteration (skipped iterations
+                                 bounded by (sinkhorn_iters - t) 2^-35 in the log-potentials; mdgat_forward_sinkhorn_status
+                                 reports t per pair); 0: float64 storage, stop only when the iterate repeats bit for bit */
     int late_from;            /* > 0: GNN layers late_from .. 2L-1 use the late_* digit-plane counts (never more planes than
                                  the first setting). Experimental and off by default: 4/4/4 from layer 7 on keeps the match
                                  indices on the 131 k-row sweep but its worst score error is 6.9e-4. 0: one
